@@ -1,0 +1,159 @@
+/* koopfit.h — C ABI of libkoopfit.so: the B200-native Ksysid EDMD fit.
+ *
+ * The reference (roahmlab/koopman-realizations) is pure MATLAB and has NO FFI
+ * for this path; the seam is created at Ksysid.get_Koopman.  Each entry point
+ * below names the reference code it replaces (file:line into the reference
+ * tree).  The MATLAB-side binding (a thin mexFunction) is shown in
+ * INTEGRATION.md; in this repository the same ABI is driven through ctypes by
+ * koopman-realizations_b200/ksysid.py.
+ *
+ * Conventions
+ *   - all matrices are double, COLUMN-MAJOR (MATLAB layout); snapshot matrices
+ *     alpha/beta (M x nzeta) and u (M x m) have leading dimension M, i.e. each
+ *     variable is one contiguous column (coalesced on the device as-is).
+ *   - caller owns every host buffer; the library owns device memory and streams
+ *     inside kf_ctx.  No library-allocated pointer crosses the ABI except the
+ *     device accumulator exposed by kf_accum_buffer (for the NCCL all-reduce).
+ *   - every call returns 0 on success or a KF_E* code; kf_last_error gives text.
+ *   - there is no CPU fallback: without a CUDA device kf_create fails.
+ */
+#ifndef KOOPFIT_H
+#define KOOPFIT_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KF_VERSION 100
+
+typedef struct kf_ctx kf_ctx;
+
+enum { KF_OK = 0, KF_EINVAL = 1, KF_ECUDA = 2, KF_ENOMEM = 3, KF_ENUMERIC = 4, KF_EUNSUPPORTED = 5 };
+
+/* obj.model_type (Ksysid.m:96-104) */
+enum { KF_LINEAR = 0, KF_BILINEAR = 1, KF_NONLINEAR = 2 };
+
+/* obj.obs_type entries (Ksysid.m:486-501) */
+enum { KF_POLY = 0, KF_FOURIER = 1, KF_FOURIER_SPARSER = 2, KF_GAUSSIAN = 3, KF_HERMITE = 4 };
+
+/* one (obs_type{i}, obs_degree(i)) pair */
+typedef struct {
+    int type;               /* KF_POLY ... */
+    int degree;             /* obs_degree(i) */
+    const double* centres;  /* KF_GAUSSIAN: zeta0 (nv x degree, column-major; Ksysid.m:803); else NULL */
+} kf_block;
+
+/* the dictionary psi = [v; block_1; ...; 1] over v (Ksysid.m:484-505) */
+typedef struct {
+    int nv;                 /* length of v: nzeta (linear, bilinear) or nzeta+m (nonlinear; Ksysid.m:475-477) */
+    int nblocks;
+    const kf_block* blocks;
+    const double* pcs;      /* dim_red: basis.pcs (N_full x n_pcs column-major, Ksysid.m:1507-1510) or NULL */
+    int n_pcs;
+} kf_basis;
+
+/* snapshotPairs (Ksysid.m:1005) */
+typedef struct {
+    long long M;            /* number of snapshot pairs (rows) */
+    int nzeta;              /* columns of alpha/beta */
+    int m;                  /* columns of u */
+    int model;              /* KF_LINEAR | KF_BILINEAR | KF_NONLINEAR */
+    const double* alpha;    /* M x nzeta */
+    const double* beta;     /* M x nzeta */
+    const double* u;        /* M x m */
+} kf_problem;
+
+/* how to solve (Ksysid.m:1068-1080) */
+enum { KF_LS_AUTO = 0, KF_LS_GRAM = 1, KF_LS_QR = 2 };
+enum { KF_PSD_AS_REFERENCE = 0, KF_PSD_NEVER = 1, KF_PSD_ALWAYS = 2 };
+typedef struct {
+    int least_squares;      /* 1: K = Px \ Py (obj.lasso >= 1e6 branch, Ksysid.m:1068-1069) */
+    int ls_method;          /* KF_LS_AUTO | KF_LS_GRAM (pivoted Cholesky of G) | KF_LS_QR (Householder QRCP of Px) */
+    double pivot_tol;       /* KF_LS_GRAM relative pivot tolerance on |R_jj|/|R_11|; <=0 -> default 1e-7 */
+    int nt;                 /* QP branch: number of L1 budgets */
+    const double* t;        /* QP branch: t_i = lasso_i * N (Ksysid.m:996,1135) */
+    int psd_shift;          /* KF_PSD_*: the `any(eig(G)<0)` +1e-6 I branch (Ksysid.m:1117-1120) */
+    int delay_constraint;   /* 1: pin the delay columns (linear, nd>=1; Ksysid.m:1139-1164) */
+    int n;                  /* params.n  (needed by the delay constraint) */
+    int nd;                 /* params.nd */
+    int qp_max_iter;        /* <=0 -> default */
+    double qp_tol;          /* relative objective/iterate tolerance; <=0 -> default 1e-10 */
+} kf_solve;
+
+typedef struct {
+    int rank;               /* numerical rank found by the LS solve */
+    int ls_method_used;     /* KF_LS_GRAM or KF_LS_QR */
+    int passes;             /* data passes (lift + contraction) */
+    int psd_shift_applied;  /* QP: 1 if 1e-6 I was added */
+    double min_pivot;       /* smallest accepted |R_jj| */
+    double max_pivot;       /* |R_11| */
+    double t_lift_gram_ms;  /* device time of lift + Gram */
+    double t_solve_ms;      /* device time of the solve */
+    double t_total_ms;      /* wall time of the call */
+} kf_info;
+
+/* caller-allocated outputs; NULL members are skipped */
+typedef struct {
+    double* K;              /* P x P x max(1,nt): koopData.K (Ksysid.m:1084) */
+    double* G;              /* P x P : Px'Px (Ksysid.m:1114) */
+    double* C;              /* P x P : Px'Py (Ksysid.m:1125) */
+    double* Px;             /* M x P : regressor (Ksysid.m:1019-1065); koopData.Px = Px(:,1:N) */
+    double* Py;             /* M x P */
+    int* perm;              /* P: pivot order (0-based), first `rank` entries = basic set */
+    double* objective;      /* nt: 0.5 tr(K'GK) - tr(C'K) per budget */
+    double* l1norm;         /* nt: ||vec K||_1 */
+    int* qp_iters;          /* nt */
+    kf_info info;
+} kf_result;
+
+/* ---- context ---------------------------------------------------------- */
+int  kf_create(kf_ctx** ctx, int device);            /* one context per GPU / per process rank */
+void kf_destroy(kf_ctx* ctx);
+const char* kf_last_error(const kf_ctx* ctx);        /* ctx may be NULL for create-time errors */
+int  kf_version(void);
+
+/* ---- dictionary -------------------------------------------------------
+ * Replaces def_observables / def_*Lift + matlabFunction (Ksysid.m:455-536, 629-863):
+ * dimensions of the dictionary, N = params.N (Ksysid.m:534 / 1511-1517) and the
+ * regressor width P (Ksysid.m:1019-1028). */
+int kf_basis_dims(const kf_basis* basis, int model, int m, int* n_full, int* N, int* P);
+
+/* exponent / multiplier table of one block in the reference's `partitions` order
+ * (partitions.m:206-219; Ksysid.m:645-648, 747-751, 848-851).  rows*cols ints, row-major.
+ * Call with table=NULL to query rows/cols. */
+int kf_block_table(int type, int degree, int nv, int* rows, int* cols, int* table);
+
+/* lift.econ_full evaluated on `rows` points (Ksysid.m:1443-1491, 1614-1618):
+ * V (rows x nv) -> Psi (rows x N), both column-major HOST buffers; runs on the GPU. */
+int kf_lift(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V, double* Psi);
+
+/* ---- the fit ----------------------------------------------------------
+ * Replaces Ksysid.get_Koopman (Ksysid.m:987-1092) + solve_KoopmanQP (1095-1176) and the
+ * lasso loop of train_models (1370-1387): lifts once, accumulates G, C once, solves
+ * LS or all nt budgets.  HOST pointers in `prob`; copies are inside the call. */
+int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out);
+
+/* ---- staged, device-resident API (one rank of a snapshot-sharded fit) ---
+ * kf_accumulate_dev: lift + Gram of this rank's shard; DEVICE pointers in `prob`;
+ *   reset!=0 zeroes the accumulator first.  Asynchronous on the context stream.
+ * kf_accum_buffer: the packed partial-Gram accumulator [G-tiles | C-tiles] to be
+ *   summed across ranks (ncclAllReduce(sum, double) by the caller, e.g. torch.distributed).
+ * kf_solve_dev: solve from the (reduced) accumulator; outputs to HOST pointers in `out`. */
+int kf_accumulate_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, int reset);
+int kf_accum_buffer(kf_ctx* ctx, double** dev_ptr, size_t* count);
+int kf_solve_dev(kf_ctx* ctx, const kf_solve* solve, kf_result* out);
+int kf_sync(kf_ctx* ctx);                            /* cudaStreamSynchronize(context stream) */
+void* kf_stream(kf_ctx* ctx);                        /* the context's cudaStream_t */
+
+/* ---- instrumentation for bench.py / tests ----------------------------- */
+/* flops issued to the FP64 tensor pipe and kernel launches since the last reset */
+int kf_counters(kf_ctx* ctx, double* dmma_flops, long long* launches, int reset);
+/* device time (ms, CUDA events on the context stream) of the last lift+Gram phase and solve phase */
+int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, double* solve_ms);
+/* tuning knobs: "chunk" (snapshots per L2-resident panel), "splitk", ... ; returns KF_EINVAL if unknown */
+int kf_set_option(kf_ctx* ctx, const char* name, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOOPFIT_H */

@@ -1,0 +1,48 @@
+// Feature program: the observable dictionary psi = [v; blocks...; 1] compiled to a flat
+// list of ops that a device thread evaluates in index order (one snapshot per thread).
+//
+// Semantics follow the reference's dictionary definitions (Ksysid.m:455-536, 629-863) and
+// the `partitions` row order (partitions.m:206-219).  Floating-point association:
+//   feature(row) = feature(row with its LAST non-zero entry zeroed) * primitive(LAST entry)
+// and v_i^k = v_i^(k-1) * v_i, mirroring get_monomial's left-to-right product
+// (Ksysid.m:687-690).  Products are plain IEEE multiplies (never fused).
+#pragma once
+#include <string>
+#include <vector>
+#include "../../include/koopfit.h"
+
+enum : int { KF_OP_VAR = 0, KF_OP_CONST = 1, KF_OP_MUL = 2, KF_OP_COS = 3, KF_OP_SIN = 4, KF_OP_HERM = 5, KF_OP_GAUSS = 6 };
+
+struct KfOp {
+    int kind;   // KF_OP_*
+    int a;      // VAR/COS/SIN/HERM: variable index; MUL: first factor; GAUSS: centre column
+    int b;      // MUL: second factor; HERM: order
+    int pad;
+    double c;   // COS/SIN: angular multiplier 2*pi*j; CONST: value
+};
+
+struct KfProgram {
+    int nv = 0;
+    std::vector<KfOp> ops;          // n_full entries
+    std::vector<double> centres;    // nv x ngauss, column-major (all gaussian blocks concatenated)
+    int ngauss = 0;
+    std::vector<double> pcs;        // n_full x n_pcs column-major (dim_red) or empty
+    int n_pcs = 0;
+    int n_full() const { return (int)ops.size(); }
+    // lifted dimension seen by the fit: Ksysid.m:534, or nv + n_pcs + 1 after dim_red (1511-1517)
+    int N() const { return n_pcs ? nv + n_pcs + 1 : n_full(); }
+};
+
+// rows of partitions(total, ones(1,nvars)) in the reference's order, appended to `out` (row-major)
+void kf_partitions_ones(int total, int nvars, std::vector<int>& out);
+
+// table of one block (rows x cols, row-major) as the reference enumerates it
+int kf_block_rows(int type, int degree, int nv, int* rows, int* cols, std::vector<int>* table, std::string& err);
+
+// compile a kf_basis; returns KF_OK or KF_EINVAL with `err` set
+int kf_build_program(const kf_basis* basis, KfProgram& prog, std::string& err);
+
+// regressor width (Ksysid.m:1019-1028)
+inline int kf_regressor_width(int model, int N, int m) {
+    return model == KF_LINEAR ? N + m : (model == KF_BILINEAR ? N * (m + 1) : N);
+}
