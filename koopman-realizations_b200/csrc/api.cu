@@ -1,0 +1,564 @@
+// C-ABI entry points of libkoopfit.so (see include/koopfit.h for the contract and the
+// reference lines each call replaces).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "kf_internal.h"
+
+namespace {
+
+thread_local std::string g_create_err;
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int pair_index(int a, int b, int m) { return a * (m + 1) - a * (a - 1) / 2 + (b - a); }
+
+// compile + upload the dictionary
+int prepare_program(kf_ctx* ctx, const kf_basis* basis) {
+    std::string err;
+    int rc = kf_build_program(basis, ctx->prog, err);
+    if (rc) {
+        ctx->err = err;
+        return rc;
+    }
+    const KfProgram& p = ctx->prog;
+    KF_CUDA(ctx, ctx->d_ops.ensure(sizeof(KfOp) * p.ops.size()));
+    KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ops.p, p.ops.data(), sizeof(KfOp) * p.ops.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!p.centres.empty()) {
+        KF_CUDA(ctx, ctx->d_centres.ensure(sizeof(double) * p.centres.size()));
+        KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_centres.p, p.centres.data(), sizeof(double) * p.centres.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!p.pcs.empty()) {
+        KF_CUDA(ctx, ctx->d_pcs.ensure(sizeof(double) * p.pcs.size()));
+        KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_pcs.p, p.pcs.data(), sizeof(double) * p.pcs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors may be rebuilt by the next call
+    return KF_OK;
+}
+
+int check_problem(kf_ctx* ctx, const kf_problem* pr) {
+    if (!pr || pr->M <= 0 || pr->nzeta <= 0 || pr->m < 0 || !pr->alpha || !pr->beta || (pr->m > 0 && !pr->u)) {
+        ctx->err = "kf_problem: M, nzeta must be > 0 and alpha/beta/u non-NULL";
+        return KF_EINVAL;
+    }
+    if (pr->model != KF_LINEAR && pr->model != KF_BILINEAR && pr->model != KF_NONLINEAR) {
+        ctx->err = "Invalid model_type chosen. Must be linear, bilinear, or nonlinear.";   // Ksysid.m:103
+        return KF_EINVAL;
+    }
+    const int nv = pr->nzeta + (pr->model == KF_NONLINEAR ? pr->m : 0);
+    if (ctx->prog.nv != nv) {
+        ctx->err = "kf_basis.nv must equal nzeta (linear, bilinear) or nzeta+m (nonlinear)";
+        return KF_EINVAL;
+    }
+    return KF_OK;
+}
+
+// layout of the panel, the tile list and the accumulator for (program, model, m, M)
+int make_layout(kf_ctx* ctx, const kf_problem* pr) {
+    KfLayout L;
+    const KfProgram& p = ctx->prog;
+    L.model = pr->model;
+    L.m = pr->m;
+    L.nzeta = pr->nzeta;
+    L.nv = p.nv;
+    L.n_full = p.n_full();
+    L.N = p.N();
+    L.P = kf_regressor_width(L.model, L.N, L.m);
+    L.Rx = L.N + (L.model == KF_LINEAR ? L.m : 0);
+    L.Rxp = (int)kf_roundup(L.Rx, KF_BM);
+    L.Ny = L.N;
+    L.Nyp = (int)kf_roundup(L.N, KF_BN);
+    L.nW = (L.model == KF_BILINEAR) ? (L.m + 1) * (L.m + 2) / 2 : 0;
+    L.x_off = 0;
+    L.y_off = L.Rxp;
+    L.w_off = L.Rxp + L.Nyp;
+    L.rows = L.w_off + (int)kf_roundup(L.nW, 8);
+    L.Pp = (int)kf_roundup(L.P, KF_BM);
+
+    // chunk: one panel should stay L2-resident
+    long long Mc = ctx->opt_chunk > 0 ? ctx->opt_chunk
+                                      : (long long)(ctx->opt_panel_mb * 1048576.0 / (8.0 * L.rows));
+    Mc = std::max<long long>(256, std::min<long long>(Mc, 32768));
+    Mc = std::min<long long>(Mc, kf_roundup(pr->M, 256));
+    Mc = kf_roundup(Mc, 256);
+    L.Mc = (int)Mc;
+
+    const int tmx = L.Rxp / KF_BM, tny = L.Nyp / KF_BN;
+    const int npairs = (L.model == KF_BILINEAR) ? L.nW : 1;
+    for (int a = 0; a <= (L.model == KF_BILINEAR ? L.m : 0); ++a)
+        for (int b = a; b <= (L.model == KF_BILINEAR ? L.m : 0); ++b) {
+            const int q = (L.model == KF_BILINEAR) ? pair_index(a, b, L.m) : 0;
+            for (int tm = 0; tm < tmx; ++tm)
+                for (int tn = 0; tn <= tm; ++tn) L.tiles.push_back(KfTile{0, q, a, b, tm, tn});
+            for (int tm = 0; tm < tmx; ++tm)
+                for (int tn = 0; tn < tny; ++tn) L.tiles.push_back(KfTile{1, q, a, b, tm, tn});
+        }
+    (void)npairs;
+    const int T = (int)L.tiles.size();
+    const int ksteps = L.Mc / KF_BK;
+    int nsplit = ctx->opt_splitk > 0 ? ctx->opt_splitk : (2 * ctx->sm_count + T - 1) / T;
+    nsplit = std::max(1, std::min(nsplit, std::max(1, ksteps / 4)));
+    L.nsplit = nsplit;
+    L.valid = true;
+
+    // buffers
+    const size_t panel_bytes = (size_t)L.rows * L.Mc * sizeof(double);
+    for (int b = 0; b < 2; ++b) {
+        KF_CUDA(ctx, ctx->d_panel[b].ensure(panel_bytes));
+        KF_CUDA(ctx, cudaMemsetAsync(ctx->d_panel[b].p, 0, panel_bytes, ctx->stream));   // pad rows must be finite
+    }
+    if (p.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * L.n_full * L.Mc * sizeof(double)));
+    KF_CUDA(ctx, ctx->d_accum.ensure((size_t)nsplit * T * KF_TILE_ELEMS * sizeof(double)));
+    KF_CUDA(ctx, ctx->d_tilemeta.ensure(sizeof(KfTile) * T));
+    KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tilemeta.p, L.tiles.data(), sizeof(KfTile) * T, cudaMemcpyHostToDevice, ctx->stream));
+
+    // task lists, one per panel buffer
+    const int per = (ksteps + nsplit - 1) / nsplit;
+    std::vector<KfGemmTask> tasks;
+    for (int b = 0; b < 2; ++b) {
+        tasks.clear();
+        double* panel = ctx->d_panel[b].as<double>();
+        for (int s = 0; s < nsplit; ++s) {
+            const int k0 = std::min(s * per, ksteps) * KF_BK, k1 = std::min((s + 1) * per, ksteps) * KF_BK;
+            if (k1 <= k0) continue;
+            for (int t = 0; t < T; ++t) {
+                const KfTile& tl = L.tiles[t];
+                KfGemmTask g{};
+                g.A = panel + (long long)(L.x_off + tl.tm * KF_BM) * L.Mc;
+                g.B = panel + (long long)((tl.kind == 0 ? L.x_off : L.y_off) + tl.tn * KF_BN) * L.Mc;
+                g.W = tl.q > 0 ? panel + (long long)(L.w_off + tl.q) * L.Mc : nullptr;
+                g.out = ctx->d_accum.as<double>() + ((long long)s * T + t) * KF_TILE_ELEMS;
+                g.lda = g.ldb = L.Mc;
+                g.ldm = KF_BN;
+                g.ldn = 1;
+                g.k0 = k0;
+                g.k1 = k1;
+                g.a_rows = KF_BM;
+                g.b_rows = KF_BN;
+                g.alpha = 1.0;
+                g.accumulate = 1;
+                tasks.push_back(g);
+            }
+        }
+        KF_CUDA(ctx, ctx->d_tasks[b].ensure(sizeof(KfGemmTask) * tasks.size()));
+        KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tasks[b].p, tasks.data(), sizeof(KfGemmTask) * tasks.size(), cudaMemcpyHostToDevice, ctx->stream));
+        KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->lay = L;
+    return KF_OK;
+}
+
+int ntasks_of(const KfLayout& L) {
+    const int ksteps = L.Mc / KF_BK;
+    const int per = (ksteps + L.nsplit - 1) / L.nsplit;
+    int used = 0;
+    for (int s = 0; s < L.nsplit; ++s)
+        if (std::min((s + 1) * per, ksteps) > std::min(s * per, ksteps)) ++used;
+    return used * (int)L.tiles.size();
+}
+
+bool same_layout(const KfLayout& L, const KfProgram& p, const kf_problem* pr, int Mc_hint) {
+    (void)Mc_hint;
+    return L.valid && L.model == pr->model && L.m == pr->m && L.nzeta == pr->nzeta && L.n_full == p.n_full() &&
+           L.N == p.N();
+}
+
+// lift + Gram of one shard whose snapshots are on the device
+int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
+    KF_TRY(check_problem(ctx, pr));
+    if (reset || !same_layout(ctx->lay, ctx->prog, pr, 0)) {
+        if (!reset && ctx->lay.valid) {
+            ctx->err = "kf_accumulate_dev: layout changed without reset";
+            return KF_EINVAL;
+        }
+        KF_TRY(make_layout(ctx, pr));
+        const KfLayout& L = ctx->lay;
+        KF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)L.nsplit * L.tiles.size() * KF_TILE_ELEMS * sizeof(double), ctx->stream));
+        ctx->accum_M = 0;
+    }
+    const KfLayout& L = ctx->lay;
+    const KfProgram& p = ctx->prog;
+    const int ntasks = ntasks_of(L);
+    const bool weighted = (L.model == KF_BILINEAR);
+    const long long nchunks = (pr->M + L.Mc - 1) / L.Mc;
+    const bool overlap = ctx->opt_overlap && nchunks > 1;
+    cudaStream_t sg = ctx->stream, sl = overlap ? ctx->stream2 : ctx->stream;
+
+    KF_CUDA(ctx, cudaEventRecord(ctx->ev[0], sg));
+    if (overlap) KF_CUDA(ctx, cudaStreamWaitEvent(sl, ctx->ev[0], 0));
+
+    const int per_k = L.Mc / KF_BK;
+    (void)per_k;
+    float gram_ms_sampled = 0.f;
+    int gram_samples = 0;
+    for (long long c = 0; c < nchunks; ++c) {
+        const int b = (int)(c & 1);
+        KfLiftArgs a{};
+        a.ops = ctx->d_ops.as<KfOp>();
+        a.centres = ctx->d_centres.as<double>();
+        a.pcs = ctx->d_pcs.as<double>();
+        a.nv = p.nv; a.n_full = p.n_full(); a.n_pcs = p.n_pcs; a.N = L.N;
+        a.nzeta = L.nzeta; a.m = L.m; a.model = L.model;
+        a.alpha = pr->alpha; a.beta = pr->beta; a.u = pr->u;
+        a.M = pr->M; a.start = c * L.Mc; a.Mc = L.Mc;
+        a.panel = ctx->d_panel[b].as<double>(); a.ld = L.Mc;
+        a.full = ctx->d_full.as<double>();
+        a.x_off = L.x_off; a.y_off = L.y_off; a.w_off = L.w_off; a.nW = L.nW;
+        if (overlap && c >= 2) KF_CUDA(ctx, cudaStreamWaitEvent(sl, ctx->ev_panel_free[b], 0));
+        KF_TRY(kf_launch_lift(ctx, a, sl));
+        if (overlap) {
+            KF_CUDA(ctx, cudaEventRecord(ctx->ev_panel_ready[b], sl));
+            KF_CUDA(ctx, cudaStreamWaitEvent(sg, ctx->ev_panel_ready[b], 0));
+        }
+        const bool sample = ctx->opt_profile && (nchunks < 8 || (c % 61) == 3);   // CUDA-event timing of the Gram kernel
+        if (sample) KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], sg));
+        KF_TRY(kf_launch_gemm_tasks(ctx, ctx->d_tasks[b].as<KfGemmTask>(), ntasks, weighted, sg));
+        if (sample) {
+            KF_CUDA(ctx, cudaEventRecord(ctx->ev[3], sg));
+            KF_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
+            float ms = 0.f;
+            KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+            gram_ms_sampled += ms;
+            ++gram_samples;
+        }
+        if (overlap) KF_CUDA(ctx, cudaEventRecord(ctx->ev_panel_free[b], sg));
+        ctx->dmma_flops += (double)L.tiles.size() * 2.0 * KF_TILE_ELEMS * (double)L.Mc;
+    }
+    KF_CUDA(ctx, cudaEventRecord(ctx->ev[1], sg));
+    ctx->accum_M += pr->M;
+    ctx->last_gram_kernel_ms = gram_samples ? gram_ms_sampled / gram_samples * (float)nchunks : 0.f;
+    return KF_OK;
+}
+
+int finish_accum(kf_ctx* ctx) {
+    const KfLayout& L = ctx->lay;
+    KF_TRY(kf_reduce_slabs(ctx, ctx->d_accum.as<double>(), (long long)L.tiles.size() * KF_TILE_ELEMS, L.nsplit, ctx->stream));
+    return KF_OK;
+}
+
+int copy_out_matrix(kf_ctx* ctx, const double* d, int Pp, int P, double* h) {
+    if (!h) return KF_OK;
+    KF_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)P * sizeof(double), d, (size_t)Pp * sizeof(double), (size_t)P * sizeof(double), P,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    return KF_OK;
+}
+
+// assemble G, C from the (already slab-reduced, possibly all-reduced) accumulator and solve
+int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
+    const KfLayout& L = ctx->lay;
+    if (!L.valid) {
+        ctx->err = "kf_solve_dev: nothing accumulated";
+        return KF_EINVAL;
+    }
+    cudaStream_t st = ctx->stream;
+    const int P = L.P, Pp = L.Pp;
+    const size_t mat = (size_t)Pp * Pp * sizeof(double);
+    KF_CUDA(ctx, ctx->d_G.ensure(mat));
+    KF_CUDA(ctx, ctx->d_C.ensure(mat));
+    KF_CUDA(ctx, ctx->d_K.ensure(mat));
+    KF_CUDA(ctx, ctx->d_W.ensure(mat));
+    KF_CUDA(ctx, ctx->d_misc.ensure(4096));
+    KF_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+    KF_TRY(kf_assemble(ctx, ctx->d_accum.as<double>(), ctx->d_tilemeta.as<KfTile>(), (int)L.tiles.size(), L,
+                       ctx->d_G.as<double>(), ctx->d_C.as<double>(), st));
+    KF_TRY(copy_out_matrix(ctx, ctx->d_G.as<double>(), Pp, P, out->G));
+    KF_TRY(copy_out_matrix(ctx, ctx->d_C.as<double>(), Pp, P, out->C));
+    if (!sv) {
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+        return KF_OK;
+    }
+    int* d_perm = reinterpret_cast<int*>(ctx->d_misc.as<char>() + 1024);
+    if ((size_t)P * sizeof(int) + 1024 > ctx->d_misc.bytes) {
+        KF_CUDA(ctx, ctx->d_misc.ensure(1024 + (size_t)Pp * sizeof(int)));
+        d_perm = reinterpret_cast<int*>(ctx->d_misc.as<char>() + 1024);
+    }
+    if (sv->least_squares) {
+        int method = sv->ls_method == KF_LS_AUTO ? KF_LS_GRAM : sv->ls_method;
+        if (method != KF_LS_GRAM) {
+            ctx->err = "kf_solve_dev: only KF_LS_GRAM can solve from the accumulator (KF_LS_QR needs the snapshots: use kf_fit)";
+            return KF_EINVAL;
+        }
+        KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_W.p, ctx->d_G.p, mat, cudaMemcpyDeviceToDevice, st));
+        const double tol = sv->pivot_tol > 0 ? sv->pivot_tol : 1e-7;
+        int rank = 0;
+        double minp = 0, maxp = 0;
+        KF_TRY(kf_solve_gram_ls(ctx, P, Pp, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), tol, d_perm,
+                                &rank, &minp, &maxp, st));
+        out->info.rank = rank;
+        out->info.ls_method_used = KF_LS_GRAM;
+        out->info.min_pivot = minp;
+        out->info.max_pivot = maxp;
+        KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K));
+        if (out->perm) KF_CUDA(ctx, cudaMemcpyAsync(out->perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (sv->nt <= 0 || !sv->t) {
+            ctx->err = "kf_solve: QP branch needs nt > 0 budgets";
+            return KF_EINVAL;
+        }
+        ctx->err = "L1-ball QP: not built in this revision";
+        return KF_EUNSUPPORTED;
+    }
+    KF_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    KF_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+    ctx->last_solve_ms = ms;
+    out->info.t_solve_ms = ms;
+    return KF_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int kf_version(void) { return KF_VERSION; }
+
+const char* kf_last_error(const kf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int kf_create(kf_ctx** out, int device) {
+    if (!out) return KF_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_err = std::string("kf_create: no CUDA device (") + cudaGetErrorString(e) + "); koopfit has no CPU fallback";
+        return KF_ECUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_create_err = "kf_create: device index out of range";
+        return KF_EINVAL;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return KF_ECUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10) {
+        g_create_err = "kf_create: libkoopfit.so is built for sm_100a (B200) only; found compute capability " +
+                       std::to_string(prop.major) + "." + std::to_string(prop.minor);
+        return KF_EUNSUPPORTED;
+    }
+    kf_ctx* ctx = new kf_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+        ok = cudaEventCreateWithFlags(&ctx->ev_panel_free[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_panel_ready[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        g_create_err = "kf_create: stream/event creation failed";
+        delete ctx;
+        return KF_ECUDA;
+    }
+    *out = ctx;
+    return KF_OK;
+}
+
+void kf_destroy(kf_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    KfBuf* bufs[] = {&ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_full,
+                     &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
+                     &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3};
+    for (KfBuf* b : bufs) b->release();
+    for (int i = 0; i < 8; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_panel_free[i]) cudaEventDestroy(ctx->ev_panel_free[i]);
+        if (ctx->ev_panel_ready[i]) cudaEventDestroy(ctx->ev_panel_ready[i]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    delete ctx;
+}
+
+int kf_basis_dims(const kf_basis* basis, int model, int m, int* n_full, int* N, int* P) {
+    KfProgram prog;
+    std::string err;
+    int rc = kf_build_program(basis, prog, err);
+    if (rc) {
+        g_create_err = err;
+        return rc;
+    }
+    if (n_full) *n_full = prog.n_full();
+    if (N) *N = prog.N();
+    if (P) *P = kf_regressor_width(model, prog.N(), m);
+    return KF_OK;
+}
+
+int kf_block_table(int type, int degree, int nv, int* rows, int* cols, int* table) {
+    std::vector<int> t;
+    std::string err;
+    int r = 0, c = 0;
+    int rc = kf_block_rows(type, degree, nv, &r, &c, table ? &t : nullptr, err);
+    if (rc) {
+        g_create_err = err;
+        return rc;
+    }
+    if (rows) *rows = r;
+    if (cols) *cols = c;
+    if (table && !t.empty()) std::memcpy(table, t.data(), sizeof(int) * t.size());
+    return KF_OK;
+}
+
+int kf_lift(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V, double* Psi) {
+    if (!ctx) return KF_EINVAL;
+    if (rows <= 0 || !V || !Psi) {
+        ctx->err = "kf_lift: rows > 0, V and Psi required";
+        return KF_EINVAL;
+    }
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    KF_TRY(prepare_program(ctx, basis));
+    const KfProgram& p = ctx->prog;
+    const size_t vin = (size_t)rows * p.nv * sizeof(double), vout = (size_t)rows * p.N() * sizeof(double);
+    const size_t vfull = p.n_pcs ? (size_t)rows * p.n_full() * sizeof(double) : 0;
+    KF_CUDA(ctx, ctx->d_in.ensure(vin));
+    KF_CUDA(ctx, ctx->d_tmp.ensure(vout));
+    if (vfull) KF_CUDA(ctx, ctx->d_full.ensure(vfull));
+    KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, V, vin, cudaMemcpyHostToDevice, ctx->stream));
+    KF_TRY(kf_launch_lift_points(ctx, ctx->d_ops.as<KfOp>(), ctx->d_centres.as<double>(), ctx->d_pcs.as<double>(), p.nv,
+                                 p.n_full(), p.n_pcs, ctx->d_in.as<double>(), rows, ctx->d_full.as<double>(),
+                                 ctx->d_tmp.as<double>(), rows, ctx->stream));
+    KF_CUDA(ctx, cudaMemcpyAsync(Psi, ctx->d_tmp.p, vout, cudaMemcpyDeviceToHost, ctx->stream));
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KF_OK;
+}
+
+int kf_accumulate_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, int reset) {
+    if (!ctx) return KF_EINVAL;
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (reset || !ctx->lay.valid) KF_TRY(prepare_program(ctx, basis));
+    return accumulate_dev(ctx, prob, reset != 0 || !ctx->lay.valid);
+}
+
+int kf_accum_buffer(kf_ctx* ctx, double** dev_ptr, size_t* count) {
+    if (!ctx || !ctx->lay.valid) return KF_EINVAL;
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    KF_TRY(finish_accum(ctx));     // slabs -> slab 0 (idempotent once nsplit slabs are folded)
+    ctx->lay.nsplit = 1;           // further accumulation continues in slab 0 only
+    // task lists still carry the old split; force a rebuild on the next reset
+    if (dev_ptr) *dev_ptr = ctx->d_accum.as<double>();
+    if (count) *count = ctx->lay.tiles.size() * (size_t)KF_TILE_ELEMS;
+    return KF_OK;
+}
+
+int kf_solve_dev(kf_ctx* ctx, const kf_solve* solve, kf_result* out) {
+    if (!ctx || !out) return KF_EINVAL;
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double t0 = now_ms();
+    KF_TRY(finish_accum(ctx));
+    int rc = solve_from_accum(ctx, solve, out);
+    ctx->lay.valid = false;        // accumulator consumed: the next accumulate must reset
+    out->info.t_total_ms = now_ms() - t0;
+    return rc;
+}
+
+int kf_sync(kf_ctx* ctx) {
+    if (!ctx) return KF_EINVAL;
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
+    return KF_OK;
+}
+
+void* kf_stream(kf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out) {
+    if (!ctx || !out || !solve) return KF_EINVAL;
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double t0 = now_ms();
+    std::memset(&out->info, 0, sizeof(out->info));
+    KF_TRY(prepare_program(ctx, basis));
+    KF_TRY(check_problem(ctx, prob));
+    // host -> device: alpha | beta | u, column-major, ld = M  (Ksysid.m:1005)
+    const long long M = prob->M;
+    const size_t nz = (size_t)M * prob->nzeta, nu = (size_t)M * prob->m;
+    KF_CUDA(ctx, ctx->d_in.ensure((2 * nz + nu + 2) * sizeof(double)));
+    double* d_alpha = ctx->d_in.as<double>();
+    double* d_beta = d_alpha + nz;
+    double* d_u = d_beta + nz;
+    KF_CUDA(ctx, cudaMemcpyAsync(d_alpha, prob->alpha, nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    KF_CUDA(ctx, cudaMemcpyAsync(d_beta, prob->beta, nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (nu) KF_CUDA(ctx, cudaMemcpyAsync(d_u, prob->u, nu * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    kf_problem dp = *prob;
+    dp.alpha = d_alpha;
+    dp.beta = d_beta;
+    dp.u = d_u;
+    ctx->lay.valid = false;
+    KF_TRY(accumulate_dev(ctx, &dp, true));
+    KF_TRY(finish_accum(ctx));
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->last_lift_gram_ms = ms;
+    out->info.t_lift_gram_ms = ms;
+    out->info.passes = 1;
+    // optional materialised regressors (koopData.Px / Py, Ksysid.m:1085-1086)
+    if (out->Px || out->Py) {
+        const int P = ctx->lay.P;
+        KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
+        KfLiftArgs a{};
+        a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
+        a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->lay.N;
+        a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
+        a.alpha = d_alpha; a.beta = d_beta; a.u = d_u; a.M = M;
+        if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * M * sizeof(double)));
+        a.full = ctx->d_full.as<double>();
+        KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, M, ctx->stream));
+        if (out->Px) KF_CUDA(ctx, cudaMemcpyAsync(out->Px, ctx->d_qr.p, (size_t)M * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (out->Py) KF_CUDA(ctx, cudaMemcpyAsync(out->Py, ctx->d_qr.as<double>() + (size_t)M * P, (size_t)M * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    int rc = solve_from_accum(ctx, solve, out);
+    ctx->lay.valid = false;
+    out->info.t_total_ms = now_ms() - t0;
+    return rc;
+}
+
+int kf_counters(kf_ctx* ctx, double* dmma_flops, long long* launches, int reset) {
+    if (!ctx) return KF_EINVAL;
+    if (dmma_flops) *dmma_flops = ctx->dmma_flops;
+    if (launches) *launches = ctx->launches;
+    if (reset) {
+        ctx->dmma_flops = 0;
+        ctx->launches = 0;
+    }
+    return KF_OK;
+}
+
+int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, double* solve_ms) {
+    if (!ctx) return KF_EINVAL;
+    if (lift_gram_ms) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_lift_gram_ms = ms;
+        *lift_gram_ms = ctx->last_lift_gram_ms;
+    }
+    if (gram_kernel_ms) *gram_kernel_ms = ctx->last_gram_kernel_ms;
+    if (solve_ms) *solve_ms = ctx->last_solve_ms;
+    return KF_OK;
+}
+
+int kf_set_option(kf_ctx* ctx, const char* name, double value) {
+    if (!ctx || !name) return KF_EINVAL;
+    const std::string n(name);
+    if (n == "chunk") ctx->opt_chunk = (int)value;
+    else if (n == "splitk") ctx->opt_splitk = (int)value;
+    else if (n == "overlap") ctx->opt_overlap = (int)value;
+    else if (n == "panel_mb") ctx->opt_panel_mb = value;
+    else if (n == "profile") ctx->opt_profile = (int)value;
+    else {
+        ctx->err = "kf_set_option: unknown option " + n;
+        return KF_EINVAL;
+    }
+    return KF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+// Internal declarations shared by the .cu files of libkoopfit.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/koopfit.h"
+#include "program.h"
+
+// ------------------------------------------------------------------ tiling constants
+constexpr int KF_BM = 128;          // output tile rows  (A-operand rows per CTA)
+constexpr int KF_BN = 128;          // output tile cols  (B-operand rows per CTA)
+constexpr int KF_BK = 16;           // contraction elements per pipeline stage
+constexpr int KF_LDS = KF_BK + 4;   // padded smem row (doubles): (row*20 + k) mod 16 distinct -> conflict-free LDS.64
+constexpr int KF_STAGES = 4;
+constexpr int KF_GEMM_THREADS = 256;
+constexpr int KF_TILE_ELEMS = KF_BM * KF_BN;
+
+inline long long kf_roundup(long long x, long long m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------ GEMM task
+// One CTA computes  out[m*ldm + n*ldn] (+)= alpha * sum_{k in [k0,k1)} w[k] * A[m*lda + k] * B[n*ldb + k]
+// for a BM x BN tile.  Both operands are "k-contiguous": row r of the operand holds the
+// contraction index contiguously (a lifted-panel row = one observable over the snapshots
+// of the chunk; a column of a column-major matrix).  k0,k1 multiples of KF_BK; rows beyond
+// a_rows/b_rows are clamped for loading and masked on store.
+struct KfGemmTask {
+    const double* A;
+    const double* B;
+    const double* W;      // per-k weights (NULL = none): bilinear u_a*u_b factor
+    double* out;
+    long long lda, ldb;   // operand row strides (doubles), multiples of 2
+    long long ldm, ldn;   // output strides
+    int k0, k1;
+    int a_rows, b_rows;   // valid rows of this tile (<= BM / BN)
+    double alpha;
+    int accumulate;       // 1: out += ; 0: out =
+    int pad;
+};
+
+// ------------------------------------------------------------------ device buffer
+struct KfBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ------------------------------------------------------------------ accumulation layout
+struct KfTile {
+    int kind;   // 0 = G tile, 1 = C tile
+    int q;      // weight row (bilinear pair index; 0 = unweighted)
+    int a, b;   // bilinear block coordinates (u_a, u_b), a <= b; 0,0 otherwise
+    int tm, tn; // tile coordinates inside the block
+};
+
+struct KfLayout {
+    int model = 0, m = 0, nzeta = 0, nv = 0;
+    int n_full = 0, N = 0, P = 0;
+    int Rx = 0, Rxp = 0;      // rows of the X section: N (+m for linear), padded to BM
+    int Ny = 0, Nyp = 0;      // rows of the Y section (N), padded
+    int nW = 0;               // weight rows (bilinear): (m+1)(m+2)/2
+    int x_off = 0, y_off = 0, w_off = 0, rows = 0;   // panel row offsets / total rows
+    int Mc = 0;               // snapshots per panel (multiple of KF_BK)
+    int nsplit = 1;           // split-K slabs
+    std::vector<KfTile> tiles;
+    int Pp = 0;               // P padded to BM: leading dimension of G, C, K work matrices
+    bool valid = false;
+};
+
+struct kf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    int sm_count = 148;
+
+    KfProgram prog;
+    KfLayout lay;
+
+    KfBuf d_ops, d_centres, d_pcs, d_panel[2], d_full, d_tasks[2], d_accum, d_tilemeta;
+    KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3;
+    cudaEvent_t ev_panel_free[2] = {}, ev_panel_ready[2] = {};
+
+    // options
+    int opt_chunk = 0;        // 0 = auto
+    int opt_splitk = 0;       // 0 = auto
+    int opt_overlap = 1;      // lift of chunk c+1 concurrent with Gram of chunk c
+    double opt_panel_mb = 24; // target bytes of one L2-resident panel
+    int opt_profile = 0;      // sample Gram-kernel durations with CUDA events (adds syncs)
+
+    // counters
+    double dmma_flops = 0;
+    long long launches = 0;
+    float last_lift_gram_ms = 0, last_gram_kernel_ms = 0, last_solve_ms = 0;
+    long long accum_M = 0;    // snapshots accumulated since reset
+};
+
+#define KF_CUDA(ctx, call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                         ":" + std::to_string(__LINE__) + ")";                                 \
+            return KF_ECUDA;                                                                   \
+        }                                                                                      \
+    } while (0)
+
+#define KF_TRY(expr)            \
+    do {                        \
+        int rc__ = (expr);      \
+        if (rc__) return rc__;  \
+    } while (0)
+
+// ------------------------------------------------------------------ kernels (host launchers)
+// gemm.cu
+int kf_launch_gemm_tasks(kf_ctx* ctx, const KfGemmTask* d_tasks, int ntasks, bool weighted, cudaStream_t st);
+// grid form: out(M x N tiles) over column-major / k-contiguous operands
+struct KfGemmGrid {
+    const double* A; const double* B; double* out;
+    long long lda, ldb, ldm, ldn;
+    int m, n;          // output extent (rows of A / rows of B)
+    int k0, k1;
+    double alpha; int accumulate;
+    int lower_only;    // 1: skip tiles strictly above the diagonal (tn > tm)
+};
+int kf_launch_gemm_grid(kf_ctx* ctx, const KfGemmGrid& g, cudaStream_t st);
+
+// lift.cu
+struct KfLiftArgs {
+    const KfOp* ops; const double* centres; const double* pcs;
+    int nv, n_full, n_pcs, N;
+    int nzeta, m, model;
+    const double* alpha; const double* beta; const double* u;   // device, column-major, ld = M
+    long long M, start;   // chunk = snapshots [start, start+Mc)
+    int Mc;
+    double* panel; long long ld;   // panel row stride (= Mc)
+    double* full;                  // scratch for dim_red: 2 * n_full rows x ld
+    int x_off, y_off, w_off, nW;
+};
+int kf_launch_lift(kf_ctx* ctx, const KfLiftArgs& a, cudaStream_t st);
+// materialised lift of arbitrary points: V (rows x nv, ld=rows) -> Psi (rows x N, ld = ldo)
+int kf_launch_lift_points(kf_ctx* ctx, const KfOp* ops, const double* centres, const double* pcs, int nv, int n_full,
+                          int n_pcs, const double* V, long long rows, double* full, double* out, long long ldo,
+                          cudaStream_t st);
+// materialised regressors Px, Py (M x P, ld = ldp) from device snapshot pairs
+int kf_launch_regressors(kf_ctx* ctx, const KfLiftArgs& a, double* Px, double* Py, long long ldp, cudaStream_t st);
+
+// solve.cu
+int kf_reduce_slabs(kf_ctx* ctx, double* accum, long long slab_elems, int nsplit, cudaStream_t st);
+int kf_assemble(kf_ctx* ctx, const double* accum, const KfTile* d_meta, int ntiles, const KfLayout& lay,
+                double* G, double* C, cudaStream_t st);
+// pivoted Cholesky basic solution of G K = C  (G, C, K: Pp x Pp column-major, ld = Pp)
+int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, double* G_work, const double* C, double* K, double tol,
+                     int* d_perm, int* rank_out, double* min_piv, double* max_piv, cudaStream_t st);
+// Householder QRCP basic solution of A X = B;  AB = [A | B] (M x (P+Pc), ld = ldab) is overwritten
+int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long long ldab, double* X, long long ldx,
+                   int* d_perm, int* rank_out, double* min_piv, double* max_piv, cudaStream_t st);
+
+// qp.cu
+struct KfQpResult { double objective; double l1; int iters; };
+int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, double t, int fix_c0, int fix_c1,
+                    const double* d_fix_target, int max_iter, double tol, double* K, KfQpResult* res, cudaStream_t st);

@@ -1,0 +1,399 @@
+// Least-squares solve of the fit on the GPU (replaces `K = Px \ Py`, Ksysid.m:1069).
+//
+// Gram route (this file, part 1): deterministic split-K slab reduction, assembly of the
+// full G = Px'Px and C = Px'Py from the accumulator tiles (expanding the bilinear
+// Kronecker blocks), diagonal-pivoted Cholesky of G with a rank tolerance, and the BASIC
+// solution on the pivot set (zeros elsewhere) — the semantics of MATLAB's mldivide for a
+// rank-deficient tall matrix (QR with column pivoting: the remaining squared column norms
+// of QRCP are exactly the Schur-complement diagonal of G, so the pivot order is the same).
+// The triangular solves are blocked: 128x128 diagonal blocks in shared memory, everything
+// else through the DMMA kernel of gemm.cu.
+#include "kf_internal.h"
+
+namespace {
+
+// ---------------------------------------------------------------- split-K slabs
+__global__ void kf_reduce_slabs_kernel(double* __restrict__ accum, long long slab, int nsplit) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slab;
+         i += (long long)gridDim.x * blockDim.x) {
+        double v = accum[i];
+        for (int s = 1; s < nsplit; ++s) v += accum[(long long)s * slab + i];   // fixed order: deterministic
+        accum[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------- assembly
+struct AsmArgs {
+    int model, N, P, m, Rx, Pp;
+    double* G;
+    double* C;
+};
+
+__global__ void __launch_bounds__(256) kf_assemble_kernel(const double* __restrict__ accum,
+                                                          const KfTile* __restrict__ meta, AsmArgs s) {
+    const KfTile t = meta[blockIdx.x];
+    const double* tile = accum + (long long)blockIdx.x * KF_TILE_ELEMS;
+    const long long ld = s.Pp;
+    for (int e = threadIdx.x; e < KF_TILE_ELEMS; e += blockDim.x) {
+        const int mm = e / KF_BN, nn = e % KF_BN;
+        const int r = t.tm * KF_BM + mm, c = t.tn * KF_BN + nn;
+        const double v = tile[e];
+        if (s.model != KF_BILINEAR) {
+            if (t.kind == 0) {
+                if (r >= s.Rx || c >= s.Rx || c > r) continue;   // lower triangle only, mirrored: exactly symmetric
+                s.G[(long long)c * ld + r] = v;
+                s.G[(long long)r * ld + c] = v;
+                if (s.model == KF_LINEAR) {   // Py = [psi(y), u]: C(:, N+i) = G(:, N+i)  (Ksysid.m:1063)
+                    if (c >= s.N) s.C[(long long)c * ld + r] = v;
+                    if (r >= s.N) s.C[(long long)r * ld + c] = v;
+                }
+            } else {
+                if (r >= s.Rx || c >= s.N) continue;
+                s.C[(long long)c * ld + r] = v;
+            }
+        } else {
+            if (r >= s.N || c >= s.N) continue;
+            const long long ra = (long long)t.a * s.N + r, rb = (long long)t.b * s.N + r;
+            const long long ca = (long long)t.a * s.N + c, cb = (long long)t.b * s.N + c;
+            if (t.kind == 0) {
+                if (c > r) continue;
+                // G[(a,r),(b,c)] = sum u_a u_b psi_r psi_c: symmetric in (a<->b) and (r<->c)
+                s.G[cb * ld + ra] = v;
+                s.G[ca * ld + rb] = v;
+                s.G[rb * ld + ca] = v;
+                s.G[ra * ld + cb] = v;
+            } else {
+                // C[(a,r),(b,c)] = sum u_a u_b psix_r psiy_c = C[(b,r),(a,c)]
+                s.C[cb * ld + ra] = v;
+                s.C[ca * ld + rb] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- pivoted Cholesky
+struct PcholState {
+    double piv0;     // first (largest) pivot = R11^2
+    double minpiv;   // smallest accepted pivot
+    int rank;
+    int done;
+};
+
+// one CTA: pick the largest remaining diagonal, symmetric swap j<->p, scale column/row j
+__global__ void __launch_bounds__(1024) kf_pchol_pivot_kernel(double* W, long long ld, int P, int j, int* perm,
+                                                              PcholState* st, double tol2) {
+    if (st->done) return;
+    __shared__ double sval[32];
+    __shared__ int sidx[32];
+    __shared__ int s_p;
+    __shared__ double s_d;
+    const int tid = threadIdx.x;
+    double best = -1.0;
+    int bi = P;
+    for (int i = j + tid; i < P; i += blockDim.x) {
+        const double v = W[(long long)i * ld + i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { sval[tid >> 5] = best; sidx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+        best = (tid < (blockDim.x >> 5)) ? sval[tid] : -1.0;
+        bi = (tid < (blockDim.x >> 5)) ? sidx[tid] : P;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (tid == 0) {
+            if (j == 0) st->piv0 = best;
+            const bool ok = (best > 0.0) && (best > tol2 * st->piv0);   // false for NaN as well
+            if (!ok) {
+                st->rank = j;
+                st->done = 1;
+                s_p = -1;
+            } else {
+                s_p = bi;
+                s_d = sqrt(best);
+                st->minpiv = best;
+                st->rank = j + 1;
+            }
+        }
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (p < 0) return;
+    if (p != j) {
+        for (int i = tid; i < P; i += blockDim.x) {   // swap columns j <-> p
+            const double a = W[(long long)j * ld + i], b = W[(long long)p * ld + i];
+            W[(long long)j * ld + i] = b;
+            W[(long long)p * ld + i] = a;
+        }
+        __syncthreads();
+        for (int i = tid; i < P; i += blockDim.x) {   // swap rows j <-> p
+            const double a = W[(long long)i * ld + j], b = W[(long long)i * ld + p];
+            W[(long long)i * ld + j] = b;
+            W[(long long)i * ld + p] = a;
+        }
+        if (tid == 0) {
+            const int a = perm[j];
+            perm[j] = perm[p];
+            perm[p] = a;
+        }
+        __syncthreads();
+    }
+    const double d = s_d;
+    for (int i = j + tid; i < P; i += blockDim.x) {
+        const double l = (i == j) ? d : W[(long long)j * ld + i] / d;
+        W[(long long)j * ld + i] = l;   // column j: L(i,j)
+        W[(long long)i * ld + j] = l;   // row j:    L(i,j) again (k-contiguous copy for the DMMA operands)
+    }
+}
+
+// trailing update W(i,k) -= L(i,j) L(k,j), i,k > j (both triangles: stays exactly symmetric)
+__global__ void __launch_bounds__(256) kf_pchol_update_kernel(double* W, long long ld, int P, int j,
+                                                              const PcholState* st) {
+    if (st->done) return;
+    const int i = j + 1 + blockIdx.x * 64 + (threadIdx.x & 63);
+    const int k0 = j + 1 + blockIdx.y * 16 + (threadIdx.x >> 6) * 4;
+    if (i >= P) return;
+    const double li = W[(long long)j * ld + i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = k0 + q;
+        if (k < P) {
+            const double lk = W[(long long)k * ld + j];
+            W[(long long)k * ld + i] = fma(-li, lk, W[(long long)k * ld + i]);
+        }
+    }
+}
+
+// zero rows/cols >= rank of the factor so padded contraction ranges contribute nothing
+__global__ void kf_pchol_clean_kernel(double* W, long long ld, int Pp, const PcholState* st) {
+    const int r = st->rank;
+    const long long n = (long long)Pp * Pp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % Pp), k = (int)(e / Pp);
+        if (i >= r || k >= r) W[(long long)k * ld + i] = 0.0;
+    }
+}
+
+// X(i,n) = C(perm[i], n) for i < rank, 0 otherwise
+__global__ void kf_gather_rows_kernel(const double* __restrict__ C, long long ldc, const int* __restrict__ perm,
+                                      const PcholState* st, int Pp, int ncols, double* X, long long ldx) {
+    const int r = st->rank;
+    const long long n = (long long)Pp * ncols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % Pp), c = (int)(e / Pp);
+        X[(long long)c * ldx + i] = (i < r) ? C[(long long)c * ldc + perm[i]] : 0.0;
+    }
+}
+
+// K(perm[i], n) = X(i,n) for i < rank; K zeroed beforehand
+__global__ void kf_scatter_rows_kernel(const double* __restrict__ X, long long ldx, const int* __restrict__ perm,
+                                       const int* __restrict__ rank_ptr, int ncols, double* K, long long ldk) {
+    const int r = *rank_ptr;
+    const long long n = (long long)r * ncols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % r), c = (int)(e / r);
+        K[(long long)c * ldk + perm[i]] = X[(long long)c * ldx + i];
+    }
+}
+
+// Triangular solve with one 128x128 diagonal block T = W[I:I+128, I:I+128] held in shared memory.
+// lower=1: solve L z = y (forward), lower=0: solve L' x = z (backward).  S[i*128+k] = W(I+k, I+i)
+// (column I+i of the full symmetric factor): forward uses k >= i (= L(k,i)), backward k <= i (= L(i,k)).
+// One warp per right-hand-side column; lane holds rows lane + 32 q.
+__global__ void __launch_bounds__(256) kf_trsm_diag_kernel(const double* __restrict__ W, long long ld, int I,
+                                                           const int* __restrict__ rank_ptr, double* X, long long ldx,
+                                                           int ncols, int lower) {
+    extern __shared__ __align__(16) double S[];
+    const int r = *rank_ptr;
+    const int nb = min(128, r - I);
+    if (nb <= 0) return;
+    for (int e = threadIdx.x; e < 128 * 128; e += blockDim.x) {
+        const int i = e >> 7, k = e & 127;
+        S[e] = (i < nb && k < nb) ? W[(long long)(I + i) * ld + I + k] : (i == k ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int col = blockIdx.x * 8 + warp; col < ncols; col += gridDim.x * 8) {
+        double* x = X + (long long)col * ldx + I;
+        double y[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) y[q] = (lane + 32 * q < nb) ? x[lane + 32 * q] : 0.0;
+        if (lower) {
+#pragma unroll
+            for (int qi = 0; qi < 4; ++qi) {
+                for (int li = 0; li < 32; ++li) {
+                    const int i = qi * 32 + li;
+                    if (i >= nb) break;
+                    const double zi = __shfl_sync(0xffffffffu, y[qi], li) / S[i * 128 + i];
+                    if (lane == li) y[qi] = zi;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = lane + 32 * q;
+                        if (q >= qi && k > i) y[q] = fma(-S[i * 128 + k], zi, y[q]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int qi = 3; qi >= 0; --qi) {
+                for (int li = 31; li >= 0; --li) {
+                    const int i = qi * 32 + li;
+                    if (i >= nb) continue;
+                    const double zi = __shfl_sync(0xffffffffu, y[qi], li) / S[i * 128 + i];
+                    if (lane == li) y[qi] = zi;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = lane + 32 * q;
+                        if (q <= qi && k < i) y[q] = fma(-S[i * 128 + k], zi, y[q]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (lane + 32 * q < nb) x[lane + 32 * q] = y[q];
+    }
+}
+
+}  // namespace
+
+int kf_reduce_slabs(kf_ctx* ctx, double* accum, long long slab_elems, int nsplit, cudaStream_t st) {
+    if (nsplit <= 1) return KF_OK;
+    int grid = (int)std::min<long long>((slab_elems + 255) / 256, (long long)ctx->sm_count * 8);
+    kf_reduce_slabs_kernel<<<grid, 256, 0, st>>>(accum, slab_elems, nsplit);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return KF_OK;
+}
+
+int kf_assemble(kf_ctx* ctx, const double* accum, const KfTile* d_meta, int ntiles, const KfLayout& lay, double* G,
+                double* C, cudaStream_t st) {
+    const size_t bytes = (size_t)lay.Pp * lay.Pp * sizeof(double);
+    KF_CUDA(ctx, cudaMemsetAsync(G, 0, bytes, st));
+    KF_CUDA(ctx, cudaMemsetAsync(C, 0, bytes, st));
+    AsmArgs s{lay.model, lay.N, lay.P, lay.m, lay.Rx, lay.Pp, G, C};
+    kf_assemble_kernel<<<ntiles, 256, 0, st>>>(accum, d_meta, s);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return KF_OK;
+}
+
+// blocked triangular solves  L Z = X, L' X = Z  on the leading rank x rank factor in W
+static int trsm_both(kf_ctx* ctx, const double* W, long long ld, int P, int rank_hint, const int* d_rank, double* X,
+                     long long ldx, int ncols, cudaStream_t st) {
+    // rank_hint: host copy of the rank (bounds the block loops)
+    static bool attr = false;
+    if (!attr) {
+        KF_CUDA(ctx, cudaFuncSetAttribute(kf_trsm_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8));
+        attr = true;
+    }
+    const int r = rank_hint;
+    const int nblk = (r + 127) / 128;
+    const int grid = std::max(1, std::min((ncols + 7) / 8, ctx->sm_count));
+    const int kmax = (int)kf_roundup(r, KF_BK);
+    // forward: for block row I: X[I,:] -= L[I,0:I) Z[0:I,:]  then solve the diagonal block
+    for (int b = 0; b < nblk; ++b) {
+        const int I = b * 128;
+        if (I > 0) {
+            KfGemmGrid g{};
+            g.A = W + (long long)I * ld;   // A[m][k] = L(I+m,k) = W(k, I+m): column I+m, k contiguous
+            g.lda = ld;
+            g.B = X;                       // B[n][k] = Z(k,n)
+            g.ldb = ldx;
+            g.out = X + I;                 // out[m][n] = X(I+m, n)
+            g.ldm = 1;
+            g.ldn = ldx;
+            g.m = std::min(128, r - I);
+            g.n = ncols;
+            g.k0 = 0;
+            g.k1 = I;
+            g.alpha = -1.0;
+            g.accumulate = 1;
+            KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+        }
+        kf_trsm_diag_kernel<<<grid, 256, 128 * 128 * 8, st>>>(W, ld, I, d_rank, X, ldx, ncols, 1);
+        KF_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    // backward: for block row I (last to first): Z[I,:] -= sum_{k>=I+128} L(k, I+m) X(k,:)
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int I = b * 128;
+        if (I + 128 < r) {
+            KfGemmGrid g{};
+            g.A = W + (long long)I * ld;   // A[m][k] = L(k, I+m) = W(k, I+m) (lower part), k contiguous
+            g.lda = ld;
+            g.B = X;
+            g.ldb = ldx;
+            g.out = X + I;
+            g.ldm = 1;
+            g.ldn = ldx;
+            g.m = 128;
+            g.n = ncols;
+            g.k0 = I + 128;
+            g.k1 = kmax;                   // rows >= rank of W and X are zero
+            g.alpha = -1.0;
+            g.accumulate = 1;
+            KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+        }
+        kf_trsm_diag_kernel<<<grid, 256, 128 * 128 * 8, st>>>(W, ld, I, d_rank, X, ldx, ncols, 0);
+        KF_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    return KF_OK;
+}
+
+int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, double* W, const double* C, double* K, double tol, int* d_perm,
+                     int* rank_out, double* min_piv, double* max_piv, cudaStream_t st) {
+    // state block in d_misc: [PcholState]
+    KF_CUDA(ctx, ctx->d_misc.ensure(4096));
+    PcholState* d_state = ctx->d_misc.as<PcholState>();
+    PcholState h0{0.0, 0.0, 0, 0};
+    KF_CUDA(ctx, cudaMemcpyAsync(d_state, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
+    {
+        std::vector<int> id(P);
+        for (int i = 0; i < P; ++i) id[i] = i;
+        KF_CUDA(ctx, cudaMemcpyAsync(d_perm, id.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));   // id goes out of scope
+    }
+    const long long ld = Pp;
+    const double tol2 = tol * tol;
+    for (int j = 0; j < P; ++j) {
+        kf_pchol_pivot_kernel<<<1, 1024, 0, st>>>(W, ld, P, j, d_perm, d_state, tol2);
+        const int rem = P - j - 1;
+        if (rem > 0) {
+            dim3 grid((rem + 63) / 64, (rem + 15) / 16);
+            kf_pchol_update_kernel<<<grid, 256, 0, st>>>(W, ld, P, j, d_state);
+        }
+    }
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2LL * P;
+    kf_pchol_clean_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W, ld, Pp, d_state);
+    PcholState hs;
+    KF_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    KF_CUDA(ctx, cudaStreamSynchronize(st));
+    const int r = hs.rank;
+    *rank_out = r;
+    *max_piv = sqrt(hs.piv0 > 0 ? hs.piv0 : 0.0);
+    *min_piv = sqrt(hs.minpiv > 0 ? hs.minpiv : 0.0);
+    // X = C(perm[0:r], :) in the K buffer's scratch twin (d_tmp), solve, scatter
+    KF_CUDA(ctx, ctx->d_tmp.ensure((size_t)Pp * Pp * sizeof(double)));
+    double* X = ctx->d_tmp.as<double>();
+    kf_gather_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(C, ld, d_perm, d_state, Pp, P, X, ld);
+    KF_CUDA(ctx, cudaGetLastError());
+    KF_CUDA(ctx, cudaMemsetAsync(K, 0, (size_t)Pp * Pp * sizeof(double), st));
+    if (r > 0) {
+        KF_TRY(trsm_both(ctx, W, ld, P, r, &d_state->rank, X, ld, P, st));
+        kf_scatter_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(X, ld, d_perm, &d_state->rank, P, K, ld);
+        KF_CUDA(ctx, cudaGetLastError());
+    }
+    ctx->launches += 4;
+    return KF_OK;
+}

@@ -1,0 +1,162 @@
+"""Thin ctypes driver of the C ABI (include/koopfit.h): one `Fitter` = one kf_ctx = one GPU.
+
+This is the Python stand-in for the MEX shim described in INTEGRATION.md: it only
+marshals column-major double buffers across the ABI; all arithmetic of the fit
+(lift, Gram, solve) happens in libkoopfit.so on the GPU.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+
+
+class Fitter:
+    def __init__(self, device=0):
+        self.lib = A.load()
+        self.ctx = C.c_void_p()
+        rc = self.lib.kf_create(C.byref(self.ctx), int(device))
+        if rc:
+            raise A.KoopfitError(f"kf_create failed ({A.ERRORS.get(rc, rc)}): "
+                                 f"{self.lib.kf_last_error(None).decode()}")
+        self.device = device
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "ctx", None) and self.ctx.value:
+            self.lib.kf_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc:
+            raise A.KoopfitError(f"{what} failed ({A.ERRORS.get(rc, rc)}): {self.lib.kf_last_error(self.ctx).decode()}")
+
+    def set_option(self, name, value):
+        self._check(self.lib.kf_set_option(self.ctx, name.encode(), float(value)), "kf_set_option")
+
+    def counters(self, reset=False):
+        f, n = C.c_double(), C.c_longlong()
+        self._check(self.lib.kf_counters(self.ctx, C.byref(f), C.byref(n), int(reset)), "kf_counters")
+        return f.value, n.value
+
+    def last_times(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._check(self.lib.kf_last_times(self.ctx, C.byref(a), C.byref(b), C.byref(c)), "kf_last_times")
+        return {"lift_gram_ms": a.value, "gram_kernel_ms": b.value, "solve_ms": c.value}
+
+    def sync(self):
+        self._check(self.lib.kf_sync(self.ctx), "kf_sync")
+
+    @property
+    def stream(self):
+        return self.lib.kf_stream(self.ctx)
+
+    # ------------------------------------------------------------------ dictionary
+    def dims(self, basis, model, m):
+        nf, N, P = C.c_int(), C.c_int(), C.c_int()
+        rc = self.lib.kf_basis_dims(basis.ref(), A.MODEL_CODE[model], int(m), C.byref(nf), C.byref(N), C.byref(P))
+        if rc:
+            raise A.KoopfitError(f"kf_basis_dims failed: {self.lib.kf_last_error(None).decode()}")
+        return nf.value, N.value, P.value
+
+    def lift(self, basis, V):
+        """lift.econ_full on the rows of V (rows x nv) -> (rows x N)."""
+        V = A.fcol(np.atleast_2d(V))
+        rows = V.shape[0]
+        _, N, _ = self.dims(basis, "nonlinear", 0)
+        out = np.empty((rows, N), order="F")
+        self._check(self.lib.kf_lift(self.ctx, basis.ref(), rows, A.dptr(V), A.dptr(out)), "kf_lift")
+        return out
+
+    # ------------------------------------------------------------------ the fit
+    @staticmethod
+    def _solve_struct(least_squares=True, ls_method="auto", pivot_tol=0.0, t=None, psd_shift="as_reference",
+                      delay_constraint=False, n=0, nd=0, qp_max_iter=0, qp_tol=0.0):
+        sv = A.kf_solve()
+        sv.least_squares = int(bool(least_squares))
+        sv.ls_method = {"auto": A.KF_LS_AUTO, "gram": A.KF_LS_GRAM, "qr": A.KF_LS_QR}[ls_method]
+        sv.pivot_tol = float(pivot_tol)
+        keep = None
+        if not least_squares:
+            keep = np.ascontiguousarray(np.atleast_1d(np.asarray(t, dtype=np.float64)))
+            sv.nt = keep.size
+            sv.t = A.dptr(keep)
+        sv.psd_shift = {"as_reference": 0, "never": 1, "always": 2}[psd_shift]
+        sv.delay_constraint = int(bool(delay_constraint))
+        sv.n, sv.nd = int(n), int(nd)
+        sv.qp_max_iter = int(qp_max_iter)
+        sv.qp_tol = float(qp_tol)
+        return sv, keep
+
+    def fit(self, basis, model_type, alpha, beta, u, want_gram=False, want_regressors=False, **solve_kw):
+        """get_Koopman for host snapshot pairs (Ksysid.m:987-1092): returns dict with K (P x P, or
+        P x P x nt for a budget vector), rank, perm, info and optionally G, C, Px, Py."""
+        alpha, beta, u = A.fcol(alpha), A.fcol(beta), A.fcol(u)
+        M, nzeta = alpha.shape
+        m = u.shape[1]
+        _, N, P = self.dims(basis, model_type, m)
+        pr = A.kf_problem(M=M, nzeta=nzeta, m=m, model=A.MODEL_CODE[model_type],
+                          alpha=alpha.ctypes.data, beta=beta.ctypes.data, u=u.ctypes.data)
+        sv, keep_t = self._solve_struct(**solve_kw)
+        nt = max(1, sv.nt) if not sv.least_squares else 1
+        res = A.kf_result()
+        K = np.zeros((P, P, nt), order="F")
+        perm = np.zeros(P, dtype=np.int32)
+        obj, l1 = np.zeros(nt), np.zeros(nt)
+        iters = np.zeros(nt, dtype=np.int32)
+        res.K, res.perm = A.dptr(K), perm.ctypes.data_as(A.c_int_p)
+        res.objective, res.l1norm, res.qp_iters = A.dptr(obj), A.dptr(l1), iters.ctypes.data_as(A.c_int_p)
+        out = {}
+        if want_gram:
+            out["G"], out["C"] = np.zeros((P, P), order="F"), np.zeros((P, P), order="F")
+            res.G, res.C = A.dptr(out["G"]), A.dptr(out["C"])
+        if want_regressors:
+            out["Px"], out["Py"] = np.zeros((M, P), order="F"), np.zeros((M, P), order="F")
+            res.Px, res.Py = A.dptr(out["Px"]), A.dptr(out["Py"])
+        self._check(self.lib.kf_fit(self.ctx, basis.ref(), C.byref(pr), C.byref(sv), C.byref(res)), "kf_fit")
+        info = {f: getattr(res.info, f) for f, _ in A.kf_info._fields_}
+        out.update(K=K[:, :, 0] if nt == 1 else K, K_all=K, rank=info["rank"], perm=perm, info=info, N=N, P=P,
+                   objective=obj, l1norm=l1, qp_iters=iters)
+        return out
+
+    # ------------------------------------------------------------------ staged / device-resident API
+    def accumulate_dev(self, basis, model_type, M, nzeta, m, alpha_ptr, beta_ptr, u_ptr, reset=True):
+        """Partial Gram of a device-resident shard (pointers from torch tensors' data_ptr());
+        column-major M x nzeta / M x m, i.e. torch tensors of shape (nzeta, M) contiguous."""
+        pr = A.kf_problem(M=int(M), nzeta=int(nzeta), m=int(m), model=A.MODEL_CODE[model_type],
+                          alpha=int(alpha_ptr), beta=int(beta_ptr), u=int(u_ptr))
+        self._check(self.lib.kf_accumulate_dev(self.ctx, basis.ref(), C.byref(pr), int(reset)), "kf_accumulate_dev")
+
+    def accum_buffer(self):
+        """(device pointer, count of doubles) of the packed partial-Gram accumulator."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.lib.kf_accum_buffer(self.ctx, C.byref(p), C.byref(n)), "kf_accum_buffer")
+        return p.value, n.value
+
+    def solve_dev(self, P, want_gram=False, **solve_kw):
+        sv, keep_t = self._solve_struct(**solve_kw)
+        nt = max(1, sv.nt) if not sv.least_squares else 1
+        res = A.kf_result()
+        K = np.zeros((P, P, nt), order="F")
+        perm = np.zeros(P, dtype=np.int32)
+        obj, l1 = np.zeros(nt), np.zeros(nt)
+        iters = np.zeros(nt, dtype=np.int32)
+        res.K, res.perm = A.dptr(K), perm.ctypes.data_as(A.c_int_p)
+        res.objective, res.l1norm, res.qp_iters = A.dptr(obj), A.dptr(l1), iters.ctypes.data_as(A.c_int_p)
+        out = {}
+        if want_gram:
+            out["G"], out["C"] = np.zeros((P, P), order="F"), np.zeros((P, P), order="F")
+            res.G, res.C = A.dptr(out["G"]), A.dptr(out["C"])
+        self._check(self.lib.kf_solve_dev(self.ctx, C.byref(sv), C.byref(res)), "kf_solve_dev")
+        info = {f: getattr(res.info, f) for f, _ in A.kf_info._fields_}
+        out.update(K=K[:, :, 0] if nt == 1 else K, K_all=K, rank=info["rank"], perm=perm, info=info,
+                   objective=obj, l1norm=l1, qp_iters=iters)
+        return out

@@ -1,0 +1,143 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI
+against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+import koopfit
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(float).eps
+
+
+def relF(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def centres_for(types, degs, nv, seed=0):
+    ng = sum(d for t, d in zip(types, degs) if t == "gaussian")
+    return 2 * np.random.default_rng(seed).random((nv, ng)) - 1 if ng else None
+
+
+LIFT_CASES = [
+    (["poly"], [2], 6), (["poly"], [3], 15), (["poly"], [13], 1), (["hermite"], [3], 4),
+    (["fourier"], [4], 3), (["fourier_sparser"], [3], 3), (["gaussian"], [8], 3),
+    (["poly", "gaussian"], [3, 569], 12),
+    (["poly", "fourier", "hermite", "gaussian", "fourier_sparser"], [2, 1, 2, 5, 2], 3),
+]
+
+
+@pytest.mark.parametrize("types,degs,nv", LIFT_CASES)
+def test_lift_matches_oracle(fitter, types, degs, nv):
+    cen = centres_for(types, degs, nv)
+    basis = koopfit.Basis(types, degs, nv, cen)
+    prog = O.build_program(types, degs, nv, cen)
+    V = 2 * np.random.default_rng(3).random((1000, nv)) - 1
+    got = fitter.lift(basis, V)
+    want = O.lift(prog, V)
+    assert got.shape == want.shape
+    if all(t in ("poly", "hermite") for t in types):
+        assert np.array_equal(got, want)                    # products only: bit-exact
+    # sin/cos/exp: CUDA libm vs numpy, a few ulp of the result scale
+    assert np.abs(got - want).max() <= 8 * EPS
+
+
+def synth(M, n, m, seed=0):
+    rng = np.random.default_rng(seed)
+    alpha = 2 * rng.random((M, n)) - 1
+    u = 2 * rng.random((M, m)) - 1
+    A0 = 0.9 * np.linalg.qr(rng.standard_normal((n, n)))[0]
+    B0 = 0.2 * rng.standard_normal((n, m))
+    beta = np.clip(alpha @ A0.T + u @ B0.T + 0.1 * alpha * u[:, :1] + 0.01 * rng.standard_normal((M, n)), -1, 1)
+    return alpha, beta, u
+
+
+@pytest.mark.parametrize("model", ["linear", "bilinear", "nonlinear"])
+@pytest.mark.parametrize("types,degs", [(["poly"], [2]), (["poly", "gaussian"], [2, 7]), (["fourier_sparser"], [2])])
+@pytest.mark.parametrize("M", [777, 5000])
+def test_gram_and_ls_synthetic(fitter, model, types, degs, M):
+    """G = Px'Px, C = Px'Py (Ksysid.m:1114,1125) to 1e-13 and K = Px\\Py to 1e-9 on well-conditioned data,
+    including ragged M (not a multiple of any tile) and P below one tile."""
+    n, m = 3, 2
+    alpha, beta, u = synth(M, n, m)
+    nv = n + (m if model == "nonlinear" else 0)
+    cen = centres_for(types, degs, nv)
+    basis = koopfit.Basis(types, degs, nv, cen)
+    prog = O.build_program(types, degs, nv, cen)
+    Px, Py = O.build_regressors(model, prog, alpha, beta, u)
+    res = fitter.fit(basis, model, alpha, beta, u, want_gram=True, ls_method="gram")
+    G, C = O.gram(Px, Py)
+    assert res["G"].shape == G.shape
+    assert relF(res["G"], G) < 1e-13 and relF(res["C"], C) < 1e-13
+    assert np.array_equal(res["G"], res["G"].T)             # exactly symmetric by construction
+    Kref, info = O.mldivide(Px, Py, return_info=True)
+    if info["rank"] == Px.shape[1]:
+        assert res["rank"] == info["rank"]
+        assert relF(res["K"], Kref) < 1e-9
+
+
+def test_regressors_materialised(fitter):
+    """koopData.Px / Py (Ksysid.m:1085-1086): the three layouts of Ksysid.m:1039-1063."""
+    alpha, beta, u = synth(1234, 3, 2)
+    for model in ("linear", "bilinear", "nonlinear"):
+        nv = 3 + (2 if model == "nonlinear" else 0)
+        basis = koopfit.Basis(["poly"], [3], nv)
+        prog = O.build_program(["poly"], [3], nv)
+        Px, Py = O.build_regressors(model, prog, alpha, beta, u)
+        res = fitter.fit(basis, model, alpha, beta, u, want_regressors=True, ls_method="gram")
+        assert np.array_equal(res["Px"], Px) and np.array_equal(res["Py"], Py)
+
+
+def test_config1_arm_bilinear_poly2(fitter, arm_data):
+    """BASELINE config 1: bilinear, poly 2, lasso=Inf on the arm data: P=112, rank 100 (exactly
+    rank-deficient) -> mldivide's pivoted basic solution; A, B to 1e-9, val RMSE to 1e-6."""
+    k = O.KsysidOracle(arm_data, model_type="bilinear", obs_type=["poly"], obs_degree=[2]).train_models()
+    koop = k.koopData[0]
+    basis = koopfit.Basis(["poly"], [2], 6)
+    res = fitter.fit(basis, "bilinear", k.pairs["alpha"], k.pairs["beta"], k.pairs["u"], want_gram=True, ls_method="gram")
+    G, C = O.gram(koop["Px"], koop["Py"])
+    assert relF(res["G"], G) < 1e-13 and relF(res["C"], C) < 1e-13
+    assert res["rank"] == koop["info"]["rank"] == 100
+    assert set(res["perm"][:100].tolist()) == set(koop["info"]["perm"][:100].tolist())
+    K = res["K"]
+    N = 28
+    A, B = K.T[:N, :N], K.T[:N, N:]
+    assert relF(A, k.model["A"]) < 1e-9 and relF(B, k.model["B"]) < 1e-9
+    assert relF(K, koop["K"]) < 1e-9
+    for trial in range(5):
+        want = k.validate(trial=trial)["error"]["rmse"]
+        got = O.val_BLmodel({"A": A, "B": B, "C": k.model["C"]}, k.prog, k.valdata[trial], 0, 6)["error"]["rmse"]
+        assert np.abs(got - want).max() < 1e-6
+
+
+def test_sharded_accumulation_equals_single_pass(fitter):
+    """Snapshot sharding: accumulating the shards one after the other into the same
+    accumulator gives the single-pass G, C up to summation order."""
+    import torch
+    alpha, beta, u = synth(6000, 3, 2, seed=5)
+    basis = koopfit.Basis(["poly"], [3], 3)
+    P = fitter.dims(basis, "bilinear", 2)[2]
+    full = fitter.fit(basis, "bilinear", alpha, beta, u, want_gram=True, ls_method="gram")
+    dev = torch.device("cuda:0")
+    first = True
+    keep = []
+    for lo, hi in ((0, 2500), (2500, 6000)):
+        ta = torch.tensor(np.ascontiguousarray(alpha[lo:hi].T), device=dev)
+        tb = torch.tensor(np.ascontiguousarray(beta[lo:hi].T), device=dev)
+        tu = torch.tensor(np.ascontiguousarray(u[lo:hi].T), device=dev)
+        torch.cuda.synchronize()
+        keep += [ta, tb, tu]
+        fitter.accumulate_dev(basis, "bilinear", hi - lo, 3, 2, ta.data_ptr(), tb.data_ptr(), tu.data_ptr(), reset=first)
+        first = False
+    fitter.sync()
+    res = fitter.solve_dev(P, want_gram=True, ls_method="gram")
+    assert relF(res["G"], full["G"]) < 1e-14 and relF(res["C"], full["C"]) < 1e-14
+    assert relF(res["K"], full["K"]) < 1e-10
+
+
+def test_errors_are_reported(fitter):
+    alpha, beta, u = synth(100, 3, 2)
+    basis = koopfit.Basis(["poly"], [2], 4)                  # wrong nv for a linear model with nzeta=3
+    with pytest.raises(koopfit.KoopfitError):
+        fitter.fit(basis, "linear", alpha, beta, u)

@@ -1,0 +1,101 @@
+"""CPU tests of the host logic: the C++ dictionary compiler (the one libkoopfit.so uses)
+against the oracle, and the C-ABI library's exported symbols."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import koopfit
+import oracle as O
+from koopfit import _abi as A
+
+CASES = [
+    (["poly"], [2], 6), (["poly"], [3], 15), (["poly"], [3], 18), (["poly"], [1], 6), (["poly"], [13], 1),
+    (["hermite"], [3], 4), (["fourier"], [4], 3), (["fourier_sparser"], [3], 3), (["gaussian"], [8], 3),
+    (["poly", "gaussian"], [3, 569], 12),
+    (["poly", "fourier", "hermite", "gaussian", "fourier_sparser"], [2, 1, 2, 5, 2], 3),
+]
+
+
+def _centres(types, degs, nv, seed=0):
+    ng = sum(d for t, d in zip(types, degs) if t == "gaussian")
+    return 2 * np.random.default_rng(seed).random((nv, ng)) - 1 if ng else None
+
+
+@pytest.mark.parametrize("types,degs,nv", CASES)
+def test_compiler_matches_oracle(hostlift, types, degs, nv):
+    cen = _centres(types, degs, nv)
+    b = A.Basis(types, degs, nv, cen)
+    prog = O.build_program(types, degs, nv, cen)
+    nf, N = C.c_int(), C.c_int()
+    assert hostlift.hostlift_dims(b.ref(), C.byref(nf), C.byref(N)) == 0
+    assert nf.value == prog.n_full == N.value
+    kinds = np.zeros(nf.value, np.int32); a_ = kinds.copy(); b_ = kinds.copy(); cs = np.zeros(nf.value)
+    ip = lambda x: x.ctypes.data_as(A.c_int_p)
+    assert hostlift.hostlift_ops(b.ref(), ip(kinds), ip(a_), ip(b_), A.dptr(cs)) == 0
+    got = [(int(k), int(x), int(y), float(c)) for k, x, y, c in zip(kinds, a_, b_, cs)]
+    assert got == [(k, a, bb, float(c)) for k, a, bb, c in prog.ops]
+    # values: the device evaluator's source compiled for the host
+    rows = 257
+    V = np.asfortranarray(2 * np.random.default_rng(1).random((rows, nv)) - 1)
+    out = np.zeros((rows, nf.value), order="F")
+    assert hostlift.hostlift_full(b.ref(), C.c_longlong(rows), A.dptr(V), A.dptr(out)) == 0
+    F = O.lift_full(prog, V)
+    exact = [j for j, op in enumerate(prog.ops) if op[0] in (O.OP_VAR, O.OP_CONST, O.OP_HERM)]
+    assert np.array_equal(out[:, exact], F[:, exact])
+    if all(t in ("poly", "hermite") for t in types):
+        assert np.array_equal(out, F)                      # pure products: bit-identical
+    assert np.abs(out - F).max() <= 4 * np.finfo(float).eps
+
+
+def test_block_tables_match_partitions(hostlift):
+    # same rows the reference enumerates (partitions.m:206-219)
+    prog = O.build_program(["poly"], [3], 4)
+    rows = np.concatenate([O.partitions_ones(k, 4) for k in (1, 2, 3)])
+    for j, r in enumerate(rows[4:]):
+        kind, a, b, _ = prog.ops[4 + j]
+        assert kind == O.OP_MUL
+
+
+def test_basis_validation():
+    with pytest.raises(ValueError):
+        A.Basis(["poly", "fourier"], [2], 3)                 # Ksysid.m:465-467
+    with pytest.raises(ValueError):
+        A.Basis(["gaussian"], [3], 3)                        # centres are an input (Ksysid.m:803)
+
+
+def test_library_exports_every_declared_symbol():
+    """libkoopfit.so loads and exports exactly what include/koopfit.h declares (no compute calls)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "koopfit.h")).read()
+    declared = set(re.findall(r"\b(kf_[a-z_0-9]+)\s*\(", hdr)) - {"kf_ctx"}
+    assert declared == set(A.EXPORTS), declared ^ set(A.EXPORTS)
+    if not os.path.exists(A.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = A.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.kf_version() == 100
+    # dictionary dimensions are host-only logic
+    b = A.Basis(["poly"], [2], 6)
+    nf, N, P = C.c_int(), C.c_int(), C.c_int()
+    assert lib.kf_basis_dims(b.ref(), A.KF_BILINEAR, 3, C.byref(nf), C.byref(N), C.byref(P)) == 0
+    assert (nf.value, N.value, P.value) == (28, 28, 112)
+    rows, cols = C.c_int(), C.c_int()
+    assert lib.kf_block_table(A.KF_POLY, 2, 3, C.byref(rows), C.byref(cols), None) == 0
+    tab = np.zeros(rows.value * cols.value, np.int32)
+    assert lib.kf_block_table(A.KF_POLY, 2, 3, C.byref(rows), C.byref(cols), tab.ctypes.data_as(A.c_int_p)) == 0
+    want = np.concatenate([O.partitions_ones(1, 3), O.partitions_ones(2, 3)])
+    assert np.array_equal(tab.reshape(rows.value, cols.value), want)
+
+
+def test_no_cuda_device_fails_loudly():
+    """Without a GPU kf_create must fail (no CPU fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(koopfit.KoopfitError):
+        koopfit.Fitter(device=0)
