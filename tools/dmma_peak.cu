@@ -7,7 +7,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 template <int NACC, int NFMA>
 __global__ void k(double* out, int iters, double x) {
-    double c[NACC][2];
+    double c[NACC > 0 ? NACC : 1][2];
     double f[NFMA > 0 ? NFMA : 1];
     for (int i = 0; i < NACC; ++i) c[i][0] = c[i][1] = 0.0;
     for (int i = 0; i < (NFMA > 0 ? NFMA : 1); ++i) f[i] = threadIdx.x * 1e-3 + i;
