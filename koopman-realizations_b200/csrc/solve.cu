@@ -397,3 +397,280 @@ int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, double* W, const double* C, dou
     ctx->launches += 4;
     return KF_OK;
 }
+
+// =====================================================================================
+// Part 2 — Householder QR with column pivoting on the materialised regressors: the same
+// algorithm LAPACK dgeqp3 / MATLAB mldivide run for `Px \ Py` (Ksysid.m:1069, 1216),
+// used when [Px | Py] fits in device memory.  Unblocked: per column one single-CTA kernel
+// (pivot search on exactly recomputed remaining column norms, column swap, dlarfg
+// reflector) and one grid-wide kernel that applies the reflector to every trailing
+// column of [A | B] and recomputes the remaining norms.  Rank is decided like MATLAB:
+// |R_jj| <= max(size(A)) * eps(|R_11|)  ->  basic solution on the first `rank` pivots.
+// =====================================================================================
+namespace {
+
+struct QrState {
+    double r11;     // |R_11|
+    double tol;     // max(M,P) * eps(|R_11|)
+    double minpiv;  // last accepted |R_jj|
+    double tau;     // current reflector
+    int rank;
+    int done;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sh[0] = v;
+    }
+    __syncthreads();
+    return sh[0];
+}
+
+__global__ void __launch_bounds__(256) kf_qr_colnorms_kernel(const double* __restrict__ A, long long ld, long long M,
+                                                             double* vn) {
+    __shared__ double sh[32];
+    const double* col = A + (long long)blockIdx.x * ld;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < M; i += blockDim.x) s = fma(col[i], col[i], s);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) vn[blockIdx.x] = s;
+}
+
+// one CTA: pivot, swap, reflector (dlarfg) for column j
+__global__ void __launch_bounds__(1024) kf_qr_pivot_kernel(double* A, long long ld, long long M, int P, int j, double* vn,
+                                                           int* perm, QrState* st) {
+    if (st->done) return;
+    __shared__ double sh[32];
+    __shared__ double sval[32];
+    __shared__ int sidx[32];
+    __shared__ int s_p;
+    const int tid = threadIdx.x;
+    double best = -1.0;
+    int bi = P;
+    for (int i = j + tid; i < P; i += blockDim.x) {
+        const double v = vn[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { sval[tid >> 5] = best; sidx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+        best = (tid < (blockDim.x >> 5)) ? sval[tid] : -1.0;
+        bi = (tid < (blockDim.x >> 5)) ? sidx[tid] : P;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (tid == 0) {
+            const double nrm = sqrt(best > 0.0 ? best : 0.0);
+            if (j == 0) {
+                st->r11 = nrm;
+                // eps(x) = distance to the next double above x
+                const double e = (nrm > 0.0) ? (__longlong_as_double(__double_as_longlong(nrm) + 1) - nrm) : 0.0;
+                st->tol = (double)(M > P ? M : P) * e;
+            }
+            if (!(nrm > st->tol)) {
+                st->rank = j;
+                st->done = 1;
+                s_p = -1;
+            } else {
+                s_p = bi;
+                st->rank = j + 1;
+                st->minpiv = nrm;
+            }
+        }
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (p < 0) return;
+    double* cj = A + (long long)j * ld;
+    if (p != j) {
+        double* cp = A + (long long)p * ld;
+        for (long long i = tid; i < M; i += blockDim.x) {
+            const double a = cj[i];
+            cj[i] = cp[i];
+            cp[i] = a;
+        }
+        if (tid == 0) {
+            const int a = perm[j];
+            perm[j] = perm[p];
+            perm[p] = a;
+            vn[p] = vn[j];
+        }
+        __syncthreads();
+    }
+    // dlarfg on x = A[j:, j]
+    double s = 0.0;
+    for (long long i = j + 1 + tid; i < M; i += blockDim.x) s = fma(cj[i], cj[i], s);
+    const double xnorm2 = block_sum(s, sh);
+    const double alpha = cj[j];
+    double tau = 0.0, beta = alpha, scale = 0.0;
+    if (xnorm2 > 0.0) {
+        beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+    }
+    __syncthreads();
+    for (long long i = j + 1 + tid; i < M; i += blockDim.x) cj[i] *= scale;
+    if (tid == 0) {
+        cj[j] = beta;
+        st->tau = tau;
+    }
+}
+
+// apply H_j = I - tau v v' (v = [1; A[j+1:, j]]) to column c = j+1+blockIdx.x of [A | B];
+// recompute the remaining norm of the column (rows > j) for columns of A.
+__global__ void __launch_bounds__(256) kf_qr_apply_kernel(double* A, long long ld, long long M, int P, int j, double* vn,
+                                                          const QrState* st) {
+    if (st->done) return;
+    __shared__ double sh[32];
+    const int c = j + 1 + blockIdx.x;
+    const double* v = A + (long long)j * ld;
+    double* col = A + (long long)c * ld;
+    const double tau = st->tau;
+    double s = 0.0;
+    for (long long i = j + 1 + threadIdx.x; i < M; i += blockDim.x) s = fma(v[i], col[i], s);
+    const double w = tau * (block_sum(s, sh) + col[j]);
+    double nn = 0.0;
+    for (long long i = j + 1 + threadIdx.x; i < M; i += blockDim.x) {
+        const double x = fma(-w, v[i], col[i]);
+        col[i] = x;
+        nn = fma(x, x, nn);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) col[j] -= w;
+    if (c < P) {
+        nn = block_sum(nn, sh);
+        if (threadIdx.x == 0) vn[c] = nn;
+    }
+}
+
+// W (Pp x Pp, zeroed) <- R11 mirrored: W(i,k) = W(k,i) = R(i,k), i <= k < rank
+__global__ void kf_qr_extract_r_kernel(const double* __restrict__ A, long long ld, const QrState* st, double* W, long long ldw) {
+    const int r = st->rank;
+    const long long n = (long long)r * r;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % r), k = (int)(e / r);
+        if (i <= k) {
+            const double v = A[(long long)k * ld + i];
+            W[(long long)k * ldw + i] = v;
+            W[(long long)i * ldw + k] = v;
+        }
+    }
+}
+
+// X(i, c) = (Q'B)(i, c) = AB(i, P + c) for i < rank, else 0
+__global__ void kf_qr_gather_rhs_kernel(const double* __restrict__ AB, long long ld, int P, int Pc, const QrState* st, double* X,
+                                        long long ldx, int Pp) {
+    const int r = st->rank;
+    const long long n = (long long)Pp * Pc;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % Pp), c = (int)(e / Pp);
+        X[(long long)c * ldx + i] = (i < r) ? AB[(long long)(P + c) * ld + i] : 0.0;
+    }
+}
+
+}  // namespace
+
+// backward substitution only:  U X = Z with U = L' stored mirrored in W
+static int trsm_backward(kf_ctx* ctx, const double* W, long long ld, int r, const int* d_rank, double* X, long long ldx, int ncols,
+                         cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        KF_CUDA(ctx, cudaFuncSetAttribute(kf_trsm_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8));
+        attr = true;
+    }
+    const int nblk = (r + 127) / 128;
+    const int grid = std::max(1, std::min((ncols + 7) / 8, ctx->sm_count));
+    const int kmax = (int)kf_roundup(r, KF_BK);
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int I = b * 128;
+        if (I + 128 < r) {
+            KfGemmGrid g{};
+            g.A = W + (long long)I * ld;
+            g.lda = ld;
+            g.B = X;
+            g.ldb = ldx;
+            g.out = X + I;
+            g.ldm = 1;
+            g.ldn = ldx;
+            g.m = 128;
+            g.n = ncols;
+            g.k0 = I + 128;
+            g.k1 = kmax;
+            g.alpha = -1.0;
+            g.accumulate = 1;
+            KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+        }
+        kf_trsm_diag_kernel<<<grid, 256, 128 * 128 * 8, st>>>(W, ld, I, d_rank, X, ldx, ncols, 0);
+        KF_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    return KF_OK;
+}
+
+int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long long ldab, double* X, long long ldx, int* d_perm,
+                   int* rank_out, double* min_piv, double* max_piv, cudaStream_t st) {
+    // X: Pp x Pc output (column-major, ld = ldx >= Pp), rows = original column index of A
+    const int Pp = (int)kf_roundup(P, KF_BM);
+    KF_CUDA(ctx, ctx->d_misc.ensure(1024 + (size_t)Pp * sizeof(int)));
+    KF_CUDA(ctx, ctx->d_K3.ensure((size_t)Pp * sizeof(double)));
+    QrState* d_state = reinterpret_cast<QrState*>(ctx->d_misc.as<char>() + 512);
+    double* vn = ctx->d_K3.as<double>();
+    QrState h0{};
+    KF_CUDA(ctx, cudaMemcpyAsync(d_state, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
+    {
+        std::vector<int> id(P);
+        for (int i = 0; i < P; ++i) id[i] = i;
+        KF_CUDA(ctx, cudaMemcpyAsync(d_perm, id.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    kf_qr_colnorms_kernel<<<P, 256, 0, st>>>(AB, ldab, M, vn);
+    const int steps = (int)std::min<long long>(M, P);
+    const int ncols = P + Pc;
+    for (int j = 0; j < steps; ++j) {
+        kf_qr_pivot_kernel<<<1, 1024, 0, st>>>(AB, ldab, M, P, j, vn, d_perm, d_state);
+        if (ncols - j - 1 > 0) kf_qr_apply_kernel<<<ncols - j - 1, 256, 0, st>>>(AB, ldab, M, P, j, vn, d_state);
+    }
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2LL * steps + 1;
+    QrState hs;
+    KF_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    KF_CUDA(ctx, cudaStreamSynchronize(st));
+    const int r = hs.rank;
+    *rank_out = r;
+    *max_piv = hs.r11;
+    *min_piv = hs.minpiv;
+    // R11 -> mirrored Pp x Pp factor in d_W; rhs -> d_tmp; back-substitute; scatter to X
+    const size_t mat = (size_t)Pp * Pp * sizeof(double);
+    const int Pcp = (int)kf_roundup(Pc, KF_BN);
+    KF_CUDA(ctx, ctx->d_W.ensure(mat));
+    KF_CUDA(ctx, ctx->d_tmp.ensure((size_t)Pp * Pcp * sizeof(double)));
+    double* W = ctx->d_W.as<double>();
+    double* Z = ctx->d_tmp.as<double>();
+    KF_CUDA(ctx, cudaMemsetAsync(W, 0, mat, st));
+    KF_CUDA(ctx, cudaMemsetAsync(Z, 0, (size_t)Pp * Pcp * sizeof(double), st));
+    KF_CUDA(ctx, cudaMemset2DAsync(X, (size_t)ldx * sizeof(double), 0, (size_t)Pp * sizeof(double), Pc, st));
+    if (r > 0) {
+        kf_qr_extract_r_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(AB, ldab, d_state, W, Pp);
+        kf_qr_gather_rhs_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(AB, ldab, P, Pc, d_state, Z, Pp, Pp);
+        KF_CUDA(ctx, cudaGetLastError());
+        KF_TRY(trsm_backward(ctx, W, Pp, r, &d_state->rank, Z, Pp, Pc, st));
+        kf_scatter_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(Z, Pp, d_perm, &d_state->rank, Pc, X, ldx);
+        KF_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 3;
+    }
+    return KF_OK;
+}
