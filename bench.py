@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — EDMD fit throughput (lift + Gram + solve) on BASELINE config 5.
+
+One step = one full bilinear fit of this rank's snapshot shard:
+    kf_accumulate_dev (fused lift -> L2-resident panel -> FP64 DMMA Gram/cross-covariance)
+    [N>1: one NCCL all-reduce of the packed partial Grams]
+    kf_solve_dev      (assemble G, C; pivoted-Cholesky basic LS solve; K to the host)
+
+Workload: synthetic snapshot pairs, n = nzeta = 12, m = 3, dictionary
+{'poly','gaussian'},[3,569] -> N = 1024, bilinear -> P = 4096.  Weak scaling: every rank owns
+`--snapshots-per-gpu` pairs (default 1.25e7 = 10^8 / 8, so N = 8 is exactly the named 10^8 job).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference      # CPU arm: the NumPy/SciPy oracle on host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "edmd_fit_snapshots_per_sec"
+UNIT = "snapshots/s"
+NZETA, M_IN, N_LIFT, P_REG = 12, 3, 1024, 4096
+OBS_TYPE, OBS_DEGREE = ["poly", "gaussian"], [3, 569]
+FLOPS_ALGO_PER_PAIR = P_REG * (P_REG + 1) + 2 * P_REG * P_REG      # P(P+1) + 2 P Pc
+
+
+def workload_constants():
+    """A0 (spectral radius 0.95), B0_i (||.||_2 = 0.1) from seed 1; gaussian centres from seed 2."""
+    rng = np.random.default_rng(1)
+    A0 = rng.standard_normal((NZETA, NZETA))
+    A0 *= 0.95 / np.max(np.abs(np.linalg.eigvals(A0)))
+    B0 = rng.standard_normal((M_IN, NZETA, NZETA))
+    B0 = np.stack([0.1 * b / np.linalg.norm(b, 2) for b in B0])
+    centres = 2 * np.random.default_rng(2).random((NZETA, OBS_DEGREE[1])) - 1
+    return A0, B0, centres
+
+
+def gen_numpy(M, seed):
+    """CPU generator of the same distribution (for the CPU arm)."""
+    A0, B0, _ = workload_constants()
+    rng = np.random.default_rng(seed)
+    zeta = 2 * rng.random((M, NZETA)) - 1
+    u = 2 * rng.random((M, M_IN)) - 1
+    beta = zeta @ A0.T + sum(u[:, i:i + 1] * (zeta @ B0[i].T) for i in range(M_IN)) + 0.01 * rng.standard_normal((M, NZETA))
+    return zeta, np.clip(beta, -1, 1), u
+
+
+def gen_torch(M, device, seed):
+    """Device generator (torch's Philox): feature-major tensors (nzeta, M) = column-major M x nzeta."""
+    import torch
+    A0, B0, _ = workload_constants()
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    tA = torch.tensor(A0, device=device)
+    tB = torch.tensor(B0, device=device)
+    alpha = torch.empty((NZETA, M), dtype=torch.float64, device=device)
+    beta = torch.empty((NZETA, M), dtype=torch.float64, device=device)
+    u = torch.empty((M_IN, M), dtype=torch.float64, device=device)
+    step = 1 << 21
+    for lo in range(0, M, step):
+        hi = min(M, lo + step)
+        z = torch.rand((NZETA, hi - lo), dtype=torch.float64, device=device, generator=g) * 2 - 1
+        uu = torch.rand((M_IN, hi - lo), dtype=torch.float64, device=device, generator=g) * 2 - 1
+        b = tA @ z
+        for i in range(M_IN):
+            b += uu[i:i + 1] * (tB[i] @ z)
+        b += 0.01 * torch.randn((NZETA, hi - lo), dtype=torch.float64, device=device, generator=g)
+        alpha[:, lo:hi], beta[:, lo:hi], u[:, lo:hi] = z, b.clamp_(-1, 1), uu
+    return alpha, beta, u
+
+
+class _CAI:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def fp64_peak_tflops():
+    """Roofline denominator: MEASURED cuBLAS DGEMM FP64 on this pool's B200
+    (profiles/r01_fp64_dgemm_peak.json, tools/fp64_peak.py); MEASURED_PEAKS.json has no FP64 entry."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_dgemm_peak.json")))
+        return float(d["dgemm_tflops_sustained"]), "measured cuBLAS DGEMM 8192^3 fp64 on this pool (profiles/r01_fp64_dgemm_peak.json)"
+    except Exception:
+        return 37.0, "fallback: nominal B200 FP64 tensor 37 TFLOP/s"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [ln.strip().split(", ") for ln in open(self.f.name) if ln.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        busy = [s for s in sm if s > 0.5 * max(mx or [1])] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_fit_rates(sample, threads):
+    """Time the oracle (kind 'port': NumPy/SciPy restatement, OpenBLAS) on a bounded sample of the workload.
+    Returns lift+Gram rate (snapshots/s), solve seconds, and what was timed."""
+    import oracle as O
+    _, _, centres = workload_constants()
+    prog = O.build_program(OBS_TYPE, OBS_DEGREE, NZETA, centres)
+    alpha, beta, u = gen_numpy(sample, seed=1234)
+    t0 = time.perf_counter()
+    Px, Py = O.build_regressors("bilinear", prog, alpha, beta, u)
+    G, C = O.gram(Px, Py)
+    t_lg = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    K = O.mldivide(Px, Py)          # dgeqp3 — the routine behind MATLAB's `\` (Ksysid.m:1069)
+    t_solve = time.perf_counter() - t0
+    assert K.shape == (P_REG, P_REG) and np.all(np.isfinite(G)) and np.all(np.isfinite(C))
+    return sample / t_lg, t_solve, t_lg
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path.  MATLAB/Octave are absent
+    (BASELINE.md §4), so this is the oracle port on the host cores, vectorised (which flatters the CPU
+    against the reference's interpreted per-snapshot loop, Ksysid.m:1030-1065)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rate_lg, t_solve, t_lg = cpu_fit_rates(sample, threads)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            # whole-job CPU estimate for the same per-rank shard: per-snapshot work scales with M, the solve is paid once
+            Mjob = args.snapshots_per_gpu * args.gpus
+            vals.append(Mjob / (Mjob / rate_lg + t_solve))
+            times.append(dt)
+    v = float(np.median(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, extra={"cpu_sample_snapshots": sample}),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} snapshots of the same workload: NumPy lift + OpenBLAS Gram timed per snapshot, "
+                                       f"dgeqp3 solve (P=4096) timed once; extrapolated linearly in M to the {args.snapshots_per_gpu * args.gpus}-snapshot job"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, extra=None):
+    d = {"workload": "BASELINE config 5: synthetic snapshots, n=12, m=3, dictionary {poly,gaussian},[3,569] -> N=1024, "
+                     "bilinear -> P=4096 lifted regressor, lasso=Inf (least squares), snapshot-sharded",
+         "snapshots_per_gpu": args.snapshots_per_gpu, "total_snapshots": args.snapshots_per_gpu * args.gpus,
+         "P": P_REG, "N": N_LIFT, "nzeta": NZETA, "m": M_IN, "model_type": "bilinear",
+         "parallelism": f"snapshot-sharded x{args.gpus}, one NCCL all-reduce of the packed partial Grams",
+         "l2_policy": "inputs (>= 216 B/snapshot x shard) exceed L2 for shards >= 1M snapshots; every step re-reads them from HBM"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--snapshots-per-gpu", type=int, default=12_500_000)
+    ap.add_argument("--cpu-sample", type=int, default=8192)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], help="kf_set_option name=value")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import koopfit
+
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    M = args.snapshots_per_gpu
+    _, _, centres = workload_constants()
+    basis = koopfit.Basis(OBS_TYPE, OBS_DEGREE, NZETA, centres)
+    fit = koopfit.Fitter(device=local_rank)
+    fit.set_option("profile", 1)
+    for kv in args.option:
+        k, v = kv.split("=")
+        fit.set_option(k, float(v))
+    alpha, beta, u = gen_torch(M, dev, seed=1000 + rank)
+    torch.cuda.synchronize()
+    kstream = torch.cuda.ExternalStream(fit.stream, device=dev)
+
+    def step_resident():
+        fit.accumulate_dev(basis, "bilinear", M, NZETA, M_IN, alpha.data_ptr(), beta.data_ptr(), u.data_ptr(), reset=True)
+        if world > 1:
+            ptr, n = fit.accum_buffer()
+            fit.sync()
+            buf = torch.as_tensor(_CAI(ptr, n), device=dev)
+            dist.all_reduce(buf)
+            torch.cuda.synchronize()
+        return fit.solve_dev(P_REG, ls_method="gram")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        fit.sync()
+
+    # ---------------- device-resident timing (value) ----------------
+    for _ in range(args.warmup):
+        res = step_resident()
+    barrier()
+    fit.counters(reset=True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gram_ms, liftgram_ms, solve_ms = [], [], []
+    e0.record(kstream)
+    for _ in range(args.steps):
+        res = step_resident()
+        t = fit.last_times()
+        gram_ms.append(t["gram_kernel_ms"]); liftgram_ms.append(t["lift_gram_ms"]); solve_ms.append(t["solve_ms"])
+    e1.record(kstream)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    flops_issued, launches = fit.counters()
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    value = M * world / (ms_step * 1e-3)
+    assert res["rank"] == P_REG, f"unexpected rank {res['rank']}"
+    assert np.all(np.isfinite(res["K"]))
+
+    # ---------------- end-to-end through the public host API (kf_fit, host buffers) ----------------
+    h_alpha = torch.empty((NZETA, M), dtype=torch.float64).pin_memory()
+    h_beta = torch.empty((NZETA, M), dtype=torch.float64).pin_memory()
+    h_u = torch.empty((M_IN, M), dtype=torch.float64).pin_memory()
+    h_alpha.copy_(alpha); h_beta.copy_(beta); h_u.copy_(u)
+    torch.cuda.synchronize()
+    na, nb, nu = h_alpha.numpy().T, h_beta.numpy().T, h_u.numpy().T     # (M x nzeta) column-major views
+    h2d = (2 * NZETA + M_IN) * 8 * M
+    d2h = P_REG * P_REG * 8
+    e2e_val = None
+    if world == 1:
+        def step_e2e():
+            return fit.fit(basis, "bilinear", na, nb, nu, ls_method="gram")
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r2 = step_e2e()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
+        e2e_val = M / (e2e_ms * 1e-3)
+    else:
+        # multi-rank end to end: pinned host shard -> device copies inside the timed region, then the staged path
+        def step_e2e():
+            alpha.copy_(h_alpha, non_blocking=True); beta.copy_(h_beta, non_blocking=True); u.copy_(h_u, non_blocking=True)
+            torch.cuda.synchronize()
+            return step_resident()
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r2 = step_e2e()
+        barrier()
+        tt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.e2e_steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_val = M * world / (float(tt.item()) * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = fp64_peak_tflops()
+        tiles_flops = flops_issued / args.steps                      # DMMA flops issued per step (incl. solver GEMMs)
+        gram_flops = 1000 * 2.0 * 128 * 128 * M                       # 10 Kronecker blocks x (36 G + 64 C) tiles
+        gk = float(np.mean(gram_ms)) if gram_ms and np.mean(gram_ms) > 0 else float(np.mean(liftgram_ms))
+        achieved = gram_flops / (gk * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(args),
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "kf_fit (host buffers)" if world == 1 else "pinned host shard -> kf_accumulate_dev/all_reduce/kf_solve_dev"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "kf_gram_tile_kernel<true> (FP64 DMMA.8x8x4 Gram/cross-covariance)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "flops_basis": "DMMA flops actually issued per step by the Gram kernel (Kronecker blocks: 1000 tiles x 2x128x128 per snapshot = 3.28e7/pair)",
+                         "achieved_algorithmic": FLOPS_ALGO_PER_PAIR * M / (gk * 1e-3) / 1e12,
+                         "algorithmic_flops_per_pair": FLOPS_ALGO_PER_PAIR, "issued_flops_per_pair": 1000 * 2.0 * 128 * 128,
+                         "gram_kernel_ms_per_step": gk, "lift_gram_ms_per_step": float(np.mean(liftgram_ms)),
+                         "solve_ms_per_step": float(np.mean(solve_ms)), "dmma_flops_issued_per_step_all_kernels": tiles_flops},
+        }
+        if not args.no_cpu_baseline:
+            rate_lg, t_solve, t_lg = cpu_fit_rates(args.cpu_sample, os.cpu_count())
+            Mjob = M * world
+            line["cpu_baseline"] = {"value": Mjob / (Mjob / rate_lg + t_solve), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{args.cpu_sample} snapshots of the same workload (oracle: NumPy lift + OpenBLAS Gram {t_lg:.1f} s, "
+                                              f"dgeqp3 solve {t_solve:.1f} s), per-snapshot part extrapolated linearly to {Mjob} snapshots"}
+        print(json.dumps(line), flush=True)
+    fit.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

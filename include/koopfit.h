@@ -133,6 +133,12 @@ int kf_lift(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V,
  * LS or all nt budgets.  HOST pointers in `prob`; copies are inside the call. */
 int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out);
 
+/* Generic MATLAB `A \\ B` for a tall A (M x P) and B (M x Pc), HOST column-major buffers:
+ * Householder QR with column pivoting on the GPU, rank by max(size(A))*eps(|R11|), basic
+ * solution X (P x Pc).  Replaces `Mtranspose = L \\ R` in get_model (Ksysid.m:1216).
+ * perm (P ints) and rank may be NULL. */
+int kf_mldivide(kf_ctx* ctx, long long M, int P, int Pc, const double* A, const double* B, double* X, int* perm, int* rank);
+
 /* ---- staged, device-resident API (one rank of a snapshot-sharded fit) ---
  * kf_accumulate_dev: lift + Gram of this rank's shard; DEVICE pointers in `prob`;
  *   reset!=0 zeroes the accumulator first.  Asynchronous on the context stream.

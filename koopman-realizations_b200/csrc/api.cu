@@ -517,10 +517,84 @@ int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_
         if (out->Px) KF_CUDA(ctx, cudaMemcpyAsync(out->Px, ctx->d_qr.p, (size_t)M * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (out->Py) KF_CUDA(ctx, cudaMemcpyAsync(out->Py, ctx->d_qr.as<double>() + (size_t)M * P, (size_t)M * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    int rc = solve_from_accum(ctx, solve, out);
+    int method = solve->ls_method;
+    if (solve->least_squares && method == KF_LS_AUTO) {
+        const double need = (double)M * 2.0 * ctx->lay.P * sizeof(double);
+        method = (need <= ctx->opt_qr_max_gb * 1073741824.0) ? KF_LS_QR : KF_LS_GRAM;
+    }
+    int rc;
+    if (solve->least_squares && method == KF_LS_QR) {
+        // Householder QRCP on the materialised regressors: the reference's own algorithm (Ksysid.m:1069)
+        rc = solve_from_accum(ctx, nullptr, out);      // G, C outputs only
+        if (rc) return rc;
+        const int P = ctx->lay.P, Pp = ctx->lay.Pp;
+        cudaStream_t st = ctx->stream;
+        KF_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+        KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
+        if (!(out->Px || out->Py)) {   // not materialised above
+            KfLiftArgs a{};
+            a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
+            a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->lay.N;
+            a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
+            a.alpha = d_alpha; a.beta = d_beta; a.u = d_u; a.M = M;
+            if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * M * sizeof(double)));
+            a.full = ctx->d_full.as<double>();
+            KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, M, st));
+        }
+        KF_CUDA(ctx, ctx->d_K.ensure((size_t)Pp * Pp * sizeof(double)));
+        KF_CUDA(ctx, ctx->d_misc.ensure(1024 + (size_t)Pp * sizeof(int)));
+        int* d_perm = reinterpret_cast<int*>(ctx->d_misc.as<char>() + 1024);
+        int rank = 0;
+        double minp = 0, maxp = 0;
+        KF_TRY(kf_solve_qr_ls(ctx, M, P, P, ctx->d_qr.as<double>(), M, ctx->d_K.as<double>(), Pp, d_perm, &rank, &minp, &maxp, st));
+        out->info.rank = rank;
+        out->info.ls_method_used = KF_LS_QR;
+        out->info.min_pivot = minp;
+        out->info.max_pivot = maxp;
+        out->info.passes = 2;
+        KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K));
+        if (out->perm) KF_CUDA(ctx, cudaMemcpyAsync(out->perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+        float sms = 0.f;
+        KF_CUDA(ctx, cudaEventElapsedTime(&sms, ctx->ev[4], ctx->ev[5]));
+        ctx->last_solve_ms = sms;
+        out->info.t_solve_ms = sms;
+    } else {
+        kf_solve sv2 = *solve;
+        if (sv2.least_squares) sv2.ls_method = KF_LS_GRAM;
+        rc = solve_from_accum(ctx, &sv2, out);
+    }
     ctx->lay.valid = false;
     out->info.t_total_ms = now_ms() - t0;
     return rc;
+}
+
+int kf_mldivide(kf_ctx* ctx, long long M, int P, int Pc, const double* A, const double* B, double* X, int* perm, int* rank) {
+    if (!ctx) return KF_EINVAL;
+    if (M <= 0 || P <= 0 || Pc <= 0 || !A || !B || !X) {
+        ctx->err = "kf_mldivide: M, P, Pc > 0 and A, B, X required";
+        return KF_EINVAL;
+    }
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int Pp = (int)kf_roundup(P, KF_BM);
+    KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * (P + Pc) * sizeof(double)));
+    KF_CUDA(ctx, ctx->d_K2.ensure((size_t)Pp * Pc * sizeof(double)));
+    KF_CUDA(ctx, ctx->d_misc.ensure(1024 + (size_t)Pp * sizeof(int)));
+    double* AB = ctx->d_qr.as<double>();
+    KF_CUDA(ctx, cudaMemcpyAsync(AB, A, (size_t)M * P * sizeof(double), cudaMemcpyHostToDevice, st));
+    KF_CUDA(ctx, cudaMemcpyAsync(AB + (size_t)M * P, B, (size_t)M * Pc * sizeof(double), cudaMemcpyHostToDevice, st));
+    int* d_perm = reinterpret_cast<int*>(ctx->d_misc.as<char>() + 1024);
+    int r = 0;
+    double minp = 0, maxp = 0;
+    KF_TRY(kf_solve_qr_ls(ctx, M, P, Pc, AB, M, ctx->d_K2.as<double>(), Pp, d_perm, &r, &minp, &maxp, st));
+    KF_CUDA(ctx, cudaMemcpy2DAsync(X, (size_t)P * sizeof(double), ctx->d_K2.p, (size_t)Pp * sizeof(double), (size_t)P * sizeof(double), Pc,
+                                   cudaMemcpyDeviceToHost, st));
+    if (perm) KF_CUDA(ctx, cudaMemcpyAsync(perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
+    KF_CUDA(ctx, cudaStreamSynchronize(st));
+    if (rank) *rank = r;
+    return KF_OK;
 }
 
 int kf_counters(kf_ctx* ctx, double* dmma_flops, long long* launches, int reset) {
@@ -554,6 +628,7 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "overlap") ctx->opt_overlap = (int)value;
     else if (n == "panel_mb") ctx->opt_panel_mb = value;
     else if (n == "profile") ctx->opt_profile = (int)value;
+    else if (n == "qr_max_gb") ctx->opt_qr_max_gb = value;
     else {
         ctx->err = "kf_set_option: unknown option " + n;
         return KF_EINVAL;

@@ -127,6 +127,18 @@ class Fitter:
                    objective=obj, l1norm=l1, qp_iters=iters)
         return out
 
+    def mldivide(self, Amat, Bmat):
+        """MATLAB `A \\ B` (QRCP basic solution) on the GPU; returns X, rank, perm."""
+        Amat, Bmat = A.fcol(Amat), A.fcol(Bmat)
+        M, P = Amat.shape
+        Pc = Bmat.shape[1]
+        X = np.zeros((P, Pc), order="F")
+        perm = np.zeros(P, dtype=np.int32)
+        rank = C.c_int()
+        self._check(self.lib.kf_mldivide(self.ctx, M, P, Pc, A.dptr(Amat), A.dptr(Bmat), A.dptr(X),
+                                         perm.ctypes.data_as(A.c_int_p), C.byref(rank)), "kf_mldivide")
+        return X, rank.value, perm
+
     # ------------------------------------------------------------------ staged / device-resident API
     def accumulate_dev(self, basis, model_type, M, nzeta, m, alpha_ptr, beta_ptr, u_ptr, reset=True):
         """Partial Gram of a device-resident shard (pointers from torch tensors' data_ptr());

@@ -141,3 +141,52 @@ def test_errors_are_reported(fitter):
     basis = koopfit.Basis(["poly"], [2], 4)                  # wrong nv for a linear model with nzeta=3
     with pytest.raises(koopfit.KoopfitError):
         fitter.fit(basis, "linear", alpha, beta, u)
+
+
+def test_mldivide_qr_rank_deficient(fitter):
+    """kf_mldivide = MATLAB A\\B: QRCP, rank by max(size)*eps(|R11|), basic solution (Ksysid.m:1069,1216)."""
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((3000, 40))
+    A[:, 7] = A[:, 3] - 2 * A[:, 11]            # exact dependencies -> rank 37
+    A[:, 20] = A[:, 0]
+    A[:, 33] = 0.5 * A[:, 1] + A[:, 2]
+    B = rng.standard_normal((3000, 9))
+    X, rank, perm = fitter.mldivide(A, B)
+    Xo, info = O.mldivide(A, B, return_info=True)
+    assert rank == info["rank"] == 37
+    assert set(perm[:rank].tolist()) == set(info["perm"][:rank].tolist())
+    assert np.all(X[perm[rank:]] == 0)
+    assert relF(X, Xo) < 1e-11
+    # full rank, ragged sizes
+    A = rng.standard_normal((1001, 131)); B = rng.standard_normal((1001, 3))
+    X, rank, _ = fitter.mldivide(A, B)
+    assert rank == 131 and relF(X, O.mldivide(A, B)) < 1e-11
+
+
+def test_config1_qr_route(fitter, arm_data):
+    k = O.KsysidOracle(arm_data, model_type="bilinear", obs_type=["poly"], obs_degree=[2]).train_models()
+    basis = koopfit.Basis(["poly"], [2], 6)
+    res = fitter.fit(basis, "bilinear", k.pairs["alpha"], k.pairs["beta"], k.pairs["u"], ls_method="qr")
+    assert res["info"]["ls_method_used"] == 2 and res["rank"] == 100
+    assert relF(res["K"], k.koopData[0]["K"]) < 1e-10
+
+
+@pytest.mark.parametrize("model,P,rank", [("linear", 819, 723), ("nonlinear", 1330, 1216)])
+def test_config2_poly3_delay1(fitter, arm_data, model, P, rank):
+    """BASELINE config 2: poly 3, delays=1 on the arm data (cond ~2e7, exactly rank-deficient): the QRCP
+    route must reproduce mldivide's basic solution; A, B (or F) to 1e-9."""
+    k = O.KsysidOracle(arm_data, model_type=model, obs_type=["poly"], obs_degree=[3], delays=1)
+    koop = O.get_koopman(model, k.prog, k.pairs, lasso=1e6, N=k.N, n=k.n, nd=1)
+    assert koop["Px"].shape[1] == P and koop["info"]["rank"] == rank
+    nv = 15 + (3 if model == "nonlinear" else 0)
+    basis = koopfit.Basis(["poly"], [3], nv)
+    res = fitter.fit(basis, model, k.pairs["alpha"], k.pairs["beta"], k.pairs["u"])      # AUTO -> QR
+    assert res["info"]["ls_method_used"] == 2
+    assert res["rank"] == rank
+    assert set(res["perm"][:rank].tolist()) == set(koop["info"]["perm"][:rank].tolist())
+    K, Ko = res["K"], koop["K"]
+    N = k.N
+    if model == "linear":
+        assert relF(K.T[:N, :N], Ko.T[:N, :N]) < 1e-9 and relF(K.T[:N, N:], Ko.T[:N, N:]) < 1e-9
+    else:
+        assert relF(K[:, :15], Ko[:, :15]) < 1e-9
