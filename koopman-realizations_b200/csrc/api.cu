@@ -37,6 +37,10 @@ int prepare_program(kf_ctx* ctx, const kf_basis* basis) {
         KF_CUDA(ctx, ctx->d_pcs.ensure(sizeof(double) * p.pcs.size()));
         KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_pcs.p, p.pcs.data(), sizeof(double) * p.pcs.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
+    std::vector<int> order;
+    kf_program_levels(p, order, ctx->level_start);
+    KF_CUDA(ctx, ctx->d_order.ensure(sizeof(int) * order.size()));
+    KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
     KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors may be rebuilt by the next call
     return KF_OK;
 }
@@ -202,6 +206,7 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
         a.ops = ctx->d_ops.as<KfOp>();
         a.centres = ctx->d_centres.as<double>();
         a.pcs = ctx->d_pcs.as<double>();
+        a.order = ctx->d_order.as<int>(); a.nsides = 2; a.extras = 1;
         a.nv = p.nv; a.n_full = p.n_full(); a.n_pcs = p.n_pcs; a.N = L.N;
         a.nzeta = L.nzeta; a.m = L.m; a.model = L.model;
         a.alpha = pr->alpha; a.beta = pr->beta; a.u = pr->u;
@@ -367,7 +372,7 @@ void kf_destroy(kf_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    KfBuf* bufs[] = {&ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_full,
+    KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_full,
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3};
     for (KfBuf* b : bufs) b->release();
@@ -508,6 +513,7 @@ int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_
         KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
         KfLiftArgs a{};
         a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
+        a.order = ctx->d_order.as<int>();
         a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->lay.N;
         a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
         a.alpha = d_alpha; a.beta = d_beta; a.u = d_u; a.M = M;
@@ -534,6 +540,7 @@ int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_
         if (!(out->Px || out->Py)) {   // not materialised above
             KfLiftArgs a{};
             a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
+            a.order = ctx->d_order.as<int>();
             a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->lay.N;
             a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
             a.alpha = d_alpha; a.beta = d_beta; a.u = d_u; a.M = M;

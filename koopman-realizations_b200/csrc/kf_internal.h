@@ -94,6 +94,8 @@ struct kf_ctx {
     KfProgram prog;
     KfLayout lay;
 
+    std::vector<int> level_start;   // offsets into the level-sorted feature order
+    KfBuf d_order;
     KfBuf d_ops, d_centres, d_pcs, d_panel[2], d_full, d_tasks[2], d_accum, d_tilemeta;
     KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3;
     cudaEvent_t ev_panel_free[2] = {}, ev_panel_ready[2] = {};
@@ -146,6 +148,8 @@ int kf_launch_gemm_grid(kf_ctx* ctx, const KfGemmGrid& g, cudaStream_t st);
 // lift.cu
 struct KfLiftArgs {
     const KfOp* ops; const double* centres; const double* pcs;
+    const int* order;              // features sorted by dependency level
+    int nsides, extras;            // 1|2 sides; extras: also write u rows / bilinear weight rows
     int nv, n_full, n_pcs, N;
     int nzeta, m, model;
     const double* alpha; const double* beta; const double* u;   // device, column-major, ld = M
@@ -155,6 +159,7 @@ struct KfLiftArgs {
     double* full;                  // scratch for dim_red: 2 * n_full rows x ld
     int x_off, y_off, w_off, nW;
 };
+void kf_program_levels(const KfProgram& p, std::vector<int>& order, std::vector<int>& level_start);
 int kf_launch_lift(kf_ctx* ctx, const KfLiftArgs& a, cudaStream_t st);
 // materialised lift of arbitrary points: V (rows x nv, ld=rows) -> Psi (rows x N, ld = ldo)
 int kf_launch_lift_points(kf_ctx* ctx, const KfOp* ops, const double* centres, const double* pcs, int nv, int n_full,

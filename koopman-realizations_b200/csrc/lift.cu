@@ -2,98 +2,89 @@
 // (replaces the interpreted per-snapshot loop Ksysid.m:1030-1065 and the matlabFunction
 // handles built at Ksysid.m:515,533,660,727,763,813,859).
 //
-// Layout: snapshots arrive column-major (one variable = one contiguous column), so a
-// warp of consecutive snapshots reads and writes fully coalesced.  One thread owns one
-// snapshot of one side (x = alpha, y = beta) and walks the feature program in index
-// order; a MUL op reads two earlier features of the same snapshot back from the panel
-// (same-thread RAW through L1/L2 — the panel never has to leave L2).  The panel is
-// feature-major: row = observable, column = snapshot of the chunk, which is exactly the
-// k-contiguous operand layout of the DMMA contraction in gemm.cu.
+// Layout: snapshots arrive column-major (one variable = one contiguous column), so a warp
+// of consecutive snapshots reads and writes fully coalesced.  The panel is feature-major:
+// row = observable, column = snapshot of the chunk — exactly the k-contiguous operand
+// layout of the DMMA contraction in gemm.cu — and is sized to stay L2-resident, so Psi is
+// produced and consumed on chip and never materialised in HBM.
+//
+// Parallelism: the feature program is evaluated level by level (level = dependency depth:
+// variables and primitives first, then products of earlier features).  One launch per
+// level; a thread owns one snapshot of one side (x = alpha / y = beta) and a slice of
+// LIFT_FS features of that level, so a chunk of 1.5k snapshots x 1k features exposes
+// ~4e5 threads instead of 3e3.  A product reads its two factors back from the panel
+// (written by an earlier level, L2 hits).
 #include "kf_internal.h"
 #include "lift_eval.h"
 
 namespace {
 
 constexpr int LIFT_THREADS = 128;
+constexpr int LIFT_FS = 8;   // features per thread
 
-template <class VarFn>
-__device__ __forceinline__ void lift_one(const KfOp* __restrict__ ops, const double* __restrict__ centres, int nv,
-                                         int n_full, VarFn var, double* F, long long ld) {
-    for (int i = 0; i < nv; ++i) F[(long long)i * ld] = var(i);
-    for (int j = nv; j < n_full; ++j) {
-        const KfOp op = ops[j];
-        F[(long long)j * ld] = kf_eval_op(op, nv, centres, [&](int k) { return F[(long long)k * ld]; });
-    }
-}
-
-// econ lift [v; pcs' psi_full; 1] (Ksysid.m:1614-1618) from the full features in `full`
-__device__ __forceinline__ void econ_rows(const double* __restrict__ pcs, int nv, int n_full, int n_pcs,
-                                          const double* full, long long ldf, double* out, long long ldo) {
-    for (int i = 0; i < nv; ++i) out[(long long)i * ldo] = full[(long long)i * ldf];
-    for (int c = 0; c < n_pcs; ++c) {
-        const double* pc = pcs + (size_t)c * n_full;
-        double acc = 0.0;
-        for (int j = 0; j < n_full; ++j) acc = fma(pc[j], full[(long long)j * ldf], acc);
-        out[(long long)(nv + c) * ldo] = acc;
-    }
-    out[(long long)(nv + n_pcs) * ldo] = 1.0;
-}
-
-// weight row index of the pair (a,b), a<=b, in 0..m (u_0 = 1)
 __host__ __device__ inline int pair_index(int a, int b, int m) { return a * (m + 1) - a * (a - 1) / 2 + (b - a); }
 
-__global__ void __launch_bounds__(LIFT_THREADS) kf_lift_panel_kernel(const KfLiftArgs a) {
+__global__ void __launch_bounds__(LIFT_THREADS) kf_lift_level_kernel(const KfLiftArgs a, int first, int count, int extras) {
     const int s = blockIdx.x * LIFT_THREADS + threadIdx.x;
     if (s >= a.Mc) return;
-    const int side = blockIdx.y;   // 0: x = alpha, 1: y = beta
+    const int side = blockIdx.z;   // 0: x = alpha, 1: y = beta
     const long long gs = a.start + s;
-    double* sec = a.panel + (long long)(side ? a.y_off : a.x_off) * a.ld + s;
-    const int sec_rows = a.N + ((side == 0 && a.model == KF_LINEAR) ? a.m : 0);
-    if (gs >= a.M) {   // tail of the last chunk contributes zeros
-        for (int j = 0; j < sec_rows; ++j) sec[(long long)j * a.ld] = 0.0;
-        if (side == 0)
-            for (int q = 0; q < a.nW; ++q) a.panel[(long long)(a.w_off + q) * a.ld + s] = 0.0;
-        return;
-    }
+    // destination of the full dictionary: the panel section, or the scratch when dim_red follows
+    double* dst = (a.n_pcs == 0) ? a.panel + (long long)(side ? a.y_off : a.x_off) * a.ld + s
+                                 : a.full + (long long)side * a.n_full * a.ld + s;
+    const int f0 = blockIdx.y * LIFT_FS;
+    const int f1 = min(count, f0 + LIFT_FS);
+    const bool valid = gs < a.M;
     const double* src = side ? a.beta : a.alpha;
-    auto var = [&](int i) -> double {
-        return i < a.nzeta ? src[(long long)i * a.M + gs] : a.u[(long long)(i - a.nzeta) * a.M + gs];
+    auto feat = [&](int k) -> double {
+        if (k < a.nv) return k < a.nzeta ? src[(long long)k * a.M + gs] : a.u[(long long)(k - a.nzeta) * a.M + gs];
+        return dst[(long long)k * a.ld];
     };
-    if (a.n_pcs == 0) {
-        lift_one(a.ops, a.centres, a.nv, a.n_full, var, sec, a.ld);
-    } else {
-        double* full = a.full + (long long)side * a.n_full * a.ld + s;
-        lift_one(a.ops, a.centres, a.nv, a.n_full, var, full, a.ld);
-        econ_rows(a.pcs, a.nv, a.n_full, a.n_pcs, full, a.ld, sec, a.ld);
+    for (int f = f0; f < f1; ++f) {
+        const int j = a.order[first + f];
+        double v = 0.0;   // the tail of the last chunk contributes zeros
+        if (valid) {
+            const KfOp op = a.ops[j];
+            v = (op.kind == KF_OP_VAR) ? feat(op.a) : kf_eval_op(op, a.nv, a.centres, feat);
+        }
+        dst[(long long)j * a.ld] = v;
     }
-    if (side == 0) {
+    if (extras && blockIdx.y == 0 && side == 0) {
+        double* sec = a.panel + (long long)a.x_off * a.ld + s;
         if (a.model == KF_LINEAR) {   // Px = [psi(x), u] (Ksysid.m:1062)
-            for (int i = 0; i < a.m; ++i) sec[(long long)(a.N + i) * a.ld] = a.u[(long long)i * a.M + gs];
-        } else if (a.model == KF_BILINEAR) {   // weights u_a*u_b of the Kronecker blocks
+            for (int i = 0; i < a.m; ++i) sec[(long long)(a.N + i) * a.ld] = valid ? a.u[(long long)i * a.M + gs] : 0.0;
+        } else if (a.model == KF_BILINEAR && a.nW > 0) {   // weights u_a*u_b of the Kronecker blocks
             double* w = a.panel + (long long)a.w_off * a.ld + s;
             for (int p = 0; p <= a.m; ++p) {
-                const double up = p ? a.u[(long long)(p - 1) * a.M + gs] : 1.0;
+                const double up = (p && valid) ? a.u[(long long)(p - 1) * a.M + gs] : 1.0;
                 for (int q = p; q <= a.m; ++q) {
-                    const double uq = q ? a.u[(long long)(q - 1) * a.M + gs] : 1.0;
-                    w[(long long)pair_index(p, q, a.m) * a.ld] = p ? KF_MUL(up, uq) : uq;
+                    const double uq = (q && valid) ? a.u[(long long)(q - 1) * a.M + gs] : 1.0;
+                    w[(long long)pair_index(p, q, a.m) * a.ld] = valid ? (p ? KF_MUL(up, uq) : uq) : 0.0;
                 }
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(LIFT_THREADS)
-kf_lift_points_kernel(const KfOp* __restrict__ ops, const double* __restrict__ centres, const double* __restrict__ pcs,
-                      int nv, int n_full, int n_pcs, const double* __restrict__ V, long long rows, double* full,
-                      double* out, long long ldo) {
-    const long long s = (long long)blockIdx.x * LIFT_THREADS + threadIdx.x;
-    if (s >= rows) return;
-    auto var = [&](int i) -> double { return V[(long long)i * rows + s]; };
-    if (n_pcs == 0) {
-        lift_one(ops, centres, nv, n_full, var, out + s, ldo);
-    } else {
-        lift_one(ops, centres, nv, n_full, var, full + s, rows);
-        econ_rows(pcs, nv, n_full, n_pcs, full + s, rows, out + s, ldo);
+// econ lift [v; pcs' psi_full; 1] (Ksysid.m:1614-1618) from the full features in the scratch:
+// thread = (snapshot, principal component slice)
+__global__ void __launch_bounds__(LIFT_THREADS) kf_lift_econ_kernel(const KfLiftArgs a) {
+    const int s = blockIdx.x * LIFT_THREADS + threadIdx.x;
+    if (s >= a.Mc) return;
+    const int side = blockIdx.z;
+    const bool valid = a.start + s < a.M;
+    const double* full = a.full + (long long)side * a.n_full * a.ld + s;
+    double* sec = a.panel + (long long)(side ? a.y_off : a.x_off) * a.ld + s;
+    const int c0 = blockIdx.y * LIFT_FS, c1 = min(a.n_pcs, c0 + LIFT_FS);
+    for (int c = c0; c < c1; ++c) {
+        const double* pc = a.pcs + (size_t)c * a.n_full;
+        double acc = 0.0;
+        for (int j = 0; j < a.n_full; ++j) acc = fma(pc[j], full[(long long)j * a.ld], acc);
+        sec[(long long)(a.nv + c) * a.ld] = valid ? acc : 0.0;
+    }
+    if (blockIdx.y == 0) {
+        for (int i = 0; i < a.nv; ++i) sec[(long long)i * a.ld] = full[(long long)i * a.ld];
+        sec[(long long)(a.nv + a.n_pcs) * a.ld] = valid ? 1.0 : 0.0;
     }
 }
 
@@ -124,11 +115,46 @@ __global__ void kf_regressor_post_kernel(int model, int N, int P, int m, const d
 
 }  // namespace
 
+// Dependency levels of the program: level 0 = variables and primitives (functions of v only),
+// level L = products whose deepest factor has level L-1.  `order` lists the features level by level.
+void kf_program_levels(const KfProgram& p, std::vector<int>& order, std::vector<int>& level_start) {
+    const int n = p.n_full();
+    std::vector<int> depth(n, 0);
+    int maxd = 0;
+    for (int j = 0; j < n; ++j) {
+        const KfOp& op = p.ops[j];
+        if (op.kind == KF_OP_MUL) {
+            const int da = op.a < p.nv ? -1 : depth[op.a], db = op.b < p.nv ? -1 : depth[op.b];
+            depth[j] = 1 + std::max(da, db);
+        }
+        maxd = std::max(maxd, depth[j]);
+    }
+    order.clear();
+    level_start.assign(1, 0);
+    for (int d = 0; d <= maxd; ++d) {
+        for (int j = 0; j < n; ++j)
+            if (depth[j] == d) order.push_back(j);
+        level_start.push_back((int)order.size());
+    }
+}
+
 int kf_launch_lift(kf_ctx* ctx, const KfLiftArgs& a, cudaStream_t st) {
-    dim3 grid((a.Mc + LIFT_THREADS - 1) / LIFT_THREADS, 2);
-    kf_lift_panel_kernel<<<grid, LIFT_THREADS, 0, st>>>(a);
+    const int nsides = a.nsides > 0 ? a.nsides : 2;
+    const unsigned gx = (unsigned)((a.Mc + LIFT_THREADS - 1) / LIFT_THREADS);
+    const int nlev = (int)ctx->level_start.size() - 1;
+    for (int l = 0; l < nlev; ++l) {
+        const int first = ctx->level_start[l], count = ctx->level_start[l + 1] - first;
+        if (count <= 0) continue;
+        dim3 grid(gx, (count + LIFT_FS - 1) / LIFT_FS, nsides);
+        kf_lift_level_kernel<<<grid, LIFT_THREADS, 0, st>>>(a, first, count, (l == 0 && a.extras) ? 1 : 0);
+        ctx->launches += 1;
+    }
+    if (a.n_pcs > 0) {
+        dim3 grid(gx, (a.n_pcs + LIFT_FS - 1) / LIFT_FS, nsides);
+        kf_lift_econ_kernel<<<grid, LIFT_THREADS, 0, st>>>(a);
+        ctx->launches += 1;
+    }
     KF_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 1;
     return KF_OK;
 }
 
@@ -136,16 +162,25 @@ int kf_launch_lift_points(kf_ctx* ctx, const KfOp* ops, const double* centres, c
                           int n_pcs, const double* V, long long rows, double* full, double* out, long long ldo,
                           cudaStream_t st) {
     if (rows <= 0) return KF_OK;
-    unsigned grid = (unsigned)((rows + LIFT_THREADS - 1) / LIFT_THREADS);
-    kf_lift_points_kernel<<<grid, LIFT_THREADS, 0, st>>>(ops, centres, pcs, nv, n_full, n_pcs, V, rows, full, out, ldo);
-    KF_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 1;
-    return KF_OK;
+    KfLiftArgs a{};
+    a.ops = ops; a.centres = centres; a.pcs = pcs; a.order = ctx->d_order.as<int>();
+    a.nv = nv; a.n_full = n_full; a.n_pcs = n_pcs; a.N = n_pcs ? nv + n_pcs + 1 : n_full;
+    a.nzeta = nv; a.m = 0; a.model = KF_NONLINEAR;
+    a.alpha = V; a.beta = V; a.u = V;
+    a.M = rows; a.start = 0; a.Mc = (int)rows;
+    a.panel = out; a.ld = ldo; a.full = full;
+    a.x_off = 0; a.y_off = 0; a.w_off = 0; a.nW = 0;
+    a.nsides = 1; a.extras = 0;
+    if (n_pcs && ldo != rows) {
+        ctx->err = "kf_launch_lift_points: dim_red needs ldo == rows";
+        return KF_EINVAL;
+    }
+    return kf_launch_lift(ctx, a, st);
 }
 
 int kf_launch_regressors(kf_ctx* ctx, const KfLiftArgs& a0, double* AB, double* /*unused*/, long long ldp,
                          cudaStream_t st) {
-    // psi(x) -> columns [0,N), psi(y) -> columns [P, P+N) of AB (ld = ldp >= M); whole data set in one launch
+    // psi(x) -> columns [0,N), psi(y) -> columns [P, P+N) of AB (ld = ldp >= M); whole data set at once
     KfLiftArgs a = a0;
     const int P = kf_regressor_width(a.model, a.N, a.m);
     a.panel = AB;
@@ -156,13 +191,12 @@ int kf_launch_regressors(kf_ctx* ctx, const KfLiftArgs& a0, double* AB, double* 
     a.y_off = P;
     a.nW = 0;
     a.w_off = 0;
-    const int model = a.model;
-    if (model == KF_BILINEAR) a.model = KF_NONLINEAR + 100;   // suppress the weight rows / u rows of panel mode
-    if (model == KF_LINEAR) a.model = KF_NONLINEAR + 100;
+    a.nsides = 2;
+    a.extras = 0;
     KF_TRY(kf_launch_lift(ctx, a, st));
-    if (model != KF_NONLINEAR) {
-        dim3 grid((unsigned)((a.M + 127) / 128), model == KF_BILINEAR ? (a.N + 63) / 64 : 1);
-        kf_regressor_post_kernel<<<grid, 128, 0, st>>>(model, a.N, P, a.m, a.u, a.M, AB, ldp);
+    if (a.model != KF_NONLINEAR) {
+        dim3 grid((unsigned)((a.M + 127) / 128), a.model == KF_BILINEAR ? (a.N + 63) / 64 : 1);
+        kf_regressor_post_kernel<<<grid, 128, 0, st>>>(a.model, a.N, P, a.m, a.u, a.M, AB, ldp);
         KF_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     }

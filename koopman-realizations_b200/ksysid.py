@@ -1,0 +1,332 @@
+"""Host-side mirror of the reference's `Ksysid` class (Ksysid.m) over the koopfit C ABI.
+
+Same constructor name-value API ('model_type', 'obs_type', 'obs_degree', 'delays', 'lasso',
+'snapshots', 'dim_red', ...), same property names (params, lift, basis, model, candidates,
+koopData, scaledown, scaleup, traindata, valdata, snapshotPairs) and the same returned
+model layout (A, B, C, M / Beta / F_func, K, params, lasso), so a Kmpc/Ksim-style consumer
+reads the result unchanged.  What moves to the GPU is the hot path: get_Koopman's lift
+loop, Px'Px / Px'Py, `\\` and the L1-ball QP (Ksysid.m:987-1176) and the lasso loop of
+train_models (1370-1387) — one kf_fit call.  The MATLAB original keeps this host logic in
+MATLAB; here it is Python because MATLAB/Octave are absent.
+
+Pre-processing (merge / scale / zeta / snapshot pairs, Ksysid.m:180-229, 380-401, 868-984)
+stays on the host as in the reference (SURVEY §8f "next #3").
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi as A
+from .fitter import Fitter
+
+
+# ------------------------------------------------------------------ host pre-processing
+def merge_trials(trials):
+    """Ksysid.m:380-401."""
+    if isinstance(trials, dict):
+        return trials
+    return {k: np.concatenate([np.asarray(t[k], dtype=np.float64) for t in trials], axis=0) for k in ("t", "y", "u")}
+
+
+def _scale_factors(data):
+    """Ksysid.m:187-204: centre and half-range per column, unit factor for constant columns."""
+    out = {}
+    for k in ("y", "u"):
+        mn, mx = data[k].min(axis=0), data[k].max(axis=0)
+        half = (mx - mn) / 2.0
+        out[k + "_offset"] = (mx + mn) / 2.0
+        out[k + "_factor"] = np.where(half == 0, 1.0, half)
+    return out
+
+
+def _zeta(y, u, nd):
+    """Ksysid.m:868-907: zeta_i = [y_i, y_{i-1..i-nd}, u_{i-1..i-nd}], uzeta_i = u_i."""
+    T = y.shape[0]
+    if nd == 0:
+        return y.copy(), u.copy()
+    cols = [y[nd:T]] + [y[nd - j:T - j] for j in range(1, nd + 1)] + [u[nd - j:T - j] for j in range(1, nd + 1)]
+    return np.concatenate(cols, axis=1), u[nd:T].copy()
+
+
+class Ksysid:
+    """Koopman-based system identification; GPU fit through libkoopfit.so.
+
+    Ksysid(data4sysid, model_type='linear'|'bilinear'|'nonlinear', obs_type=['poly',...],
+           obs_degree=[...], delays=0, lasso=Inf|vector, snapshots=Inf, dim_red=None, ...)
+
+    data4sysid: dict with 'train' and 'val' lists of trials, each a dict with t (T,), y (T,n), u (T,m).
+    Extra (not in the reference): `centres` — gaussian centres (the reference draws them from MATLAB's
+    global rand, Ksysid.m:803; they must be an input here), `device`, `fitter`, `ls_method`.
+    """
+
+    def __init__(self, data4sysid, **kw):
+        if "train" not in data4sysid or "val" not in data4sysid:
+            raise ValueError("Input must have *train* and *val* fields of type cell array")   # Ksysid.m:46-48
+        # defaults, Ksysid.m:73-81 (dim_red has NO default there: [] behaves as "reduce", see 137-141)
+        self.isupdate = False
+        self.obs_type = ["poly"]
+        self.obs_degree = [1]
+        self.snapshots = np.inf
+        self.lasso = [1e6]
+        self.delays = 0
+        self.model_type = "linear"
+        self.loaded = False
+        self.time_type = "discrete"
+        self.dim_red = None
+        extras = {"centres": None, "device": 0, "fitter": None, "ls_method": "auto", "rng_seed": 0}
+        for k, v in kw.items():          # parse_args, Ksysid.m:147-158
+            if k in extras:
+                extras[k] = v
+            else:
+                setattr(self, k, v)
+        self.lasso = np.atleast_1d(np.asarray(self.lasso, dtype=np.float64)).copy()
+        if np.all(np.isinf(self.lasso)):
+            self.lasso = np.array([1e6])                     # Ksysid.m:155-157
+        if isinstance(self.obs_type, str):
+            self.obs_type = [self.obs_type]
+        self.obs_degree = [int(d) for d in np.atleast_1d(self.obs_degree)]
+        if self.model_type not in ("linear", "bilinear", "nonlinear"):
+            raise ValueError("Invalid model_type chosen. Must be linear, bilinear, or nonlinear.")   # 103
+        if self.loaded:
+            raise NotImplementedError("loaded (w) dictionaries are outside the hot-path scope (SURVEY §2a)")
+        if self.time_type != "discrete":
+            raise NotImplementedError("continuous-time (logm) models are outside the hot-path scope (SURVEY §8f #4)")
+        self.liftinput = {"linear": 0, "nonlinear": 1, "bilinear": 2}[self.model_type]
+        self._ls_method = extras["ls_method"]
+
+        tr0 = data4sysid["train"][0]
+        y0, u0 = np.atleast_2d(np.asarray(tr0["y"], float)), np.atleast_2d(np.asarray(tr0["u"], float))
+        self.params = {"n": y0.shape[1], "m": u0.shape[1],
+                       "Ts": float(np.mean(np.diff(np.asarray(tr0["t"], float)))), "isfake": False}
+        self.params["nd"] = int(self.delays)
+        n, m, nd = self.params["n"], self.params["m"], self.params["nd"]
+        self.params["nzeta"] = n * (nd + 1) + m * nd
+        self.params["nw"] = 0
+
+        # merge + scale (Ksysid.m:119-128)
+        merged = merge_trials(data4sysid["train"])
+        sc = _scale_factors(merged)
+        self.params["scale"] = sc
+        self.scaledown = {"y": lambda y: (y - sc["y_offset"]) / sc["y_factor"], "u": lambda u: (u - sc["u_offset"]) / sc["u_factor"]}
+        self.scaleup = {"y": lambda y: y * sc["y_factor"] + sc["y_offset"], "u": lambda u: u * sc["u_factor"] + sc["u_offset"]}
+        self.traindata = {"t": merged["t"], "y": self.scaledown["y"](merged["y"]), "u": self.scaledown["u"](merged["u"])}
+        self.valdata = [self.scale_data(v) for v in data4sysid["val"]]
+        self.snapshotPairs = self.get_snapshotPairs(self.traindata, self.snapshots)
+
+        # dictionary (def_observables, Ksysid.m:455-536): a numeric descriptor crosses the ABI
+        nv = self.params["nzeta"] + (m if self.model_type == "nonlinear" else 0)
+        self.basis = A.Basis(self.obs_type, self.obs_degree, nv, centres=extras["centres"])
+        self.fitter = extras["fitter"] or Fitter(device=extras["device"])
+        self.lift = {"full": lambda v: self._lift(v, econ=False), "econ_full": lambda v: self._lift(v, econ=True),
+                     "econ_full_input": self._lift_input}
+        if self.dim_red is None or self.dim_red:            # `if ~obj.dim_red ... else` with [] -> reduce (137-141)
+            self._reduce_dimension()
+        self.params["N"] = self.fitter.dims(self.basis, self.model_type, m)[1]
+        print(f"Number of basis functions: {self.params['N']}")     # Ksysid.m:143
+        self.model = None
+        self.candidates = None
+        self.koopData = None
+
+    # ------------------------------------------------------------------ data helpers
+    def scale_data(self, trial, down=True):
+        """Ksysid.m:308-343."""
+        f = self.scaledown if down else self.scaleup
+        return {"t": np.asarray(trial["t"], float), "y": f["y"](np.asarray(trial["y"], float)),
+                "u": f["u"](np.asarray(trial["u"], float))}
+
+    def get_zeta(self, data):
+        """Ksysid.m:868-907."""
+        zeta, uzeta = _zeta(data["y"], data["u"], self.params["nd"])
+        out = dict(data)
+        out["zeta"], out["uzeta"] = zeta, uzeta
+        return out, zeta
+
+    def get_snapshotPairs(self, data, snapshots=np.inf):
+        """Ksysid.m:910-984.  Trial-boundary pairs dropped (948); num_max = kept-1 (960).  With
+        snapshots=Inf the reference permutes the first num_max kept pairs (974-975); order does not
+        change G, C or K, so natural order is kept.  A smaller `snapshots` draws without replacement
+        from numpy's generator (MATLAB's mlfg6331_64 stream is not reproducible here)."""
+        print("Constructing snapshots...")
+        data = merge_trials(data)
+        nd = self.params["nd"]
+        zeta, uzeta = _zeta(data["y"], data["u"], nd)
+        t = data["t"]
+        good = np.nonzero(t[nd:-1] < t[nd + 1:])[0]
+        num_max = good.size - 1
+        idx = good[:num_max]
+        if np.isfinite(snapshots) and snapshots <= num_max - 1:
+            idx = np.sort(np.random.default_rng(0).choice(idx, size=int(snapshots), replace=False))
+        elif np.isfinite(snapshots):
+            print(f"Number of snapshot pairs cannot exceed {num_max}. Taking {num_max} pairs instead.")
+        return {"alpha": zeta[:-1][idx], "beta": zeta[1:][idx], "u": uzeta[:-1][idx]}
+
+    # ------------------------------------------------------------------ lifting
+    def _lift(self, v, econ=True):
+        v = np.asarray(v, dtype=np.float64)
+        single = v.ndim == 1
+        V = v[None, :] if single else v
+        if econ or self.basis.pcs is None:
+            out = self.fitter.lift(self.basis, V)
+        else:
+            full = A.Basis(self.obs_type, self.obs_degree, self.basis.nv, centres=self.basis.centres)
+            out = self.fitter.lift(full, V)
+        return out[0] if single else out
+
+    def _lift_input(self, zeta, u):
+        """lift.econ_full_input (Ksysid.m:1593-1604): [psi; u_1 psi; ...; u_m psi]."""
+        z = self._lift(zeta)
+        u = np.asarray(u, float)
+        return np.concatenate([z] + [u[..., k:k + 1] * z for k in range(u.shape[-1])], axis=-1)
+
+    def _reduce_dimension(self):
+        """lift_snapshots + get_econ_observables with dim_red (Ksysid.m:1394-1432, 1495-1517).
+        The covariance of the lifted alpha snapshots comes from the same GPU lift + Gram pass: with the
+        constant observable last, G = Psi'Psi gives both sum(psi psi') and sum(psi)."""
+        print("Performing dimensional reduction...")
+        sp = self.snapshotPairs
+        m = self.params["m"]
+        # a 'nonlinear' pass over [alpha, u] (or alpha alone) accumulates Psi_full' Psi_full
+        if self.model_type == "nonlinear":
+            res = self.fitter.fit(self.basis, "nonlinear", sp["alpha"], sp["alpha"], sp["u"], want_gram=True, ls_method="gram")
+        else:
+            res = self.fitter.fit(self.basis, "nonlinear", sp["alpha"], sp["alpha"], np.zeros((sp["alpha"].shape[0], 0)),
+                                  want_gram=True, ls_method="gram")
+        G = res["G"]
+        M = sp["alpha"].shape[0]
+        mu = G[:, -1] / M                                   # last observable is the constant 1
+        cov = (G - M * np.outer(mu, mu)) / (M - 1)
+        lam, vec = np.linalg.eigh((cov + cov.T) / 2)
+        lam, vec = lam[::-1], vec[:, ::-1]
+        lam = np.maximum(lam, 0.0)
+        for j in range(vec.shape[1]):                       # MATLAB pca sign convention
+            i = np.argmax(np.abs(vec[:, j]))
+            if vec[i, j] < 0:
+                vec[:, j] = -vec[:, j]
+        explained = 100.0 * lam / lam.sum()
+        num_pcs = 1
+        while explained[:num_pcs].sum() < 99:               # Ksysid.m:1501-1504
+            num_pcs += 1
+        self.basis.set_pcs(vec[:, :num_pcs])
+
+    # ------------------------------------------------------------------ the fit
+    def get_Koopman(self, snapshotPairs, lasso=None):
+        """Ksysid.m:987-1092 — one GPU call; `lasso` may be a vector (all budgets share G, C)."""
+        print("Finding Koopman operator approximation...")
+        N = self.params["N"]
+        lasso = self.lasso if lasso is None else np.atleast_1d(np.asarray(lasso, dtype=np.float64))
+        want_reg = self.model_type == "linear"              # get_model needs koopData.Px / Py (1206-1216)
+        if np.all(self.lasso >= 1e6):                       # branch test on the PROPERTY (Ksysid.m:1068)
+            res = self.fitter.fit(self.basis, self.model_type, snapshotPairs["alpha"], snapshotPairs["beta"],
+                                  snapshotPairs["u"], want_regressors=want_reg, least_squares=True, ls_method=self._ls_method)
+        else:
+            res = self.fitter.fit(self.basis, self.model_type, snapshotPairs["alpha"], snapshotPairs["beta"],
+                                  snapshotPairs["u"], want_regressors=want_reg, least_squares=False, t=lasso * N,
+                                  delay_constraint=(self.model_type == "linear" and self.params["nd"] >= 1),
+                                  n=self.params["n"], nd=self.params["nd"])
+        out = []
+        for i in range(res["K_all"].shape[2]):
+            kd = {"K": np.array(res["K_all"][:, :, i]), "u": snapshotPairs["u"], "alpha": snapshotPairs["alpha"],
+                  "info": res["info"], "rank": res["rank"]}
+            if want_reg:
+                kd["Px"], kd["Py"] = res["Px"][:, :N], res["Py"][:, :N]     # Ksysid.m:1085-1086
+            out.append(kd)
+        return out
+
+    def get_model(self, koopData):
+        """Ksysid.m:1179-1235 (discrete): A, B, C and the projection M = (L \\ R)'."""
+        N, n = self.params["N"], self.params["n"]
+        UT = koopData["K"].T
+        Amat, Bmat = UT[:N, :N], UT[:N, N:]
+        Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
+        L = koopData["Px"] @ Amat.T + koopData["u"] @ Bmat.T
+        Mt, _, _ = self.fitter.mldivide(L, koopData["Py"])          # `L \ R` on the GPU (Ksysid.m:1216)
+        Mp = Mt.T
+        return {"A": Mp @ Amat, "B": Mp @ Bmat, "C": Cy, "M": Mp, "params": self.params, "K": koopData["K"]}
+
+    def get_BLmodel(self, koopData):
+        """Ksysid.m:1238-1282."""
+        N, n, m = self.params["N"], self.params["n"], self.params["m"]
+        UT = koopData["K"].T
+        Amat, Bmat = UT[:N, :N], UT[:N, N:]
+        Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
+        return {"A": Amat, "B": Bmat, "Beta": lambda z: Bmat @ np.kron(np.eye(m), np.asarray(z).reshape(-1, 1)),
+                "C": Cy, "params": self.params, "K": koopData["K"]}
+
+    def get_NLmodel(self, koopData):
+        """Ksysid.m:1298-1341: F(zeta,u) = K(:,1:nzeta)' psi([zeta;u]); C = I_n."""
+        nz, n = self.params["nzeta"], self.params["n"]
+        F = koopData["K"][:, :nz].T.copy()
+        return {"F_sym": F, "F_func": lambda zeta, u: F @ self._lift(np.concatenate([np.ravel(zeta), np.ravel(u)])),
+                "params": self.params, "C": np.eye(n), "K": koopData["K"]}
+
+    def train_models(self, lasso=None):
+        """Ksysid.m:1344-1389: candidates per lasso value; model = candidates{1}."""
+        lasso = self.lasso if lasso is None else np.atleast_1d(np.asarray(lasso, dtype=np.float64))
+        kds = self.get_Koopman(self.snapshotPairs, lasso)
+        extract = {"nonlinear": self.get_NLmodel, "bilinear": self.get_BLmodel, "linear": self.get_model}[self.model_type]
+        cands = []
+        for i, kd in enumerate(kds):
+            mdl = extract(kd)
+            mdl["lasso"] = float(lasso[min(i, len(lasso) - 1)])
+            cands.append(mdl)
+        if len(lasso) < 2:
+            self.koopData, self.candidates, self.model = kds[0], cands[0], cands[0]
+        else:
+            self.koopData, self.candidates, self.model = kds, cands, cands[0]
+        return self
+
+    # ------------------------------------------------------------------ validation (Ksysid.m:1623-1898)
+    def get_error(self, sim, real):
+        d = sim["y"] - real["y"]
+        T = len(real["t"])
+        rmse = np.sqrt(np.sum(d ** 2, axis=0) / T)
+        eu = np.sqrt(np.sum(d ** 2, axis=1))
+        return {"abs": np.abs(d), "mean": np.mean(np.abs(d), axis=0), "rmse": rmse,
+                "nrmse": rmse / np.abs(real["y"].max(axis=0) - real["y"].min(axis=0)),
+                "euclid": eu, "euclid_mean": float(eu.sum() / T)}
+
+    def _val_setup(self, valdata):
+        nd = self.params["nd"]
+        _, zetareal = self.get_zeta(valdata)
+        return valdata["t"][nd:], valdata["y"][nd:], valdata["u"][nd:], zetareal
+
+    def val_model(self, model, valdata):
+        treal, yreal, ureal, zetareal = self._val_setup(valdata)
+        z = self._lift(zetareal[0])
+        ysim = np.zeros_like(yreal); ysim[0] = yreal[0]
+        zsim = np.zeros((len(treal), z.size)); zsim[0] = z
+        for j in range(len(treal) - 1):
+            z = model["A"] @ z + model["B"] @ ureal[j]                    # Ksysid.m:1685
+            zsim[j + 1], ysim[j + 1] = z, model["C"] @ z
+        res = {"t": treal, "sim": {"t": treal, "u": ureal, "y": ysim, "z": zsim}, "real": {"t": treal, "u": ureal, "y": yreal}}
+        res["error"] = self.get_error(res["sim"], res["real"])
+        return res
+
+    def val_BLmodel(self, model, valdata):
+        treal, yreal, ureal, zetareal = self._val_setup(valdata)
+        z = self._lift(zetareal[0])
+        ysim = np.zeros_like(yreal); ysim[0] = yreal[0]
+        for j in range(len(treal) - 1):
+            z = model["A"] @ z + model["Beta"](z) @ ureal[j]              # Ksysid.m:1783
+            ysim[j + 1] = model["C"] @ z
+        res = {"t": treal, "sim": {"t": treal, "u": ureal, "y": ysim}, "real": {"t": treal, "u": ureal, "y": yreal}}
+        res["error"] = self.get_error(res["sim"], res["real"])
+        return res
+
+    def val_NLmodel(self, model, valdata):
+        treal, yreal, ureal, zetareal = self._val_setup(valdata)
+        n = self.params["n"]
+        zeta = zetareal[0].copy()
+        ysim = np.zeros_like(yreal); ysim[0] = zeta[:n]
+        for j in range(len(treal) - 1):
+            zeta = model["F_func"](zeta, ureal[j])                         # Ksysid.m:1860
+            ysim[j + 1] = zeta[:n]
+        res = {"t": treal, "sim": {"t": treal, "u": ureal, "y": ysim}, "real": {"t": treal, "u": ureal, "y": yreal}}
+        res["error"] = self.get_error(res["sim"], res["real"])
+        return res
+
+    def valNplot_model(self, trial=None, **_):
+        """valNplot_model without the plots (Ksysid.m:1928-1972): validate the chosen model on val trials."""
+        trials = range(len(self.valdata)) if trial is None else [trial]
+        fn = {"nonlinear": self.val_NLmodel, "bilinear": self.val_BLmodel, "linear": self.val_model}[self.model_type]
+        return [fn(self.model, self.valdata[i]) for i in trials]
