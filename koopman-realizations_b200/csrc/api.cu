@@ -105,7 +105,9 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
     (void)npairs;
     const int T = (int)L.tiles.size();
     const int ksteps = L.Mc / KF_BK;
-    int nsplit = ctx->opt_splitk > 0 ? ctx->opt_splitk : (2 * ctx->sm_count + T - 1) / T;
+    // split-K so that small problems still fill the machine: aim at ~2 waves of 2 CTAs per SM
+    const int ctas = T * (KF_BM / KF_CTA_M) * (KF_BN / KF_CTA_N);
+    int nsplit = ctx->opt_splitk > 0 ? ctx->opt_splitk : (4 * ctx->sm_count + ctas - 1) / ctas;
     nsplit = std::max(1, std::min(nsplit, std::max(1, ksteps / 4)));
     L.nsplit = nsplit;
     L.valid = true;
@@ -130,24 +132,28 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
         for (int s = 0; s < nsplit; ++s) {
             const int k0 = std::min(s * per, ksteps) * KF_BK, k1 = std::min((s + 1) * per, ksteps) * KF_BK;
             if (k1 <= k0) continue;
-            for (int t = 0; t < T; ++t) {
-                const KfTile& tl = L.tiles[t];
-                KfGemmTask g{};
-                g.A = panel + (long long)(L.x_off + tl.tm * KF_BM) * L.Mc;
-                g.B = panel + (long long)((tl.kind == 0 ? L.x_off : L.y_off) + tl.tn * KF_BN) * L.Mc;
-                g.W = tl.q > 0 ? panel + (long long)(L.w_off + tl.q) * L.Mc : nullptr;
-                g.out = ctx->d_accum.as<double>() + ((long long)s * T + t) * KF_TILE_ELEMS;
-                g.lda = g.ldb = L.Mc;
-                g.ldm = KF_BN;
-                g.ldn = 1;
-                g.k0 = k0;
-                g.k1 = k1;
-                g.a_rows = KF_BM;
-                g.b_rows = KF_BN;
-                g.alpha = 1.0;
-                g.accumulate = 1;
-                tasks.push_back(g);
-            }
+            // every 128 x 128 accumulator tile is covered by (128/CTA_M) x (128/CTA_N) CTA tasks
+            for (int t = 0; t < T; ++t)
+                for (int sm = 0; sm < KF_BM / KF_CTA_M; ++sm)
+                    for (int sn = 0; sn < KF_BN / KF_CTA_N; ++sn) {
+                        const KfTile& tl = L.tiles[t];
+                        KfGemmTask g{};
+                        g.A = panel + (long long)(L.x_off + tl.tm * KF_BM + sm * KF_CTA_M) * L.Mc;
+                        g.B = panel + (long long)((tl.kind == 0 ? L.x_off : L.y_off) + tl.tn * KF_BN + sn * KF_CTA_N) * L.Mc;
+                        g.W = tl.q > 0 ? panel + (long long)(L.w_off + tl.q) * L.Mc : nullptr;
+                        g.out = ctx->d_accum.as<double>() + ((long long)s * T + t) * KF_TILE_ELEMS +
+                                (long long)sm * KF_CTA_M * KF_BN + sn * KF_CTA_N;
+                        g.lda = g.ldb = L.Mc;
+                        g.ldm = KF_BN;
+                        g.ldn = 1;
+                        g.k0 = k0;
+                        g.k1 = k1;
+                        g.a_rows = KF_CTA_M;
+                        g.b_rows = KF_CTA_N;
+                        g.alpha = 1.0;
+                        g.accumulate = 1;
+                        tasks.push_back(g);
+                    }
         }
         KF_CUDA(ctx, ctx->d_tasks[b].ensure(sizeof(KfGemmTask) * tasks.size()));
         KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tasks[b].p, tasks.data(), sizeof(KfGemmTask) * tasks.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -163,7 +169,7 @@ int ntasks_of(const KfLayout& L) {
     int used = 0;
     for (int s = 0; s < L.nsplit; ++s)
         if (std::min((s + 1) * per, ksteps) > std::min(s * per, ksteps)) ++used;
-    return used * (int)L.tiles.size();
+    return used * (int)L.tiles.size() * (KF_BM / KF_CTA_M) * (KF_BN / KF_CTA_N);
 }
 
 bool same_layout(const KfLayout& L, const KfProgram& p, const kf_problem* pr, int Mc_hint) {
@@ -305,8 +311,69 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
             ctx->err = "kf_solve: QP branch needs nt > 0 budgets";
             return KF_EINVAL;
         }
-        ctx->err = "L1-ball QP: not built in this revision";
-        return KF_EUNSUPPORTED;
+        // --- `any(eig(G) < 0)` -> G += 1e-6 I (Ksysid.m:1117-1120).  For a numerically singular G the sign
+        // of the smallest computed eigenvalue is rounding noise, so AS_REFERENCE shifts exactly when the
+        // pivoted Cholesky finds G rank-deficient (a non-positive / negligible pivot).
+        const double tol = sv->pivot_tol > 0 ? sv->pivot_tol : 1e-7;
+        int rank = 0;
+        double minp = 0, maxp = 0;
+        KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_W.p, ctx->d_G.p, mat, cudaMemcpyDeviceToDevice, st));
+        KF_TRY(kf_solve_gram_ls(ctx, P, Pp, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), tol, d_perm,
+                                &rank, &minp, &maxp, st));
+        bool shift = sv->psd_shift == KF_PSD_ALWAYS || (sv->psd_shift == KF_PSD_AS_REFERENCE && rank < P);
+        if (shift) {
+            KF_TRY(kf_add_diag(ctx, ctx->d_G.as<double>(), Pp, P, 1e-6, st));
+            KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_W.p, ctx->d_G.p, mat, cudaMemcpyDeviceToDevice, st));
+            KF_TRY(kf_solve_gram_ls(ctx, P, Pp, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), 1e-14,
+                                    d_perm, &rank, &minp, &maxp, st));   // unconstrained minimiser of the shifted problem
+            if (out->G) KF_TRY(copy_out_matrix(ctx, ctx->d_G.as<double>(), Pp, P, out->G));   // the G the QP used
+        }
+        out->info.rank = rank;
+        out->info.psd_shift_applied = shift ? 1 : 0;
+        out->info.min_pivot = minp;
+        out->info.max_pivot = maxp;
+        // --- pinned delay columns (linear model, nd >= 1; Ksysid.m:1139-1164, indices replicated as written)
+        int c0 = 0, c1 = 0;
+        double pinned_l1 = 0;
+        std::vector<double> target;
+        if (sv->delay_constraint && L.model == KF_LINEAR && sv->nd >= 1) {
+            const int n = sv->n, nd = sv->nd, m = L.m, N = L.N, Nm = P;
+            const int nnd = n * nd, mnd = m * nd;
+            target.assign((size_t)Nm * (nnd + mnd), 0.0);
+            for (int i = 1; i <= nnd; ++i) target[(size_t)(Nm + 1) * (i - 1)] = 1.0;
+            for (int i = 1; i <= m; ++i) target[(size_t)Nm * nnd + N + (size_t)(Nm + 1) * (i - 1)] = 1.0;
+            for (int i = 1; i <= m * (nd - 1); ++i) {
+                const size_t idx = (size_t)Nm * (nnd + m) + nnd + (size_t)(Nm + 1) * (i - 1);
+                if (idx < target.size()) target[idx] = 1.0;
+            }
+            c0 = n;
+            c1 = n * (nd + 1) + mnd;
+            for (double v : target) pinned_l1 += std::fabs(v);
+        }
+        KF_CUDA(ctx, ctx->d_Kt.ensure(mat));
+        for (int it = 0; it < sv->nt; ++it) {
+            const double t_free = sv->t[it] - pinned_l1;
+            if (t_free < 0) {
+                ctx->err = "L1 budget smaller than the pinned delay entries: the QP is infeasible";
+                return KF_ENUMERIC;
+            }
+            double* Kt = ctx->d_Kt.as<double>();
+            KF_CUDA(ctx, cudaMemcpyAsync(Kt, ctx->d_K.p, mat, cudaMemcpyDeviceToDevice, st));   // warm start: LS minimiser
+            if (c1 > c0)
+                KF_CUDA(ctx, cudaMemcpy2DAsync(Kt + (size_t)c0 * Pp, (size_t)Pp * sizeof(double), target.data(), (size_t)P * sizeof(double),
+                                               (size_t)P * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, st));
+            KfQpResult qr{};
+            KF_TRY(kf_solve_l1ball(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), t_free, c0, c1, nullptr, sv->qp_max_iter,
+                                   sv->qp_tol, Kt, &qr, st));
+            // objective and ||K||_1 over ALL columns (the pinned ones count towards the budget row, Ksysid.m:1136)
+            KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt, &qr, st));
+            if (out->objective) out->objective[it] = qr.objective;
+            if (out->l1norm) out->l1norm[it] = qr.l1;
+            if (out->qp_iters) out->qp_iters[it] = qr.iters;
+            if (out->K) KF_TRY(copy_out_matrix(ctx, Kt, Pp, P, out->K + (size_t)it * P * P));
+            KF_CUDA(ctx, cudaStreamSynchronize(st));   // `target` and Kt are reused by the next budget
+        }
+        if (out->perm) KF_CUDA(ctx, cudaMemcpyAsync(out->perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
     }
     KF_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
     KF_CUDA(ctx, cudaStreamSynchronize(st));
@@ -374,7 +441,7 @@ void kf_destroy(kf_ctx* ctx) {
     cudaDeviceSynchronize();
     KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_full,
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
-                     &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3};
+                     &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt};
     for (KfBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

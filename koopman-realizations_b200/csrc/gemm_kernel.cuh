@@ -1,6 +1,6 @@
 // FP64 tensor-core (DMMA) tile kernel body, templated on the pipeline configuration.
 //
-//   out[m][n] (+)= alpha * sum_k w[k] * A[m][k] * B[n][k]      (128 x 128 tile per CTA)
+//   out[m][n] (+)= alpha * sum_k w[k] * A[m][k] * B[n][k]      (BM x BN tile per CTA)
 //
 // On sm_100a the FP64 tensor path is the warp-level mma.sync m8n8k4 (SASS DMMA.8x8x4);
 // tcgen05 has no f64 kind.  Operands stream global/L2 -> shared through a STAGES-deep
@@ -33,17 +33,18 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
-template <int BK_, int STAGES_, int WM_, int WN_, bool VEC_>
+template <int BK_, int STAGES_, int WM_, int WN_, bool VEC_, int BM_ = KF_BM, int BN_ = KF_BN, int MINB_ = 1>
 struct Cfg {
-    static constexpr int BK = BK_, STAGES = STAGES_, WM = WM_, WN = WN_;
+    static constexpr int BK = BK_, STAGES = STAGES_, WM = WM_, WN = WN_, BM = BM_, BN = BN_, MINB = MINB_;
     static constexpr bool VEC = VEC_;
     static constexpr int THREADS = 32 * WM * WN;
     static constexpr int LDSP = VEC ? BK + 8 : BK + 4;       // padded smem row, doubles
-    static constexpr int A_STAGE = KF_BM * LDSP, B_STAGE = KF_BN * LDSP;
-    static constexpr int MI = KF_BM / WM / 8, NJ = KF_BN / WN / 8;   // DMMA tiles per warp
-    static constexpr int CHUNKS = KF_BM * (BK / 2) / THREADS;         // 16-byte chunks per thread per operand
+    static constexpr int A_STAGE = BM * LDSP, B_STAGE = BN * LDSP;
+    static constexpr int MI = BM / WM / 8, NJ = BN / WN / 8;          // DMMA tiles per warp
+    static constexpr int CHUNKS_A = BM * (BK / 2) / THREADS;          // 16-byte chunks per thread, A operand
+    static constexpr int CHUNKS_B = BN * (BK / 2) / THREADS;
     static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE + BK) * sizeof(double);
-    static_assert(KF_BM * (BK / 2) % THREADS == 0, "loader mapping");
+    static_assert(BM * (BK / 2) % THREADS == 0 && BN * (BK / 2) % THREADS == 0, "loader mapping");
 };
 
 template <class C, bool WEIGHTED, bool PREFETCH>
@@ -57,17 +58,15 @@ __device__ __forceinline__ void gemm_tile_body(const KfGemmTask& t, double* smem
 
     // global->shared assignment: 128 rows x BK/2 sixteen-byte chunks per operand per stage
     constexpr int CPR = BK / 2;   // chunks per row
-    const double* a_src[C::CHUNKS];
-    const double* b_src[C::CHUNKS];
-    int s_off[C::CHUNKS];
+    const double* a_src[C::CHUNKS_A];
+    const double* b_src[C::CHUNKS_B];
+    const int l_row = tid / CPR, l_kc = (tid % CPR) * 2;      // chunk i of a thread: row l_row + i * RSTEP
+    constexpr int RSTEP = C::THREADS / CPR;
 #pragma unroll
-    for (int i = 0; i < C::CHUNKS; ++i) {
-        const int c = tid + i * C::THREADS;
-        const int row = c / CPR, kc = (c % CPR) * 2;
-        a_src[i] = t.A + (long long)min(row, t.a_rows - 1) * t.lda + kc;
-        b_src[i] = t.B + (long long)min(row, t.b_rows - 1) * t.ldb + kc;
-        s_off[i] = row * LDSP + kc;
-    }
+    for (int i = 0; i < C::CHUNKS_A; ++i) a_src[i] = t.A + (long long)min(l_row + i * RSTEP, t.a_rows - 1) * t.lda + l_kc;
+#pragma unroll
+    for (int i = 0; i < C::CHUNKS_B; ++i) b_src[i] = t.B + (long long)min(l_row + i * RSTEP, t.b_rows - 1) * t.ldb + l_kc;
+    const int s_off0 = l_row * LDSP + l_kc;
     const int nk = (t.k1 - t.k0) / BK;
 
     auto load_stage = [&](int stage, int kt) {
@@ -75,10 +74,9 @@ __device__ __forceinline__ void gemm_tile_body(const KfGemmTask& t, double* smem
         double* as = As + stage * C::A_STAGE;
         double* bs = Bs + stage * C::B_STAGE;
 #pragma unroll
-        for (int i = 0; i < C::CHUNKS; ++i) {
-            cp_async16(as + s_off[i], a_src[i] + k);
-            cp_async16(bs + s_off[i], b_src[i] + k);
-        }
+        for (int i = 0; i < C::CHUNKS_A; ++i) cp_async16(as + s_off0 + i * RSTEP * LDSP, a_src[i] + k);
+#pragma unroll
+        for (int i = 0; i < C::CHUNKS_B; ++i) cp_async16(bs + s_off0 + i * RSTEP * LDSP, b_src[i] + k);
         if (WEIGHTED && tid < CPR) cp_async16(Ws + stage * BK + tid * 2, t.W + k + tid * 2);
     };
 
@@ -95,7 +93,7 @@ __device__ __forceinline__ void gemm_tile_body(const KfGemmTask& t, double* smem
     }
 
     const int fr = (lane >> 2) * LDSP + (C::VEC ? 2 * (lane & 3) : (lane & 3));
-    const int a_row0 = wm * (KF_BM / C::WM), b_row0 = wn * (KF_BN / C::WN);
+    const int a_row0 = wm * (C::BM / C::WM), b_row0 = wn * (C::BN / C::WN);
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -107,7 +105,9 @@ __device__ __forceinline__ void gemm_tile_body(const KfGemmTask& t, double* smem
         if (PREFETCH && t.accumulate && t.ldn == 1 && kt == nk - 4) {
             // pull this tile's accumulator lines into L2 ahead of the read-modify-write epilogue
             const char* o = reinterpret_cast<const char*>(t.out);
-            for (int l = tid; l < KF_BM * KF_BN * 8 / 128; l += C::THREADS) prefetch_l2(o + (size_t)l * 128);
+            constexpr int LPR = C::BN * 8 / 128;   // 128-byte lines per output row
+            for (int l = tid; l < C::BM * LPR; l += C::THREADS)
+                prefetch_l2(o + ((size_t)(l / LPR) * t.ldm * 8) + (size_t)(l % LPR) * 128);
         }
         const int stage = kt % STAGES;
         const double* as = As + stage * C::A_STAGE + a_row0 * LDSP + fr;

@@ -14,9 +14,12 @@
 constexpr int KF_BM = 128;          // output tile rows  (A-operand rows per CTA)
 constexpr int KF_BN = 128;          // output tile cols  (B-operand rows per CTA)
 constexpr int KF_BK = 16;           // contraction elements per pipeline stage
-constexpr int KF_LDS = KF_BK + 4;   // padded smem row (doubles): (row*20 + k) mod 16 distinct -> conflict-free LDS.64
-constexpr int KF_STAGES = 4;
-constexpr int KF_GEMM_THREADS = 256;
+constexpr int KF_STAGES = 3;
+// CTA tile of the production DMMA kernel: 128 x 64, 4 warps (2 x 2, warp tile 64 x 32), 2 CTAs per SM —
+// the best of the configurations measured in profiles/r01_gemm_variants_v2.txt
+constexpr int KF_CTA_M = 128;
+constexpr int KF_CTA_N = 64;
+constexpr int KF_GEMM_THREADS = 128;
 constexpr int KF_TILE_ELEMS = KF_BM * KF_BN;
 
 inline long long kf_roundup(long long x, long long m) { return (x + m - 1) / m * m; }
@@ -97,7 +100,7 @@ struct kf_ctx {
     std::vector<int> level_start;   // offsets into the level-sorted feature order
     KfBuf d_order;
     KfBuf d_ops, d_centres, d_pcs, d_panel[2], d_full, d_tasks[2], d_accum, d_tilemeta;
-    KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3;
+    KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3, d_Kt;
     cudaEvent_t ev_panel_free[2] = {}, ev_panel_ready[2] = {};
 
     // options
@@ -183,3 +186,5 @@ int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long lon
 struct KfQpResult { double objective; double l1; int iters; };
 int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, double t, int fix_c0, int fix_c1,
                     const double* d_fix_target, int max_iter, double tol, double* K, KfQpResult* res, cudaStream_t st);
+int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_t st);
+int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, KfQpResult* res, cudaStream_t st);

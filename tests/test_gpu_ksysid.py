@@ -1,0 +1,62 @@
+"""GPU tests of the host-side `Ksysid` mirror (same name-value API and model layout as the reference class)."""
+import numpy as np
+import pytest
+
+import koopfit
+from koopfit.ksysid import Ksysid
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def relF(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_example_sysid_bilinear(fitter, arm_data):
+    """example_sysid.m:34-43 with 'dim_red',false, poly 2: Ksysid(...).train_models; model fields as in
+    get_BLmodel (Ksysid.m:1273-1278); A, B to 1e-9 and validation RMSE to 1e-6 on the 5 val trials."""
+    ks = Ksysid(arm_data, model_type="bilinear", obs_type=["poly"], obs_degree=[2], snapshots=np.inf, lasso=[np.inf],
+                delays=0, dim_red=False, fitter=fitter)
+    ks = ks.train_models()
+    ko = O.KsysidOracle(arm_data, model_type="bilinear", obs_type=["poly"], obs_degree=[2]).train_models()
+    assert ks.params["N"] == 28 and ks.params["nzeta"] == 6 and ks.params["m"] == 3
+    assert set(ks.model) >= {"A", "B", "Beta", "C", "params", "K", "lasso"}
+    assert relF(ks.model["A"], ko.model["A"]) < 1e-9 and relF(ks.model["B"], ko.model["B"]) < 1e-9
+    assert np.array_equal(ks.model["C"], ko.model["C"])
+    z = np.arange(28.0)
+    assert np.allclose(ks.model["Beta"](z), ks.model["B"] @ np.kron(np.eye(3), z[:, None]))
+    for i, r in enumerate(ks.valNplot_model()):
+        want = ko.validate(trial=i)["error"]["rmse"]
+        assert np.abs(r["error"]["rmse"] - want).max() < 1e-6
+
+
+def test_linear_model_with_projection(fitter, arm_data):
+    """get_model (Ksysid.m:1179-1235): A <- M A, B <- M B with M = (L \\ R)' solved by the GPU QRCP."""
+    ks = Ksysid(arm_data, model_type="linear", obs_type=["poly"], obs_degree=[2], dim_red=False, fitter=fitter).train_models()
+    ko = O.KsysidOracle(arm_data, model_type="linear", obs_type=["poly"], obs_degree=[2]).train_models()
+    assert set(ks.model) >= {"A", "B", "C", "M", "K", "params", "lasso"}
+    assert relF(ks.model["K"], ko.model["K"]) < 1e-9
+    assert relF(ks.model["A"], ko.model["A"]) < 1e-8 and relF(ks.model["B"], ko.model["B"]) < 1e-8
+    r = ks.val_model(ks.model, ks.valdata[0])
+    assert np.abs(r["error"]["rmse"] - ko.validate(trial=0)["error"]["rmse"]).max() < 1e-6
+
+
+def test_nonlinear_model(fitter, arm_data):
+    ks = Ksysid(arm_data, model_type="nonlinear", obs_type=["poly"], obs_degree=[2], dim_red=False, fitter=fitter).train_models()
+    ko = O.KsysidOracle(arm_data, model_type="nonlinear", obs_type=["poly"], obs_degree=[2]).train_models()
+    assert relF(ks.model["F_sym"], ko.model["F"]) < 1e-9
+    assert np.array_equal(ks.model["C"], np.eye(6))
+    r = ks.val_NLmodel(ks.model, ks.valdata[1])
+    assert np.abs(r["error"]["rmse"] - ko.validate(trial=1)["error"]["rmse"]).max() < 1e-6
+
+
+def test_default_dim_red_reproduces_golden_Z(fitter, arm_data, golden_Z):
+    """Reference default: dim_red is [] -> reduction ON (Ksysid.m:137-141).  poly 3 -> N = 34 as in the shipped
+    models, and lift.econ_full on the GPU reproduces the reference's own lifted states res_lin.Z."""
+    ks = Ksysid(arm_data, model_type="linear", obs_type=["poly"], obs_degree=[3], fitter=fitter)
+    assert ks.params["N"] == 34
+    Y, Zg = golden_Z["lin_Y"], golden_Z["lin_Z"]
+    Z = ks.lift["econ_full"](ks.scaledown["y"](Y[:Zg.shape[0]]))
+    assert Z.shape == Zg.shape
+    assert np.abs(Z - Zg).max() < 1e-9

@@ -1,13 +1,14 @@
 // Standalone benchmark of the DMMA tile kernel variants (gemm_kernel.cuh) on the config-5 task
 // list: 10 Kronecker blocks x (36 G + 64 C) tiles over an L2-resident panel.  Prints TFLOP/s
-// (flops issued) per variant and a checksum to confirm the variants agree.
+// (flops issued) per variant and a checksum to confirm the variants agree; plus register-level
+// probes of the warp-tile inner loop (no global memory) to separate pipe limits from feeding limits.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include "../koopman-realizations_b200/csrc/gemm_kernel.cuh"
 
 template <class C, bool W, bool PF>
-__global__ void __launch_bounds__(C::THREADS, 1) bench_kernel(const KfGemmTask* __restrict__ tasks) {
+__global__ void __launch_bounds__(C::THREADS, C::MINB) bench_kernel(const KfGemmTask* __restrict__ tasks) {
     extern __shared__ __align__(16) double smem[];
     const KfGemmTask t = tasks[blockIdx.x];
     if (W && t.W == nullptr) { kfg::gemm_tile_body<C, false, PF>(t, smem); return; }
@@ -26,15 +27,31 @@ __global__ void checksum(const double* p, size_t n, double* out) {
 }
 
 template <class C, bool W, bool PF>
-void run(const char* name, const KfGemmTask* d_tasks, int ntasks, int Mc, double* accum, size_t accum_n, double* d_sum) {
+void run(const char* name, const std::vector<KfGemmTask>& base, int Mc, double* accum, size_t accum_n, double* d_sum) {
+    // split every 128x128 tile into (128/BM) x (128/BN) CTA tasks
+    std::vector<KfGemmTask> tasks;
+    for (const auto& b : base)
+        for (int sm = 0; sm < 128 / C::BM; ++sm)
+            for (int sn = 0; sn < 128 / C::BN; ++sn) {
+                KfGemmTask g = b;
+                g.A = b.A + (size_t)sm * C::BM * b.lda;
+                g.B = b.B + (size_t)sn * C::BN * b.ldb;
+                g.out = b.out + (size_t)sm * C::BM * 128 + sn * C::BN;
+                g.a_rows = C::BM; g.b_rows = C::BN;
+                tasks.push_back(g);
+            }
+    const int ntasks = (int)tasks.size();
+    KfGemmTask* d_tasks; cudaMalloc(&d_tasks, tasks.size() * sizeof(KfGemmTask));
+    cudaMemcpy(d_tasks, tasks.data(), tasks.size() * sizeof(KfGemmTask), cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(bench_kernel<C, W, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bench_kernel<C, W, PF>, C::THREADS, C::SMEM);
     cudaMemset(accum, 0, accum_n * 8);
     bench_kernel<C, W, PF><<<ntasks, C::THREADS, C::SMEM>>>(d_tasks);
     cudaMemset(d_sum, 0, 8);
     checksum<<<1, 1024>>>(accum, accum_n, d_sum);
     double h = 0; cudaMemcpy(&h, d_sum, 8, cudaMemcpyDeviceToHost);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { printf("%-34s ERROR %s\n", name, cudaGetErrorString(e)); return; }
+    if (e != cudaSuccess) { printf("%-40s ERROR %s\n", name, cudaGetErrorString(e)); cudaFree(d_tasks); return; }
     bench_kernel<C, W, PF><<<ntasks, C::THREADS, C::SMEM>>>(d_tasks);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int reps = 10;
@@ -42,8 +59,61 @@ void run(const char* name, const KfGemmTask* d_tasks, int ntasks, int Mc, double
     for (int r = 0; r < reps; ++r) bench_kernel<C, W, PF><<<ntasks, C::THREADS, C::SMEM>>>(d_tasks);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
-    double tf = (double)ntasks * 2.0 * 128 * 128 * Mc / ms / 1e9;
-    printf("%-34s thr=%4d smem=%6zu  %.3f ms  %.2f TF  checksum %.10e\n", name, C::THREADS, C::SMEM, ms, tf, h);
+    double tf = (double)base.size() * 2.0 * 128 * 128 * Mc / ms / 1e9;
+    printf("%-40s thr=%4d smem=%6zu occ=%d ctas=%5d  %.3f ms  %.2f TF  checksum %.10e\n", name, C::THREADS, C::SMEM, occ, ntasks, ms, tf, h);
+    cudaFree(d_tasks);
+}
+
+// ---- register-level probes: the warp-tile inner loop without global memory
+template <int MI, int NJ, bool LDS_, bool SYNC, bool WEIGHT>
+__global__ void __launch_bounds__(256, 1) probe_kernel(double* out, int iters) {
+    __shared__ double sm[2 * 128 * 20 + 16];
+    for (int i = threadIdx.x; i < 2 * 128 * 20 + 16; i += 256) sm[i] = 1e-3 * (i % 13);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp >> 2, wn = warp & 3;
+    double acc[MI][NJ][2];
+    for (int i = 0; i < MI; ++i) for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0;
+    const double* as = sm + (wm * 8 * MI + (lane >> 2)) * 20 + (lane & 3);
+    const double* bs = sm + 128 * 20 + (wn * 8 * NJ + (lane >> 2)) * 20 + (lane & 3);
+    double a[MI], b[NJ];
+    for (int i = 0; i < MI; ++i) a[i] = as[i * 8 * 20];
+    for (int j = 0; j < NJ; ++j) b[j] = bs[j * 8 * 20];
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            if (LDS_) {
+#pragma unroll
+                for (int i = 0; i < MI; ++i) a[i] = as[i * 8 * 20 + kk * 4];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) b[j] = bs[j * 8 * 20 + kk * 4];
+            }
+            if (WEIGHT) {
+                const double w = sm[2 * 128 * 20 + kk * 4 + (lane & 3)];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) b[j] *= w;
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) kfg::dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        if (SYNC) __syncthreads();
+    }
+    double s = 0;
+    for (int i = 0; i < MI; ++i) for (int j = 0; j < NJ; ++j) s += acc[i][j][0] + acc[i][j][1];
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+template <int MI, int NJ, bool LDS_, bool SYNC, bool WEIGHT>
+void probe(const char* name, double* out) {
+    const int iters = 2000;
+    probe_kernel<MI, NJ, LDS_, SYNC, WEIGHT><<<148, 256>>>(out, 10);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    probe_kernel<MI, NJ, LDS_, SYNC, WEIGHT><<<148, 256>>>(out, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double tf = 148.0 * 8 * iters * 4.0 * MI * NJ * 512.0 / ms / 1e9;
+    printf("probe %-44s %.3f ms  %.2f TF\n", name, ms, tf);
 }
 
 int main(int argc, char** argv) {
@@ -55,7 +125,7 @@ int main(int argc, char** argv) {
     size_t ntile = 0;
     cudaMalloc(&panel, (size_t)rows * Mc * 8);
     fill<<<1024, 256>>>(panel, (size_t)rows * Mc, 17u);
-    for (int q = 0; q < nW; ++q) {
+    for (int q = 0; q < nW; ++q)
         for (int kind = 0; kind < 2; ++kind)
             for (int a = 0; a < tm; ++a)
                 for (int b = 0; b < (kind == 0 ? a + 1 : tm); ++b) {
@@ -68,26 +138,29 @@ int main(int argc, char** argv) {
                     g.alpha = 1.0; g.accumulate = 1;
                     tasks.push_back(g); ++ntile;
                 }
-    }
     cudaMalloc(&accum, ntile * 16384 * 8);
     for (auto& g : tasks) g.out = accum + ((size_t)g.out / 8);
-    KfGemmTask* d_tasks; cudaMalloc(&d_tasks, tasks.size() * sizeof(KfGemmTask));
-    cudaMemcpy(d_tasks, tasks.data(), tasks.size() * sizeof(KfGemmTask), cudaMemcpyHostToDevice);
     cudaMalloc(&d_sum, 8);
-    printf("tasks=%zu Mc=%d panel=%.1f MB accum=%.1f MB\n", tasks.size(), Mc, rows * (double)Mc * 8 / 1e6, ntile * 16384 * 8 / 1e6);
-    const int nt = (int)tasks.size();
+    printf("tiles=%zu Mc=%d panel=%.1f MB accum=%.1f MB\n", tasks.size(), Mc, rows * (double)Mc * 8 / 1e6, ntile * 16384 * 8 / 1e6);
     using namespace kfg;
-    run<Cfg<16, 4, 2, 4, false>, true, false>("BK16 S4 2x4 lds64 (r1 baseline)", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<16, 4, 2, 4, false>, true, true>("BK16 S4 2x4 lds64 +prefetch", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<16, 4, 2, 4, false>, false, false>("BK16 S4 2x4 lds64 unweighted", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<32, 3, 2, 4, false>, true, true>("BK32 S3 2x4 lds64 +pf", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<16, 4, 2, 4, true>, true, true>("BK16 S4 2x4 lds128 +pf", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<32, 2, 2, 4, true>, true, true>("BK32 S2 2x4 lds128 +pf", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<16, 5, 2, 4, false>, true, true>("BK16 S5 2x4 lds64 +pf", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<16, 4, 4, 4, false>, true, true>("BK16 S4 4x4 lds64 +pf (16 warps)", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<16, 4, 4, 4, true>, true, true>("BK16 S4 4x4 lds128 +pf (16 warps)", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<32, 3, 4, 4, false>, true, true>("BK32 S3 4x4 lds64 +pf (16 warps)", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<16, 4, 4, 2, false>, true, true>("BK16 S4 4x2 lds64 +pf (32x64 wt)", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
-    run<Cfg<16, 4, 2, 8, false>, true, true>("BK16 S4 2x8 lds64 +pf (64x16 wt)", d_tasks, nt, Mc, accum, ntile * 16384, d_sum);
+    const size_t an = ntile * 16384;
+    probe<8, 4, false, false, false>("64x32 warp tile, regs only (no LDS, no sync)", accum);
+    probe<8, 4, true, false, false>("64x32 + LDS fragments", accum);
+    probe<8, 4, true, true, false>("64x32 + LDS + __syncthreads/16k", accum);
+    probe<8, 4, true, true, true>("64x32 + LDS + sync + weights", accum);
+    probe<4, 4, true, true, true>("32x32 + LDS + sync + weights", accum);
+    probe<4, 2, true, true, true>("32x16 + LDS + sync + weights", accum);
+    run<Cfg<16, 4, 2, 4, false>, true, true>("128x128 BK16 S4 2x4 +pf (r1)", tasks, Mc, accum, an, d_sum);
+    run<Cfg<32, 2, 2, 4, true>, true, true>("128x128 BK32 S2 2x4 lds128 +pf", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 2, 2, false, 128, 64, 2>, true, true>("128x64 BK16 S3 2x2 occ2", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 2, 2, true, 128, 64, 2>, true, true>("128x64 BK16 S3 2x2 lds128 occ2", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 4, 2, 2, false, 64, 64, 3>, true, true>("64x64 BK16 S4 2x2 occ3", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 2, 2, false, 64, 64, 4>, true, true>("64x64 BK16 S3 2x2 occ4", tasks, Mc, accum, an, d_sum);
+    run<Cfg<32, 3, 2, 2, false, 64, 64, 3>, true, true>("64x64 BK32 S3 2x2 occ3", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 4, 2, 1, false, 64, 32, 6>, true, true>("64x32 BK16 S4 2x1 occ6", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 4, 2, 2, false, 64, 32, 4>, true, true>("64x32 BK16 S4 2x2(32x16) occ4", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 1, 4, false, 64, 128, 2>, true, true>("64x128 BK16 S3 1x4 occ2", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 4, 2, false, 128, 64, 1>, true, true>("128x64 BK16 S3 4x2(32x32) 8w occ1", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 4, 2, false, 128, 64, 2>, true, true>("128x64 BK16 S3 4x2(32x32) 8w occ2", tasks, Mc, accum, an, d_sum);
     return 0;
 }
