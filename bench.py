@@ -219,6 +219,7 @@ def main():
     import torch
     import torch.distributed as dist
     import koopfit
+    from koopfit.sharding import DeviceArrayView, allreduce_sum_
 
     if world != args.gpus and world > 1:
         args.gpus = world
@@ -245,8 +246,8 @@ def main():
         if world > 1:
             ptr, n = fit.accum_buffer()
             fit.sync()
-            buf = torch.as_tensor(_CAI(ptr, n), device=dev)
-            dist.all_reduce(buf)
+            buf = torch.as_tensor(DeviceArrayView(ptr, n), device=dev)
+            allreduce_sum_(buf)                      # the one collective: sum of the packed partial Grams (NCCL)
             torch.cuda.synchronize()
         return fit.solve_dev(P_REG, ls_method="gram")
 

@@ -304,7 +304,10 @@ int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C
         return KF_OK;
     }
     // 2. bracket lam: phi(lam_max) = -t < 0; halve until phi > 0 (warm-started from K = 0)
-    KF_CUDA(ctx, cudaMemset2DAsync(K, ld * sizeof(double), 0, (size_t)P * sizeof(double), P, st));
+    if (fix_c0 > 0) KF_CUDA(ctx, cudaMemset2DAsync(K, ld * sizeof(double), 0, (size_t)P * sizeof(double), fix_c0, st));
+    if (fix_c1 < P)   // the pinned columns [fix_c0, fix_c1) keep their pattern
+        KF_CUDA(ctx, cudaMemset2DAsync(K + (size_t)std::max(fix_c1, 0) * ld, ld * sizeof(double), 0, (size_t)P * sizeof(double),
+                                       P - std::max(fix_c1, 0), st));
     double lam_hi = lam_max, phi_hi = -t, lam_lo = 0, phi_lo = 0, lam = lam_max;
     bool bracket = false;
     for (int it = 0; it < 200; ++it) {

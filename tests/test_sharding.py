@@ -1,0 +1,81 @@
+"""CPU tests of the multi-GPU host logic with a world_size-2 gloo group: shard bounds, the single sum
+all-reduce of the partial Grams, and the replicated solve."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle as O
+from koopfit.sharding import allreduce_sum_, budgets_for_rank, shard_bounds
+
+
+def test_shard_bounds_cover_everything():
+    for M, W in ((10, 3), (100000000, 8), (7, 8), (11999, 2)):
+        spans = [shard_bounds(M, r, W) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == M
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 3, 3)
+    assert sorted(np.concatenate([budgets_for_rank(64, r, 8) for r in range(8)]).tolist()) == list(range(64))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)                      # same data on every rank
+    M, n, m = 2001, 3, 2
+    alpha = 2 * rng.random((M, n)) - 1
+    u = 2 * rng.random((M, m)) - 1
+    beta = np.clip(alpha @ (0.9 * np.eye(n)) + 0.1 * u @ rng.standard_normal((m, n)), -1, 1)
+    prog = O.build_program(["poly"], [2], n)
+    lo, hi = shard_bounds(M, rank, world)
+    Px, Py = O.build_regressors("bilinear", prog, alpha[lo:hi], beta[lo:hi], u[lo:hi])
+    G, C = O.gram(Px, Py)
+    packed = torch.from_numpy(np.concatenate([G.ravel(), C.ravel()]))
+    allreduce_sum_(packed)                              # the ONE collective of the fit
+    P = G.shape[0]
+    Gs, Cs = packed[:P * P].numpy().reshape(P, P), packed[P * P:].numpy().reshape(P, P)
+    K = np.linalg.solve(Gs, Cs)                         # replicated solve
+    q.put((rank, Gs, Cs, K))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_equals_single_pass():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(0)
+    M, n, m = 2001, 3, 2
+    alpha = 2 * rng.random((M, n)) - 1
+    u = 2 * rng.random((M, m)) - 1
+    beta = np.clip(alpha @ (0.9 * np.eye(n)) + 0.1 * u @ rng.standard_normal((m, n)), -1, 1)
+    prog = O.build_program(["poly"], [2], n)
+    Px, Py = O.build_regressors("bilinear", prog, alpha, beta, u)
+    G, C = O.gram(Px, Py)
+    for rank, Gs, Cs, K in out:
+        assert np.linalg.norm(Gs - G) <= 1e-13 * np.linalg.norm(G)
+        assert np.linalg.norm(Cs - C) <= 1e-13 * np.linalg.norm(C)
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][3], out[1][3])   # ranks agree bit for bit
