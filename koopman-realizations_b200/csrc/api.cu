@@ -119,7 +119,8 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
         KF_CUDA(ctx, cudaMemsetAsync(ctx->d_panel[b].p, 0, panel_bytes, ctx->stream));   // pad rows must be finite
     }
     if (p.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * L.n_full * L.Mc * sizeof(double)));
-    KF_CUDA(ctx, ctx->d_accum.ensure((size_t)nsplit * T * KF_TILE_ELEMS * sizeof(double)));
+    // two slab sets (one per chunk pipeline) x nsplit split-K slabs; folded into slab 0 by kf_reduce_slabs
+    KF_CUDA(ctx, ctx->d_accum.ensure((size_t)2 * nsplit * T * KF_TILE_ELEMS * sizeof(double)));
     KF_CUDA(ctx, ctx->d_tilemeta.ensure(sizeof(KfTile) * T));
     KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tilemeta.p, L.tiles.data(), sizeof(KfTile) * T, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -141,7 +142,7 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
                         g.A = panel + (long long)(L.x_off + tl.tm * KF_BM + sm * KF_CTA_M) * L.Mc;
                         g.B = panel + (long long)((tl.kind == 0 ? L.x_off : L.y_off) + tl.tn * KF_BN + sn * KF_CTA_N) * L.Mc;
                         g.W = tl.q > 0 ? panel + (long long)(L.w_off + tl.q) * L.Mc : nullptr;
-                        g.out = ctx->d_accum.as<double>() + ((long long)s * T + t) * KF_TILE_ELEMS +
+                        g.out = ctx->d_accum.as<double>() + ((long long)(b * nsplit + s) * T + t) * KF_TILE_ELEMS +
                                 (long long)sm * KF_CTA_M * KF_BN + sn * KF_CTA_N;
                         g.lda = g.ldb = L.Mc;
                         g.ldm = KF_BN;
@@ -188,7 +189,7 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
         }
         KF_TRY(make_layout(ctx, pr));
         const KfLayout& L = ctx->lay;
-        KF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)L.nsplit * L.tiles.size() * KF_TILE_ELEMS * sizeof(double), ctx->stream));
+        KF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)2 * L.nsplit * L.tiles.size() * KF_TILE_ELEMS * sizeof(double), ctx->stream));
         ctx->accum_M = 0;
     }
     const KfLayout& L = ctx->lay;
@@ -196,18 +197,20 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
     const int ntasks = ntasks_of(L);
     const bool weighted = (L.model == KF_BILINEAR);
     const long long nchunks = (pr->M + L.Mc - 1) / L.Mc;
+    // Two software pipelines: even chunks run lift -> Gram on stream A (panel 0, slab set 0), odd chunks on
+    // stream B (panel 1, slab set 1).  The pipelines are independent (own panel, own accumulator slabs), so the
+    // tail wave / epilogue of one Gram launch is filled by the next chunk's CTAs and the lifts hide under DMMAs.
     const bool overlap = ctx->opt_overlap && nchunks > 1;
-    cudaStream_t sg = ctx->stream, sl = overlap ? ctx->stream2 : ctx->stream;
+    cudaStream_t S[2] = {ctx->stream, overlap ? ctx->stream2 : ctx->stream};
 
-    KF_CUDA(ctx, cudaEventRecord(ctx->ev[0], sg));
-    if (overlap) KF_CUDA(ctx, cudaStreamWaitEvent(sl, ctx->ev[0], 0));
+    KF_CUDA(ctx, cudaEventRecord(ctx->ev[0], S[0]));
+    if (overlap) KF_CUDA(ctx, cudaStreamWaitEvent(S[1], ctx->ev[0], 0));
 
-    const int per_k = L.Mc / KF_BK;
-    (void)per_k;
     float gram_ms_sampled = 0.f;
     int gram_samples = 0;
     for (long long c = 0; c < nchunks; ++c) {
         const int b = (int)(c & 1);
+        cudaStream_t sl = S[b], sg = S[b];
         KfLiftArgs a{};
         a.ops = ctx->d_ops.as<KfOp>();
         a.centres = ctx->d_centres.as<double>();
@@ -220,27 +223,34 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
         a.panel = ctx->d_panel[b].as<double>(); a.ld = L.Mc;
         a.full = ctx->d_full.as<double>();
         a.x_off = L.x_off; a.y_off = L.y_off; a.w_off = L.w_off; a.nW = L.nW;
-        if (overlap && c >= 2) KF_CUDA(ctx, cudaStreamWaitEvent(sl, ctx->ev_panel_free[b], 0));
         KF_TRY(kf_launch_lift(ctx, a, sl));
-        if (overlap) {
-            KF_CUDA(ctx, cudaEventRecord(ctx->ev_panel_ready[b], sl));
-            KF_CUDA(ctx, cudaStreamWaitEvent(sg, ctx->ev_panel_ready[b], 0));
+        // CUDA-event timing of the Gram kernel on the stream it is launched on.  A sampled launch is isolated
+        // from the other pipeline (which waits), so the duration is the kernel's own, not a time-shared one.
+        const bool sample = ctx->opt_profile && (nchunks < 8 || (c % 61) == 3);
+        if (sample) {
+            if (overlap) {
+                KF_CUDA(ctx, cudaEventRecord(ctx->ev[6], S[1 - b]));
+                KF_CUDA(ctx, cudaStreamWaitEvent(sg, ctx->ev[6], 0));
+            }
+            KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], sg));
         }
-        const bool sample = ctx->opt_profile && (nchunks < 8 || (c % 61) == 3);   // CUDA-event timing of the Gram kernel
-        if (sample) KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], sg));
         KF_TRY(kf_launch_gemm_tasks(ctx, ctx->d_tasks[b].as<KfGemmTask>(), ntasks, weighted, sg));
         if (sample) {
             KF_CUDA(ctx, cudaEventRecord(ctx->ev[3], sg));
+            if (overlap) KF_CUDA(ctx, cudaStreamWaitEvent(S[1 - b], ctx->ev[3], 0));
             KF_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
             float ms = 0.f;
             KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
             gram_ms_sampled += ms;
             ++gram_samples;
         }
-        if (overlap) KF_CUDA(ctx, cudaEventRecord(ctx->ev_panel_free[b], sg));
         ctx->dmma_flops += (double)L.tiles.size() * 2.0 * KF_TILE_ELEMS * (double)L.Mc;
     }
-    KF_CUDA(ctx, cudaEventRecord(ctx->ev[1], sg));
+    if (overlap) {   // join pipeline B into the context stream
+        KF_CUDA(ctx, cudaEventRecord(ctx->ev[7], S[1]));
+        KF_CUDA(ctx, cudaStreamWaitEvent(S[0], ctx->ev[7], 0));
+    }
+    KF_CUDA(ctx, cudaEventRecord(ctx->ev[1], S[0]));
     ctx->accum_M += pr->M;
     ctx->last_gram_kernel_ms = gram_samples ? gram_ms_sampled / gram_samples * (float)nchunks : 0.f;
     return KF_OK;
@@ -248,7 +258,7 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
 
 int finish_accum(kf_ctx* ctx) {
     const KfLayout& L = ctx->lay;
-    KF_TRY(kf_reduce_slabs(ctx, ctx->d_accum.as<double>(), (long long)L.tiles.size() * KF_TILE_ELEMS, L.nsplit, ctx->stream));
+    KF_TRY(kf_reduce_slabs(ctx, ctx->d_accum.as<double>(), (long long)L.tiles.size() * KF_TILE_ELEMS, 2 * L.nsplit, ctx->stream));
     return KF_OK;
 }
 
@@ -516,9 +526,7 @@ int kf_accumulate_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob
 int kf_accum_buffer(kf_ctx* ctx, double** dev_ptr, size_t* count) {
     if (!ctx || !ctx->lay.valid) return KF_EINVAL;
     KF_CUDA(ctx, cudaSetDevice(ctx->device));
-    KF_TRY(finish_accum(ctx));     // slabs -> slab 0 (idempotent once nsplit slabs are folded)
-    ctx->lay.nsplit = 1;           // further accumulation continues in slab 0 only
-    // task lists still carry the old split; force a rebuild on the next reset
+    KF_TRY(finish_accum(ctx));     // all slabs -> slab 0 (the folded slabs are zeroed, so this is idempotent)
     if (dev_ptr) *dev_ptr = ctx->d_accum.as<double>();
     if (count) *count = ctx->lay.tiles.size() * (size_t)KF_TILE_ELEMS;
     return KF_OK;

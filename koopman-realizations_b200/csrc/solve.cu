@@ -17,7 +17,10 @@ __global__ void kf_reduce_slabs_kernel(double* __restrict__ accum, long long sla
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slab;
          i += (long long)gridDim.x * blockDim.x) {
         double v = accum[i];
-        for (int s = 1; s < nsplit; ++s) v += accum[(long long)s * slab + i];   // fixed order: deterministic
+        for (int s = 1; s < nsplit; ++s) {   // fixed order: deterministic
+            v += accum[(long long)s * slab + i];
+            accum[(long long)s * slab + i] = 0.0;   // folded: a later accumulate / reduce starts from zero
+        }
         accum[i] = v;
     }
 }
@@ -170,6 +173,104 @@ __global__ void __launch_bounds__(256) kf_pchol_update_kernel(double* W, long lo
             W[(long long)k * ld + i] = fma(-li, lk, W[(long long)k * ld + i]);
         }
     }
+}
+
+// ---- blocked variant (LAPACK dpstrf structure): inside a block of NB columns the factor is built
+// left-looking (the Schur-complement diagonal is tracked as W(i,i) - dots[i]), and the trailing matrix is
+// updated once per block by the DMMA kernel instead of once per column by a memory-bound rank-1 kernel.
+constexpr int PCHOL_NB = 64;
+
+// one CTA: pivot on d_i = W(i,i) - dots[i], symmetric swap j<->p (and dots), L(j,j)
+__global__ void __launch_bounds__(1024) kf_pcholb_pivot_kernel(double* W, long long ld, int P, int j, int j0, int* perm,
+                                                               double* dots, PcholState* st, double tol2) {
+    if (st->done) return;
+    __shared__ double sval[32];
+    __shared__ int sidx[32];
+    __shared__ int s_p;
+    const int tid = threadIdx.x;
+    double best = -1.0;
+    int bi = P;
+    for (int i = j + tid; i < P; i += blockDim.x) {
+        const double v = W[(long long)i * ld + i] - dots[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { sval[tid >> 5] = best; sidx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+        best = (tid < (blockDim.x >> 5)) ? sval[tid] : -1.0;
+        bi = (tid < (blockDim.x >> 5)) ? sidx[tid] : P;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (tid == 0) {
+            if (j == 0) st->piv0 = best;
+            const bool ok = (best > 0.0) && (best > tol2 * st->piv0);
+            if (!ok) {
+                st->rank = j;
+                st->done = 1;
+                s_p = -1;
+            } else {
+                s_p = bi;
+                st->minpiv = best;
+                st->rank = j + 1;
+            }
+        }
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (p < 0) return;
+    if (p != j) {
+        for (int i = tid; i < P; i += blockDim.x) {   // swap columns j <-> p
+            const double a = W[(long long)j * ld + i], b = W[(long long)p * ld + i];
+            W[(long long)j * ld + i] = b;
+            W[(long long)p * ld + i] = a;
+        }
+        __syncthreads();
+        for (int i = tid; i < P; i += blockDim.x) {   // swap rows j <-> p
+            const double a = W[(long long)i * ld + j], b = W[(long long)i * ld + p];
+            W[(long long)i * ld + j] = b;
+            W[(long long)i * ld + p] = a;
+        }
+        if (tid == 0) {
+            const int a = perm[j];
+            perm[j] = perm[p];
+            perm[p] = a;
+            const double d = dots[j];
+            dots[j] = dots[p];
+            dots[p] = d;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double ljj = sqrt(W[(long long)j * ld + j] - dots[j]);
+        W[(long long)j * ld + j] = ljj;
+    }
+}
+
+// column j of the factor: L(i,j) = (W(i,j) - sum_{k=j0}^{j-1} L(i,k) L(j,k)) / L(j,j), i > j; mirrored copy; dots
+__global__ void __launch_bounds__(256) kf_pcholb_col_kernel(double* W, long long ld, int P, int j, int j0, double* dots,
+                                                            const PcholState* st) {
+    if (st->done) return;
+    const int i = j + 1 + blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    double v = W[(long long)j * ld + i];
+    for (int k = j0; k < j; ++k) v = fma(-W[(long long)k * ld + i], W[(long long)k * ld + j], v);
+    const double l = v / W[(long long)j * ld + j];
+    W[(long long)j * ld + i] = l;
+    W[(long long)i * ld + j] = l;
+    dots[i] = fma(l, l, dots[i]);
+}
+
+__global__ void kf_zero_kernel(double* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
 }
 
 // zero rows/cols >= rank of the factor so padded contraction ranges contribute nothing
@@ -365,16 +466,50 @@ int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, double* W, const double* C, dou
     }
     const long long ld = Pp;
     const double tol2 = tol * tol;
-    for (int j = 0; j < P; ++j) {
-        kf_pchol_pivot_kernel<<<1, 1024, 0, st>>>(W, ld, P, j, d_perm, d_state, tol2);
-        const int rem = P - j - 1;
-        if (rem > 0) {
-            dim3 grid((rem + 63) / 64, (rem + 15) / 16);
-            kf_pchol_update_kernel<<<grid, 256, 0, st>>>(W, ld, P, j, d_state);
+    if (P <= 2 * PCHOL_NB) {
+        // small problems: unblocked right-looking factorisation (2 launches per column)
+        for (int j = 0; j < P; ++j) {
+            kf_pchol_pivot_kernel<<<1, 1024, 0, st>>>(W, ld, P, j, d_perm, d_state, tol2);
+            const int rem = P - j - 1;
+            if (rem > 0) {
+                dim3 grid((rem + 63) / 64, (rem + 15) / 16);
+                kf_pchol_update_kernel<<<grid, 256, 0, st>>>(W, ld, P, j, d_state);
+            }
+        }
+        ctx->launches += 2LL * P;
+    } else {
+        // blocked (dpstrf structure): left-looking inside a 64-column block, DMMA trailing update per block
+        KF_CUDA(ctx, ctx->d_K3.ensure((size_t)(4 * Pp + 8) * sizeof(double) + (size_t)(Pp + 4) * sizeof(int)));
+        double* dots = ctx->d_K3.as<double>();
+        for (int j0 = 0; j0 < P; j0 += PCHOL_NB) {
+            const int j1 = std::min(P, j0 + PCHOL_NB);
+            kf_zero_kernel<<<(P + 255) / 256, 256, 0, st>>>(dots, P);
+            for (int j = j0; j < j1; ++j) {
+                kf_pcholb_pivot_kernel<<<1, 1024, 0, st>>>(W, ld, P, j, j0, d_perm, dots, d_state, tol2);
+                const int rem = P - j - 1;
+                if (rem > 0) kf_pcholb_col_kernel<<<(rem + 255) / 256, 256, 0, st>>>(W, ld, P, j, j0, dots, d_state);
+            }
+            ctx->launches += 1 + 2LL * (j1 - j0);
+            if (j1 < P) {
+                KfGemmGrid g{};
+                g.A = W + (long long)j1 * ld;   // A[m][c] = W(c, j1+m) = L(j1+m, c): mirrored copy, c contiguous
+                g.lda = ld;
+                g.B = W + (long long)j1 * ld;
+                g.ldb = ld;
+                g.out = W + (long long)j1 * ld + j1;   // out[m][n] = W(j1+m, j1+n)
+                g.ldm = 1;
+                g.ldn = ld;
+                g.m = P - j1;
+                g.n = P - j1;
+                g.k0 = j0;
+                g.k1 = j1;               // j1 - j0 = 64 for every block that has a trailing part
+                g.alpha = -1.0;
+                g.accumulate = 1;
+                KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+            }
         }
     }
     KF_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 2LL * P;
     kf_pchol_clean_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W, ld, Pp, d_state);
     PcholState hs;
     KF_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, st));
