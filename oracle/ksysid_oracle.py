@@ -418,7 +418,51 @@ def delay_constraint_targets(N, n, m, nd):
     return n, n * (nd + 1) + mnd, bd.reshape(nnd + mnd, Nm).T.copy()
 
 
-def solve_l1ball_qp(G, C, t, fixed=None, tol=1e-13, max_outer=200, verbose=False):
+def _l1ball_qp_homotopy(G, Cf, t_free):
+    """Exact solution of  min 0.5 tr(K'GK) - tr(Cf'K)  s.t. ||K||_1 = t_free  by per-column lasso paths."""
+    from sklearn.linear_model import lars_path_gram
+
+    P, Pc = Cf.shape
+    paths = []
+    knots = [0.0]
+    for j in range(Pc):
+        if not np.any(Cf[:, j]):
+            paths.append(None)
+            continue
+        alphas, _, coefs = lars_path_gram(Xy=Cf[:, j].copy(), Gram=G.copy(), n_samples=1, method="lasso",
+                                          alpha_min=0.0, max_iter=20 * P, return_path=True)
+        paths.append((alphas[::-1].copy(), coefs[:, ::-1].copy()))       # increasing lam for np.interp
+        knots.extend(alphas.tolist())
+    knots = np.unique(np.asarray(knots))                                  # ascending
+
+    def K_at(lam):
+        K = np.zeros((P, Pc))
+        for j, pth in enumerate(paths):
+            if pth is None:
+                continue
+            al, co = pth
+            if lam >= al[-1]:
+                continue
+            i = np.searchsorted(al, lam, side="right")                   # al[i-1] <= lam < al[i]
+            if i == 0:
+                K[:, j] = co[:, 0]
+            else:
+                w = (lam - al[i - 1]) / (al[i] - al[i - 1])
+                K[:, j] = (1 - w) * co[:, i - 1] + w * co[:, i]
+        return K
+
+    l1 = np.array([np.abs(K_at(x)).sum() for x in knots])                 # non-increasing in lam
+    if l1[0] < t_free:
+        raise RuntimeError("budget inactive")
+    i = np.nonzero(l1 >= t_free)[0][-1]                                   # l1[i] >= t > l1[i+1]
+    if i + 1 >= len(knots):
+        return K_at(knots[i]), float(knots[i])
+    lo, hi = knots[i], knots[i + 1]
+    lam = lo + (l1[i] - t_free) / (l1[i] - l1[i + 1]) * (hi - lo)        # linear on the segment
+    return K_at(lam), float(lam)
+
+
+def solve_l1ball_qp(G, C, t, fixed=None, tol=1e-13, max_outer=200, verbose=False, use_lars=None):
     """Exact solver for   min 0.5 tr(K'GK) - tr(C'K)  s.t. ||vec K||_1 <= t
     (the QP of Ksysid.m:1095-1176 in un-split variables; `quadprog` stand-in).
 
@@ -467,6 +511,22 @@ def solve_l1ball_qp(G, C, t, fixed=None, tol=1e-13, max_outer=200, verbose=False
     if np.abs(K0).sum() <= t_free:
         return assemble(K0), {"lam": 0.0, "active": False}
 
+    # Exact homotopy for small problems: each column's lasso path k_j(lam) is piecewise linear in lam
+    # (LARS with the lasso modification on the Gram), so ||K(lam)||_1 is piecewise linear too and the
+    # multiplier with ||K||_1 = t is found exactly on the union of the knots.
+    if use_lars is None:
+        use_lars = P <= 160
+    if use_lars:
+        try:
+            Kl, lam_l = _l1ball_qp_homotopy(G, Cf, t_free)
+            grad = G @ Kl - Cf
+            viol = np.max(np.where(Kl == 0, np.abs(grad) - lam_l, 0.0))
+            act = np.abs(grad[Kl != 0] + lam_l * np.sign(Kl[Kl != 0])).max() if np.any(Kl != 0) else 0.0
+            if viol <= 1e-8 * max(lam_l, 1.0) and act <= 1e-8 * max(lam_l, 1.0) and abs(np.abs(Kl).sum() - t_free) <= 1e-10 * t_free:
+                return assemble(Kl), {"lam": lam_l, "active": True, "method": "homotopy"}
+        except Exception:
+            pass
+
     def polish(K, lam):
         """Exact solve on the current support/sign pattern, column by column."""
         out = np.zeros_like(K)
@@ -486,7 +546,7 @@ def solve_l1ball_qp(G, C, t, fixed=None, tol=1e-13, max_outer=200, verbose=False
             out[S, j] = kS
         return out, ok
 
-    def cd(lam, K, sweeps=20000):
+    def cd(lam, K, sweeps=3000):
         """Cyclic coordinate descent on all columns at once, covariance form."""
         R = Cf - G @ K                       # residual correlation  c - G k
         for it in range(sweeps):
