@@ -34,6 +34,16 @@ OBS_TYPE, OBS_DEGREE = ["poly", "gaussian"], [3, 569]
 FLOPS_ALGO_PER_PAIR = P_REG * (P_REG + 1) + 2 * P_REG * P_REG      # P(P+1) + 2 P Pc
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def workload_constants():
     """A0 (spectral radius 0.95), B0_i (||.||_2 = 0.1) from seed 1; gaussian centres from seed 2."""
     rng = np.random.default_rng(1)
@@ -180,7 +190,7 @@ def run_reference(args, rank):
                              "sample": f"{sample} snapshots of the same workload: NumPy lift + OpenBLAS Gram timed per snapshot, "
                                        f"dgeqp3 solve (P=4096) timed once; extrapolated linearly in M to the {args.snapshots_per_gpu * args.gpus}-snapshot job"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(args, extra=None):
@@ -212,6 +222,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: anything libraries print (e.g. "NCCL version ...") goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -349,7 +364,7 @@ def main():
             line["cpu_baseline"] = {"value": Mjob / (Mjob / rate_lg + t_solve), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{args.cpu_sample} snapshots of the same workload (oracle: NumPy lift + OpenBLAS Gram {t_lg:.1f} s, "
                                               f"dgeqp3 solve {t_solve:.1f} s), per-snapshot part extrapolated linearly to {Mjob} snapshots"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     fit.close()
     if world > 1:
         dist.destroy_process_group()

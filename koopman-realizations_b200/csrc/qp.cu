@@ -241,6 +241,17 @@ __global__ void kf_absmax_kernel(const double* C, long long ld, int P, int ncols
     }
 }
 
+// the dynamic shared-memory limit of the CD kernel only ever grows (a smaller value would make a later,
+// larger launch fail with "invalid argument")
+int ensure_cd_smem(kf_ctx* ctx, size_t smem) {
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        KF_CUDA(ctx, cudaFuncSetAttribute(kf_cd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    return KF_OK;
+}
+
 }  // namespace
 
 // Solve one budget t.  G (possibly shifted), C: Pp-strided P x P; K: warm start in, solution out.
@@ -250,11 +261,7 @@ int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C
                     const double* /*d_fix_target*/, int max_iter, double tol, double* K, KfQpResult* res, cudaStream_t st) {
     const long long ld = Pp;
     const size_t smem = (size_t)P * (2 * sizeof(double) + sizeof(int)) + 16;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        KF_CUDA(ctx, cudaFuncSetAttribute(kf_cd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    KF_TRY(ensure_cd_smem(ctx, smem));
     // scratch: dG[P] | l1[P] | obj[P] | aux[P] | out[4] | iters[P] | flips
     KF_CUDA(ctx, ctx->d_K3.ensure((size_t)(4 * Pp + 8) * sizeof(double) + (size_t)(Pp + 4) * sizeof(int)));
     double* dG = ctx->d_K3.as<double>();
@@ -380,7 +387,7 @@ int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_
 int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, KfQpResult* res, cudaStream_t st) {
     const long long ld = Pp;
     const size_t smem = (size_t)P * (2 * sizeof(double) + sizeof(int)) + 16;
-    KF_CUDA(ctx, cudaFuncSetAttribute(kf_cd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KF_TRY(ensure_cd_smem(ctx, smem));
     KF_CUDA(ctx, ctx->d_K3.ensure((size_t)(4 * Pp + 8) * sizeof(double) + (size_t)(Pp + 4) * sizeof(int)));
     double* dG = ctx->d_K3.as<double>();
     double* c_l1 = dG + Pp;

@@ -268,6 +268,115 @@ __global__ void __launch_bounds__(256) kf_pcholb_col_kernel(double* W, long long
     dots[i] = fma(l, l, dots[i]);
 }
 
+// ---- v2 of the in-block column step: three small grid-parallel kernels per column instead of one
+// single-CTA kernel whose strided row swap cost 22 us (profiles/r01_launch_list_summary.txt).
+// dcur[i] is the current Schur-complement diagonal (contiguous, so the pivot search is coalesced).
+struct PcholStep {   // lives right after PcholState in device memory
+    int p;           // pivot row of the current column (-1: stop)
+    int pad;
+    double ljj;      // L(j,j)
+};
+
+__global__ void kf_pchol_diag_kernel(const double* __restrict__ W, long long ld, int P, double* dcur) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) dcur[i] = W[(long long)i * ld + i];
+}
+
+__global__ void __launch_bounds__(1024) kf_pcholc_argmax_kernel(int P, int j, int* perm, double* dcur, PcholState* st,
+                                                                PcholStep* step, double tol2) {
+    if (st->done) {
+        if (threadIdx.x == 0) step->p = -1;
+        return;
+    }
+    __shared__ double sval[32];
+    __shared__ int sidx[32];
+    const int tid = threadIdx.x;
+    double best = -1.0;
+    int bi = P;
+    for (int i = j + tid; i < P; i += blockDim.x) {
+        const double v = dcur[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { sval[tid >> 5] = best; sidx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+        best = (tid < (blockDim.x >> 5)) ? sval[tid] : -1.0;
+        bi = (tid < (blockDim.x >> 5)) ? sidx[tid] : P;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (tid == 0) {
+            if (j == 0) st->piv0 = best;
+            const bool ok = (best > 0.0) && (best > tol2 * st->piv0);
+            if (!ok) {
+                st->rank = j;
+                st->done = 1;
+                step->p = -1;
+            } else {
+                step->p = bi;
+                step->ljj = sqrt(best);
+                st->minpiv = best;
+                st->rank = j + 1;
+                if (bi != j) {
+                    const int a = perm[j];
+                    perm[j] = perm[bi];
+                    perm[bi] = a;
+                    const double d = dcur[j];
+                    dcur[j] = dcur[bi];
+                    dcur[bi] = d;
+                }
+            }
+        }
+    }
+}
+
+// symmetric permutation j <-> p of the full matrix, one thread per index i
+__global__ void __launch_bounds__(256) kf_pcholc_swap_kernel(double* W, long long ld, int P, int j, const PcholStep* step) {
+    const int p = step->p;
+    if (p < 0 || p == j) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (i != j && i != p) {
+        double a = W[(long long)j * ld + i], b = W[(long long)p * ld + i];   // column entries (i,j) <-> (i,p)
+        W[(long long)j * ld + i] = b;
+        W[(long long)p * ld + i] = a;
+        a = W[(long long)i * ld + j];                                         // row entries (j,i) <-> (p,i)
+        b = W[(long long)i * ld + p];
+        W[(long long)i * ld + j] = b;
+        W[(long long)i * ld + p] = a;
+    } else if (i == j) {                                                      // the 2 x 2 intersection
+        double a = W[(long long)j * ld + j], b = W[(long long)p * ld + p];
+        W[(long long)j * ld + j] = b;
+        W[(long long)p * ld + p] = a;
+        a = W[(long long)p * ld + j];
+        b = W[(long long)j * ld + p];
+        W[(long long)p * ld + j] = b;
+        W[(long long)j * ld + p] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256) kf_pcholc_col_kernel(double* W, long long ld, int P, int j, int j0, double* dcur,
+                                                            const PcholStep* step) {
+    if (step->p < 0) return;
+    const double ljj = step->ljj;
+    const int i = j + 1 + blockIdx.x * 256 + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) W[(long long)j * ld + j] = ljj;
+    if (i >= P) return;
+    double v = W[(long long)j * ld + i];
+    for (int k = j0; k < j; ++k) v = fma(-W[(long long)k * ld + i], W[(long long)k * ld + j], v);
+    const double l = v / ljj;
+    W[(long long)j * ld + i] = l;
+    W[(long long)i * ld + j] = l;
+    dcur[i] = fma(-l, l, dcur[i]);
+}
+
 __global__ void kf_zero_kernel(double* p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0.0;
@@ -480,16 +589,18 @@ int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, double* W, const double* C, dou
     } else {
         // blocked (dpstrf structure): left-looking inside a 64-column block, DMMA trailing update per block
         KF_CUDA(ctx, ctx->d_K3.ensure((size_t)(4 * Pp + 8) * sizeof(double) + (size_t)(Pp + 4) * sizeof(int)));
-        double* dots = ctx->d_K3.as<double>();
+        double* dcur = ctx->d_K3.as<double>();
+        PcholStep* d_step = reinterpret_cast<PcholStep*>(d_state + 1);
         for (int j0 = 0; j0 < P; j0 += PCHOL_NB) {
             const int j1 = std::min(P, j0 + PCHOL_NB);
-            kf_zero_kernel<<<(P + 255) / 256, 256, 0, st>>>(dots, P);
+            kf_pchol_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(W, ld, P, dcur);   // Schur diagonal at block start
             for (int j = j0; j < j1; ++j) {
-                kf_pcholb_pivot_kernel<<<1, 1024, 0, st>>>(W, ld, P, j, j0, d_perm, dots, d_state, tol2);
+                kf_pcholc_argmax_kernel<<<1, 1024, 0, st>>>(P, j, d_perm, dcur, d_state, d_step, tol2);
+                kf_pcholc_swap_kernel<<<(P + 255) / 256, 256, 0, st>>>(W, ld, P, j, d_step);
                 const int rem = P - j - 1;
-                if (rem > 0) kf_pcholb_col_kernel<<<(rem + 255) / 256, 256, 0, st>>>(W, ld, P, j, j0, dots, d_state);
+                kf_pcholc_col_kernel<<<std::max(1, (rem + 255) / 256), 256, 0, st>>>(W, ld, P, j, j0, dcur, d_step);
             }
-            ctx->launches += 1 + 2LL * (j1 - j0);
+            ctx->launches += 1 + 3LL * (j1 - j0);
             if (j1 < P) {
                 KfGemmGrid g{};
                 g.A = W + (long long)j1 * ld;   // A[m][c] = W(c, j1+m) = L(j1+m, c): mirrored copy, c contiguous
