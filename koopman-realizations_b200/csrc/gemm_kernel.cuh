@@ -47,6 +47,106 @@ struct Cfg {
     static_assert(BM * (BK / 2) % THREADS == 0 && BN * (BK / 2) % THREADS == 0, "loader mapping");
 };
 
+// one pipeline stage of DMMAs: acc += sum over the BK k-values of the stage of (A row) x (w * B row)
+template <class C, bool WEIGHTED>
+__device__ __forceinline__ void mma_stage(const double* as, const double* bs, const double* ws,
+                                          double (&acc)[C::MI][C::NJ][2]) {
+    constexpr int BK = C::BK, LDSP = C::LDSP, MI = C::MI, NJ = C::NJ;
+    if constexpr (!C::VEC) {
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double a[MI], b[NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[i] = as[i * 8 * LDSP + kk * 4];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[j] = bs[j * 8 * LDSP + kk * 4];
+            if (WEIGHTED) {
+                const double w = ws[kk * 4];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) b[j] *= w;
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    } else {
+#pragma unroll
+        for (int k2 = 0; k2 < BK / 8; ++k2) {
+            double2 a[MI], b[NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double2*>(as + i * 8 * LDSP + k2 * 8);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double2*>(bs + j * 8 * LDSP + k2 * 8);
+            if (WEIGHTED) {
+                const double2 w = *reinterpret_cast<const double2*>(ws + k2 * 8);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    b[j].x *= w.x;
+                    b[j].y *= w.y;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+        }
+    }
+}
+
+// epilogue: thread holds (m = lane/4, n = 2*(lane%4)+{0,1}) of every 8x8 DMMA tile
+template <class C>
+__device__ __forceinline__ void store_tile(const KfGemmTask& t, const double (&acc)[C::MI][C::NJ][2], int a_row0, int b_row0,
+                                           int lane) {
+    const int m_base = a_row0 + (lane >> 2);
+    const int n_base = b_row0 + 2 * (lane & 3);
+    const bool vec = (t.ldn == 1);
+#pragma unroll
+    for (int i = 0; i < C::MI; ++i) {
+        const int m = m_base + i * 8;
+        if (m >= t.a_rows) continue;
+#pragma unroll
+        for (int j = 0; j < C::NJ; ++j) {
+            const int n = n_base + j * 8;
+            double v0 = t.alpha * acc[i][j][0], v1 = t.alpha * acc[i][j][1];
+            double* p = t.out + (long long)m * t.ldm + (long long)n * t.ldn;
+            if (vec && n + 1 < t.b_rows) {
+                double2* p2 = reinterpret_cast<double2*>(p);
+                if (t.accumulate) {
+                    double2 o = *p2;
+                    v0 += o.x;
+                    v1 += o.y;
+                }
+                *p2 = make_double2(v0, v1);
+            } else {
+                if (n < t.b_rows) {
+                    if (t.accumulate) v0 += p[0];
+                    p[0] = v0;
+                }
+                if (n + 1 < t.b_rows) {
+                    if (t.accumulate) v1 += p[t.ldn];
+                    p[t.ldn] = v1;
+                }
+            }
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void prefetch_out_tile(const KfGemmTask& t, int tid) {
+    // pull this tile's accumulator lines into L2 ahead of the read-modify-write epilogue
+    const char* o = reinterpret_cast<const char*>(t.out);
+    constexpr int LPR = C::BN * 8 / 128;   // 128-byte lines per output row
+    for (int l = tid; l < C::BM * LPR; l += C::THREADS)
+        prefetch_l2(o + ((size_t)(l / LPR) * t.ldm * 8) + (size_t)(l % LPR) * 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Body 1: per-thread cp.async (LDGSTS) pipeline, one __syncthreads per stage.
 template <class C, bool WEIGHTED, bool PREFETCH>
 __device__ __forceinline__ void gemm_tile_body(const KfGemmTask& t, double* smem) {
     constexpr int BK = C::BK, STAGES = C::STAGES, LDSP = C::LDSP, MI = C::MI, NJ = C::NJ;
@@ -56,7 +156,7 @@ __device__ __forceinline__ void gemm_tile_body(const KfGemmTask& t, double* smem
     double* Bs = smem + STAGES * C::A_STAGE;
     double* Ws = Bs + STAGES * C::B_STAGE;
 
-    // global->shared assignment: 128 rows x BK/2 sixteen-byte chunks per operand per stage
+    // global->shared assignment: rows x BK/2 sixteen-byte chunks per operand per stage
     constexpr int CPR = BK / 2;   // chunks per row
     const double* a_src[C::CHUNKS_A];
     const double* b_src[C::CHUNKS_B];
@@ -102,97 +202,125 @@ __device__ __forceinline__ void gemm_tile_body(const KfGemmTask& t, double* smem
             if (nxt < nk) load_stage(nxt % STAGES, nxt);
             cp_async_commit();
         }
-        if (PREFETCH && t.accumulate && t.ldn == 1 && kt == nk - 4) {
-            // pull this tile's accumulator lines into L2 ahead of the read-modify-write epilogue
-            const char* o = reinterpret_cast<const char*>(t.out);
-            constexpr int LPR = C::BN * 8 / 128;   // 128-byte lines per output row
-            for (int l = tid; l < C::BM * LPR; l += C::THREADS)
-                prefetch_l2(o + ((size_t)(l / LPR) * t.ldm * 8) + (size_t)(l % LPR) * 128);
-        }
+        if (PREFETCH && t.accumulate && t.ldn == 1 && kt == nk - 4) prefetch_out_tile<C>(t, tid);
         const int stage = kt % STAGES;
-        const double* as = As + stage * C::A_STAGE + a_row0 * LDSP + fr;
-        const double* bs = Bs + stage * C::B_STAGE + b_row0 * LDSP + fr;
-        const double* ws = Ws + stage * BK + (C::VEC ? 2 * (lane & 3) : (lane & 3));
-        if constexpr (!C::VEC) {
-#pragma unroll
-            for (int kk = 0; kk < BK / 4; ++kk) {
-                double a[MI], b[NJ];
-#pragma unroll
-                for (int i = 0; i < MI; ++i) a[i] = as[i * 8 * LDSP + kk * 4];
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) b[j] = bs[j * 8 * LDSP + kk * 4];
-                if (WEIGHTED) {
-                    const double w = ws[kk * 4];
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) b[j] *= w;
-                }
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-        } else {
-#pragma unroll
-            for (int k2 = 0; k2 < BK / 8; ++k2) {
-                double2 a[MI], b[NJ];
-#pragma unroll
-                for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double2*>(as + i * 8 * LDSP + k2 * 8);
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double2*>(bs + j * 8 * LDSP + k2 * 8);
-                if (WEIGHTED) {
-                    const double2 w = *reinterpret_cast<const double2*>(ws + k2 * 8);
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        b[j].x *= w.x;
-                        b[j].y *= w.y;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
-            }
-        }
+        mma_stage<C, WEIGHTED>(As + stage * C::A_STAGE + a_row0 * LDSP + fr, Bs + stage * C::B_STAGE + b_row0 * LDSP + fr,
+                               Ws + stage * BK + (C::VEC ? 2 * (lane & 3) : (lane & 3)), acc);
     }
     cp_async_wait<0>();
+    store_tile<C>(t, acc, a_row0, b_row0, lane);
+}
 
-    // epilogue: thread holds (m = lane/4, n = 2*(lane%4)+{0,1}) of every 8x8 DMMA tile
-    const int m_base = a_row0 + (lane >> 2);
-    const int n_base = b_row0 + 2 * (lane & 3);
-    const bool vec = (t.ldn == 1);
+// ------------------------------------------------------------------------------------------------
+// Body 2: TMA bulk-copy pipeline (cp.async.bulk, SASS UBLKCP) with mbarrier full/empty rings.
+// Warp 0 is the producer: it issues one 1-D bulk copy per operand row per stage (BK doubles = 128 B
+// into the padded shared row) and arms the stage's `full` barrier with the byte count; every warp
+// waits on `full`, runs the stage's DMMAs, and one lane per warp arrives on `empty`.  No per-thread
+// LDGSTS address arithmetic and no CTA-wide barrier in the main loop.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <class C>
+constexpr size_t bulk_smem_bytes() {
+    return C::SMEM + 2 * C::STAGES * sizeof(uint64_t);
+}
+
+template <class C, bool WEIGHTED, bool PREFETCH>
+__device__ __forceinline__ void gemm_tile_body_bulk(const KfGemmTask& t, double* smem) {
+    constexpr int BK = C::BK, STAGES = C::STAGES, LDSP = C::LDSP, MI = C::MI, NJ = C::NJ;
+    constexpr int NWARPS = C::THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / C::WN, wn = warp % C::WN;
+    double* As = smem;
+    double* Bs = smem + STAGES * C::A_STAGE;
+    double* Ws = Bs + STAGES * C::B_STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(Ws + STAGES * BK);
+    uint64_t* empty = full + STAGES;
+    const int nk = (t.k1 - t.k0) / BK;
+
+    if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < MI; ++i) {
-        const int m = m_base + i * 8;
-        if (m >= t.a_rows) continue;
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, NWARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    constexpr unsigned ROW_BYTES = BK * sizeof(double);
+    constexpr unsigned STAGE_BYTES = (C::BM + C::BN) * ROW_BYTES + (WEIGHTED ? ROW_BYTES : 0);
+    auto produce = [&](int kt) {   // warp 0 only
+        const int stage = kt % STAGES;
+        const int k = t.k0 + kt * BK;
+        if (lane == 0) mbar_expect_tx(full + stage, STAGE_BYTES);
+        __syncwarp();
+        double* as = As + stage * C::A_STAGE;
+        double* bs = Bs + stage * C::B_STAGE;
+        for (int r = lane; r < C::BM; r += 32)
+            bulk_copy_g2s(as + r * LDSP, t.A + (long long)min(r, t.a_rows - 1) * t.lda + k, ROW_BYTES, full + stage);
+        for (int r = lane; r < C::BN; r += 32)
+            bulk_copy_g2s(bs + r * LDSP, t.B + (long long)min(r, t.b_rows - 1) * t.ldb + k, ROW_BYTES, full + stage);
+        if (WEIGHTED && lane == 0) bulk_copy_g2s(Ws + stage * BK, t.W + k, ROW_BYTES, full + stage);
+    };
+
+    double acc[MI][NJ][2];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int n = n_base + j * 8;
-            double v0 = t.alpha * acc[i][j][0], v1 = t.alpha * acc[i][j][1];
-            double* p = t.out + (long long)m * t.ldm + (long long)n * t.ldn;
-            if (vec && n + 1 < t.b_rows) {
-                double2* p2 = reinterpret_cast<double2*>(p);
-                if (t.accumulate) {
-                    double2 o = *p2;
-                    v0 += o.x;
-                    v1 += o.y;
-                }
-                *p2 = make_double2(v0, v1);
-            } else {
-                if (n < t.b_rows) {
-                    if (t.accumulate) v0 += p[0];
-                    p[0] = v0;
-                }
-                if (n + 1 < t.b_rows) {
-                    if (t.accumulate) v1 += p[t.ldn];
-                    p[t.ldn] = v1;
-                }
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    if (warp == 0)
+        for (int s = 0; s < STAGES - 1 && s < nk; ++s) produce(s);
+
+    const int fr = (lane >> 2) * LDSP + (C::VEC ? 2 * (lane & 3) : (lane & 3));
+    const int a_row0 = wm * (C::BM / C::WM), b_row0 = wn * (C::BN / C::WN);
+    for (int kt = 0; kt < nk; ++kt) {
+        const int stage = kt % STAGES;
+        if (warp == 0) {
+            // refill the slot consumed at iteration kt-1 with tile kt+STAGES-1 once every warp has released it
+            const int nxt = kt + STAGES - 1;
+            if (nxt < nk) {
+                if (kt > 0) mbar_wait(empty + (nxt % STAGES), ((kt - 1) / STAGES) & 1);
+                produce(nxt);
             }
         }
+        mbar_wait(full + stage, (kt / STAGES) & 1);
+        if (PREFETCH && t.accumulate && t.ldn == 1 && kt == nk - 4) prefetch_out_tile<C>(t, tid);
+        mma_stage<C, WEIGHTED>(As + stage * C::A_STAGE + a_row0 * LDSP + fr, Bs + stage * C::B_STAGE + b_row0 * LDSP + fr,
+                               Ws + stage * BK + (C::VEC ? 2 * (lane & 3) : (lane & 3)), acc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);
     }
+    store_tile<C>(t, acc, a_row0, b_row0, lane);
 }
 
 }  // namespace kfg

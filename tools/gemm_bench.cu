@@ -7,12 +7,17 @@
 #include <vector>
 #include "../koopman-realizations_b200/csrc/gemm_kernel.cuh"
 
-template <class C, bool W, bool PF>
+template <class C, bool W, bool PF, bool BULK = false>
 __global__ void __launch_bounds__(C::THREADS, C::MINB) bench_kernel(const KfGemmTask* __restrict__ tasks) {
     extern __shared__ __align__(16) double smem[];
     const KfGemmTask t = tasks[blockIdx.x];
-    if (W && t.W == nullptr) { kfg::gemm_tile_body<C, false, PF>(t, smem); return; }
-    kfg::gemm_tile_body<C, W, PF>(t, smem);
+    if constexpr (BULK) {
+        if (W && t.W == nullptr) { kfg::gemm_tile_body_bulk<C, false, PF>(t, smem); return; }
+        kfg::gemm_tile_body_bulk<C, W, PF>(t, smem);
+    } else {
+        if (W && t.W == nullptr) { kfg::gemm_tile_body<C, false, PF>(t, smem); return; }
+        kfg::gemm_tile_body<C, W, PF>(t, smem);
+    }
 }
 
 __global__ void fill(double* p, size_t n, unsigned seed) {
@@ -26,7 +31,7 @@ __global__ void checksum(const double* p, size_t n, double* out) {
     atomicAdd(out, s);
 }
 
-template <class C, bool W, bool PF>
+template <class C, bool W, bool PF, bool BULK = false>
 void run(const char* name, const std::vector<KfGemmTask>& base, int Mc, double* accum, size_t accum_n, double* d_sum) {
     // split every 128x128 tile into (128/BM) x (128/BN) CTA tasks
     std::vector<KfGemmTask> tasks;
@@ -43,24 +48,24 @@ void run(const char* name, const std::vector<KfGemmTask>& base, int Mc, double* 
     const int ntasks = (int)tasks.size();
     KfGemmTask* d_tasks; cudaMalloc(&d_tasks, tasks.size() * sizeof(KfGemmTask));
     cudaMemcpy(d_tasks, tasks.data(), tasks.size() * sizeof(KfGemmTask), cudaMemcpyHostToDevice);
-    cudaFuncSetAttribute(bench_kernel<C, W, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bench_kernel<C, W, PF>, C::THREADS, C::SMEM);
+    cudaFuncSetAttribute(bench_kernel<C, W, PF, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BULK ? kfg::bulk_smem_bytes<C>() : C::SMEM));
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bench_kernel<C, W, PF, BULK>, C::THREADS, (BULK ? kfg::bulk_smem_bytes<C>() : C::SMEM));
     cudaMemset(accum, 0, accum_n * 8);
-    bench_kernel<C, W, PF><<<ntasks, C::THREADS, C::SMEM>>>(d_tasks);
+    bench_kernel<C, W, PF, BULK><<<ntasks, C::THREADS, (BULK ? kfg::bulk_smem_bytes<C>() : C::SMEM)>>>(d_tasks);
     cudaMemset(d_sum, 0, 8);
     checksum<<<1, 1024>>>(accum, accum_n, d_sum);
     double h = 0; cudaMemcpy(&h, d_sum, 8, cudaMemcpyDeviceToHost);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { printf("%-40s ERROR %s\n", name, cudaGetErrorString(e)); cudaFree(d_tasks); return; }
-    bench_kernel<C, W, PF><<<ntasks, C::THREADS, C::SMEM>>>(d_tasks);
+    bench_kernel<C, W, PF, BULK><<<ntasks, C::THREADS, (BULK ? kfg::bulk_smem_bytes<C>() : C::SMEM)>>>(d_tasks);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int reps = 10;
     cudaEventRecord(e0);
-    for (int r = 0; r < reps; ++r) bench_kernel<C, W, PF><<<ntasks, C::THREADS, C::SMEM>>>(d_tasks);
+    for (int r = 0; r < reps; ++r) bench_kernel<C, W, PF, BULK><<<ntasks, C::THREADS, (BULK ? kfg::bulk_smem_bytes<C>() : C::SMEM)>>>(d_tasks);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
     double tf = (double)base.size() * 2.0 * 128 * 128 * Mc / ms / 1e9;
-    printf("%-40s thr=%4d smem=%6zu occ=%d ctas=%5d  %.3f ms  %.2f TF  checksum %.10e\n", name, C::THREADS, C::SMEM, occ, ntasks, ms, tf, h);
+    printf("%-40s thr=%4d smem=%6zu occ=%d ctas=%5d  %.3f ms  %.2f TF  checksum %.10e\n", name, C::THREADS, (BULK ? kfg::bulk_smem_bytes<C>() : C::SMEM), occ, ntasks, ms, tf, h);
     cudaFree(d_tasks);
 }
 
@@ -150,17 +155,14 @@ int main(int argc, char** argv) {
     probe<8, 4, true, true, true>("64x32 + LDS + sync + weights", accum);
     probe<4, 4, true, true, true>("32x32 + LDS + sync + weights", accum);
     probe<4, 2, true, true, true>("32x16 + LDS + sync + weights", accum);
-    run<Cfg<16, 4, 2, 4, false>, true, true>("128x128 BK16 S4 2x4 +pf (r1)", tasks, Mc, accum, an, d_sum);
-    run<Cfg<32, 2, 2, 4, true>, true, true>("128x128 BK32 S2 2x4 lds128 +pf", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 2, 2, false, 128, 64, 2>, true, true>("128x64 BK16 S3 2x2 occ2", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 2, 2, true, 128, 64, 2>, true, true>("128x64 BK16 S3 2x2 lds128 occ2", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 4, 2, 2, false, 64, 64, 3>, true, true>("64x64 BK16 S4 2x2 occ3", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 2, 2, false, 64, 64, 4>, true, true>("64x64 BK16 S3 2x2 occ4", tasks, Mc, accum, an, d_sum);
-    run<Cfg<32, 3, 2, 2, false, 64, 64, 3>, true, true>("64x64 BK32 S3 2x2 occ3", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 4, 2, 1, false, 64, 32, 6>, true, true>("64x32 BK16 S4 2x1 occ6", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 4, 2, 2, false, 64, 32, 4>, true, true>("64x32 BK16 S4 2x2(32x16) occ4", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 1, 4, false, 64, 128, 2>, true, true>("64x128 BK16 S3 1x4 occ2", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 4, 2, false, 128, 64, 1>, true, true>("128x64 BK16 S3 4x2(32x32) 8w occ1", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 4, 2, false, 128, 64, 2>, true, true>("128x64 BK16 S3 4x2(32x32) 8w occ2", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 2, 2, true, 128, 64, 2>, true, true>("128x64 BK16 S3 2x2 lds128 occ2 (prod)", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 1, 4, true, 128, 64, 2>, true, true>("128x64 BK16 S3 1x4(128x16) lds128 occ2", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 1, 4, false, 128, 64, 2>, true, true>("128x64 BK16 S3 1x4(128x16) lds64 occ2", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 2, 2, true, 128, 64, 2>, true, true, true>("BULK 128x64 BK16 S3 2x2 lds128 occ2", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 4, 2, 2, true, 128, 64, 2>, true, true, true>("BULK 128x64 BK16 S4 2x2 lds128 occ2", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 1, 4, true, 128, 64, 2>, true, true, true>("BULK 128x64 BK16 S3 1x4 lds128 occ2", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 2, 2, false, 128, 64, 2>, true, true, true>("BULK 128x64 BK16 S3 2x2 lds64 occ2", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 3, 2, 2, true, 128, 64, 2>, false, true, true>("BULK 128x64 S3 2x2 lds128 unweighted", tasks, Mc, accum, an, d_sum);
+    run<Cfg<16, 4, 2, 4, true, 128, 128, 1>, true, true, true>("BULK 128x128 BK16 S4 2x4 lds128 occ1", tasks, Mc, accum, an, d_sum);
     return 0;
 }
