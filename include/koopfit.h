@@ -90,6 +90,8 @@ typedef struct {
     double t_lift_gram_ms;  /* device time of lift + Gram */
     double t_solve_ms;      /* device time of the solve */
     double t_total_ms;      /* wall time of the call */
+    int qp_capped;          /* QP: inner coordinate-descent solves that hit the sweep bound (0 = all converged) */
+    int reserved;
 } kf_info;
 
 /* caller-allocated outputs; NULL members are skipped */
@@ -133,9 +135,9 @@ int kf_lift(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V,
  * LS or all nt budgets.  HOST pointers in `prob`; copies are inside the call. */
 int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out);
 
-/* Generic MATLAB `A \\ B` for a tall A (M x P) and B (M x Pc), HOST column-major buffers:
+/* Generic MATLAB `A \ B` for a tall A (M x P) and B (M x Pc), HOST column-major buffers:
  * Householder QR with column pivoting on the GPU, rank by max(size(A))*eps(|R11|), basic
- * solution X (P x Pc).  Replaces `Mtranspose = L \\ R` in get_model (Ksysid.m:1216).
+ * solution X (P x Pc).  Replaces `Mtranspose = L \ R` in get_model (Ksysid.m:1216).
  * perm (P ints) and rank may be NULL. */
 int kf_mldivide(kf_ctx* ctx, long long M, int P, int Pc, const double* A, const double* B, double* X, int* perm, int* rank);
 

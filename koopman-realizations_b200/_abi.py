@@ -51,7 +51,8 @@ class kf_solve(C.Structure):
 class kf_info(C.Structure):
     _fields_ = [("rank", C.c_int), ("ls_method_used", C.c_int), ("passes", C.c_int),
                 ("psd_shift_applied", C.c_int), ("min_pivot", C.c_double), ("max_pivot", C.c_double),
-                ("t_lift_gram_ms", C.c_double), ("t_solve_ms", C.c_double), ("t_total_ms", C.c_double)]
+                ("t_lift_gram_ms", C.c_double), ("t_solve_ms", C.c_double), ("t_total_ms", C.c_double),
+                ("qp_capped", C.c_int), ("reserved", C.c_int)]
 
 
 class kf_result(C.Structure):

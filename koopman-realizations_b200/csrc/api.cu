@@ -361,28 +361,56 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
             for (double v : target) pinned_l1 += std::fabs(v);
         }
         KF_CUDA(ctx, ctx->d_Kt.ensure(mat));
-        for (int it = 0; it < sv->nt; ++it) {
+        double* Kt = ctx->d_Kt.as<double>();
+        // the unconstrained minimiser with the pinned columns in place: ||.||_1 decides which budgets are active
+        if (c1 > c0)
+            KF_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_K.as<double>() + (size_t)c0 * Pp, (size_t)Pp * sizeof(double), target.data(),
+                                           (size_t)P * sizeof(double), (size_t)P * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, st));
+        KfQpResult ls{};
+        KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), &ls, st));
+        // budgets in ascending order: each active solve starts from the previous solution and multiplier
+        std::vector<int> order(sv->nt);
+        for (int i = 0; i < sv->nt; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return sv->t[a] < sv->t[b]; });
+        double lam_prev = 0, l1_prev_free = 0;
+        int capped = 0;
+        for (int oi = 0; oi < sv->nt; ++oi) {
+            const int it = order[oi];
             const double t_free = sv->t[it] - pinned_l1;
             if (t_free < 0) {
                 ctx->err = "L1 budget smaller than the pinned delay entries: the QP is infeasible";
                 return KF_ENUMERIC;
             }
-            double* Kt = ctx->d_Kt.as<double>();
-            KF_CUDA(ctx, cudaMemcpyAsync(Kt, ctx->d_K.p, mat, cudaMemcpyDeviceToDevice, st));   // warm start: LS minimiser
-            if (c1 > c0)
-                KF_CUDA(ctx, cudaMemcpy2DAsync(Kt + (size_t)c0 * Pp, (size_t)Pp * sizeof(double), target.data(), (size_t)P * sizeof(double),
-                                               (size_t)P * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, st));
             KfQpResult qr{};
-            KF_TRY(kf_solve_l1ball(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), t_free, c0, c1, nullptr, sv->qp_max_iter,
-                                   sv->qp_tol, Kt, &qr, st));
-            // objective and ||K||_1 over ALL columns (the pinned ones count towards the budget row, Ksysid.m:1136)
-            KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt, &qr, st));
+            const double* Kres = Kt;
+            if (ls.l1 <= sv->t[it]) {   // inactive budget: lam = 0, K = unconstrained minimiser
+                qr = ls;
+                qr.iters = 0;
+                Kres = ctx->d_K.as<double>();
+            } else {
+                if (lam_prev <= 0) {   // cold start (kf_solve_l1ball zeroes the free columns)
+                    if (c1 > c0)
+                        KF_CUDA(ctx, cudaMemcpy2DAsync(Kt + (size_t)c0 * Pp, (size_t)Pp * sizeof(double), target.data(), (size_t)P * sizeof(double),
+                                                       (size_t)P * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, st));
+                }
+                KF_TRY(kf_solve_l1ball(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), t_free, c0, c1, lam_prev,
+                                       l1_prev_free - t_free, sv->qp_max_iter, sv->qp_tol, Kt, &qr, st));
+                lam_prev = qr.lam;
+                l1_prev_free = qr.l1;
+                capped += qr.capped;
+                const int evals = qr.iters;
+                // objective and ||K||_1 over ALL columns (the pinned ones count towards the budget row, Ksysid.m:1136)
+                KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt, &qr, st));
+                qr.iters = evals;
+            }
             if (out->objective) out->objective[it] = qr.objective;
             if (out->l1norm) out->l1norm[it] = qr.l1;
             if (out->qp_iters) out->qp_iters[it] = qr.iters;
-            if (out->K) KF_TRY(copy_out_matrix(ctx, Kt, Pp, P, out->K + (size_t)it * P * P));
-            KF_CUDA(ctx, cudaStreamSynchronize(st));   // `target` and Kt are reused by the next budget
+            if (out->K) KF_TRY(copy_out_matrix(ctx, Kres, Pp, P, out->K + (size_t)it * P * P));
+            KF_CUDA(ctx, cudaStreamSynchronize(st));
         }
+        out->info.passes = 1;
+        out->info.qp_capped = capped;
         if (out->perm) KF_CUDA(ctx, cudaMemcpyAsync(out->perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
     }
     KF_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));

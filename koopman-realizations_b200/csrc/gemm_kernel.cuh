@@ -323,4 +323,145 @@ __device__ __forceinline__ void gemm_tile_body_bulk(const KfGemmTask& t, double*
     store_tile<C>(t, acc, a_row0, b_row0, lane);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Body 3: tensor-map TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) with SWIZZLE_128B.
+// The panel is described once by a 2-D tensor map (inner dim = snapshots, outer = observable rows,
+// box = 16 snapshots x 64 rows = 128-byte rows).  One elected thread issues 3 tensor copies + one
+// 128-byte weight copy per stage; shared rows are dense 128 B and XOR-swizzled by the TMA unit
+// (16-byte chunk c of row r lives at chunk c ^ (r & 7)).  To keep the LDS.128 fragment loads
+// conflict-free under that swizzle the DMMA row index g = lane/4 is mapped to tile row
+// (g >> 1) + 4 * (g & 1): the two rows of a quarter-warp then differ in bit 2 of (r & 7) and the
+// eight 16-byte chunks they touch fill the 128-byte bank window exactly once.  The same permutation
+// is applied to A rows, B rows and (inverted) in the epilogue.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <int STAGES_>
+struct TmaCfg {
+    static constexpr int BM = 128, BN = 64, BK = 16, STAGES = STAGES_, WM = 2, WN = 2, THREADS = 128, MINB = 2;
+    static constexpr int MI = BM / WM / 8, NJ = BN / WN / 8;
+    static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, W_BYTES = 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + 1024;          // weights in their own 1 KB slot (keeps 1 KB alignment)
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;   // + alignment slack
+};
+
+// task.A / task.B are interpreted as panel ROW indices (a_row, b_row), task.W as the weight row index + 1 (0 = none)
+struct KfTmaTask {
+    int a_row, b_row, w_row;   // w_row < 0: unweighted
+    int k0, k1;
+    int pad;
+    double* out;               // 128 x 64 sub-tile of a 128 x 128 accumulator tile (ldm = 128)
+    const double* W;           // weight row pointer (global) or nullptr
+};
+
+template <class C, bool WEIGHTED>
+__device__ __forceinline__ void gemm_tile_body_tma(const KfTmaTask& t, const void* tmap, unsigned char* smem_raw) {
+    constexpr int STAGES = C::STAGES, MI = C::MI, NJ = C::NJ, BK = C::BK;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / C::WN, wn = warp % C::WN;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * C::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    const int nk = (t.k1 - t.k0) / BK;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, C::THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    constexpr unsigned TX_BYTES = C::A_BYTES + C::B_BYTES + (WEIGHTED ? C::W_BYTES : 0);
+    auto produce = [&](int kt) {   // one elected thread
+        unsigned char* st = smem + (size_t)(kt % STAGES) * C::STAGE_BYTES;
+        uint64_t* bar = full + (kt % STAGES);
+        const int k = t.k0 + kt * BK;
+        mbar_expect_tx(bar, TX_BYTES);
+        tma_load_2d(st, tmap, k, t.a_row, bar);                         // A rows   0..63
+        tma_load_2d(st + 64 * 128, tmap, k, t.a_row + 64, bar);         // A rows  64..127
+        tma_load_2d(st + C::A_BYTES, tmap, k, t.b_row, bar);            // B rows   0..63
+        if (WEIGHTED) bulk_copy_g2s(st + C::A_BYTES + C::B_BYTES, t.W + k, C::W_BYTES, bar);
+    };
+
+    double acc[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    if (tid == 0)
+        for (int s = 0; s < STAGES - 1 && s < nk; ++s) produce(s);
+
+    // fragment addressing under SWIZZLE_128B
+    const int g = lane >> 2, q = lane & 3;
+    const int rp = (g >> 1) + 4 * (g & 1);                 // permuted row inside an 8-row group; also (row & 7)
+    const int a_row0 = wm * (C::BM / C::WM), b_row0 = wn * (C::BN / C::WN);
+    const int a_off = (a_row0 + rp) * 128, b_off = C::A_BYTES + (b_row0 + rp) * 128;
+    const int ch0 = ((0 * 4 + q) ^ rp) * 16, ch1 = ((1 * 4 + q) ^ rp) * 16;   // k2 = 0, 1
+
+    for (int kt = 0; kt < nk; ++kt) {
+        const int stage = kt % STAGES;
+        if (tid == 0) {
+            const int nxt = kt + STAGES - 1;
+            if (nxt < nk) {
+                if (kt > 0) mbar_wait(empty + (nxt % STAGES), ((kt - 1) / STAGES) & 1);
+                produce(nxt);
+            }
+        }
+        mbar_wait(full + stage, (kt / STAGES) & 1);
+        if (t.out && kt == nk - 4) {   // pull the accumulator sub-tile into L2 ahead of the RMW epilogue
+            const char* o = reinterpret_cast<const char*>(t.out);
+            for (int l = tid; l < C::BM * 4; l += C::THREADS) prefetch_l2(o + (size_t)(l >> 2) * 128 * 8 + (size_t)(l & 3) * 128);
+        }
+        const unsigned char* st = smem + (size_t)stage * C::STAGE_BYTES;
+        const double2 w0 = WEIGHTED ? *reinterpret_cast<const double2*>(st + C::A_BYTES + C::B_BYTES + (0 * 8 + 2 * q) * 8) : make_double2(1, 1);
+        const double2 w1 = WEIGHTED ? *reinterpret_cast<const double2*>(st + C::A_BYTES + C::B_BYTES + (1 * 8 + 2 * q) * 8) : make_double2(1, 1);
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+            const int ch = k2 ? ch1 : ch0;
+            double2 a[MI], b[NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double2*>(st + a_off + i * 8 * 128 + ch);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const double2*>(st + b_off + j * 8 * 128 + ch);
+            if (WEIGHTED) {
+                const double2 w = k2 ? w1 : w0;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    b[j].x *= w.x;
+                    b[j].y *= w.y;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);
+    }
+    // epilogue (accumulate into the 128-wide accumulator tile): DMMA (m = g, n = 2q + e) -> tile (row rp(g), col rp(2q+e))
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int m = a_row0 + i * 8 + rp;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            double* p = t.out + (size_t)m * 128 + b_row0 + j * 8;
+            p[q] += acc[i][j][0];          // n index 2q   -> column q
+            p[q + 4] += acc[i][j][1];      // n index 2q+1 -> column q + 4
+        }
+    }
+}
+
 }  // namespace kfg

@@ -183,8 +183,8 @@ int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long lon
                    int* d_perm, int* rank_out, double* min_piv, double* max_piv, cudaStream_t st);
 
 // qp.cu
-struct KfQpResult { double objective; double l1; int iters; };
+struct KfQpResult { double objective; double l1; int iters; double lam; int capped; };
 int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, double t, int fix_c0, int fix_c1,
-                    const double* d_fix_target, int max_iter, double tol, double* K, KfQpResult* res, cudaStream_t st);
+                    double lam_start, double phi_start, int max_iter, double tol, double* K, KfQpResult* res, cudaStream_t st);
 int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_t st);
 int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, KfQpResult* res, cudaStream_t st);

@@ -254,11 +254,13 @@ int ensure_cd_smem(kf_ctx* ctx, size_t smem) {
 
 }  // namespace
 
-// Solve one budget t.  G (possibly shifted), C: Pp-strided P x P; K: warm start in, solution out.
-// fix columns [fix_c0, fix_c1) hold the pinned delay pattern already written into K by the caller;
-// t_free = t - ||pinned||_1 is what `t` means here.
+// Solve one ACTIVE budget t (the caller has checked that the unconstrained minimiser violates it).
+// G (possibly shifted), C: Pp-strided P x P.  K: warm start in / solution out.  Columns [fix_c0, fix_c1) hold the
+// pinned delay pattern (already in K); `t` is the budget left for the free columns.
+// lam_start > 0: an upper bracket from the previous (smaller) budget of an ascending sweep, with K = K(lam_start)
+// and phi_start = ||K||_1 - t < 0; lam_start <= 0: cold start from lam_max with K = 0.
 int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, double t, int fix_c0, int fix_c1,
-                    const double* /*d_fix_target*/, int max_iter, double tol, double* K, KfQpResult* res, cudaStream_t st) {
+                    double lam_start, double phi_start, int max_iter, double tol, double* K, KfQpResult* res, cudaStream_t st) {
     const long long ld = Pp;
     const size_t smem = (size_t)P * (2 * sizeof(double) + sizeof(int)) + 16;
     KF_TRY(ensure_cd_smem(ctx, smem));
@@ -275,15 +277,13 @@ int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C
     double* D = ctx->d_K2.as<double>();
 
     kf_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(G, ld, P, 0.0, nullptr, dG);
-    kf_absmax_kernel<<<1, 1024, 0, st>>>(C, ld, P, P, fix_c0, fix_c1, d_out);
-    double lam_max = 0;
-    KF_CUDA(ctx, cudaMemcpyAsync(&lam_max, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
-    KF_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->launches += 2;
+    ctx->launches += 1;
 
-    const int max_sweeps = max_iter > 0 ? max_iter : 100000;
+    // inner sweeps per evaluation are bounded so that an ill-conditioned Gram cannot run away; a column that
+    // hits the bound is reported through res->capped
+    const int max_sweeps = max_iter > 0 ? max_iter : (P <= 256 ? 100000 : 2000);
     const double cd_tol = tol > 0 ? tol : 1e-13;
-    int evals = 0;
+    int evals = 0, capped = 0;
     double h[4];
     auto run_cd = [&](int mode, double lam, double* Kout, const double* K0) -> int {
         CdArgs a{};
@@ -299,23 +299,29 @@ int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C
         KF_CUDA(ctx, cudaStreamSynchronize(st));
         ctx->launches += 2;
         ++evals;
+        if (mode != 2 && h[3] >= max_sweeps) ++capped;
         return KF_OK;
     };
 
-    // 1. is the budget inactive?  The caller passes the unconstrained minimiser as the warm start in K.
-    KF_TRY(run_cd(2, 0.0, K, nullptr));
-    if (h[0] <= t) {
-        res->objective = h[1];
-        res->l1 = h[0];
-        res->iters = evals;
-        return KF_OK;
+    double lam_hi, phi_hi, lam_lo = 0, phi_lo = 0, lam;
+    if (lam_start > 0) {
+        lam_hi = lam_start;
+        phi_hi = phi_start;
+    } else {
+        kf_absmax_kernel<<<1, 1024, 0, st>>>(C, ld, P, P, fix_c0, fix_c1, d_out);
+        double lam_max = 0;
+        KF_CUDA(ctx, cudaMemcpyAsync(&lam_max, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->launches += 1;
+        lam_hi = lam_max;   // K(lam_max) = 0
+        phi_hi = -t;
+        if (fix_c0 > 0) KF_CUDA(ctx, cudaMemset2DAsync(K, ld * sizeof(double), 0, (size_t)P * sizeof(double), fix_c0, st));
+        if (fix_c1 < P)   // the pinned columns [fix_c0, fix_c1) keep their pattern
+            KF_CUDA(ctx, cudaMemset2DAsync(K + (size_t)std::max(fix_c1, 0) * ld, ld * sizeof(double), 0, (size_t)P * sizeof(double),
+                                           P - std::max(fix_c1, 0), st));
     }
-    // 2. bracket lam: phi(lam_max) = -t < 0; halve until phi > 0 (warm-started from K = 0)
-    if (fix_c0 > 0) KF_CUDA(ctx, cudaMemset2DAsync(K, ld * sizeof(double), 0, (size_t)P * sizeof(double), fix_c0, st));
-    if (fix_c1 < P)   // the pinned columns [fix_c0, fix_c1) keep their pattern
-        KF_CUDA(ctx, cudaMemset2DAsync(K + (size_t)std::max(fix_c1, 0) * ld, ld * sizeof(double), 0, (size_t)P * sizeof(double),
-                                       P - std::max(fix_c1, 0), st));
-    double lam_hi = lam_max, phi_hi = -t, lam_lo = 0, phi_lo = 0, lam = lam_max;
+    // 1. bracket: shrink lam geometrically (warm-started) until ||K||_1 > t
+    lam = lam_hi;
     bool bracket = false;
     for (int it = 0; it < 200; ++it) {
         lam *= 0.5;
@@ -326,13 +332,15 @@ int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C
         if (lam < 1e-300) break;
     }
     if (bracket) {
+        // 2. Illinois secant on phi(lam) = ||K(lam)||_1 - t; the exact step below removes the remaining error,
+        //    so a modest tolerance is enough here
         int side = 0;
-        for (int it = 0; it < 200; ++it) {
+        for (int it = 0; it < 60; ++it) {
             lam = (lam_lo * phi_hi - lam_hi * phi_lo) / (phi_hi - phi_lo);
             if (!(lam > lam_lo && lam < lam_hi)) lam = 0.5 * (lam_lo + lam_hi);
             KF_TRY(run_cd(0, lam, K, nullptr));
             const double phi = h[0] - t;
-            if (fabs(phi) <= 1e-12 * t) break;
+            if (fabs(phi) <= 1e-10 * t) break;
             if (phi > 0) {
                 lam_lo = lam; phi_lo = phi;
                 if (side == 1) phi_hi *= 0.5;
@@ -342,7 +350,7 @@ int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C
                 if (side == -1) phi_lo *= 0.5;
                 side = -1;
             }
-            if (lam_hi - lam_lo <= 1e-15 * lam_hi) break;
+            if (lam_hi - lam_lo <= 1e-14 * lam_hi) break;
         }
         // 3. exact last step on the fixed sign pattern: D = dK/dlam, ||K(lam + dl)||_1 = ||K||_1 - dl * sum s'd
         const double l1_0 = h[0];
@@ -371,6 +379,8 @@ int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C
     res->objective = h[1];
     res->l1 = h[0];
     res->iters = evals;
+    res->lam = lam;
+    res->capped = capped;
     return KF_OK;
 }
 

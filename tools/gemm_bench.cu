@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../koopman-realizations_b200/csrc/gemm_kernel.cuh"
+#include "../koopman-realizations_b200/csrc/tma_host.h"
 
 template <class C, bool W, bool PF, bool BULK = false>
 __global__ void __launch_bounds__(C::THREADS, C::MINB) bench_kernel(const KfGemmTask* __restrict__ tasks) {
@@ -66,6 +67,54 @@ void run(const char* name, const std::vector<KfGemmTask>& base, int Mc, double* 
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
     double tf = (double)base.size() * 2.0 * 128 * 128 * Mc / ms / 1e9;
     printf("%-40s thr=%4d smem=%6zu occ=%d ctas=%5d  %.3f ms  %.2f TF  checksum %.10e\n", name, C::THREADS, (BULK ? kfg::bulk_smem_bytes<C>() : C::SMEM), occ, ntasks, ms, tf, h);
+    cudaFree(d_tasks);
+}
+
+template <class C, bool W>
+__global__ void __launch_bounds__(C::THREADS, C::MINB) tma_kernel(const kfg::KfTmaTask* __restrict__ tasks, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const kfg::KfTmaTask t = tasks[blockIdx.x];
+    if (W && t.W == nullptr) { kfg::gemm_tile_body_tma<C, false>(t, &tmap, smem_raw); return; }
+    kfg::gemm_tile_body_tma<C, W>(t, &tmap, smem_raw);
+}
+
+template <class C>
+void run_tma(const char* name, const std::vector<KfGemmTask>& base, double* panel, int rows, int Mc, double* accum, size_t accum_n, double* d_sum) {
+    CUtensorMap tmap;
+    int rc = kf_make_panel_tensor_map(&tmap, panel, Mc, rows);
+    if (rc) { printf("%-40s tensor map encode failed rc=%d\n", name, rc); return; }
+    std::vector<kfg::KfTmaTask> tasks;
+    for (const auto& b : base)
+        for (int sn = 0; sn < 2; ++sn) {
+            kfg::KfTmaTask g{};
+            g.a_row = (int)((b.A - panel) / Mc);
+            g.b_row = (int)((b.B - panel) / Mc) + sn * 64;
+            g.W = b.W; g.w_row = b.W ? 0 : -1;
+            g.k0 = 0; g.k1 = Mc;
+            g.out = b.out + sn * 64;
+            tasks.push_back(g);
+        }
+    const int ntasks = (int)tasks.size();
+    kfg::KfTmaTask* d_tasks; cudaMalloc(&d_tasks, tasks.size() * sizeof(kfg::KfTmaTask));
+    cudaMemcpy(d_tasks, tasks.data(), tasks.size() * sizeof(kfg::KfTmaTask), cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(tma_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tma_kernel<C, true>, C::THREADS, C::SMEM);
+    cudaMemset(accum, 0, accum_n * 8);
+    tma_kernel<C, true><<<ntasks, C::THREADS, C::SMEM>>>(d_tasks, tmap);
+    cudaMemset(d_sum, 0, 8);
+    checksum<<<1, 1024>>>(accum, accum_n, d_sum);
+    double h = 0; cudaMemcpy(&h, d_sum, 8, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { printf("%-40s ERROR %s\n", name, cudaGetErrorString(e)); cudaFree(d_tasks); return; }
+    tma_kernel<C, true><<<ntasks, C::THREADS, C::SMEM>>>(d_tasks, tmap);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int reps = 10;
+    cudaEventRecord(e0);
+    for (int r = 0; r < reps; ++r) tma_kernel<C, true><<<ntasks, C::THREADS, C::SMEM>>>(d_tasks, tmap);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+    double tf = (double)base.size() * 2.0 * 128 * 128 * Mc / ms / 1e9;
+    printf("%-40s thr=%4d smem=%6zu occ=%d ctas=%5d  %.3f ms  %.2f TF  checksum %.10e\n", name, C::THREADS, (size_t)C::SMEM, occ, ntasks, ms, tf, h);
     cudaFree(d_tasks);
 }
 
@@ -156,13 +205,8 @@ int main(int argc, char** argv) {
     probe<4, 4, true, true, true>("32x32 + LDS + sync + weights", accum);
     probe<4, 2, true, true, true>("32x16 + LDS + sync + weights", accum);
     run<Cfg<16, 3, 2, 2, true, 128, 64, 2>, true, true>("128x64 BK16 S3 2x2 lds128 occ2 (prod)", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 1, 4, true, 128, 64, 2>, true, true>("128x64 BK16 S3 1x4(128x16) lds128 occ2", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 1, 4, false, 128, 64, 2>, true, true>("128x64 BK16 S3 1x4(128x16) lds64 occ2", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 2, 2, true, 128, 64, 2>, true, true, true>("BULK 128x64 BK16 S3 2x2 lds128 occ2", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 4, 2, 2, true, 128, 64, 2>, true, true, true>("BULK 128x64 BK16 S4 2x2 lds128 occ2", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 1, 4, true, 128, 64, 2>, true, true, true>("BULK 128x64 BK16 S3 1x4 lds128 occ2", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 2, 2, false, 128, 64, 2>, true, true, true>("BULK 128x64 BK16 S3 2x2 lds64 occ2", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 3, 2, 2, true, 128, 64, 2>, false, true, true>("BULK 128x64 S3 2x2 lds128 unweighted", tasks, Mc, accum, an, d_sum);
-    run<Cfg<16, 4, 2, 4, true, 128, 128, 1>, true, true, true>("BULK 128x128 BK16 S4 2x4 lds128 occ1", tasks, Mc, accum, an, d_sum);
+    run_tma<kfg::TmaCfg<3>>("TMA tensor-map swz128 128x64 S3 occ2", tasks, panel, rows, Mc, accum, an, d_sum);
+    run_tma<kfg::TmaCfg<4>>("TMA tensor-map swz128 128x64 S4 occ2", tasks, panel, rows, Mc, accum, an, d_sum);
+    run_tma<kfg::TmaCfg<6>>("TMA tensor-map swz128 128x64 S6 occ1?", tasks, panel, rows, Mc, accum, an, d_sum);
     return 0;
 }
