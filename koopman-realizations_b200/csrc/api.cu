@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "kf_internal.h"
+#include "tma_host.h"
 
 namespace {
 
@@ -127,8 +128,10 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
     // task lists, one per panel buffer
     const int per = (ksteps + nsplit - 1) / nsplit;
     std::vector<KfGemmTask> tasks;
+    std::vector<KfTmaTask> ttasks;
     for (int b = 0; b < 2; ++b) {
         tasks.clear();
+        ttasks.clear();
         double* panel = ctx->d_panel[b].as<double>();
         for (int s = 0; s < nsplit; ++s) {
             const int k0 = std::min(s * per, ksteps) * KF_BK, k1 = std::min((s + 1) * per, ksteps) * KF_BK;
@@ -154,10 +157,28 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
                         g.alpha = 1.0;
                         g.accumulate = 1;
                         tasks.push_back(g);
+                        KfTmaTask tt{};   // same CTA task for the tensor-map TMA kernel (128 x 64 sub-tile)
+                        tt.a_row = L.x_off + tl.tm * KF_BM + sm * KF_CTA_M;
+                        tt.b_row = (tl.kind == 0 ? L.x_off : L.y_off) + tl.tn * KF_BN + sn * KF_CTA_N;
+                        tt.w_row = tl.q > 0 ? L.w_off + tl.q : -1;
+                        tt.k0 = k0;
+                        tt.k1 = k1;
+                        tt.out = g.out;
+                        tt.W = g.W;
+                        ttasks.push_back(tt);
                     }
         }
         KF_CUDA(ctx, ctx->d_tasks[b].ensure(sizeof(KfGemmTask) * tasks.size()));
         KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tasks[b].p, tasks.data(), sizeof(KfGemmTask) * tasks.size(), cudaMemcpyHostToDevice, ctx->stream));
+        KF_CUDA(ctx, ctx->d_tma_tasks[b].ensure(sizeof(KfTmaTask) * ttasks.size()));
+        KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tma_tasks[b].p, ttasks.data(), sizeof(KfTmaTask) * ttasks.size(), cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->opt_tma) {
+            const int rc = kf_make_panel_tensor_map(&ctx->tmap[b], panel, (unsigned long long)L.Mc, (unsigned long long)L.rows);
+            if (rc) {
+                ctx->err = "cuTensorMapEncodeTiled failed for the lifted panel (rc=" + std::to_string(rc) + ")";
+                return KF_ECUDA;
+            }
+        }
         KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     ctx->lay = L;
@@ -234,7 +255,10 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
             }
             KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], sg));
         }
-        KF_TRY(kf_launch_gemm_tasks(ctx, ctx->d_tasks[b].as<KfGemmTask>(), ntasks, weighted, sg));
+        if (ctx->opt_tma)
+            KF_TRY(kf_launch_gram_tma(ctx, ctx->d_tma_tasks[b].as<KfTmaTask>(), ntasks, weighted, ctx->tmap[b], sg));
+        else
+            KF_TRY(kf_launch_gemm_tasks(ctx, ctx->d_tasks[b].as<KfGemmTask>(), ntasks, weighted, sg));
         if (sample) {
             KF_CUDA(ctx, cudaEventRecord(ctx->ev[3], sg));
             if (overlap) KF_CUDA(ctx, cudaStreamWaitEvent(S[1 - b], ctx->ev[3], 0));
@@ -478,7 +502,7 @@ void kf_destroy(kf_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_full,
-                     &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
+                     &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt};
     for (KfBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i)
@@ -738,6 +762,7 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "overlap") ctx->opt_overlap = (int)value;
     else if (n == "panel_mb") ctx->opt_panel_mb = value;
     else if (n == "profile") ctx->opt_profile = (int)value;
+    else if (n == "tma") ctx->opt_tma = (int)value;
     else if (n == "qr_max_gb") ctx->opt_qr_max_gb = value;
     else {
         ctx->err = "kf_set_option: unknown option " + n;

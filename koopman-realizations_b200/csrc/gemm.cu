@@ -49,6 +49,23 @@ __global__ void __launch_bounds__(KF_GEMM_THREADS, GramCfg::MINB) kf_gemm_grid_k
     kfg::gemm_tile_body<GramCfg, false, false>(t, kf_smem);
 }
 
+// Gram kernel, TMA operand path (gemm_kernel.cuh body 3): tensor-map loads with SWIZZLE_128B + mbarrier ring.
+using TmaGramCfg = kfg::TmaCfg<4>;
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(TmaGramCfg::THREADS, TmaGramCfg::MINB)
+kf_gram_tma_kernel(const KfTmaTask* __restrict__ tasks, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char kf_smem_raw[];
+    const KfTmaTask t = tasks[blockIdx.x];
+    if (WEIGHTED) {
+        if (t.W == nullptr) {
+            kfg::gemm_tile_body_tma<TmaGramCfg, false>(t, &tmap, kf_smem_raw);
+            return;
+        }
+    }
+    kfg::gemm_tile_body_tma<TmaGramCfg, WEIGHTED>(t, &tmap, kf_smem_raw);
+}
+
 bool g_attr_set = false;
 cudaError_t ensure_attrs() {
     if (g_attr_set) return cudaSuccess;
@@ -58,6 +75,10 @@ cudaError_t ensure_attrs() {
     e = cudaFuncSetAttribute(kf_gram_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(kf_gemm_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kf_gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaGramCfg::SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kf_gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaGramCfg::SMEM);
     if (e != cudaSuccess) return e;
     g_attr_set = true;
     return cudaSuccess;
@@ -72,6 +93,18 @@ int kf_launch_gemm_tasks(kf_ctx* ctx, const KfGemmTask* d_tasks, int ntasks, boo
         kf_gram_tile_kernel<true><<<ntasks, KF_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(d_tasks);
     else
         kf_gram_tile_kernel<false><<<ntasks, KF_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(d_tasks);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return KF_OK;
+}
+
+int kf_launch_gram_tma(kf_ctx* ctx, const KfTmaTask* d_tasks, int ntasks, bool weighted, const CUtensorMap& tmap, cudaStream_t st) {
+    if (ntasks <= 0) return KF_OK;
+    KF_CUDA(ctx, ensure_attrs());
+    if (weighted)
+        kf_gram_tma_kernel<true><<<ntasks, TmaGramCfg::THREADS, TmaGramCfg::SMEM, st>>>(d_tasks, tmap);
+    else
+        kf_gram_tma_kernel<false><<<ntasks, TmaGramCfg::THREADS, TmaGramCfg::SMEM, st>>>(d_tasks, tmap);
     KF_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return KF_OK;

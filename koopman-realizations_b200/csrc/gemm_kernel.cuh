@@ -349,15 +349,6 @@ struct TmaCfg {
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;   // + alignment slack
 };
 
-// task.A / task.B are interpreted as panel ROW indices (a_row, b_row), task.W as the weight row index + 1 (0 = none)
-struct KfTmaTask {
-    int a_row, b_row, w_row;   // w_row < 0: unweighted
-    int k0, k1;
-    int pad;
-    double* out;               // 128 x 64 sub-tile of a 128 x 128 accumulator tile (ldm = 128)
-    const double* W;           // weight row pointer (global) or nullptr
-};
-
 template <class C, bool WEIGHTED>
 __device__ __forceinline__ void gemm_tile_body_tma(const KfTmaTask& t, const void* tmap, unsigned char* smem_raw) {
     constexpr int STAGES = C::STAGES, MI = C::MI, NJ = C::NJ, BK = C::BK;

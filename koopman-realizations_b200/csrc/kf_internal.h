@@ -1,5 +1,6 @@
 // Internal declarations shared by the .cu files of libkoopfit.so (not part of the ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -42,6 +43,16 @@ struct KfGemmTask {
     double alpha;
     int accumulate;       // 1: out += ; 0: out =
     int pad;
+};
+
+// Task of the tensor-map TMA Gram kernel: operands are addressed by panel ROW (the panel itself is described by
+// a CUtensorMap), one CTA = one 128 x 64 sub-tile of a 128 x 128 accumulator tile.
+struct KfTmaTask {
+    int a_row, b_row, w_row;   // first panel row of the A / B operand; w_row unused (kept for debugging)
+    int k0, k1;                // snapshot range inside the panel, multiples of 16
+    int pad;
+    double* out;               // sub-tile base inside the accumulator tile (row stride 128)
+    const double* W;           // weight row (global pointer) or nullptr = unweighted
 };
 
 // ------------------------------------------------------------------ device buffer
@@ -99,7 +110,8 @@ struct kf_ctx {
 
     std::vector<int> level_start;   // offsets into the level-sorted feature order
     KfBuf d_order;
-    KfBuf d_ops, d_centres, d_pcs, d_panel[2], d_full, d_tasks[2], d_accum, d_tilemeta;
+    KfBuf d_ops, d_centres, d_pcs, d_panel[2], d_full, d_tasks[2], d_tma_tasks[2], d_accum, d_tilemeta;
+    CUtensorMap tmap[2];            // tensor maps of the two panels (SWIZZLE_128B, box 16 x 64)
     KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3, d_Kt;
     cudaEvent_t ev_panel_free[2] = {}, ev_panel_ready[2] = {};
 
@@ -110,6 +122,7 @@ struct kf_ctx {
     double opt_panel_mb = 64; // target size of one L2-resident panel (24/48/64 MB measured: 31.7/32.5/32.8 TF)
     double opt_qr_max_gb = 16; // KF_LS_AUTO takes the QRCP route when [Px|Py] is at most this large
     int opt_profile = 0;      // sample Gram-kernel durations with CUDA events (adds syncs)
+    int opt_tma = 1;          // Gram kernel operand path: 1 = tensor-map TMA + mbarrier ring, 0 = per-thread cp.async
 
     // counters
     double dmma_flops = 0;
@@ -137,6 +150,7 @@ struct kf_ctx {
 // ------------------------------------------------------------------ kernels (host launchers)
 // gemm.cu
 int kf_launch_gemm_tasks(kf_ctx* ctx, const KfGemmTask* d_tasks, int ntasks, bool weighted, cudaStream_t st);
+int kf_launch_gram_tma(kf_ctx* ctx, const KfTmaTask* d_tasks, int ntasks, bool weighted, const CUtensorMap& tmap, cudaStream_t st);
 // grid form: out(M x N tiles) over column-major / k-contiguous operands
 struct KfGemmGrid {
     const double* A; const double* B; double* out;

@@ -71,9 +71,9 @@ void run(const char* name, const std::vector<KfGemmTask>& base, int Mc, double* 
 }
 
 template <class C, bool W>
-__global__ void __launch_bounds__(C::THREADS, C::MINB) tma_kernel(const kfg::KfTmaTask* __restrict__ tasks, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(C::THREADS, C::MINB) tma_kernel(const KfTmaTask* __restrict__ tasks, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const kfg::KfTmaTask t = tasks[blockIdx.x];
+    const KfTmaTask t = tasks[blockIdx.x];
     if (W && t.W == nullptr) { kfg::gemm_tile_body_tma<C, false>(t, &tmap, smem_raw); return; }
     kfg::gemm_tile_body_tma<C, W>(t, &tmap, smem_raw);
 }
@@ -83,10 +83,10 @@ void run_tma(const char* name, const std::vector<KfGemmTask>& base, double* pane
     CUtensorMap tmap;
     int rc = kf_make_panel_tensor_map(&tmap, panel, Mc, rows);
     if (rc) { printf("%-40s tensor map encode failed rc=%d\n", name, rc); return; }
-    std::vector<kfg::KfTmaTask> tasks;
+    std::vector<KfTmaTask> tasks;
     for (const auto& b : base)
         for (int sn = 0; sn < 2; ++sn) {
-            kfg::KfTmaTask g{};
+            KfTmaTask g{};
             g.a_row = (int)((b.A - panel) / Mc);
             g.b_row = (int)((b.B - panel) / Mc) + sn * 64;
             g.W = b.W; g.w_row = b.W ? 0 : -1;
@@ -95,8 +95,8 @@ void run_tma(const char* name, const std::vector<KfGemmTask>& base, double* pane
             tasks.push_back(g);
         }
     const int ntasks = (int)tasks.size();
-    kfg::KfTmaTask* d_tasks; cudaMalloc(&d_tasks, tasks.size() * sizeof(kfg::KfTmaTask));
-    cudaMemcpy(d_tasks, tasks.data(), tasks.size() * sizeof(kfg::KfTmaTask), cudaMemcpyHostToDevice);
+    KfTmaTask* d_tasks; cudaMalloc(&d_tasks, tasks.size() * sizeof(KfTmaTask));
+    cudaMemcpy(d_tasks, tasks.data(), tasks.size() * sizeof(KfTmaTask), cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(tma_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tma_kernel<C, true>, C::THREADS, C::SMEM);
     cudaMemset(accum, 0, accum_n * 8);
