@@ -39,3 +39,43 @@ class DeviceArrayView:
 
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def fit_sharded(fitter, basis, model_type, alpha_dev, beta_dev, u_dev, P, budgets=None, group=None, **solve_kw):
+    """One rank's part of a snapshot-sharded fit (one process per GPU).
+
+    alpha_dev / beta_dev / u_dev: this rank's shard as CUDA tensors of shape (nzeta, M_r) / (m, M_r), float64,
+    contiguous (= column-major M_r x nzeta).  Steps: local lift + Gram (kf_accumulate_dev), ONE all-reduce of the
+    packed partial Grams, then either the replicated LS solve or — for a lasso vector — this rank's round-robin
+    share of the budgets (all ranks hold the same G, C), gathered so that every rank returns all candidates.
+    Returns the dict of Fitter.solve_dev with K_all ordered like `budgets`.
+    """
+    import torch
+    import torch.distributed as dist
+
+    nzeta, M = alpha_dev.shape
+    m = u_dev.shape[0]
+    fitter.accumulate_dev(basis, model_type, M, nzeta, m, alpha_dev.data_ptr(), beta_dev.data_ptr(), u_dev.data_ptr(), reset=True)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    if world > 1:
+        ptr, n = fitter.accum_buffer()
+        fitter.sync()
+        allreduce_sum_(torch.as_tensor(DeviceArrayView(ptr, n), device=alpha_dev.device), group)
+        torch.cuda.synchronize(alpha_dev.device)
+    if budgets is None:
+        return fitter.solve_dev(P, **solve_kw)
+    budgets = np.atleast_1d(np.asarray(budgets, dtype=np.float64))
+    mine = budgets_for_rank(budgets.size, rank, world)
+    res = fitter.solve_dev(P, least_squares=False, t=budgets[mine] if mine.size else budgets[:1], **solve_kw)
+    if world == 1:
+        return res
+    parts = [None] * world
+    dist.all_gather_object(parts, (mine, res["K_all"][:, :, :mine.size], res["objective"][:mine.size], res["l1norm"][:mine.size]), group=group)
+    K_all = np.zeros((P, P, budgets.size), order="F")
+    obj, l1 = np.zeros(budgets.size), np.zeros(budgets.size)
+    for idx, Kp, ob, ln in parts:
+        for j, i in enumerate(idx):
+            K_all[:, :, i], obj[i], l1[i] = Kp[:, :, j], ob[j], ln[j]
+    res.update(K_all=K_all, K=K_all[:, :, 0], objective=obj, l1norm=l1)
+    return res

@@ -190,3 +190,26 @@ def test_config2_poly3_delay1(fitter, arm_data, model, P, rank):
         assert relF(K.T[:N, :N], Ko.T[:N, :N]) < 1e-9 and relF(K.T[:N, N:], Ko.T[:N, N:]) < 1e-9
     else:
         assert relF(K[:, :15], Ko[:, :15]) < 1e-9
+
+
+def test_fit_sharded_single_rank_lasso_vector(fitter):
+    """sharding.fit_sharded with one rank: device-resident shard -> accumulate -> (no-op all-reduce) -> budgets."""
+    import torch
+    from koopfit.sharding import fit_sharded
+    alpha, beta, u = synth(3000, 3, 2, seed=9)
+    basis = koopfit.Basis(["poly"], [2], 3)
+    prog = O.build_program(["poly"], [2], 3)
+    Px, Py = O.build_regressors("linear", prog, alpha, beta, u)
+    G, C = O.gram(Px, Py)
+    P = Px.shape[1]
+    dev = torch.device("cuda:0")
+    ta, tb, tu = (torch.tensor(np.ascontiguousarray(x.T), device=dev) for x in (alpha, beta, u))
+    l1 = np.abs(np.linalg.solve(G, C)).sum()
+    budgets = np.array([0.2, 0.6]) * l1
+    res = fit_sharded(fitter, basis, "linear", ta, tb, tu, P, budgets=budgets, psd_shift="never")
+    for i, t in enumerate(budgets):
+        Ko, _ = O.solve_l1ball_qp(G, C, t)
+        fo, fg = O.qp_objective(G, C, Ko), O.qp_objective(G, C, res["K_all"][:, :, i])
+        assert abs(fg - fo) <= 1e-8 * abs(fo)
+    res = fit_sharded(fitter, basis, "linear", ta, tb, tu, P, ls_method="gram")
+    assert relF(res["K"], O.mldivide(Px, Py)) < 1e-9
