@@ -89,13 +89,6 @@ def gen_torch(M, device, seed):
     return alpha, beta, u
 
 
-class _CAI:
-    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-
 def fp64_peak_tflops():
     """Roofline denominator: MEASURED cuBLAS DGEMM FP64 on this pool's B200
     (profiles/r01_fp64_dgemm_peak.json, tools/fp64_peak.py); MEASURED_PEAKS.json has no FP64 entry."""

@@ -135,6 +135,13 @@ int kf_lift(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V,
  * LS or all nt budgets.  HOST pointers in `prob`; copies are inside the call. */
 int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out);
 
+/* Many independent fits in one call (evaluate_rand_models.m:45-144 fits 23 small models per random system).
+ * Least-squares problems with P <= 32 and no dim_red run CONCURRENTLY, one CTA per problem, entirely on chip
+ * (tile-wise Householder TSQR of [Px | Py] + pivoted QR of the small triangular factor: mldivide semantics);
+ * every other problem is solved by kf_fit one after the other.  bases[i], probs[i], solves[i], outs[i] describe
+ * problem i (HOST pointers, as in kf_fit); problems that share the same alpha pointer share one upload. */
+int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, const kf_solve* solves, kf_result* outs);
+
 /* Generic MATLAB `A \ B` for a tall A (M x P) and B (M x Pc), HOST column-major buffers:
  * Householder QR with column pivoting on the GPU, rank by max(size(A))*eps(|R11|), basic
  * solution X (P x Pc).  Replaces `Mtranspose = L \ R` in get_model (Ksysid.m:1216).

@@ -147,6 +147,7 @@ def load():
         "kf_block_table": (i, [i, i, i, c_int_p, c_int_p, c_int_p]),
         "kf_lift": (i, [vp, P(kf_basis), ll, c_double_p, c_double_p]),
         "kf_fit": (i, [vp, P(kf_basis), P(kf_problem), P(kf_solve), P(kf_result)]),
+        "kf_fit_batch": (i, [vp, i, P(P(kf_basis)), P(kf_problem), P(kf_solve), P(kf_result)]),
         "kf_mldivide": (i, [vp, ll, i, i, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]),
         "kf_accumulate_dev": (i, [vp, P(kf_basis), P(kf_problem), i]),
         "kf_accum_buffer": (i, [vp, P(vp), P(C.c_size_t)]),
@@ -165,5 +166,5 @@ def load():
 
 
 EXPORTS = ["kf_create", "kf_destroy", "kf_last_error", "kf_version", "kf_basis_dims", "kf_block_table",
-           "kf_lift", "kf_fit", "kf_mldivide", "kf_accumulate_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
+           "kf_lift", "kf_fit", "kf_fit_batch", "kf_mldivide", "kf_accumulate_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
            "kf_stream", "kf_counters", "kf_last_times", "kf_set_option"]

@@ -94,7 +94,6 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
     L.Mc = (int)Mc;
 
     const int tmx = L.Rxp / KF_BM, tny = L.Nyp / KF_BN;
-    const int npairs = (L.model == KF_BILINEAR) ? L.nW : 1;
     for (int a = 0; a <= (L.model == KF_BILINEAR ? L.m : 0); ++a)
         for (int b = a; b <= (L.model == KF_BILINEAR ? L.m : 0); ++b) {
             const int q = (L.model == KF_BILINEAR) ? pair_index(a, b, L.m) : 0;
@@ -103,7 +102,6 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
             for (int tm = 0; tm < tmx; ++tm)
                 for (int tn = 0; tn < tny; ++tn) L.tiles.push_back(KfTile{1, q, a, b, tm, tn});
         }
-    (void)npairs;
     const int T = (int)L.tiles.size();
     const int ksteps = L.Mc / KF_BK;
     // split-K so that small problems still fill the machine: aim at ~2 waves of 2 CTAs per SM
@@ -485,9 +483,6 @@ int kf_create(kf_ctx** out, int device) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; ++i)
-        ok = cudaEventCreateWithFlags(&ctx->ev_panel_free[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ev_panel_ready[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         g_create_err = "kf_create: stream/event creation failed";
         delete ctx;
@@ -507,10 +502,6 @@ void kf_destroy(kf_ctx* ctx) {
     for (KfBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (int i = 0; i < 2; ++i) {
-        if (ctx->ev_panel_free[i]) cudaEventDestroy(ctx->ev_panel_free[i]);
-        if (ctx->ev_panel_ready[i]) cudaEventDestroy(ctx->ev_panel_ready[i]);
-    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
@@ -702,6 +693,34 @@ int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_
     ctx->lay.valid = false;
     out->info.t_total_ms = now_ms() - t0;
     return rc;
+}
+
+int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, const kf_solve* solves, kf_result* outs) {
+    if (!ctx) return KF_EINVAL;
+    if (nprob < 0 || (nprob && (!bases || !probs || !solves || !outs))) {
+        ctx->err = "kf_fit_batch: bases, probs, solves, outs required";
+        return KF_EINVAL;
+    }
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int> small, rest;
+    for (int i = 0; i < nprob; ++i) {
+        int N = 0, P = 0;
+        if (!bases[i]) { ctx->err = "kf_fit_batch: NULL basis"; return KF_EINVAL; }
+        KF_TRY(kf_basis_dims(bases[i], probs[i].model, probs[i].m, nullptr, &N, &P));
+        const bool ok = solves[i].least_squares && P <= 32 && bases[i]->n_pcs == 0 && probs[i].M > 0 && probs[i].alpha &&
+                        probs[i].beta && (probs[i].m == 0 || probs[i].u) && !outs[i].G && !outs[i].C && !outs[i].Px && !outs[i].Py &&
+                        (probs[i].model == KF_LINEAR || probs[i].model == KF_BILINEAR || probs[i].model == KF_NONLINEAR) &&
+                        bases[i]->nv == probs[i].nzeta + (probs[i].model == KF_NONLINEAR ? probs[i].m : 0);
+        (ok ? small : rest).push_back(i);
+    }
+    // concurrent part, in groups that bound the staging memory
+    const size_t group = 2048;
+    for (size_t g0 = 0; g0 < small.size(); g0 += group) {
+        const int n = (int)std::min(group, small.size() - g0);
+        KF_TRY(kf_fit_batch_small(ctx, nprob, bases, probs, outs, small.data() + g0, n));
+    }
+    for (int i : rest) KF_TRY(kf_fit(ctx, bases[i], &probs[i], &solves[i], &outs[i]));
+    return KF_OK;
 }
 
 int kf_mldivide(kf_ctx* ctx, long long M, int P, int Pc, const double* A, const double* B, double* X, int* perm, int* rank) {

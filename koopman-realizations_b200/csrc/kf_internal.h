@@ -113,12 +113,11 @@ struct kf_ctx {
     KfBuf d_ops, d_centres, d_pcs, d_panel[2], d_full, d_tasks[2], d_tma_tasks[2], d_accum, d_tilemeta;
     CUtensorMap tmap[2];            // tensor maps of the two panels (SWIZZLE_128B, box 16 x 64)
     KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3, d_Kt;
-    cudaEvent_t ev_panel_free[2] = {}, ev_panel_ready[2] = {};
 
     // options
     int opt_chunk = 0;        // 0 = auto
     int opt_splitk = 0;       // 0 = auto
-    int opt_overlap = 1;      // lift of chunk c+1 concurrent with Gram of chunk c
+    int opt_overlap = 1;      // even / odd chunks as two independent lift -> Gram pipelines on two streams
     double opt_panel_mb = 64; // target size of one L2-resident panel (24/48/64 MB measured: 31.7/32.5/32.8 TF)
     double opt_qr_max_gb = 16; // KF_LS_AUTO takes the QRCP route when [Px|Py] is at most this large
     int opt_profile = 0;      // sample Gram-kernel durations with CUDA events (adds syncs)
@@ -195,6 +194,10 @@ int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, double* G_work, const double* C
 // Householder QRCP basic solution of A X = B;  AB = [A | B] (M x (P+Pc), ld = ldab) is overwritten
 int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long long ldab, double* X, long long ldx,
                    int* d_perm, int* rank_out, double* min_piv, double* max_piv, cudaStream_t st);
+
+// batch.cu
+int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, kf_result* outs,
+                       const int* which, int nwhich);
 
 // qp.cu
 struct KfQpResult { double objective; double l1; int iters; double lam; int capped; };

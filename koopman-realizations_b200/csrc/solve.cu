@@ -180,96 +180,8 @@ __global__ void __launch_bounds__(256) kf_pchol_update_kernel(double* W, long lo
 // updated once per block by the DMMA kernel instead of once per column by a memory-bound rank-1 kernel.
 constexpr int PCHOL_NB = 64;
 
-// one CTA: pivot on d_i = W(i,i) - dots[i], symmetric swap j<->p (and dots), L(j,j)
-__global__ void __launch_bounds__(1024) kf_pcholb_pivot_kernel(double* W, long long ld, int P, int j, int j0, int* perm,
-                                                               double* dots, PcholState* st, double tol2) {
-    if (st->done) return;
-    __shared__ double sval[32];
-    __shared__ int sidx[32];
-    __shared__ int s_p;
-    const int tid = threadIdx.x;
-    double best = -1.0;
-    int bi = P;
-    for (int i = j + tid; i < P; i += blockDim.x) {
-        const double v = W[(long long)i * ld + i] - dots[i];
-        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-        const double ov = __shfl_down_sync(0xffffffffu, best, off);
-        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if ((tid & 31) == 0) { sval[tid >> 5] = best; sidx[tid >> 5] = bi; }
-    __syncthreads();
-    if (tid < 32) {
-        best = (tid < (blockDim.x >> 5)) ? sval[tid] : -1.0;
-        bi = (tid < (blockDim.x >> 5)) ? sidx[tid] : P;
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ov = __shfl_down_sync(0xffffffffu, best, off);
-            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if (tid == 0) {
-            if (j == 0) st->piv0 = best;
-            const bool ok = (best > 0.0) && (best > tol2 * st->piv0);
-            if (!ok) {
-                st->rank = j;
-                st->done = 1;
-                s_p = -1;
-            } else {
-                s_p = bi;
-                st->minpiv = best;
-                st->rank = j + 1;
-            }
-        }
-    }
-    __syncthreads();
-    const int p = s_p;
-    if (p < 0) return;
-    if (p != j) {
-        for (int i = tid; i < P; i += blockDim.x) {   // swap columns j <-> p
-            const double a = W[(long long)j * ld + i], b = W[(long long)p * ld + i];
-            W[(long long)j * ld + i] = b;
-            W[(long long)p * ld + i] = a;
-        }
-        __syncthreads();
-        for (int i = tid; i < P; i += blockDim.x) {   // swap rows j <-> p
-            const double a = W[(long long)i * ld + j], b = W[(long long)i * ld + p];
-            W[(long long)i * ld + j] = b;
-            W[(long long)i * ld + p] = a;
-        }
-        if (tid == 0) {
-            const int a = perm[j];
-            perm[j] = perm[p];
-            perm[p] = a;
-            const double d = dots[j];
-            dots[j] = dots[p];
-            dots[p] = d;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        const double ljj = sqrt(W[(long long)j * ld + j] - dots[j]);
-        W[(long long)j * ld + j] = ljj;
-    }
-}
-
-// column j of the factor: L(i,j) = (W(i,j) - sum_{k=j0}^{j-1} L(i,k) L(j,k)) / L(j,j), i > j; mirrored copy; dots
-__global__ void __launch_bounds__(256) kf_pcholb_col_kernel(double* W, long long ld, int P, int j, int j0, double* dots,
-                                                            const PcholState* st) {
-    if (st->done) return;
-    const int i = j + 1 + blockIdx.x * 256 + threadIdx.x;
-    if (i >= P) return;
-    double v = W[(long long)j * ld + i];
-    for (int k = j0; k < j; ++k) v = fma(-W[(long long)k * ld + i], W[(long long)k * ld + j], v);
-    const double l = v / W[(long long)j * ld + j];
-    W[(long long)j * ld + i] = l;
-    W[(long long)i * ld + j] = l;
-    dots[i] = fma(l, l, dots[i]);
-}
-
-// ---- v2 of the in-block column step: three small grid-parallel kernels per column instead of one
-// single-CTA kernel whose strided row swap cost 22 us (profiles/r01_launch_list_summary.txt).
+// In-block column step: three small grid-parallel kernels per column (a single-CTA kernel doing the strided
+// row swap cost 22 us per column).
 // dcur[i] is the current Schur-complement diagonal (contiguous, so the pivot search is coalesced).
 struct PcholStep {   // lives right after PcholState in device memory
     int p;           // pivot row of the current column (-1: stop)
@@ -375,11 +287,6 @@ __global__ void __launch_bounds__(256) kf_pcholc_col_kernel(double* W, long long
     W[(long long)j * ld + i] = l;
     W[(long long)i * ld + j] = l;
     dcur[i] = fma(-l, l, dcur[i]);
-}
-
-__global__ void kf_zero_kernel(double* p, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = 0.0;
 }
 
 // zero rows/cols >= rank of the factor so padded contraction ranges contribute nothing

@@ -127,6 +127,49 @@ class Fitter:
                    objective=obj, l1norm=l1, qp_iters=iters)
         return out
 
+    def fit_batch(self, problems):
+        """Many independent fits in one call (kf_fit_batch).  `problems`: list of dicts with keys basis, model_type,
+        alpha, beta, u and optional solve keywords (as Fitter.fit).  Small least-squares problems (P <= 32) run
+        concurrently on the GPU, one CTA each; the rest are solved one after the other.  Returns a list of dicts
+        (K, rank, perm, info [, objective, l1norm])."""
+        n = len(problems)
+        bases = (C.POINTER(A.kf_basis) * n)()
+        probs = (A.kf_problem * n)()
+        solves = (A.kf_solve * n)()
+        outs = (A.kf_result * n)()
+        keep, results = [], []
+        for i, pb in enumerate(problems):
+            alpha, beta, u = pb["alpha"], pb["beta"], pb["u"]
+            if not (isinstance(alpha, np.ndarray) and alpha.flags.f_contiguous and alpha.dtype == np.float64):
+                alpha = A.fcol(alpha)
+            if not (isinstance(beta, np.ndarray) and beta.flags.f_contiguous and beta.dtype == np.float64):
+                beta = A.fcol(beta)
+            if not (isinstance(u, np.ndarray) and u.flags.f_contiguous and u.dtype == np.float64):
+                u = A.fcol(u)
+            M, nzeta = alpha.shape
+            m = u.shape[1]
+            _, N, P = self.dims(pb["basis"], pb["model_type"], m)
+            bases[i] = C.pointer(pb["basis"].struct)
+            probs[i] = A.kf_problem(M=M, nzeta=nzeta, m=m, model=A.MODEL_CODE[pb["model_type"]],
+                                    alpha=alpha.ctypes.data, beta=beta.ctypes.data, u=u.ctypes.data)
+            kw = {k: v for k, v in pb.items() if k not in ("basis", "model_type", "alpha", "beta", "u")}
+            sv, keep_t = self._solve_struct(**kw)
+            solves[i] = sv
+            nt = max(1, sv.nt) if not sv.least_squares else 1
+            K = np.zeros((P, P, nt), order="F")
+            perm = np.zeros(P, dtype=np.int32)
+            obj, l1 = np.zeros(nt), np.zeros(nt)
+            iters = np.zeros(nt, dtype=np.int32)
+            outs[i].K, outs[i].perm = A.dptr(K), perm.ctypes.data_as(A.c_int_p)
+            outs[i].objective, outs[i].l1norm, outs[i].qp_iters = A.dptr(obj), A.dptr(l1), iters.ctypes.data_as(A.c_int_p)
+            keep.append((alpha, beta, u, keep_t, sv))
+            results.append(dict(K_all=K, perm=perm, objective=obj, l1norm=l1, qp_iters=iters, N=N, P=P, nt=nt))
+        self._check(self.lib.kf_fit_batch(self.ctx, n, bases, probs, solves, outs), "kf_fit_batch")
+        for i, r in enumerate(results):
+            info = {f: getattr(outs[i].info, f) for f, _ in A.kf_info._fields_}
+            r.update(K=r["K_all"][:, :, 0] if r["nt"] == 1 else r["K_all"], rank=info["rank"], info=info)
+        return results
+
     def mldivide(self, Amat, Bmat):
         """MATLAB `A \\ B` (QRCP basic solution) on the GPU; returns X, rank, perm."""
         Amat, Bmat = A.fcol(Amat), A.fcol(Bmat)

@@ -141,3 +141,37 @@ def test_config4_rand_system_fits(fitter, rsys_data):
                 err_o = k.validate()["error"]
                 yr = k.valdata[0]["y"]
                 assert abs(err_g["mean"] / np.mean(np.abs(yr)) - err_o["mean"] / np.mean(np.abs(yr))).max() < 1e-6
+
+
+def test_config4_batched_fits_match_sequential_and_oracle(fitter, rsys_data):
+    """kf_fit_batch on the evaluate_rand_models.m fit list (linear deg 1-13, bilinear 1-6 by least squares; nonlinear
+    1-4 with lasso = 4) for the shipped subset of random systems: the concurrent one-CTA-per-problem path must give
+    mldivide's solution (oracle) for every fit, and the QP ones fall through to the general path."""
+    problems, refs = [], []
+    for d in rsys_data:
+        base = O.KsysidOracle(d, model_type="linear", obs_type=["poly"], obs_degree=[1])
+        a, b, u = (np.asfortranarray(base.pairs[k]) for k in ("alpha", "beta", "u"))
+        for model, degs, lasso in (("linear", range(1, 14), None), ("bilinear", range(1, 7), None), ("nonlinear", range(1, 5), 4.0)):
+            for deg in degs:
+                nv = 1 + (1 if model == "nonlinear" else 0)
+                prog = O.build_program(["poly"], [deg], nv)
+                pb = dict(basis=koopfit.Basis(["poly"], [deg], nv), model_type=model, alpha=a, beta=b, u=u)
+                if lasso is not None:
+                    pb.update(least_squares=False, t=[lasso * prog.N], psd_shift="as_reference")
+                problems.append(pb)
+                refs.append((model, deg, prog, lasso))
+    res = fitter.fit_batch(problems)
+    assert len(res) == len(problems) == 23 * len(rsys_data)
+    for pb, r, (model, deg, prog, lasso) in zip(problems, res, refs):
+        Px, Py = O.build_regressors(model, prog, pb["alpha"], pb["beta"], pb["u"])
+        if lasso is None:
+            Ko, info = O.mldivide(Px, Py, return_info=True)
+            assert r["rank"] == info["rank"], (model, deg)
+            assert relF(r["K"], Ko) < 1e-8, (model, deg, relF(r["K"], Ko))
+        else:
+            G, C = O.gram(Px, Py)
+            if O.needs_psd_shift(G):
+                G = G + 1e-6 * np.eye(G.shape[0])
+            Ko, _ = O.solve_l1ball_qp(G, C, lasso * prog.N)
+            fo, fg = O.qp_objective(G, C, Ko), O.qp_objective(G, C, r["K"])
+            assert abs(fg - fo) <= 1e-8 * abs(fo), (model, deg)

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log
+timeout 300 python tools/batch_timing.py > gpurun_out/batch_timing.log 2>&1; echo rc=$? >> gpurun_out/batch_timing.log; tail -4 gpurun_out/batch_timing.log | cut -c1-400
