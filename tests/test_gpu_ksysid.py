@@ -60,3 +60,34 @@ def test_default_dim_red_reproduces_golden_Z(fitter, arm_data, golden_Z):
     Z = ks.lift["econ_full"](ks.scaledown["y"](Y[:Zg.shape[0]]))
     assert Z.shape == Zg.shape
     assert np.abs(Z - Zg).max() < 1e-9
+
+
+def test_train_models_with_lasso_vector(fitter, snake_data):
+    """train_models over a lasso vector (Ksysid.m:1370-1387): candidates{i} with .lasso, model = candidates{1};
+    every candidate's K minimises the L1-ball QP for t = lasso(i) * N (objective within 1e-8 of the oracle)."""
+    cen = 2 * np.random.default_rng(0).random((3, 4)) - 1
+    lassos = [0.05, 0.5, 50.0]
+    ks = Ksysid(snake_data, model_type="bilinear", obs_type=["gaussian"], obs_degree=[4], lasso=lassos, dim_red=False,
+                centres=cen, fitter=fitter).train_models()
+    assert isinstance(ks.candidates, list) and len(ks.candidates) == 3 and ks.model is ks.candidates[0]
+    assert [c["lasso"] for c in ks.candidates] == lassos
+    ko = O.KsysidOracle(snake_data, model_type="bilinear", obs_type=["gaussian"], obs_degree=[4], centres=cen)
+    Px, Py = O.build_regressors("bilinear", ko.prog, ko.pairs["alpha"], ko.pairs["beta"], ko.pairs["u"])
+    G, C = O.gram(Px, Py)
+    for cand, lam in zip(ks.candidates, lassos):
+        Kref, _ = O.solve_l1ball_qp(G, C, lam * ko.N)
+        fo, fg = O.qp_objective(G, C, Kref), O.qp_objective(G, C, cand["K"])
+        assert abs(fg - fo) <= 1e-8 * abs(fo)
+        assert np.abs(cand["K"]).sum() <= lam * ko.N * (1 + 1e-12)
+        assert cand["A"].shape == (8, 8) and cand["B"].shape == (8, 8)
+
+
+def test_delays_and_val_trials(fitter, arm_data):
+    """delays = 1: nzeta = n(nd+1) + m nd (Ksysid.m:86), zeta layout (868-907), validation starts at row nd+1 (1630)."""
+    ks = Ksysid(arm_data, model_type="bilinear", obs_type=["poly"], obs_degree=[1], delays=1, dim_red=False, fitter=fitter).train_models()
+    ko = O.KsysidOracle(arm_data, model_type="bilinear", obs_type=["poly"], obs_degree=[1], delays=1).train_models()
+    assert ks.params["nzeta"] == 15 and ks.snapshotPairs["alpha"].shape == (11998, 15)
+    assert relF(ks.model["A"], ko.model["A"]) < 1e-9 and relF(ks.model["B"], ko.model["B"]) < 1e-9
+    r = ks.val_BLmodel(ks.model, ks.valdata[2])
+    assert r["sim"]["y"].shape == (400, 6)
+    assert np.abs(r["error"]["rmse"] - ko.validate(trial=2)["error"]["rmse"]).max() < 1e-6
