@@ -344,7 +344,11 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "kf_gram_tile_kernel<true> (FP64 DMMA.8x8x4 Gram/cross-covariance)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (4096-snapshot panel) from
+                         # the ncu --set full capture in profiles/r01_gram_tma_ncu_summary.txt: 587 MB + 119 MB
+                         "traffic": 7.07e8, "traffic_unit": "bytes per launch (ncu, 4096-snapshot chunk; 67 MB panel + accumulator RMW)",
+                         "algorithmic_flops_per_launch": FLOPS_ALGO_PER_PAIR * 4096, "issued_flops_per_launch": 1000 * 2.0 * 128 * 128 * 4096,
+                         "peak_source": peak_src,
                          "flops_basis": "DMMA flops actually issued per step by the Gram kernel (Kronecker blocks: 1000 tiles x 2x128x128 per snapshot = 3.28e7/pair)",
                          "achieved_algorithmic": FLOPS_ALGO_PER_PAIR * M / (gk * 1e-3) / 1e12,
                          "algorithmic_flops_per_pair": FLOPS_ALGO_PER_PAIR, "issued_flops_per_pair": 1000 * 2.0 * 128 * 128,

@@ -382,53 +382,56 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
             c1 = n * (nd + 1) + mnd;
             for (double v : target) pinned_l1 += std::fabs(v);
         }
-        KF_CUDA(ctx, ctx->d_Kt.ensure(mat));
-        double* Kt = ctx->d_Kt.as<double>();
         // the unconstrained minimiser with the pinned columns in place: ||.||_1 decides which budgets are active
         if (c1 > c0)
             KF_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_K.as<double>() + (size_t)c0 * Pp, (size_t)Pp * sizeof(double), target.data(),
                                            (size_t)P * sizeof(double), (size_t)P * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, st));
         KfQpResult ls{};
         KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), &ls, st));
-        // budgets in ascending order: each active solve starts from the previous solution and multiplier
-        std::vector<int> order(sv->nt);
-        for (int i = 0; i < sv->nt; ++i) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](int a, int b) { return sv->t[a] < sv->t[b]; });
-        double lam_prev = 0, l1_prev_free = 0;
-        int capped = 0;
-        for (int oi = 0; oi < sv->nt; ++oi) {
-            const int it = order[oi];
-            const double t_free = sv->t[it] - pinned_l1;
-            if (t_free < 0) {
+        std::vector<int> act;   // budgets whose constraint is active
+        for (int it = 0; it < sv->nt; ++it) {
+            if (sv->t[it] - pinned_l1 < 0) {
                 ctx->err = "L1 budget smaller than the pinned delay entries: the QP is infeasible";
                 return KF_ENUMERIC;
             }
-            KfQpResult qr{};
-            const double* Kres = Kt;
-            if (ls.l1 <= sv->t[it]) {   // inactive budget: lam = 0, K = unconstrained minimiser
-                qr = ls;
-                qr.iters = 0;
-                Kres = ctx->d_K.as<double>();
+            if (ls.l1 <= sv->t[it]) {   // inactive: lam = 0, K = unconstrained minimiser
+                if (out->objective) out->objective[it] = ls.objective;
+                if (out->l1norm) out->l1norm[it] = ls.l1;
+                if (out->qp_iters) out->qp_iters[it] = 0;
+                if (out->K) KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K + (size_t)it * P * P));
             } else {
-                if (lam_prev <= 0) {   // cold start (kf_solve_l1ball zeroes the free columns)
-                    if (c1 > c0)
-                        KF_CUDA(ctx, cudaMemcpy2DAsync(Kt + (size_t)c0 * Pp, (size_t)Pp * sizeof(double), target.data(), (size_t)P * sizeof(double),
-                                                       (size_t)P * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, st));
-                }
-                KF_TRY(kf_solve_l1ball(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), t_free, c0, c1, lam_prev,
-                                       l1_prev_free - t_free, sv->qp_max_iter, sv->qp_tol, Kt, &qr, st));
-                lam_prev = qr.lam;
-                l1_prev_free = qr.l1;
-                capped += qr.capped;
-                const int evals = qr.iters;
-                // objective and ||K||_1 over ALL columns (the pinned ones count towards the budget row, Ksysid.m:1136)
-                KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt, &qr, st));
-                qr.iters = evals;
+                act.push_back(it);
             }
-            if (out->objective) out->objective[it] = qr.objective;
-            if (out->l1norm) out->l1norm[it] = qr.l1;
-            if (out->qp_iters) out->qp_iters[it] = qr.iters;
-            if (out->K) KF_TRY(copy_out_matrix(ctx, Kres, Pp, P, out->K + (size_t)it * P * P));
+        }
+        // all active budgets of the lasso vector are solved in lockstep, in groups that bound the device memory
+        // (K_b and dK_b/dlam per budget)
+        int capped = 0;
+        const size_t per = 2 * mat;
+        const int gmax = (int)std::max<size_t>(1, std::min<size_t>(256, (size_t)(12.0 * 1073741824.0) / per));
+        for (size_t g0 = 0; g0 < act.size(); g0 += gmax) {
+            const int nb = (int)std::min<size_t>(gmax, act.size() - g0);
+            KF_CUDA(ctx, ctx->d_Kt.ensure((size_t)nb * mat));
+            double* Kt = ctx->d_Kt.as<double>();
+            std::vector<double> tf(nb);
+            for (int b = 0; b < nb; ++b) {
+                tf[b] = sv->t[act[g0 + b]] - pinned_l1;
+                if (c1 > c0)
+                    KF_CUDA(ctx, cudaMemcpy2DAsync(Kt + (size_t)b * Pp * Pp + (size_t)c0 * Pp, (size_t)Pp * sizeof(double), target.data(),
+                                                   (size_t)P * sizeof(double), (size_t)P * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, st));
+            }
+            std::vector<KfQpResult> qr(nb);
+            KF_TRY(kf_solve_l1ball_multi(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1, sv->qp_max_iter,
+                                         sv->qp_tol, Kt, qr.data(), st));
+            for (int b = 0; b < nb; ++b) {
+                const int it = act[g0 + b];
+                capped += qr[b].capped;
+                KfQpResult ev{};   // objective and ||K||_1 over ALL columns (the pinned ones count towards the budget row, Ksysid.m:1136)
+                KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt + (size_t)b * Pp * Pp, &ev, st));
+                if (out->objective) out->objective[it] = ev.objective;
+                if (out->l1norm) out->l1norm[it] = ev.l1;
+                if (out->qp_iters) out->qp_iters[it] = qr[b].iters;
+                if (out->K) KF_TRY(copy_out_matrix(ctx, Kt + (size_t)b * Pp * Pp, Pp, P, out->K + (size_t)it * P * P));
+            }
             KF_CUDA(ctx, cudaStreamSynchronize(st));
         }
         out->info.passes = 1;

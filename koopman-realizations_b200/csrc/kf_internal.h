@@ -201,7 +201,7 @@ int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, con
 
 // qp.cu
 struct KfQpResult { double objective; double l1; int iters; double lam; int capped; };
-int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, double t, int fix_c0, int fix_c1,
-                    double lam_start, double phi_start, int max_iter, double tol, double* K, KfQpResult* res, cudaStream_t st);
+int kf_solve_l1ball_multi(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, int nb, const double* t, int fix_c0,
+                          int fix_c1, int max_iter, double tol, double* K_all, KfQpResult* res, cudaStream_t st);
 int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_t st);
 int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, KfQpResult* res, cudaStream_t st);

@@ -6,16 +6,16 @@
 // The columns of K couple only through the single budget t, so by the KKT conditions
 // there is one multiplier lam >= 0 such that every column solves the penalised problem
 // min 0.5 k'Gk - c_j'k + lam ||k||_1, and either (lam = 0, ||K||_1 <= t) or ||K||_1 = t.
-//   * inner solve: cyclic coordinate descent in covariance form, ONE CTA PER COLUMN, the
-//     column k_j and its gradient residual q_j = c_j - G k_j live in shared memory; all P
-//     columns (and so all SMs) run concurrently with no inter-CTA synchronisation; glmnet-style
-//     active-set sweeps;
-//   * outer solve: bracketing + Illinois secant on phi(lam) = ||K(lam)||_1 - t (host-driven,
-//     one tiny reduction per evaluation), warm-started;
-//   * exact last step: on the final sign pattern K(lam) is affine in lam; D = dK/dlam is
-//     obtained with the same kernel (restricted Gauss-Seidel on G_SS d = sign_S) and lam is
-//     corrected so that ||K||_1 = t to rounding.
-// A whole vector of budgets reuses G, C and warm-starts from the previous budget.
+//   * inner solve: cyclic coordinate descent in covariance form, ONE CTA PER (COLUMN, BUDGET): the
+//     column k_j and its gradient residual q_j = c_j - G k_j live in shared memory; all columns of
+//     ALL budgets of a lasso vector run concurrently (grid = P x nt) with no inter-CTA
+//     synchronisation; glmnet-style active-set sweeps;
+//   * outer solve: every budget runs its own bracketing + Illinois secant on
+//     phi_b(lam) = ||K_b(lam)||_1 - t_b, in lockstep (one launch evaluates all unfinished budgets,
+//     one tiny per-budget reduction), warm-started from its previous iterate;
+//   * exact last step: on the final sign pattern K(lam) is affine in lam; D = dK/dlam comes from
+//     the same kernel (restricted Gauss-Seidel on G_SS d = sign_S) and lam is corrected so that
+//     ||K||_1 = t to rounding.
 #include <algorithm>
 #include <cmath>
 
@@ -27,16 +27,18 @@ constexpr int CD_THREADS = 256;
 
 struct CdArgs {
     const double* G; long long ldg;
-    const double* dG;            // diag(G)
-    const double* R; long long ldr;   // right-hand sides: C (mode 0/2) ; ignored in mode 1
-    double* K; long long ldk;    // mode 0: warm start in / solution out; mode 1: D out; mode 2: read only
-    const double* K0; long long ldk0;  // mode 1: support + signs
+    const double* dG;                 // diag(G)
+    const double* R; long long ldr;   // right-hand sides C (mode 0/2)
+    double* K; long long ldk;         // budget b: K + b * kstride.  mode 0: warm start in / solution out; 1: D out; 2: read only
+    const double* K0; long long ldk0; // mode 1: support + signs (budget b: K0 + b * kstride)
+    long long kstride;
     int P;
-    int col0;                    // first column handled (columns col0 .. col0+gridDim.x-1)
-    int skip0, skip1;            // pinned columns [skip0, skip1) are left untouched
-    double lam, tol;
-    int max_sweeps, mode;        // 0 lasso CD, 1 restricted Gauss-Seidel for dK/dlam, 2 evaluate
-    double* col_l1; double* col_obj; double* col_aux; int* col_iters;
+    int skip0, skip1;                 // pinned columns [skip0, skip1) are left untouched
+    const double* lam;                // per budget
+    const int* active;                // per budget: 0 = skip this launch
+    double tol;
+    int max_sweeps, mode;             // 0 lasso CD, 1 restricted Gauss-Seidel for dK/dlam, 2 evaluate
+    double* col_l1; double* col_obj; double* col_aux; int* col_iters;   // [budget][column]
 };
 
 __device__ __forceinline__ double soft(double x, double lam) {
@@ -61,17 +63,19 @@ __device__ __forceinline__ double cta_sum(double v, double* sh) {
 __global__ void __launch_bounds__(CD_THREADS) kf_cd_kernel(const CdArgs a) {
     extern __shared__ __align__(16) double cd_smem[];
     __shared__ double red[32];
+    __shared__ int s_nact;
     const int P = a.P, tid = threadIdx.x;
-    const int col = a.col0 + blockIdx.x;
+    const int col = blockIdx.x, bud = blockIdx.y;
+    if (!a.active[bud]) return;
     if (col >= a.skip0 && col < a.skip1) return;
     double* k = cd_smem;            // current column
     double* q = cd_smem + P;        // q = rhs - G k
     int* act = reinterpret_cast<int*>(cd_smem + 2 * P);   // active index list
-    __shared__ int s_nact;
+    const double lam = a.lam[bud];
 
     // ---- initialise k, rhs
-    const double* Kcol = a.K + (long long)col * a.ldk;
-    const double* K0col = a.mode == 1 ? a.K0 + (long long)col * a.ldk0 : nullptr;
+    double* Kcol = a.K + bud * a.kstride + (long long)col * a.ldk;
+    const double* K0col = a.mode == 1 ? a.K0 + bud * a.kstride + (long long)col * a.ldk0 : nullptr;
     for (int i = tid; i < P; i += CD_THREADS) {
         if (a.mode == 1) {
             const double s0 = K0col[i];
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(CD_THREADS) kf_cd_kernel(const CdArgs a) {
                 if (!(gii > 0.0) || !in_support(i)) continue;
                 const double ki = k[i];
                 const double rho = fma(gii, ki, q[i]);
-                const double nw = (a.mode == 0 ? soft(rho, a.lam) : rho) / gii;
+                const double nw = (a.mode == 0 ? soft(rho, lam) : rho) / gii;
                 const double d = nw - ki;
                 if (d != 0.0) {   // uniform across the CTA: every thread sees the same k, q
                     __syncthreads();          // all reads of q[i], k[i] done before they change
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(CD_THREADS) kf_cd_kernel(const CdArgs a) {
     double l1 = 0.0, ob = 0.0, aux = 0.0;
     for (int i = tid; i < P; i += CD_THREADS) {
         const double ki = k[i];
-        if (a.mode != 2) a.K[(long long)col * a.ldk + i] = ki;
+        if (a.mode != 2) Kcol[i] = ki;
         l1 += fabs(ki);
         if (a.mode == 1) {
             const double s0 = K0col[i];
@@ -157,26 +161,30 @@ __global__ void __launch_bounds__(CD_THREADS) kf_cd_kernel(const CdArgs a) {
     ob = cta_sum(ob, red);
     aux = cta_sum(aux, red);
     if (tid == 0) {
-        a.col_l1[col] = l1;
-        a.col_obj[col] = ob;
-        a.col_aux[col] = aux;
-        a.col_iters[col] = sweeps;
+        const long long o = (long long)bud * P + col;
+        a.col_l1[o] = l1;
+        a.col_obj[o] = ob;
+        a.col_aux[o] = aux;
+        a.col_iters[o] = sweeps;
     }
 }
 
-// single CTA: sums of the per-column outputs (fixed order -> deterministic); out[0..2] = l1, obj, aux, out[3] = max sweeps
-__global__ void __launch_bounds__(1024) kf_cd_reduce_kernel(const double* l1, const double* ob, const double* aux,
-                                                            const int* iters, int n, int skip0, int skip1, double* out) {
+// one CTA per budget: sums of the per-column outputs (fixed order -> deterministic);
+// out[b][0..2] = l1, obj, aux, out[b][3] = max sweeps
+__global__ void __launch_bounds__(256) kf_cd_reduce_kernel(const double* l1, const double* ob, const double* aux, const int* iters,
+                                                           int n, int skip0, int skip1, const int* active, double* out) {
     __shared__ double red[32];
+    const int bud = blockIdx.x;
+    if (!active[bud]) return;
+    const long long base = (long long)bud * n;
     double a = 0, b = 0, c = 0, m = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (i >= skip0 && i < skip1) continue;
-        a += l1[i]; b += ob[i]; c += aux[i]; m = fmax(m, (double)iters[i]);
+        a += l1[base + i]; b += ob[base + i]; c += aux[base + i]; m = fmax(m, (double)iters[base + i]);
     }
     a = cta_sum(a, red);
     b = cta_sum(b, red);
     c = cta_sum(c, red);
-    // max via sum trick is wrong; do a proper max reduction
     for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, off));
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(1024) kf_cd_reduce_kernel(const double* l1, co
     if (threadIdx.x == 0) {
         double mm = 0;
         for (int w = 0; w < (blockDim.x >> 5); ++w) mm = fmax(mm, red[w]);
-        out[0] = a; out[1] = b; out[2] = c; out[3] = mm;
+        out[bud * 4 + 0] = a; out[bud * 4 + 1] = b; out[bud * 4 + 2] = c; out[bud * 4 + 3] = mm;
     }
 }
 
@@ -197,27 +205,40 @@ __global__ void kf_diag_kernel(const double* G, long long ld, int P, double shif
     dG[i] = d;
 }
 
-// K = K0 - dl * D on columns outside [skip0, skip1); flags sign flips
-__global__ void kf_axpy_sign_kernel(double* K, const double* D, long long ld, int P, int ncols, int skip0, int skip1, double dl,
-                                    int* flips) {
+// budget b = blockIdx.y.  apply == 0: count sign flips of K - dl_b * D;  apply == 1: K -= dl_b * D where allowed[b]
+__global__ void kf_axpy_sign_kernel(double* K, const double* D, long long kstride, long long ld, int P, int ncols, int skip0, int skip1,
+                                    const double* dl, const int* allowed, int* flips, int apply) {
+    const int b = blockIdx.y;
+    if (!allowed[b]) return;
+    if (apply && flips[b]) return;
+    double* Kb = K + b * kstride;
+    const double* Db = D + b * kstride;
+    const double d = dl[b];
     const long long n = (long long)P * ncols;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(e % P), c = (int)(e / P);
         if (c >= skip0 && c < skip1) continue;
-        const double k0 = K[(long long)c * ld + i];
+        const double k0 = Kb[(long long)c * ld + i];
         if (k0 == 0.0) continue;
-        const double k1 = k0 - dl * D[(long long)c * ld + i];
-        if ((k1 > 0.0) != (k0 > 0.0)) atomicAdd(flips, 1);
-        K[(long long)c * ld + i] = k1;
+        const double k1 = k0 - d * Db[(long long)c * ld + i];
+        if (!apply) {
+            if ((k1 > 0.0) != (k0 > 0.0)) atomicAdd(flips + b, 1);
+        } else {
+            Kb[(long long)c * ld + i] = k1;
+        }
     }
 }
 
-__global__ void kf_scale_kernel(double* K, long long ld, int P, int ncols, int skip0, int skip1, double s) {
+__global__ void kf_scale_kernel(double* K, long long kstride, long long ld, int P, int ncols, int skip0, int skip1, const double* s) {
+    const int b = blockIdx.y;
+    const double sc = s[b];
+    if (sc == 1.0) return;
+    double* Kb = K + b * kstride;
     const long long n = (long long)P * ncols;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(e % P), c = (int)(e / P);
         if (c >= skip0 && c < skip1) continue;
-        K[(long long)c * ld + i] *= s;
+        Kb[(long long)c * ld + i] *= sc;
     }
 }
 
@@ -252,171 +273,212 @@ int ensure_cd_smem(kf_ctx* ctx, size_t smem) {
     return KF_OK;
 }
 
+struct Scratch {
+    double *dG, *c_l1, *c_ob, *c_aux, *d_out, *d_lam, *d_dl;
+    int *c_it, *d_active, *d_flips;
+};
+
+// scratch for nb budgets: dG[Pp] | l1,obj,aux [nb*Pp] | out[4 nb] | lam[nb] | dl[nb] | iters[nb*Pp] | active[nb] | flips[nb]
+int carve(kf_ctx* ctx, int Pp, int nb, Scratch* s) {
+    const size_t nd = (size_t)Pp + 3ull * nb * Pp + 6ull * nb + 8;
+    const size_t ni = (size_t)nb * Pp + 2ull * nb + 8;
+    KF_CUDA(ctx, ctx->d_K3.ensure(nd * sizeof(double) + ni * sizeof(int)));
+    double* p = ctx->d_K3.as<double>();
+    s->dG = p; p += Pp;
+    s->c_l1 = p; p += (size_t)nb * Pp;
+    s->c_ob = p; p += (size_t)nb * Pp;
+    s->c_aux = p; p += (size_t)nb * Pp;
+    s->d_out = p; p += 4 * nb;
+    s->d_lam = p; p += nb;
+    s->d_dl = p; p += nb + 8;
+    int* q = reinterpret_cast<int*>(p);
+    s->c_it = q; q += (size_t)nb * Pp;
+    s->d_active = q; q += nb;
+    s->d_flips = q;
+    return KF_OK;
+}
+
 }  // namespace
 
-// Solve one ACTIVE budget t (the caller has checked that the unconstrained minimiser violates it).
-// G (possibly shifted), C: Pp-strided P x P.  K: warm start in / solution out.  Columns [fix_c0, fix_c1) hold the
-// pinned delay pattern (already in K); `t` is the budget left for the free columns.
-// lam_start > 0: an upper bracket from the previous (smaller) budget of an ascending sweep, with K = K(lam_start)
-// and phi_start = ||K||_1 - t < 0; lam_start <= 0: cold start from lam_max with K = 0.
-int kf_solve_l1ball(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, double t, int fix_c0, int fix_c1,
-                    double lam_start, double phi_start, int max_iter, double tol, double* K, KfQpResult* res, cudaStream_t st) {
-    const long long ld = Pp;
+// Solve nb ACTIVE budgets t[0..nb) at once (the caller has checked that the unconstrained minimiser violates each).
+// G (possibly shifted), C: Pp-strided P x P.  K_all: nb matrices (stride Pp*Pp), solutions out; the pinned delay
+// columns [fix_c0, fix_c1) must already hold their pattern in every K_b; t[] is the budget left for the free columns.
+int kf_solve_l1ball_multi(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, int nb, const double* t, int fix_c0,
+                          int fix_c1, int max_iter, double tol, double* K_all, KfQpResult* res, cudaStream_t st) {
+    if (nb <= 0) return KF_OK;
+    const long long ld = Pp, kstride = (long long)Pp * Pp;
     const size_t smem = (size_t)P * (2 * sizeof(double) + sizeof(int)) + 16;
     KF_TRY(ensure_cd_smem(ctx, smem));
-    // scratch: dG[P] | l1[P] | obj[P] | aux[P] | out[4] | iters[P] | flips
-    KF_CUDA(ctx, ctx->d_K3.ensure((size_t)(4 * Pp + 8) * sizeof(double) + (size_t)(Pp + 4) * sizeof(int)));
-    double* dG = ctx->d_K3.as<double>();
-    double* c_l1 = dG + Pp;
-    double* c_ob = c_l1 + Pp;
-    double* c_aux = c_ob + Pp;
-    double* d_out = c_aux + Pp;
-    int* c_it = reinterpret_cast<int*>(d_out + 8);
-    int* d_flips = c_it + Pp;
-    KF_CUDA(ctx, ctx->d_K2.ensure((size_t)Pp * Pp * sizeof(double)));   // D = dK/dlam
-    double* D = ctx->d_K2.as<double>();
+    Scratch sc;
+    KF_TRY(carve(ctx, Pp, nb, &sc));
+    KF_CUDA(ctx, ctx->d_K2.ensure((size_t)nb * kstride * sizeof(double)));   // D_b = dK_b/dlam
+    double* D_all = ctx->d_K2.as<double>();
 
-    kf_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(G, ld, P, 0.0, nullptr, dG);
-    ctx->launches += 1;
+    kf_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(G, ld, P, 0.0, nullptr, sc.dG);
+    kf_absmax_kernel<<<1, 1024, 0, st>>>(C, ld, P, P, fix_c0, fix_c1, sc.d_out);
+    double lam_max = 0;
+    KF_CUDA(ctx, cudaMemcpyAsync(&lam_max, sc.d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    KF_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->launches += 2;
+    // K_b = 0 on the free columns (K(lam_max) = 0)
+    for (int b = 0; b < nb; ++b) {
+        double* Kb = K_all + b * kstride;
+        if (fix_c0 > 0) KF_CUDA(ctx, cudaMemset2DAsync(Kb, ld * sizeof(double), 0, (size_t)P * sizeof(double), fix_c0, st));
+        if (fix_c1 < P)
+            KF_CUDA(ctx, cudaMemset2DAsync(Kb + (size_t)std::max(fix_c1, 0) * ld, ld * sizeof(double), 0, (size_t)P * sizeof(double),
+                                           P - std::max(fix_c1, 0), st));
+    }
 
-    // inner sweeps per evaluation are bounded so that an ill-conditioned Gram cannot run away; a column that
-    // hits the bound is reported through res->capped
+    // inner sweeps per evaluation are bounded so that an ill-conditioned Gram cannot run away
     const int max_sweeps = max_iter > 0 ? max_iter : (P <= 256 ? 100000 : 2000);
     const double cd_tol = tol > 0 ? tol : 1e-13;
-    int evals = 0, capped = 0;
-    double h[4];
-    auto run_cd = [&](int mode, double lam, double* Kout, const double* K0) -> int {
+
+    struct BState { double lam_hi, phi_hi, lam_lo, phi_lo, lam, l1; int side, phase, its, evals, capped; };   // phase 0 bracket, 1 secant, 2 done
+    std::vector<BState> B(nb);
+    std::vector<double> h_lam(nb), h_out(4 * nb), h_dl(nb, 0.0);
+    std::vector<int> h_act(nb, 0);
+    for (int b = 0; b < nb; ++b) B[b] = BState{lam_max, -t[b], 0, 0, lam_max, 0, 0, 0, 0, 0, 0};
+
+    auto launch = [&](int mode, double* Kout, const double* K0) -> int {
+        KF_CUDA(ctx, cudaMemcpyAsync(sc.d_lam, h_lam.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+        KF_CUDA(ctx, cudaMemcpyAsync(sc.d_active, h_act.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
         CdArgs a{};
-        a.G = G; a.ldg = ld; a.dG = dG; a.R = C; a.ldr = ld;
-        a.K = Kout; a.ldk = ld; a.K0 = K0; a.ldk0 = ld;
-        a.P = P; a.col0 = 0; a.skip0 = fix_c0; a.skip1 = fix_c1;
-        a.lam = lam; a.tol = cd_tol; a.max_sweeps = max_sweeps; a.mode = mode;
-        a.col_l1 = c_l1; a.col_obj = c_ob; a.col_aux = c_aux; a.col_iters = c_it;
-        kf_cd_kernel<<<P, CD_THREADS, smem, st>>>(a);
-        kf_cd_reduce_kernel<<<1, 1024, 0, st>>>(c_l1, c_ob, c_aux, c_it, P, fix_c0, fix_c1, d_out);
+        a.G = G; a.ldg = ld; a.dG = sc.dG; a.R = C; a.ldr = ld;
+        a.K = Kout; a.ldk = ld; a.K0 = K0; a.ldk0 = ld; a.kstride = kstride;
+        a.P = P; a.skip0 = fix_c0; a.skip1 = fix_c1;
+        a.lam = sc.d_lam; a.active = sc.d_active; a.tol = cd_tol; a.max_sweeps = max_sweeps; a.mode = mode;
+        a.col_l1 = sc.c_l1; a.col_obj = sc.c_ob; a.col_aux = sc.c_aux; a.col_iters = sc.c_it;
+        kf_cd_kernel<<<dim3(P, nb), CD_THREADS, smem, st>>>(a);
+        kf_cd_reduce_kernel<<<nb, 256, 0, st>>>(sc.c_l1, sc.c_ob, sc.c_aux, sc.c_it, P, fix_c0, fix_c1, sc.d_active, sc.d_out);
         KF_CUDA(ctx, cudaGetLastError());
-        KF_CUDA(ctx, cudaMemcpyAsync(h, d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaMemcpyAsync(h_out.data(), sc.d_out, sizeof(double) * 4 * nb, cudaMemcpyDeviceToHost, st));
         KF_CUDA(ctx, cudaStreamSynchronize(st));
         ctx->launches += 2;
-        ++evals;
-        if (mode != 2 && h[3] >= max_sweeps) ++capped;
         return KF_OK;
     };
 
-    double lam_hi, phi_hi, lam_lo = 0, phi_lo = 0, lam;
-    if (lam_start > 0) {
-        lam_hi = lam_start;
-        phi_hi = phi_start;
-    } else {
-        kf_absmax_kernel<<<1, 1024, 0, st>>>(C, ld, P, P, fix_c0, fix_c1, d_out);
-        double lam_max = 0;
-        KF_CUDA(ctx, cudaMemcpyAsync(&lam_max, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
-        KF_CUDA(ctx, cudaStreamSynchronize(st));
-        ctx->launches += 1;
-        lam_hi = lam_max;   // K(lam_max) = 0
-        phi_hi = -t;
-        if (fix_c0 > 0) KF_CUDA(ctx, cudaMemset2DAsync(K, ld * sizeof(double), 0, (size_t)P * sizeof(double), fix_c0, st));
-        if (fix_c1 < P)   // the pinned columns [fix_c0, fix_c1) keep their pattern
-            KF_CUDA(ctx, cudaMemset2DAsync(K + (size_t)std::max(fix_c1, 0) * ld, ld * sizeof(double), 0, (size_t)P * sizeof(double),
-                                           P - std::max(fix_c1, 0), st));
-    }
-    // 1. bracket: shrink lam geometrically (warm-started) until ||K||_1 > t
-    lam = lam_hi;
-    bool bracket = false;
-    for (int it = 0; it < 200; ++it) {
-        lam *= 0.5;
-        KF_TRY(run_cd(0, lam, K, nullptr));
-        const double phi = h[0] - t;
-        if (phi > 0) { lam_lo = lam; phi_lo = phi; bracket = true; break; }
-        lam_hi = lam; phi_hi = phi;
-        if (lam < 1e-300) break;
-    }
-    if (bracket) {
-        // 2. Illinois secant on phi(lam) = ||K(lam)||_1 - t; the exact step below removes the remaining error,
-        //    so a modest tolerance is enough here
-        int side = 0;
-        for (int it = 0; it < 60; ++it) {
-            lam = (lam_lo * phi_hi - lam_hi * phi_lo) / (phi_hi - phi_lo);
-            if (!(lam > lam_lo && lam < lam_hi)) lam = 0.5 * (lam_lo + lam_hi);
-            KF_TRY(run_cd(0, lam, K, nullptr));
-            const double phi = h[0] - t;
-            if (fabs(phi) <= 1e-10 * t) break;
-            if (phi > 0) {
-                lam_lo = lam; phi_lo = phi;
-                if (side == 1) phi_hi *= 0.5;
-                side = 1;
+    // ---- lockstep bracketing + Illinois secant, one multiplier per budget
+    for (int round = 0; round < 320; ++round) {
+        int nact = 0;
+        for (int b = 0; b < nb; ++b) {
+            BState& s = B[b];
+            h_act[b] = 0;
+            if (s.phase == 2) continue;
+            if (s.phase == 0) {
+                s.lam *= 0.5;
+                if (s.lam < 1e-300 || s.its >= 200) { s.phase = 2; continue; }
             } else {
-                lam_hi = lam; phi_hi = phi;
-                if (side == -1) phi_lo *= 0.5;
-                side = -1;
+                if (s.its >= 60 || s.lam_hi - s.lam_lo <= 1e-14 * s.lam_hi) { s.phase = 2; continue; }
+                double l = (s.lam_lo * s.phi_hi - s.lam_hi * s.phi_lo) / (s.phi_hi - s.phi_lo);
+                if (!(l > s.lam_lo && l < s.lam_hi)) l = 0.5 * (s.lam_lo + s.lam_hi);
+                s.lam = l;
             }
-            if (lam_hi - lam_lo <= 1e-14 * lam_hi) break;
+            h_lam[b] = s.lam;
+            h_act[b] = 1;
+            ++nact;
         }
-        // 3. exact last step on the fixed sign pattern: D = dK/dlam, ||K(lam + dl)||_1 = ||K||_1 - dl * sum s'd
-        const double l1_0 = h[0];
-        KF_TRY(run_cd(1, 0.0, D, K));
-        const double den = h[2];
-        if (den > 0) {
-            const double dl = (l1_0 - t) / den;
-            KF_CUDA(ctx, cudaMemsetAsync(d_flips, 0, sizeof(int), st));
-            KF_CUDA(ctx, ctx->d_tmp.ensure((size_t)Pp * Pp * sizeof(double)));
-            double* Kbak = ctx->d_tmp.as<double>();
-            KF_CUDA(ctx, cudaMemcpyAsync(Kbak, K, (size_t)Pp * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
-            kf_axpy_sign_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(K, D, ld, P, P, fix_c0, fix_c1, dl, d_flips);
-            int flips = 0;
-            KF_CUDA(ctx, cudaMemcpyAsync(&flips, d_flips, sizeof(int), cudaMemcpyDeviceToHost, st));
-            KF_CUDA(ctx, cudaStreamSynchronize(st));
-            if (flips) KF_CUDA(ctx, cudaMemcpyAsync(K, Kbak, (size_t)Pp * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
-            else lam += dl;
+        if (!nact) break;
+        KF_TRY(launch(0, K_all, nullptr));
+        for (int b = 0; b < nb; ++b) {
+            if (!h_act[b]) continue;
+            BState& s = B[b];
+            ++s.evals;
+            ++s.its;
+            if (h_out[4 * b + 3] >= max_sweeps) ++s.capped;
+            s.l1 = h_out[4 * b + 0];
+            const double phi = s.l1 - t[b];
+            if (s.phase == 0) {
+                if (phi > 0) { s.lam_lo = s.lam; s.phi_lo = phi; s.phase = 1; s.its = 0; s.side = 0; }
+                else { s.lam_hi = s.lam; s.phi_hi = phi; }
+            } else {
+                if (fabs(phi) <= 1e-10 * t[b]) { s.phase = 2; continue; }
+                if (phi > 0) {
+                    s.lam_lo = s.lam; s.phi_lo = phi;
+                    if (s.side == 1) s.phi_hi *= 0.5;
+                    s.side = 1;
+                } else {
+                    s.lam_hi = s.lam; s.phi_hi = phi;
+                    if (s.side == -1) s.phi_lo *= 0.5;
+                    s.side = -1;
+                }
+            }
         }
     }
-    // 4. evaluate; enforce feasibility to rounding
-    KF_TRY(run_cd(2, 0.0, K, nullptr));
-    if (h[0] > t && h[0] > 0) {
-        kf_scale_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(K, ld, P, P, fix_c0, fix_c1, t / h[0]);
-        KF_TRY(run_cd(2, 0.0, K, nullptr));
+    // ---- exact last step on the fixed sign pattern: D = dK/dlam, ||K(lam + dl)||_1 = ||K||_1 - dl * sum s'd
+    for (int b = 0; b < nb; ++b) { h_act[b] = 1; h_lam[b] = 0.0; }
+    KF_TRY(launch(1, D_all, K_all));
+    std::vector<int> allowed(nb, 0);
+    for (int b = 0; b < nb; ++b) {
+        const double den = h_out[4 * b + 2];
+        if (den > 0 && B[b].l1 > 0) { h_dl[b] = (B[b].l1 - t[b]) / den; allowed[b] = 1; }
     }
-    res->objective = h[1];
-    res->l1 = h[0];
-    res->iters = evals;
-    res->lam = lam;
-    res->capped = capped;
+    KF_CUDA(ctx, cudaMemcpyAsync(sc.d_dl, h_dl.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+    KF_CUDA(ctx, cudaMemcpyAsync(sc.d_active, allowed.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+    KF_CUDA(ctx, cudaMemsetAsync(sc.d_flips, 0, sizeof(int) * nb, st));
+    const dim3 egrid(ctx->sm_count * 2, nb);
+    kf_axpy_sign_kernel<<<egrid, 256, 0, st>>>(K_all, D_all, kstride, ld, P, P, fix_c0, fix_c1, sc.d_dl, sc.d_active, sc.d_flips, 0);
+    kf_axpy_sign_kernel<<<egrid, 256, 0, st>>>(K_all, D_all, kstride, ld, P, P, fix_c0, fix_c1, sc.d_dl, sc.d_active, sc.d_flips, 1);
+    std::vector<int> flips(nb, 0);
+    KF_CUDA(ctx, cudaMemcpyAsync(flips.data(), sc.d_flips, sizeof(int) * nb, cudaMemcpyDeviceToHost, st));
+    KF_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->launches += 2;
+    for (int b = 0; b < nb; ++b)
+        if (allowed[b] && !flips[b]) B[b].lam += h_dl[b];
+    // ---- evaluate; enforce feasibility to rounding
+    for (int b = 0; b < nb; ++b) h_act[b] = 1;
+    KF_TRY(launch(2, K_all, nullptr));
+    bool rescale = false;
+    std::vector<double> scl(nb, 1.0);
+    for (int b = 0; b < nb; ++b)
+        if (h_out[4 * b] > t[b] && h_out[4 * b] > 0) { scl[b] = t[b] / h_out[4 * b]; rescale = true; }
+    if (rescale) {
+        KF_CUDA(ctx, cudaMemcpyAsync(sc.d_dl, scl.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+        kf_scale_kernel<<<egrid, 256, 0, st>>>(K_all, kstride, ld, P, P, fix_c0, fix_c1, sc.d_dl);
+        KF_TRY(launch(2, K_all, nullptr));
+    }
+    for (int b = 0; b < nb; ++b) {
+        res[b].l1 = h_out[4 * b + 0];
+        res[b].objective = h_out[4 * b + 1];
+        res[b].iters = B[b].evals;
+        res[b].lam = B[b].lam;
+        res[b].capped = B[b].capped;
+    }
     return KF_OK;
 }
 
 // G += shift * I  (the PSD conditioning branch, Ksysid.m:1119)
 int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_t st) {
-    KF_CUDA(ctx, ctx->d_K3.ensure((size_t)(4 * Pp + 8) * sizeof(double) + (size_t)(Pp + 4) * sizeof(int)));
-    kf_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(G, Pp, P, shift, G, ctx->d_K3.as<double>());
+    Scratch sc;
+    KF_TRY(carve(ctx, Pp, 1, &sc));
+    kf_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(G, Pp, P, shift, G, sc.dG);
     KF_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return KF_OK;
 }
 
-// objective 0.5 tr(K'GK) - tr(C'K) and ||vec K||_1 over all P columns
+// objective 0.5 tr(K'GK) - tr(C'K) and ||vec K||_1 over ALL P columns of one matrix
 int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, KfQpResult* res, cudaStream_t st) {
     const long long ld = Pp;
     const size_t smem = (size_t)P * (2 * sizeof(double) + sizeof(int)) + 16;
     KF_TRY(ensure_cd_smem(ctx, smem));
-    KF_CUDA(ctx, ctx->d_K3.ensure((size_t)(4 * Pp + 8) * sizeof(double) + (size_t)(Pp + 4) * sizeof(int)));
-    double* dG = ctx->d_K3.as<double>();
-    double* c_l1 = dG + Pp;
-    double* c_ob = c_l1 + Pp;
-    double* c_aux = c_ob + Pp;
-    double* d_out = c_aux + Pp;
-    int* c_it = reinterpret_cast<int*>(d_out + 8);
-    kf_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(G, ld, P, 0.0, nullptr, dG);
+    Scratch sc;
+    KF_TRY(carve(ctx, Pp, 1, &sc));
+    kf_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(G, ld, P, 0.0, nullptr, sc.dG);
+    const double zero = 0.0;
+    const int one = 1;
+    KF_CUDA(ctx, cudaMemcpyAsync(sc.d_lam, &zero, sizeof(double), cudaMemcpyHostToDevice, st));
+    KF_CUDA(ctx, cudaMemcpyAsync(sc.d_active, &one, sizeof(int), cudaMemcpyHostToDevice, st));
     CdArgs a{};
-    a.G = G; a.ldg = ld; a.dG = dG; a.R = C; a.ldr = ld;
-    a.K = const_cast<double*>(K); a.ldk = ld; a.K0 = nullptr; a.ldk0 = ld;
-    a.P = P; a.col0 = 0; a.skip0 = 0; a.skip1 = 0;
-    a.lam = 0; a.tol = 0; a.max_sweeps = 0; a.mode = 2;
-    a.col_l1 = c_l1; a.col_obj = c_ob; a.col_aux = c_aux; a.col_iters = c_it;
-    kf_cd_kernel<<<P, CD_THREADS, smem, st>>>(a);
-    kf_cd_reduce_kernel<<<1, 1024, 0, st>>>(c_l1, c_ob, c_aux, c_it, P, 0, 0, d_out);
+    a.G = G; a.ldg = ld; a.dG = sc.dG; a.R = C; a.ldr = ld;
+    a.K = const_cast<double*>(K); a.ldk = ld; a.K0 = nullptr; a.ldk0 = ld; a.kstride = 0;
+    a.P = P; a.skip0 = 0; a.skip1 = 0;
+    a.lam = sc.d_lam; a.active = sc.d_active; a.tol = 0; a.max_sweeps = 0; a.mode = 2;
+    a.col_l1 = sc.c_l1; a.col_obj = sc.c_ob; a.col_aux = sc.c_aux; a.col_iters = sc.c_it;
+    kf_cd_kernel<<<dim3(P, 1), CD_THREADS, smem, st>>>(a);
+    kf_cd_reduce_kernel<<<1, 256, 0, st>>>(sc.c_l1, sc.c_ob, sc.c_aux, sc.c_it, P, 0, 0, sc.d_active, sc.d_out);
     KF_CUDA(ctx, cudaGetLastError());
     double h[4];
-    KF_CUDA(ctx, cudaMemcpyAsync(h, d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    KF_CUDA(ctx, cudaMemcpyAsync(h, sc.d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     KF_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->launches += 3;
     res->l1 = h[0];
