@@ -213,3 +213,26 @@ def test_fit_sharded_single_rank_lasso_vector(fitter):
         assert abs(fg - fo) <= 1e-8 * abs(fo)
     res = fit_sharded(fitter, basis, "linear", ta, tb, tu, P, ls_method="gram")
     assert relF(res["K"], O.mldivide(Px, Py)) < 1e-9
+
+
+def test_config5_parity_on_subsample(fitter):
+    """BASELINE config 5 (n=12, m=3, {'poly','gaussian'},[3,569] -> N=1024, bilinear P=4096) on a subsample of the
+    bench workload: the Gram route the benchmark times (Kronecker-block DMMA accumulation + pivoted Cholesky) against
+    the oracle's dgeqp3 solution: A, B_i to 1e-9 (parity for C5 on a subsample)."""
+    import bench
+    M = 6144
+    _, _, centres = bench.workload_constants()
+    alpha, beta, u = bench.gen_numpy(M, seed=7)
+    prog = O.build_program(bench.OBS_TYPE, bench.OBS_DEGREE, bench.NZETA, centres)
+    basis = koopfit.Basis(bench.OBS_TYPE, bench.OBS_DEGREE, bench.NZETA, centres)
+    Px, Py = O.build_regressors("bilinear", prog, alpha, beta, u)
+    assert Px.shape == (M, 4096)
+    res = fitter.fit(basis, "bilinear", alpha, beta, u, want_gram=True, ls_method="gram")
+    G, C = O.gram(Px, Py)
+    assert relF(res["G"], G) < 1e-13 and relF(res["C"], C) < 1e-13
+    Ko, info = O.mldivide(Px, Py, return_info=True)
+    assert res["rank"] == info["rank"] == 4096
+    N = 1024
+    assert relF(res["K"].T[:N, :N], Ko.T[:N, :N]) < 1e-9
+    for i in range(3):
+        assert relF(res["K"].T[:N, N * (i + 1):N * (i + 2)], Ko.T[:N, N * (i + 1):N * (i + 2)]) < 1e-9
