@@ -61,6 +61,10 @@ typedef struct {
     const double* alpha;    /* M x nzeta */
     const double* beta;     /* M x nzeta */
     const double* u;        /* M x m */
+    int pc_cols;            /* opt-in fast mode: compute only the first pc_cols columns of K (and C); 0 = all P.
+                               Downstream only K(:,1:N) (linear, bilinear: A, B — Ksysid.m:1199-1200, 1258-1259) or
+                               K(:,1:nzeta) (nonlinear: F — 1329) is consumed; least-squares branch only. */
+    int reserved;
 } kf_problem;
 
 /* how to solve (Ksysid.m:1068-1080) */
@@ -96,7 +100,7 @@ typedef struct {
 
 /* caller-allocated outputs; NULL members are skipped */
 typedef struct {
-    double* K;              /* P x P x max(1,nt): koopData.K (Ksysid.m:1084) */
+    double* K;              /* P x Pc x max(1,nt), Pc = pc_cols or P: koopData.K (Ksysid.m:1084) */
     double* G;              /* P x P : Px'Px (Ksysid.m:1114) */
     double* C;              /* P x P : Px'Py (Ksysid.m:1125) */
     double* Px;             /* M x P : regressor (Ksysid.m:1019-1065); koopData.Px = Px(:,1:N) */

@@ -38,7 +38,8 @@ class kf_basis(C.Structure):
 
 class kf_problem(C.Structure):
     _fields_ = [("M", C.c_longlong), ("nzeta", C.c_int), ("m", C.c_int), ("model", C.c_int),
-                ("alpha", C.c_void_p), ("beta", C.c_void_p), ("u", C.c_void_p)]
+                ("alpha", C.c_void_p), ("beta", C.c_void_p), ("u", C.c_void_p),
+                ("pc_cols", C.c_int), ("reserved", C.c_int)]
 
 
 class kf_solve(C.Structure):

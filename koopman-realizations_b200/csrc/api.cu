@@ -84,6 +84,7 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
     L.w_off = L.Rxp + L.Nyp;
     L.rows = L.w_off + (int)kf_roundup(L.nW, 8);
     L.Pp = (int)kf_roundup(L.P, KF_BM);
+    L.Pc = (pr->pc_cols > 0 && pr->pc_cols < L.P) ? pr->pc_cols : L.P;
 
     // chunk: one panel should stay L2-resident
     long long Mc = ctx->opt_chunk > 0 ? ctx->opt_chunk
@@ -99,8 +100,17 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
             const int q = (L.model == KF_BILINEAR) ? pair_index(a, b, L.m) : 0;
             for (int tm = 0; tm < tmx; ++tm)
                 for (int tn = 0; tn <= tm; ++tn) L.tiles.push_back(KfTile{0, q, a, b, tm, tn});
+            // C tiles: only the column blocks that reach the first Pc columns of K (pc_cols fast mode).
+            // bilinear: stored block (a,b), a <= b, serves C[(a,.),(b,.)] and C[(b,.),(a,.)] -> needed iff a < ceil(Pc/N);
+            // otherwise: tile columns below min(Pc, N) (the u columns of a linear model come from G).
+            int tn_end = tny;
+            if (L.model == KF_BILINEAR) {
+                if (a >= (L.Pc + L.N - 1) / L.N) tn_end = 0;
+            } else {
+                tn_end = std::min(tny, (std::min(L.Pc, L.N) + KF_BN - 1) / KF_BN);
+            }
             for (int tm = 0; tm < tmx; ++tm)
-                for (int tn = 0; tn < tny; ++tn) L.tiles.push_back(KfTile{1, q, a, b, tm, tn});
+                for (int tn = 0; tn < tn_end; ++tn) L.tiles.push_back(KfTile{1, q, a, b, tm, tn});
         }
     const int T = (int)L.tiles.size();
     const int ksteps = L.Mc / KF_BK;
@@ -194,8 +204,10 @@ int ntasks_of(const KfLayout& L) {
 
 bool same_layout(const KfLayout& L, const KfProgram& p, const kf_problem* pr, int Mc_hint) {
     (void)Mc_hint;
+    const int P = kf_regressor_width(pr->model, p.N(), pr->m);
+    const int Pc = (pr->pc_cols > 0 && pr->pc_cols < P) ? pr->pc_cols : P;
     return L.valid && L.model == pr->model && L.m == pr->m && L.nzeta == pr->nzeta && L.n_full == p.n_full() &&
-           L.N == p.N();
+           L.N == p.N() && L.Pc == Pc;
 }
 
 // lift + Gram of one shard whose snapshots are on the device
@@ -284,10 +296,10 @@ int finish_accum(kf_ctx* ctx) {
     return KF_OK;
 }
 
-int copy_out_matrix(kf_ctx* ctx, const double* d, int Pp, int P, double* h) {
+int copy_out_matrix(kf_ctx* ctx, const double* d, int Pp, int P, double* h, int ncols = -1) {
     if (!h) return KF_OK;
-    KF_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)P * sizeof(double), d, (size_t)Pp * sizeof(double), (size_t)P * sizeof(double), P,
-                                   cudaMemcpyDeviceToHost, ctx->stream));
+    KF_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)P * sizeof(double), d, (size_t)Pp * sizeof(double), (size_t)P * sizeof(double),
+                                   ncols < 0 ? P : ncols, cudaMemcpyDeviceToHost, ctx->stream));
     return KF_OK;
 }
 
@@ -330,17 +342,21 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
         const double tol = sv->pivot_tol > 0 ? sv->pivot_tol : 1e-7;
         int rank = 0;
         double minp = 0, maxp = 0;
-        KF_TRY(kf_solve_gram_ls(ctx, P, Pp, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), tol, d_perm,
+        KF_TRY(kf_solve_gram_ls(ctx, P, Pp, L.Pc, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), tol, d_perm,
                                 &rank, &minp, &maxp, st));
         out->info.rank = rank;
         out->info.ls_method_used = KF_LS_GRAM;
         out->info.min_pivot = minp;
         out->info.max_pivot = maxp;
-        KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K));
+        KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K, L.Pc));
         if (out->perm) KF_CUDA(ctx, cudaMemcpyAsync(out->perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
     } else {
         if (sv->nt <= 0 || !sv->t) {
             ctx->err = "kf_solve: QP branch needs nt > 0 budgets";
+            return KF_EINVAL;
+        }
+        if (L.Pc != P) {
+            ctx->err = "pc_cols (column-restricted K) is only valid for the least-squares branch: the L1 budget couples all P columns";
             return KF_EINVAL;
         }
         // --- `any(eig(G) < 0)` -> G += 1e-6 I (Ksysid.m:1117-1120).  For a numerically singular G the sign
@@ -350,13 +366,13 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
         int rank = 0;
         double minp = 0, maxp = 0;
         KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_W.p, ctx->d_G.p, mat, cudaMemcpyDeviceToDevice, st));
-        KF_TRY(kf_solve_gram_ls(ctx, P, Pp, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), tol, d_perm,
+        KF_TRY(kf_solve_gram_ls(ctx, P, Pp, P, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), tol, d_perm,
                                 &rank, &minp, &maxp, st));
         bool shift = sv->psd_shift == KF_PSD_ALWAYS || (sv->psd_shift == KF_PSD_AS_REFERENCE && rank < P);
         if (shift) {
             KF_TRY(kf_add_diag(ctx, ctx->d_G.as<double>(), Pp, P, 1e-6, st));
             KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_W.p, ctx->d_G.p, mat, cudaMemcpyDeviceToDevice, st));
-            KF_TRY(kf_solve_gram_ls(ctx, P, Pp, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), 1e-14,
+            KF_TRY(kf_solve_gram_ls(ctx, P, Pp, P, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), 1e-14,
                                     d_perm, &rank, &minp, &maxp, st));   // unconstrained minimiser of the shifted problem
             if (out->G) KF_TRY(copy_out_matrix(ctx, ctx->d_G.as<double>(), Pp, P, out->G));   // the G the QP used
         }
@@ -674,13 +690,14 @@ int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_
         int* d_perm = reinterpret_cast<int*>(ctx->d_misc.as<char>() + 1024);
         int rank = 0;
         double minp = 0, maxp = 0;
-        KF_TRY(kf_solve_qr_ls(ctx, M, P, P, ctx->d_qr.as<double>(), M, ctx->d_K.as<double>(), Pp, d_perm, &rank, &minp, &maxp, st));
+        const int Pc = ctx->lay.Pc;
+        KF_TRY(kf_solve_qr_ls(ctx, M, P, Pc, ctx->d_qr.as<double>(), M, ctx->d_K.as<double>(), Pp, d_perm, &rank, &minp, &maxp, st));
         out->info.rank = rank;
         out->info.ls_method_used = KF_LS_QR;
         out->info.min_pivot = minp;
         out->info.max_pivot = maxp;
         out->info.passes = 2;
-        KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K));
+        KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K, Pc));
         if (out->perm) KF_CUDA(ctx, cudaMemcpyAsync(out->perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
         KF_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
         KF_CUDA(ctx, cudaStreamSynchronize(st));
@@ -710,7 +727,7 @@ int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_
         int N = 0, P = 0;
         if (!bases[i]) { ctx->err = "kf_fit_batch: NULL basis"; return KF_EINVAL; }
         KF_TRY(kf_basis_dims(bases[i], probs[i].model, probs[i].m, nullptr, &N, &P));
-        const bool ok = solves[i].least_squares && P <= 32 && bases[i]->n_pcs == 0 && probs[i].M > 0 && probs[i].alpha &&
+        const bool ok = solves[i].least_squares && P <= 32 && probs[i].pc_cols == 0 && bases[i]->n_pcs == 0 && probs[i].M > 0 && probs[i].alpha &&
                         probs[i].beta && (probs[i].m == 0 || probs[i].u) && !outs[i].G && !outs[i].C && !outs[i].Px && !outs[i].Py &&
                         (probs[i].model == KF_LINEAR || probs[i].model == KF_BILINEAR || probs[i].model == KF_NONLINEAR) &&
                         bases[i]->nv == probs[i].nzeta + (probs[i].model == KF_NONLINEAR ? probs[i].m : 0);

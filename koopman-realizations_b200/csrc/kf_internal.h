@@ -87,6 +87,7 @@ struct KfTile {
 struct KfLayout {
     int model = 0, m = 0, nzeta = 0, nv = 0;
     int n_full = 0, N = 0, P = 0;
+    int Pc = 0;               // columns of C / K actually computed (pc_cols fast mode), <= P
     int Rx = 0, Rxp = 0;      // rows of the X section: N (+m for linear), padded to BM
     int Ny = 0, Nyp = 0;      // rows of the Y section (N), padded
     int nW = 0;               // weight rows (bilinear): (m+1)(m+2)/2
@@ -189,7 +190,7 @@ int kf_reduce_slabs(kf_ctx* ctx, double* accum, long long slab_elems, int nsplit
 int kf_assemble(kf_ctx* ctx, const double* accum, const KfTile* d_meta, int ntiles, const KfLayout& lay,
                 double* G, double* C, cudaStream_t st);
 // pivoted Cholesky basic solution of G K = C  (G, C, K: Pp x Pp column-major, ld = Pp)
-int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, double* G_work, const double* C, double* K, double tol,
+int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, int ncols, double* G_work, const double* C, double* K, double tol,
                      int* d_perm, int* rank_out, double* min_piv, double* max_piv, cudaStream_t st);
 // Householder QRCP basic solution of A X = B;  AB = [A | B] (M x (P+Pc), ld = ldab) is overwritten
 int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long long ldab, double* X, long long ldx,

@@ -467,7 +467,7 @@ static int trsm_both(kf_ctx* ctx, const double* W, long long ld, int P, int rank
     return KF_OK;
 }
 
-int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, double* W, const double* C, double* K, double tol, int* d_perm,
+int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const double* C, double* K, double tol, int* d_perm,
                      int* rank_out, double* min_piv, double* max_piv, cudaStream_t st) {
     // state block in d_misc: [PcholState]
     KF_CUDA(ctx, ctx->d_misc.ensure(4096));
@@ -539,12 +539,12 @@ int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, double* W, const double* C, dou
     // X = C(perm[0:r], :) in the K buffer's scratch twin (d_tmp), solve, scatter
     KF_CUDA(ctx, ctx->d_tmp.ensure((size_t)Pp * Pp * sizeof(double)));
     double* X = ctx->d_tmp.as<double>();
-    kf_gather_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(C, ld, d_perm, d_state, Pp, P, X, ld);
+    kf_gather_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(C, ld, d_perm, d_state, Pp, ncols, X, ld);
     KF_CUDA(ctx, cudaGetLastError());
     KF_CUDA(ctx, cudaMemsetAsync(K, 0, (size_t)Pp * Pp * sizeof(double), st));
     if (r > 0) {
-        KF_TRY(trsm_both(ctx, W, ld, P, r, &d_state->rank, X, ld, P, st));
-        kf_scatter_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(X, ld, d_perm, &d_state->rank, P, K, ld);
+        KF_TRY(trsm_both(ctx, W, ld, P, r, &d_state->rank, X, ld, ncols, st));
+        kf_scatter_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(X, ld, d_perm, &d_state->rank, ncols, K, ld);
         KF_CUDA(ctx, cudaGetLastError());
     }
     ctx->launches += 4;

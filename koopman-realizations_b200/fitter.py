@@ -96,19 +96,21 @@ class Fitter:
         sv.qp_tol = float(qp_tol)
         return sv, keep
 
-    def fit(self, basis, model_type, alpha, beta, u, want_gram=False, want_regressors=False, **solve_kw):
+    def fit(self, basis, model_type, alpha, beta, u, want_gram=False, want_regressors=False, pc_cols=0, **solve_kw):
         """get_Koopman for host snapshot pairs (Ksysid.m:987-1092): returns dict with K (P x P, or
-        P x P x nt for a budget vector), rank, perm, info and optionally G, C, Px, Py."""
+        P x P x nt for a budget vector), rank, perm, info and optionally G, C, Px, Py.
+        pc_cols > 0 (opt-in fast mode, least squares only): only the first pc_cols columns of K are computed."""
         alpha, beta, u = A.fcol(alpha), A.fcol(beta), A.fcol(u)
         M, nzeta = alpha.shape
         m = u.shape[1]
         _, N, P = self.dims(basis, model_type, m)
+        Pc = int(pc_cols) if 0 < int(pc_cols) < P else P
         pr = A.kf_problem(M=M, nzeta=nzeta, m=m, model=A.MODEL_CODE[model_type],
-                          alpha=alpha.ctypes.data, beta=beta.ctypes.data, u=u.ctypes.data)
+                          alpha=alpha.ctypes.data, beta=beta.ctypes.data, u=u.ctypes.data, pc_cols=int(pc_cols))
         sv, keep_t = self._solve_struct(**solve_kw)
         nt = max(1, sv.nt) if not sv.least_squares else 1
         res = A.kf_result()
-        K = np.zeros((P, P, nt), order="F")
+        K = np.zeros((P, Pc, nt), order="F")
         perm = np.zeros(P, dtype=np.int32)
         obj, l1 = np.zeros(nt), np.zeros(nt)
         iters = np.zeros(nt, dtype=np.int32)
@@ -183,11 +185,11 @@ class Fitter:
         return X, rank.value, perm
 
     # ------------------------------------------------------------------ staged / device-resident API
-    def accumulate_dev(self, basis, model_type, M, nzeta, m, alpha_ptr, beta_ptr, u_ptr, reset=True):
+    def accumulate_dev(self, basis, model_type, M, nzeta, m, alpha_ptr, beta_ptr, u_ptr, reset=True, pc_cols=0):
         """Partial Gram of a device-resident shard (pointers from torch tensors' data_ptr());
         column-major M x nzeta / M x m, i.e. torch tensors of shape (nzeta, M) contiguous."""
         pr = A.kf_problem(M=int(M), nzeta=int(nzeta), m=int(m), model=A.MODEL_CODE[model_type],
-                          alpha=int(alpha_ptr), beta=int(beta_ptr), u=int(u_ptr))
+                          alpha=int(alpha_ptr), beta=int(beta_ptr), u=int(u_ptr), pc_cols=int(pc_cols))
         self._check(self.lib.kf_accumulate_dev(self.ctx, basis.ref(), C.byref(pr), int(reset)), "kf_accumulate_dev")
 
     def accum_buffer(self):
@@ -196,11 +198,13 @@ class Fitter:
         self._check(self.lib.kf_accum_buffer(self.ctx, C.byref(p), C.byref(n)), "kf_accum_buffer")
         return p.value, n.value
 
-    def solve_dev(self, P, want_gram=False, **solve_kw):
+    def solve_dev(self, P, want_gram=False, pc_cols=0, **solve_kw):
+        """Solve from the (all-reduced) accumulator; pc_cols must match the one given to accumulate_dev."""
         sv, keep_t = self._solve_struct(**solve_kw)
         nt = max(1, sv.nt) if not sv.least_squares else 1
         res = A.kf_result()
-        K = np.zeros((P, P, nt), order="F")
+        Pc = int(pc_cols) if 0 < int(pc_cols) < P else P
+        K = np.zeros((P, Pc, nt), order="F")
         perm = np.zeros(P, dtype=np.int32)
         obj, l1 = np.zeros(nt), np.zeros(nt)
         iters = np.zeros(nt, dtype=np.int32)

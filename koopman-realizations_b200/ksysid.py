@@ -73,7 +73,7 @@ class Ksysid:
         self.loaded = False
         self.time_type = "discrete"
         self.dim_red = None
-        extras = {"centres": None, "device": 0, "fitter": None, "ls_method": "auto", "rng_seed": 0}
+        extras = {"centres": None, "device": 0, "fitter": None, "ls_method": "auto", "rng_seed": 0, "fast_cols": False}
         for k, v in kw.items():          # parse_args, Ksysid.m:147-158
             if k in extras:
                 extras[k] = v
@@ -93,6 +93,8 @@ class Ksysid:
             raise NotImplementedError("continuous-time (logm) models are outside the hot-path scope (SURVEY §8f #4)")
         self.liftinput = {"linear": 0, "nonlinear": 1, "bilinear": 2}[self.model_type]
         self._ls_method = extras["ls_method"]
+        # opt-in: compute only the K columns the model consumes (K(:,1:N) or K(:,1:nzeta)); model['K'] is then P x Pc
+        self._fast_cols = bool(extras["fast_cols"])
 
         tr0 = data4sysid["train"][0]
         y0, u0 = np.atleast_2d(np.asarray(tr0["y"], float)), np.atleast_2d(np.asarray(tr0["u"], float))
@@ -216,8 +218,10 @@ class Ksysid:
         lasso = self.lasso if lasso is None else np.atleast_1d(np.asarray(lasso, dtype=np.float64))
         want_reg = self.model_type == "linear"              # get_model needs koopData.Px / Py (1206-1216)
         if np.all(self.lasso >= 1e6):                       # branch test on the PROPERTY (Ksysid.m:1068)
+            pc = (self.params["nzeta"] if self.model_type == "nonlinear" else N) if self._fast_cols else 0
             res = self.fitter.fit(self.basis, self.model_type, snapshotPairs["alpha"], snapshotPairs["beta"],
-                                  snapshotPairs["u"], want_regressors=want_reg, least_squares=True, ls_method=self._ls_method)
+                                  snapshotPairs["u"], want_regressors=want_reg, least_squares=True, ls_method=self._ls_method,
+                                  pc_cols=pc)
         else:
             res = self.fitter.fit(self.basis, self.model_type, snapshotPairs["alpha"], snapshotPairs["beta"],
                                   snapshotPairs["u"], want_regressors=want_reg, least_squares=False, t=lasso * N,
@@ -235,7 +239,7 @@ class Ksysid:
     def get_model(self, koopData):
         """Ksysid.m:1179-1235 (discrete): A, B, C and the projection M = (L \\ R)'."""
         N, n = self.params["N"], self.params["n"]
-        UT = koopData["K"].T
+        UT = koopData["K"][:, :N].T
         Amat, Bmat = UT[:N, :N], UT[:N, N:]
         Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
         L = koopData["Px"] @ Amat.T + koopData["u"] @ Bmat.T
@@ -246,7 +250,7 @@ class Ksysid:
     def get_BLmodel(self, koopData):
         """Ksysid.m:1238-1282."""
         N, n, m = self.params["N"], self.params["n"], self.params["m"]
-        UT = koopData["K"].T
+        UT = koopData["K"][:, :N].T
         Amat, Bmat = UT[:N, :N], UT[:N, N:]
         Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
         return {"A": Amat, "B": Bmat, "Beta": lambda z: Bmat @ np.kron(np.eye(m), np.asarray(z).reshape(-1, 1)),

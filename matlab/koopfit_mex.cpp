@@ -58,6 +58,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     pr.alpha = mxGetPr(prhs[1]);
     pr.beta = mxGetPr(prhs[2]);
     pr.u = mxGetPr(prhs[3]);
+    pr.pc_cols = 0;   /* full K, as the reference returns it */
+    pr.reserved = 0;
 
     // dictionary descriptor
     const mxArray* desc = prhs[5];
