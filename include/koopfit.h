@@ -109,6 +109,8 @@ typedef struct {
     double* objective;      /* nt: 0.5 tr(K'GK) - tr(C'K) per budget */
     double* l1norm;         /* nt: ||vec K||_1 */
     int* qp_iters;          /* nt */
+    double* qp_gap;         /* nt: certified optimality gap of the returned K: f(K) - min f <= qp_gap (Frank-Wolfe gap
+                               <GK - C, K> + t ||GK - C||_inf over the free columns); compare with 1e-8 |objective| */
     kf_info info;
 } kf_result;
 
@@ -151,6 +153,27 @@ int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_
  * solution X (P x Pc).  Replaces `Mtranspose = L \ R` in get_model (Ksysid.m:1216).
  * perm (P ints) and rank may be NULL. */
 int kf_mldivide(kf_ctx* ctx, long long M, int P, int Pc, const double* A, const double* B, double* X, int* perm, int* rank);
+
+/* ---- validation rollouts -------------------------------
+ * The fitted model as get_model / get_BLmodel / get_NLmodel return it (Ksysid.m:1179-1341), discrete time. */
+typedef struct {
+    int model;              /* KF_LINEAR | KF_BILINEAR | KF_NONLINEAR */
+    int n, m, nzeta, N;     /* params.n, params.m, params.nzeta, params.N */
+    const double* A;        /* N x N (linear, bilinear), column-major */
+    const double* B;        /* N x m (linear) | N x (N m) = [B_1 ... B_m] (bilinear) */
+    const double* F;        /* nonlinear: nzeta x N, F = K(:,1:nzeta)' (Ksysid.m:1329) */
+} kf_model;
+
+/* val_model / val_BLmodel / val_NLmodel (Ksysid.m:1623-1879; discrete, unloaded): open-loop simulation of `nmodels`
+ * candidate models (e.g. the candidates of a lasso vector, train_models 1370-1387; all of one model type and size) on
+ * `ntrials` validation trials at once, one CTA per (trial, candidate).  Trial k: T[k] samples, initial delay-embedded
+ * state zeta0[k] (nzeta), inputs u[k] (T[k] x m column-major).  Output ysim[c * ntrials + k] (T[k] x nout column-major,
+ * caller-allocated): the first nout state rows per step, nout = n gives y = C z with C = [I_n 0] (Ksysid.m:1203, 1262)
+ * or zeta(1:n) (1864); nout = nzeta gives results.sim.zeta, nout = N results.sim.z (1700-1703); nout <= 0 means n.
+ *   z_1 = lift.econ_full(zeta0); z+ = A z + B u (1685) | A z + Beta(z) u (1783) | zeta+ = F psi([zeta;u]) (1860).
+ * Error metrics (get_error, 1882-1898) stay on the host. */
+int kf_rollout(kf_ctx* ctx, const kf_basis* basis, int nmodels, const kf_model* models, int ntrials, const int* T,
+               const double* const* zeta0, const double* const* u, int nout, double* const* ysim);
 
 /* ---- staged, device-resident API (one rank of a snapshot-sharded fit) ---
  * kf_accumulate_dev: lift + Gram of this rank's shard; DEVICE pointers in `prob`;

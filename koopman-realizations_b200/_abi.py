@@ -59,7 +59,12 @@ class kf_info(C.Structure):
 class kf_result(C.Structure):
     _fields_ = [("K", c_double_p), ("G", c_double_p), ("C", c_double_p), ("Px", c_double_p),
                 ("Py", c_double_p), ("perm", c_int_p), ("objective", c_double_p),
-                ("l1norm", c_double_p), ("qp_iters", c_int_p), ("info", kf_info)]
+                ("l1norm", c_double_p), ("qp_iters", c_int_p), ("qp_gap", c_double_p), ("info", kf_info)]
+
+
+class kf_model(C.Structure):
+    _fields_ = [("model", C.c_int), ("n", C.c_int), ("m", C.c_int), ("nzeta", C.c_int), ("N", C.c_int),
+                ("A", c_double_p), ("B", c_double_p), ("F", c_double_p)]
 
 
 class KoopfitError(RuntimeError):
@@ -149,6 +154,7 @@ def load():
         "kf_lift": (i, [vp, P(kf_basis), ll, c_double_p, c_double_p]),
         "kf_fit": (i, [vp, P(kf_basis), P(kf_problem), P(kf_solve), P(kf_result)]),
         "kf_fit_batch": (i, [vp, i, P(P(kf_basis)), P(kf_problem), P(kf_solve), P(kf_result)]),
+        "kf_rollout": (i, [vp, P(kf_basis), i, P(kf_model), i, c_int_p, P(c_double_p), P(c_double_p), i, P(c_double_p)]),
         "kf_mldivide": (i, [vp, ll, i, i, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]),
         "kf_accumulate_dev": (i, [vp, P(kf_basis), P(kf_problem), i]),
         "kf_accum_buffer": (i, [vp, P(vp), P(C.c_size_t)]),
@@ -167,5 +173,5 @@ def load():
 
 
 EXPORTS = ["kf_create", "kf_destroy", "kf_last_error", "kf_version", "kf_basis_dims", "kf_block_table",
-           "kf_lift", "kf_fit", "kf_fit_batch", "kf_mldivide", "kf_accumulate_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
+           "kf_lift", "kf_fit", "kf_fit_batch", "kf_rollout", "kf_mldivide", "kf_accumulate_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
            "kf_stream", "kf_counters", "kf_last_times", "kf_set_option"]

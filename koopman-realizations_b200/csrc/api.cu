@@ -403,7 +403,7 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
             KF_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_K.as<double>() + (size_t)c0 * Pp, (size_t)Pp * sizeof(double), target.data(),
                                            (size_t)P * sizeof(double), (size_t)P * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, st));
         KfQpResult ls{};
-        KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), &ls, st));
+        KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), c0, c1, 0.0, &ls, st));
         std::vector<int> act;   // budgets whose constraint is active
         for (int it = 0; it < sv->nt; ++it) {
             if (sv->t[it] - pinned_l1 < 0) {
@@ -414,6 +414,7 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
                 if (out->objective) out->objective[it] = ls.objective;
                 if (out->l1norm) out->l1norm[it] = ls.l1;
                 if (out->qp_iters) out->qp_iters[it] = 0;
+                if (out->qp_gap) out->qp_gap[it] = std::max(0.0, ls.grad_inner + (sv->t[it] - pinned_l1) * ls.grad_max);
                 if (out->K) KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K + (size_t)it * P * P));
             } else {
                 act.push_back(it);
@@ -442,10 +443,11 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
                 const int it = act[g0 + b];
                 capped += qr[b].capped;
                 KfQpResult ev{};   // objective and ||K||_1 over ALL columns (the pinned ones count towards the budget row, Ksysid.m:1136)
-                KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt + (size_t)b * Pp * Pp, &ev, st));
+                KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt + (size_t)b * Pp * Pp, c0, c1, tf[b], &ev, st));
                 if (out->objective) out->objective[it] = ev.objective;
                 if (out->l1norm) out->l1norm[it] = ev.l1;
                 if (out->qp_iters) out->qp_iters[it] = qr[b].iters;
+                if (out->qp_gap) out->qp_gap[it] = ev.gap;
                 if (out->K) KF_TRY(copy_out_matrix(ctx, Kt + (size_t)b * Pp * Pp, Pp, P, out->K + (size_t)it * P * P));
             }
             KF_CUDA(ctx, cudaStreamSynchronize(st));
@@ -741,6 +743,19 @@ int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_
     }
     for (int i : rest) KF_TRY(kf_fit(ctx, bases[i], &probs[i], &solves[i], &outs[i]));
     return KF_OK;
+}
+
+int kf_rollout(kf_ctx* ctx, const kf_basis* basis, int nmodels, const kf_model* models, int ntrials, const int* T,
+               const double* const* zeta0, const double* const* u, int nout, double* const* ysim) {
+    if (!ctx) return KF_EINVAL;
+    if (!models || nmodels <= 0 || ntrials <= 0 || !T || !zeta0 || !ysim || (models[0].m > 0 && !u)) {
+        ctx->err = "kf_rollout: models, T, zeta0, u, ysim required";
+        return KF_EINVAL;
+    }
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    KF_TRY(prepare_program(ctx, basis));
+    ctx->lay.valid = false;
+    return kf_rollout_impl(ctx, nmodels, models, ntrials, T, zeta0, u, nout, ysim);
 }
 
 int kf_mldivide(kf_ctx* ctx, long long M, int P, int Pc, const double* A, const double* B, double* X, int* perm, int* rank) {

@@ -200,9 +200,14 @@ int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long lon
 int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, kf_result* outs,
                        const int* which, int nwhich);
 
+// rollout.cu
+int kf_rollout_impl(kf_ctx* ctx, int nmodels, const kf_model* mdls, int ntrials, const int* T, const double* const* zeta0,
+                    const double* const* u, int nout, double* const* ysim);
+
 // qp.cu
-struct KfQpResult { double objective; double l1; int iters; double lam; int capped; };
+struct KfQpResult { double objective; double l1; int iters; double lam; int capped; double gap; double grad_inner; double grad_max; };
 int kf_solve_l1ball_multi(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, int nb, const double* t, int fix_c0,
                           int fix_c1, int max_iter, double tol, double* K_all, KfQpResult* res, cudaStream_t st);
 int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_t st);
-int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, KfQpResult* res, cudaStream_t st);
+int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, int fix_c0, int fix_c1, double t_free,
+                   KfQpResult* res, cudaStream_t st);

@@ -39,6 +39,7 @@ struct CdArgs {
     double tol;
     int max_sweeps, mode;             // 0 lasso CD, 1 restricted Gauss-Seidel for dK/dlam, 2 evaluate
     double* col_l1; double* col_obj; double* col_aux; int* col_iters;   // [budget][column]
+    double* col_gmax;                 // mode 2: max_i |grad_i| of the column (duality-gap certificate)
 };
 
 __device__ __forceinline__ double soft(double x, double lam) {
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(CD_THREADS) kf_cd_kernel(const CdArgs a) {
     }
 
     // ---- outputs: column, ||k||_1, objective -0.5 k'(c + q)  (k'Gk = k'(c - q)), s'd for mode 1
-    double l1 = 0.0, ob = 0.0, aux = 0.0;
+    double l1 = 0.0, ob = 0.0, aux = 0.0, gmax = 0.0;
     for (int i = tid; i < P; i += CD_THREADS) {
         const double ki = k[i];
         if (a.mode != 2) Kcol[i] = ki;
@@ -155,11 +156,25 @@ __global__ void __launch_bounds__(CD_THREADS) kf_cd_kernel(const CdArgs a) {
         } else {
             const double c = a.R[(long long)col * a.ldr + i];
             ob += -0.5 * ki * (c + q[i]);
+            if (a.mode == 2) {                // q = -grad: <grad, k> and ||grad||_inf for the Frank-Wolfe gap
+                aux -= q[i] * ki;
+                gmax = fmax(gmax, fabs(q[i]));
+            }
         }
     }
     l1 = cta_sum(l1, red);
     ob = cta_sum(ob, red);
     aux = cta_sum(aux, red);
+    if (a.mode == 2 && a.col_gmax) {
+        for (int off = 16; off > 0; off >>= 1) gmax = fmax(gmax, __shfl_down_sync(0xffffffffu, gmax, off));
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = gmax;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < CD_THREADS / 32; ++w) gmax = fmax(gmax, red[w]);
+            a.col_gmax[(long long)bud * P + col] = gmax;
+        }
+    }
     if (tid == 0) {
         const long long o = (long long)bud * P + col;
         a.col_l1[o] = l1;
@@ -193,6 +208,27 @@ __global__ void __launch_bounds__(256) kf_cd_reduce_kernel(const double* l1, con
         double mm = 0;
         for (int w = 0; w < (blockDim.x >> 5); ++w) mm = fmax(mm, red[w]);
         out[bud * 4 + 0] = a; out[bud * 4 + 1] = b; out[bud * 4 + 2] = c; out[bud * 4 + 3] = mm;
+    }
+}
+
+// single CTA: Frank-Wolfe duality gap pieces over the free columns: out[0] = sum <grad_j, k_j>, out[1] = max |grad|
+__global__ void __launch_bounds__(256) kf_gap_reduce_kernel(const double* aux, const double* gmax, int n, int skip0, int skip1, double* out) {
+    __shared__ double red[32];
+    double a = 0, m = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (i >= skip0 && i < skip1) continue;
+        a += aux[i];
+        m = fmax(m, gmax[i]);
+    }
+    a = cta_sum(a, red);
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, off));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mm = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) mm = fmax(mm, red[w]);
+        out[0] = a; out[1] = mm;
     }
 }
 
@@ -274,13 +310,13 @@ int ensure_cd_smem(kf_ctx* ctx, size_t smem) {
 }
 
 struct Scratch {
-    double *dG, *c_l1, *c_ob, *c_aux, *d_out, *d_lam, *d_dl;
+    double *dG, *c_l1, *c_ob, *c_aux, *c_gmax, *d_out, *d_lam, *d_dl;
     int *c_it, *d_active, *d_flips;
 };
 
-// scratch for nb budgets: dG[Pp] | l1,obj,aux [nb*Pp] | out[4 nb] | lam[nb] | dl[nb] | iters[nb*Pp] | active[nb] | flips[nb]
+// scratch for nb budgets: dG[Pp] | l1,obj,aux,gmax [nb*Pp] | out[4 nb] | lam[nb] | dl[nb] | iters[nb*Pp] | active[nb] | flips[nb]
 int carve(kf_ctx* ctx, int Pp, int nb, Scratch* s) {
-    const size_t nd = (size_t)Pp + 3ull * nb * Pp + 6ull * nb + 8;
+    const size_t nd = (size_t)Pp + 4ull * nb * Pp + 6ull * nb + 8;
     const size_t ni = (size_t)nb * Pp + 2ull * nb + 8;
     KF_CUDA(ctx, ctx->d_K3.ensure(nd * sizeof(double) + ni * sizeof(int)));
     double* p = ctx->d_K3.as<double>();
@@ -288,6 +324,7 @@ int carve(kf_ctx* ctx, int Pp, int nb, Scratch* s) {
     s->c_l1 = p; p += (size_t)nb * Pp;
     s->c_ob = p; p += (size_t)nb * Pp;
     s->c_aux = p; p += (size_t)nb * Pp;
+    s->c_gmax = p; p += (size_t)nb * Pp;
     s->d_out = p; p += 4 * nb;
     s->d_lam = p; p += nb;
     s->d_dl = p; p += nb + 8;
@@ -456,8 +493,11 @@ int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_
     return KF_OK;
 }
 
-// objective 0.5 tr(K'GK) - tr(C'K) and ||vec K||_1 over ALL P columns of one matrix
-int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, KfQpResult* res, cudaStream_t st) {
+// objective 0.5 tr(K'GK) - tr(C'K) and ||vec K||_1 over ALL P columns of one matrix, and the Frank-Wolfe duality gap
+//   gap = <grad, K> + t_free * ||grad||_inf  >=  f(K) - min{ f(Z) : ||Z_free||_1 <= t_free, pinned columns fixed }
+// over the free columns (grad = G K - C): a certificate of the objective that needs no reference solver.
+int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, int fix_c0, int fix_c1,
+                   double t_free, KfQpResult* res, cudaStream_t st) {
     const long long ld = Pp;
     const size_t smem = (size_t)P * (2 * sizeof(double) + sizeof(int)) + 16;
     KF_TRY(ensure_cd_smem(ctx, smem));
@@ -473,15 +513,19 @@ int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C,
     a.K = const_cast<double*>(K); a.ldk = ld; a.K0 = nullptr; a.ldk0 = ld; a.kstride = 0;
     a.P = P; a.skip0 = 0; a.skip1 = 0;
     a.lam = sc.d_lam; a.active = sc.d_active; a.tol = 0; a.max_sweeps = 0; a.mode = 2;
-    a.col_l1 = sc.c_l1; a.col_obj = sc.c_ob; a.col_aux = sc.c_aux; a.col_iters = sc.c_it;
+    a.col_l1 = sc.c_l1; a.col_obj = sc.c_ob; a.col_aux = sc.c_aux; a.col_iters = sc.c_it; a.col_gmax = sc.c_gmax;
     kf_cd_kernel<<<dim3(P, 1), CD_THREADS, smem, st>>>(a);
     kf_cd_reduce_kernel<<<1, 256, 0, st>>>(sc.c_l1, sc.c_ob, sc.c_aux, sc.c_it, P, 0, 0, sc.d_active, sc.d_out);
+    kf_gap_reduce_kernel<<<1, 256, 0, st>>>(sc.c_aux, sc.c_gmax, P, fix_c0, fix_c1, sc.d_out + 4);
     KF_CUDA(ctx, cudaGetLastError());
-    double h[4];
-    KF_CUDA(ctx, cudaMemcpyAsync(h, sc.d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    double h[6];
+    KF_CUDA(ctx, cudaMemcpyAsync(h, sc.d_out, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
     KF_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->launches += 3;
+    ctx->launches += 4;
     res->l1 = h[0];
     res->objective = h[1];
+    res->gap = std::max(0.0, h[4] + std::max(t_free, 0.0) * h[5]);
+    res->grad_inner = h[4];
+    res->grad_max = h[5];
     return KF_OK;
 }

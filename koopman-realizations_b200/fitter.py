@@ -112,10 +112,11 @@ class Fitter:
         res = A.kf_result()
         K = np.zeros((P, Pc, nt), order="F")
         perm = np.zeros(P, dtype=np.int32)
-        obj, l1 = np.zeros(nt), np.zeros(nt)
+        obj, l1, gap = np.zeros(nt), np.zeros(nt), np.zeros(nt)
         iters = np.zeros(nt, dtype=np.int32)
         res.K, res.perm = A.dptr(K), perm.ctypes.data_as(A.c_int_p)
         res.objective, res.l1norm, res.qp_iters = A.dptr(obj), A.dptr(l1), iters.ctypes.data_as(A.c_int_p)
+        res.qp_gap = A.dptr(gap)
         out = {}
         if want_gram:
             out["G"], out["C"] = np.zeros((P, P), order="F"), np.zeros((P, P), order="F")
@@ -126,7 +127,7 @@ class Fitter:
         self._check(self.lib.kf_fit(self.ctx, basis.ref(), C.byref(pr), C.byref(sv), C.byref(res)), "kf_fit")
         info = {f: getattr(res.info, f) for f, _ in A.kf_info._fields_}
         out.update(K=K[:, :, 0] if nt == 1 else K, K_all=K, rank=info["rank"], perm=perm, info=info, N=N, P=P,
-                   objective=obj, l1norm=l1, qp_iters=iters)
+                   objective=obj, l1norm=l1, qp_iters=iters, qp_gap=gap)
         return out
 
     def fit_batch(self, problems):
@@ -172,6 +173,45 @@ class Fitter:
             r.update(K=r["K_all"][:, :, 0] if r["nt"] == 1 else r["K_all"], rank=info["rank"], info=info)
         return results
 
+    def rollout(self, basis, model_type, n, m, nzeta, models, trials, nout=0):
+        """Open-loop validation rollouts on the GPU (kf_rollout; val_model / val_BLmodel / val_NLmodel,
+        Ksysid.m:1623-1879).  models: list of dicts with A, B (linear, bilinear) or F (nonlinear: K(:,1:nzeta)');
+        trials: list of (zeta0 (nzeta,), u (T x m)).  Returns out[c][k] = (T_k x nout) simulated state rows
+        (nout = n: y; nzeta: zeta; N: z) for candidate c on trial k."""
+        nc, nt = len(models), len(trials)
+        _, N, _ = self.dims(basis, model_type, m)
+        nout = int(nout) if nout else int(n)
+        mds = (A.kf_model * nc)()
+        keep = []
+        for c, md in enumerate(models):
+            mds[c].model = A.MODEL_CODE[model_type]
+            mds[c].n, mds[c].m, mds[c].nzeta, mds[c].N = int(n), int(m), int(nzeta), int(N)
+            for name in ("A", "B", "F"):
+                if md.get(name) is not None:
+                    arr = A.fcol(md[name])
+                    keep.append(arr)
+                    setattr(mds[c], name, A.dptr(arr))
+        T = (C.c_int * nt)()
+        z0 = (A.c_double_p * nt)()
+        up = (A.c_double_p * nt)()
+        yp = (A.c_double_p * (nt * nc))()
+        for k, (zeta0, u) in enumerate(trials):
+            zz = np.ascontiguousarray(np.asarray(zeta0, dtype=np.float64).ravel())
+            uu = A.fcol(np.asarray(u, dtype=np.float64).reshape(-1, m))
+            keep += [zz, uu]
+            T[k] = uu.shape[0]
+            z0[k], up[k] = A.dptr(zz), A.dptr(uu)
+        out = []
+        for c in range(nc):
+            row = []
+            for k in range(nt):
+                yy = np.zeros((T[k], nout), order="F")
+                row.append(yy)
+                yp[c * nt + k] = A.dptr(yy)
+            out.append(row)
+        self._check(self.lib.kf_rollout(self.ctx, basis.ref(), nc, mds, nt, T, z0, up, nout, yp), "kf_rollout")
+        return out
+
     def mldivide(self, Amat, Bmat):
         """MATLAB `A \\ B` (QRCP basic solution) on the GPU; returns X, rank, perm."""
         Amat, Bmat = A.fcol(Amat), A.fcol(Bmat)
@@ -206,10 +246,11 @@ class Fitter:
         Pc = int(pc_cols) if 0 < int(pc_cols) < P else P
         K = np.zeros((P, Pc, nt), order="F")
         perm = np.zeros(P, dtype=np.int32)
-        obj, l1 = np.zeros(nt), np.zeros(nt)
+        obj, l1, gap = np.zeros(nt), np.zeros(nt), np.zeros(nt)
         iters = np.zeros(nt, dtype=np.int32)
         res.K, res.perm = A.dptr(K), perm.ctypes.data_as(A.c_int_p)
         res.objective, res.l1norm, res.qp_iters = A.dptr(obj), A.dptr(l1), iters.ctypes.data_as(A.c_int_p)
+        res.qp_gap = A.dptr(gap)
         out = {}
         if want_gram:
             out["G"], out["C"] = np.zeros((P, P), order="F"), np.zeros((P, P), order="F")
@@ -217,5 +258,5 @@ class Fitter:
         self._check(self.lib.kf_solve_dev(self.ctx, C.byref(sv), C.byref(res)), "kf_solve_dev")
         info = {f: getattr(res.info, f) for f, _ in A.kf_info._fields_}
         out.update(K=K[:, :, 0] if nt == 1 else K, K_all=K, rank=info["rank"], perm=perm, info=info,
-                   objective=obj, l1norm=l1, qp_iters=iters)
+                   objective=obj, l1norm=l1, qp_iters=iters, qp_gap=gap)
         return out

@@ -294,40 +294,51 @@ class Ksysid:
         _, zetareal = self.get_zeta(valdata)
         return valdata["t"][nd:], valdata["y"][nd:], valdata["u"][nd:], zetareal
 
-    def val_model(self, model, valdata):
-        treal, yreal, ureal, zetareal = self._val_setup(valdata)
-        z = self._lift(zetareal[0])
-        ysim = np.zeros_like(yreal); ysim[0] = yreal[0]
-        zsim = np.zeros((len(treal), z.size)); zsim[0] = z
-        for j in range(len(treal) - 1):
-            z = model["A"] @ z + model["B"] @ ureal[j]                    # Ksysid.m:1685
-            zsim[j + 1], ysim[j + 1] = z, model["C"] @ z
-        res = {"t": treal, "sim": {"t": treal, "u": ureal, "y": ysim, "z": zsim}, "real": {"t": treal, "u": ureal, "y": yreal}}
+    def _rollout(self, models, valdatas, nout):
+        """All (candidate, trial) open-loop simulations in one kf_rollout call (one CTA each)."""
+        setups = [self._val_setup(v) for v in valdatas]
+        trials = [(zetareal[0], ureal) for (_, _, ureal, zetareal) in setups]
+        p = self.params
+        key = {"linear": ("A", "B"), "bilinear": ("A", "B"), "nonlinear": ("F_sym",)}[self.model_type]
+        mds = [{("F" if k == "F_sym" else k): mdl[k] for k in key} for mdl in models]
+        sims = self.fitter.rollout(self.basis, self.model_type, p["n"], p["m"], p["nzeta"], mds, trials, nout=nout)
+        return setups, sims
+
+    def _val_result(self, setup, states):
+        treal, yreal, ureal, _ = setup
+        n, nz = self.params["n"], self.params["nzeta"]
+        sim = {"t": treal, "u": ureal, "y": np.ascontiguousarray(states[:, :n])}
+        if states.shape[1] >= nz:
+            sim["zeta"] = np.ascontiguousarray(states[:, :nz])
+        if self.model_type != "nonlinear" and states.shape[1] == self.params["N"]:
+            sim["z"] = states
+        res = {"t": treal, "sim": sim, "real": {"t": treal, "u": ureal, "y": yreal}}
         res["error"] = self.get_error(res["sim"], res["real"])
         return res
+
+    def val_model(self, model, valdata):
+        """Ksysid.m:1623-1722 (discrete, unloaded): z+ = A z + B u (1685), y = C z; on the GPU (kf_rollout)."""
+        setups, sims = self._rollout([model], [valdata], self.params["N"])
+        return self._val_result(setups[0], sims[0][0])
 
     def val_BLmodel(self, model, valdata):
-        treal, yreal, ureal, zetareal = self._val_setup(valdata)
-        z = self._lift(zetareal[0])
-        ysim = np.zeros_like(yreal); ysim[0] = yreal[0]
-        for j in range(len(treal) - 1):
-            z = model["A"] @ z + model["Beta"](z) @ ureal[j]              # Ksysid.m:1783
-            ysim[j + 1] = model["C"] @ z
-        res = {"t": treal, "sim": {"t": treal, "u": ureal, "y": ysim}, "real": {"t": treal, "u": ureal, "y": yreal}}
-        res["error"] = self.get_error(res["sim"], res["real"])
-        return res
+        """Ksysid.m:1725-1820: z+ = A z + Beta(z) u (1783)."""
+        setups, sims = self._rollout([model], [valdata], self.params["N"])
+        return self._val_result(setups[0], sims[0][0])
 
     def val_NLmodel(self, model, valdata):
-        treal, yreal, ureal, zetareal = self._val_setup(valdata)
-        n = self.params["n"]
-        zeta = zetareal[0].copy()
-        ysim = np.zeros_like(yreal); ysim[0] = zeta[:n]
-        for j in range(len(treal) - 1):
-            zeta = model["F_func"](zeta, ureal[j])                         # Ksysid.m:1860
-            ysim[j + 1] = zeta[:n]
-        res = {"t": treal, "sim": {"t": treal, "u": ureal, "y": ysim}, "real": {"t": treal, "u": ureal, "y": yreal}}
-        res["error"] = self.get_error(res["sim"], res["real"])
-        return res
+        """Ksysid.m:1823-1879: zeta+ = F_func(zeta, u) (1860), y = zeta(1:n) (1864)."""
+        setups, sims = self._rollout([model], [valdata], self.params["nzeta"])
+        return self._val_result(setups[0], sims[0][0])
+
+    def validate_candidates(self, candidates=None, trials=None):
+        """Every candidate of a lasso vector (train_models 1370-1387) on every validation trial in ONE GPU call
+        (grid = trials x candidates); returns results[c][k] in the val_* layout.  The reference would loop
+        valNplot_model over candidates and trials (Ksysid.m:1928-1972)."""
+        cands = candidates if candidates is not None else (self.candidates if isinstance(self.candidates, list) else [self.model])
+        vals = self.valdata if trials is None else [self.valdata[i] for i in trials]
+        setups, sims = self._rollout(cands, vals, self.params["nzeta"])
+        return [[self._val_result(setups[k], sims[c][k]) for k in range(len(vals))] for c in range(len(cands))]
 
     def valNplot_model(self, trial=None, **_):
         """valNplot_model without the plots (Ksysid.m:1928-1972): validate the chosen model on val trials."""

@@ -71,11 +71,12 @@ def fit_sharded(fitter, basis, model_type, alpha_dev, beta_dev, u_dev, P, budget
     if world == 1:
         return res
     parts = [None] * world
-    dist.all_gather_object(parts, (mine, res["K_all"][:, :, :mine.size], res["objective"][:mine.size], res["l1norm"][:mine.size]), group=group)
+    dist.all_gather_object(parts, (mine, res["K_all"][:, :, :mine.size], res["objective"][:mine.size], res["l1norm"][:mine.size],
+                                   res["qp_gap"][:mine.size]), group=group)
     K_all = np.zeros((P, P, budgets.size), order="F")
-    obj, l1 = np.zeros(budgets.size), np.zeros(budgets.size)
-    for idx, Kp, ob, ln in parts:
+    obj, l1, gap = np.zeros(budgets.size), np.zeros(budgets.size), np.zeros(budgets.size)
+    for idx, Kp, ob, ln, gp in parts:
         for j, i in enumerate(idx):
-            K_all[:, :, i], obj[i], l1[i] = Kp[:, :, j], ob[j], ln[j]
-    res.update(K_all=K_all, K=K_all[:, :, 0], objective=obj, l1norm=l1)
+            K_all[:, :, i], obj[i], l1[i], gap[i] = Kp[:, :, j], ob[j], ln[j], gp[j]
+    res.update(K_all=K_all, K=K_all[:, :, 0], objective=obj, l1norm=l1, qp_gap=gap)
     return res

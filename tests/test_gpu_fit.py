@@ -243,17 +243,16 @@ def test_pc_cols_fast_mode(fitter, model, ls_method):
     """Opt-in fast mode (SURVEY §8a note): only the K columns consumed downstream — K(:,1:N) for A, B
     (Ksysid.m:1199-1200, 1258-1259) or K(:,1:nzeta) for F (1329) — are computed; they must equal the same columns
     of the full solve."""
-    n, m = 3, 2
-    alpha, beta, u = synth(4000, n, m, seed=4)
+    n, m = 6, 2
+    alpha, beta, u = synth(5000, n, m, seed=4)
     nv = n + (m if model == "nonlinear" else 0)
-    cen = centres_for(["poly", "gaussian"], [3, 130], nv)
-    basis = koopfit.Basis(["poly", "gaussian"], [3, 130], nv, cen)       # N > 128: several tile columns
+    basis = koopfit.Basis(["poly"], [4 if model != "nonlinear" else 3], nv)     # N = 210 / 165 > 128: several tile columns
     _, N, P = fitter.dims(basis, model, m)
     pc = n if model == "nonlinear" else N
     full = fitter.fit(basis, model, alpha, beta, u, ls_method=ls_method)
     fast = fitter.fit(basis, model, alpha, beta, u, ls_method=ls_method, pc_cols=pc)
     assert fast["K"].shape == (P, pc) and full["K"].shape == (P, P)
     assert fast["rank"] == full["rank"]
-    assert relF(fast["K"], full["K"][:, :pc]) < 1e-12
+    assert relF(fast["K"], full["K"][:, :pc]) < 1e-9      # same G; only the split-K summation order may differ
     with pytest.raises(koopfit.KoopfitError):
         fitter.fit(basis, model, alpha, beta, u, pc_cols=pc, least_squares=False, t=[1.0])

@@ -48,6 +48,11 @@ def test_qp_budget_vector_matches_oracle(fitter, model):
         fg = O.qp_objective(G, C, Kg)
         assert abs(fg - fo) <= 1e-8 * abs(fo), (t / l1, fg, fo)
         assert abs(res["objective"][i] - fg) <= 1e-9 * abs(fg)
+        # certified optimality gap (Frank-Wolfe): bounds f(K) - f* from above without any reference solver
+        grad = G @ Kg - C
+        gap = float((grad * Kg).sum() + t * np.abs(grad).max())
+        assert abs(res["qp_gap"][i] - max(gap, 0.0)) <= 1e-9 * abs(fg) + 1e-6 * abs(gap)
+        assert fg - fo <= res["qp_gap"][i] + 1e-9 * abs(fo) and res["qp_gap"][i] <= 1e-8 * abs(fo)
         if info["active"]:
             assert relF(Kg, Ko) < 1e-6
         else:
