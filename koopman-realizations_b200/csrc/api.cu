@@ -429,6 +429,7 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
             const int nb = (int)std::min<size_t>(gmax, act.size() - g0);
             KF_CUDA(ctx, ctx->d_Kt.ensure((size_t)nb * mat));
             double* Kt = ctx->d_Kt.as<double>();
+            KF_CUDA(ctx, cudaMemsetAsync(Kt, 0, (size_t)nb * mat, st));
             std::vector<double> tf(nb);
             for (int b = 0; b < nb; ++b) {
                 tf[b] = sv->t[act[g0 + b]] - pinned_l1;
@@ -437,13 +438,22 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
                                                    (size_t)P * sizeof(double), (size_t)P * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, st));
             }
             std::vector<KfQpResult> qr(nb);
-            KF_TRY(kf_solve_l1ball_multi(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1, sv->qp_max_iter,
-                                         sv->qp_tol, Kt, qr.data(), st));
+            const bool active_set = ctx->opt_qp_method == 2 || (ctx->opt_qp_method == 0 && P > 256);
+            if (active_set)
+                KF_TRY(kf_solve_l1ball_as(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1, sv->qp_max_iter,
+                                          Kt, qr.data(), st));
+            else
+                KF_TRY(kf_solve_l1ball_multi(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1, sv->qp_max_iter,
+                                             sv->qp_tol, Kt, qr.data(), st));
             for (int b = 0; b < nb; ++b) {
                 const int it = act[g0 + b];
                 capped += qr[b].capped;
                 KfQpResult ev{};   // objective and ||K||_1 over ALL columns (the pinned ones count towards the budget row, Ksysid.m:1136)
                 KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt + (size_t)b * Pp * Pp, c0, c1, tf[b], &ev, st));
+                if (ev.l1 > sv->t[it] * (1.0 + 1e-13) && ev.l1 > pinned_l1) {   // an unconverged iterate: make it feasible
+                    KF_TRY(kf_qp_scale_free(ctx, Kt + (size_t)b * Pp * Pp, P, Pp, c0, c1, tf[b] / (ev.l1 - pinned_l1), st));
+                    KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt + (size_t)b * Pp * Pp, c0, c1, tf[b], &ev, st));
+                }
                 if (out->objective) out->objective[it] = ev.objective;
                 if (out->l1norm) out->l1norm[it] = ev.l1;
                 if (out->qp_iters) out->qp_iters[it] = qr[b].iters;
@@ -519,7 +529,8 @@ void kf_destroy(kf_ctx* ctx) {
     cudaDeviceSynchronize();
     KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_full,
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
-                     &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt};
+                     &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,
+                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws};
     for (KfBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -818,6 +829,8 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "profile") ctx->opt_profile = (int)value;
     else if (n == "tma") ctx->opt_tma = (int)value;
     else if (n == "qr_max_gb") ctx->opt_qr_max_gb = value;
+    else if (n == "qp_method") ctx->opt_qp_method = (int)value;
+    else if (n == "as_ws_gb") ctx->opt_as_ws_gb = value;
     else {
         ctx->err = "kf_set_option: unknown option " + n;
         return KF_EINVAL;

@@ -114,6 +114,7 @@ struct kf_ctx {
     KfBuf d_ops, d_centres, d_pcs, d_panel[2], d_full, d_tasks[2], d_tma_tasks[2], d_accum, d_tilemeta;
     CUtensorMap tmap[2];            // tensor maps of the two panels (SWIZZLE_128B, box 16 x 64)
     KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3, d_Kt;
+    KfBuf d_as_mat, d_as_aux, d_as_ws;   // active-set QP solver: pattern/solution matrices, index lists, Cholesky factors
 
     // options
     int opt_chunk = 0;        // 0 = auto
@@ -122,6 +123,8 @@ struct kf_ctx {
     double opt_panel_mb = 64; // target size of one L2-resident panel (24/48/64 MB measured: 31.7/32.5/32.8 TF)
     double opt_qr_max_gb = 16; // KF_LS_AUTO takes the QRCP route when [Px|Py] is at most this large
     int opt_profile = 0;      // sample Gram-kernel durations with CUDA events (adds syncs)
+    int opt_qp_method = 0;    // L1-ball QP: 0 auto (coordinate descent for P <= 256, exact active set above), 1 CD, 2 active set
+    double opt_as_ws_gb = 8;  // active-set solver: bound on the per-column Cholesky workspace (columns run in chunks that fit)
     int opt_tma = 1;          // Gram kernel operand path: 1 = tensor-map TMA + mbarrier ring, 0 = per-thread cp.async
 
     // counters
@@ -208,6 +211,10 @@ int kf_rollout_impl(kf_ctx* ctx, int nmodels, const kf_model* mdls, int ntrials,
 struct KfQpResult { double objective; double l1; int iters; double lam; int capped; double gap; double grad_inner; double grad_max; };
 int kf_solve_l1ball_multi(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, int nb, const double* t, int fix_c0,
                           int fix_c1, int max_iter, double tol, double* K_all, KfQpResult* res, cudaStream_t st);
+// qp_as.cu: exact primal-dual active-set solver (per-column batched Cholesky); same contract as kf_solve_l1ball_multi
+int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, int nb, const double* t, int fix_c0, int fix_c1,
+                       int max_iter, double* K_all, KfQpResult* res, cudaStream_t st);
+int kf_qp_scale_free(kf_ctx* ctx, double* K, int P, int Pp, int fix_c0, int fix_c1, double s, cudaStream_t st);
 int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_t st);
 int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, int fix_c0, int fix_c1, double t_free,
                    KfQpResult* res, cudaStream_t st);

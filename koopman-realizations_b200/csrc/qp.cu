@@ -483,6 +483,18 @@ int kf_solve_l1ball_multi(kf_ctx* ctx, int P, int Pp, const double* G, const dou
     return KF_OK;
 }
 
+// K(:, free columns) *= s   (feasibility to rounding after a solve)
+int kf_qp_scale_free(kf_ctx* ctx, double* K, int P, int Pp, int fix_c0, int fix_c1, double s, cudaStream_t st) {
+    Scratch sc;
+    KF_TRY(carve(ctx, Pp, 1, &sc));
+    KF_CUDA(ctx, cudaMemcpyAsync(sc.d_dl, &s, sizeof(double), cudaMemcpyHostToDevice, st));
+    kf_scale_kernel<<<dim3(ctx->sm_count * 2, 1), 256, 0, st>>>(K, 0, Pp, P, P, fix_c0, fix_c1, sc.d_dl);
+    KF_CUDA(ctx, cudaGetLastError());
+    KF_CUDA(ctx, cudaStreamSynchronize(st));     // `s` is a stack variable
+    ctx->launches += 1;
+    return KF_OK;
+}
+
 // G += shift * I  (the PSD conditioning branch, Ksysid.m:1119)
 int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_t st) {
     Scratch sc;
