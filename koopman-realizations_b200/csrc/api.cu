@@ -831,6 +831,7 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "qr_max_gb") ctx->opt_qr_max_gb = value;
     else if (n == "qp_method") ctx->opt_qp_method = (int)value;
     else if (n == "as_ws_gb") ctx->opt_as_ws_gb = value;
+    else if (n == "as_frac") ctx->opt_as_frac = value;
     else {
         ctx->err = "kf_set_option: unknown option " + n;
         return KF_EINVAL;

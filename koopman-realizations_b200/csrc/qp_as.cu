@@ -298,7 +298,8 @@ __global__ void __launch_bounds__(256) kf_as_index_kernel(const double* SG, long
 // single CTA: the multiplier that meets the budget on the current pattern, lam_b = (sum_j s'a_j - t) / sum_j s'b_j over
 // the free columns, under a trust region: lam = max(lam_b, lam_prev / 2).  Without it a budget the current support
 // cannot use up gives lam = 0, every off-support entry enters at once and the iteration never recovers (observed);
-// halving at most lets the support grow along the regularisation path.  scal = [lam, num, den, dead, clamped]
+// halving at most lets the support grow along the regularisation path (the host bounds the step further by the number
+// of pattern changes, see below).  scal = [lam, num, den, dead]
 __global__ void __launch_bounds__(256) kf_as_lambda_kernel(const double* col_num, const double* col_den, const int* col_dead, int P, int skip0,
                                                            int skip1, double t, double lam_prev, double* scal) {
     __shared__ double r0[256], r1[256], r2[256];
@@ -319,29 +320,14 @@ __global__ void __launch_bounds__(256) kf_as_lambda_kernel(const double* col_num
     }
     if (threadIdx.x == 0) {
         const double lam_b = r1[0] > 0.0 ? fmax((r0[0] - t) / r1[0], 0.0) : 0.0;
-        const double lam = fmax(lam_b, 0.5 * lam_prev);
-        scal[0] = lam; scal[1] = r0[0]; scal[2] = r1[0]; scal[3] = r2[0]; scal[4] = lam > lam_b ? 1.0 : 0.0;
+        scal[0] = fmax(lam_b, 0.5 * lam_prev); scal[1] = r0[0]; scal[2] = r1[0]; scal[3] = r2[0];
     }
 }
 
-// K = A - lam B on the support, 0 elsewhere (free columns only)
-__global__ void kf_as_combine_kernel(const double* A, const double* B, const double* SG, double* K, long long ld, int P, int skip0, int skip1,
-                                     const double* scal) {
-    const double lam = scal[0];
-    const long long n = (long long)P * P;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(e % P), c = (int)(e / P);
-        if (c >= skip0 && c < skip1) continue;
-        const long long o = i + (long long)c * ld;
-        K[o] = SG[o] != 0.0 ? fma(-lam, B[o], A[o]) : 0.0;
-    }
-}
-
-// support update from K (exact on the old pattern) and GK = G K:  sign flips leave, dual violators enter.
-// counts[0] = left, counts[1] = entered
-__global__ void kf_as_update_kernel(double* K, double* SG, const double* GK, const double* C, long long ld, int P, int skip0, int skip1,
-                                    const double* scal, double rel, int* counts) {
-    const double lam = scal[0];
+// Pattern changes a trial multiplier would cause: K(lam) = A - lam B and grad(lam) = G A - lam G B - C are both affine in
+// lam, so every trial costs one element-wise pass and no factorisation.  counts[0] = leaving, counts[1] = entering
+__global__ void kf_as_count_kernel(const double* A, const double* B, const double* SG, const double* GA, const double* GB, const double* C,
+                                   long long ld, int P, int skip0, int skip1, double lam, double rel, int* counts) {
     const long long n = (long long)P * P;
     int left = 0, entered = 0;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -350,10 +336,10 @@ __global__ void kf_as_update_kernel(double* K, double* SG, const double* GK, con
         const long long o = i + (long long)c * ld;
         const double s = SG[o];
         if (s != 0.0) {
-            if (!(K[o] * s > 0.0)) { K[o] = 0.0; SG[o] = 0.0; ++left; }
+            if (!(fma(-lam, B[o], A[o]) * s > 0.0)) ++left;
         } else {
-            const double g = GK[o] - C[o];
-            if (fabs(g) > lam * (1.0 + rel)) { SG[o] = g > 0.0 ? -1.0 : 1.0; ++entered; }
+            const double g = fma(-lam, GB[o], GA[o]) - C[o];
+            if (fabs(g) > lam * (1.0 + rel)) ++entered;
         }
     }
     for (int off = 16; off > 0; off >>= 1) {
@@ -363,6 +349,27 @@ __global__ void kf_as_update_kernel(double* K, double* SG, const double* GK, con
     if ((threadIdx.x & 31) == 0) {
         if (left) atomicAdd(counts + 0, left);
         if (entered) atomicAdd(counts + 1, entered);
+    }
+}
+
+// K = A - lam B on the support; entries whose sign flipped leave (K = 0), dual violators enter with sign -sign(grad)
+__global__ void kf_as_apply_kernel(const double* A, const double* B, double* SG, const double* GA, const double* GB, const double* C, double* K,
+                                   long long ld, int P, int skip0, int skip1, double lam, double rel) {
+    const long long n = (long long)P * P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % P), c = (int)(e / P);
+        if (c >= skip0 && c < skip1) continue;
+        const long long o = i + (long long)c * ld;
+        const double s = SG[o];
+        double k = 0.0;
+        if (s != 0.0) {
+            k = fma(-lam, B[o], A[o]);
+            if (!(k * s > 0.0)) { k = 0.0; SG[o] = 0.0; }
+        } else {
+            const double g = fma(-lam, GB[o], GA[o]) - C[o];
+            if (fabs(g) > lam * (1.0 + rel)) SG[o] = g > 0.0 ? -1.0 : 1.0;
+        }
+        K[o] = k;
     }
 }
 
@@ -413,12 +420,13 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     }
     const long long ld = Pp;
     const size_t mat = (size_t)Pp * Pp;
-    // matrices: SG | A | B | GK ; ints: idx[P*P] | cnt[P] | cols[P] | dead[P] | counts[2] ; doubles: num[P] | den[P] | scal[8] ; offsets[P]
-    KF_CUDA(ctx, ctx->d_as_mat.ensure(4 * mat * sizeof(double)));
+    // matrices: SG | A | B | GA | GB ; ints: idx[P*P] | cnt[P] | cols[P] | dead[P] | counts[2] ; doubles: num[P] | den[P] | scal[8] ; offsets[P]
+    KF_CUDA(ctx, ctx->d_as_mat.ensure(5 * mat * sizeof(double)));
     double* SG = ctx->d_as_mat.as<double>();
     double* Am = SG + mat;
     double* Bm = Am + mat;
-    double* GK = Bm + mat;
+    double* GA = Bm + mat;      // G A
+    double* GB = GA + mat;      // G B
     const size_t n_int = (size_t)P * P + 3ull * P + 8;
     const size_t n_dbl = 2ull * P + 8;
     KF_CUDA(ctx, ctx->d_as_aux.ensure(n_dbl * sizeof(double) + (size_t)P * sizeof(long long) + n_int * sizeof(int) + 64));
@@ -465,6 +473,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
 
     // one exact step on the current pattern SG for budget tb; K (unclipped) -> Kout, pattern updated
     double lam_prev = 0.0;
+    bool clamped = false;
     auto step = [&](double tb, double* Kout) -> int {
         kf_as_index_kernel<<<P, 256, 0, st>>>(SG, ld, P, fix_c0, fix_c1, d_idx, d_cnt);
         KF_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
@@ -501,22 +510,50 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
             c0 = c1;
         }
         kf_as_lambda_kernel<<<1, 256, 0, st>>>(d_num, d_den, d_dead, P, fix_c0, fix_c1, tb, lam_prev, d_scal);
-        kf_as_combine_kernel<<<egrid, 256, 0, st>>>(Am, Bm, SG, Kout, ld, P, fix_c0, fix_c1, d_scal);
-        KfGemmGrid g{};                      // GK = G K  (G symmetric: row i of G = column i)
-        g.A = G; g.lda = ld; g.B = Kout; g.ldb = ld; g.out = GK; g.ldm = 1; g.ldn = ld;
-        g.m = P; g.n = P; g.k0 = 0; g.k1 = Pp; g.alpha = 1.0; g.accumulate = 0; g.lower_only = 0;
-        KF_TRY(kf_launch_gemm_grid(ctx, g, st));
-        KF_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 2 * sizeof(int), st));
-        kf_as_update_kernel<<<egrid, 256, 0, st>>>(Kout, SG, GK, C, ld, P, fix_c0, fix_c1, d_scal, 1e-10, d_counts);
-        KF_CUDA(ctx, cudaGetLastError());
         KF_CUDA(ctx, cudaMemcpyAsync(h_scal, d_scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
-        KF_CUDA(ctx, cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+        for (int q = 0; q < 2; ++q) {        // GA = G A, GB = G B  (G symmetric: row i of G = column i)
+            KfGemmGrid g{};
+            g.A = G; g.lda = ld; g.B = q ? Bm : Am; g.ldb = ld; g.out = q ? GB : GA; g.ldm = 1; g.ldn = ld;
+            g.m = P; g.n = P; g.k0 = 0; g.k1 = Pp; g.alpha = 1.0; g.accumulate = 0; g.lower_only = 0;
+            KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+        }
         KF_CUDA(ctx, cudaStreamSynchronize(st));
+        long long nnz = 0;
+        for (int j = 0; j < P; ++j) nnz += h_cnt[j];
+        const long long limit = std::max<long long>((long long)(ctx->opt_as_frac * (double)nnz), P);
+        auto count = [&](double lam) -> int {
+            KF_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 2 * sizeof(int), st));
+            kf_as_count_kernel<<<egrid, 256, 0, st>>>(Am, Bm, SG, GA, GB, C, ld, P, fix_c0, fix_c1, lam, 1e-10, d_counts);
+            KF_CUDA(ctx, cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+            KF_CUDA(ctx, cudaStreamSynchronize(st));
+            ctx->launches += 1;
+            return KF_OK;
+        };
+        // the multiplier the budget asks for, approached only as far as the pattern change stays bounded: a step that
+        // swaps a large part of the support at once is not a contraction any more (observed from ~40 % density on)
+        const double lam_goal = h_scal[0];
+        double lam = lam_goal;
+        clamped = lam_goal > (h_scal[2] > 0.0 ? (h_scal[1] - tb) / h_scal[2] : 0.0);
+        KF_TRY(count(lam));
+        if ((long long)h_counts[0] + h_counts[1] > limit && lam_prev > 0.0 && lam_goal != lam_prev) {
+            double lo = 0.0, hi = 1.0;
+            for (int r = 0; r < 10; ++r) {
+                const double th = 0.5 * (lo + hi);
+                KF_TRY(count(lam_prev + th * (lam_goal - lam_prev)));
+                if ((long long)h_counts[0] + h_counts[1] > limit) hi = th; else lo = th;
+            }
+            lam = lam_prev + lo * (lam_goal - lam_prev);
+            clamped = true;
+            KF_TRY(count(lam));
+        }
+        kf_as_apply_kernel<<<egrid, 256, 0, st>>>(Am, Bm, SG, GA, GB, C, Kout, ld, P, fix_c0, fix_c1, lam, 1e-10);
+        KF_CUDA(ctx, cudaGetLastError());
         ctx->launches += 5;
-        lam_prev = h_scal[0];
+        h_scal[0] = lam;
+        lam_prev = lam;
         return KF_OK;
     };
-    auto settled = [&]() { return h_counts[0] == 0 && h_counts[1] == 0 && h_scal[4] == 0.0; };
+    auto settled = [&]() { return h_counts[0] == 0 && h_counts[1] == 0 && !clamped; };
 
     // ---- cold start: the pattern is the largest |C| entry and lam starts at max|C| (K = 0 is optimal there)
     kf_as_absmax_kernel<<<1, 1024, 0, st>>>(C, ld, P, fix_c0, fix_c1, d_scal);

@@ -261,3 +261,32 @@ def test_active_set_qp_delay_constraint_and_shift(as_fitter, arm_data):
     assert np.abs(res["K"]).sum() <= 0.3 * N * (1 + 1e-12)
     assert abs(fg - fo) <= 1e-8 * abs(fo)
     assert res["qp_gap"][0] <= 1e-8 * abs(fo)
+
+
+def test_config3a_snake_fourier_lasso_budgets_certified(fitter, snake_data):
+    """BASELINE config 3 at FULL size (snake-data, bilinear, fourier degree 4: N = 732, P = 1464, cond(G) ~ 2e13 — the
+    reference's quadprog formulation needs 4 P^3 non-zeros and cannot be assembled).  No CPU solver finishes this in
+    test time, so parity is certified instead: for budgets across logspace(-2, 2, 64) * N the returned K is feasible
+    and its Frank-Wolfe gap, recomputed here in NumPy from the oracle's G and C, bounds f(K) - f* by 1e-8 |f|."""
+    k = O.KsysidOracle(snake_data, model_type="bilinear", obs_type=["fourier"], obs_degree=[4])
+    assert k.N == 732
+    Px, Py = O.build_regressors("bilinear", k.prog, k.pairs["alpha"], k.pairs["beta"], k.pairs["u"])
+    G, C = O.gram(Px, Py)
+    ts = np.logspace(-2, 2, 64)[[0, 21, 42, 63]] * k.N
+    basis = koopfit.Basis(["fourier"], [4], 3)
+    res = fitter.fit(basis, "bilinear", k.pairs["alpha"], k.pairs["beta"], k.pairs["u"], least_squares=False, t=ts,
+                     psd_shift="as_reference", want_gram=True)
+    assert res["info"]["psd_shift_applied"] == 0 and res["info"]["qp_capped"] == 0
+    assert relF(res["G"], G) < 1e-12 and relF(res["C"], C) < 1e-12
+    fs = []
+    for i, t in enumerate(ts):
+        K = res["K_all"][:, :, i]
+        assert np.abs(K).sum() <= t * (1 + 1e-12)
+        grad = G @ K - C
+        f = 0.5 * np.sum(K * (grad - C))                 # 0.5 tr(K'GK) - tr(C'K) = 0.5 <K, GK - 2C>
+        gap = float(np.sum(grad * K) + t * np.abs(grad).max())
+        assert gap <= 1e-8 * abs(f), (t, gap, f)
+        assert abs(res["objective"][i] - f) <= 1e-9 * abs(f)
+        assert res["qp_gap"][i] <= 1e-8 * abs(f)
+        fs.append(f)
+    assert all(b < a for a, b in zip(fs, fs[1:]))        # a larger budget can only lower the objective

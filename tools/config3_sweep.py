@@ -33,3 +33,6 @@ out = dict(P=int(res["P"]), N=int(N), budgets=nb, seconds=dt, solve_ms=res["info
            capped=int(res["info"]["qp_capped"]), worst_rel_gap=float(rel.max()), total_steps=int(res["qp_iters"].sum()), rows=rows)
 print({k: v for k, v in out.items() if k != "rows"}, flush=True)
 json.dump(out, open("gpurun_out/config3_sweep.json", "w"), indent=1)
+if os.environ.get("KF_SAVE_K"):
+    for i in [int(x) for x in os.environ["KF_SAVE_K"].split(",")]:
+        np.save(f"gpurun_out/c3a_K_{i}.npy", res["K_all"][:, :, i])
