@@ -141,6 +141,30 @@ int kf_lift(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V,
  * LS or all nt budgets.  HOST pointers in `prob`; copies are inside the call. */
 int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out);
 
+/* The same fit from the RAW merged training series: get_scale (Ksysid.m:180-229), get_zeta (868-907) and
+ * get_snapshotPairs (910-984, snapshots = Inf) run on the device, so the series crosses the boundary once
+ * (T (1 + n + m) doubles instead of M (2 nzeta + m)) and the pairs are written straight into the buffers the lift reads. */
+typedef struct {
+    long long T;            /* rows of the merged training trials (merge_trials, Ksysid.m:380-401) */
+    int n, m, nd;           /* params.n, params.m, params.nd (delays) */
+    int model;              /* KF_LINEAR | KF_BILINEAR | KF_NONLINEAR */
+    const double* t;        /* T: time stamps; a pair is dropped where t does not increase (trial boundary, 948) */
+    const double* y;        /* T x n column-major, unscaled */
+    const double* u;        /* T x m */
+    int prescaled;          /* 1: y, u are already scaled into [-1, 1] (offset 0, factor 1 are returned) */
+    int pc_cols;            /* as kf_problem.pc_cols */
+} kf_series;
+typedef struct {
+    double* y_offset;       /* n: params.scale.y_offset (Ksysid.m:226); NULL members are skipped */
+    double* y_factor;       /* n */
+    double* u_offset;       /* m */
+    double* u_factor;       /* m */
+    long long M;            /* out: snapshot pairs used = (kept pairs) - 1 (Ksysid.m:960) */
+} kf_scale;
+/* rows M of kf_result.Px / Py for a series, so the caller can allocate them (host scan of t) */
+long long kf_series_pairs(long long T, int nd, const double* t);
+int kf_fit_series(kf_ctx* ctx, const kf_basis* basis, const kf_series* series, const kf_solve* solve, kf_scale* scale, kf_result* out);
+
 /* Many independent fits in one call (evaluate_rand_models.m:45-144 fits 23 small models per random system).
  * Least-squares problems with P <= 32 and no dim_red run CONCURRENTLY, one CTA per problem, entirely on chip
  * (tile-wise Householder TSQR of [Px | Py] + pivoted QR of the small triangular factor: mldivide semantics);

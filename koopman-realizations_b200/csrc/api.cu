@@ -477,6 +477,92 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
 
 }  // namespace
 
+// the fit from DEVICE snapshot pairs (prob->alpha/beta/u are device pointers, column-major, ld = M); the dictionary is prepared
+int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* solve, kf_result* out, double t0) {
+    const long long M = prob->M;
+    const double* d_alpha = prob->alpha;
+    const double* d_beta = prob->beta;
+    const double* d_u = prob->u;
+    ctx->lay.valid = false;
+    KF_TRY(accumulate_dev(ctx, prob, true));
+    KF_TRY(finish_accum(ctx));
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->last_lift_gram_ms = ms;
+    out->info.t_lift_gram_ms = ms;
+    out->info.passes = 1;
+    // optional materialised regressors (koopData.Px / Py, Ksysid.m:1085-1086)
+    if (out->Px || out->Py) {
+        const int P = ctx->lay.P;
+        KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
+        KfLiftArgs a{};
+        a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
+        a.order = ctx->d_order.as<int>();
+        a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->lay.N;
+        a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
+        a.alpha = d_alpha; a.beta = d_beta; a.u = d_u; a.M = M;
+        if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * M * sizeof(double)));
+        a.full = ctx->d_full.as<double>();
+        KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, M, ctx->stream));
+        if (out->Px) KF_CUDA(ctx, cudaMemcpyAsync(out->Px, ctx->d_qr.p, (size_t)M * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (out->Py) KF_CUDA(ctx, cudaMemcpyAsync(out->Py, ctx->d_qr.as<double>() + (size_t)M * P, (size_t)M * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    int method = solve->ls_method;
+    if (solve->least_squares && method == KF_LS_AUTO) {
+        const double need = (double)M * 2.0 * ctx->lay.P * sizeof(double);
+        method = (need <= ctx->opt_qr_max_gb * 1073741824.0) ? KF_LS_QR : KF_LS_GRAM;
+    }
+    int rc;
+    if (solve->least_squares && method == KF_LS_QR) {
+        // Householder QRCP on the materialised regressors: the reference's own algorithm (Ksysid.m:1069)
+        rc = solve_from_accum(ctx, nullptr, out);      // G, C outputs only
+        if (rc) return rc;
+        const int P = ctx->lay.P, Pp = ctx->lay.Pp;
+        cudaStream_t st = ctx->stream;
+        KF_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+        KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
+        if (!(out->Px || out->Py)) {   // not materialised above
+            KfLiftArgs a{};
+            a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
+            a.order = ctx->d_order.as<int>();
+            a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->lay.N;
+            a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
+            a.alpha = d_alpha; a.beta = d_beta; a.u = d_u; a.M = M;
+            if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * M * sizeof(double)));
+            a.full = ctx->d_full.as<double>();
+            KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, M, st));
+        }
+        KF_CUDA(ctx, ctx->d_K.ensure((size_t)Pp * Pp * sizeof(double)));
+        KF_CUDA(ctx, ctx->d_misc.ensure(1024 + (size_t)Pp * sizeof(int)));
+        int* d_perm = reinterpret_cast<int*>(ctx->d_misc.as<char>() + 1024);
+        int rank = 0;
+        double minp = 0, maxp = 0;
+        const int Pc = ctx->lay.Pc;
+        KF_TRY(kf_solve_qr_ls(ctx, M, P, Pc, ctx->d_qr.as<double>(), M, ctx->d_K.as<double>(), Pp, d_perm, &rank, &minp, &maxp, st));
+        out->info.rank = rank;
+        out->info.ls_method_used = KF_LS_QR;
+        out->info.min_pivot = minp;
+        out->info.max_pivot = maxp;
+        out->info.passes = 2;
+        KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K, Pc));
+        if (out->perm) KF_CUDA(ctx, cudaMemcpyAsync(out->perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+        float sms = 0.f;
+        KF_CUDA(ctx, cudaEventElapsedTime(&sms, ctx->ev[4], ctx->ev[5]));
+        ctx->last_solve_ms = sms;
+        out->info.t_solve_ms = sms;
+    } else {
+        kf_solve sv2 = *solve;
+        if (sv2.least_squares) sv2.ls_method = KF_LS_GRAM;
+        rc = solve_from_accum(ctx, &sv2, out);
+    }
+    ctx->lay.valid = false;
+    out->info.t_total_ms = now_ms() - t0;
+    return rc;
+}
+
 // ====================================================================== C ABI
 extern "C" {
 
@@ -530,7 +616,7 @@ void kf_destroy(kf_ctx* ctx) {
     KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_full,
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,
-                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws};
+                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series};
     for (KfBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -648,84 +734,78 @@ int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_
     dp.alpha = d_alpha;
     dp.beta = d_beta;
     dp.u = d_u;
-    ctx->lay.valid = false;
-    KF_TRY(accumulate_dev(ctx, &dp, true));
-    KF_TRY(finish_accum(ctx));
-    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    float ms = 0.f;
-    KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-    ctx->last_lift_gram_ms = ms;
-    out->info.t_lift_gram_ms = ms;
-    out->info.passes = 1;
-    // optional materialised regressors (koopData.Px / Py, Ksysid.m:1085-1086)
-    if (out->Px || out->Py) {
-        const int P = ctx->lay.P;
-        KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
-        KfLiftArgs a{};
-        a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
-        a.order = ctx->d_order.as<int>();
-        a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->lay.N;
-        a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
-        a.alpha = d_alpha; a.beta = d_beta; a.u = d_u; a.M = M;
-        if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * M * sizeof(double)));
-        a.full = ctx->d_full.as<double>();
-        KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, M, ctx->stream));
-        if (out->Px) KF_CUDA(ctx, cudaMemcpyAsync(out->Px, ctx->d_qr.p, (size_t)M * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        if (out->Py) KF_CUDA(ctx, cudaMemcpyAsync(out->Py, ctx->d_qr.as<double>() + (size_t)M * P, (size_t)M * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return kf_fit_device_pairs(ctx, &dp, solve, out, t0);
+}
+
+long long kf_series_pairs(long long T, int nd, const double* t) {
+    if (!t || T - nd - 1 < 1) return 0;
+    long long kept = 0;
+    for (long long j = 0; j < T - nd - 1; ++j) kept += t[nd + j] < t[nd + j + 1] ? 1 : 0;
+    return kept > 0 ? kept - 1 : 0;
+}
+
+int kf_fit_series(kf_ctx* ctx, const kf_basis* basis, const kf_series* ser, const kf_solve* solve, kf_scale* scale, kf_result* out) {
+    if (!ctx || !out || !solve) return KF_EINVAL;
+    if (!ser || ser->T < 3 || ser->n < 1 || ser->m < 0 || ser->nd < 0 || !ser->t || !ser->y || (ser->m > 0 && !ser->u)) {
+        ctx->err = "kf_fit_series: T >= 3, n >= 1, t, y (and u when m > 0) required";
+        return KF_EINVAL;
     }
-    int method = solve->ls_method;
-    if (solve->least_squares && method == KF_LS_AUTO) {
-        const double need = (double)M * 2.0 * ctx->lay.P * sizeof(double);
-        method = (need <= ctx->opt_qr_max_gb * 1073741824.0) ? KF_LS_QR : KF_LS_GRAM;
-    }
-    int rc;
-    if (solve->least_squares && method == KF_LS_QR) {
-        // Householder QRCP on the materialised regressors: the reference's own algorithm (Ksysid.m:1069)
-        rc = solve_from_accum(ctx, nullptr, out);      // G, C outputs only
-        if (rc) return rc;
-        const int P = ctx->lay.P, Pp = ctx->lay.Pp;
-        cudaStream_t st = ctx->stream;
-        KF_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-        KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
-        if (!(out->Px || out->Py)) {   // not materialised above
-            KfLiftArgs a{};
-            a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
-            a.order = ctx->d_order.as<int>();
-            a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->lay.N;
-            a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
-            a.alpha = d_alpha; a.beta = d_beta; a.u = d_u; a.M = M;
-            if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * M * sizeof(double)));
-            a.full = ctx->d_full.as<double>();
-            KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, M, st));
-        }
-        KF_CUDA(ctx, ctx->d_K.ensure((size_t)Pp * Pp * sizeof(double)));
-        KF_CUDA(ctx, ctx->d_misc.ensure(1024 + (size_t)Pp * sizeof(int)));
-        int* d_perm = reinterpret_cast<int*>(ctx->d_misc.as<char>() + 1024);
-        int rank = 0;
-        double minp = 0, maxp = 0;
-        const int Pc = ctx->lay.Pc;
-        KF_TRY(kf_solve_qr_ls(ctx, M, P, Pc, ctx->d_qr.as<double>(), M, ctx->d_K.as<double>(), Pp, d_perm, &rank, &minp, &maxp, st));
-        out->info.rank = rank;
-        out->info.ls_method_used = KF_LS_QR;
-        out->info.min_pivot = minp;
-        out->info.max_pivot = maxp;
-        out->info.passes = 2;
-        KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K, Pc));
-        if (out->perm) KF_CUDA(ctx, cudaMemcpyAsync(out->perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
-        KF_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double t0 = now_ms();
+    std::memset(&out->info, 0, sizeof(out->info));
+    KF_TRY(prepare_program(ctx, basis));
+    cudaStream_t st = ctx->stream;
+    const long long T = ser->T;
+    const int n = ser->n, m = ser->m, nd = ser->nd, ncol = n + m;
+    const int nzeta = n * (nd + 1) + m * nd;          // Ksysid.m:86
+    // device: t | y | u | scale
+    KF_CUDA(ctx, ctx->d_series.ensure(((size_t)T * (1 + ncol) + 2 * ncol + 2) * sizeof(double)));
+    double* d_t = ctx->d_series.as<double>();
+    double* d_y = d_t + T;
+    double* d_u = d_y + (size_t)T * n;
+    double* d_scale = d_u + (size_t)T * m;
+    KF_CUDA(ctx, cudaMemcpyAsync(d_t, ser->t, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, st));
+    KF_CUDA(ctx, cudaMemcpyAsync(d_y, ser->y, (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (m) KF_CUDA(ctx, cudaMemcpyAsync(d_u, ser->u, (size_t)T * m * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (ser->prescaled) {
+        std::vector<double> one(2 * ncol, 0.0);
+        for (int c = 0; c < ncol; ++c) one[ncol + c] = 1.0;
+        KF_CUDA(ctx, cudaMemcpyAsync(d_scale, one.data(), one.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         KF_CUDA(ctx, cudaStreamSynchronize(st));
-        float sms = 0.f;
-        KF_CUDA(ctx, cudaEventElapsedTime(&sms, ctx->ev[4], ctx->ev[5]));
-        ctx->last_solve_ms = sms;
-        out->info.t_solve_ms = sms;
     } else {
-        kf_solve sv2 = *solve;
-        if (sv2.least_squares) sv2.ls_method = KF_LS_GRAM;
-        rc = solve_from_accum(ctx, &sv2, out);
+        KF_TRY(kf_pp_scale(ctx, d_y, d_u, T, n, m, d_scale, st));
     }
-    ctx->lay.valid = false;
-    out->info.t_total_ms = now_ms() - t0;
-    return rc;
+    long long M = 0;
+    KF_TRY(kf_pp_count_pairs(ctx, d_t, T, nd, &M, st));
+    if (M < 1) {
+        ctx->err = "kf_fit_series: the series yields no snapshot pairs";
+        return KF_EINVAL;
+    }
+    if (scale) {
+        std::vector<double> h(2 * ncol);
+        KF_CUDA(ctx, cudaMemcpyAsync(h.data(), d_scale, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int c = 0; c < n; ++c) {
+            if (scale->y_offset) scale->y_offset[c] = h[c];
+            if (scale->y_factor) scale->y_factor[c] = h[ncol + c];
+        }
+        for (int c = 0; c < m; ++c) {
+            if (scale->u_offset) scale->u_offset[c] = h[n + c];
+            if (scale->u_factor) scale->u_factor[c] = h[ncol + n + c];
+        }
+        scale->M = M;
+    }
+    const size_t nz = (size_t)M * nzeta, nu = (size_t)M * m;
+    KF_CUDA(ctx, ctx->d_in.ensure((2 * nz + nu + 2) * sizeof(double)));
+    double* d_alpha = ctx->d_in.as<double>();
+    double* d_beta = d_alpha + nz;
+    double* d_uo = d_beta + nz;
+    KF_TRY(kf_pp_pairs(ctx, d_t, d_y, d_u, d_scale, T, n, m, nd, M, d_alpha, d_beta, d_uo, st));
+    kf_problem dp{};
+    dp.M = M; dp.nzeta = nzeta; dp.m = m; dp.model = ser->model;
+    dp.alpha = d_alpha; dp.beta = d_beta; dp.u = d_uo; dp.pc_cols = ser->pc_cols;
+    KF_TRY(check_problem(ctx, &dp));
+    return kf_fit_device_pairs(ctx, &dp, solve, out, t0);
 }
 
 int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, const kf_solve* solves, kf_result* outs) {

@@ -114,6 +114,7 @@ struct kf_ctx {
     KfBuf d_ops, d_centres, d_pcs, d_panel[2], d_full, d_tasks[2], d_tma_tasks[2], d_accum, d_tilemeta;
     CUtensorMap tmap[2];            // tensor maps of the two panels (SWIZZLE_128B, box 16 x 64)
     KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3, d_Kt;
+    KfBuf d_series;                      // raw merged series t | y | u and the scale factors (kf_fit_series)
     KfBuf d_as_mat, d_as_aux, d_as_ws;   // active-set QP solver: pattern/solution matrices, index lists, Cholesky factors
 
     // options
@@ -203,6 +204,13 @@ int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long lon
 // batch.cu
 int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, kf_result* outs,
                        const int* which, int nwhich);
+
+// preprocess.cu: get_scale / get_zeta / get_snapshotPairs on the device
+int kf_pp_scale(kf_ctx* ctx, const double* d_y, const double* d_u, long long T, int n, int m, double* d_scale, cudaStream_t st);
+int kf_pp_count_pairs(kf_ctx* ctx, const double* d_t, long long T, int nd, long long* M_out, cudaStream_t st);
+int kf_pp_pairs(kf_ctx* ctx, const double* d_t, const double* d_y, const double* d_u, const double* d_scale, long long T, int n, int m,
+                int nd, long long M, double* d_alpha, double* d_beta, double* d_uo, cudaStream_t st);
+int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* solve, kf_result* out, double t0);
 
 // rollout.cu
 int kf_rollout_impl(kf_ctx* ctx, int nmodels, const kf_model* mdls, int ntrials, const int* T, const double* const* zeta0,
