@@ -62,6 +62,16 @@ class kf_result(C.Structure):
                 ("l1norm", c_double_p), ("qp_iters", c_int_p), ("qp_gap", c_double_p), ("info", kf_info)]
 
 
+class kf_series(C.Structure):
+    _fields_ = [("T", C.c_longlong), ("n", C.c_int), ("m", C.c_int), ("nd", C.c_int), ("model", C.c_int),
+                ("t", c_double_p), ("y", c_double_p), ("u", c_double_p), ("prescaled", C.c_int), ("pc_cols", C.c_int)]
+
+
+class kf_scale(C.Structure):
+    _fields_ = [("y_offset", c_double_p), ("y_factor", c_double_p), ("u_offset", c_double_p), ("u_factor", c_double_p),
+                ("M", C.c_longlong)]
+
+
 class kf_model(C.Structure):
     _fields_ = [("model", C.c_int), ("n", C.c_int), ("m", C.c_int), ("nzeta", C.c_int), ("N", C.c_int),
                 ("A", c_double_p), ("B", c_double_p), ("F", c_double_p)]
@@ -153,6 +163,8 @@ def load():
         "kf_block_table": (i, [i, i, i, c_int_p, c_int_p, c_int_p]),
         "kf_lift": (i, [vp, P(kf_basis), ll, c_double_p, c_double_p]),
         "kf_fit": (i, [vp, P(kf_basis), P(kf_problem), P(kf_solve), P(kf_result)]),
+        "kf_fit_series": (i, [vp, P(kf_basis), P(kf_series), P(kf_solve), P(kf_scale), P(kf_result)]),
+        "kf_series_pairs": (ll, [ll, i, c_double_p]),
         "kf_fit_batch": (i, [vp, i, P(P(kf_basis)), P(kf_problem), P(kf_solve), P(kf_result)]),
         "kf_rollout": (i, [vp, P(kf_basis), i, P(kf_model), i, c_int_p, P(c_double_p), P(c_double_p), i, P(c_double_p)]),
         "kf_mldivide": (i, [vp, ll, i, i, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]),
@@ -173,5 +185,5 @@ def load():
 
 
 EXPORTS = ["kf_create", "kf_destroy", "kf_last_error", "kf_version", "kf_basis_dims", "kf_block_table",
-           "kf_lift", "kf_fit", "kf_fit_batch", "kf_rollout", "kf_mldivide", "kf_accumulate_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
+           "kf_lift", "kf_fit", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_mldivide", "kf_accumulate_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
            "kf_stream", "kf_counters", "kf_last_times", "kf_set_option"]

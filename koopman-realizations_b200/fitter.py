@@ -130,6 +130,47 @@ class Fitter:
                    objective=obj, l1norm=l1, qp_iters=iters, qp_gap=gap)
         return out
 
+    def fit_series(self, basis, model_type, t, y, u, nd=0, prescaled=False, want_gram=False, want_regressors=False, pc_cols=0,
+                   **solve_kw):
+        """The fit from the raw merged training series (kf_fit_series): scaling (Ksysid.m:180-229), delay embedding
+        (868-907) and snapshot pairs (910-984, snapshots = Inf) are built on the device.  Returns the dict of `fit`
+        plus scale = {y_offset, y_factor, u_offset, u_factor} and M."""
+        t = np.ascontiguousarray(np.asarray(t, dtype=np.float64).ravel())
+        y = A.fcol(np.asarray(y, dtype=np.float64).reshape(t.size, -1))
+        u = np.zeros((t.size, 0), order="F") if u is None or np.size(u) == 0 else A.fcol(np.asarray(u, dtype=np.float64).reshape(t.size, -1))
+        T, n = y.shape
+        m = u.shape[1]
+        _, N, P = self.dims(basis, model_type, m)
+        Pc = int(pc_cols) if 0 < int(pc_cols) < P else P
+        ser = A.kf_series(T=T, n=n, m=m, nd=int(nd), model=A.MODEL_CODE[model_type], t=A.dptr(t), y=A.dptr(y), u=A.dptr(u),
+                          prescaled=int(bool(prescaled)), pc_cols=int(pc_cols))
+        sv, keep_t = self._solve_struct(**solve_kw)
+        nt = max(1, sv.nt) if not sv.least_squares else 1
+        res = A.kf_result()
+        K = np.zeros((P, Pc, nt), order="F")
+        perm = np.zeros(P, dtype=np.int32)
+        obj, l1, gap = np.zeros(nt), np.zeros(nt), np.zeros(nt)
+        iters = np.zeros(nt, dtype=np.int32)
+        res.K, res.perm = A.dptr(K), perm.ctypes.data_as(A.c_int_p)
+        res.objective, res.l1norm, res.qp_iters, res.qp_gap = A.dptr(obj), A.dptr(l1), iters.ctypes.data_as(A.c_int_p), A.dptr(gap)
+        out = {}
+        if want_gram:
+            out["G"], out["C"] = np.zeros((P, P), order="F"), np.zeros((P, P), order="F")
+            res.G, res.C = A.dptr(out["G"]), A.dptr(out["C"])
+        if want_regressors:
+            M = int(self.lib.kf_series_pairs(T, int(nd), A.dptr(t)))
+            out["Px"], out["Py"] = np.zeros((M, P), order="F"), np.zeros((M, P), order="F")
+            res.Px, res.Py = A.dptr(out["Px"]), A.dptr(out["Py"])
+        sc = A.kf_scale()
+        scale = {k: np.zeros(n if k[0] == "y" else m) for k in ("y_offset", "y_factor", "u_offset", "u_factor")}
+        for k, v in scale.items():
+            setattr(sc, k, A.dptr(v))
+        self._check(self.lib.kf_fit_series(self.ctx, basis.ref(), C.byref(ser), C.byref(sv), C.byref(sc), C.byref(res)), "kf_fit_series")
+        info = {f: getattr(res.info, f) for f, _ in A.kf_info._fields_}
+        out.update(K=K[:, :, 0] if nt == 1 else K, K_all=K, rank=info["rank"], perm=perm, info=info, N=N, P=P,
+                   objective=obj, l1norm=l1, qp_iters=iters, qp_gap=gap, scale=scale, M=int(sc.M))
+        return out
+
     def fit_batch(self, problems):
         """Many independent fits in one call (kf_fit_batch).  `problems`: list of dicts with keys basis, model_type,
         alpha, beta, u and optional solve keywords (as Fitter.fit).  Small least-squares problems (P <= 32) run
@@ -186,11 +227,14 @@ class Fitter:
         for c, md in enumerate(models):
             mds[c].model = A.MODEL_CODE[model_type]
             mds[c].n, mds[c].m, mds[c].nzeta, mds[c].N = int(n), int(m), int(nzeta), int(N)
-            for name in ("A", "B", "F"):
-                if md.get(name) is not None:
-                    arr = A.fcol(md[name])
-                    keep.append(arr)
-                    setattr(mds[c], name, A.dptr(arr))
+            want = {"linear": {"A": (N, N), "B": (N, m)}, "bilinear": {"A": (N, N), "B": (N, N * m)},
+                    "nonlinear": {"F": (nzeta, N)}}[model_type]
+            for name, shape in want.items():
+                if md.get(name) is None or np.shape(md[name]) != shape:
+                    raise A.KoopfitError(f"rollout: model {c} needs {name} of shape {shape}, got {np.shape(md.get(name))}")
+                arr = A.fcol(md[name])
+                keep.append(arr)
+                setattr(mds[c], name, A.dptr(arr))
         T = (C.c_int * nt)()
         z0 = (A.c_double_p * nt)()
         up = (A.c_double_p * nt)()

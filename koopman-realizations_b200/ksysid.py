@@ -9,8 +9,10 @@ loop, Px'Px / Px'Py, `\\` and the L1-ball QP (Ksysid.m:987-1176) and the lasso l
 train_models (1370-1387) — one kf_fit call.  The MATLAB original keeps this host logic in
 MATLAB; here it is Python because MATLAB/Octave are absent.
 
-Pre-processing (merge / scale / zeta / snapshot pairs, Ksysid.m:180-229, 380-401, 868-984)
-stays on the host as in the reference (SURVEY §8f "next #3").
+Pre-processing (merge / scale / zeta / snapshot pairs, Ksysid.m:180-229, 380-401, 868-984) is
+available both ways: the host mirror below (the `traindata` / `snapshotPairs` properties of the
+reference) and, with `device_preprocess=True`, kf_fit_series, which takes the raw merged series and
+builds scale factors, delay embedding and pairs on the GPU (SURVEY §8f "next #3").
 """
 from __future__ import annotations
 
@@ -73,7 +75,8 @@ class Ksysid:
         self.loaded = False
         self.time_type = "discrete"
         self.dim_red = None
-        extras = {"centres": None, "device": 0, "fitter": None, "ls_method": "auto", "rng_seed": 0, "fast_cols": False}
+        extras = {"centres": None, "device": 0, "fitter": None, "ls_method": "auto", "rng_seed": 0, "fast_cols": False,
+                  "device_preprocess": False}
         for k, v in kw.items():          # parse_args, Ksysid.m:147-158
             if k in extras:
                 extras[k] = v
@@ -95,6 +98,8 @@ class Ksysid:
         self._ls_method = extras["ls_method"]
         # opt-in: compute only the K columns the model consumes (K(:,1:N) or K(:,1:nzeta)); model['K'] is then P x Pc
         self._fast_cols = bool(extras["fast_cols"])
+        # opt-in: train_models hands the raw merged series to the GPU (bilinear / nonlinear models, snapshots = Inf)
+        self._device_preprocess = bool(extras["device_preprocess"])
 
         tr0 = data4sysid["train"][0]
         y0, u0 = np.atleast_2d(np.asarray(tr0["y"], float)), np.atleast_2d(np.asarray(tr0["u"], float))
@@ -107,6 +112,7 @@ class Ksysid:
 
         # merge + scale (Ksysid.m:119-128)
         merged = merge_trials(data4sysid["train"])
+        self._merged_raw = merged
         sc = _scale_factors(merged)
         self.params["scale"] = sc
         self.scaledown = {"y": lambda y: (y - sc["y_offset"]) / sc["y_factor"], "u": lambda u: (u - sc["u_offset"]) / sc["u_factor"]}
@@ -263,10 +269,32 @@ class Ksysid:
         return {"F_sym": F, "F_func": lambda zeta, u: F @ self._lift(np.concatenate([np.ravel(zeta), np.ravel(u)])),
                 "params": self.params, "C": np.eye(n), "K": koopData["K"]}
 
+    def get_Koopman_series(self, lasso=None):
+        """get_Koopman from the raw merged training series: scaling, zeta and the pairs are built on the GPU
+        (kf_fit_series); same outputs as get_Koopman (koopData without Px / Py)."""
+        print("Finding Koopman operator approximation...")
+        N = self.params["N"]
+        lasso = self.lasso if lasso is None else np.atleast_1d(np.asarray(lasso, dtype=np.float64))
+        raw = self._merged_raw
+        kw = dict(nd=self.params["nd"])
+        if np.all(self.lasso >= 1e6):
+            pc = (self.params["nzeta"] if self.model_type == "nonlinear" else N) if self._fast_cols else 0
+            res = self.fitter.fit_series(self.basis, self.model_type, raw["t"], raw["y"], raw["u"], least_squares=True,
+                                         ls_method=self._ls_method, pc_cols=pc, **kw)
+        else:
+            res = self.fitter.fit_series(self.basis, self.model_type, raw["t"], raw["y"], raw["u"], least_squares=False,
+                                         t=lasso * N, **kw)
+        self.params["scale_device"] = res["scale"]
+        return [{"K": np.array(res["K_all"][:, :, i]), "info": res["info"], "rank": res["rank"], "M": res["M"]}
+                for i in range(res["K_all"].shape[2])]
+
     def train_models(self, lasso=None):
         """Ksysid.m:1344-1389: candidates per lasso value; model = candidates{1}."""
         lasso = self.lasso if lasso is None else np.atleast_1d(np.asarray(lasso, dtype=np.float64))
-        kds = self.get_Koopman(self.snapshotPairs, lasso)
+        if self._device_preprocess and self.model_type != "linear" and not np.isfinite(self.snapshots):
+            kds = self.get_Koopman_series(lasso)
+        else:
+            kds = self.get_Koopman(self.snapshotPairs, lasso)
         extract = {"nonlinear": self.get_NLmodel, "bilinear": self.get_BLmodel, "linear": self.get_model}[self.model_type]
         cands = []
         for i, kd in enumerate(kds):
