@@ -199,6 +199,17 @@ typedef struct {
 int kf_rollout(kf_ctx* ctx, const kf_basis* basis, int nmodels, const kf_model* models, int ntrials, const int* T,
                const double* const* zeta0, const double* const* u, int nout, double* const* ysim);
 
+/* ---- lasso sweep split across ranks (one process per GPU) -------------------
+ * After the all-reduce of the partial Grams every rank holds the same G, C.  With a column partition the exact
+ * active-set solver of rank r factors and updates only the columns [col_lo, col_hi) of K for ALL budgets; the columns
+ * couple through the multiplier and the step control alone, i.e. a few doubles per step, which the library hands to
+ * `allreduce` (op 0: sum, op 1: max over the ranks, in place; return 0 on success).  Every rank then takes the same
+ * decisions; K comes back with only this rank's columns filled (the caller gathers the column blocks), objective, l1norm
+ * and qp_gap are the global values.  col_hi <= col_lo restores the unpartitioned solve.  Not combinable with the pinned
+ * delay columns (linear model with delays). */
+typedef int (*kf_allreduce_fn)(void* user, double* vals, int n, int op);
+int kf_set_qp_partition(kf_ctx* ctx, int col_lo, int col_hi, kf_allreduce_fn allreduce, void* user);
+
 /* ---- staged, device-resident API (one rank of a snapshot-sharded fit) ---
  * kf_accumulate_dev: lift + Gram of this rank's shard; DEVICE pointers in `prob`;
  *   reset!=0 zeroes the accumulator first.  Asynchronous on the context stream.

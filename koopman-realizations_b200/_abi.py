@@ -77,6 +77,9 @@ class kf_model(C.Structure):
                 ("A", c_double_p), ("B", c_double_p), ("F", c_double_p)]
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_int, C.c_int)
+
+
 class KoopfitError(RuntimeError):
     pass
 
@@ -167,6 +170,7 @@ def load():
         "kf_series_pairs": (ll, [ll, i, c_double_p]),
         "kf_fit_batch": (i, [vp, i, P(P(kf_basis)), P(kf_problem), P(kf_solve), P(kf_result)]),
         "kf_rollout": (i, [vp, P(kf_basis), i, P(kf_model), i, c_int_p, P(c_double_p), P(c_double_p), i, P(c_double_p)]),
+        "kf_set_qp_partition": (i, [vp, i, i, ALLREDUCE_FN, vp]),
         "kf_mldivide": (i, [vp, ll, i, i, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]),
         "kf_accumulate_dev": (i, [vp, P(kf_basis), P(kf_problem), i]),
         "kf_accum_buffer": (i, [vp, P(vp), P(C.c_size_t)]),
@@ -185,5 +189,5 @@ def load():
 
 
 EXPORTS = ["kf_create", "kf_destroy", "kf_last_error", "kf_version", "kf_basis_dims", "kf_block_table",
-           "kf_lift", "kf_fit", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_mldivide", "kf_accumulate_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
+           "kf_lift", "kf_fit", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_set_qp_partition", "kf_mldivide", "kf_accumulate_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
            "kf_stream", "kf_counters", "kf_last_times", "kf_set_option"]

@@ -439,20 +439,37 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
             }
             std::vector<KfQpResult> qr(nb);
             const bool active_set = ctx->opt_qp_method == 2 || (ctx->opt_qp_method == 0 && P > 256);
+            const bool split = active_set && ctx->qp_hi > ctx->qp_lo;     // column partition across ranks
             if (active_set)
                 KF_TRY(kf_solve_l1ball_as(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1, sv->qp_max_iter,
                                           Kt, qr.data(), st));
             else
                 KF_TRY(kf_solve_l1ball_multi(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1, sv->qp_max_iter,
                                              sv->qp_tol, Kt, qr.data(), st));
+            // objective, ||K||_1 and the gap: over ALL columns (the pinned ones count towards the budget row, Ksysid.m:1136);
+            // with a column partition the per-rank pieces are combined through the caller's all-reduce
+            auto evaluate = [&](int b, KfQpResult* ev) -> int {
+                KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt + (size_t)b * Pp * Pp, c0, c1, tf[b], ev, st,
+                                      split ? ctx->qp_lo : 0, split ? ctx->qp_hi : 0));
+                if (split && ctx->qp_allreduce) {
+                    double v[3] = {ev->objective, ev->l1, ev->grad_inner}, mx = ev->grad_max;
+                    if (ctx->qp_allreduce(ctx->qp_user, v, 3, 0) || ctx->qp_allreduce(ctx->qp_user, &mx, 1, 1)) {
+                        ctx->err = "kf_solve: the all-reduce hook failed";
+                        return KF_EINVAL;
+                    }
+                    ev->objective = v[0]; ev->l1 = v[1]; ev->grad_inner = v[2]; ev->grad_max = mx;
+                    ev->gap = std::max(0.0, v[2] + std::max(tf[b], 0.0) * mx);
+                }
+                return KF_OK;
+            };
             for (int b = 0; b < nb; ++b) {
                 const int it = act[g0 + b];
                 capped += qr[b].capped;
-                KfQpResult ev{};   // objective and ||K||_1 over ALL columns (the pinned ones count towards the budget row, Ksysid.m:1136)
-                KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt + (size_t)b * Pp * Pp, c0, c1, tf[b], &ev, st));
+                KfQpResult ev{};
+                KF_TRY(evaluate(b, &ev));
                 if (ev.l1 > sv->t[it] * (1.0 + 1e-13) && ev.l1 > pinned_l1) {   // an unconverged iterate: make it feasible
                     KF_TRY(kf_qp_scale_free(ctx, Kt + (size_t)b * Pp * Pp, P, Pp, c0, c1, tf[b] / (ev.l1 - pinned_l1), st));
-                    KF_TRY(kf_qp_evaluate(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), Kt + (size_t)b * Pp * Pp, c0, c1, tf[b], &ev, st));
+                    KF_TRY(evaluate(b, &ev));
                 }
                 if (out->objective) out->objective[it] = ev.objective;
                 if (out->l1norm) out->l1norm[it] = ev.l1;
@@ -847,6 +864,19 @@ int kf_rollout(kf_ctx* ctx, const kf_basis* basis, int nmodels, const kf_model* 
     KF_TRY(prepare_program(ctx, basis));
     ctx->lay.valid = false;
     return kf_rollout_impl(ctx, nmodels, models, ntrials, T, zeta0, u, nout, ysim);
+}
+
+int kf_set_qp_partition(kf_ctx* ctx, int col_lo, int col_hi, kf_allreduce_fn allreduce, void* user) {
+    if (!ctx) return KF_EINVAL;
+    if (col_hi > col_lo && (col_lo < 0 || !allreduce)) {
+        ctx->err = "kf_set_qp_partition: col_lo >= 0 and an all-reduce hook are required";
+        return KF_EINVAL;
+    }
+    ctx->qp_lo = col_hi > col_lo ? col_lo : 0;
+    ctx->qp_hi = col_hi > col_lo ? col_hi : 0;
+    ctx->qp_allreduce = col_hi > col_lo ? allreduce : nullptr;
+    ctx->qp_user = user;
+    return KF_OK;
 }
 
 int kf_mldivide(kf_ctx* ctx, long long M, int P, int Pc, const double* A, const double* B, double* X, int* perm, int* rank) {

@@ -129,6 +129,11 @@ struct kf_ctx {
     double opt_as_ws_gb = 8;  // active-set solver: bound on the per-column Cholesky workspace (columns run in chunks that fit)
     int opt_tma = 1;          // Gram kernel operand path: 1 = tensor-map TMA + mbarrier ring, 0 = per-thread cp.async
 
+    // column partition of the active-set QP solver across ranks (kf_set_qp_partition)
+    int qp_lo = 0, qp_hi = 0;
+    kf_allreduce_fn qp_allreduce = nullptr;
+    void* qp_user = nullptr;
+
     // counters
     double dmma_flops = 0;
     long long launches = 0;
@@ -226,4 +231,4 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
 int kf_qp_scale_free(kf_ctx* ctx, double* K, int P, int Pp, int fix_c0, int fix_c1, double s, cudaStream_t st);
 int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_t st);
 int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, int fix_c0, int fix_c1, double t_free,
-                   KfQpResult* res, cudaStream_t st);
+                   KfQpResult* res, cudaStream_t st, int own_lo = 0, int own_hi = 0);

@@ -212,11 +212,12 @@ __global__ void __launch_bounds__(256) kf_cd_reduce_kernel(const double* l1, con
 }
 
 // single CTA: Frank-Wolfe duality gap pieces over the free columns: out[0] = sum <grad_j, k_j>, out[1] = max |grad|
-__global__ void __launch_bounds__(256) kf_gap_reduce_kernel(const double* aux, const double* gmax, int n, int skip0, int skip1, double* out) {
+__global__ void __launch_bounds__(256) kf_gap_reduce_kernel(const double* aux, const double* gmax, int n, int skip0, int skip1, int own_lo,
+                                                            int own_hi, double* out) {
     __shared__ double red[32];
     double a = 0, m = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        if (i >= skip0 && i < skip1) continue;
+        if ((i >= skip0 && i < skip1) || i < own_lo || i >= own_hi) continue;
         a += aux[i];
         m = fmax(m, gmax[i]);
     }
@@ -509,7 +510,8 @@ int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_
 //   gap = <grad, K> + t_free * ||grad||_inf  >=  f(K) - min{ f(Z) : ||Z_free||_1 <= t_free, pinned columns fixed }
 // over the free columns (grad = G K - C): a certificate of the objective that needs no reference solver.
 int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, int fix_c0, int fix_c1,
-                   double t_free, KfQpResult* res, cudaStream_t st) {
+                   double t_free, KfQpResult* res, cudaStream_t st, int own_lo, int own_hi) {
+    if (own_hi <= own_lo) { own_lo = 0; own_hi = P; }
     const long long ld = Pp;
     const size_t smem = (size_t)P * (2 * sizeof(double) + sizeof(int)) + 16;
     KF_TRY(ensure_cd_smem(ctx, smem));
@@ -528,7 +530,7 @@ int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C,
     a.col_l1 = sc.c_l1; a.col_obj = sc.c_ob; a.col_aux = sc.c_aux; a.col_iters = sc.c_it; a.col_gmax = sc.c_gmax;
     kf_cd_kernel<<<dim3(P, 1), CD_THREADS, smem, st>>>(a);
     kf_cd_reduce_kernel<<<1, 256, 0, st>>>(sc.c_l1, sc.c_ob, sc.c_aux, sc.c_it, P, 0, 0, sc.d_active, sc.d_out);
-    kf_gap_reduce_kernel<<<1, 256, 0, st>>>(sc.c_aux, sc.c_gmax, P, fix_c0, fix_c1, sc.d_out + 4);
+    kf_gap_reduce_kernel<<<1, 256, 0, st>>>(sc.c_aux, sc.c_gmax, P, fix_c0, fix_c1, own_lo, own_hi, sc.d_out + 4);
     KF_CUDA(ctx, cudaGetLastError());
     double h[6];
     KF_CUDA(ctx, cudaMemcpyAsync(h, sc.d_out, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));

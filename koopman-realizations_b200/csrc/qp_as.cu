@@ -28,6 +28,13 @@ constexpr int AS_NB = 32;      // block-column width of the factorisation
 constexpr int AS_TM = 128;     // rows per tile
 constexpr int AS_TLD = AS_TM + 1;
 
+// columns a rank works on: [lo, hi) minus the pinned delay columns [skip0, skip1)
+struct AsCols {
+    int lo, hi, skip0, skip1;
+    __host__ __device__ bool on(int c) const { return c >= lo && c < hi && !(c >= skip0 && c < skip1); }
+};
+constexpr int AS_NL = 16;      // trial multipliers evaluated per pass of the step control
+
 struct AsArgs {
     const double* G; long long ldg;
     const double* C; const double* SG; double* Aout; double* Bout; long long ld;   // P x P, column-major
@@ -263,13 +270,13 @@ __global__ void __launch_bounds__(AS_THREADS, 2) kf_as_chol_kernel(const AsArgs 
 }
 
 // one CTA per column: ascending list of the support {i : SG(i, col) != 0} and its size
-__global__ void __launch_bounds__(256) kf_as_index_kernel(const double* SG, long long ld, int P, int skip0, int skip1, int* idx, int* cnt) {
+__global__ void __launch_bounds__(256) kf_as_index_kernel(const double* SG, long long ld, int P, AsCols cs, int* idx, int* cnt) {
     __shared__ int wsum[8];
     __shared__ int base;
     const int col = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) base = 0;
     __syncthreads();
-    if (col >= skip0 && col < skip1) {
+    if (!cs.on(col)) {
         if (tid == 0) cnt[col] = 0;
         return;
     }
@@ -295,17 +302,13 @@ __global__ void __launch_bounds__(256) kf_as_index_kernel(const double* SG, long
     if (tid == 0) cnt[col] = base;
 }
 
-// single CTA: the multiplier that meets the budget on the current pattern, lam_b = (sum_j s'a_j - t) / sum_j s'b_j over
-// the free columns, under a trust region: lam = max(lam_b, lam_prev / 2).  Without it a budget the current support
-// cannot use up gives lam = 0, every off-support entry enters at once and the iteration never recovers (observed);
-// halving at most lets the support grow along the regularisation path (the host bounds the step further by the number
-// of pattern changes, see below).  scal = [lam, num, den, dead]
-__global__ void __launch_bounds__(256) kf_as_lambda_kernel(const double* col_num, const double* col_den, const int* col_dead, int P, int skip0,
-                                                           int skip1, double t, double lam_prev, double* scal) {
+// single CTA: scal = [sum_j s'a_j, sum_j s'b_j, skipped pivots] over this rank's columns (fixed order: deterministic)
+__global__ void __launch_bounds__(256) kf_as_sums_kernel(const double* col_num, const double* col_den, const int* col_dead, int P, AsCols cs,
+                                                         double* scal) {
     __shared__ double r0[256], r1[256], r2[256];
     double n = 0.0, d = 0.0, dd = 0.0;
     for (int i = threadIdx.x; i < P; i += 256) {
-        if (i >= skip0 && i < skip1) continue;
+        if (!cs.on(i)) continue;
         n += col_num[i]; d += col_den[i]; dd += col_dead[i];
     }
     r0[threadIdx.x] = n; r1[threadIdx.x] = d; r2[threadIdx.x] = dd;
@@ -318,47 +321,57 @@ __global__ void __launch_bounds__(256) kf_as_lambda_kernel(const double* col_num
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        const double lam_b = r1[0] > 0.0 ? fmax((r0[0] - t) / r1[0], 0.0) : 0.0;
-        scal[0] = fmax(lam_b, 0.5 * lam_prev); scal[1] = r0[0]; scal[2] = r1[0]; scal[3] = r2[0];
-    }
+    if (threadIdx.x == 0) { scal[0] = r0[0]; scal[1] = r1[0]; scal[2] = r2[0]; }
 }
 
-// Pattern changes a trial multiplier would cause: K(lam) = A - lam B and grad(lam) = G A - lam G B - C are both affine in
-// lam, so every trial costs one element-wise pass and no factorisation.  counts[0] = leaving, counts[1] = entering
-__global__ void kf_as_count_kernel(const double* A, const double* B, const double* SG, const double* GA, const double* GB, const double* C,
-                                   long long ld, int P, int skip0, int skip1, double lam, double rel, int* counts) {
-    const long long n = (long long)P * P;
-    int left = 0, entered = 0;
+// Pattern changes that trial multipliers would cause: K(lam) = A - lam B and grad(lam) = G A - lam G B - C are both
+// affine in lam, so AS_NL trials cost ONE element-wise pass and no factorisation.  counts[l] = leaving + entering for lams[l]
+struct AsLams { double v[AS_NL]; };
+__global__ void __launch_bounds__(256) kf_as_count_kernel(const double* A, const double* B, const double* SG, const double* GA, const double* GB,
+                                                          const double* C, long long ld, int P, AsCols cs, AsLams lams, int nl, double rel,
+                                                          unsigned long long* counts) {
+    __shared__ unsigned int sc[AS_NL];
+    if (threadIdx.x < AS_NL) sc[threadIdx.x] = 0;
+    __syncthreads();
+    const int ncol = cs.hi - cs.lo;
+    const long long n = (long long)P * ncol;
+    int cnt[AS_NL];
+#pragma unroll
+    for (int l = 0; l < AS_NL; ++l) cnt[l] = 0;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(e % P), c = (int)(e / P);
-        if (c >= skip0 && c < skip1) continue;
+        const int i = (int)(e % P), c = cs.lo + (int)(e / P);
+        if (c >= cs.skip0 && c < cs.skip1) continue;
         const long long o = i + (long long)c * ld;
         const double s = SG[o];
         if (s != 0.0) {
-            if (!(fma(-lam, B[o], A[o]) * s > 0.0)) ++left;
+            const double a = A[o], b = B[o];
+#pragma unroll
+            for (int l = 0; l < AS_NL; ++l)
+                if (l < nl && !(fma(-lams.v[l], b, a) * s > 0.0)) ++cnt[l];
         } else {
-            const double g = fma(-lam, GB[o], GA[o]) - C[o];
-            if (fabs(g) > lam * (1.0 + rel)) ++entered;
+            const double ga = GA[o] - C[o], gb = GB[o];
+#pragma unroll
+            for (int l = 0; l < AS_NL; ++l)
+                if (l < nl && fabs(fma(-lams.v[l], gb, ga)) > lams.v[l] * (1.0 + rel)) ++cnt[l];
         }
     }
-    for (int off = 16; off > 0; off >>= 1) {
-        left += __shfl_down_sync(0xffffffffu, left, off);
-        entered += __shfl_down_sync(0xffffffffu, entered, off);
+#pragma unroll
+    for (int l = 0; l < AS_NL; ++l) {
+        int v = cnt[l];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sc[l], (unsigned)v);
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (left) atomicAdd(counts + 0, left);
-        if (entered) atomicAdd(counts + 1, entered);
-    }
+    __syncthreads();
+    if (threadIdx.x < nl && sc[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)sc[threadIdx.x]);
 }
 
 // K = A - lam B on the support; entries whose sign flipped leave (K = 0), dual violators enter with sign -sign(grad)
 __global__ void kf_as_apply_kernel(const double* A, const double* B, double* SG, const double* GA, const double* GB, const double* C, double* K,
-                                   long long ld, int P, int skip0, int skip1, double lam, double rel) {
-    const long long n = (long long)P * P;
+                                   long long ld, int P, AsCols cs, double lam, double rel) {
+    const long long n = (long long)P * (cs.hi - cs.lo);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(e % P), c = (int)(e / P);
-        if (c >= skip0 && c < skip1) continue;
+        const int i = (int)(e % P), c = cs.lo + (int)(e / P);
+        if (c >= cs.skip0 && c < cs.skip1) continue;
         const long long o = i + (long long)c * ld;
         const double s = SG[o];
         double k = 0.0;
@@ -374,12 +387,12 @@ __global__ void kf_as_apply_kernel(const double* A, const double* B, double* SG,
 }
 
 // cold start: SG = sign(C) where |C| >= thr (free columns), 0 elsewhere;  warm start: SG = sign(K)
-__global__ void kf_as_init_kernel(const double* src, double thr, double* SG, long long ld, int P, int Pp, int skip0, int skip1) {
+__global__ void kf_as_init_kernel(const double* src, double thr, double* SG, long long ld, int P, int Pp, AsCols cs) {
     const long long n = (long long)Pp * Pp;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(e % Pp), c = (int)(e / Pp);
         double s = 0.0;
-        if (i < P && c < P && !(c >= skip0 && c < skip1)) {
+        if (i < P && c < P && cs.on(c)) {
             const double v = src[i + (long long)c * ld];
             if (fabs(v) >= thr && v != 0.0) s = v > 0.0 ? 1.0 : -1.0;
         }
@@ -387,13 +400,13 @@ __global__ void kf_as_init_kernel(const double* src, double thr, double* SG, lon
     }
 }
 
-__global__ void kf_as_absmax_kernel(const double* C, long long ld, int P, int skip0, int skip1, double* out) {
+__global__ void kf_as_absmax_kernel(const double* C, long long ld, int P, AsCols cs, double* out) {
     __shared__ double red[32];
     double m = 0;
     const long long n = (long long)P * P;
     for (long long e = threadIdx.x; e < n; e += blockDim.x) {
         const int i = (int)(e % P), c = (int)(e / P);
-        if (c >= skip0 && c < skip1) continue;
+        if (!cs.on(c)) continue;
         m = fmax(m, fabs(C[i + (long long)c * ld]));
     }
     for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, off));
@@ -411,6 +424,9 @@ __global__ void kf_as_absmax_kernel(const double* C, long long ld, int P, int sk
 // Solve the nb ACTIVE budgets t[0..nb) (any order; traversed ascending, each warm-started from the previous support).
 // G, C: Pp-strided P x P.  K_all: nb matrices (stride Pp*Pp); the pinned delay columns [fix_c0, fix_c1) must already
 // hold their pattern in every K_b and t[] is the budget left for the free columns.
+// Column partition (kf_set_qp_partition): this rank factors and updates only the columns [qp_lo, qp_hi) of K — the
+// columns couple through the multiplier and the step control alone, i.e. through a handful of scalars per step that are
+// summed over the ranks by the caller's all-reduce hook; every rank then takes identical decisions.
 int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, int nb, const double* t, int fix_c0, int fix_c1,
                        int max_iter, double* K_all, KfQpResult* res, cudaStream_t st) {
     if (nb <= 0) return KF_OK;
@@ -418,9 +434,24 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
         ctx->err = "active-set QP solver: P > 4096 is not supported";
         return KF_EUNSUPPORTED;
     }
+    const bool split = ctx->qp_hi > ctx->qp_lo;
+    AsCols cs{split ? std::max(ctx->qp_lo, 0) : 0, split ? std::min(ctx->qp_hi, P) : P, fix_c0, fix_c1};
+    if (split && fix_c1 > fix_c0) {
+        ctx->err = "active-set QP solver: a column partition cannot be combined with pinned delay columns";
+        return KF_EUNSUPPORTED;
+    }
+    auto reduce = [&](double* v, int n, int op) -> int {       // op 0 = sum, 1 = max over the ranks
+        if (!split || !ctx->qp_allreduce) return KF_OK;
+        if (ctx->qp_allreduce(ctx->qp_user, v, n, op)) {
+            ctx->err = "active-set QP solver: the all-reduce hook failed";
+            return KF_EINVAL;
+        }
+        return KF_OK;
+    };
+    const int ncol = cs.hi - cs.lo;
     const long long ld = Pp;
     const size_t mat = (size_t)Pp * Pp;
-    // matrices: SG | A | B | GA | GB ; ints: idx[P*P] | cnt[P] | cols[P] | dead[P] | counts[2] ; doubles: num[P] | den[P] | scal[8] ; offsets[P]
+    // matrices: SG | A | B | GA | GB ; ints: idx[P*P] | cnt[P] | cols[P] | dead[P] ; doubles: num[P] | den[P] | scal[8] ; offsets[P]
     KF_CUDA(ctx, ctx->d_as_mat.ensure(5 * mat * sizeof(double)));
     double* SG = ctx->d_as_mat.as<double>();
     double* Am = SG + mat;
@@ -429,22 +460,22 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     double* GB = GA + mat;      // G B
     const size_t n_int = (size_t)P * P + 3ull * P + 8;
     const size_t n_dbl = 2ull * P + 8;
-    KF_CUDA(ctx, ctx->d_as_aux.ensure(n_dbl * sizeof(double) + (size_t)P * sizeof(long long) + n_int * sizeof(int) + 64));
+    KF_CUDA(ctx, ctx->d_as_aux.ensure(n_dbl * sizeof(double) + (size_t)(P + AS_NL + 2) * sizeof(long long) + n_int * sizeof(int) + 64));
     double* d_num = ctx->d_as_aux.as<double>();
     double* d_den = d_num + P;
     double* d_scal = d_den + P;
     long long* d_off = reinterpret_cast<long long*>(d_scal + 8);
-    int* d_idx = reinterpret_cast<int*>(d_off + P);
+    unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(d_off + P);
+    int* d_idx = reinterpret_cast<int*>(d_counts + AS_NL + 2);
     int* d_cnt = d_idx + (size_t)P * P;
     int* d_cols = d_cnt + P;
     int* d_dead = d_cols + P;
-    int* d_counts = d_dead + P;
 
     // workspace for the factors: bounded (option as_ws_gb, default 8 GB), columns are processed in chunks that fit
     size_t free_b = 0, total_b = 0;
     KF_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     const size_t one_col = (size_t)(P + 3) * P * sizeof(double);
-    size_t ws_bytes = std::min<size_t>((size_t)(ctx->opt_as_ws_gb * 1073741824.0), (size_t)P * one_col);
+    size_t ws_bytes = std::min<size_t>((size_t)(ctx->opt_as_ws_gb * 1073741824.0), (size_t)std::max(ncol, 1) * one_col);
     ws_bytes = std::max(ws_bytes, one_col);
     if (ctx->d_as_ws.bytes < ws_bytes) {
         if (ws_bytes > ctx->d_as_ws.bytes + free_b) ws_bytes = std::max(one_col, (size_t)(0.8 * (double)(ctx->d_as_ws.bytes + free_b)));
@@ -461,6 +492,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     }
     const int egrid = ctx->sm_count * 4;
     const int iter_cap = max_iter > 0 ? max_iter : 200;
+    const double rel = 1e-10;
 
     std::vector<int> order(nb);
     std::iota(order.begin(), order.end(), 0);
@@ -468,20 +500,36 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
 
     std::vector<int> h_cnt(P), h_cols(P);
     std::vector<long long> h_off(P);
-    double h_scal[8];
-    int h_counts[2];
-
-    // one exact step on the current pattern SG for budget tb; K (unclipped) -> Kout, pattern updated
-    double lam_prev = 0.0;
+    unsigned long long h_counts[AS_NL];
+    double lam_prev = 0.0, lam_now = 0.0;
     bool clamped = false;
-    auto step = [&](double tb, double* Kout) -> int {
-        kf_as_index_kernel<<<P, 256, 0, st>>>(SG, ld, P, fix_c0, fix_c1, d_idx, d_cnt);
-        KF_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
-        KF_CUDA(ctx, cudaMemsetAsync(Am, 0, mat * sizeof(double), st));
-        KF_CUDA(ctx, cudaMemsetAsync(Bm, 0, mat * sizeof(double), st));
+    long long changed = 0;
+
+    // counts[l] = entries that would leave or enter at lams[l], summed over the ranks
+    auto count = [&](const double* lams, int nl, double* out) -> int {
+        AsLams L{};
+        for (int l = 0; l < nl; ++l) L.v[l] = lams[l];
+        KF_CUDA(ctx, cudaMemsetAsync(d_counts, 0, AS_NL * sizeof(unsigned long long), st));
+        kf_as_count_kernel<<<egrid, 256, 0, st>>>(Am, Bm, SG, GA, GB, C, ld, P, cs, L, nl, rel, d_counts);
+        KF_CUDA(ctx, cudaGetLastError());
+        KF_CUDA(ctx, cudaMemcpyAsync(h_counts, d_counts, AS_NL * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         KF_CUDA(ctx, cudaStreamSynchronize(st));
-        for (int j = 0; j < P; ++j) h_cols[j] = j;
-        std::stable_sort(h_cols.begin(), h_cols.end(), [&](int x, int y) { return h_cnt[x] > h_cnt[y]; });   // heavy columns first
+        ctx->launches += 1;
+        for (int l = 0; l < nl; ++l) out[l] = (double)h_counts[l];
+        return reduce(out, nl, 0);
+    };
+
+    // one exact step on the current pattern SG for budget tb; K -> Kout, pattern updated
+    auto step = [&](double tb, double* Kout) -> int {
+        kf_as_index_kernel<<<P, 256, 0, st>>>(SG, ld, P, cs, d_idx, d_cnt);
+        KF_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaMemsetAsync(Am + (size_t)cs.lo * ld, 0, (size_t)ncol * ld * sizeof(double), st));
+        KF_CUDA(ctx, cudaMemsetAsync(Bm + (size_t)cs.lo * ld, 0, (size_t)ncol * ld * sizeof(double), st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+        int nown = 0;
+        for (int j = cs.lo; j < cs.hi; ++j)
+            if (cs.on(j)) h_cols[nown++] = j;
+        std::stable_sort(h_cols.begin(), h_cols.begin() + nown, [&](int x, int y) { return h_cnt[x] > h_cnt[y]; });   // heavy columns first
         AsArgs a{};
         a.G = G; a.ldg = ld; a.C = C; a.SG = SG; a.Aout = Am; a.Bout = Bm; a.ld = ld;
         a.idx = d_idx; a.cnt = d_cnt; a.ws = ctx->d_as_ws.as<double>();
@@ -490,77 +538,99 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
         std::vector<int> chunk_end;
         {
             size_t used = 0;
-            for (int c = 0; c < P; ++c) {
+            for (int c = 0; c < nown; ++c) {
                 const int n = h_cnt[h_cols[c]];
                 const size_t need = (size_t)((n + 3) & ~1) * (size_t)std::max(n, 1);
                 if (used > 0 && used + need > ws_doubles) { chunk_end.push_back(c); used = 0; }
                 h_off[c] = (long long)used;
                 used += need;
             }
-            chunk_end.push_back(P);
+            chunk_end.push_back(nown);
         }
-        KF_CUDA(ctx, cudaMemcpyAsync(d_cols, h_cols.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
-        KF_CUDA(ctx, cudaMemcpyAsync(d_off, h_off.data(), sizeof(long long) * P, cudaMemcpyHostToDevice, st));
+        if (nown) {
+            KF_CUDA(ctx, cudaMemcpyAsync(d_cols, h_cols.data(), sizeof(int) * nown, cudaMemcpyHostToDevice, st));
+            KF_CUDA(ctx, cudaMemcpyAsync(d_off, h_off.data(), sizeof(long long) * nown, cudaMemcpyHostToDevice, st));
+        }
         int c0 = 0;
         for (int c1 : chunk_end) {
-            a.cols = d_cols + c0; a.ws_off = d_off + c0;
-            kf_as_chol_kernel<<<c1 - c0, AS_THREADS, smem, st>>>(a);
-            KF_CUDA(ctx, cudaGetLastError());
-            ctx->launches += 1;
+            if (c1 > c0) {
+                a.cols = d_cols + c0; a.ws_off = d_off + c0;
+                kf_as_chol_kernel<<<c1 - c0, AS_THREADS, smem, st>>>(a);
+                KF_CUDA(ctx, cudaGetLastError());
+                ctx->launches += 1;
+            }
             c0 = c1;
         }
-        kf_as_lambda_kernel<<<1, 256, 0, st>>>(d_num, d_den, d_dead, P, fix_c0, fix_c1, tb, lam_prev, d_scal);
-        KF_CUDA(ctx, cudaMemcpyAsync(h_scal, d_scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
-        for (int q = 0; q < 2; ++q) {        // GA = G A, GB = G B  (G symmetric: row i of G = column i)
-            KfGemmGrid g{};
-            g.A = G; g.lda = ld; g.B = q ? Bm : Am; g.ldb = ld; g.out = q ? GB : GA; g.ldm = 1; g.ldn = ld;
-            g.m = P; g.n = P; g.k0 = 0; g.k1 = Pp; g.alpha = 1.0; g.accumulate = 0; g.lower_only = 0;
-            KF_TRY(kf_launch_gemm_grid(ctx, g, st));
-        }
-        KF_CUDA(ctx, cudaStreamSynchronize(st));
-        long long nnz = 0;
-        for (int j = 0; j < P; ++j) nnz += h_cnt[j];
-        const long long limit = std::max<long long>((long long)(ctx->opt_as_frac * (double)nnz), P);
-        auto count = [&](double lam) -> int {
-            KF_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 2 * sizeof(int), st));
-            kf_as_count_kernel<<<egrid, 256, 0, st>>>(Am, Bm, SG, GA, GB, C, ld, P, fix_c0, fix_c1, lam, 1e-10, d_counts);
-            KF_CUDA(ctx, cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
-            KF_CUDA(ctx, cudaStreamSynchronize(st));
-            ctx->launches += 1;
-            return KF_OK;
-        };
-        // the multiplier the budget asks for, approached only as far as the pattern change stays bounded: a step that
-        // swaps a large part of the support at once is not a contraction any more (observed from ~40 % density on)
-        const double lam_goal = h_scal[0];
-        double lam = lam_goal;
-        clamped = lam_goal > (h_scal[2] > 0.0 ? (h_scal[1] - tb) / h_scal[2] : 0.0);
-        KF_TRY(count(lam));
-        if ((long long)h_counts[0] + h_counts[1] > limit && lam_prev > 0.0 && lam_goal != lam_prev) {
-            double lo = 0.0, hi = 1.0;
-            for (int r = 0; r < 10; ++r) {
-                const double th = 0.5 * (lo + hi);
-                KF_TRY(count(lam_prev + th * (lam_goal - lam_prev)));
-                if ((long long)h_counts[0] + h_counts[1] > limit) hi = th; else lo = th;
+        kf_as_sums_kernel<<<1, 256, 0, st>>>(d_num, d_den, d_dead, P, cs, d_scal);
+        double sums[4] = {0, 0, 0, 0};
+        KF_CUDA(ctx, cudaMemcpyAsync(sums, d_scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (ncol > 0)
+            for (int q = 0; q < 2; ++q) {        // GA = G A, GB = G B on this rank's columns  (G symmetric: row i of G = column i)
+                KfGemmGrid g{};
+                g.A = G; g.lda = ld; g.B = (q ? Bm : Am) + (size_t)cs.lo * ld; g.ldb = ld; g.out = (q ? GB : GA) + (size_t)cs.lo * ld;
+                g.ldm = 1; g.ldn = ld;
+                g.m = P; g.n = ncol; g.k0 = 0; g.k1 = Pp; g.alpha = 1.0; g.accumulate = 0; g.lower_only = 0;
+                KF_TRY(kf_launch_gemm_grid(ctx, g, st));
             }
-            lam = lam_prev + lo * (lam_goal - lam_prev);
-            clamped = true;
-            KF_TRY(count(lam));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int j = 0; j < nown; ++j) sums[3] += h_cnt[h_cols[j]];
+        KF_TRY(reduce(sums, 4, 0));                 // s'a, s'b, skipped pivots, support size: summed over the ranks
+        const double nnz = sums[3];
+        const double limit = std::max(ctx->opt_as_frac * nnz, (double)P);
+        // The multiplier that meets the budget on the current pattern, lam_b = (sum s'a - t) / sum s'b, under two step
+        // controls.  (1) lam at most halves per step: a budget the current support cannot use up would give lam = 0,
+        // every off-support entry would enter at once and the iteration never recovers (observed).  (2) The step towards
+        // that goal is shortened until the pattern change stays below `limit`: a step that swaps a large part of the
+        // support at once is no contraction any more (observed from ~40 % density on).
+        const double lam_b = sums[1] > 0.0 ? std::max((sums[0] - tb) / sums[1], 0.0) : 0.0;
+        const double lam_goal = std::max(lam_b, 0.5 * lam_prev);
+        clamped = lam_goal > lam_b;
+        double lam = lam_goal, cnts[AS_NL], lams[AS_NL];
+        if (!(lam_prev > 0.0) || lam_goal == lam_prev) {
+            KF_TRY(count(&lam_goal, 1, cnts));
+            changed = (long long)cnts[0];
+        } else {
+            // theta in (0, 1]: lam = lam_prev + theta (lam_goal - lam_prev); a grid of AS_NL trials per pass, theta = 1 included
+            double lo = 0.0, hi = 1.0;
+            for (int pass = 0; pass < 2; ++pass) {
+                const double w = (hi - lo) / AS_NL;
+                for (int l = 0; l < AS_NL; ++l) lams[l] = lam_prev + (lo + w * (l + 1)) * (lam_goal - lam_prev);
+                if (pass == 0) lams[AS_NL - 1] = lam_goal;
+                KF_TRY(count(lams, AS_NL, cnts));
+                if (pass == 0 && cnts[AS_NL - 1] <= limit) {      // the full step is fine
+                    changed = (long long)cnts[AS_NL - 1];
+                    lo = 1.0;
+                    break;
+                }
+                int best = -1;
+                for (int l = 0; l < AS_NL; ++l)
+                    if (cnts[l] <= limit) best = l; else break;
+                if (best >= 0) changed = (long long)cnts[best];
+                lo = lo + w * (best + 1);
+                hi = lo + w;
+                clamped = true;
+            }
+            lam = lo >= 1.0 ? lam_goal : lam_prev + lo * (lam_goal - lam_prev);
+            if (lo == 0.0) {                      // even the smallest step swaps too much: settle the pattern at lam_prev first
+                KF_TRY(count(&lam, 1, cnts));
+                changed = (long long)cnts[0];
+            }
         }
-        kf_as_apply_kernel<<<egrid, 256, 0, st>>>(Am, Bm, SG, GA, GB, C, Kout, ld, P, fix_c0, fix_c1, lam, 1e-10);
+        kf_as_apply_kernel<<<egrid, 256, 0, st>>>(Am, Bm, SG, GA, GB, C, Kout, ld, P, cs, lam, rel);
         KF_CUDA(ctx, cudaGetLastError());
         ctx->launches += 5;
-        h_scal[0] = lam;
+        lam_now = lam;
         lam_prev = lam;
         return KF_OK;
     };
-    auto settled = [&]() { return h_counts[0] == 0 && h_counts[1] == 0 && !clamped; };
+    auto settled = [&]() { return changed == 0 && !clamped; };
 
     // ---- cold start: the pattern is the largest |C| entry and lam starts at max|C| (K = 0 is optimal there)
-    kf_as_absmax_kernel<<<1, 1024, 0, st>>>(C, ld, P, fix_c0, fix_c1, d_scal);
+    kf_as_absmax_kernel<<<1, 1024, 0, st>>>(C, ld, P, AsCols{0, P, fix_c0, fix_c1}, d_scal);
     double cmax = 0;
     KF_CUDA(ctx, cudaMemcpyAsync(&cmax, d_scal, sizeof(double), cudaMemcpyDeviceToHost, st));
     KF_CUDA(ctx, cudaStreamSynchronize(st));
-    kf_as_init_kernel<<<egrid, 256, 0, st>>>(C, cmax, SG, ld, P, Pp, fix_c0, fix_c1);
+    kf_as_init_kernel<<<egrid, 256, 0, st>>>(C, cmax, SG, ld, P, Pp, cs);
     ctx->launches += 2;
     lam_prev = cmax;
     // ---- the budgets, ascending
@@ -573,7 +643,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
             if (settled()) { conv = 1; ++it; break; }
         }
         res[b].iters = it;
-        res[b].lam = h_scal[0];
+        res[b].lam = lam_now;
         res[b].capped = conv ? 0 : 1;
         res[b].l1 = 0;
         res[b].objective = 0;

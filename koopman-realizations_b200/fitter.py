@@ -42,6 +42,24 @@ class Fitter:
     def set_option(self, name, value):
         self._check(self.lib.kf_set_option(self.ctx, name.encode(), float(value)), "kf_set_option")
 
+    def set_qp_partition(self, col_lo, col_hi, allreduce=None):
+        """Column partition of the exact active-set QP solver (kf_set_qp_partition): this rank solves the columns
+        [col_lo, col_hi) of K; `allreduce(values: np.ndarray, op)` must reduce `values` in place over the ranks
+        (op 0 = sum, 1 = max).  col_hi <= col_lo switches the partition off."""
+        if col_hi > col_lo:
+            def hook(_user, ptr, n, op):
+                try:
+                    allreduce(np.ctypeslib.as_array(ptr, shape=(n,)), int(op))
+                    return 0
+                except Exception:       # an exception must not cross the C frame
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self._qp_hook = A.ALLREDUCE_FN(hook)        # keep the trampoline alive
+        else:
+            self._qp_hook = A.ALLREDUCE_FN()
+        self._check(self.lib.kf_set_qp_partition(self.ctx, int(col_lo), int(col_hi), self._qp_hook, None), "kf_set_qp_partition")
+
     def counters(self, reset=False):
         f, n = C.c_double(), C.c_longlong()
         self._check(self.lib.kf_counters(self.ctx, C.byref(f), C.byref(n), int(reset)), "kf_counters")

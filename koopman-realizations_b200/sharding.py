@@ -41,13 +41,15 @@ class DeviceArrayView:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
-def fit_sharded(fitter, basis, model_type, alpha_dev, beta_dev, u_dev, P, budgets=None, group=None, **solve_kw):
+def fit_sharded(fitter, basis, model_type, alpha_dev, beta_dev, u_dev, P, budgets=None, group=None, split="budgets", **solve_kw):
     """One rank's part of a snapshot-sharded fit (one process per GPU).
 
     alpha_dev / beta_dev / u_dev: this rank's shard as CUDA tensors of shape (nzeta, M_r) / (m, M_r), float64,
     contiguous (= column-major M_r x nzeta).  Steps: local lift + Gram (kf_accumulate_dev), ONE all-reduce of the
     packed partial Grams, then either the replicated LS solve or — for a lasso vector — this rank's round-robin
     share of the budgets (all ranks hold the same G, C), gathered so that every rank returns all candidates.
+    split = "columns": the exact active-set solver instead, every rank solving a block of COLUMNS of K for all budgets
+    (the right split for the regularisation-path solver: a budget split would make every rank walk the whole path).
     Returns the dict of Fitter.solve_dev with K_all ordered like `budgets`.
     """
     import torch
@@ -66,6 +68,8 @@ def fit_sharded(fitter, basis, model_type, alpha_dev, beta_dev, u_dev, P, budget
     if budgets is None:
         return fitter.solve_dev(P, **solve_kw)
     budgets = np.atleast_1d(np.asarray(budgets, dtype=np.float64))
+    if world > 1 and split == "columns":
+        return _solve_column_split(fitter, P, budgets, rank, world, alpha_dev.device, group, **solve_kw)
     mine = budgets_for_rank(budgets.size, rank, world)
     res = fitter.solve_dev(P, least_squares=False, t=budgets[mine] if mine.size else budgets[:1], **solve_kw)
     if world == 1:
@@ -79,4 +83,57 @@ def fit_sharded(fitter, basis, model_type, alpha_dev, beta_dev, u_dev, P, budget
         for j, i in enumerate(idx):
             K_all[:, :, i], obj[i], l1[i], gap[i] = Kp[:, :, j], ob[j], ln[j], gp[j]
     res.update(K_all=K_all, K=K_all[:, :, 0], objective=obj, l1norm=l1, qp_gap=gap)
+    return res
+
+
+def column_bounds(P, rank, world):
+    """Contiguous block [lo, hi) of the P columns of K that `rank` solves in a column-split lasso sweep."""
+    return shard_bounds(P, rank, world)
+
+
+def make_allreduce(device, group=None):
+    """The reduction hook of kf_set_qp_partition on top of torch.distributed: values (a small float64 numpy view)
+    are reduced in place over the ranks; op 0 = sum, 1 = max.  NCCL needs device tensors, gloo takes host ones."""
+    import torch
+    import torch.distributed as dist
+    on_gpu = dist.get_backend(group) == "nccl"
+
+    buf = torch.zeros(64, dtype=torch.float64, device=device if on_gpu else "cpu")     # reused: the hook runs a few times per step
+
+    def hook(values, op):
+        n = values.size
+        tns = buf[:n] if n <= buf.numel() else torch.zeros(n, dtype=torch.float64, device=buf.device)
+        tns.copy_(torch.from_numpy(values))
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM, group=group)
+        values[:] = tns.cpu().numpy()
+    return hook
+
+
+def _solve_column_split(fitter, P, budgets, rank, world, device, group, **solve_kw):
+    """Lasso sweep split across the GPUs by COLUMNS of K (exact active-set solver): every rank holds the same
+    (G, C) after the all-reduce, factors only its own columns for all budgets and exchanges a few scalars per step;
+    the column blocks of K are gathered at the end."""
+    import torch
+    import torch.distributed as dist
+    lo, hi = column_bounds(P, rank, world)
+    fitter.set_option("qp_method", 2)
+    fitter.set_qp_partition(lo, hi, make_allreduce(device, group))
+    try:
+        res = fitter.solve_dev(P, least_squares=False, t=budgets, **solve_kw)
+    finally:
+        fitter.set_qp_partition(0, 0)
+        fitter.set_option("qp_method", 0)
+    nt = budgets.size
+    wmax = max(column_bounds(P, r, world)[1] - column_bounds(P, r, world)[0] for r in range(world))
+    mine = np.zeros((nt, wmax, P))                       # [budget][column][row]: contiguous column blocks
+    mine[:, :hi - lo, :] = np.transpose(res["K_all"][:, lo:hi, :], (2, 1, 0))
+    on_gpu = dist.get_backend(group) == "nccl"
+    src = torch.from_numpy(mine).to(device) if on_gpu else torch.from_numpy(mine)
+    parts = [torch.empty_like(src) for _ in range(world)]
+    dist.all_gather(parts, src, group=group)
+    K_all = np.zeros((P, P, nt), order="F")
+    for r, part in enumerate(parts):
+        a, b = column_bounds(P, r, world)
+        K_all[:, a:b, :] = np.transpose(part.cpu().numpy()[:, :b - a, :], (2, 1, 0))
+    res.update(K_all=K_all, K=K_all[:, :, 0])
     return res

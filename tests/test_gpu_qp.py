@@ -290,3 +290,60 @@ def test_config3a_snake_fourier_lasso_budgets_certified(fitter, snake_data):
         assert res["qp_gap"][i] <= 1e-8 * abs(f)
         fs.append(f)
     assert all(b < a for a, b in zip(fs, fs[1:]))        # a larger budget can only lower the objective
+
+
+def test_active_set_column_partition_two_ranks_on_one_gpu(fitter):
+    """kf_set_qp_partition: two contexts on the same GPU act as two ranks (threads; the all-reduce hook is a barrier
+    exchange).  Each solves half of the columns of K for all budgets; the gathered K, the objective and the certified
+    gap equal the unpartitioned solve."""
+    import threading
+    n, m = 5, 1
+    alpha, beta, u = synth(8000, n, m, seed=9)
+    basis = koopfit.Basis(["poly"], [4], n)
+    fitter.set_option("qp_method", 2)
+    try:
+        ls = fitter.fit(basis, "bilinear", alpha, beta, u, ls_method="gram")
+        ts = np.array([0.01, 0.1, 0.5]) * np.abs(ls["K"]).sum()
+        whole = fitter.fit(basis, "bilinear", alpha, beta, u, least_squares=False, t=ts, psd_shift="never")
+    finally:
+        fitter.set_option("qp_method", 0)
+    P, world = 252, 2
+    bar = threading.Barrier(world)
+    slots = [None] * world
+    results = [None] * world
+
+    def make_hook(rank):
+        def hook(values, op):
+            slots[rank] = values.copy()
+            bar.wait(timeout=120)
+            red = np.max(slots, axis=0) if op == 1 else np.sum(slots, axis=0)
+            bar.wait(timeout=120)
+            values[:] = red
+        return hook
+
+    def run(rank):
+        f = koopfit.Fitter(device=0)
+        try:
+            lo, hi = rank * P // world, (rank + 1) * P // world
+            f.set_option("qp_method", 2)
+            f.set_qp_partition(lo, hi, make_hook(rank))
+            results[rank] = (lo, hi, f.fit(basis, "bilinear", alpha, beta, u, least_squares=False, t=ts, psd_shift="never"))
+        finally:
+            f.close()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join(timeout=300)
+    assert all(r is not None for r in results)
+    K = np.zeros_like(whole["K_all"])
+    for lo, hi, r in results:
+        assert np.count_nonzero(r["K_all"][:, :lo, :]) == 0 and np.count_nonzero(r["K_all"][:, hi:, :]) == 0
+        K[:, lo:hi, :] = r["K_all"][:, lo:hi, :]
+        assert np.allclose(r["objective"], whole["objective"], rtol=1e-12, atol=0)
+        assert np.all(r["qp_gap"] <= 1e-9 * np.abs(whole["objective"]))
+        assert r["info"]["qp_capped"] == 0
+    for i, t in enumerate(ts):
+        assert relF(K[:, :, i], whole["K_all"][:, :, i]) < 1e-9
+        assert np.abs(K[:, :, i]).sum() <= t * (1 + 1e-12)

@@ -79,3 +79,38 @@ def test_two_rank_allreduce_equals_single_pass():
         assert np.linalg.norm(Gs - G) <= 1e-13 * np.linalg.norm(G)
         assert np.linalg.norm(Cs - C) <= 1e-13 * np.linalg.norm(C)
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][3], out[1][3])   # ranks agree bit for bit
+
+
+def _hook_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from koopfit.sharding import make_allreduce
+    hook = make_allreduce(torch.device("cpu"))
+    v = np.array([1.0 + rank, 10.0 * (rank + 1), -3.0])
+    hook(v, 0)                                          # sum over ranks, in place
+    w = np.array([float(rank), -float(rank)])
+    hook(w, 1)                                          # max over ranks
+    q.put((rank, v, w))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_qp_partition_hook_and_column_bounds():
+    """The reduction hook the column-split lasso sweep hands to kf_set_qp_partition (sum / max, in place) on a
+    world_size-2 gloo group, and the column blocks covering K."""
+    from koopfit.sharding import column_bounds
+    spans = [column_bounds(1464, r, 8) for r in range(8)]
+    assert spans[0][0] == 0 and spans[-1][1] == 1464 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hook_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, v, w in out:
+        assert np.array_equal(v, [3.0, 30.0, -6.0]) and np.array_equal(w, [1.0, 0.0])
