@@ -166,10 +166,12 @@ long long kf_series_pairs(long long T, int nd, const double* t);
 int kf_fit_series(kf_ctx* ctx, const kf_basis* basis, const kf_series* series, const kf_solve* solve, kf_scale* scale, kf_result* out);
 
 /* Many independent fits in one call (evaluate_rand_models.m:45-144 fits 23 small models per random system).
- * Least-squares problems with P <= 32 and no dim_red run CONCURRENTLY, one CTA per problem, entirely on chip
- * (tile-wise Householder TSQR of [Px | Py] + pivoted QR of the small triangular factor: mldivide semantics);
- * every other problem is solved by kf_fit one after the other.  bases[i], probs[i], solves[i], outs[i] describe
- * problem i (HOST pointers, as in kf_fit); problems that share the same alpha pointer share one upload. */
+ * Problems with P <= 32 and no dim_red run CONCURRENTLY, one CTA per problem, entirely on chip (tile-wise Householder
+ * TSQR of [Px | Py] + pivoted QR of the small triangular factor: mldivide semantics): all least-squares fits, and the QP
+ * fits (no pinned columns, psd_shift != ALWAYS) whose LS solution has full rank and lies inside every budget — it is then
+ * the minimiser of solve_KoopmanQP too (the script's nonlinear models use lasso = 4, usually inactive); objective, l1norm
+ * and qp_gap are filled.  Every other problem is solved by kf_fit one after the other.  bases[i], probs[i], solves[i],
+ * outs[i] describe problem i (HOST pointers, as in kf_fit); problems that share the same alpha pointer share one upload. */
 int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, const kf_solve* solves, kf_result* outs);
 
 /* Generic MATLAB `A \ B` for a tall A (M x P) and B (M x Pc), HOST column-major buffers:

@@ -837,7 +837,11 @@ int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_
         int N = 0, P = 0;
         if (!bases[i]) { ctx->err = "kf_fit_batch: NULL basis"; return KF_EINVAL; }
         KF_TRY(kf_basis_dims(bases[i], probs[i].model, probs[i].m, nullptr, &N, &P));
-        const bool ok = solves[i].least_squares && P <= 32 && probs[i].pc_cols == 0 && bases[i]->n_pcs == 0 && probs[i].M > 0 && probs[i].alpha &&
+        // least-squares fits, and QP fits without pinned columns / forced shift: if the LS solution turns out to lie inside
+        // every budget (evaluate_rand_models.m fits its nonlinear models with lasso = 4, usually inactive) it is the QP answer too
+        const bool solve_ok = solves[i].least_squares ||
+                              (solves[i].nt >= 1 && solves[i].t && !solves[i].delay_constraint && solves[i].psd_shift != KF_PSD_ALWAYS);
+        const bool ok = solve_ok && P <= 32 && probs[i].pc_cols == 0 && bases[i]->n_pcs == 0 && probs[i].M > 0 && probs[i].alpha &&
                         probs[i].beta && (probs[i].m == 0 || probs[i].u) && !outs[i].G && !outs[i].C && !outs[i].Px && !outs[i].Py &&
                         (probs[i].model == KF_LINEAR || probs[i].model == KF_BILINEAR || probs[i].model == KF_NONLINEAR) &&
                         bases[i]->nv == probs[i].nzeta + (probs[i].model == KF_NONLINEAR ? probs[i].m : 0);
@@ -845,9 +849,12 @@ int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_
     }
     // concurrent part, in groups that bound the staging memory
     const size_t group = 2048;
+    std::vector<int> accepted(group);
     for (size_t g0 = 0; g0 < small.size(); g0 += group) {
         const int n = (int)std::min(group, small.size() - g0);
-        KF_TRY(kf_fit_batch_small(ctx, nprob, bases, probs, outs, small.data() + g0, n));
+        KF_TRY(kf_fit_batch_small(ctx, nprob, bases, probs, solves, outs, small.data() + g0, n, accepted.data()));
+        for (int w = 0; w < n; ++w)
+            if (!accepted[w]) rest.push_back(small[g0 + w]);
     }
     for (int i : rest) KF_TRY(kf_fit(ctx, bases[i], &probs[i], &solves[i], &outs[i]));
     return KF_OK;

@@ -38,6 +38,11 @@ struct KfBatchOut {
     int rank;
     int perm[BT_PMAX];
     double r11, minpiv;
+    // of the returned K (for the QP branch with an inactive budget, where K is also the QP minimiser):
+    double proj2;      // ||Q1'Py||_F^2 = tr(C'K): objective 0.5 tr(K'GK) - tr(C'K) = -0.5 proj2
+    double l1;         // ||vec K||_1
+    double ginner;     // <G K - C, K>   (rounding level)
+    double gmax;       // ||G K - C||_inf
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -230,10 +235,43 @@ kf_batch_ls_kernel(const KfBatchDesc* __restrict__ descs, const KfOp* __restrict
             }
             for (int i = 0; i < rank; ++i) Kout[(long long)c * P + perm[i]] = xs[i];
         }
+        // objective pieces and the gradient G K - C = R11'(R11 K - Q1'Py) of column `lane` (pivoted order)
+        double proj2 = 0.0, l1 = 0.0, ginner = 0.0, gmax = 0.0;
+        if (lane < P) {
+            const int c = lane;
+            double xs[BT_PMAX], es[BT_PMAX];
+            for (int i = rank - 1; i >= 0; --i) {       // the same recurrence as above (bit-identical xs)
+                double acc = R[i * BT_LD + P + c];
+                for (int k = i + 1; k < rank; ++k) acc = fma(-R[i * BT_LD + k], xs[k], acc);
+                xs[i] = acc / R[i * BT_LD + i];
+            }
+            for (int i = 0; i < rank; ++i) {
+                const double rhs = R[i * BT_LD + P + c];
+                double acc = -rhs;
+                for (int k = i; k < rank; ++k) acc = fma(R[i * BT_LD + k], xs[k], acc);
+                es[i] = acc;
+                proj2 = fma(rhs, rhs, proj2);
+                l1 += fabs(xs[i]);
+            }
+            for (int k = 0; k < rank; ++k) {
+                double g = 0.0;
+                for (int i = 0; i <= k; ++i) g = fma(R[i * BT_LD + k], es[i], g);
+                ginner = fma(g, xs[k], ginner);
+                gmax = fmax(gmax, fabs(g));
+            }
+        }
+        proj2 = warp_sum(proj2);
+        l1 = warp_sum(l1);
+        ginner = warp_sum(ginner);
+        for (int off = 16; off > 0; off >>= 1) gmax = fmax(gmax, __shfl_down_sync(0xffffffffu, gmax, off));
         if (lane == 0) {
             out->rank = rank;
             out->r11 = r11;
             out->minpiv = minpiv;
+            out->proj2 = proj2;
+            out->l1 = l1;
+            out->ginner = ginner;
+            out->gmax = gmax;
         }
         if (lane < BT_PMAX) out->perm[lane] = lane < P ? perm[lane] : -1;
     }
@@ -242,8 +280,11 @@ kf_batch_ls_kernel(const KfBatchDesc* __restrict__ descs, const KfOp* __restrict
 }  // namespace
 
 // nprob independent LS fits; problems with P > 32 (or non-LS solves) are not handled here (caller falls back to kf_fit)
-int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, kf_result* outs,
-                       const int* which, int nwhich) {
+// (solves[ip].least_squares == 0: the QP branch — accepted[w] = 1 only if the LS solution has full rank and lies inside every
+// budget, in which case it is the QP minimiser too (Ksysid.m:1135-1137 inactive, no 1e-6 I shift); otherwise the caller
+// sends the problem down the general path)
+int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, const kf_solve* solves, kf_result* outs,
+                       const int* which, int nwhich, int* accepted) {
     cudaStream_t st = ctx->stream;
     std::vector<KfBatchDesc> descs;
     std::vector<KfOp> ops;
@@ -318,8 +359,24 @@ int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, con
         const int ip = which[w];
         const KfBatchDesc& d = descs[w];
         kf_result& o = outs[ip];
+        const kf_solve& sv = solves[ip];
+        accepted[w] = 1;
+        if (!sv.least_squares) {
+            double tmin = sv.nt > 0 ? sv.t[0] : 0.0;
+            for (int q = 1; q < sv.nt; ++q) tmin = std::min(tmin, sv.t[q]);
+            if (oh[w].rank < d.P || !(oh[w].l1 <= tmin)) { accepted[w] = 0; continue; }
+        }
         std::memset(&o.info, 0, sizeof(o.info));
-        if (o.K) std::memcpy(o.K, Kh.data() + d.out_off, (size_t)d.P * d.P * sizeof(double));
+        const int nt = sv.least_squares ? 1 : std::max(sv.nt, 1);
+        for (int q = 0; q < nt; ++q) {
+            if (o.K) std::memcpy(o.K + (size_t)q * d.P * d.P, Kh.data() + d.out_off, (size_t)d.P * d.P * sizeof(double));
+            if (!sv.least_squares) {
+                if (o.objective) o.objective[q] = -0.5 * oh[w].proj2;
+                if (o.l1norm) o.l1norm[q] = oh[w].l1;
+                if (o.qp_iters) o.qp_iters[q] = 0;
+                if (o.qp_gap) o.qp_gap[q] = std::max(0.0, oh[w].ginner + sv.t[q] * oh[w].gmax);
+            }
+        }
         if (o.perm) std::memcpy(o.perm, oh[w].perm, sizeof(int) * d.P);
         o.info.rank = oh[w].rank;
         o.info.ls_method_used = KF_LS_QR;

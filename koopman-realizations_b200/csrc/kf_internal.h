@@ -207,8 +207,8 @@ int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long lon
                    int* d_perm, int* rank_out, double* min_piv, double* max_piv, cudaStream_t st);
 
 // batch.cu
-int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, kf_result* outs,
-                       const int* which, int nwhich);
+int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, const kf_solve* solves, kf_result* outs,
+                       const int* which, int nwhich, int* accepted);
 
 // preprocess.cu: get_scale / get_zeta / get_snapshotPairs on the device
 int kf_pp_scale(kf_ctx* ctx, const double* d_y, const double* d_u, long long T, int n, int m, double* d_scale, cudaStream_t st);

@@ -191,8 +191,9 @@ class Fitter:
 
     def fit_batch(self, problems):
         """Many independent fits in one call (kf_fit_batch).  `problems`: list of dicts with keys basis, model_type,
-        alpha, beta, u and optional solve keywords (as Fitter.fit).  Small least-squares problems (P <= 32) run
-        concurrently on the GPU, one CTA each; the rest are solved one after the other.  Returns a list of dicts
+        alpha, beta, u and optional solve keywords (as Fitter.fit).  Small problems (P <= 32) run concurrently on the GPU, one
+        CTA each: least-squares fits, and QP fits whose LS solution lies inside every budget (then it is the QP minimiser);
+        the rest are solved one after the other.  Returns a list of dicts
         (K, rank, perm, info [, objective, l1norm])."""
         n = len(problems)
         bases = (C.POINTER(A.kf_basis) * n)()
@@ -220,12 +221,13 @@ class Fitter:
             nt = max(1, sv.nt) if not sv.least_squares else 1
             K = np.zeros((P, P, nt), order="F")
             perm = np.zeros(P, dtype=np.int32)
-            obj, l1 = np.zeros(nt), np.zeros(nt)
+            obj, l1, gap = np.zeros(nt), np.zeros(nt), np.zeros(nt)
             iters = np.zeros(nt, dtype=np.int32)
             outs[i].K, outs[i].perm = A.dptr(K), perm.ctypes.data_as(A.c_int_p)
             outs[i].objective, outs[i].l1norm, outs[i].qp_iters = A.dptr(obj), A.dptr(l1), iters.ctypes.data_as(A.c_int_p)
+            outs[i].qp_gap = A.dptr(gap)
             keep.append((alpha, beta, u, keep_t, sv))
-            results.append(dict(K_all=K, perm=perm, objective=obj, l1norm=l1, qp_iters=iters, N=N, P=P, nt=nt))
+            results.append(dict(K_all=K, perm=perm, objective=obj, l1norm=l1, qp_iters=iters, qp_gap=gap, N=N, P=P, nt=nt))
         self._check(self.lib.kf_fit_batch(self.ctx, n, bases, probs, solves, outs), "kf_fit_batch")
         for i, r in enumerate(results):
             info = {f: getattr(outs[i].info, f) for f, _ in A.kf_info._fields_}

@@ -151,7 +151,8 @@ def test_config4_rand_system_fits(fitter, rsys_data):
 def test_config4_batched_fits_match_sequential_and_oracle(fitter, rsys_data):
     """kf_fit_batch on the evaluate_rand_models.m fit list (linear deg 1-13, bilinear 1-6 by least squares; nonlinear
     1-4 with lasso = 4) for the shipped subset of random systems: the concurrent one-CTA-per-problem path must give
-    mldivide's solution (oracle) for every fit, and the QP ones fall through to the general path."""
+    mldivide's solution (oracle) for every fit; the QP fits whose budget is inactive are answered by the same concurrent
+    kernel (LS solution inside the ball = QP minimiser), the others fall through to the general path."""
     problems, refs = [], []
     for d in rsys_data:
         base = O.KsysidOracle(d, model_type="linear", obs_type=["poly"], obs_degree=[1])
@@ -167,6 +168,7 @@ def test_config4_batched_fits_match_sequential_and_oracle(fitter, rsys_data):
                 refs.append((model, deg, prog, lasso))
     res = fitter.fit_batch(problems)
     assert len(res) == len(problems) == 23 * len(rsys_data)
+    batched_qp = 0
     for pb, r, (model, deg, prog, lasso) in zip(problems, res, refs):
         Px, Py = O.build_regressors(model, prog, pb["alpha"], pb["beta"], pb["u"])
         if lasso is None:
@@ -180,6 +182,10 @@ def test_config4_batched_fits_match_sequential_and_oracle(fitter, rsys_data):
             Ko, _ = O.solve_l1ball_qp(G, C, lasso * prog.N)
             fo, fg = O.qp_objective(G, C, Ko), O.qp_objective(G, C, r["K"])
             assert abs(fg - fo) <= 1e-8 * abs(fo), (model, deg)
+            assert abs(r["objective"][0] - fg) <= 1e-8 * abs(fg) and abs(r["l1norm"][0] - np.abs(r["K"]).sum()) <= 1e-9 * np.abs(r["K"]).sum()
+            assert r["qp_gap"][0] <= 1e-8 * abs(fo)
+            batched_qp += int(r["info"]["ls_method_used"] == 2 and r["qp_iters"][0] == 0)
+    assert batched_qp >= 1          # at least some of the lasso = 4 fits were answered by the concurrent kernel
 
 
 # ------------------------------------------------------------------ exact active-set solver (qp_as.cu)
