@@ -219,6 +219,12 @@ int kf_set_qp_partition(kf_ctx* ctx, int col_lo, int col_hi, kf_allreduce_fn all
  *   summed across ranks (ncclAllReduce(sum, double) by the caller, e.g. torch.distributed).
  * kf_solve_dev: solve from the (reduced) accumulator; outputs to HOST pointers in `out`. */
 int kf_accumulate_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, int reset);
+/* Lift-only mode on DEVICE buffers (asynchronous on the context stream): the materialised regressors [Px | Py]
+ * (Ksysid.m:1019-1065; M x 2P column-major, leading dimension ld >= M) of the device snapshot pairs in `prob`, and
+ * lift.econ_full of `rows` device points (V rows x nv -> Psi rows x N).  HBM-bound: 8 (2 nzeta + m) B read and
+ * 16 P B written per pair. */
+int kf_regressors_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, double* dev_PxPy, long long ld);
+int kf_lift_dev(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* dev_V, double* dev_Psi);
 int kf_accum_buffer(kf_ctx* ctx, double** dev_ptr, size_t* count);
 int kf_solve_dev(kf_ctx* ctx, const kf_solve* solve, kf_result* out);
 int kf_sync(kf_ctx* ctx);                            /* cudaStreamSynchronize(context stream) */

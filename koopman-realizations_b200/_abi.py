@@ -173,6 +173,8 @@ def load():
         "kf_set_qp_partition": (i, [vp, i, i, ALLREDUCE_FN, vp]),
         "kf_mldivide": (i, [vp, ll, i, i, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]),
         "kf_accumulate_dev": (i, [vp, P(kf_basis), P(kf_problem), i]),
+        "kf_regressors_dev": (i, [vp, P(kf_basis), P(kf_problem), vp, ll]),
+        "kf_lift_dev": (i, [vp, P(kf_basis), ll, vp, vp]),
         "kf_accum_buffer": (i, [vp, P(vp), P(C.c_size_t)]),
         "kf_solve_dev": (i, [vp, P(kf_solve), P(kf_result)]),
         "kf_sync": (i, [vp]),
@@ -189,5 +191,5 @@ def load():
 
 
 EXPORTS = ["kf_create", "kf_destroy", "kf_last_error", "kf_version", "kf_basis_dims", "kf_block_table",
-           "kf_lift", "kf_fit", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_set_qp_partition", "kf_mldivide", "kf_accumulate_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
+           "kf_lift", "kf_fit", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_set_qp_partition", "kf_mldivide", "kf_accumulate_dev", "kf_regressors_dev", "kf_lift_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
            "kf_stream", "kf_counters", "kf_last_times", "kf_set_option"]

@@ -701,6 +701,35 @@ int kf_accumulate_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob
     return accumulate_dev(ctx, prob, reset != 0 || !ctx->lay.valid);
 }
 
+int kf_regressors_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, double* dev_PxPy, long long ld) {
+    if (!ctx || !prob || !dev_PxPy) return KF_EINVAL;
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    KF_TRY(prepare_program(ctx, basis));
+    ctx->lay.valid = false;
+    KF_TRY(check_problem(ctx, prob));
+    if (ld < prob->M) { ctx->err = "kf_regressors_dev: ld < M"; return KF_EINVAL; }
+    KfLiftArgs a{};
+    a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
+    a.order = ctx->d_order.as<int>();
+    a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->prog.N();
+    a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
+    a.alpha = prob->alpha; a.beta = prob->beta; a.u = prob->u; a.M = prob->M;
+    if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * prob->M * sizeof(double)));
+    a.full = ctx->d_full.as<double>();
+    return kf_launch_regressors(ctx, a, dev_PxPy, nullptr, ld, ctx->stream);
+}
+
+int kf_lift_dev(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* dev_V, double* dev_Psi) {
+    if (!ctx || rows < 0 || (rows && (!dev_V || !dev_Psi))) return KF_EINVAL;
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    KF_TRY(prepare_program(ctx, basis));
+    ctx->lay.valid = false;
+    const KfProgram& p = ctx->prog;
+    if (p.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)p.n_full() * rows * sizeof(double)));
+    return kf_launch_lift_points(ctx, ctx->d_ops.as<KfOp>(), ctx->d_centres.as<double>(), ctx->d_pcs.as<double>(), p.nv, p.n_full(),
+                                 p.n_pcs, dev_V, rows, ctx->d_full.as<double>(), dev_Psi, rows, ctx->stream);
+}
+
 int kf_accum_buffer(kf_ctx* ctx, double** dev_ptr, size_t* count) {
     if (!ctx || !ctx->lay.valid) return KF_EINVAL;
     KF_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -949,6 +978,7 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "qp_method") ctx->opt_qp_method = (int)value;
     else if (n == "as_ws_gb") ctx->opt_as_ws_gb = value;
     else if (n == "as_frac") ctx->opt_as_frac = value;
+    else if (n == "lift_tile") ctx->opt_lift_tile = (int)value;
     else {
         ctx->err = "kf_set_option: unknown option " + n;
         return KF_EINVAL;

@@ -127,6 +127,7 @@ struct kf_ctx {
     int opt_qp_method = 0;    // L1-ball QP: 0 auto (coordinate descent for P <= 256, exact active set above), 1 CD, 2 active set
     double opt_as_frac = 0.05; // active-set solver: bound on the pattern change per step, as a fraction of the support size
     double opt_as_ws_gb = 8;  // active-set solver: bound on the per-column Cholesky workspace (columns run in chunks that fit)
+    int opt_lift_tile = 1;    // materialising lift: whole program per 16-snapshot tile in shared memory (0: level-by-level kernel)
     int opt_tma = 1;          // Gram kernel operand path: 1 = tensor-map TMA + mbarrier ring, 0 = per-thread cp.async
 
     // column partition of the active-set QP solver across ranks (kf_set_qp_partition)

@@ -14,6 +14,8 @@
 // LIFT_FS features of that level, so a chunk of 1.5k snapshots x 1k features exposes
 // ~4e5 threads instead of 3e3.  A product reads its two factors back from the panel
 // (written by an earlier level, L2 hits).
+#include <algorithm>
+
 #include "kf_internal.h"
 #include "lift_eval.h"
 
@@ -113,6 +115,197 @@ __global__ void kf_regressor_post_kernel(int model, int N, int P, int m, const d
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Materialising lift (lift-only mode: kf_lift / kf_lift_dev, koopData.Px / Py, the QRCP route).  HBM-bound by
+// construction — 8 (2 nzeta + m) B read and 16 P B written per pair — so every byte must move once:
+// a CTA evaluates the WHOLE feature program for a tile of LT_S snapshots with all features in shared memory
+// (products read their factors from shared memory, not back from HBM as the level kernel would for an
+// HBM-resident output), then streams the rows of [Px | Py] (or Psi) out once, 128-byte segments per feature;
+// the bilinear blocks u_k psi and the dim_red projection are formed from shared memory too.
+constexpr int LT_THREADS = 256;
+constexpr int LT_MAXLEV = 32;
+
+struct KfLiftTileArgs {
+    const KfOp* ops; const double* centres; const double* pcs; const int* order;
+    int level_start[LT_MAXLEV + 1]; int nlevels;
+    int nv, n_full, n_pcs, N;          // N = lifted dimension (n_full, or nv + n_pcs + 1 with dim_red)
+    int nzeta, m, model;
+    int mode;                           // 0: points V -> Psi (rows x N);  1: regressors [Px | Py] (M x 2P)
+    int P;
+    const double* alpha; const double* beta; const double* u; long long M;
+    double* out; long long ld;
+};
+
+struct LtOp { int kind, a, b, j; double c; };   // one op of the level-ordered program, staged in shared memory
+
+__device__ __forceinline__ void lt_ld4(const double* p, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void lt_st4(double* p, const double (&v)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+
+// LS = snapshots per tile (8 or 16: 64- or 128-byte segments per output row), chosen by the host so that several CTAs fit
+// an SM and the load / evaluate / store phases of different tiles overlap.  Work split: evaluation — a thread takes one op
+// (read from the shared-memory copy of the level-ordered program) and applies it to 4 snapshots with 128-bit shared-memory
+// accesses, so the interpretive overhead is paid once per 4 elements; store — 2 snapshots (one 128-bit store) per thread.
+template <int LS>
+__global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTileArgs a) {
+    extern __shared__ __align__(16) double lt_smem[];
+    double* sh = lt_smem;                              // [n_full][LS]
+    double* su = sh + (size_t)a.n_full * LS;           // [m][LS]   inputs u of the tile
+    double* se = su + (size_t)a.m * LS;                // [N][LS]   econ features (dim_red only)
+    LtOp* sop = reinterpret_cast<LtOp*>(se + (a.n_pcs > 0 ? (size_t)a.N * LS : 0));   // [n_full] in level order
+    const int tid = threadIdx.x;
+    const int side = blockIdx.y;
+    const double* src = side ? a.beta : a.alpha;
+    const long long ntiles = (a.M + LS - 1) / LS;
+    const bool vec2 = ((a.ld & 1) == 0) && ((reinterpret_cast<unsigned long long>(a.out) & 15ull) == 0);
+    for (int e = tid; e < a.n_full; e += LT_THREADS) {
+        const int j = a.order[e];
+        const KfOp op = a.ops[j];
+        sop[e] = LtOp{op.kind, op.a, op.b, j, op.c};
+    }
+    __syncthreads();
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long g0 = tile * LS;
+        // ---- A: the variables v (features 0 .. nv-1) and u of the tile; the tail of the last tile is zero
+        for (int idx = tid; idx < (a.nv + a.m) * LS; idx += LT_THREADS) {
+            const int k = idx / LS, s = idx & (LS - 1);
+            const long long gs = g0 + s;
+            double v = 0.0;
+            if (gs < a.M) {
+                if (k < a.nv) v = k < a.nzeta ? src[(long long)k * a.M + gs] : a.u[(long long)(k - a.nzeta) * a.M + gs];
+                else v = a.u[(long long)(k - a.nv) * a.M + gs];
+            }
+            if (k < a.nv) sh[k * LS + s] = v; else su[(k - a.nv) * LS + s] = v;
+        }
+        __syncthreads();
+        // ---- B: the program, level by level
+        {
+            constexpr int QS = LS / 4;                 // snapshot quads per tile
+            constexpr int NF = LT_THREADS / QS;
+            const int s0 = (tid % QS) * 4, fs = tid / QS;
+            for (int l = 0; l < a.nlevels; ++l) {
+                const int first = a.level_start[l], last = a.level_start[l + 1];
+                for (int e = first + fs; e < last; e += NF) {
+                    const LtOp op = sop[e];
+                    double v[4];
+                    if (op.kind == KF_OP_MUL) {
+                        double x[4], y[4];
+                        lt_ld4(sh + op.a * LS + s0, x);
+                        lt_ld4(sh + op.b * LS + s0, y);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) v[t] = KF_MUL(x[t], y[t]);
+                    } else if (op.kind == KF_OP_VAR) {
+                        if (op.a == op.j) continue;              // loaded in A
+                        lt_ld4(sh + op.a * LS + s0, v);
+                    } else {
+                        KfOp o{};
+                        o.kind = op.kind; o.a = op.a; o.b = op.b; o.c = op.c;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const double* col = sh + s0 + t;
+                            v[t] = kf_eval_op(o, a.nv, a.centres, [&](int k) -> double { return col[k * LS]; });
+                        }
+                    }
+                    lt_st4(sh + op.j * LS + s0, v);
+                }
+                __syncthreads();
+            }
+        }
+        const double* psi = sh;
+        if (a.n_pcs > 0) {      // econ lift [v; pcs' psi_full; 1]  (Ksysid.m:1614-1618)
+            const int s = tid & (LS - 1), fs = tid / LS;
+            constexpr int NF = LT_THREADS / LS;
+            const bool valid = g0 + s < a.M;
+            for (int c = fs; c < a.n_pcs; c += NF) {
+                const double* pc = a.pcs + (size_t)c * a.n_full;
+                double acc = 0.0;
+                for (int j = 0; j < a.n_full; ++j) acc = fma(pc[j], sh[j * LS + s], acc);
+                se[(a.nv + c) * LS + s] = valid ? acc : 0.0;
+            }
+            for (int i = fs; i < a.nv; i += NF) se[i * LS + s] = sh[i * LS + s];
+            if (fs == 0) se[(a.nv + a.n_pcs) * LS + s] = valid ? 1.0 : 0.0;
+            __syncthreads();
+            psi = se;
+        }
+        // ---- C: stream the rows out, once
+        {
+            constexpr int PS = LS / 2;                 // snapshot pairs per tile
+            constexpr int NR = LT_THREADS / PS;
+            const int p2 = (tid % PS) * 2, rr = tid / PS;
+            const long long gs = g0 + p2;
+            const bool ok0 = gs < a.M, ok1 = gs + 1 < a.M;
+            auto put = [&](double* dst, double v0, double v1) {
+                if (ok1 && vec2) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                else {
+                    if (ok0) dst[0] = v0;
+                    if (ok1) dst[1] = v1;
+                }
+            };
+            if (ok0) {
+                double* base = a.out + (a.mode == 0 ? 0 : (long long)(side ? a.P : 0) * a.ld) + gs;
+                for (int j = rr; j < a.N; j += NR) {
+                    const double2 v = *reinterpret_cast<const double2*>(psi + j * LS + p2);
+                    put(base + (long long)j * a.ld, v.x, v.y);
+                }
+                if (a.mode == 1 && a.model == KF_LINEAR) {              // [psi, u]  (Ksysid.m:1062-1063)
+                    for (int i = rr; i < a.m; i += NR) put(base + (long long)(a.N + i) * a.ld, su[i * LS + p2], su[i * LS + p2 + 1]);
+                } else if (a.mode == 1 && a.model == KF_BILINEAR) {     // blocks u_k psi  (Ksysid.m:510-511)
+                    for (int k = 0; k < a.m; ++k) {
+                        const double u0 = su[k * LS + p2], u1 = su[k * LS + p2 + 1];
+                        double* bk = base + (long long)(k + 1) * a.N * a.ld;
+                        for (int j = rr; j < a.N; j += NR) {
+                            const double2 v = *reinterpret_cast<const double2*>(psi + j * LS + p2);
+                            put(bk + (long long)j * a.ld, KF_MUL(u0, v.x), KF_MUL(u1, v.y));
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// launches the tile kernel if the program fits (levels, shared memory); returns false otherwise
+template <int LS>
+bool lift_tile_launch_ls(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, size_t smem, cudaStream_t st, int* rc) {
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(kf_lift_tile_kernel<LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        smem_set = smem;
+    }
+    const long long ntiles = (a.M + LS - 1) / LS;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem + 1024, 1)));
+    const unsigned gx = (unsigned)std::min<long long>(ntiles, (long long)ctx->sm_count * per_sm);
+    kf_lift_tile_kernel<LS><<<dim3(gx, nsides), LT_THREADS, smem, st>>>(a);
+    if (cudaGetLastError() != cudaSuccess) { *rc = KF_ECUDA; ctx->err = "kf_lift_tile_kernel launch failed"; }
+    ctx->launches += 1;
+    return true;
+}
+
+bool lift_tile_launch(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, cudaStream_t st, int* rc) {
+    *rc = KF_OK;
+    const int nlev = (int)ctx->level_start.size() - 1;
+    if (nlev > LT_MAXLEV || a.M <= 0) return false;
+    for (int l = 0; l <= nlev; ++l) a.level_start[l] = ctx->level_start[l];
+    a.nlevels = nlev;
+    auto bytes = [&](int ls) {
+        return ((size_t)a.n_full + (size_t)a.m + (a.n_pcs > 0 ? (size_t)a.N : 0)) * ls * sizeof(double) + (size_t)a.n_full * sizeof(LtOp);
+    };
+    // 16 snapshots per tile (128-byte segments) while at least three CTAs fit an SM, else 8
+    if (bytes(16) <= 72 * 1024) return lift_tile_launch_ls<16>(ctx, a, nsides, bytes(16), st, rc);
+    if (bytes(8) <= 200 * 1024) return lift_tile_launch_ls<8>(ctx, a, nsides, bytes(8), st, rc);
+    return false;
+}
+
 }  // namespace
 
 // Dependency levels of the program: level 0 = variables and primitives (functions of v only),
@@ -162,6 +355,15 @@ int kf_launch_lift_points(kf_ctx* ctx, const KfOp* ops, const double* centres, c
                           int n_pcs, const double* V, long long rows, double* full, double* out, long long ldo,
                           cudaStream_t st) {
     if (rows <= 0) return KF_OK;
+    if (ctx->opt_lift_tile) {
+        KfLiftTileArgs t{};
+        t.ops = ops; t.centres = centres; t.pcs = pcs; t.order = ctx->d_order.as<int>();
+        t.nv = nv; t.n_full = n_full; t.n_pcs = n_pcs; t.N = n_pcs ? nv + n_pcs + 1 : n_full;
+        t.nzeta = nv; t.m = 0; t.model = KF_NONLINEAR; t.mode = 0; t.P = t.N;
+        t.alpha = V; t.beta = V; t.u = V; t.M = rows; t.out = out; t.ld = ldo;
+        int rc = KF_OK;
+        if (lift_tile_launch(ctx, t, 1, st, &rc)) return rc;
+    }
     KfLiftArgs a{};
     a.ops = ops; a.centres = centres; a.pcs = pcs; a.order = ctx->d_order.as<int>();
     a.nv = nv; a.n_full = n_full; a.n_pcs = n_pcs; a.N = n_pcs ? nv + n_pcs + 1 : n_full;
@@ -183,6 +385,15 @@ int kf_launch_regressors(kf_ctx* ctx, const KfLiftArgs& a0, double* AB, double* 
     // psi(x) -> columns [0,N), psi(y) -> columns [P, P+N) of AB (ld = ldp >= M); whole data set at once
     KfLiftArgs a = a0;
     const int P = kf_regressor_width(a.model, a.N, a.m);
+    if (ctx->opt_lift_tile) {
+        KfLiftTileArgs t{};
+        t.ops = a.ops; t.centres = a.centres; t.pcs = a.pcs; t.order = a.order;
+        t.nv = a.nv; t.n_full = a.n_full; t.n_pcs = a.n_pcs; t.N = a.N;
+        t.nzeta = a.nzeta; t.m = a.m; t.model = a.model; t.mode = 1; t.P = P;
+        t.alpha = a.alpha; t.beta = a.beta; t.u = a.u; t.M = a.M; t.out = AB; t.ld = ldp;
+        int rc = KF_OK;
+        if (lift_tile_launch(ctx, t, 2, st, &rc)) return rc;
+    }
     a.panel = AB;
     a.ld = ldp;
     a.start = 0;

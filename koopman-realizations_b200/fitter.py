@@ -296,6 +296,17 @@ class Fitter:
                           alpha=int(alpha_ptr), beta=int(beta_ptr), u=int(u_ptr), pc_cols=int(pc_cols))
         self._check(self.lib.kf_accumulate_dev(self.ctx, basis.ref(), C.byref(pr), int(reset)), "kf_accumulate_dev")
 
+    def regressors_dev(self, basis, model_type, M, nzeta, m, alpha_ptr, beta_ptr, u_ptr, out_ptr, ld=None):
+        """Lift-only mode on device buffers (kf_regressors_dev): [Px | Py] (M x 2P, column-major, ld >= M) written to
+        out_ptr; asynchronous on the context stream."""
+        pr = A.kf_problem(M=int(M), nzeta=int(nzeta), m=int(m), model=A.MODEL_CODE[model_type],
+                          alpha=int(alpha_ptr), beta=int(beta_ptr), u=int(u_ptr), pc_cols=0)
+        self._check(self.lib.kf_regressors_dev(self.ctx, basis.ref(), C.byref(pr), int(out_ptr), int(ld if ld else M)), "kf_regressors_dev")
+
+    def lift_dev(self, basis, rows, v_ptr, psi_ptr):
+        """lift.econ_full on `rows` device points (kf_lift_dev): V (rows x nv) -> Psi (rows x N), column-major."""
+        self._check(self.lib.kf_lift_dev(self.ctx, basis.ref(), int(rows), int(v_ptr), int(psi_ptr)), "kf_lift_dev")
+
     def accum_buffer(self):
         """(device pointer, count of doubles) of the packed partial-Gram accumulator."""
         p, n = C.c_void_p(), C.c_size_t()

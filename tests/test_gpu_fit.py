@@ -171,6 +171,24 @@ def test_config1_qr_route(fitter, arm_data):
     assert relF(res["K"], k.koopData[0]["K"]) < 1e-10
 
 
+def test_config1_gpu_against_extended_precision_truth(fitter, arm_data):
+    """with no reference output to pin K, the x87 extended-precision basic solution (same basic set) is the
+    ground truth; the GPU's QRCP route must be as close to it as the float64 LAPACK oracle is, the Gram route within
+    cond^2 eps (still inside the 1e-9 tolerance)."""
+    k = O.KsysidOracle(arm_data, model_type="bilinear", obs_type=["poly"], obs_degree=[2]).train_models()
+    koop = k.koopData[0]
+    basic = koop["info"]["perm"][:100]
+    truth = O.basic_solution_extended(koop["Px"], koop["Py"], basic).astype(np.float64)
+    e_oracle = relF(koop["K"], truth)
+    basis = koopfit.Basis(["poly"], [2], 6)
+    qr = fitter.fit(basis, "bilinear", k.pairs["alpha"], k.pairs["beta"], k.pairs["u"], ls_method="qr")
+    gr = fitter.fit(basis, "bilinear", k.pairs["alpha"], k.pairs["beta"], k.pairs["u"], ls_method="gram")
+    assert set(qr["perm"][:100].tolist()) == set(basic.tolist()) == set(gr["perm"][:100].tolist())
+    e_qr, e_gram = relF(qr["K"], truth), relF(gr["K"], truth)
+    assert e_qr < max(20 * e_oracle, 1e-13), (e_qr, e_oracle)
+    assert e_gram < 1e-9, e_gram
+
+
 @pytest.mark.parametrize("model,P,rank", [("linear", 819, 723), ("nonlinear", 1330, 1216)])
 def test_config2_poly3_delay1(fitter, arm_data, model, P, rank):
     """BASELINE config 2: poly 3, delays=1 on the arm data (cond ~2e7, exactly rank-deficient): the QRCP

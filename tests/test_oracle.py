@@ -109,3 +109,18 @@ def test_delay_constraint_pattern():
     c0, c1, tgt = O.delay_constraint_targets(N, n, m, nd)
     assert (c0, c1) == (2, 5) and tgt.shape == (N + m, 3)
     assert tgt[0, 0] == 1 and tgt[1, 1] == 1 and tgt[N, 2] == 1 and tgt.sum() == 3
+
+
+def test_config1_oracle_against_extended_precision_truth(arm_data):
+    """K is 'parity unpinned' (no reference output exists), so the oracle's dgeqp3 solution is checked against
+    the same basic solution computed in x87 extended precision: the float64 oracle is within cond * eps of the truth."""
+    k = O.KsysidOracle(arm_data, model_type="bilinear", obs_type=["poly"], obs_degree=[2]).train_models()
+    koop = k.koopData[0]
+    basic = koop["info"]["perm"][:koop["info"]["rank"]]
+    truth = O.basic_solution_extended(koop["Px"], koop["Py"], basic)
+    err = float(np.linalg.norm((koop["K"] - truth).astype(np.float64)) / np.linalg.norm(truth.astype(np.float64)))
+    assert err < 1e-11, err
+    # the truth satisfies the normal equations on the basic set far better than float64 could
+    Px, Py = koop["Px"].astype(np.longdouble), koop["Py"].astype(np.longdouble)
+    res = Px[:, basic].T @ (Px[:, basic] @ truth[basic] - Py)
+    assert float(np.abs(res).max()) < 1e-12
