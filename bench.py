@@ -347,6 +347,35 @@ def main():
         fast = {"pc_cols": N_LIFT, "value": M * world / (float(tf.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tf.item()), "steps": 1,
                 "note": "kf_problem.pc_cols = N: 616 accumulator tiles instead of 1000 and N right-hand sides; K(:,1:N) identical to the full solve"}
 
+    # ---------------- K1 alone (lift-only mode): HBM-bound, 8 (2 nzeta + m) + 16 P bytes per pair ----------------
+    lift_only = None
+    if world == 1 and rank == 0:
+        try:
+            Ml = min(M, 65536)
+            out_buf = torch.empty((2 * P_REG, Ml), dtype=torch.float64, device=dev)
+            for _ in range(2):
+                fit.regressors_dev(basis, "bilinear", Ml, NZETA, M_IN, alpha.data_ptr(), beta.data_ptr(), u.data_ptr(), out_buf.data_ptr(), ld=Ml)
+            barrier()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record(kstream)
+            for _ in range(5):
+                fit.regressors_dev(basis, "bilinear", Ml, NZETA, M_IN, alpha.data_ptr(), beta.data_ptr(), u.data_ptr(), out_buf.data_ptr(), ld=Ml)
+            l1.record(kstream)
+            barrier()
+            lms = l0.elapsed_time(l1) / 5
+            lbytes = Ml * (8.0 * (2 * NZETA + M_IN) + 16.0 * P_REG)
+            hbm = 6554.6
+            try:
+                hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            except Exception:
+                pass
+            lift_only = {"bound": "hbm", "kernel": "kf_lift_tile_kernel (materialised [Px | Py], not on the fit path)", "pairs": Ml,
+                         "achieved": lbytes / lms / 1e6, "peak": hbm, "unit": "GB/s", "frac": lbytes / lms / 1e6 / hbm,
+                         "algorithmic_bytes_per_pair": 8.0 * (2 * NZETA + M_IN) + 16.0 * P_REG, "ms": lms}
+            del out_buf
+        except Exception as exc:      # an extra, never the reason for a failed bench
+            lift_only = {"error": str(exc)[:200]}
+
     if rank == 0:
         peak, peak_src = fp64_peak_tflops()
         tiles_flops = flops_issued / args.steps                      # DMMA flops issued per step (incl. solver GEMMs)
@@ -362,7 +391,8 @@ def main():
                     "api": "kf_fit (host buffers)" if world == 1 else "pinned host shard -> kf_accumulate_dev/all_reduce/kf_solve_dev"},
             "gpu_launches": int(launches),
             "fast_mode": fast,
-            "roofline": {"bound": "tensor", "kernel": "kf_gram_tile_kernel<true> (FP64 DMMA.8x8x4 Gram/cross-covariance)",
+            "lift_only": lift_only,
+            "roofline": {"bound": "tensor", "kernel": "kf_gram_tma_kernel<true> (FP64 DMMA.8x8x4 Gram/cross-covariance, tensor-map TMA operands)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (4096-snapshot panel) from
                          # the ncu --set full capture in profiles/r01_gram_tma_ncu_summary.txt: 587 MB + 119 MB
