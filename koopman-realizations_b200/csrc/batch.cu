@@ -335,11 +335,7 @@ int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, con
     KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_centres.p, cen.data(), cen.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tasks[0].p, descs.data(), descs.size() * sizeof(KfBatchDesc), cudaMemcpyHostToDevice, st));
     const size_t smem = (size_t)(BT_ROWS * BT_LD + BT_PMAX * BT_LD + BT_ROWS) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-        KF_CUDA(ctx, cudaFuncSetAttribute(kf_batch_ls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    KF_CUDA(ctx, kf_ensure_smem(ctx, kf_batch_ls_kernel, smem));
     KF_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
     kf_batch_ls_kernel<<<(unsigned)descs.size(), BT_ROWS, smem, st>>>(ctx->d_tasks[0].as<KfBatchDesc>(), ctx->d_ops.as<KfOp>(),
                                                                       ctx->d_centres.as<double>(), ctx->d_in.as<double>(),

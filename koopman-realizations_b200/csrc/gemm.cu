@@ -66,29 +66,20 @@ kf_gram_tma_kernel(const KfTmaTask* __restrict__ tasks, const __grid_constant__ 
     kfg::gemm_tile_body_tma<TmaGramCfg, WEIGHTED>(t, &tmap, kf_smem_raw);
 }
 
-bool g_attr_set = false;
-cudaError_t ensure_attrs() {
-    if (g_attr_set) return cudaSuccess;
+cudaError_t ensure_attrs(kf_ctx* ctx) {
     cudaError_t e;
-    e = cudaFuncSetAttribute(kf_gram_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kf_gram_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kf_gemm_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kf_gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaGramCfg::SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kf_gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaGramCfg::SMEM);
-    if (e != cudaSuccess) return e;
-    g_attr_set = true;
-    return cudaSuccess;
+    if ((e = kf_ensure_smem(ctx, kf_gram_tile_kernel<false>, (size_t)GEMM_SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = kf_ensure_smem(ctx, kf_gram_tile_kernel<true>, (size_t)GEMM_SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = kf_ensure_smem(ctx, kf_gemm_grid_kernel, (size_t)GEMM_SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = kf_ensure_smem(ctx, kf_gram_tma_kernel<false>, (size_t)TmaGramCfg::SMEM)) != cudaSuccess) return e;
+    return kf_ensure_smem(ctx, kf_gram_tma_kernel<true>, (size_t)TmaGramCfg::SMEM);
 }
 
 }  // namespace
 
 int kf_launch_gemm_tasks(kf_ctx* ctx, const KfGemmTask* d_tasks, int ntasks, bool weighted, cudaStream_t st) {
     if (ntasks <= 0) return KF_OK;
-    KF_CUDA(ctx, ensure_attrs());
+    KF_CUDA(ctx, ensure_attrs(ctx));
     if (weighted)
         kf_gram_tile_kernel<true><<<ntasks, KF_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(d_tasks);
     else
@@ -100,7 +91,7 @@ int kf_launch_gemm_tasks(kf_ctx* ctx, const KfGemmTask* d_tasks, int ntasks, boo
 
 int kf_launch_gram_tma(kf_ctx* ctx, const KfTmaTask* d_tasks, int ntasks, bool weighted, const CUtensorMap& tmap, cudaStream_t st) {
     if (ntasks <= 0) return KF_OK;
-    KF_CUDA(ctx, ensure_attrs());
+    KF_CUDA(ctx, ensure_attrs(ctx));
     if (weighted)
         kf_gram_tma_kernel<true><<<ntasks, TmaGramCfg::THREADS, TmaGramCfg::SMEM, st>>>(d_tasks, tmap);
     else
@@ -112,7 +103,7 @@ int kf_launch_gram_tma(kf_ctx* ctx, const KfTmaTask* d_tasks, int ntasks, bool w
 
 int kf_launch_gemm_grid(kf_ctx* ctx, const KfGemmGrid& g, cudaStream_t st) {
     if (g.m <= 0 || g.n <= 0 || g.k1 <= g.k0) return KF_OK;
-    KF_CUDA(ctx, ensure_attrs());
+    KF_CUDA(ctx, ensure_attrs(ctx));
     dim3 grid((g.n + KF_CTA_N - 1) / KF_CTA_N, (g.m + KF_CTA_M - 1) / KF_CTA_M);
     kf_gemm_grid_kernel<<<grid, KF_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
     KF_CUDA(ctx, cudaGetLastError());

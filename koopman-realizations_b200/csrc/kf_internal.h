@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -135,6 +136,10 @@ struct kf_ctx {
     kf_allreduce_fn qp_allreduce = nullptr;
     void* qp_user = nullptr;
 
+    // largest dynamic shared-memory limit requested per kernel ON THIS CONTEXT'S DEVICE (the attribute is per device and
+    // only ever grows: a smaller value would make a later, larger launch fail)
+    std::map<const void*, size_t> smem_attr;
+
     // counters
     double dmma_flops = 0;
     long long launches = 0;
@@ -151,6 +156,17 @@ struct kf_ctx {
             return KF_ECUDA;                                                                   \
         }                                                                                      \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize of `func` raised to at least `bytes` on the context's device
+template <class F>
+inline cudaError_t kf_ensure_smem(kf_ctx* ctx, F* func, size_t bytes) {
+    size_t& have = ctx->smem_attr[reinterpret_cast<const void*>(func)];
+    if (have == 0) have = 48 * 1024;
+    if (bytes <= have) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
 
 #define KF_TRY(expr)            \
     do {                        \

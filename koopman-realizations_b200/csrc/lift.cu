@@ -274,13 +274,9 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
 // launches the tile kernel if the program fits (levels, shared memory); returns false otherwise
 template <int LS>
 bool lift_tile_launch_ls(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, size_t smem, cudaStream_t st, int* rc) {
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
-        if (cudaFuncSetAttribute(kf_lift_tile_kernel<LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        smem_set = smem;
+    if (kf_ensure_smem(ctx, kf_lift_tile_kernel<LS>, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
     }
     const long long ntiles = (a.M + LS - 1) / LS;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem + 1024, 1)));

@@ -302,11 +302,7 @@ __global__ void kf_absmax_kernel(const double* C, long long ld, int P, int ncols
 // the dynamic shared-memory limit of the CD kernel only ever grows (a smaller value would make a later,
 // larger launch fail with "invalid argument")
 int ensure_cd_smem(kf_ctx* ctx, size_t smem) {
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
-        KF_CUDA(ctx, cudaFuncSetAttribute(kf_cd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    KF_CUDA(ctx, kf_ensure_smem(ctx, kf_cd_kernel, smem));
     return KF_OK;
 }
 

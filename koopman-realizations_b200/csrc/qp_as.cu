@@ -485,11 +485,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
 
     const size_t smem = (size_t)(AS_NB * AS_TM + AS_NB * AS_TLD + AS_NB * AS_NB + AS_NB * (AS_NB + 1) + AS_NB) * sizeof(double) +
                         (size_t)(AS_NB + P) * sizeof(int) + 16;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        KF_CUDA(ctx, cudaFuncSetAttribute(kf_as_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    KF_CUDA(ctx, kf_ensure_smem(ctx, kf_as_chol_kernel, smem));
     const int egrid = ctx->sm_count * 4;
     const int iter_cap = max_iter > 0 ? max_iter : 200;
     const double rel = 1e-10;

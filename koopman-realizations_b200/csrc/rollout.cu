@@ -209,11 +209,7 @@ int kf_rollout_impl(kf_ctx* ctx, int nmodels, const kf_model* mdls, int ntrials,
         ctx->err = "kf_rollout: lifted state does not fit in shared memory (N + n_full too large)";
         return KF_EINVAL;
     }
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
-        KF_CUDA(ctx, cudaFuncSetAttribute(kf_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    KF_CUDA(ctx, kf_ensure_smem(ctx, kf_rollout_kernel, smem));
     const int width = std::max(N, p.n_full());
     const int threads = std::min(RO_MAX_THREADS, std::max(128, (width + 31) / 32 * 32));
     kf_rollout_kernel<<<dim3(ntrials, nmodels), threads, smem, st>>>(a);

@@ -407,11 +407,7 @@ int kf_assemble(kf_ctx* ctx, const double* accum, const KfTile* d_meta, int ntil
 static int trsm_both(kf_ctx* ctx, const double* W, long long ld, int P, int rank_hint, const int* d_rank, double* X,
                      long long ldx, int ncols, cudaStream_t st) {
     // rank_hint: host copy of the rank (bounds the block loops)
-    static bool attr = false;
-    if (!attr) {
-        KF_CUDA(ctx, cudaFuncSetAttribute(kf_trsm_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8));
-        attr = true;
-    }
+    KF_CUDA(ctx, kf_ensure_smem(ctx, kf_trsm_diag_kernel, (size_t)128 * 128 * 8));
     const int r = rank_hint;
     const int nblk = (r + 127) / 128;
     const int grid = std::max(1, std::min((ncols + 7) / 8, ctx->sm_count));
@@ -740,11 +736,7 @@ __global__ void kf_qr_gather_rhs_kernel(const double* __restrict__ AB, long long
 // backward substitution only:  U X = Z with U = L' stored mirrored in W
 static int trsm_backward(kf_ctx* ctx, const double* W, long long ld, int r, const int* d_rank, double* X, long long ldx, int ncols,
                          cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        KF_CUDA(ctx, cudaFuncSetAttribute(kf_trsm_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8));
-        attr = true;
-    }
+    KF_CUDA(ctx, kf_ensure_smem(ctx, kf_trsm_diag_kernel, (size_t)128 * 128 * 8));
     const int nblk = (r + 127) / 128;
     const int grid = std::max(1, std::min((ncols + 7) / 8, ctx->sm_count));
     const int kmax = (int)kf_roundup(r, KF_BK);
