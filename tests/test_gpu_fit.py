@@ -274,3 +274,50 @@ def test_pc_cols_fast_mode(fitter, model, ls_method):
     assert relF(fast["K"], full["K"][:, :pc]) < 1e-9      # same G; only the split-K summation order may differ
     with pytest.raises(koopfit.KoopfitError):
         fitter.fit(basis, model, alpha, beta, u, pc_cols=pc, least_squares=False, t=[1.0])
+
+
+@pytest.mark.parametrize("model,types,degs,nz,m,M", [
+    ("bilinear", ["poly"], [2], 4, 2, 4096),                 # even M: 128-bit stores, 16-snapshot tiles
+    ("linear", ["poly"], [3], 5, 2, 4097),                   # odd M: scalar stores, tail tile
+    ("nonlinear", ["poly", "fourier_sparser"], [2, 2], 3, 2, 1000),
+    ("bilinear", ["poly"], [4], 8, 1, 530),                  # 495 features: 8-snapshot tiles
+    ("linear", ["hermite", "gaussian"], [2, 7], 3, 1, 777),
+])
+def test_device_lift_only_mode(fitter, model, types, degs, nz, m, M):
+    """kf_regressors_dev / kf_lift_dev (lift-only mode on device buffers, shared-memory tile kernel): [Px | Py] and Psi
+    equal the oracle's regressors (Ksysid.m:1019-1065) — polynomial / Hermite columns bit for bit — and the level-by-level
+    kernel (option lift_tile = 0) gives the identical bytes."""
+    import torch
+    rng = np.random.default_rng(M)
+    alpha, beta, u = 2 * rng.random((M, nz)) - 1, 2 * rng.random((M, nz)) - 1, 2 * rng.random((M, m)) - 1
+    nv = nz + (m if model == "nonlinear" else 0)
+    cen = centres_for(types, degs, nv)
+    basis = koopfit.Basis(types, degs, nv, cen)
+    prog = O.build_program(types, degs, nv, cen)
+    Px, Py = O.build_regressors(model, prog, alpha, beta, u)
+    P = Px.shape[1]
+    dev = torch.device("cuda", 0)
+    ta, tb, tu = (torch.from_numpy(np.ascontiguousarray(x.T)).to(dev) for x in (alpha, beta, u))
+    outs = []
+    for tile in (1, 0):
+        fitter.set_option("lift_tile", tile)
+        out = torch.full((2 * P, M), float("nan"), dtype=torch.float64, device=dev)
+        fitter.regressors_dev(basis, model, M, nz, m, ta.data_ptr(), tb.data_ptr(), tu.data_ptr(), out.data_ptr())
+        fitter.sync()
+        outs.append(out.cpu().numpy().T)
+    fitter.set_option("lift_tile", 1)
+    got = outs[0]
+    assert np.array_equal(outs[0], outs[1])
+    exact = all(t in ("poly", "hermite") for t in types)
+    if exact:
+        assert np.array_equal(got[:, :P], Px) and np.array_equal(got[:, P:], Py)
+    else:
+        assert np.abs(got[:, :P] - Px).max() < 1e-14 and np.abs(got[:, P:] - Py).max() < 1e-14
+    # lift.econ_full on device points
+    V = np.concatenate([alpha, u], axis=1)[:, :nv] if model == "nonlinear" else alpha
+    tv = torch.from_numpy(np.ascontiguousarray(V.T)).to(dev)
+    psi = torch.empty((prog.N, M), dtype=torch.float64, device=dev)
+    fitter.lift_dev(basis, M, tv.data_ptr(), psi.data_ptr())
+    fitter.sync()
+    want = O.lift(prog, V)
+    assert np.abs(psi.cpu().numpy().T - want).max() < (1e-300 if exact else 1e-14)
