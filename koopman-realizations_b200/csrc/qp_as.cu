@@ -25,8 +25,8 @@ namespace {
 
 constexpr int AS_THREADS = 256;
 constexpr int AS_NB = 32;      // block-column width of the factorisation
-constexpr int AS_TM = 128;     // rows per tile
-constexpr int AS_TLD = AS_TM + 1;
+constexpr int AS_KC = 16;      // contraction elements per pipeline stage
+constexpr int AS_NST = 4;      // cp.async stages
 
 // columns a rank works on: [lo, hi) minus the pinned delay columns [skip0, skip1)
 struct AsCols {
@@ -50,15 +50,30 @@ struct AsArgs {
 
 __device__ __forceinline__ int as_ldl(int n) { return (n + 2 + 1) & ~1; }
 
-__global__ void __launch_bounds__(AS_THREADS, 2) kf_as_chol_kernel(const AsArgs a) {
+// 16-byte asynchronous copy global -> shared; bytes = 0 zero-fills the destination
+__device__ __forceinline__ void as_cp16(double* dst, const double* src, int bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+// Tile geometry as template parameters: TM rows per tile, thread tile TR rows x TC columns (TR * TC = TM / 8), MINB CTAs per SM.
+//   <128, 4, 4, 2> is the production geometry: two CTAs per SM overlap the sequential phases of the factorisation (diagonal
+//   block by one warp, panel solve by one thread per row) with the other CTA's update.  <256, 2, 16, 1> (3.3x less shared-memory
+//   traffic per FMA, but one CTA per SM) was measured slower even on the heavy columns alone (config 3a sweep 8.0 s vs 5.9 s):
+//   the kernel is bound by those serial phases and by latency, not by shared-memory or HBM bandwidth.
+template <int TM, int TR, int TC, int MINB>
+__global__ void __launch_bounds__(AS_THREADS, MINB) kf_as_chol_kernel(const AsArgs a) {
+    constexpr int TLD = TM + 1;
+    constexpr int RT = TM / TR;            // row threads; column groups = AS_THREADS / RT = AS_NB / TC
+    static_assert(TR * TC * AS_THREADS == TM * AS_NB && (AS_THREADS / RT) * TC == AS_NB && TC % 2 == 0, "tile geometry");
     extern __shared__ __align__(16) double as_smem[];
-    double* sA = as_smem;                       // [AS_NB][AS_TM]   k-chunk of the row-tile operand
-    double* sT = sA + AS_NB * AS_TM;            // [AS_NB][AS_TLD]  updated tile, column-major
-    double* sB = sT + AS_NB * AS_TLD;           // [AS_NB][AS_NB]   k-chunk of the block-row operand: sB[k][c]
-    double* sD = sB + AS_NB * AS_NB;            // [AS_NB][AS_NB+1] diagonal block factor: sD[r][c]
-    double* sInv = sD + AS_NB * (AS_NB + 1);    // [AS_NB] 1 / diag
-    int* sDead = reinterpret_cast<int*>(sInv + AS_NB);   // [AS_NB]
-    int* sIdx = sDead + AS_NB;                  // [P]
+    double* sA = as_smem;                              // [AS_NST][AS_KC][TM]  k-chunks of the row-tile operand (cp.async ring)
+    double* sB = sA + AS_NST * AS_KC * TM;          // [AS_NST][AS_KC][AS_NB]  k-chunks of the block-row operand: sB[k][c]
+    double* sD = sB + AS_NST * AS_KC * AS_NB;          // [AS_NB][AS_NB+1] diagonal block factor: sD[r][c]
+    double* sInv = sD + AS_NB * (AS_NB + 1);           // [AS_NB] 1 / diag
+    int* sDead = reinterpret_cast<int*>(sInv + AS_NB); // [AS_NB]
+    int* sIdx = sDead + AS_NB;                         // [P]
+    double* sT = sA;                                   // [AS_NB][TLD]  updated tile, column-major (aliases the ring: idle after the k loop)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col = a.cols[blockIdx.x];
@@ -77,73 +92,80 @@ __global__ void __launch_bounds__(AS_THREADS, 2) kf_as_chol_kernel(const AsArgs 
     const int nrows = n + 2;      // rows n, n+1: the right-hand sides c_S and s_S
     int ndead = 0;
 
-    const int tr = lane, tc = warp;   // thread owns tile rows tr + 32 i (i < 4) and tile columns 4 tc + j (j < 4)
+    const int tr = tid % RT, tc = tid / RT;   // thread owns tile rows tr + RT i (i < TR) and tile columns TC tc + j (j < TC)
     for (int J0 = 0; J0 < n; J0 += AS_NB) {
         const int w = min(AS_NB, n - J0);
-        for (int R0 = J0; R0 < nrows; R0 += AS_TM) {
-            double acc[4][4];
+        for (int R0 = J0; R0 < nrows; R0 += TM) {
+            double acc[TR][TC];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TR; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-            // ---- acc = L[R0.., 0:J0] * L[J0.., 0:J0]'   (register-prefetched k-chunks of 32)
-            double pa[16], pb[4];
-            auto fetch = [&](int k0) {
+                for (int j = 0; j < TC; ++j) acc[i][j] = 0.0;
+            // ---- acc = L[R0.., 0:J0] * L[J0.., 0:J0]': k-chunks of AS_KC through an AS_NST-deep cp.async ring, so that the
+            // factor data (HBM: the factors of the ~300 columns in flight do not fit L2) is requested 3 chunks ahead.
+            // Pairs of consecutive rows (16 bytes; ldl, R0, J0 are even and L is 16-byte aligned)
+            auto stage = [&](int k0, int b) {
+                double* dA = sA + b * AS_KC * TM;
+                double* dB = sB + b * AS_KC * AS_NB;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int e = tid + i * AS_THREADS;     // e = kk * 128 + r
-                    const int r = e & (AS_TM - 1), kk = e >> 7;
+                for (int i = 0; i < (AS_KC * TM / 2) / AS_THREADS; ++i) {
+                    const int e = tid + i * AS_THREADS;     // pair index: kk * 64 + r / 2
+                    const int r = (e & (TM / 2 - 1)) * 2, kk = e / (TM / 2);
                     const int gr = R0 + r;
-                    pa[i] = gr < nrows ? L[gr + (long long)(k0 + kk) * ldl] : 0.0;
+                    as_cp16(dA + kk * TM + r, L + (gr < nrows ? gr : 0) + (long long)(k0 + kk) * ldl, gr < nrows ? 16 : 0);
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int e = tid + i * AS_THREADS;     // e = kk * 32 + c
-                    const int c = e & 31, kk = e >> 5;
-                    pb[i] = c < w ? L[(J0 + c) + (long long)(k0 + kk) * ldl] : 0.0;
+                {
+                    const int e = tid;                      // pair index: kk * 16 + c / 2   (AS_KC * AS_NB / 2 = 256 pairs)
+                    const int c = (e & (AS_NB / 2 - 1)) * 2, kk = e / (AS_NB / 2);
+                    as_cp16(dB + kk * AS_NB + c, L + (J0 + (c < w ? c : 0)) + (long long)(k0 + kk) * ldl, c < w ? 16 : 0);
                 }
             };
-            if (J0 > 0) fetch(0);
-            for (int k0 = 0; k0 < J0; k0 += AS_NB) {
+            const int nchunk = J0 / AS_KC;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) sA[tid + i * AS_THREADS] = pa[i];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int e = tid + i * AS_THREADS;
-                    sB[e] = pb[i];
-                }
-                __syncthreads();
-                if (k0 + AS_NB < J0) fetch(k0 + AS_NB);
-#pragma unroll 8
-                for (int kk = 0; kk < AS_NB; ++kk) {
-                    double av[4], bv[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) av[i] = sA[kk * AS_TM + tr + 32 * i];
-                    const double2 b01 = *reinterpret_cast<const double2*>(&sB[kk * AS_NB + 4 * tc]);
-                    const double2 b23 = *reinterpret_cast<const double2*>(&sB[kk * AS_NB + 4 * tc + 2]);
-                    bv[0] = b01.x; bv[1] = b01.y; bv[2] = b23.x; bv[3] = b23.y;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-                }
-                __syncthreads();
+            for (int p = 0; p < AS_NST - 1; ++p) {
+                if (p < nchunk) stage(p * AS_KC, p);
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
+            for (int q = 0; q < nchunk; ++q) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(AS_NST - 2) : "memory");
+                __syncthreads();                            // chunk q has landed; everyone is done with chunk q - 1
+                if (q + AS_NST - 1 < nchunk) stage((q + AS_NST - 1) * AS_KC, (q + AS_NST - 1) % AS_NST);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                const double* cA = sA + (q % AS_NST) * AS_KC * TM + tr;
+                const double* cB = sB + (q % AS_NST) * AS_KC * AS_NB + TC * tc;
+#pragma unroll 4
+                for (int kk = 0; kk < AS_KC; ++kk) {
+                    double av[TR], bv[TC];
+#pragma unroll
+                    for (int i = 0; i < TR; ++i) av[i] = cA[kk * TM + RT * i];
+#pragma unroll
+                    for (int j = 0; j < TC / 2; ++j) {
+                        const double2 t2 = *reinterpret_cast<const double2*>(cB + kk * AS_NB + 2 * j);
+                        bv[2 * j] = t2.x; bv[2 * j + 1] = t2.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < TR; ++i)
+#pragma unroll
+                        for (int j = 0; j < TC; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+                }
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                // the ring is idle: sT may overwrite it
             // ---- tile = A[R0.., J0..] - acc, A gathered from G (rows < n), c_S (row n), s_S (row n+1)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = 4 * tc + j;
+            for (int j = 0; j < TC; ++j) {
+                const int c = TC * tc + j;
                 const int gc = c < w ? sIdx[J0 + c] : 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = tr + 32 * i, gr = R0 + r;
+                for (int i = 0; i < TR; ++i) {
+                    const int r = tr + RT * i, gr = R0 + r;
                     double v = 0.0;
                     if (c < w && gr < nrows && gr >= J0 + c) {
                         if (gr < n) v = a.G[sIdx[gr] + (long long)gc * a.ldg];
                         else v = (gr == n) ? Ccol[gc] : Scol[gc];
                         v -= acc[i][j];
                     }
-                    sT[c * AS_TLD + r] = v;
+                    sT[c * TLD + r] = v;
                 }
             }
             __syncthreads();
@@ -151,30 +173,30 @@ __global__ void __launch_bounds__(AS_THREADS, 2) kf_as_chol_kernel(const AsArgs 
                 // ---- factor the w x w diagonal block (tile rows 0..w-1) with warp 0; lane = row
                 if (warp == 0) {
                     for (int c = 0; c < w; ++c) {
-                        const double p = sT[c * AS_TLD + c];
+                        const double p = sT[c * TLD + c];
                         const double g0 = a.G[sIdx[J0 + c] + (long long)sIdx[J0 + c] * a.ldg];
                         const bool dead = !(p > 2e-15 * g0);
                         const double d = dead ? 1.0 : sqrt(p);
                         const double inv = 1.0 / d;
                         __syncwarp();
                         double lrc = 0.0;
-                        if (lane > c && lane < w) lrc = dead ? 0.0 : sT[c * AS_TLD + lane] * inv;
-                        if (lane == c) { sT[c * AS_TLD + c] = d; sInv[c] = inv; sDead[c] = dead ? 1 : 0; }
-                        if (lane > c && lane < w) sT[c * AS_TLD + lane] = lrc;
+                        if (lane > c && lane < w) lrc = dead ? 0.0 : sT[c * TLD + lane] * inv;
+                        if (lane == c) { sT[c * TLD + c] = d; sInv[c] = inv; sDead[c] = dead ? 1 : 0; }
+                        if (lane > c && lane < w) sT[c * TLD + lane] = lrc;
                         __syncwarp();
                         // trailing update inside the block: T[r][k] -= l[r] * l[k] for c < k <= r
                         if (lane > c && lane < w) {
-                            for (int k = c + 1; k <= lane; ++k) sT[k * AS_TLD + lane] -= lrc * sT[c * AS_TLD + k];
+                            for (int k = c + 1; k <= lane; ++k) sT[k * TLD + lane] -= lrc * sT[c * TLD + k];
                         }
                         __syncwarp();
                     }
                     for (int c = 0; c < w; ++c)
-                        if (lane < w) sD[lane * (AS_NB + 1) + c] = lane >= c ? sT[c * AS_TLD + lane] : 0.0;
+                        if (lane < w) sD[lane * (AS_NB + 1) + c] = lane >= c ? sT[c * TLD + lane] : 0.0;
                 }
                 __syncthreads();
             }
             // ---- rows below the diagonal block: X = T * L_D^-T (one thread per row), write the block column of L
-            if (tid < AS_TM) {
+            if (tid < TM) {
                 const int r = tid, gr = R0 + r;
                 if (gr < nrows) {
                     if (gr < J0 + w) {               // a row of the diagonal block
@@ -182,7 +204,7 @@ __global__ void __launch_bounds__(AS_THREADS, 2) kf_as_chol_kernel(const AsArgs 
                     } else {
                         double x[AS_NB];
 #pragma unroll
-                        for (int c = 0; c < AS_NB; ++c) x[c] = c < w ? sT[c * AS_TLD + r] : 0.0;
+                        for (int c = 0; c < AS_NB; ++c) x[c] = c < w ? sT[c * TLD + r] : 0.0;
 #pragma unroll
                         for (int c = 0; c < AS_NB; ++c) {
                             if (c < w) {
@@ -203,7 +225,7 @@ __global__ void __launch_bounds__(AS_THREADS, 2) kf_as_chol_kernel(const AsArgs 
     }
 
     // ---- back-substitution L' x = y for both right-hand sides (y = rows n, n+1 of L); x lives in shared memory
-    double* xs = as_smem;            // [2][n], aliases sA | sT (n <= 4096)
+    double* xs = as_smem;            // [2][n] (n <= 4096), aliases the ring
     for (int i = tid; i < n; i += AS_THREADS) {
         xs[i] = L[n + (long long)i * ldl];
         xs[n + i] = L[n + 1 + (long long)i * ldl];
@@ -483,9 +505,11 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     }
     const size_t ws_doubles = ctx->d_as_ws.bytes / sizeof(double);
 
-    const size_t smem = (size_t)(AS_NB * AS_TM + AS_NB * AS_TLD + AS_NB * AS_NB + AS_NB * (AS_NB + 1) + AS_NB) * sizeof(double) +
-                        (size_t)(AS_NB + P) * sizeof(int) + 16;
-    KF_CUDA(ctx, kf_ensure_smem(ctx, kf_as_chol_kernel, smem));
+    auto smem_of = [&](int tm) {
+        return (size_t)(AS_NST * AS_KC * (tm + AS_NB) + AS_NB * (AS_NB + 1) + AS_NB) * sizeof(double) + (size_t)(AS_NB + P) * sizeof(int) + 16;
+    };
+    const size_t smem = smem_of(128);
+    KF_CUDA(ctx, kf_ensure_smem(ctx, kf_as_chol_kernel<128, 4, 4, 2>, smem));
     const int egrid = ctx->sm_count * 4;
     const int iter_cap = max_iter > 0 ? max_iter : 200;
     const double rel = 1e-10;
@@ -552,7 +576,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
         for (int c1 : chunk_end) {
             if (c1 > c0) {
                 a.cols = d_cols + c0; a.ws_off = d_off + c0;
-                kf_as_chol_kernel<<<c1 - c0, AS_THREADS, smem, st>>>(a);
+                kf_as_chol_kernel<128, 4, 4, 2><<<c1 - c0, AS_THREADS, smem, st>>>(a);
                 KF_CUDA(ctx, cudaGetLastError());
                 ctx->launches += 1;
             }
