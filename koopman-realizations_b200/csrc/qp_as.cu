@@ -172,26 +172,33 @@ __global__ void __launch_bounds__(AS_THREADS, MINB) kf_as_chol_kernel(const AsAr
             if (R0 == J0) {
                 // ---- factor the w x w diagonal block (tile rows 0..w-1) with warp 0; lane = row
                 if (warp == 0) {
-                    for (int c = 0; c < w; ++c) {
-                        const double p = sT[c * TLD + c];
-                        const double g0 = a.G[sIdx[J0 + c] + (long long)sIdx[J0 + c] * a.ldg];
-                        const bool dead = !(p > 2e-15 * g0);
-                        const double d = dead ? 1.0 : sqrt(p);
-                        const double inv = 1.0 / d;
-                        __syncwarp();
-                        double lrc = 0.0;
-                        if (lane > c && lane < w) lrc = dead ? 0.0 : sT[c * TLD + lane] * inv;
-                        if (lane == c) { sT[c * TLD + c] = d; sInv[c] = inv; sDead[c] = dead ? 1 : 0; }
-                        if (lane > c && lane < w) sT[c * TLD + lane] = lrc;
-                        __syncwarp();
-                        // trailing update inside the block: T[r][k] -= l[r] * l[k] for c < k <= r
-                        if (lane > c && lane < w) {
-                            for (int k = c + 1; k <= lane; ++k) sT[k * TLD + lane] -= lrc * sT[c * TLD + k];
+                    // lane r keeps row r of the block in registers (x[k] = T[r][k], k <= r); column c of the factor is broadcast
+                    // lane to lane with shuffles — no shared-memory round trips inside the 32 dependent steps
+                    double x[AS_NB];
+#pragma unroll
+                    for (int k = 0; k < AS_NB; ++k) x[k] = (lane < w && k <= lane) ? sT[k * TLD + lane] : 0.0;
+                    const double g0 = lane < w ? a.G[sIdx[J0 + lane] + (long long)sIdx[J0 + lane] * a.ldg] : 1.0;
+#pragma unroll
+                    for (int c = 0; c < AS_NB; ++c) {
+                        if (c < w) {                                   // uniform
+                            const double p = __shfl_sync(0xffffffffu, x[c], c);
+                            const double gc = __shfl_sync(0xffffffffu, g0, c);
+                            const bool dead = !(p > 2e-15 * gc);
+                            const double d = dead ? 1.0 : sqrt(p);
+                            const double inv = 1.0 / d;
+                            const double lrc = (lane > c && !dead) ? x[c] * inv : 0.0;     // L[lane][c]
+#pragma unroll
+                            for (int k = c + 1; k < AS_NB; ++k) {
+                                const double lk = __shfl_sync(0xffffffffu, lrc, k);        // L[k][c]
+                                x[k] = fma(-lrc, lk, x[k]);                               // only k <= lane is ever read
+                            }
+                            x[c] = (lane == c) ? d : lrc;
+                            if (lane == c) { sInv[c] = inv; sDead[c] = dead ? 1 : 0; }
                         }
-                        __syncwarp();
                     }
-                    for (int c = 0; c < w; ++c)
-                        if (lane < w) sD[lane * (AS_NB + 1) + c] = lane >= c ? sT[c * TLD + lane] : 0.0;
+#pragma unroll
+                    for (int c = 0; c < AS_NB; ++c)
+                        if (c < w && lane < w) sD[lane * (AS_NB + 1) + c] = lane >= c ? x[c] : 0.0;
                 }
                 __syncthreads();
             }
