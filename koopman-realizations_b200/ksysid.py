@@ -92,8 +92,8 @@ class Ksysid:
             raise ValueError("Invalid model_type chosen. Must be linear, bilinear, or nonlinear.")   # 103
         if self.loaded:
             raise NotImplementedError("loaded (w) dictionaries are outside the hot-path scope (SURVEY §2a)")
-        if self.time_type != "discrete":
-            raise NotImplementedError("continuous-time (logm) models are outside the hot-path scope (SURVEY §8f #4)")
+        if self.time_type not in ("discrete", "continuous"):
+            raise ValueError("time_type must be discrete or continuous")
         self.liftinput = {"linear": 0, "nonlinear": 1, "bilinear": 2}[self.model_type]
         self._ls_method = extras["ls_method"]
         # opt-in: compute only the K columns the model consumes (K(:,1:N) or K(:,1:nzeta)); model['K'] is then P x Pc
@@ -242,21 +242,37 @@ class Ksysid:
             out.append(kd)
         return out
 
+    def _UT(self, K):
+        """K' for a discrete model; (1/Ts) logm(K' + 1e-12 I) for a continuous one (Ksysid.m:1186-1190, 1245-1249).
+        Needs the whole K (not the fast-columns variant).  A complex logarithm (negative real eigenvalues) is returned as
+        MATLAB would; a negligible imaginary part is dropped."""
+        if self.time_type != "continuous":
+            return K.T
+        if K.shape[0] != K.shape[1]:
+            raise ValueError("continuous-time models need the full K (fast_cols must be off)")
+        from scipy.linalg import logm
+        UT = logm(K.T + 1e-12 * np.eye(K.shape[0])) / self.params["Ts"]
+        if np.iscomplexobj(UT) and np.abs(UT.imag).max() <= 1e-9 * max(np.abs(UT.real).max(), 1e-300):
+            UT = UT.real
+        return UT
+
     def get_model(self, koopData):
-        """Ksysid.m:1179-1235 (discrete): A, B, C and the projection M = (L \\ R)'."""
+        """Ksysid.m:1179-1235: A, B, C and the projection M = (L \\ R)' (applied to A, B only for discrete models)."""
         N, n = self.params["N"], self.params["n"]
-        UT = koopData["K"][:, :N].T
+        UT = self._UT(koopData["K"])[:N, :]
         Amat, Bmat = UT[:N, :N], UT[:N, N:]
         Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
         L = koopData["Px"] @ Amat.T + koopData["u"] @ Bmat.T
         Mt, _, _ = self.fitter.mldivide(L, koopData["Py"])          # `L \ R` on the GPU (Ksysid.m:1216)
         Mp = Mt.T
+        if self.time_type == "continuous":                  # Ksysid.m:1220-1222: no projection for continuous models
+            return {"A": Amat, "B": Bmat, "C": Cy, "M": Mp, "params": self.params, "K": koopData["K"]}
         return {"A": Mp @ Amat, "B": Mp @ Bmat, "C": Cy, "M": Mp, "params": self.params, "K": koopData["K"]}
 
     def get_BLmodel(self, koopData):
         """Ksysid.m:1238-1282."""
         N, n, m = self.params["N"], self.params["n"], self.params["m"]
-        UT = koopData["K"][:, :N].T
+        UT = self._UT(koopData["K"])[:N, :]
         Amat, Bmat = UT[:N, :N], UT[:N, N:]
         Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
         return {"A": Amat, "B": Bmat, "Beta": lambda z: Bmat @ np.kron(np.eye(m), np.asarray(z).reshape(-1, 1)),
@@ -265,7 +281,8 @@ class Ksysid:
     def get_NLmodel(self, koopData):
         """Ksysid.m:1298-1341: F(zeta,u) = K(:,1:nzeta)' psi([zeta;u]); C = I_n."""
         nz, n = self.params["nzeta"], self.params["n"]
-        F = koopData["K"][:, :nz].T.copy()
+        Kc = self._UT(koopData["K"]).T if self.time_type == "continuous" else koopData["K"]    # Ksysid.m:1308-1311
+        F = np.array(Kc[:, :nz].T)
         return {"F_sym": F, "F_func": lambda zeta, u: F @ self._lift(np.concatenate([np.ravel(zeta), np.ravel(u)])),
                 "params": self.params, "C": np.eye(n), "K": koopData["K"]}
 
@@ -344,18 +361,48 @@ class Ksysid:
         res["error"] = self.get_error(res["sim"], res["real"])
         return res
 
+    def _val_continuous(self, model, valdata):
+        """Continuous-time validation (Ksysid.m:1681-1684, 1777-1780, 1852-1855): every sample interval is integrated
+        with RK45 (ode45's pair; MATLAB's default tolerances RelTol 1e-3, AbsTol 1e-6) holding the input.  Host side, as
+        in the reference: the GPU rollout kernel covers the discrete models."""
+        from scipy.integrate import solve_ivp
+        setup = self._val_setup(valdata)
+        treal, yreal, ureal, zetareal = setup
+        Ts = self.params["Ts"]
+        if self.model_type == "nonlinear":
+            x = zetareal[0].copy()
+            rhs = lambda uj: (lambda t, zeta: model["F_func"](zeta, uj))
+        elif self.model_type == "bilinear":
+            x = self._lift(zetareal[0])
+            rhs = lambda uj: (lambda t, z: model["A"] @ z + model["Beta"](z) @ uj)
+        else:
+            x = self._lift(zetareal[0])
+            rhs = lambda uj: (lambda t, z: model["A"] @ z + model["B"] @ uj)
+        states = np.zeros((len(treal), x.size))
+        states[0] = x
+        for j in range(len(treal) - 1):
+            x = solve_ivp(rhs(ureal[j]), (0.0, Ts), x, method="RK45", rtol=1e-3, atol=1e-6).y[:, -1]
+            states[j + 1] = x
+        return self._val_result(setup, states)
+
     def val_model(self, model, valdata):
         """Ksysid.m:1623-1722 (discrete, unloaded): z+ = A z + B u (1685), y = C z; on the GPU (kf_rollout)."""
+        if self.time_type == "continuous":
+            return self._val_continuous(model, valdata)
         setups, sims = self._rollout([model], [valdata], self.params["N"])
         return self._val_result(setups[0], sims[0][0])
 
     def val_BLmodel(self, model, valdata):
         """Ksysid.m:1725-1820: z+ = A z + Beta(z) u (1783)."""
+        if self.time_type == "continuous":
+            return self._val_continuous(model, valdata)
         setups, sims = self._rollout([model], [valdata], self.params["N"])
         return self._val_result(setups[0], sims[0][0])
 
     def val_NLmodel(self, model, valdata):
         """Ksysid.m:1823-1879: zeta+ = F_func(zeta, u) (1860), y = zeta(1:n) (1864)."""
+        if self.time_type == "continuous":
+            return self._val_continuous(model, valdata)
         setups, sims = self._rollout([model], [valdata], self.params["nzeta"])
         return self._val_result(setups[0], sims[0][0])
 
@@ -365,6 +412,8 @@ class Ksysid:
         valNplot_model over candidates and trials (Ksysid.m:1928-1972)."""
         cands = candidates if candidates is not None else (self.candidates if isinstance(self.candidates, list) else [self.model])
         vals = self.valdata if trials is None else [self.valdata[i] for i in trials]
+        if self.time_type == "continuous":
+            return [[self._val_continuous(c, v) for v in vals] for c in cands]
         setups, sims = self._rollout(cands, vals, self.params["nzeta"])
         return [[self._val_result(setups[k], sims[c][k]) for k in range(len(vals))] for c in range(len(cands))]
 

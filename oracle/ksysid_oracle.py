@@ -30,7 +30,7 @@ import numpy as np
 import scipy.linalg as sla
 
 __all__ = [
-    "basic_solution_extended",
+    "basic_solution_extended", "continuous_UT",
     "load_data4sysid", "load_rand_systems", "merge_trials", "get_scale", "scale_data",
     "get_zeta", "get_snapshot_pairs", "partitions_ones", "FeatureProgram", "build_program",
     "lift", "lift_full", "build_regressors", "regressor_width", "mldivide", "gram", "qp_objective",
@@ -711,23 +711,31 @@ def get_koopman(model_type, prog, pairs, lasso=1e6, N=None, n=None, nd=0, psd_sh
 
 
 # --------------------------------------------------------------------------- models
-def get_model(koop, n):
-    """Linear model A,B,C with the projection M = (L \\ R)' (Ksysid.m:1179-1235, discrete)."""
+def continuous_UT(K, Ts):
+    """(1/Ts) logm(K' + 1e-12 I): the continuous-time generator (Ksysid.m:1186-1187, 1245-1246; 1310 for K itself)."""
+    return sla.logm(K.T + 1e-12 * np.eye(K.shape[0])) / Ts
+
+
+def get_model(koop, n, Ts=None):
+    """Linear model A,B,C with the projection M = (L \\ R)' (Ksysid.m:1179-1235); Ts given = continuous time:
+    A, B from the matrix logarithm and NOT projected (1220-1222)."""
     K, N = koop["K"], koop["N"]
-    UT = K.T
+    UT = K.T if Ts is None else continuous_UT(K, Ts)
     A, B = UT[:N, :N], UT[:N, N:]
     Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
     Pxs, Pys, U = koop["Px"][:, :N], koop["Py"][:, :N], koop["u"]
     L = Pxs @ A.T + U @ B.T
     Mt = mldivide(L, Pys)
     Mp = Mt.T
+    if Ts is not None:
+        return {"A": A, "B": B, "C": Cy, "M": Mp, "K": K}
     return {"A": Mp @ A, "B": Mp @ B, "C": Cy, "M": Mp, "K": K}
 
 
-def get_BLmodel(koop, n):
+def get_BLmodel(koop, n, Ts=None):
     """Bilinear model: A, B=[B_1..B_m], Beta(z)=B kron(I_m,z) (Ksysid.m:1238-1295)."""
     K, N = koop["K"], koop["N"]
-    UT = K.T
+    UT = K.T if Ts is None else continuous_UT(K, Ts)
     A, B = UT[:N, :N], UT[:N, N:]
     Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
     return {"A": A, "B": B, "C": Cy, "K": K}

@@ -192,3 +192,24 @@ def test_rollout_argument_errors(fitter):
         fitter.rollout(basis, "linear", 3, 1, 3, [{"A": np.eye(4), "B": np.zeros((4, 1))}], [(np.zeros(3), np.zeros((5, 1)))])   # N mismatch
     with pytest.raises(koopfit.KoopfitError):
         fitter.rollout(basis, "linear", 3, 1, 3, [{"A": None, "B": None}], [(np.zeros(3), np.zeros((5, 1)))])
+
+
+def test_continuous_time_models(fitter, snake_data):
+    """time_type = 'continuous' (Ksysid.m:1186-1190, 1220-1222, 1681-1684): A, B from (1/Ts) logm(K' + 1e-12 I) of the GPU
+    fit, no projection for the linear model, validation by RK45 over every sample interval."""
+    for model_type in ("linear", "bilinear"):
+        ks = Ksysid(snake_data, model_type=model_type, obs_type=["poly"], obs_degree=[2], dim_red=False, time_type="continuous",
+                    fitter=fitter).train_models()
+        ko = O.KsysidOracle(snake_data, model_type=model_type, obs_type=["poly"], obs_degree=[2]).train_models()
+        Ts = ks.params["Ts"]
+        want = (O.get_model if model_type == "linear" else O.get_BLmodel)(ko.koopData[0], ko.n, Ts=Ts)
+        N = ks.params["N"]
+        assert ks.model["A"].shape == (N, N) and ks.model["B"].shape[0] == N
+        assert relF(ks.model["A"], want["A"]) < 1e-5 and relF(ks.model["B"], want["B"]) < 1e-5
+        if model_type == "linear":
+            assert "M" in ks.model                        # computed, but not applied to A, B (1220-1222)
+        if not np.iscomplexobj(ks.model["A"]):
+            v = {k: x[:40] for k, x in ks.valdata[0].items()}
+            r = (ks.val_model if model_type == "linear" else ks.val_BLmodel)(ks.model, v)
+            assert r["sim"]["y"].shape == (40, ks.params["n"]) and np.all(np.isfinite(r["sim"]["y"]))
+            assert np.abs(r["sim"]["y"][0] - r["real"]["y"][0]).max() == 0.0

@@ -124,3 +124,25 @@ def test_config1_oracle_against_extended_precision_truth(arm_data):
     Px, Py = koop["Px"].astype(np.longdouble), koop["Py"].astype(np.longdouble)
     res = Px[:, basic].T @ (Px[:, basic] @ truth[basic] - Py)
     assert float(np.abs(res).max()) < 1e-12
+
+
+def test_continuous_time_generator_roundtrip():
+    """time_type = 'continuous' (Ksysid.m:1186-1190): UT = logm(K' + 1e-12 I) / Ts, so expm(Ts UT) gives K' back; the host
+    mirror's _UT and the oracle agree (both are the same few lines over scipy.linalg.logm — the reference calls MATLAB's)."""
+    import scipy.linalg as sla
+    from koopfit.ksysid import Ksysid
+    rng = np.random.default_rng(4)
+    N, m, Ts = 6, 2, 0.05
+    A0 = sla.expm(Ts * (rng.standard_normal((N, N)) - 2 * np.eye(N)))          # a discrete-time map with a real logarithm
+    K = np.zeros((N + m, N + m))
+    K[:N, :N] = A0.T
+    K[N:, :N] = 0.1 * rng.standard_normal((m, N))
+    K[N:, N:] = np.eye(m)
+    UT = O.continuous_UT(K, Ts)
+    assert np.abs(np.imag(UT)).max() < 1e-12
+    assert np.abs(sla.expm(Ts * np.real(UT)) - K.T).max() < 1e-9
+    ks = Ksysid.__new__(Ksysid)                      # host logic only: no GPU context
+    ks.time_type, ks.params = "continuous", {"Ts": Ts}
+    assert np.abs(ks._UT(K) - np.real(UT)).max() < 1e-13
+    ks.time_type = "discrete"
+    assert np.array_equal(ks._UT(K), K.T)
