@@ -146,3 +146,24 @@ def test_continuous_time_generator_roundtrip():
     assert np.abs(ks._UT(K) - np.real(UT)).max() < 1e-13
     ks.time_type = "discrete"
     assert np.array_equal(ks._UT(K), K.T)
+
+
+def test_host_mirror_preprocessing_matches_oracle(arm_data):
+    """The host side of the Ksysid mirror (merge / scale / zeta: Ksysid.m:180-229, 380-401, 868-907) against the oracle's
+    restatement, without a GPU (module-level helpers only)."""
+    from koopfit import ksysid as KS
+    merged = KS.merge_trials(arm_data["train"])
+    want = O.merge_trials(arm_data["train"])
+    assert all(np.array_equal(merged[k], want[k]) for k in ("t", "y", "u"))
+    sc = KS._scale_factors(merged)
+    _, so = O.get_scale(want)
+    assert all(np.array_equal(sc[k], so[k]) for k in ("y_offset", "y_factor", "u_offset", "u_factor"))
+    flat = dict(merged)
+    flat["y"] = merged["y"].copy()
+    flat["y"][:, 2] = 7.0                                   # constant column: factor 1 (Ksysid.m:196-198)
+    assert KS._scale_factors(flat)["y_factor"][2] == 1.0 and KS._scale_factors(flat)["y_offset"][2] == 7.0
+    for nd in (0, 1, 3):
+        z, uz = KS._zeta(merged["y"], merged["u"], nd)
+        zo, uo = O.get_zeta(want, nd)
+        assert np.array_equal(z, zo) and np.array_equal(uz, uo)
+        assert z.shape == (merged["y"].shape[0] - nd, 6 * (nd + 1) + 3 * nd)
