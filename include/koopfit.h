@@ -80,8 +80,10 @@ typedef struct {
     int delay_constraint;   /* 1: pin the delay columns (linear, nd>=1; Ksysid.m:1139-1164) */
     int n;                  /* params.n  (needed by the delay constraint) */
     int nd;                 /* params.nd */
-    int qp_max_iter;        /* <=0 -> default */
-    double qp_tol;          /* relative objective/iterate tolerance; <=0 -> default 1e-10 */
+    int qp_max_iter;        /* <=0 -> default.  Coordinate descent: sweeps per evaluation of the multiplier (100000 for P <= 256,
+                               else 2000); active set: exact steps per attempt of a budget (200) */
+    double qp_tol;          /* coordinate descent: relative iterate tolerance of a sweep; <=0 -> default 1e-13 (the active-set
+                               solver is exact and ignores it) */
 } kf_solve;
 
 typedef struct {
@@ -94,7 +96,8 @@ typedef struct {
     double t_lift_gram_ms;  /* device time of lift + Gram */
     double t_solve_ms;      /* device time of the solve */
     double t_total_ms;      /* wall time of the call */
-    int qp_capped;          /* QP: inner coordinate-descent solves that hit the sweep bound (0 = all converged) */
+    int qp_capped;          /* QP: coordinate-descent evaluations that hit the sweep bound / active-set budgets that did not
+                               settle (0 = all converged; kf_result.qp_gap tells how far off the returned K can be) */
     int reserved;
 } kf_info;
 
@@ -108,7 +111,7 @@ typedef struct {
     int* perm;              /* P: pivot order (0-based), first `rank` entries = basic set */
     double* objective;      /* nt: 0.5 tr(K'GK) - tr(C'K) per budget */
     double* l1norm;         /* nt: ||vec K||_1 */
-    int* qp_iters;          /* nt */
+    int* qp_iters;          /* nt: multiplier evaluations (coordinate descent) or exact active-set steps spent on the budget */
     double* qp_gap;         /* nt: certified optimality gap of the returned K: f(K) - min f <= qp_gap (Frank-Wolfe gap
                                <GK - C, K> + t ||GK - C||_inf over the free columns); compare with 1e-8 |objective| */
     kf_info info;
@@ -235,7 +238,12 @@ void* kf_stream(kf_ctx* ctx);                        /* the context's cudaStream
 int kf_counters(kf_ctx* ctx, double* dmma_flops, long long* launches, int reset);
 /* device time (ms, CUDA events on the context stream) of the last lift+Gram phase and solve phase */
 int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, double* solve_ms);
-/* tuning knobs: "chunk" (snapshots per L2-resident panel), "splitk", ... ; returns KF_EINVAL if unknown */
+/* tuning knobs; returns KF_EINVAL if unknown:
+ *   "chunk" (snapshots per L2-resident panel), "panel_mb", "splitk", "overlap" (two chunk pipelines), "tma" (Gram operands by
+ *   tensor-map TMA = 1 / cp.async = 0), "profile" (sample Gram-kernel durations), "qr_max_gb" (KF_LS_AUTO takes the QRCP route
+ *   up to this size of [Px | Py]), "qp_method" (0 auto: coordinate descent for P <= 256, exact active set above; 1; 2),
+ *   "as_frac" (active set: bound on the pattern change per step, fraction of the support, default 0.05, self-tuning downwards),
+ *   "as_ws_gb" (active set: bound on the factor workspace), "lift_tile" (materialising lift: shared-memory tile kernel = 1) */
 int kf_set_option(kf_ctx* ctx, const char* name, double value);
 
 #ifdef __cplusplus
