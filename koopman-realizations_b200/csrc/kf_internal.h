@@ -56,6 +56,16 @@ struct KfTmaTask {
     const double* W;           // weight row (global pointer) or nullptr = unweighted
 };
 
+// ------------------------------------------------------------------ feature groups of the materialising lift (lift.cu)
+constexpr int KF_LT_MAXLEV = 32;
+struct LtOp { int kind, a, b, j; double c; };      // op of a group in level order; a, b, j are SLOTS (GAUSS: a = centre column)
+struct LtGroup {
+    int op_off, nops;                  // ops of the group in the global op array
+    int st_off, nst;                   // stored features: (slot, output row) pairs
+    int nslots, nlevels;
+    int level_start[KF_LT_MAXLEV + 1]; // offsets into the group's ops
+};
+
 // ------------------------------------------------------------------ device buffer
 struct KfBuf {
     void* p = nullptr;
@@ -115,6 +125,7 @@ struct kf_ctx {
     KfBuf d_ops, d_centres, d_pcs, d_panel[2], d_full, d_tasks[2], d_tma_tasks[2], d_accum, d_tilemeta;
     CUtensorMap tmap[2];            // tensor maps of the two panels (SWIZZLE_128B, box 16 x 64)
     KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3, d_Kt;
+    KfBuf d_lift_groups;                 // feature groups of the materialising lift (ops | store lists | group records)
     KfBuf d_series;                      // raw merged series t | y | u and the scale factors (kf_fit_series)
     KfBuf d_as_mat, d_as_aux, d_as_ws;   // active-set QP solver: pattern/solution matrices, index lists, Cholesky factors
 
@@ -128,8 +139,14 @@ struct kf_ctx {
     int opt_qp_method = 0;    // L1-ball QP: 0 auto (coordinate descent for P <= 256, exact active set above), 1 CD, 2 active set
     double opt_as_frac = 0.05; // active-set solver: bound on the pattern change per step, as a fraction of the support size
     double opt_as_ws_gb = 8;  // active-set solver: bound on the per-column Cholesky workspace (columns run in chunks that fit)
+    int opt_lift_ls = 0;      // materialising lift: snapshots per tile (8 | 16 | 32 | 64; 0 = auto)
     int opt_lift_tile = 1;    // materialising lift: whole program per 16-snapshot tile in shared memory (0: level-by-level kernel)
     int opt_tma = 1;          // Gram kernel operand path: 1 = tensor-map TMA + mbarrier ring, 0 = per-thread cp.async
+
+    // host staging of the lift feature groups (kept alive across the asynchronous upload)
+    std::vector<LtOp> lt_ops;
+    std::vector<int2> lt_store;
+    std::vector<LtGroup> lt_groups;
 
     // column partition of the active-set QP solver across ranks (kf_set_qp_partition)
     int qp_lo = 0, qp_hi = 0;

@@ -124,20 +124,24 @@ __global__ void kf_regressor_post_kernel(int model, int N, int P, int m, const d
 // HBM-resident output), then streams the rows of [Px | Py] (or Psi) out once, 128-byte segments per feature;
 // the bilinear blocks u_k psi and the dim_red projection are formed from shared memory too.
 constexpr int LT_THREADS = 256;
-constexpr int LT_MAXLEV = 32;
+constexpr int LT_MAXLEV = KF_LT_MAXLEV;
+constexpr int LT_SLOTS = 440;      // target size of a feature group (shared-memory slots): 3 CTAs per SM with 16-snapshot tiles
 
+// A feature GROUP (LtGroup / LtOp, kf_internal.h): a contiguous range of output features plus everything they depend on
+// (their dependency closure), renumbered into compact shared-memory slots.  Splitting a large dictionary into groups that
+// run as separate CTAs keeps the shared memory per CTA small (several CTAs per SM) at the price of re-evaluating shared
+// parents (cheap products).
 struct KfLiftTileArgs {
-    const KfOp* ops; const double* centres; const double* pcs; const int* order;
-    int level_start[LT_MAXLEV + 1]; int nlevels;
+    const KfOp* ops; const double* centres; const double* pcs; const int* order;   // ops / order: unused by the tile kernel
+    const LtOp* gops; const int2* gstore; const LtGroup* groups; int ngroups;
     int nv, n_full, n_pcs, N;          // N = lifted dimension (n_full, or nv + n_pcs + 1 with dim_red)
     int nzeta, m, model;
     int mode;                           // 0: points V -> Psi (rows x N);  1: regressors [Px | Py] (M x 2P)
     int P;
+    int max_slots, max_ops, max_nst;
     const double* alpha; const double* beta; const double* u; long long M;
     double* out; long long ld;
 };
-
-struct LtOp { int kind, a, b, j; double c; };   // one op of the level-ordered program, staged in shared memory
 
 __device__ __forceinline__ void lt_ld4(const double* p, double (&v)[4]) {
     const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
@@ -149,30 +153,32 @@ __device__ __forceinline__ void lt_st4(double* p, const double (&v)[4]) {
 }
 
 // LS = snapshots per tile (8 or 16: 64- or 128-byte segments per output row), chosen by the host so that several CTAs fit
-// an SM and the load / evaluate / store phases of different tiles overlap.  Work split: evaluation — a thread takes one op
-// (read from the shared-memory copy of the level-ordered program) and applies it to 4 snapshots with 128-bit shared-memory
-// accesses, so the interpretive overhead is paid once per 4 elements; store — 2 snapshots (one 128-bit store) per thread.
+// an SM and the load / evaluate / store phases of different tiles overlap.  blockIdx.y = side * ngroups + group.
+// Work split: evaluation — a thread takes one op (read from the shared-memory copy of the group's level-ordered program)
+// and applies it to 4 snapshots with 128-bit shared-memory accesses, so the interpretive overhead is paid once per
+// 4 elements; store — 2 snapshots (one 128-bit store) per thread.
 template <int LS>
 __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTileArgs a) {
     extern __shared__ __align__(16) double lt_smem[];
-    double* sh = lt_smem;                              // [n_full][LS]
-    double* su = sh + (size_t)a.n_full * LS;           // [m][LS]   inputs u of the tile
-    double* se = su + (size_t)a.m * LS;                // [N][LS]   econ features (dim_red only)
-    LtOp* sop = reinterpret_cast<LtOp*>(se + (a.n_pcs > 0 ? (size_t)a.N * LS : 0));   // [n_full] in level order
+    double* sh = lt_smem;                              // [max_slots][LS]; slots 0 .. nv-1 are the variables
+    double* su = sh + (size_t)a.max_slots * LS;        // [m][LS]   inputs u of the tile
+    double* se = su + (size_t)a.m * LS;                // [N][LS]   econ features (dim_red only, single group)
+    LtOp* sop = reinterpret_cast<LtOp*>(se + (a.n_pcs > 0 ? (size_t)a.N * LS : 0));   // [max_ops] in level order
+    int2* sst = reinterpret_cast<int2*>(sop + a.max_ops);                             // [max_nst] (slot, output row)
+    __shared__ LtGroup grp;
     const int tid = threadIdx.x;
-    const int side = blockIdx.y;
+    const int side = blockIdx.y / a.ngroups, g = blockIdx.y % a.ngroups;
     const double* src = side ? a.beta : a.alpha;
     const long long ntiles = (a.M + LS - 1) / LS;
     const bool vec2 = ((a.ld & 1) == 0) && ((reinterpret_cast<unsigned long long>(a.out) & 15ull) == 0);
-    for (int e = tid; e < a.n_full; e += LT_THREADS) {
-        const int j = a.order[e];
-        const KfOp op = a.ops[j];
-        sop[e] = LtOp{op.kind, op.a, op.b, j, op.c};
-    }
+    if (tid == 0) grp = a.groups[g];
+    __syncthreads();
+    for (int e = tid; e < grp.nops; e += LT_THREADS) sop[e] = a.gops[grp.op_off + e];
+    for (int e = tid; e < grp.nst; e += LT_THREADS) sst[e] = a.gstore[grp.st_off + e];
     __syncthreads();
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long g0 = tile * LS;
-        // ---- A: the variables v (features 0 .. nv-1) and u of the tile; the tail of the last tile is zero
+        // ---- A: the variables v (slots 0 .. nv-1) and u of the tile; the tail of the last tile is zero
         for (int idx = tid; idx < (a.nv + a.m) * LS; idx += LT_THREADS) {
             const int k = idx / LS, s = idx & (LS - 1);
             const long long gs = g0 + s;
@@ -184,13 +190,13 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
             if (k < a.nv) sh[k * LS + s] = v; else su[(k - a.nv) * LS + s] = v;
         }
         __syncthreads();
-        // ---- B: the program, level by level
+        // ---- B: the group's program, level by level
         {
             constexpr int QS = LS / 4;                 // snapshot quads per tile
             constexpr int NF = LT_THREADS / QS;
             const int s0 = (tid % QS) * 4, fs = tid / QS;
-            for (int l = 0; l < a.nlevels; ++l) {
-                const int first = a.level_start[l], last = a.level_start[l + 1];
+            for (int l = 0; l < grp.nlevels; ++l) {
+                const int first = grp.level_start[l], last = grp.level_start[l + 1];
                 for (int e = first + fs; e < last; e += NF) {
                     const LtOp op = sop[e];
                     double v[4];
@@ -201,7 +207,6 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
 #pragma unroll
                         for (int t = 0; t < 4; ++t) v[t] = KF_MUL(x[t], y[t]);
                     } else if (op.kind == KF_OP_VAR) {
-                        if (op.a == op.j) continue;              // loaded in A
                         lt_ld4(sh + op.a * LS + s0, v);
                     } else {
                         KfOp o{};
@@ -217,8 +222,7 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
                 __syncthreads();
             }
         }
-        const double* psi = sh;
-        if (a.n_pcs > 0) {      // econ lift [v; pcs' psi_full; 1]  (Ksysid.m:1614-1618)
+        if (a.n_pcs > 0) {      // econ lift [v; pcs' psi_full; 1]  (Ksysid.m:1614-1618); single group, slot = feature index
             const int s = tid & (LS - 1), fs = tid / LS;
             constexpr int NF = LT_THREADS / LS;
             const bool valid = g0 + s < a.M;
@@ -231,9 +235,8 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
             for (int i = fs; i < a.nv; i += NF) se[i * LS + s] = sh[i * LS + s];
             if (fs == 0) se[(a.nv + a.n_pcs) * LS + s] = valid ? 1.0 : 0.0;
             __syncthreads();
-            psi = se;
         }
-        // ---- C: stream the rows out, once
+        // ---- C: stream the stored rows out, once
         {
             constexpr int PS = LS / 2;                 // snapshot pairs per tile
             constexpr int NR = LT_THREADS / PS;
@@ -249,25 +252,102 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
             };
             if (ok0) {
                 double* base = a.out + (a.mode == 0 ? 0 : (long long)(side ? a.P : 0) * a.ld) + gs;
-                for (int j = rr; j < a.N; j += NR) {
-                    const double2 v = *reinterpret_cast<const double2*>(psi + j * LS + p2);
-                    put(base + (long long)j * a.ld, v.x, v.y);
-                }
-                if (a.mode == 1 && a.model == KF_LINEAR) {              // [psi, u]  (Ksysid.m:1062-1063)
-                    for (int i = rr; i < a.m; i += NR) put(base + (long long)(a.N + i) * a.ld, su[i * LS + p2], su[i * LS + p2 + 1]);
-                } else if (a.mode == 1 && a.model == KF_BILINEAR) {     // blocks u_k psi  (Ksysid.m:510-511)
-                    for (int k = 0; k < a.m; ++k) {
-                        const double u0 = su[k * LS + p2], u1 = su[k * LS + p2 + 1];
-                        double* bk = base + (long long)(k + 1) * a.N * a.ld;
-                        for (int j = rr; j < a.N; j += NR) {
-                            const double2 v = *reinterpret_cast<const double2*>(psi + j * LS + p2);
-                            put(bk + (long long)j * a.ld, KF_MUL(u0, v.x), KF_MUL(u1, v.y));
+                const bool direct = a.n_pcs > 0 || a.ngroups == 1;       // slot = output row = feature index
+                const int nrow = direct ? a.N : grp.nst;
+                const double* psi = a.n_pcs > 0 ? se : sh;
+                for (int e = rr; e < nrow; e += NR) {
+                    int slot = e, row = e;
+                    if (!direct) { const int2 sr = sst[e]; slot = sr.x; row = sr.y; }
+                    const double2 v = *reinterpret_cast<const double2*>(psi + slot * LS + p2);
+                    put(base + (long long)row * a.ld, v.x, v.y);
+                    if (a.mode == 1 && a.model == KF_BILINEAR) {       // blocks u_k psi  (Ksysid.m:510-511)
+                        for (int k = 0; k < a.m; ++k) {
+                            const double u0 = su[k * LS + p2], u1 = su[k * LS + p2 + 1];
+                            put(base + ((long long)(k + 1) * a.N + row) * a.ld, KF_MUL(u0, v.x), KF_MUL(u1, v.y));
                         }
                     }
+                }
+                if (a.mode == 1 && a.model == KF_LINEAR && g == 0) {   // [psi, u]  (Ksysid.m:1062-1063)
+                    for (int i = rr; i < a.m; i += NR) put(base + (long long)(a.N + i) * a.ld, su[i * LS + p2], su[i * LS + p2 + 1]);
                 }
             }
         }
         __syncthreads();
+    }
+}
+
+// Partition of the dictionary into dependency-closed feature groups of at most `max_slots` shared-memory slots
+// (one group with slot = feature index if everything fits, or for dim_red, whose projection needs all features).
+void lift_build_groups(const KfProgram& p, int max_slots, bool single, std::vector<LtOp>& gops, std::vector<int2>& gstore,
+                       std::vector<LtGroup>& groups) {
+    const int n = p.n_full(), nv = p.nv;
+    std::vector<int> depth(n, 0);
+    for (int j = 0; j < n; ++j) {
+        const KfOp& op = p.ops[j];
+        if (op.kind == KF_OP_MUL) {
+            const int da = op.a < nv ? -1 : depth[op.a], db = op.b < nv ? -1 : depth[op.b];
+            depth[j] = 1 + std::max(da, db);
+        }
+    }
+    auto parents = [&](int j, int* out) -> int {       // features an op reads (variables excluded: always resident)
+        const KfOp& op = p.ops[j];
+        int c = 0;
+        if (op.kind == KF_OP_MUL) { if (op.a >= nv) out[c++] = op.a; if (op.b >= nv) out[c++] = op.b; }
+        return c;
+    };
+    gops.clear(); gstore.clear(); groups.clear();
+    std::vector<char> in(n, 0);
+    std::vector<int> members, stack, add, slot(n, -1);
+    int j = 0;
+    while (j < n) {
+        // grow the group [j, j1) while its closure fits
+        std::fill(in.begin(), in.end(), 0);
+        members.clear();
+        int count = nv, j1 = j;
+        while (j1 < n) {
+            stack.assign(1, j1);
+            add.clear();
+            while (!stack.empty()) {                   // closure of feature j1 not yet in the group
+                const int f = stack.back(); stack.pop_back();
+                if (f < nv || in[f]) continue;
+                in[f] = 2; add.push_back(f);
+                int pr[2];
+                const int np = parents(f, pr);
+                for (int q = 0; q < np; ++q) stack.push_back(pr[q]);
+            }
+            if (!single && j1 > j && count + (int)add.size() > max_slots) {
+                for (int f : add) in[f] = 0;
+                break;
+            }
+            for (int f : add) { in[f] = 1; members.push_back(f); }
+            count += (int)add.size();
+            ++j1;
+        }
+        // evaluation order: by depth, then by feature index; slots: variables 0 .. nv-1, then in that order (or identity)
+        std::sort(members.begin(), members.end(), [&](int x, int y) { return depth[x] != depth[y] ? depth[x] < depth[y] : x < y; });
+        std::fill(slot.begin(), slot.end(), -1);
+        for (int v = 0; v < nv; ++v) slot[v] = v;
+        int next = nv;
+        for (int f : members) slot[f] = single ? f : next++;
+        LtGroup G{};
+        G.op_off = (int)gops.size(); G.st_off = (int)gstore.size();
+        G.nslots = single ? n : next;
+        int lev = -1;
+        for (int f : members) {
+            while (lev < depth[f]) { G.level_start[G.nlevels++] = (int)gops.size() - G.op_off; ++lev; }
+            const KfOp& op = p.ops[f];
+            LtOp o{op.kind, op.a, op.b, slot[f], op.c};
+            if (op.kind == KF_OP_MUL) { o.a = slot[op.a]; o.b = slot[op.b]; }
+            gops.push_back(o);
+        }
+        G.level_start[G.nlevels] = (int)gops.size() - G.op_off;
+        G.nops = (int)gops.size() - G.op_off;
+        if (groups.empty())
+            for (int v = 0; v < nv; ++v) gstore.push_back(make_int2(v, v));      // the variables are rows 0 .. nv-1 of psi
+        for (int f = std::max(j, nv); f < j1; ++f) gstore.push_back(make_int2(slot[f], f));
+        G.nst = (int)gstore.size() - G.st_off;
+        groups.push_back(G);
+        j = j1;
     }
 }
 
@@ -279,9 +359,10 @@ bool lift_tile_launch_ls(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, size_t smem
         return false;
     }
     const long long ntiles = (a.M + LS - 1) / LS;
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem + 1024, 1)));
-    const unsigned gx = (unsigned)std::min<long long>(ntiles, (long long)ctx->sm_count * per_sm);
-    kf_lift_tile_kernel<LS><<<dim3(gx, nsides), LT_THREADS, smem, st>>>(a);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / std::max<size_t>(smem + 1024, 1)));
+    const int rows = std::max(1, (ctx->sm_count * per_sm) / std::max(1, nsides * a.ngroups));
+    const unsigned gx = (unsigned)std::min<long long>(ntiles, (long long)rows);
+    kf_lift_tile_kernel<LS><<<dim3(gx, nsides * a.ngroups), LT_THREADS, smem, st>>>(a);
     if (cudaGetLastError() != cudaSuccess) { *rc = KF_ECUDA; ctx->err = "kf_lift_tile_kernel launch failed"; }
     ctx->launches += 1;
     return true;
@@ -291,14 +372,53 @@ bool lift_tile_launch(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, cudaStream_t s
     *rc = KF_OK;
     const int nlev = (int)ctx->level_start.size() - 1;
     if (nlev > LT_MAXLEV || a.M <= 0) return false;
-    for (int l = 0; l <= nlev; ++l) a.level_start[l] = ctx->level_start[l];
-    a.nlevels = nlev;
-    auto bytes = [&](int ls) {
-        return ((size_t)a.n_full + (size_t)a.m + (a.n_pcs > 0 ? (size_t)a.N : 0)) * ls * sizeof(double) + (size_t)a.n_full * sizeof(LtOp);
+    const KfProgram& p = ctx->prog;
+    auto bytes = [&](int ls, int slots, int ops, int nst) {
+        return ((size_t)slots + (size_t)a.m + (a.n_pcs > 0 ? (size_t)a.N : 0)) * ls * sizeof(double) + (size_t)ops * sizeof(LtOp) +
+               (size_t)nst * sizeof(int2) + 64;
     };
-    // 16 snapshots per tile (128-byte segments) while at least three CTAs fit an SM, else 8
-    if (bytes(16) <= 72 * 1024) return lift_tile_launch_ls<16>(ctx, a, nsides, bytes(16), st, rc);
-    if (bytes(8) <= 200 * 1024) return lift_tile_launch_ls<8>(ctx, a, nsides, bytes(8), st, rc);
+    // Tile width LS (snapshots per tile = contiguous bytes per output row / 8): the wider, the longer the contiguous runs the
+    // DRAM sees (128-byte runs scattered over GBs cap the write rate near 2.6 TB/s), but the fewer features fit a CTA, i.e.
+    // more dependency-closed groups.  Option lift_ls forces it; default 16.
+    int ls = ctx->opt_lift_ls;
+    if (ls != 8 && ls != 16 && ls != 32 && ls != 64) ls = 16;      // measured: 32 ties, 64 and 8 lose (profiles/r01_lift_only_bandwidth.json)
+    if (a.n_pcs > 0 && ls > 16) ls = 16;                 // dim_red needs every feature in one CTA
+    const int slots_target = std::max(p.nv + 8, (int)((56 * 1024) / (ls * sizeof(double))));
+    const bool single = a.n_pcs > 0 || bytes(ls, p.n_full(), p.n_full(), p.n_full()) <= 74 * 1024;
+    lift_build_groups(p, slots_target, single, ctx->lt_ops, ctx->lt_store, ctx->lt_groups);
+    a.ngroups = (int)ctx->lt_groups.size();
+    a.max_slots = a.max_ops = a.max_nst = 0;
+    for (const LtGroup& g : ctx->lt_groups) {
+        a.max_slots = std::max(a.max_slots, g.nslots);
+        a.max_ops = std::max(a.max_ops, g.nops);
+        a.max_nst = std::max(a.max_nst, g.nst);
+    }
+    const size_t nb_ops = ctx->lt_ops.size() * sizeof(LtOp), nb_st = ctx->lt_store.size() * sizeof(int2), nb_g = ctx->lt_groups.size() * sizeof(LtGroup);
+    const size_t o_st = (nb_ops + 15) & ~(size_t)15, o_g = (o_st + nb_st + 15) & ~(size_t)15;
+    if (ctx->d_lift_groups.ensure(o_g + nb_g) != cudaSuccess) { cudaGetLastError(); return false; }
+    char* base = ctx->d_lift_groups.as<char>();
+    cudaMemcpyAsync(base, ctx->lt_ops.data(), nb_ops, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(base + o_st, ctx->lt_store.data(), nb_st, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(base + o_g, ctx->lt_groups.data(), nb_g, cudaMemcpyHostToDevice, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) {     // the host vectors are reused by the next launch
+        *rc = KF_ECUDA;
+        ctx->err = "lift groups upload failed";
+        return true;
+    }
+    a.gops = reinterpret_cast<const LtOp*>(base);
+    a.gstore = reinterpret_cast<const int2*>(base + o_st);
+    a.groups = reinterpret_cast<const LtGroup*>(base + o_g);
+    for (;;) {
+        const size_t b = bytes(ls, a.max_slots, a.max_ops, a.max_nst);
+        if (b <= 200 * 1024) {
+            if (ls == 64) return lift_tile_launch_ls<64>(ctx, a, nsides, b, st, rc);
+            if (ls == 32) return lift_tile_launch_ls<32>(ctx, a, nsides, b, st, rc);
+            if (ls == 16) return lift_tile_launch_ls<16>(ctx, a, nsides, b, st, rc);
+            return lift_tile_launch_ls<8>(ctx, a, nsides, b, st, rc);
+        }
+        if (ls == 8) break;
+        ls /= 2;                                         // a single group (dim_red, or one huge closure) that does not fit: narrower tile
+    }
     return false;
 }
 

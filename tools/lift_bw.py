@@ -49,8 +49,9 @@ for name, types, degs, cen, nz, m, model, M in cases:
     o = torch.empty((2 * P, M), dtype=torch.float64, device=dev)
     alg = M * (8.0 * (2 * nz + m) + 16.0 * P)
     rec = {"case": name, "M": M, "N": N, "P": P, "algorithmic_bytes": alg, "output_GB": 16.0 * P * M / 1e9}
-    for tile in (1, 0):
+    for tile, ls in ((1, 0), (1, 16), (1, 32), (1, 64), (0, 0)):
         fit.set_option("lift_tile", tile)
+        fit.set_option("lift_ls", ls)
         for _ in range(3):
             fit.regressors_dev(basis, model, M, nz, m, a.data_ptr(), b.data_ptr(), u.data_ptr(), o.data_ptr())
         fit.sync()
@@ -63,7 +64,9 @@ for name, types, degs, cen, nz, m, model, M in cases:
             e1.record(st)
         fit.sync(); torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / reps
-        rec["tile_kernel" if tile else "level_kernel"] = {"ms": ms, "GB_s": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peak}
+        key = ("tile_kernel" if ls == 0 else f"tile_kernel_ls{ls}") if tile else "level_kernel"
+        rec[key] = {"ms": round(ms, 4), "GB_s": round(alg / ms / 1e6, 1), "frac_of_hbm_peak": round(alg / ms / 1e6 / peak, 4)}
+    fit.set_option("lift_ls", 0)
     fit.set_option("lift_tile", 1)
     print(rec, flush=True)
     out["cases"].append(rec)
