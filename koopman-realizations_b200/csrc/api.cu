@@ -634,6 +634,7 @@ void kf_destroy(kf_ctx* ctx) {
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,
                      &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups};
+    if (ctx->pchol_graph.exec) cudaGraphExecDestroy(ctx->pchol_graph.exec);
     for (KfBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -980,6 +981,7 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "as_frac") ctx->opt_as_frac = value;
     else if (n == "lift_tile") ctx->opt_lift_tile = (int)value;
     else if (n == "lift_ls") ctx->opt_lift_ls = (int)value;
+    else if (n == "graphs") ctx->opt_graphs = (int)value;
     else {
         ctx->err = "kf_set_option: unknown option " + n;
         return KF_EINVAL;

@@ -110,6 +110,17 @@ struct KfLayout {
     bool valid = false;
 };
 
+// the blocked pivoted Cholesky of kf_solve_gram_ls as an instantiated CUDA graph, valid for one set of buffers / sizes
+struct KfPcholGraph {
+    cudaGraphExec_t exec = nullptr;
+    const void *W = nullptr, *perm = nullptr, *dcur = nullptr, *state = nullptr;
+    int P = 0, Pp = 0;
+    double tol2 = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    double flops = 0;
+};
+
 struct kf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -156,6 +167,9 @@ struct kf_ctx {
     // largest dynamic shared-memory limit requested per kernel ON THIS CONTEXT'S DEVICE (the attribute is per device and
     // only ever grows: a smaller value would make a later, larger launch fail)
     std::map<const void*, size_t> smem_attr;
+
+    KfPcholGraph pchol_graph;
+    int opt_graphs = 1;       // replay the launch-bound pivoted-Cholesky loop as a CUDA graph
 
     // counters
     double dmma_flops = 0;

@@ -494,33 +494,67 @@ int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const dou
         KF_CUDA(ctx, ctx->d_K3.ensure((size_t)(4 * Pp + 8) * sizeof(double) + (size_t)(Pp + 4) * sizeof(int)));
         double* dcur = ctx->d_K3.as<double>();
         PcholStep* d_step = reinterpret_cast<PcholStep*>(d_state + 1);
-        for (int j0 = 0; j0 < P; j0 += PCHOL_NB) {
-            const int j1 = std::min(P, j0 + PCHOL_NB);
-            kf_pchol_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(W, ld, P, dcur);   // Schur diagonal at block start
-            for (int j = j0; j < j1; ++j) {
-                kf_pcholc_argmax_kernel<<<1, 1024, 0, st>>>(P, j, d_perm, dcur, d_state, d_step, tol2);
-                kf_pcholc_swap_kernel<<<(P + 255) / 256, 256, 0, st>>>(W, ld, P, j, d_step);
-                const int rem = P - j - 1;
-                kf_pcholc_col_kernel<<<std::max(1, (rem + 255) / 256), 256, 0, st>>>(W, ld, P, j, j0, dcur, d_step);
+        // The loop is launch-bound (3 tiny kernels per column + one DMMA update per block: ~6,000 launches at P = 4096, no
+        // host decision anywhere — pivots and ranks live in device state), so it is captured ONCE into a CUDA graph per
+        // (buffers, P, tolerance) and replayed by every later fit.
+        auto enqueue = [&]() -> int {
+            for (int j0 = 0; j0 < P; j0 += PCHOL_NB) {
+                const int j1 = std::min(P, j0 + PCHOL_NB);
+                kf_pchol_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(W, ld, P, dcur);   // Schur diagonal at block start
+                for (int j = j0; j < j1; ++j) {
+                    kf_pcholc_argmax_kernel<<<1, 1024, 0, st>>>(P, j, d_perm, dcur, d_state, d_step, tol2);
+                    kf_pcholc_swap_kernel<<<(P + 255) / 256, 256, 0, st>>>(W, ld, P, j, d_step);
+                    const int rem = P - j - 1;
+                    kf_pcholc_col_kernel<<<std::max(1, (rem + 255) / 256), 256, 0, st>>>(W, ld, P, j, j0, dcur, d_step);
+                }
+                ctx->launches += 1 + 3LL * (j1 - j0);
+                if (j1 < P) {
+                    KfGemmGrid g{};
+                    g.A = W + (long long)j1 * ld;   // A[m][c] = W(c, j1+m) = L(j1+m, c): mirrored copy, c contiguous
+                    g.lda = ld;
+                    g.B = W + (long long)j1 * ld;
+                    g.ldb = ld;
+                    g.out = W + (long long)j1 * ld + j1;   // out[m][n] = W(j1+m, j1+n)
+                    g.ldm = 1;
+                    g.ldn = ld;
+                    g.m = P - j1;
+                    g.n = P - j1;
+                    g.k0 = j0;
+                    g.k1 = j1;               // j1 - j0 = 64 for every block that has a trailing part
+                    g.alpha = -1.0;
+                    g.accumulate = 1;
+                    KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+                }
             }
-            ctx->launches += 1 + 3LL * (j1 - j0);
-            if (j1 < P) {
-                KfGemmGrid g{};
-                g.A = W + (long long)j1 * ld;   // A[m][c] = W(c, j1+m) = L(j1+m, c): mirrored copy, c contiguous
-                g.lda = ld;
-                g.B = W + (long long)j1 * ld;
-                g.ldb = ld;
-                g.out = W + (long long)j1 * ld + j1;   // out[m][n] = W(j1+m, j1+n)
-                g.ldm = 1;
-                g.ldn = ld;
-                g.m = P - j1;
-                g.n = P - j1;
-                g.k0 = j0;
-                g.k1 = j1;               // j1 - j0 = 64 for every block that has a trailing part
-                g.alpha = -1.0;
-                g.accumulate = 1;
-                KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+            return KF_OK;
+        };
+        KfPcholGraph& G = ctx->pchol_graph;
+        const bool same = G.exec && G.W == W && G.perm == d_perm && G.dcur == dcur && G.state == d_state && G.P == P && G.Pp == Pp &&
+                          G.tol2 == tol2 && G.stream == st;
+        if (!ctx->opt_graphs) {
+            KF_TRY(enqueue());
+        } else {
+            if (!same) {
+                if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+                const long long l0 = ctx->launches;
+                const double f0 = ctx->dmma_flops;
+                cudaGraph_t graph = nullptr;
+                KF_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                const int rc = enqueue();
+                const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                KF_CUDA(ctx, ce);
+                KF_CUDA(ctx, cudaGraphInstantiate(&G.exec, graph, 0));
+                cudaGraphDestroy(graph);
+                G.W = W; G.perm = d_perm; G.dcur = dcur; G.state = d_state; G.P = P; G.Pp = Pp; G.tol2 = tol2; G.stream = st;
+                G.launches = ctx->launches - l0;
+                G.flops = ctx->dmma_flops - f0;
+                ctx->launches = l0;                      // counted per replay below
+                ctx->dmma_flops = f0;
             }
+            KF_CUDA(ctx, cudaGraphLaunch(G.exec, st));
+            ctx->launches += G.launches;
+            ctx->dmma_flops += G.flops;
         }
     }
     KF_CUDA(ctx, cudaGetLastError());
