@@ -56,16 +56,6 @@ struct KfTmaTask {
     const double* W;           // weight row (global pointer) or nullptr = unweighted
 };
 
-// ------------------------------------------------------------------ feature groups of the materialising lift (lift.cu)
-constexpr int KF_LT_MAXLEV = 32;
-struct LtOp { int kind, a, b, j; double c; };      // op of a group in level order; a, b, j are SLOTS (GAUSS: a = centre column)
-struct LtGroup {
-    int op_off, nops;                  // ops of the group in the global op array
-    int st_off, nst;                   // stored features: (slot, output row) pairs
-    int nslots, nlevels;
-    int level_start[KF_LT_MAXLEV + 1]; // offsets into the group's ops
-};
-
 // ------------------------------------------------------------------ device buffer
 struct KfBuf {
     void* p = nullptr;
@@ -156,7 +146,7 @@ struct kf_ctx {
 
     // host staging of the lift feature groups (kept alive across the asynchronous upload)
     std::vector<LtOp> lt_ops;
-    std::vector<int2> lt_store;
+    std::vector<LtStore> lt_store;
     std::vector<LtGroup> lt_groups;
 
     // column partition of the active-set QP solver across ranks (kf_set_qp_partition)

@@ -133,7 +133,7 @@ constexpr int LT_SLOTS = 440;      // target size of a feature group (shared-mem
 // parents (cheap products).
 struct KfLiftTileArgs {
     const KfOp* ops; const double* centres; const double* pcs; const int* order;   // ops / order: unused by the tile kernel
-    const LtOp* gops; const int2* gstore; const LtGroup* groups; int ngroups;
+    const LtOp* gops; const LtStore* gstore; const LtGroup* groups; int ngroups;
     int nv, n_full, n_pcs, N;          // N = lifted dimension (n_full, or nv + n_pcs + 1 with dim_red)
     int nzeta, m, model;
     int mode;                           // 0: points V -> Psi (rows x N);  1: regressors [Px | Py] (M x 2P)
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
     double* su = sh + (size_t)a.max_slots * LS;        // [m][LS]   inputs u of the tile
     double* se = su + (size_t)a.m * LS;                // [N][LS]   econ features (dim_red only, single group)
     LtOp* sop = reinterpret_cast<LtOp*>(se + (a.n_pcs > 0 ? (size_t)a.N * LS : 0));   // [max_ops] in level order
-    int2* sst = reinterpret_cast<int2*>(sop + a.max_ops);                             // [max_nst] (slot, output row)
+    LtStore* sst = reinterpret_cast<LtStore*>(sop + a.max_ops);                       // [max_nst] (slot, output row)
     __shared__ LtGroup grp;
     const int tid = threadIdx.x;
     const int side = blockIdx.y / a.ngroups, g = blockIdx.y % a.ngroups;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
                 const double* psi = a.n_pcs > 0 ? se : sh;
                 for (int e = rr; e < nrow; e += NR) {
                     int slot = e, row = e;
-                    if (!direct) { const int2 sr = sst[e]; slot = sr.x; row = sr.y; }
+                    if (!direct) { const LtStore sr = sst[e]; slot = sr.slot; row = sr.row; }
                     const double2 v = *reinterpret_cast<const double2*>(psi + slot * LS + p2);
                     put(base + (long long)row * a.ld, v.x, v.y);
                     if (a.mode == 1 && a.model == KF_BILINEAR) {       // blocks u_k psi  (Ksysid.m:510-511)
@@ -273,81 +273,6 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
             }
         }
         __syncthreads();
-    }
-}
-
-// Partition of the dictionary into dependency-closed feature groups of at most `max_slots` shared-memory slots
-// (one group with slot = feature index if everything fits, or for dim_red, whose projection needs all features).
-void lift_build_groups(const KfProgram& p, int max_slots, bool single, std::vector<LtOp>& gops, std::vector<int2>& gstore,
-                       std::vector<LtGroup>& groups) {
-    const int n = p.n_full(), nv = p.nv;
-    std::vector<int> depth(n, 0);
-    for (int j = 0; j < n; ++j) {
-        const KfOp& op = p.ops[j];
-        if (op.kind == KF_OP_MUL) {
-            const int da = op.a < nv ? -1 : depth[op.a], db = op.b < nv ? -1 : depth[op.b];
-            depth[j] = 1 + std::max(da, db);
-        }
-    }
-    auto parents = [&](int j, int* out) -> int {       // features an op reads (variables excluded: always resident)
-        const KfOp& op = p.ops[j];
-        int c = 0;
-        if (op.kind == KF_OP_MUL) { if (op.a >= nv) out[c++] = op.a; if (op.b >= nv) out[c++] = op.b; }
-        return c;
-    };
-    gops.clear(); gstore.clear(); groups.clear();
-    std::vector<char> in(n, 0);
-    std::vector<int> members, stack, add, slot(n, -1);
-    int j = 0;
-    while (j < n) {
-        // grow the group [j, j1) while its closure fits
-        std::fill(in.begin(), in.end(), 0);
-        members.clear();
-        int count = nv, j1 = j;
-        while (j1 < n) {
-            stack.assign(1, j1);
-            add.clear();
-            while (!stack.empty()) {                   // closure of feature j1 not yet in the group
-                const int f = stack.back(); stack.pop_back();
-                if (f < nv || in[f]) continue;
-                in[f] = 2; add.push_back(f);
-                int pr[2];
-                const int np = parents(f, pr);
-                for (int q = 0; q < np; ++q) stack.push_back(pr[q]);
-            }
-            if (!single && j1 > j && count + (int)add.size() > max_slots) {
-                for (int f : add) in[f] = 0;
-                break;
-            }
-            for (int f : add) { in[f] = 1; members.push_back(f); }
-            count += (int)add.size();
-            ++j1;
-        }
-        // evaluation order: by depth, then by feature index; slots: variables 0 .. nv-1, then in that order (or identity)
-        std::sort(members.begin(), members.end(), [&](int x, int y) { return depth[x] != depth[y] ? depth[x] < depth[y] : x < y; });
-        std::fill(slot.begin(), slot.end(), -1);
-        for (int v = 0; v < nv; ++v) slot[v] = v;
-        int next = nv;
-        for (int f : members) slot[f] = single ? f : next++;
-        LtGroup G{};
-        G.op_off = (int)gops.size(); G.st_off = (int)gstore.size();
-        G.nslots = single ? n : next;
-        int lev = -1;
-        for (int f : members) {
-            while (lev < depth[f]) { G.level_start[G.nlevels++] = (int)gops.size() - G.op_off; ++lev; }
-            const KfOp& op = p.ops[f];
-            LtOp o{op.kind, op.a, op.b, slot[f], op.c};
-            if (op.kind == KF_OP_MUL) { o.a = slot[op.a]; o.b = slot[op.b]; }
-            gops.push_back(o);
-        }
-        G.level_start[G.nlevels] = (int)gops.size() - G.op_off;
-        G.nops = (int)gops.size() - G.op_off;
-        if (groups.empty())
-            for (int v = 0; v < nv; ++v) gstore.push_back(make_int2(v, v));      // the variables are rows 0 .. nv-1 of psi
-        for (int f = std::max(j, nv); f < j1; ++f) gstore.push_back(make_int2(slot[f], f));
-        G.nst = (int)gstore.size() - G.st_off;
-        groups.push_back(G);
-        j = j1;
     }
 }
 
@@ -375,7 +300,7 @@ bool lift_tile_launch(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, cudaStream_t s
     const KfProgram& p = ctx->prog;
     auto bytes = [&](int ls, int slots, int ops, int nst) {
         return ((size_t)slots + (size_t)a.m + (a.n_pcs > 0 ? (size_t)a.N : 0)) * ls * sizeof(double) + (size_t)ops * sizeof(LtOp) +
-               (size_t)nst * sizeof(int2) + 64;
+               (size_t)nst * sizeof(LtStore) + 64;
     };
     // Tile width LS (snapshots per tile = contiguous bytes per output row / 8): the wider, the longer the contiguous runs the
     // DRAM sees (128-byte runs scattered over GBs cap the write rate near 2.6 TB/s), but the fewer features fit a CTA, i.e.
@@ -385,7 +310,7 @@ bool lift_tile_launch(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, cudaStream_t s
     if (a.n_pcs > 0 && ls > 16) ls = 16;                 // dim_red needs every feature in one CTA
     const int slots_target = std::max(p.nv + 8, (int)((56 * 1024) / (ls * sizeof(double))));
     const bool single = a.n_pcs > 0 || bytes(ls, p.n_full(), p.n_full(), p.n_full()) <= 74 * 1024;
-    lift_build_groups(p, slots_target, single, ctx->lt_ops, ctx->lt_store, ctx->lt_groups);
+    if (!kf_build_lift_groups(p, slots_target, single, ctx->lt_ops, ctx->lt_store, ctx->lt_groups)) return false;
     a.ngroups = (int)ctx->lt_groups.size();
     a.max_slots = a.max_ops = a.max_nst = 0;
     for (const LtGroup& g : ctx->lt_groups) {
@@ -393,7 +318,7 @@ bool lift_tile_launch(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, cudaStream_t s
         a.max_ops = std::max(a.max_ops, g.nops);
         a.max_nst = std::max(a.max_nst, g.nst);
     }
-    const size_t nb_ops = ctx->lt_ops.size() * sizeof(LtOp), nb_st = ctx->lt_store.size() * sizeof(int2), nb_g = ctx->lt_groups.size() * sizeof(LtGroup);
+    const size_t nb_ops = ctx->lt_ops.size() * sizeof(LtOp), nb_st = ctx->lt_store.size() * sizeof(LtStore), nb_g = ctx->lt_groups.size() * sizeof(LtGroup);
     const size_t o_st = (nb_ops + 15) & ~(size_t)15, o_g = (o_st + nb_st + 15) & ~(size_t)15;
     if (ctx->d_lift_groups.ensure(o_g + nb_g) != cudaSuccess) { cudaGetLastError(); return false; }
     char* base = ctx->d_lift_groups.as<char>();
@@ -406,7 +331,7 @@ bool lift_tile_launch(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, cudaStream_t s
         return true;
     }
     a.gops = reinterpret_cast<const LtOp*>(base);
-    a.gstore = reinterpret_cast<const int2*>(base + o_st);
+    a.gstore = reinterpret_cast<const LtStore*>(base + o_st);
     a.groups = reinterpret_cast<const LtGroup*>(base + o_g);
     for (;;) {
         const size_t b = bytes(ls, a.max_slots, a.max_ops, a.max_nst);

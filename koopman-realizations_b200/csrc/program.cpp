@@ -1,6 +1,8 @@
 // Host-side compiler: kf_basis -> KfProgram.  See program.h for the semantics.
 #include "program.h"
 
+#include <algorithm>
+
 #include <cmath>
 #include <map>
 
@@ -177,3 +179,84 @@ int kf_build_program(const kf_basis* basis, KfProgram& prog, std::string& err) {
     }
     return KF_OK;
 }
+
+// Partition of the dictionary into dependency-closed feature groups of at most `max_slots` shared-memory slots
+// (one group with slot = feature index if everything fits, or for dim_red, whose projection needs all features).
+bool kf_build_lift_groups(const KfProgram& p, int max_slots, bool single, std::vector<LtOp>& gops, std::vector<LtStore>& gstore,
+                          std::vector<LtGroup>& groups) {
+    const int n = p.n_full(), nv = p.nv;
+    std::vector<int> depth(n, 0);
+    for (int j = 0; j < n; ++j) {
+        const KfOp& op = p.ops[j];
+        if (op.kind == KF_OP_MUL) {
+            const int da = op.a < nv ? -1 : depth[op.a], db = op.b < nv ? -1 : depth[op.b];
+            depth[j] = 1 + std::max(da, db);
+        }
+    }
+    auto parents = [&](int j, int* out) -> int {       // features an op reads (variables excluded: always resident)
+        const KfOp& op = p.ops[j];
+        int c = 0;
+        if (op.kind == KF_OP_MUL) { if (op.a >= nv) out[c++] = op.a; if (op.b >= nv) out[c++] = op.b; }
+        return c;
+    };
+    gops.clear(); gstore.clear(); groups.clear();
+    std::vector<char> in(n, 0);
+    std::vector<int> members, stack, add, slot(n, -1);
+    int j = 0;
+    while (j < n) {
+        // grow the group [j, j1) while its closure fits
+        std::fill(in.begin(), in.end(), 0);
+        members.clear();
+        int count = nv, j1 = j;
+        while (j1 < n) {
+            stack.assign(1, j1);
+            add.clear();
+            while (!stack.empty()) {                   // closure of feature j1 not yet in the group
+                const int f = stack.back(); stack.pop_back();
+                if (f < nv || in[f]) continue;
+                in[f] = 2; add.push_back(f);
+                int pr[2];
+                const int np = parents(f, pr);
+                for (int q = 0; q < np; ++q) stack.push_back(pr[q]);
+            }
+            if (!single && j1 > j && count + (int)add.size() > max_slots) {
+                for (int f : add) in[f] = 0;
+                break;
+            }
+            for (int f : add) { in[f] = 1; members.push_back(f); }
+            count += (int)add.size();
+            ++j1;
+        }
+        // evaluation order: by depth, then by feature index; slots: variables 0 .. nv-1, then in that order (or identity)
+        std::sort(members.begin(), members.end(), [&](int x, int y) { return depth[x] != depth[y] ? depth[x] < depth[y] : x < y; });
+        std::fill(slot.begin(), slot.end(), -1);
+        for (int v = 0; v < nv; ++v) slot[v] = v;
+        int next = nv;
+        for (int f : members) slot[f] = single ? f : next++;
+        LtGroup G{};
+        G.op_off = (int)gops.size(); G.st_off = (int)gstore.size();
+        G.nslots = single ? n : next;
+        int lev = -1;
+        for (int f : members) {
+            while (lev < depth[f]) {
+                if (G.nlevels >= KF_LT_MAXLEV) return false;
+                G.level_start[G.nlevels++] = (int)gops.size() - G.op_off;
+                ++lev;
+            }
+            const KfOp& op = p.ops[f];
+            LtOp o{op.kind, op.a, op.b, slot[f], op.c};
+            if (op.kind == KF_OP_MUL) { o.a = slot[op.a]; o.b = slot[op.b]; }
+            gops.push_back(o);
+        }
+        G.level_start[G.nlevels] = (int)gops.size() - G.op_off;
+        G.nops = (int)gops.size() - G.op_off;
+        if (groups.empty())
+            for (int v = 0; v < nv; ++v) gstore.push_back(LtStore{v, v});      // the variables are rows 0 .. nv-1 of psi
+        for (int f = std::max(j, nv); f < j1; ++f) gstore.push_back(LtStore{slot[f], f});
+        G.nst = (int)gstore.size() - G.st_off;
+        groups.push_back(G);
+        j = j1;
+    }
+    return true;
+}
+

@@ -33,6 +33,22 @@ struct KfProgram {
     int N() const { return n_pcs ? nv + n_pcs + 1 : n_full(); }
 };
 
+// ---- feature groups of the materialising lift (lift.cu): a contiguous range of output features plus everything they
+// depend on (their dependency closure), renumbered into compact slots; slots 0 .. nv-1 are always the variables.
+constexpr int KF_LT_MAXLEV = 32;
+struct LtOp { int kind, a, b, j; double c; };      // op of a group in level order; a, b, j are SLOTS (GAUSS: a = centre column)
+struct LtStore { int slot, row; };                 // a stored feature: slot in the group, output row = feature index
+struct LtGroup {
+    int op_off, nops;                  // ops of the group in the global op array
+    int st_off, nst;                   // stored features in the global store array
+    int nslots, nlevels;
+    int level_start[KF_LT_MAXLEV + 1]; // offsets into the group's ops; a level only reads slots written by earlier levels
+};
+// Partition into groups of at most max_slots slots (single: one group with slot = feature index, whatever its size).
+// Returns false if a dependency chain is deeper than KF_LT_MAXLEV levels.
+bool kf_build_lift_groups(const KfProgram& p, int max_slots, bool single, std::vector<LtOp>& gops, std::vector<LtStore>& gstore,
+                          std::vector<LtGroup>& groups);
+
 // rows of partitions(total, ones(1,nvars)) in the reference's order, appended to `out` (row-major)
 void kf_partitions_ones(int total, int nvars, std::vector<int>& out);
 

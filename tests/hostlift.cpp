@@ -47,3 +47,56 @@ extern "C" int hostlift_full(const kf_basis* basis, long long rows, const double
     }
     return 0;
 }
+
+// The lift evaluated GROUP by group exactly as kf_lift_tile_kernel does (slots, level order, store lists), with the
+// invariants checked on the way: an op only reads slots written by the variables or an EARLIER level of its own group,
+// every group stays within max_slots (unless it is a single feature's closure), every feature is stored exactly once.
+// Returns 0, or a negative code naming the violated invariant.  out: rows x n_full column-major.
+extern "C" int hostlift_groups(const kf_basis* basis, int max_slots, int single, long long rows, const double* V, double* out,
+                               int* ngroups, int* max_used) {
+    KfProgram prog;
+    std::string err;
+    int rc = kf_build_program(basis, prog, err);
+    if (rc) return rc;
+    std::vector<LtOp> gops;
+    std::vector<LtStore> gstore;
+    std::vector<LtGroup> groups;
+    if (!kf_build_lift_groups(prog, max_slots, single != 0, gops, gstore, groups)) return -1;
+    const int nf = prog.n_full(), nv = prog.nv;
+    std::vector<int> stored(nf, 0);
+    *ngroups = (int)groups.size();
+    *max_used = 0;
+    for (const LtGroup& g : groups) {
+        if (g.nslots > *max_used) *max_used = g.nslots;
+        std::vector<int> wlevel(g.nslots, 1 << 30);          // level at which a slot becomes readable
+        for (int v = 0; v < nv; ++v) wlevel[v] = -1;
+        for (int l = 0; l < g.nlevels; ++l)
+            for (int e = g.level_start[l]; e < g.level_start[l + 1]; ++e) {
+                const LtOp& op = gops[g.op_off + e];
+                if (op.j < nv || op.j >= g.nslots) return -2;
+                if (op.kind == KF_OP_MUL && (wlevel[op.a] >= l || wlevel[op.b] >= l)) return -3;
+                if ((op.kind == KF_OP_COS || op.kind == KF_OP_SIN || op.kind == KF_OP_HERM || op.kind == KF_OP_VAR) && op.a >= nv) return -4;
+                wlevel[op.j] = l;
+            }
+        if (g.level_start[g.nlevels] != g.nops) return -5;
+        for (int e = 0; e < g.nst; ++e) {
+            const LtStore& sr = gstore[g.st_off + e];
+            if (sr.slot < 0 || sr.slot >= g.nslots || sr.row < 0 || sr.row >= nf || wlevel[sr.slot] == (1 << 30)) return -6;
+            stored[sr.row] += 1;
+        }
+        std::vector<double> sh(g.nslots);
+        for (long long s = 0; s < rows; ++s) {
+            for (int i = 0; i < nv; ++i) sh[i] = V[(size_t)i * rows + s];
+            for (int e = 0; e < g.nops; ++e) {
+                const LtOp& op = gops[g.op_off + e];
+                KfOp o{};
+                o.kind = op.kind; o.a = op.a; o.b = op.b; o.c = op.c;
+                sh[op.j] = kf_eval_op(o, nv, prog.centres.data(), [&](int k) { return sh[k]; });
+            }
+            for (int e = 0; e < g.nst; ++e) out[(size_t)gstore[g.st_off + e].row * rows + s] = sh[gstore[g.st_off + e].slot];
+        }
+    }
+    for (int j = 0; j < nf; ++j)
+        if (stored[j] != 1) return -7;
+    return 0;
+}

@@ -99,3 +99,36 @@ def test_no_cuda_device_fails_loudly():
         pytest.skip("GPU present")
     with pytest.raises(koopfit.KoopfitError):
         koopfit.Fitter(device=0)
+
+
+@pytest.mark.parametrize("types,degs,nv,max_slots", [
+    (["poly"], [4], 8, 120), (["poly"], [3], 12, 64), (["poly", "gaussian"], [3, 569], 12, 440),
+    (["fourier"], [4], 3, 100), (["fourier_sparser"], [3], 4, 40), (["hermite", "poly"], [3, 2], 4, 30),
+    (["poly"], [13], 1, 6), (["gaussian"], [50], 5, 16),
+])
+def test_lift_feature_groups(hostlift, types, degs, nv, max_slots):
+    """The dependency-closed feature groups of the materialising lift (program.cpp:kf_build_lift_groups, evaluated on the host
+    exactly as kf_lift_tile_kernel does): operands are always written by an earlier level of the same group, every feature
+    is stored exactly once, groups respect the slot budget, and the group-wise evaluation reproduces the plain one bit for bit."""
+    rng = np.random.default_rng(1)
+    ng = sum(d for t, d in zip(types, degs) if t == "gaussian")
+    cen = 2 * rng.random((nv, ng)) - 1 if ng else None
+    b = A.Basis(types, degs, nv, centres=cen)
+    nf, N = C.c_int(), C.c_int()
+    assert hostlift.hostlift_dims(b.ref(), C.byref(nf), C.byref(N)) == 0
+    rows = 7
+    V = np.asfortranarray(2 * rng.random((rows, nv)) - 1)
+    plain = np.zeros((rows, nf.value), order="F")
+    assert hostlift.hostlift_full(b.ref(), C.c_longlong(rows), A.dptr(V), A.dptr(plain)) == 0
+    for single in (0, 1):
+        out = np.full((rows, nf.value), np.nan, order="F")
+        ngroups, used = C.c_int(), C.c_int()
+        rc = hostlift.hostlift_groups(b.ref(), max_slots, single, C.c_longlong(rows), A.dptr(V), A.dptr(out), C.byref(ngroups), C.byref(used))
+        assert rc == 0, rc
+        assert np.array_equal(out, plain)
+        if single:
+            assert ngroups.value == 1 and used.value == nf.value
+        else:
+            assert ngroups.value >= 1 and (used.value <= max_slots or ngroups.value == nf.value - nv or used.value <= nv + 1 + 2 * max(degs))
+            if nf.value > 4 * max_slots:
+                assert ngroups.value >= 2

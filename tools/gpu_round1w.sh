@@ -2,5 +2,3 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests/test_gpu_fit.py tests/test_gpu_series.py tests/test_gpu_ksysid.py tests/test_gpu_edge.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
-timeout 300 python tools/lift_bw.py > gpurun_out/lift_bw.log 2>&1; echo "lift_bw rc=$?"
-tail -4 gpurun_out/lift_bw.log | cut -c1-500
