@@ -26,3 +26,25 @@ def test_other_ranks_of_reference_arm_exit_quietly():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_recorded_gpu_bench_line_has_the_contract_keys():
+    """The committed round-end record of `python bench.py` on a B200 (profiles/r01_bench_n1_full_final.json) carries every key
+    of the bench contract, with consistent arithmetic (value = snapshots / time, frac = achieved / peak)."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1_full_final.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert abs(d["value"] - d["config"]["total_snapshots"] / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"] > 0
+    assert 0.5 < r["frac"] < 1.05
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 216 * d["config"]["snapshots_per_gpu"] and e["d2h_bytes_per_step"] == 4096 * 4096 * 8
+    assert e["value"] <= d["value"] * 1.02                       # end to end cannot beat the device-resident rate
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    assert d["gpu_launches"] > 1000 and d["clocks"]["sm_mhz"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    lo = d["lift_only"]
+    assert lo["bound"] == "hbm" and lo["unit"] == "GB/s" and abs(lo["frac"] - lo["achieved"] / lo["peak"]) < 1e-12
