@@ -122,12 +122,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         out.Py = mxGetPr(Py);
     }
     mxArray* obj = mxCreateDoubleMatrix(nt, 1, mxREAL);
+    mxArray* gap = mxCreateDoubleMatrix(nt, 1, mxREAL);   /* certified f(K) - f* per budget (kf_result.qp_gap) */
     out.objective = mxGetPr(obj);
+    out.qp_gap = mxGetPr(gap);
     if (kf_fit(g_ctx, &bs, &pr, &sv, &out)) mexErrMsgIdAndTxt("koopfit:fit", kf_last_error(g_ctx));
 
     if (nlhs > 1) {
-        const char* fn[] = {"rank", "ls_method_used", "psd_shift_applied", "min_pivot", "max_pivot", "t_lift_gram_ms", "t_solve_ms", "objective"};
-        plhs[1] = mxCreateStructMatrix(1, 1, 8, fn);
+        const char* fn[] = {"rank", "ls_method_used", "psd_shift_applied", "min_pivot", "max_pivot", "t_lift_gram_ms", "t_solve_ms", "objective",
+                            "qp_gap", "qp_capped"};
+        plhs[1] = mxCreateStructMatrix(1, 1, 10, fn);
         mxSetField(plhs[1], 0, "rank", mxCreateDoubleScalar(out.info.rank));
         mxSetField(plhs[1], 0, "ls_method_used", mxCreateDoubleScalar(out.info.ls_method_used));
         mxSetField(plhs[1], 0, "psd_shift_applied", mxCreateDoubleScalar(out.info.psd_shift_applied));
@@ -136,6 +139,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         mxSetField(plhs[1], 0, "t_lift_gram_ms", mxCreateDoubleScalar(out.info.t_lift_gram_ms));
         mxSetField(plhs[1], 0, "t_solve_ms", mxCreateDoubleScalar(out.info.t_solve_ms));
         mxSetField(plhs[1], 0, "objective", obj);
+        mxSetField(plhs[1], 0, "qp_gap", gap);
+        mxSetField(plhs[1], 0, "qp_capped", mxCreateDoubleScalar(out.info.qp_capped));
     }
     if (nlhs > 2) plhs[2] = Px ? Px : mxCreateDoubleMatrix(0, 0, mxREAL);
     if (nlhs > 3) plhs[3] = Py ? Py : mxCreateDoubleMatrix(0, 0, mxREAL);
