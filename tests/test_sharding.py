@@ -114,3 +114,68 @@ def test_qp_partition_hook_and_column_bounds():
         assert p.exitcode == 0
     for rank, v, w in out:
         assert np.array_equal(v, [3.0, 30.0, -6.0]) and np.array_equal(w, [1.0, 0.0])
+
+
+class _FakeFitter:
+    """Stands in for koopfit.Fitter in the column-split path: records the partition, calls the reduction hook the way the
+    library does, and 'solves' by filling only its own columns of a known K (K[i, j, b] = 1000 b + i + j / 1000)."""
+
+    def __init__(self):
+        self.options, self.lo, self.hi, self.hook = {}, 0, 0, None
+
+    def set_option(self, name, value):
+        self.options[name] = value
+
+    def set_qp_partition(self, lo, hi, allreduce=None):
+        self.lo, self.hi, self.hook = lo, hi, allreduce
+
+    def solve_dev(self, P, least_squares=False, t=None, **kw):
+        assert self.hi > self.lo and self.options.get("qp_method") == 2 and not least_squares
+        nt = len(t)
+        v = np.array([float(self.hi - self.lo), 1.0])
+        self.hook(v, 0)                                   # sum over ranks: total number of columns, number of ranks
+        assert v[0] == P
+        w = np.array([float(self.lo)])
+        self.hook(w, 1)                                   # max over ranks
+        K = np.zeros((P, P, nt), order="F")
+        i, j, b = np.meshgrid(np.arange(P), np.arange(self.lo, self.hi), np.arange(nt), indexing="ij")
+        K[:, self.lo:self.hi, :] = 1000.0 * b + i + j / 1000.0
+        return {"K_all": K, "K": K[:, :, 0], "objective": np.arange(nt, dtype=float), "l1norm": np.ones(nt), "qp_gap": np.zeros(nt),
+                "qp_iters": np.ones(nt, dtype=np.int32), "info": {"qp_capped": 0, "nranks": int(v[1]), "max_lo": float(w[0])}}
+
+
+def _split_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from koopfit.sharding import _solve_column_split, column_bounds
+    P, budgets = 11, np.array([1.0, 2.0, 3.0])
+    f = _FakeFitter()
+    res = _solve_column_split(f, P, budgets, rank, world, torch.device("cpu"), None)
+    q.put((rank, res["K_all"], res["info"], (f.lo, f.hi), f.options.get("qp_method"), column_bounds(P, rank, world)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_column_split_gathers_the_column_blocks():
+    """sharding._solve_column_split on a world_size-2 gloo group with a fake fitter: every rank solves its own column block
+    (uneven: 6 + 5 of 11 columns), the hook reduces across ranks, and every rank ends up with the complete K for all budgets;
+    the partition and the solver choice are switched off again afterwards."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_split_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    P, nt = 11, 3
+    i, j, b = np.meshgrid(np.arange(P), np.arange(P), np.arange(nt), indexing="ij")
+    want = 1000.0 * b + i + j / 1000.0
+    for rank, K_all, info, part, method, bounds in out:
+        assert np.array_equal(K_all, want)
+        assert info["nranks"] == 2 and info["max_lo"] == 6.0
+        assert part == (0, 0) and method == 0              # restored
+        assert bounds == ((0, 6) if rank == 0 else (6, 11))
