@@ -24,11 +24,14 @@
 extern "C" {
 #endif
 
-#define KF_VERSION 100
+#define KF_VERSION 200
 
 typedef struct kf_ctx kf_ctx;
 
-enum { KF_OK = 0, KF_EINVAL = 1, KF_ECUDA = 2, KF_ENOMEM = 3, KF_ENUMERIC = 4, KF_EUNSUPPORTED = 5 };
+enum { KF_OK = 0, KF_EINVAL = 1, KF_ECUDA = 2, KF_ENOMEM = 3, KF_ENUMERIC = 4, KF_EUNSUPPORTED = 5,
+       KF_EAGAIN = 6,   /* staged API only: kf_solve_dev needs ANOTHER data pass over the shard (ill-conditioned regressor, see
+                           kf_solve_dev); not an error */
+       KF_ECOMM = 7 };  /* NCCL failure */
 
 /* obj.model_type (Ksysid.m:96-104) */
 enum { KF_LINEAR = 0, KF_BILINEAR = 1, KF_NONLINEAR = 2 };
@@ -99,6 +102,10 @@ typedef struct {
     int qp_capped;          /* QP: coordinate-descent evaluations that hit the sweep bound / active-set budgets that did not
                                settle (0 = all converged; kf_result.qp_gap tells how far off the returned K can be) */
     int reserved;
+    double cond_est;        /* KF_LS_GRAM: max/min accepted |R_jj| of the first factorisation, a lower bound of cond(Px(:,basic));
+                               above the "refine_kappa" option (1e3) the Gram route re-orthogonalises with extra data passes */
+    int refine_passes;      /* KF_LS_GRAM: extra data passes of the multi-level pivoted Cholesky-QR refinement (0: one pass) */
+    int refine_capped;      /* 1: the refinement hit its level limit before the basis was well conditioned (K is best effort) */
 } kf_info;
 
 /* caller-allocated outputs; NULL members are skipped */
@@ -220,7 +227,14 @@ int kf_set_qp_partition(kf_ctx* ctx, int col_lo, int col_hi, kf_allreduce_fn all
  *   reset!=0 zeroes the accumulator first.  Asynchronous on the context stream.
  * kf_accum_buffer: the packed partial-Gram accumulator [G-tiles | C-tiles] to be
  *   summed across ranks (ncclAllReduce(sum, double) by the caller, e.g. torch.distributed).
- * kf_solve_dev: solve from the (reduced) accumulator; outputs to HOST pointers in `out`. */
+ * kf_solve_dev: solve from the (reduced) accumulator; outputs to HOST pointers in `out`.
+ *   Least squares on an ill-conditioned regressor (kf_info.cond_est above the "refine_kappa" option): the Gram route squares
+ *   the condition number, so it re-orthogonalises with extra data passes (multi-level pivoted Cholesky-QR: every pass lifts the
+ *   shard again, applies the basis change found so far and accumulates the Gram of the NEW features).  kf_solve_dev then returns
+ *   KF_EAGAIN and the caller repeats, with the SAME shard(s):
+ *       kf_accumulate_dev(ctx, basis, prob, 0);  [all-reduce kf_accum_buffer across ranks];  kf_solve_dev(ctx, solve, out);
+ *   until it returns KF_OK (usually after one extra pass).  Every rank takes the same decisions (they all factor the same
+ *   reduced matrices).  kf_fit / kf_fit_series / kf_fit_multi run this loop internally. */
 int kf_accumulate_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, int reset);
 /* Lift-only mode on DEVICE buffers (asynchronous on the context stream): the materialised regressors [Px | Py]
  * (Ksysid.m:1019-1065; M x 2P column-major, leading dimension ld >= M) of the device snapshot pairs in `prob`, and
@@ -243,7 +257,9 @@ int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, dou
  *   tensor-map TMA = 1 / cp.async = 0), "profile" (sample Gram-kernel durations), "qr_max_gb" (KF_LS_AUTO takes the QRCP route
  *   up to this size of [Px | Py]), "qp_method" (0 auto: coordinate descent for P <= 256, exact active set above; 1; 2),
  *   "as_frac" (active set: bound on the pattern change per step, fraction of the support, default 0.05, self-tuning downwards),
- *   "as_ws_gb" (active set: bound on the factor workspace), "lift_tile" (materialising lift: shared-memory tile kernel = 1) */
+ *   "as_ws_gb" (active set: bound on the factor workspace), "lift_tile" (materialising lift: shared-memory tile kernel = 1),
+ *   "refine" (Gram-route refinement: 0 off, 1 adaptive = default, 2 always at least one extra pass), "refine_kappa" (pivot-ratio
+ *   threshold, default 1e3), "refine_level_tol" (dynamic range one level resolves, default 1e-5), "refine_max" (level limit, 4) */
 int kf_set_option(kf_ctx* ctx, const char* name, double value);
 
 #ifdef __cplusplus

@@ -21,7 +21,8 @@ OBS_CODE = {"poly": KF_POLY, "fourier": KF_FOURIER, "fourier_sparser": KF_FOURIE
             "gaussian": KF_GAUSSIAN, "hermite": KF_HERMITE}
 KF_LS_AUTO, KF_LS_GRAM, KF_LS_QR = 0, 1, 2
 KF_PSD_AS_REFERENCE, KF_PSD_NEVER, KF_PSD_ALWAYS = 0, 1, 2
-ERRORS = {1: "KF_EINVAL", 2: "KF_ECUDA", 3: "KF_ENOMEM", 4: "KF_ENUMERIC", 5: "KF_EUNSUPPORTED"}
+KF_EAGAIN, KF_ECOMM = 6, 7
+ERRORS = {1: "KF_EINVAL", 2: "KF_ECUDA", 3: "KF_ENOMEM", 4: "KF_ENUMERIC", 5: "KF_EUNSUPPORTED", 6: "KF_EAGAIN", 7: "KF_ECOMM"}
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -53,7 +54,8 @@ class kf_info(C.Structure):
     _fields_ = [("rank", C.c_int), ("ls_method_used", C.c_int), ("passes", C.c_int),
                 ("psd_shift_applied", C.c_int), ("min_pivot", C.c_double), ("max_pivot", C.c_double),
                 ("t_lift_gram_ms", C.c_double), ("t_solve_ms", C.c_double), ("t_total_ms", C.c_double),
-                ("qp_capped", C.c_int), ("reserved", C.c_int)]
+                ("qp_capped", C.c_int), ("reserved", C.c_int), ("cond_est", C.c_double),
+                ("refine_passes", C.c_int), ("refine_capped", C.c_int)]
 
 
 class kf_result(C.Structure):

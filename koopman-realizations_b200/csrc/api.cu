@@ -113,6 +113,7 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
                 for (int tn = 0; tn < tn_end; ++tn) L.tiles.push_back(KfTile{1, q, a, b, tm, tn});
         }
     const int T = (int)L.tiles.size();
+    L.slab = (long long)T * KF_TILE_ELEMS + KF_ACC_TRAILER;
     const int ksteps = L.Mc / KF_BK;
     // split-K so that small problems still fill the machine: aim at ~2 waves of 2 CTAs per SM
     const int ctas = T * (KF_BM / KF_CTA_M) * (KF_BN / KF_CTA_N);
@@ -129,7 +130,7 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
     }
     if (p.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * L.n_full * L.Mc * sizeof(double)));
     // two slab sets (one per chunk pipeline) x nsplit split-K slabs; folded into slab 0 by kf_reduce_slabs
-    KF_CUDA(ctx, ctx->d_accum.ensure((size_t)2 * nsplit * T * KF_TILE_ELEMS * sizeof(double)));
+    KF_CUDA(ctx, ctx->d_accum.ensure((size_t)2 * nsplit * L.slab * sizeof(double)));
     KF_CUDA(ctx, ctx->d_tilemeta.ensure(sizeof(KfTile) * T));
     KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tilemeta.p, L.tiles.data(), sizeof(KfTile) * T, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -153,7 +154,7 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
                         g.A = panel + (long long)(L.x_off + tl.tm * KF_BM + sm * KF_CTA_M) * L.Mc;
                         g.B = panel + (long long)((tl.kind == 0 ? L.x_off : L.y_off) + tl.tn * KF_BN + sn * KF_CTA_N) * L.Mc;
                         g.W = tl.q > 0 ? panel + (long long)(L.w_off + tl.q) * L.Mc : nullptr;
-                        g.out = ctx->d_accum.as<double>() + ((long long)(b * nsplit + s) * T + t) * KF_TILE_ELEMS +
+                        g.out = ctx->d_accum.as<double>() + (long long)(b * nsplit + s) * L.slab + (long long)t * KF_TILE_ELEMS +
                                 (long long)sm * KF_CTA_M * KF_BN + sn * KF_CTA_N;
                         g.lda = g.ldb = L.Mc;
                         g.ldm = KF_BN;
@@ -220,8 +221,9 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
         }
         KF_TRY(make_layout(ctx, pr));
         const KfLayout& L = ctx->lay;
-        KF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)2 * L.nsplit * L.tiles.size() * KF_TILE_ELEMS * sizeof(double), ctx->stream));
+        KF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)2 * L.nsplit * L.slab * sizeof(double), ctx->stream));
         ctx->accum_M = 0;
+        ctx->rf.pending = false;
     }
     const KfLayout& L = ctx->lay;
     const KfProgram& p = ctx->prog;
@@ -292,7 +294,17 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
 
 int finish_accum(kf_ctx* ctx) {
     const KfLayout& L = ctx->lay;
-    KF_TRY(kf_reduce_slabs(ctx, ctx->d_accum.as<double>(), (long long)L.tiles.size() * KF_TILE_ELEMS, 2 * L.nsplit, ctx->stream));
+    KF_TRY(kf_reduce_slabs(ctx, ctx->d_accum.as<double>(), L.slab, 2 * L.nsplit, ctx->stream));
+    return KF_OK;
+}
+
+// the snapshot count of this rank into the trailer of slab 0: the all-reduce of the packed accumulator then also sums it, so
+// every rank knows the total M (MATLAB's rank tolerance max(size(Px)) * eps(|R11|) needs it) without a second collective
+int write_trailer(kf_ctx* ctx) {
+    const KfLayout& L = ctx->lay;
+    ctx->accum_M_d = (double)ctx->accum_M;
+    KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_accum.as<double>() + (L.slab - KF_ACC_TRAILER), &ctx->accum_M_d, sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->stream));
     return KF_OK;
 }
 
@@ -300,6 +312,214 @@ int copy_out_matrix(kf_ctx* ctx, const double* d, int Pp, int P, double* h, int 
     if (!h) return KF_OK;
     KF_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)P * sizeof(double), d, (size_t)Pp * sizeof(double), (size_t)P * sizeof(double),
                                    ncols < 0 ? P : ncols, cudaMemcpyDeviceToHost, ctx->stream));
+    return KF_OK;
+}
+
+KfLiftArgs lift_args_of(kf_ctx* ctx, const kf_problem* pr) {
+    KfLiftArgs a{};
+    const KfProgram& p = ctx->prog;
+    a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
+    a.order = ctx->d_order.as<int>();
+    a.nv = p.nv; a.n_full = p.n_full(); a.n_pcs = p.n_pcs; a.N = p.N();
+    a.nzeta = pr->nzeta; a.m = pr->m; a.model = pr->model;
+    a.alpha = pr->alpha; a.beta = pr->beta; a.u = pr->u; a.M = pr->M;
+    return a;
+}
+
+double eps_of(double x) {   // MATLAB eps(x): spacing of doubles at |x|
+    x = std::fabs(x);
+    if (!(x > 0) || !std::isfinite(x)) return std::ldexp(1.0, -1074);
+    int e = 0;
+    std::frexp(x, &e);      // x = f * 2^e, f in [0.5, 1)
+    return std::ldexp(1.0, e - 53);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gram-route refinement: one more data pass over a shard (device pointers in `pr`).  The regressors of a chunk are
+// materialised feature-major ([Px | Py] rows x Mc snapshots, L2-resident), transformed by the current basis,
+//     Z = S Px            (DMMA, B operand k-major: kf_launch_gemm_bkmajor),
+// and the Gram / cross products of the NEW features are accumulated:  G2 += Z Z',  C2 += Z Py'.  Z has an almost
+// orthonormal leading block and small residual columns behind it, so G2 carries the information that the plain Gram
+// G = Px'Px loses to cond(Px)^2 * eps  (Ksysid.m:1069 solves by QR and never squares the condition number).
+int refine_pass(kf_ctx* ctx, const kf_problem* pr) {
+    KF_TRY(check_problem(ctx, pr));
+    KfRefine& R = ctx->rf;
+    const KfLayout& L = ctx->lay;
+    if (!L.valid || !R.pending || !same_layout(L, ctx->prog, pr, 0)) {
+        ctx->err = "refinement pass: no pending refinement for this problem layout";
+        return KF_EINVAL;
+    }
+    cudaStream_t st = ctx->stream;
+    const int P = L.P, Pp = L.Pp, Mc = R.Mc;
+    const long long rp_rows = 2LL * P + KF_BM;          // rows [0,P) Px, [P,2P) Py, finite padding behind (k range runs to Pp)
+    const bool fresh = ctx->rf.d_RP.bytes < (size_t)rp_rows * Mc * sizeof(double);
+    KF_CUDA(ctx, R.d_RP.ensure((size_t)rp_rows * Mc * sizeof(double)));
+    KF_CUDA(ctx, R.d_Z.ensure((size_t)Pp * Mc * sizeof(double)));
+    if (fresh) KF_CUDA(ctx, cudaMemsetAsync(R.d_RP.p, 0, (size_t)rp_rows * Mc * sizeof(double), st));
+    if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * ctx->prog.n_full() * Mc * sizeof(double)));
+    double* RP = R.d_RP.as<double>();
+    double* Z = R.d_Z.as<double>();
+    double* G2 = R.d_G2C2.as<double>();
+    double* C2 = G2 + (size_t)Pp * Pp;
+    const long long nchunks = (pr->M + Mc - 1) / Mc;
+    for (long long c = 0; c < nchunks; ++c) {
+        const long long count = std::min<long long>(Mc, pr->M - c * Mc);
+        if (count < Mc) KF_CUDA(ctx, cudaMemsetAsync(RP, 0, (size_t)2 * P * Mc * sizeof(double), st));   // tail columns contribute zeros
+        KfLiftArgs a = lift_args_of(ctx, pr);
+        a.start = c * Mc;
+        a.Mc = Mc;
+        a.full = ctx->d_full.as<double>();
+        KF_TRY(kf_launch_regressors(ctx, a, RP, nullptr, Mc, st));
+        KfGemmGrid g{};
+        g.A = R.d_St.as<double>(); g.lda = Pp;           // A[q][i] = S(q, i): row q of S contiguous in i (= S' column-major)
+        g.B = RP; g.ldb = Mc;                            // B[i][snapshot]
+        g.out = Z; g.ldm = Mc; g.ldn = 1;
+        g.m = P; g.n = Mc; g.k0 = 0; g.k1 = Pp; g.alpha = 1.0; g.accumulate = 0;
+        KF_TRY(kf_launch_gemm_bkmajor(ctx, g, st));
+        KfGemmGrid gg{};                                 // G2(m, n) += sum_s Z[m][s] Z[n][s], lower tiles
+        gg.A = Z; gg.B = Z; gg.lda = gg.ldb = Mc; gg.out = G2; gg.ldm = 1; gg.ldn = Pp;
+        gg.m = P; gg.n = P; gg.k0 = 0; gg.k1 = Mc; gg.alpha = 1.0; gg.accumulate = 1; gg.lower_only = 1;
+        KF_TRY(kf_launch_gemm_grid(ctx, gg, st));
+        KfGemmGrid gc{};                                 // C2(m, n) += sum_s Z[m][s] Py[n][s]
+        gc.A = Z; gc.B = RP + (size_t)P * Mc; gc.lda = gc.ldb = Mc; gc.out = C2; gc.ldm = 1; gc.ldn = Pp;
+        gc.m = P; gc.n = L.Pc; gc.k0 = 0; gc.k1 = Mc; gc.alpha = 1.0; gc.accumulate = 1;
+        KF_TRY(kf_launch_gemm_grid(ctx, gc, st));
+    }
+    return KF_OK;
+}
+
+// start / continue the refinement after a factorisation (W = factor, not cleaned; d_perm its pivot order, r its rank)
+int refine_advance(kf_ctx* ctx, int P, int Pp, int r, const int* d_perm) {
+    KfRefine& R = ctx->rf;
+    cudaStream_t st = ctx->stream;
+    const size_t mat = (size_t)Pp * Pp * sizeof(double);
+    KF_CUDA(ctx, R.d_S.ensure(mat));
+    KF_CUDA(ctx, R.d_St.ensure(mat));
+    KF_CUDA(ctx, R.d_Sp.ensure(mat));
+    KF_CUDA(ctx, R.d_G2C2.ensure(2 * mat));
+    if (R.level == 0) {
+        KF_TRY(kf_rf_identity(ctx, R.d_S.as<double>(), P, Pp, st));
+        R.orig.resize(P);
+        for (int i = 0; i < P; ++i) R.orig[i] = i;
+    }
+    KF_TRY(kf_rf_update_basis(ctx, P, Pp, ctx->d_W.as<double>(), d_perm, r, R.d_S.as<double>(), R.d_Sp.as<double>(), st));
+    KF_TRY(kf_rf_transpose(ctx, R.d_S.as<double>(), R.d_St.as<double>(), Pp, st));
+    std::vector<int> perm(P), o2(P);
+    KF_CUDA(ctx, cudaMemcpyAsync(perm.data(), d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
+    KF_CUDA(ctx, cudaMemsetAsync(R.d_G2C2.p, 0, 2 * mat, st));
+    KF_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int j = 0; j < P; ++j) o2[j] = R.orig[perm[j]];
+    R.orig.swap(o2);
+    R.forced = r;
+    R.pending = true;
+    // chunk of a refinement pass: [Px | Py] rows + Z rows of Mc snapshots should stay L2-resident
+    long long Mc = (long long)(ctx->opt_panel_mb * 1048576.0 / (8.0 * (2.0 * P + Pp + KF_BM)));
+    Mc = std::max<long long>(256, std::min<long long>(Mc / 256 * 256, 8192));
+    R.Mc = (int)Mc;
+    return KF_OK;
+}
+
+// One step of the Gram-route least-squares solve (K = Px \ Py, Ksysid.m:1069) from the reduced matrices on the device.
+// Returns KF_OK with K (Pp x Pp, ld Pp, rows in ORIGINAL column order) in *K_out, or KF_EAGAIN when another data pass
+// (refine_pass over every shard + all-reduce of rf.d_G2C2) is needed first.
+int gram_ls_step(kf_ctx* ctx, const kf_solve* sv, kf_result* out, int* d_perm, double** K_out) {
+    const KfLayout& L = ctx->lay;
+    KfRefine& R = ctx->rf;
+    cudaStream_t st = ctx->stream;
+    const int P = L.P, Pp = L.Pp;
+    const size_t mat = (size_t)Pp * Pp * sizeof(double);
+    const double tol = sv->pivot_tol > 0 ? sv->pivot_tol : 1e-7;
+    const double ltol = ctx->opt_refine_level_tol;
+    std::vector<double> piv(P);
+    int rank = 0;
+    double minp = 0, maxp = 0, rej = -1;
+    auto ratio = [&](int a, int b) {   // max / min of the accepted pivots [a, b)
+        double lo = 0, hi = 0;
+        for (int j = a; j < b; ++j) {
+            lo = (j == a) ? piv[j] : std::min(lo, piv[j]);
+            hi = std::max(hi, piv[j]);
+        }
+        return (b > a && lo > 0) ? hi / lo : 1.0;
+    };
+    if (!R.pending) {
+        // ---- first factorisation: G itself
+        KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_W.p, ctx->d_G.p, mat, cudaMemcpyDeviceToDevice, st));
+        KF_TRY(kf_pchol_factor(ctx, P, Pp, ctx->d_W.as<double>(), tol, 0.0, 0, d_perm, &rank, &minp, &maxp, piv.data(), st, &rej));
+        const double kappa = ratio(0, rank);
+        R.level = 0;
+        R.cond_est = kappa;
+        R.r11 = maxp;
+        R.min_piv = minp;
+        out->info.cond_est = kappa;
+        out->info.max_pivot = maxp;
+        const bool refine = rank > 0 && (ctx->opt_refine == 2 || (ctx->opt_refine == 1 && kappa > ctx->opt_refine_kappa));
+        if (!refine) {
+            KF_TRY(kf_pchol_solve(ctx, P, Pp, L.Pc, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), d_perm, rank, 1, st));
+            out->info.rank = rank;
+            out->info.min_pivot = minp;
+            out->info.refine_passes = 0;
+            *K_out = ctx->d_K.as<double>();
+            return KF_OK;
+        }
+        // level 0 keeps the pivots within the level's dynamic range of |R_11|; the factor of that prefix is the one just
+        // computed unless the user tolerance let smaller pivots in
+        if (minp < ltol * maxp) {
+            KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_W.p, ctx->d_G.p, mat, cudaMemcpyDeviceToDevice, st));
+            KF_TRY(kf_pchol_factor(ctx, P, Pp, ctx->d_W.as<double>(), ltol, 0.0, 0, d_perm, &rank, &minp, &maxp, piv.data(), st, &rej));
+            R.min_piv = minp;
+        }
+        KF_TRY(refine_advance(ctx, P, Pp, rank, d_perm));
+        return KF_EAGAIN;
+    }
+    // ---- a refinement pass has been accumulated (and reduced): factor the Gram of the new features
+    double* G2 = R.d_G2C2.as<double>();
+    double* C2 = G2 + (size_t)Pp * Pp;
+    KF_TRY(kf_rf_symmetrize(ctx, G2, Pp, st));
+    KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_W.p, G2, mat, cudaMemcpyDeviceToDevice, st));
+    // rank tolerance of mldivide: |R_jj| <= max(size(Px)) * eps(|R_11|); an explicit pivot_tol stays a relative floor
+    const double mtol = (double)std::max<long long>(R.M_total, P) * eps_of(R.r11);
+    const double tolabs = std::max(mtol, sv->pivot_tol > 0 ? sv->pivot_tol * R.r11 : 0.0);
+    KF_TRY(kf_pchol_factor(ctx, P, Pp, ctx->d_W.as<double>(), ltol, tolabs, R.forced, d_perm, &rank, &minp, &maxp, piv.data(), st, &rej));
+    R.level += 1;
+    const double kp = ratio(0, R.forced), kr = ratio(R.forced, rank);
+    for (int j = R.forced; j < rank; ++j) R.min_piv = std::min(R.min_piv, piv[j]);   // residual pivots are true |R_jj|
+    // stopped at the level floor with candidates left above the rank tolerance: they need a level of their own
+    const bool unresolved = rank < P && rej > tolabs;
+    const bool converged = std::max(kp, kr) <= ctx->opt_refine_kappa && !unresolved;
+    if (!converged && R.level < ctx->opt_refine_max) {
+        KF_TRY(refine_advance(ctx, P, Pp, rank, d_perm));
+        return KF_EAGAIN;
+    }
+    // ---- solve in the new basis and map back:  K = (Pi S)' K_Z
+    KF_TRY(kf_rf_gather_rows(ctx, R.d_S.as<double>(), d_perm, P, Pp, R.d_Sp.as<double>(), st));
+    KF_TRY(kf_pchol_solve(ctx, P, Pp, L.Pc, ctx->d_W.as<double>(), C2, ctx->d_K.as<double>(), d_perm, rank, 0, st));
+    KF_CUDA(ctx, ctx->d_tmp.ensure(mat));
+    KF_CUDA(ctx, cudaMemsetAsync(ctx->d_tmp.p, 0, mat, st));
+    {
+        KfGemmGrid g{};
+        g.A = R.d_Sp.as<double>(); g.lda = Pp;           // A[i][j] = Sp(j, i): column i of Sp, j contiguous
+        g.B = ctx->d_K.as<double>(); g.ldb = Pp;         // B[c][j] = K_Z(j, c)
+        g.out = ctx->d_tmp.as<double>(); g.ldm = 1; g.ldn = Pp;
+        g.m = P; g.n = L.Pc; g.k0 = 0; g.k1 = (int)kf_roundup(rank, KF_BK); g.alpha = 1.0; g.accumulate = 0;
+        KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+    }
+    // pivot order in original column indices
+    {
+        std::vector<int> perm(P), o2(P);
+        KF_CUDA(ctx, cudaMemcpyAsync(perm.data(), d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int j = 0; j < P; ++j) o2[j] = R.orig[perm[j]];
+        KF_CUDA(ctx, cudaMemcpyAsync(d_perm, o2.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    out->info.rank = rank;
+    out->info.min_pivot = R.min_piv;
+    out->info.max_pivot = R.r11;
+    out->info.cond_est = R.cond_est;
+    out->info.refine_passes = R.level;
+    out->info.refine_capped = converged ? 0 : 1;
+    R.pending = false;
+    *K_out = ctx->d_tmp.as<double>();
     return KF_OK;
 }
 
@@ -319,10 +539,17 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
     KF_CUDA(ctx, ctx->d_W.ensure(mat));
     KF_CUDA(ctx, ctx->d_misc.ensure(4096));
     KF_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    KF_TRY(kf_assemble(ctx, ctx->d_accum.as<double>(), ctx->d_tilemeta.as<KfTile>(), (int)L.tiles.size(), L,
-                       ctx->d_G.as<double>(), ctx->d_C.as<double>(), st));
-    KF_TRY(copy_out_matrix(ctx, ctx->d_G.as<double>(), Pp, P, out->G));
-    KF_TRY(copy_out_matrix(ctx, ctx->d_C.as<double>(), Pp, P, out->C));
+    if (!ctx->rf.pending) {
+        KF_TRY(kf_assemble(ctx, ctx->d_accum.as<double>(), ctx->d_tilemeta.as<KfTile>(), (int)L.tiles.size(), L,
+                           ctx->d_G.as<double>(), ctx->d_C.as<double>(), st));
+        KF_TRY(copy_out_matrix(ctx, ctx->d_G.as<double>(), Pp, P, out->G));
+        KF_TRY(copy_out_matrix(ctx, ctx->d_C.as<double>(), Pp, P, out->C));
+        // total snapshot count: the trailer of the accumulator if it went through an all-reduce, else this rank's count
+        double tr = 0;
+        KF_CUDA(ctx, cudaMemcpyAsync(&tr, ctx->d_accum.as<double>() + (L.slab - KF_ACC_TRAILER), sizeof(double), cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->rf.M_total = tr >= 1.0 ? (long long)(tr + 0.5) : ctx->accum_M;
+    }
     if (!sv) {
         KF_CUDA(ctx, cudaStreamSynchronize(st));
         return KF_OK;
@@ -338,17 +565,19 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
             ctx->err = "kf_solve_dev: only KF_LS_GRAM can solve from the accumulator (KF_LS_QR needs the snapshots: use kf_fit)";
             return KF_EINVAL;
         }
-        KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_W.p, ctx->d_G.p, mat, cudaMemcpyDeviceToDevice, st));
-        const double tol = sv->pivot_tol > 0 ? sv->pivot_tol : 1e-7;
-        int rank = 0;
-        double minp = 0, maxp = 0;
-        KF_TRY(kf_solve_gram_ls(ctx, P, Pp, L.Pc, ctx->d_W.as<double>(), ctx->d_C.as<double>(), ctx->d_K.as<double>(), tol, d_perm,
-                                &rank, &minp, &maxp, st));
-        out->info.rank = rank;
+        double* Kdev = nullptr;
+        const int rc = gram_ls_step(ctx, sv, out, d_perm, &Kdev);
+        if (rc == KF_EAGAIN) {
+            float ms0 = 0.f;
+            KF_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+            KF_CUDA(ctx, cudaStreamSynchronize(st));
+            KF_CUDA(ctx, cudaEventElapsedTime(&ms0, ctx->ev[4], ctx->ev[5]));
+            out->info.t_solve_ms += ms0;
+            return KF_EAGAIN;
+        }
+        if (rc) return rc;
         out->info.ls_method_used = KF_LS_GRAM;
-        out->info.min_pivot = minp;
-        out->info.max_pivot = maxp;
-        KF_TRY(copy_out_matrix(ctx, ctx->d_K.as<double>(), Pp, P, out->K, L.Pc));
+        KF_TRY(copy_out_matrix(ctx, Kdev, Pp, P, out->K, L.Pc));
         if (out->perm) KF_CUDA(ctx, cudaMemcpyAsync(out->perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
     } else {
         if (sv->nt <= 0 || !sv->t) {
@@ -487,8 +716,8 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
     KF_CUDA(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
     KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
-    ctx->last_solve_ms = ms;
-    out->info.t_solve_ms = ms;
+    out->info.t_solve_ms += ms;
+    ctx->last_solve_ms = (float)out->info.t_solve_ms;
     return KF_OK;
 }
 
@@ -574,8 +803,24 @@ int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* sol
         kf_solve sv2 = *solve;
         if (sv2.least_squares) sv2.ls_method = KF_LS_GRAM;
         rc = solve_from_accum(ctx, &sv2, out);
+        // ill-conditioned regressor: extra data passes of the multi-level Cholesky-QR refinement (see gram_ls_step)
+        ctx->last_refine_ms = 0.f;
+        while (rc == KF_EAGAIN) {
+            KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+            rc = refine_pass(ctx, prob);
+            if (rc) break;
+            KF_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+            KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            float rms = 0.f;
+            KF_CUDA(ctx, cudaEventElapsedTime(&rms, ctx->ev[2], ctx->ev[3]));
+            ctx->last_refine_ms += rms;
+            out->info.t_lift_gram_ms += rms;
+            rc = solve_from_accum(ctx, &sv2, out);
+        }
+        out->info.passes = 1 + out->info.refine_passes;
     }
     ctx->lay.valid = false;
+    ctx->rf.pending = false;
     out->info.t_total_ms = now_ms() - t0;
     return rc;
 }
@@ -633,7 +878,8 @@ void kf_destroy(kf_ctx* ctx) {
     KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_full,
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,
-                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups};
+                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups,
+                     &ctx->rf.d_S, &ctx->rf.d_St, &ctx->rf.d_Sp, &ctx->rf.d_G2C2, &ctx->rf.d_RP, &ctx->rf.d_Z};
     if (ctx->pchol_graph.exec) cudaGraphExecDestroy(ctx->pchol_graph.exec);
     for (KfBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i)
@@ -698,6 +944,7 @@ int kf_lift(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V,
 int kf_accumulate_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, int reset) {
     if (!ctx) return KF_EINVAL;
     KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!reset && ctx->lay.valid && ctx->rf.pending) return refine_pass(ctx, prob);   // kf_solve_dev returned KF_EAGAIN
     if (reset || !ctx->lay.valid) KF_TRY(prepare_program(ctx, basis));
     return accumulate_dev(ctx, prob, reset != 0 || !ctx->lay.valid);
 }
@@ -734,9 +981,15 @@ int kf_lift_dev(kf_ctx* ctx, const kf_basis* basis, long long rows, const double
 int kf_accum_buffer(kf_ctx* ctx, double** dev_ptr, size_t* count) {
     if (!ctx || !ctx->lay.valid) return KF_EINVAL;
     KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->rf.pending) {         // a refinement pass: the Gram / cross products of the new features
+        if (dev_ptr) *dev_ptr = ctx->rf.d_G2C2.as<double>();
+        if (count) *count = (size_t)2 * ctx->lay.Pp * ctx->lay.Pp;
+        return KF_OK;
+    }
     KF_TRY(finish_accum(ctx));     // all slabs -> slab 0 (the folded slabs are zeroed, so this is idempotent)
+    KF_TRY(write_trailer(ctx));    // + this rank's snapshot count, summed by the same all-reduce
     if (dev_ptr) *dev_ptr = ctx->d_accum.as<double>();
-    if (count) *count = ctx->lay.tiles.size() * (size_t)KF_TILE_ELEMS;
+    if (count) *count = (size_t)ctx->lay.slab;
     return KF_OK;
 }
 
@@ -744,9 +997,15 @@ int kf_solve_dev(kf_ctx* ctx, const kf_solve* solve, kf_result* out) {
     if (!ctx || !out) return KF_EINVAL;
     KF_CUDA(ctx, cudaSetDevice(ctx->device));
     const double t0 = now_ms();
-    KF_TRY(finish_accum(ctx));
+    if (!ctx->rf.pending) {
+        std::memset(&out->info, 0, sizeof(out->info));
+        KF_TRY(finish_accum(ctx));
+    }
     int rc = solve_from_accum(ctx, solve, out);
+    if (rc == KF_EAGAIN) return rc;   // another data pass: kf_accumulate_dev(reset = 0), all-reduce kf_accum_buffer, call again
+    out->info.passes = 1 + out->info.refine_passes;
     ctx->lay.valid = false;        // accumulator consumed: the next accumulate must reset
+    ctx->rf.pending = false;
     out->info.t_total_ms = now_ms() - t0;
     return rc;
 }
@@ -959,7 +1218,7 @@ int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, dou
     if (lift_gram_ms) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_lift_gram_ms = ms;
-        *lift_gram_ms = ctx->last_lift_gram_ms;
+        *lift_gram_ms = ctx->last_lift_gram_ms + ctx->last_refine_ms;
     }
     if (gram_kernel_ms) *gram_kernel_ms = ctx->last_gram_kernel_ms;
     if (solve_ms) *solve_ms = ctx->last_solve_ms;
@@ -982,6 +1241,10 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "lift_tile") ctx->opt_lift_tile = (int)value;
     else if (n == "lift_ls") ctx->opt_lift_ls = (int)value;
     else if (n == "graphs") ctx->opt_graphs = (int)value;
+    else if (n == "refine") ctx->opt_refine = (int)value;
+    else if (n == "refine_kappa") ctx->opt_refine_kappa = value;
+    else if (n == "refine_level_tol") ctx->opt_refine_level_tol = value;
+    else if (n == "refine_max") ctx->opt_refine_max = (int)value;
     else {
         ctx->err = "kf_set_option: unknown option " + n;
         return KF_EINVAL;

@@ -49,6 +49,24 @@ __global__ void __launch_bounds__(KF_GEMM_THREADS, GramCfg::MINB) kf_gemm_grid_k
     kfg::gemm_tile_body<GramCfg, false, false>(t, kf_smem);
 }
 
+// out[m][n] (+)= alpha * sum_k A[m][k] * B[k][n], B k-major (gemm_kernel.cuh body 1b); n padded to a multiple of 64
+__global__ void __launch_bounds__(KF_GEMM_THREADS, GramCfg::MINB) kf_gemm_bkmajor_kernel(const KfGemmGrid g) {
+    extern __shared__ __align__(16) double kf_smem[];
+    const int tm = blockIdx.y, tn = blockIdx.x;
+    KfGemmTask t;
+    t.A = g.A + (long long)tm * KF_CTA_M * g.lda;
+    t.B = g.B + (long long)tn * KF_CTA_N;
+    t.W = nullptr;
+    t.out = g.out + (long long)tm * KF_CTA_M * g.ldm + (long long)tn * KF_CTA_N * g.ldn;
+    t.lda = g.lda; t.ldb = g.ldb; t.ldm = g.ldm; t.ldn = g.ldn;
+    t.k0 = g.k0; t.k1 = g.k1;
+    t.a_rows = min(KF_CTA_M, g.m - tm * KF_CTA_M);
+    t.b_rows = KF_CTA_N;
+    t.alpha = g.alpha;
+    t.accumulate = g.accumulate;
+    kfg::gemm_tile_body_bkmajor<GramCfg>(t, kf_smem);
+}
+
 // Gram kernel, TMA operand path (gemm_kernel.cuh body 3): tensor-map loads with SWIZZLE_128B + mbarrier ring.
 using TmaGramCfg = kfg::TmaCfg<4>;
 
@@ -71,6 +89,7 @@ cudaError_t ensure_attrs(kf_ctx* ctx) {
     if ((e = kf_ensure_smem(ctx, kf_gram_tile_kernel<false>, (size_t)GEMM_SMEM_BYTES)) != cudaSuccess) return e;
     if ((e = kf_ensure_smem(ctx, kf_gram_tile_kernel<true>, (size_t)GEMM_SMEM_BYTES)) != cudaSuccess) return e;
     if ((e = kf_ensure_smem(ctx, kf_gemm_grid_kernel, (size_t)GEMM_SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = kf_ensure_smem(ctx, kf_gemm_bkmajor_kernel, kfg::bkmajor_smem_bytes<GramCfg>())) != cudaSuccess) return e;
     if ((e = kf_ensure_smem(ctx, kf_gram_tma_kernel<false>, (size_t)TmaGramCfg::SMEM)) != cudaSuccess) return e;
     return kf_ensure_smem(ctx, kf_gram_tma_kernel<true>, (size_t)TmaGramCfg::SMEM);
 }
@@ -111,5 +130,21 @@ int kf_launch_gemm_grid(kf_ctx* ctx, const KfGemmGrid& g, cudaStream_t st) {
     double tiles = (double)grid.x * grid.y;
     if (g.lower_only) tiles *= 0.5;
     ctx->dmma_flops += tiles * 2.0 * KF_CTA_M * KF_CTA_N * (double)(g.k1 - g.k0);
+    return KF_OK;
+}
+
+// out[m][n] (+)= alpha * sum_{k in [k0,k1)} A[m * lda + k] * B[k * ldb + n]   (B k-major; n a multiple of 64, k0/k1 of 16)
+int kf_launch_gemm_bkmajor(kf_ctx* ctx, const KfGemmGrid& g, cudaStream_t st) {
+    if (g.m <= 0 || g.n <= 0 || g.k1 <= g.k0) return KF_OK;
+    if (g.n % KF_CTA_N || (g.k1 - g.k0) % KF_BK || (g.ldb & 1) || (reinterpret_cast<unsigned long long>(g.B) & 15ull)) {
+        ctx->err = "kf_launch_gemm_bkmajor: n must be a multiple of 64, the k range of 16, B 16-byte aligned with an even ld";
+        return KF_EINVAL;
+    }
+    KF_CUDA(ctx, ensure_attrs(ctx));
+    dim3 grid(g.n / KF_CTA_N, (g.m + KF_CTA_M - 1) / KF_CTA_M);
+    kf_gemm_bkmajor_kernel<<<grid, KF_GEMM_THREADS, kfg::bkmajor_smem_bytes<GramCfg>(), st>>>(g);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    ctx->dmma_flops += (double)grid.x * grid.y * 2.0 * KF_CTA_M * KF_CTA_N * (double)(g.k1 - g.k0);
     return KF_OK;
 }

@@ -212,6 +212,104 @@ __device__ __forceinline__ void gemm_tile_body(const KfGemmTask& t, double* smem
 }
 
 // ------------------------------------------------------------------------------------------------
+// Body 1b: same pipeline, but the B operand is K-MAJOR:  out[m][n] (+)= alpha * sum_k A[m][k] * B[k][n]  with B stored
+// B[k * ldb + n] (n contiguous) — a plain row-major "NN" product.  Used by the refinement pass of the Gram route
+// (solve.cu / api.cu): Z = S * Px, where the lifted panel Px is feature-major (row = feature k, column = snapshot n),
+// i.e. the contraction index is NOT contiguous in it.  B tile in shared memory: [BK][BN + 2] doubles; the lane (g, q) of a
+// DMMA needs B[k = 8 k2 + 2q (+1)][n = g]: rows 2q apart are 2 * 66 * 8 B = 32 B (mod 128) apart and g spans 32 B, so a
+// half-warp's LDS.64 hit 16 distinct 8-byte banks -> conflict-free.  Requires b_rows == BN (n padded by the caller).
+template <class C>
+__device__ __forceinline__ void gemm_tile_body_bkmajor(const KfGemmTask& t, double* smem) {
+    static_assert(C::VEC, "A fragments use the LDS.128 layout");
+    constexpr int BK = C::BK, STAGES = C::STAGES, LDSP = C::LDSP, MI = C::MI, NJ = C::NJ, BN = C::BN;
+    constexpr int LDN = BN + 2;
+    constexpr int B_STAGE = BK * LDN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / C::WN, wn = warp % C::WN;
+    double* As = smem;
+    double* Bs = smem + STAGES * C::A_STAGE;
+
+    constexpr int CPR = BK / 2;
+    const double* a_src[C::CHUNKS_A];
+    const int l_row = tid / CPR, l_kc = (tid % CPR) * 2;
+    constexpr int RSTEP = C::THREADS / CPR;
+#pragma unroll
+    for (int i = 0; i < C::CHUNKS_A; ++i) a_src[i] = t.A + (long long)min(l_row + i * RSTEP, t.a_rows - 1) * t.lda + l_kc;
+    const int s_off0 = l_row * LDSP + l_kc;
+    // B: BK rows x BN/2 sixteen-byte chunks per stage
+    constexpr int BCPR = BN / 2;
+    constexpr int CHUNKS_B = BK * BCPR / C::THREADS;
+    static_assert(BK * BCPR % C::THREADS == 0, "B loader mapping");
+    const int nk = (t.k1 - t.k0) / BK;
+
+    auto load_stage = [&](int stage, int kt) {
+        const int k = t.k0 + kt * BK;
+        double* as = As + stage * C::A_STAGE;
+        double* bs = Bs + stage * B_STAGE;
+#pragma unroll
+        for (int i = 0; i < C::CHUNKS_A; ++i) cp_async16(as + s_off0 + i * RSTEP * LDSP, a_src[i] + k);
+#pragma unroll
+        for (int i = 0; i < CHUNKS_B; ++i) {
+            const int c = tid + i * C::THREADS, kr = c / BCPR, nc = (c % BCPR) * 2;
+            cp_async16(bs + kr * LDN + nc, t.B + (long long)(k + kr) * t.ldb + nc);
+        }
+    };
+
+    double acc[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    const int g = lane >> 2, q = lane & 3;
+    const int a_row0 = wm * (C::BM / C::WM), b_row0 = wn * (BN / C::WN);
+    const int fra = g * LDSP + 2 * q;
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nxt = kt + STAGES - 1;
+            if (nxt < nk) load_stage(nxt % STAGES, nxt);
+            cp_async_commit();
+        }
+        const int stage = kt % STAGES;
+        const double* as = As + stage * C::A_STAGE + a_row0 * LDSP + fra;
+        const double* bs = Bs + stage * B_STAGE + b_row0 + g;
+#pragma unroll
+        for (int k2 = 0; k2 < BK / 8; ++k2) {
+            double2 a[MI];
+            double b0[NJ], b1[NJ];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const double2*>(as + i * 8 * LDSP + k2 * 8);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                b0[j] = bs[(k2 * 8 + 2 * q) * LDN + j * 8];
+                b1[j] = bs[(k2 * 8 + 2 * q + 1) * LDN + j * 8];
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b0[j]);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b1[j]);
+        }
+    }
+    cp_async_wait<0>();
+    store_tile<C>(t, acc, a_row0, b_row0, lane);
+}
+
+template <class C>
+constexpr size_t bkmajor_smem_bytes() {
+    return (size_t)C::STAGES * (C::A_STAGE + C::BK * (C::BN + 2)) * sizeof(double);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Body 2: TMA bulk-copy pipeline (cp.async.bulk, SASS UBLKCP) with mbarrier full/empty rings.
 // Warp 0 is the producer: it issues one 1-D bulk copy per operand row per stage (BK doubles = 128 B
 // into the padded shared row) and arms the stage's `full` barrier with the byte count; every warp

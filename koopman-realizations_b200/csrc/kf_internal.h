@@ -97,7 +97,26 @@ struct KfLayout {
     int nsplit = 1;           // split-K slabs
     std::vector<KfTile> tiles;
     int Pp = 0;               // P padded to BM: leading dimension of G, C, K work matrices
+    long long slab = 0;       // doubles per accumulator slab: tiles * 128 * 128 + KF_ACC_TRAILER (the trailer of slab 0 carries
+                              // the snapshot count through the all-reduce)
     bool valid = false;
+};
+constexpr int KF_ACC_TRAILER = 16;
+
+// state of the Gram-route refinement (multi-level pivoted Cholesky-QR; api.cu: gram_ls_step / refine_pass)
+struct KfRefine {
+    bool pending = false;     // the solve asked for another data pass; kf_accumulate_dev(reset = 0) then runs refine_pass
+    int level = 0;            // refinement passes done
+    int forced = 0;           // features accepted (and orthonormalised) so far
+    int Mc = 0;               // snapshots per chunk of a refinement pass
+    double r11 = 0;           // |R_11| of the first factorisation (MATLAB's rank tolerance refers to it)
+    double min_piv = 0;       // smallest accepted |R_jj| so far (true scale)
+    double cond_est = 0;
+    long long M_total = 0;    // snapshots over all ranks
+    std::vector<int> orig;    // original regressor column of feature j
+    KfBuf d_S, d_St, d_Sp;    // basis S (row = new feature, column = original; column-major), its transpose, Pi S
+    KfBuf d_G2C2;             // [G2 | C2] of the new features: what the ranks all-reduce in a refinement pass
+    KfBuf d_RP, d_Z;          // chunk panels: materialised [Px | Py] rows and the transformed features
 };
 
 // the blocked pivoted Cholesky of kf_solve_gram_ls as an instantiated CUDA graph, valid for one set of buffers / sizes
@@ -105,7 +124,6 @@ struct KfPcholGraph {
     cudaGraphExec_t exec = nullptr;
     const void *W = nullptr, *perm = nullptr, *dcur = nullptr, *state = nullptr;
     int P = 0, Pp = 0;
-    double tol2 = 0;
     cudaStream_t stream = nullptr;
     long long launches = 0;
     double flops = 0;
@@ -143,6 +161,12 @@ struct kf_ctx {
     int opt_lift_ls = 0;      // materialising lift: snapshots per tile (8 | 16 | 32 | 64; 0 = auto)
     int opt_lift_tile = 1;    // materialising lift: whole program per 16-snapshot tile in shared memory (0: level-by-level kernel)
     int opt_tma = 1;          // Gram kernel operand path: 1 = tensor-map TMA + mbarrier ring, 0 = per-thread cp.async
+    int opt_refine = 1;       // Gram-route refinement: 0 off, 1 adaptive, 2 always one extra pass
+    double opt_refine_kappa = 1e3;      // refine when the pivot ratio of the first factorisation exceeds this
+    double opt_refine_level_tol = 1e-5; // dynamic range of |R_jj| one level resolves (its square must stay well above eps)
+    int opt_refine_max = 4;   // level limit
+    KfRefine rf;
+    double accum_M_d = 0;     // accum_M as a double (source of the accumulator trailer upload)
 
     // host staging of the lift feature groups (kept alive across the asynchronous upload)
     std::vector<LtOp> lt_ops;
@@ -164,7 +188,7 @@ struct kf_ctx {
     // counters
     double dmma_flops = 0;
     long long launches = 0;
-    float last_lift_gram_ms = 0, last_gram_kernel_ms = 0, last_solve_ms = 0;
+    float last_lift_gram_ms = 0, last_gram_kernel_ms = 0, last_solve_ms = 0, last_refine_ms = 0;
     long long accum_M = 0;    // snapshots accumulated since reset
 };
 
@@ -209,6 +233,7 @@ struct KfGemmGrid {
     int lower_only;    // 1: skip tiles strictly above the diagonal (tn > tm)
 };
 int kf_launch_gemm_grid(kf_ctx* ctx, const KfGemmGrid& g, cudaStream_t st);
+int kf_launch_gemm_bkmajor(kf_ctx* ctx, const KfGemmGrid& g, cudaStream_t st);   // B stored k-major: B[k * ldb + n]
 
 // lift.cu
 struct KfLiftArgs {
@@ -240,6 +265,15 @@ int kf_assemble(kf_ctx* ctx, const double* accum, const KfTile* d_meta, int ntil
 // pivoted Cholesky basic solution of G K = C  (G, C, K: Pp x Pp column-major, ld = Pp)
 int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, int ncols, double* G_work, const double* C, double* K, double tol,
                      int* d_perm, int* rank_out, double* min_piv, double* max_piv, cudaStream_t st);
+int kf_pchol_factor(kf_ctx* ctx, int P, int Pp, double* W, double tol, double tolabs, int forced, int* d_perm, int* rank_out,
+                    double* min_piv, double* max_piv, double* pivots_host, cudaStream_t st, double* rejected_out);
+int kf_rf_identity(kf_ctx* ctx, double* S, int P, int Pp, cudaStream_t st);
+int kf_rf_symmetrize(kf_ctx* ctx, double* G, int Pp, cudaStream_t st);
+int kf_rf_transpose(kf_ctx* ctx, const double* A, double* At, int n, cudaStream_t st);
+int kf_rf_gather_rows(kf_ctx* ctx, const double* S, const int* d_perm, int P, int Pp, double* Sp, cudaStream_t st);
+int kf_rf_update_basis(kf_ctx* ctx, int P, int Pp, double* W, const int* d_perm, int r, double* S, double* Sp_out, cudaStream_t st);
+int kf_pchol_solve(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const double* C, double* K, const int* d_perm, int r, int scatter,
+                   cudaStream_t st);
 // Householder QRCP basic solution of A X = B;  AB = [A | B] (M x (P+Pc), ld = ldab) is overwritten
 int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long long ldab, double* X, long long ldx,
                    int* d_perm, int* rank_out, double* min_piv, double* max_piv, cudaStream_t st);

@@ -93,20 +93,20 @@ __global__ void __launch_bounds__(LIFT_THREADS) kf_lift_econ_kernel(const KfLift
 // Complete materialised regressors AB = [Px | Py] (M x 2P, ld): columns [0,N) and [P,P+N)
 // already hold psi(x), psi(y).  linear: append u to both (Ksysid.m:1062-1063); bilinear:
 // blocks u_k * psi (Ksysid.m:510-511).
-__global__ void kf_regressor_post_kernel(int model, int N, int P, int m, const double* __restrict__ u, long long M,
+__global__ void kf_regressor_post_kernel(int model, int N, int P, int m, const double* __restrict__ u, long long M, long long ldu,
                                          double* AB, long long ld) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= M) return;
     if (model == KF_LINEAR) {
         for (int i = 0; i < m; ++i) {
-            const double ui = u[(long long)i * M + s];
+            const double ui = u[(long long)i * ldu + s];
             AB[(long long)(N + i) * ld + s] = ui;
             AB[(long long)(P + N + i) * ld + s] = ui;
         }
     } else if (model == KF_BILINEAR) {
         const int j0 = blockIdx.y * 64;
         for (int k = 0; k < m; ++k) {
-            const double uk = u[(long long)k * M + s];
+            const double uk = u[(long long)k * ldu + s];
             for (int j = j0; j < min(N, j0 + 64); ++j) {
                 AB[(long long)((k + 1) * N + j) * ld + s] = KF_MUL(uk, AB[(long long)j * ld + s]);
                 AB[(long long)(P + (k + 1) * N + j) * ld + s] = KF_MUL(uk, AB[(long long)(P + j) * ld + s]);
@@ -139,7 +139,8 @@ struct KfLiftTileArgs {
     int mode;                           // 0: points V -> Psi (rows x N);  1: regressors [Px | Py] (M x 2P)
     int P;
     int max_slots, max_ops, max_nst;
-    const double* alpha; const double* beta; const double* u; long long M;
+    const double* alpha; const double* beta; const double* u; long long M;   // M = points of this launch
+    long long ldin;                     // leading dimension of alpha / beta / u (>= M; a chunk of a longer column)
     double* out; long long ld;
 };
 
@@ -184,8 +185,8 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
             const long long gs = g0 + s;
             double v = 0.0;
             if (gs < a.M) {
-                if (k < a.nv) v = k < a.nzeta ? src[(long long)k * a.M + gs] : a.u[(long long)(k - a.nzeta) * a.M + gs];
-                else v = a.u[(long long)(k - a.nv) * a.M + gs];
+                if (k < a.nv) v = k < a.nzeta ? src[(long long)k * a.ldin + gs] : a.u[(long long)(k - a.nzeta) * a.ldin + gs];
+                else v = a.u[(long long)(k - a.nv) * a.ldin + gs];
             }
             if (k < a.nv) sh[k * LS + s] = v; else su[(k - a.nv) * LS + s] = v;
         }
@@ -401,7 +402,7 @@ int kf_launch_lift_points(kf_ctx* ctx, const KfOp* ops, const double* centres, c
         t.ops = ops; t.centres = centres; t.pcs = pcs; t.order = ctx->d_order.as<int>();
         t.nv = nv; t.n_full = n_full; t.n_pcs = n_pcs; t.N = n_pcs ? nv + n_pcs + 1 : n_full;
         t.nzeta = nv; t.m = 0; t.model = KF_NONLINEAR; t.mode = 0; t.P = t.N;
-        t.alpha = V; t.beta = V; t.u = V; t.M = rows; t.out = out; t.ld = ldo;
+        t.alpha = V; t.beta = V; t.u = V; t.M = rows; t.ldin = rows; t.out = out; t.ld = ldo;
         int rc = KF_OK;
         if (lift_tile_launch(ctx, t, 1, st, &rc)) return rc;
     }
@@ -421,24 +422,28 @@ int kf_launch_lift_points(kf_ctx* ctx, const KfOp* ops, const double* centres, c
     return kf_launch_lift(ctx, a, st);
 }
 
+// Materialised regressors of the snapshots [a0.start, a0.start + count) (count = min(a0.Mc, a0.M - a0.start); a0.Mc <= 0: all):
+// psi(x) -> columns [0,N), psi(y) -> columns [P, P+N) of AB (ld = ldp >= count), plus the u / u (x) psi columns.
 int kf_launch_regressors(kf_ctx* ctx, const KfLiftArgs& a0, double* AB, double* /*unused*/, long long ldp,
                          cudaStream_t st) {
-    // psi(x) -> columns [0,N), psi(y) -> columns [P, P+N) of AB (ld = ldp >= M); whole data set at once
     KfLiftArgs a = a0;
+    if (a.Mc <= 0) { a.start = 0; a.Mc = (int)a.M; }
+    const long long count = std::min<long long>(a.Mc, a.M - a.start);
+    if (count <= 0) return KF_OK;
     const int P = kf_regressor_width(a.model, a.N, a.m);
     if (ctx->opt_lift_tile) {
         KfLiftTileArgs t{};
         t.ops = a.ops; t.centres = a.centres; t.pcs = a.pcs; t.order = a.order;
         t.nv = a.nv; t.n_full = a.n_full; t.n_pcs = a.n_pcs; t.N = a.N;
         t.nzeta = a.nzeta; t.m = a.m; t.model = a.model; t.mode = 1; t.P = P;
-        t.alpha = a.alpha; t.beta = a.beta; t.u = a.u; t.M = a.M; t.out = AB; t.ld = ldp;
+        t.alpha = a.alpha + a.start; t.beta = a.beta + a.start; t.u = a.u ? a.u + a.start : a.u; t.M = count; t.ldin = a.M;
+        t.out = AB; t.ld = ldp;
         int rc = KF_OK;
         if (lift_tile_launch(ctx, t, 2, st, &rc)) return rc;
     }
     a.panel = AB;
     a.ld = ldp;
-    a.start = 0;
-    a.Mc = (int)a.M;
+    a.Mc = (int)count;
     a.x_off = 0;
     a.y_off = P;
     a.nW = 0;
@@ -447,8 +452,8 @@ int kf_launch_regressors(kf_ctx* ctx, const KfLiftArgs& a0, double* AB, double* 
     a.extras = 0;
     KF_TRY(kf_launch_lift(ctx, a, st));
     if (a.model != KF_NONLINEAR) {
-        dim3 grid((unsigned)((a.M + 127) / 128), a.model == KF_BILINEAR ? (a.N + 63) / 64 : 1);
-        kf_regressor_post_kernel<<<grid, 128, 0, st>>>(a.model, a.N, P, a.m, a.u, a.M, AB, ldp);
+        dim3 grid((unsigned)((count + 127) / 128), a.model == KF_BILINEAR ? (a.N + 63) / 64 : 1);
+        kf_regressor_post_kernel<<<grid, 128, 0, st>>>(a.model, a.N, P, a.m, a.u + a.start, count, a.M, AB, ldp);
         KF_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     }

@@ -80,11 +80,19 @@ struct PcholState {
     double minpiv;   // smallest accepted pivot
     int rank;
     int done;
+    // parameters (written by the host before the factorisation; the kernels only read them, so one captured graph
+    // serves every tolerance and every forced prefix)
+    double tol2;     // relative tolerance^2 against `ref`
+    double tolabs2;  // absolute tolerance^2 (0: none)
+    double ref;      // the pivot the relative tolerance refers to: the first FREE pivot (column `forced`)
+    int forced;      // the first `forced` columns are taken in their given order (no search, no swap)
+    int pad;
+    double rejected; // the pivot candidate the factorisation stopped at (-1: none, every column was accepted)
 };
 
 // one CTA: pick the largest remaining diagonal, symmetric swap j<->p, scale column/row j
 __global__ void __launch_bounds__(1024) kf_pchol_pivot_kernel(double* W, long long ld, int P, int j, int* perm,
-                                                              PcholState* st, double tol2) {
+                                                              PcholState* st, double* pivots) {
     if (st->done) return;
     __shared__ double sval[32];
     __shared__ int sidx[32];
@@ -93,7 +101,8 @@ __global__ void __launch_bounds__(1024) kf_pchol_pivot_kernel(double* W, long lo
     const int tid = threadIdx.x;
     double best = -1.0;
     int bi = P;
-    for (int i = j + tid; i < P; i += blockDim.x) {
+    const int jend = (j < st->forced) ? j + 1 : P;   // forced prefix: column j itself
+    for (int i = j + tid; i < jend; i += blockDim.x) {
         const double v = W[(long long)i * ld + i];
         if (v > best || (v == best && i < bi)) { best = v; bi = i; }
     }
@@ -114,10 +123,14 @@ __global__ void __launch_bounds__(1024) kf_pchol_pivot_kernel(double* W, long lo
         }
         if (tid == 0) {
             if (j == 0) st->piv0 = best;
-            const bool ok = (best > 0.0) && (best > tol2 * st->piv0);   // false for NaN as well
+            if (j == st->forced) st->ref = best;
+            // a forced column only has to be positive; a free one must clear both tolerances (false for NaN as well)
+            const bool ok = (best > 0.0) && (j < st->forced || (best > st->tol2 * st->ref && best > st->tolabs2));
+            if (ok && pivots) pivots[j] = best;
             if (!ok) {
                 st->rank = j;
                 st->done = 1;
+                st->rejected = best;
                 s_p = -1;
             } else {
                 s_p = bi;
@@ -195,7 +208,7 @@ __global__ void kf_pchol_diag_kernel(const double* __restrict__ W, long long ld,
 }
 
 __global__ void __launch_bounds__(1024) kf_pcholc_argmax_kernel(int P, int j, int* perm, double* dcur, PcholState* st,
-                                                                PcholStep* step, double tol2) {
+                                                                PcholStep* step, double* pivots) {
     if (st->done) {
         if (threadIdx.x == 0) step->p = -1;
         return;
@@ -205,7 +218,8 @@ __global__ void __launch_bounds__(1024) kf_pcholc_argmax_kernel(int P, int j, in
     const int tid = threadIdx.x;
     double best = -1.0;
     int bi = P;
-    for (int i = j + tid; i < P; i += blockDim.x) {
+    const int jend = (j < st->forced) ? j + 1 : P;   // forced prefix: column j itself
+    for (int i = j + tid; i < jend; i += blockDim.x) {
         const double v = dcur[i];
         if (v > best || (v == best && i < bi)) { best = v; bi = i; }
     }
@@ -226,10 +240,13 @@ __global__ void __launch_bounds__(1024) kf_pcholc_argmax_kernel(int P, int j, in
         }
         if (tid == 0) {
             if (j == 0) st->piv0 = best;
-            const bool ok = (best > 0.0) && (best > tol2 * st->piv0);
+            if (j == st->forced) st->ref = best;
+            const bool ok = (best > 0.0) && (j < st->forced || (best > st->tol2 * st->ref && best > st->tolabs2));
+            if (ok && pivots) pivots[j] = best;
             if (!ok) {
                 st->rank = j;
                 st->done = 1;
+                st->rejected = best;
                 step->p = -1;
             } else {
                 step->p = bi;
@@ -403,16 +420,13 @@ int kf_assemble(kf_ctx* ctx, const double* accum, const KfTile* d_meta, int ntil
     return KF_OK;
 }
 
-// blocked triangular solves  L Z = X, L' X = Z  on the leading rank x rank factor in W
-static int trsm_both(kf_ctx* ctx, const double* W, long long ld, int P, int rank_hint, const int* d_rank, double* X,
-                     long long ldx, int ncols, cudaStream_t st) {
-    // rank_hint: host copy of the rank (bounds the block loops)
+// blocked forward substitution  L Z = X  on the leading r x r factor in W (mirrored storage), X(i, n) at X[n * ldx + i]
+static int trsm_forward(kf_ctx* ctx, const double* W, long long ld, int r, const int* d_rank, double* X, long long ldx, int ncols,
+                        cudaStream_t st) {
     KF_CUDA(ctx, kf_ensure_smem(ctx, kf_trsm_diag_kernel, (size_t)128 * 128 * 8));
-    const int r = rank_hint;
     const int nblk = (r + 127) / 128;
     const int grid = std::max(1, std::min((ncols + 7) / 8, ctx->sm_count));
-    const int kmax = (int)kf_roundup(r, KF_BK);
-    // forward: for block row I: X[I,:] -= L[I,0:I) Z[0:I,:]  then solve the diagonal block
+    // for block row I: X[I,:] -= L[I,0:I) Z[0:I,:]  then solve the diagonal block
     for (int b = 0; b < nblk; ++b) {
         const int I = b * 128;
         if (I > 0) {
@@ -436,6 +450,18 @@ static int trsm_both(kf_ctx* ctx, const double* W, long long ld, int P, int rank
         KF_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     }
+    return KF_OK;
+}
+
+// blocked triangular solves  L Z = X, L' X = Z  on the leading rank x rank factor in W
+static int trsm_both(kf_ctx* ctx, const double* W, long long ld, int P, int rank_hint, const int* d_rank, double* X,
+                     long long ldx, int ncols, cudaStream_t st) {
+    // rank_hint: host copy of the rank (bounds the block loops)
+    const int r = rank_hint;
+    const int nblk = (r + 127) / 128;
+    const int grid = std::max(1, std::min((ncols + 7) / 8, ctx->sm_count));
+    const int kmax = (int)kf_roundup(r, KF_BK);
+    KF_TRY(trsm_forward(ctx, W, ld, r, d_rank, X, ldx, ncols, st));
     // backward: for block row I (last to first): Z[I,:] -= sum_{k>=I+128} L(k, I+m) X(k,:)
     for (int b = nblk - 1; b >= 0; --b) {
         const int I = b * 128;
@@ -463,25 +489,151 @@ static int trsm_both(kf_ctx* ctx, const double* W, long long ld, int P, int rank
     return KF_OK;
 }
 
-int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const double* C, double* K, double tol, int* d_perm,
-                     int* rank_out, double* min_piv, double* max_piv, cudaStream_t st) {
-    // state block in d_misc: [PcholState]
+// ---------------------------------------------------------------- refinement basis (multi-level pivoted Cholesky-QR)
+namespace {
+// Sp(j, i) = S(perm[j], i): row gather of a Pp x Pp column-major matrix (rows >= P stay zero)
+__global__ void kf_rf_gather_rows_kernel(const double* __restrict__ S, const int* __restrict__ perm, int P, int Pp, double* Sp) {
+    const long long n = (long long)Pp * Pp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e % Pp), i = (int)(e / Pp);
+        Sp[e] = (j < P && i < P) ? S[(long long)i * Pp + perm[j]] : 0.0;
+    }
+}
+// W(k, c) = 0 for k in [r, r16) and all columns c >= r (mirrored storage: the k-contiguous column c) so that a contraction
+// over k in [0, r16) sees exactly L(c, 0:r)
+__global__ void kf_rf_zero_kpad_kernel(double* W, long long ld, int P, int r, int r16) {
+    const int c = r + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P) return;
+    for (int k = r; k < r16; ++k) W[(long long)c * ld + k] = 0.0;
+}
+__global__ void kf_rf_transpose_kernel(const double* __restrict__ A, double* __restrict__ At, int n) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = bx + threadIdx.x, j = by + r;
+        tile[r][threadIdx.x] = (i < n && j < n) ? A[(long long)j * n + i] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = by + threadIdx.x, j = bx + r;
+        if (i < n && j < n) At[(long long)j * n + i] = tile[threadIdx.x][r];
+    }
+}
+__global__ void kf_rf_identity_kernel(double* S, int P, int Pp) {
+    const long long n = (long long)Pp * Pp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e % Pp), i = (int)(e / Pp);
+        S[e] = (i == j && i < P) ? 1.0 : 0.0;
+    }
+}
+// mirror the lower triangle into the upper one (exactly symmetric input for the pivoted Cholesky)
+__global__ void kf_rf_symmetrize_kernel(double* G, int Pp) {
+    const long long n = (long long)Pp * Pp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % Pp), j = (int)(e / Pp);
+        if (i < j) G[e] = G[(long long)i * Pp + j];
+    }
+}
+}  // namespace
+
+int kf_rf_identity(kf_ctx* ctx, double* S, int P, int Pp, cudaStream_t st) {
+    kf_rf_identity_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(S, P, Pp);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return KF_OK;
+}
+int kf_rf_symmetrize(kf_ctx* ctx, double* G, int Pp, cudaStream_t st) {
+    kf_rf_symmetrize_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(G, Pp);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return KF_OK;
+}
+int kf_rf_transpose(kf_ctx* ctx, const double* A, double* At, int n, cudaStream_t st) {
+    kf_rf_transpose_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, st>>>(A, At, n);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return KF_OK;
+}
+int kf_rf_gather_rows(kf_ctx* ctx, const double* S, const int* d_perm, int P, int Pp, double* Sp, cudaStream_t st) {
+    kf_rf_gather_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(S, d_perm, P, Pp, Sp);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return KF_OK;
+}
+
+// One level of the refinement basis.  W holds the factor of kf_pchol_factor (NOT cleaned) of the Gram of the current
+// features Z = Px S', rank r, pivot order perm.  With L_ext = [[L11, 0], [L21, I]] the new basis is
+//     S_new = L_ext^-1 (Pi S)          (S, Sp, S_new: Pp x Pp column-major, row = new feature, column = original feature)
+// i.e. the first r new features are orthonormalised (Z_new[:r] = L11^-1 Z[perm[:r]]) and the remaining ones are the residuals
+// of the not-yet-accepted columns against them (Z_new[r:] = Z[perm[r:]] - L21 Z_new[:r]).  Sp = Pi S is left in `Sp_out`
+// and the result is written over `S`.
+int kf_rf_update_basis(kf_ctx* ctx, int P, int Pp, double* W, const int* d_perm, int r, double* S, double* Sp_out, cudaStream_t st) {
+    const long long ld = Pp;
+    PcholState* d_state = ctx->d_misc.as<PcholState>();
+    KF_TRY(kf_rf_gather_rows(ctx, S, d_perm, P, Pp, Sp_out, st));
+    KF_CUDA(ctx, cudaMemcpyAsync(S, Sp_out, (size_t)Pp * Pp * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (r <= 0) return KF_OK;
+    KF_TRY(trsm_forward(ctx, W, ld, r, &d_state->rank, S, ld, P, st));
+    if (r < P) {
+        const int r16 = (int)kf_roundup(r, KF_BK);
+        if (r16 > r) {
+            kf_rf_zero_kpad_kernel<<<(P - r + 255) / 256, 256, 0, st>>>(W, ld, P, r, r16);
+            KF_CUDA(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
+        // S[r:P, :] -= L21 S[0:r, :]     (S rows [r, r16) enter with zero coefficients)
+        KfGemmGrid g{};
+        g.A = W + (long long)r * ld;   // A[m][k] = W(k, r+m) = L(r+m, k)
+        g.lda = ld;
+        g.B = S;                       // B[n][k] = S(k, n)
+        g.ldb = ld;
+        g.out = S + r;                 // out[m][n] = S(r+m, n)
+        g.ldm = 1;
+        g.ldn = ld;
+        g.m = P - r;
+        g.n = P;
+        g.k0 = 0;
+        g.k1 = r16;
+        g.alpha = -1.0;
+        g.accumulate = 1;
+        KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+    }
+    return KF_OK;
+}
+
+// Diagonal-pivoted Cholesky of the symmetric W (Pp x Pp, ld = Pp; overwritten by the mirrored factor, see the kernels).
+//   tol     relative tolerance on |R_jj| against the first FREE pivot; tolabs: absolute tolerance on |R_jj| (0: none)
+//   forced  the first `forced` columns are pivots in their given order (refinement passes: the columns accepted by the
+//           previous level, already orthonormalised)
+//   d_perm  pivot order (ints on the device); initialised to the identity here
+//   pivots_host (optional, P doubles): the accepted pivots |R_jj|, j < rank;  rejected_out (optional): |R_jj| candidate the
+//           factorisation stopped at (-1 if every column was accepted, 0 for a non-positive candidate)
+// The rows / columns >= rank of W still hold L21 (rows) and the untouched Schur complement: kf_pchol_solve cleans them.
+int kf_pchol_factor(kf_ctx* ctx, int P, int Pp, double* W, double tol, double tolabs, int forced, int* d_perm, int* rank_out,
+                    double* min_piv, double* max_piv, double* pivots_host, cudaStream_t st, double* rejected_out) {
+    // state block in d_misc: [PcholState | PcholStep]
     KF_CUDA(ctx, ctx->d_misc.ensure(4096));
     PcholState* d_state = ctx->d_misc.as<PcholState>();
-    PcholState h0{0.0, 0.0, 0, 0};
+    PcholState h0{};
+    h0.tol2 = tol * tol;
+    h0.tolabs2 = tolabs * tolabs;
+    h0.forced = forced;
+    h0.rejected = -1.0;
     KF_CUDA(ctx, cudaMemcpyAsync(d_state, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
     {
         std::vector<int> id(P);
         for (int i = 0; i < P; ++i) id[i] = i;
         KF_CUDA(ctx, cudaMemcpyAsync(d_perm, id.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
-        KF_CUDA(ctx, cudaStreamSynchronize(st));   // id goes out of scope
+        KF_CUDA(ctx, cudaStreamSynchronize(st));   // id, h0 go out of scope
     }
     const long long ld = Pp;
-    const double tol2 = tol * tol;
+    KF_CUDA(ctx, ctx->d_K3.ensure((size_t)(4 * Pp + 8) * sizeof(double) + (size_t)(Pp + 4) * sizeof(int)));
+    double* dcur = ctx->d_K3.as<double>();
+    double* pivots = dcur + 2 * (size_t)Pp;
     if (P <= 2 * PCHOL_NB) {
         // small problems: unblocked right-looking factorisation (2 launches per column)
         for (int j = 0; j < P; ++j) {
-            kf_pchol_pivot_kernel<<<1, 1024, 0, st>>>(W, ld, P, j, d_perm, d_state, tol2);
+            kf_pchol_pivot_kernel<<<1, 1024, 0, st>>>(W, ld, P, j, d_perm, d_state, pivots);
             const int rem = P - j - 1;
             if (rem > 0) {
                 dim3 grid((rem + 63) / 64, (rem + 15) / 16);
@@ -491,18 +643,16 @@ int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const dou
         ctx->launches += 2LL * P;
     } else {
         // blocked (dpstrf structure): left-looking inside a 64-column block, DMMA trailing update per block
-        KF_CUDA(ctx, ctx->d_K3.ensure((size_t)(4 * Pp + 8) * sizeof(double) + (size_t)(Pp + 4) * sizeof(int)));
-        double* dcur = ctx->d_K3.as<double>();
         PcholStep* d_step = reinterpret_cast<PcholStep*>(d_state + 1);
         // The loop is launch-bound (3 tiny kernels per column + one DMMA update per block: ~6,000 launches at P = 4096, no
-        // host decision anywhere — pivots and ranks live in device state), so it is captured ONCE into a CUDA graph per
-        // (buffers, P, tolerance) and replayed by every later fit.
+        // host decision anywhere — pivots, ranks AND the tolerances / forced prefix live in device state), so it is captured
+        // ONCE into a CUDA graph per (buffers, P) and replayed by every later factorisation.
         auto enqueue = [&]() -> int {
             for (int j0 = 0; j0 < P; j0 += PCHOL_NB) {
                 const int j1 = std::min(P, j0 + PCHOL_NB);
                 kf_pchol_diag_kernel<<<(P + 255) / 256, 256, 0, st>>>(W, ld, P, dcur);   // Schur diagonal at block start
                 for (int j = j0; j < j1; ++j) {
-                    kf_pcholc_argmax_kernel<<<1, 1024, 0, st>>>(P, j, d_perm, dcur, d_state, d_step, tol2);
+                    kf_pcholc_argmax_kernel<<<1, 1024, 0, st>>>(P, j, d_perm, dcur, d_state, d_step, pivots);
                     kf_pcholc_swap_kernel<<<(P + 255) / 256, 256, 0, st>>>(W, ld, P, j, d_step);
                     const int rem = P - j - 1;
                     kf_pcholc_col_kernel<<<std::max(1, (rem + 255) / 256), 256, 0, st>>>(W, ld, P, j, j0, dcur, d_step);
@@ -530,7 +680,7 @@ int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const dou
         };
         KfPcholGraph& G = ctx->pchol_graph;
         const bool same = G.exec && G.W == W && G.perm == d_perm && G.dcur == dcur && G.state == d_state && G.P == P && G.Pp == Pp &&
-                          G.tol2 == tol2 && G.stream == st;
+                          G.stream == st;
         if (!ctx->opt_graphs) {
             KF_TRY(enqueue());
         } else {
@@ -546,7 +696,7 @@ int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const dou
                 KF_CUDA(ctx, ce);
                 KF_CUDA(ctx, cudaGraphInstantiate(&G.exec, graph, 0));
                 cudaGraphDestroy(graph);
-                G.W = W; G.perm = d_perm; G.dcur = dcur; G.state = d_state; G.P = P; G.Pp = Pp; G.tol2 = tol2; G.stream = st;
+                G.W = W; G.perm = d_perm; G.dcur = dcur; G.state = d_state; G.P = P; G.Pp = Pp; G.stream = st;
                 G.launches = ctx->launches - l0;
                 G.flops = ctx->dmma_flops - f0;
                 ctx->launches = l0;                      // counted per replay below
@@ -558,27 +708,55 @@ int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const dou
         }
     }
     KF_CUDA(ctx, cudaGetLastError());
-    kf_pchol_clean_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W, ld, Pp, d_state);
     PcholState hs;
     KF_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, st));
     KF_CUDA(ctx, cudaStreamSynchronize(st));
     const int r = hs.rank;
+    if (pivots_host && r > 0) {
+        KF_CUDA(ctx, cudaMemcpyAsync(pivots_host, pivots, sizeof(double) * r, cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int j = 0; j < r; ++j) pivots_host[j] = sqrt(pivots_host[j] > 0 ? pivots_host[j] : 0.0);
+    }
+    if (r < forced) {
+        ctx->err = "pivoted Cholesky broke down inside the forced prefix (column " + std::to_string(r) + " of " +
+                   std::to_string(forced) + "): the refinement basis lost positive definiteness";
+        return KF_ENUMERIC;
+    }
     *rank_out = r;
     *max_piv = sqrt(hs.piv0 > 0 ? hs.piv0 : 0.0);
     *min_piv = sqrt(hs.minpiv > 0 ? hs.minpiv : 0.0);
+    if (rejected_out) *rejected_out = hs.rejected > 0 ? sqrt(hs.rejected) : (hs.rejected < 0 ? -1.0 : 0.0);
+    return KF_OK;
+}
+
+// Basic solution from the factor of kf_pchol_factor: K(perm[0:r], :) = (L11 L11')^-1 C(perm[0:r], :), zeros elsewhere.
+// scatter = 0 leaves the solution in PIVOT order (rows 0..r-1 of K) instead of scattering it by perm.
+int kf_pchol_solve(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const double* C, double* K, const int* d_perm, int r, int scatter,
+                   cudaStream_t st) {
+    const long long ld = Pp;
+    PcholState* d_state = ctx->d_misc.as<PcholState>();
+    kf_pchol_clean_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W, ld, Pp, d_state);
     // X = C(perm[0:r], :) in the K buffer's scratch twin (d_tmp), solve, scatter
     KF_CUDA(ctx, ctx->d_tmp.ensure((size_t)Pp * Pp * sizeof(double)));
-    double* X = ctx->d_tmp.as<double>();
+    double* X = scatter ? ctx->d_tmp.as<double>() : K;
     kf_gather_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(C, ld, d_perm, d_state, Pp, ncols, X, ld);
     KF_CUDA(ctx, cudaGetLastError());
-    KF_CUDA(ctx, cudaMemsetAsync(K, 0, (size_t)Pp * Pp * sizeof(double), st));
+    if (scatter) KF_CUDA(ctx, cudaMemsetAsync(K, 0, (size_t)Pp * Pp * sizeof(double), st));
     if (r > 0) {
         KF_TRY(trsm_both(ctx, W, ld, P, r, &d_state->rank, X, ld, ncols, st));
-        kf_scatter_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(X, ld, d_perm, &d_state->rank, ncols, K, ld);
-        KF_CUDA(ctx, cudaGetLastError());
+        if (scatter) {
+            kf_scatter_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(X, ld, d_perm, &d_state->rank, ncols, K, ld);
+            KF_CUDA(ctx, cudaGetLastError());
+        }
     }
     ctx->launches += 4;
     return KF_OK;
+}
+
+int kf_solve_gram_ls(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const double* C, double* K, double tol, int* d_perm,
+                     int* rank_out, double* min_piv, double* max_piv, cudaStream_t st) {
+    KF_TRY(kf_pchol_factor(ctx, P, Pp, W, tol, 0.0, 0, d_perm, rank_out, min_piv, max_piv, nullptr, st, nullptr));
+    return kf_pchol_solve(ctx, P, Pp, ncols, W, C, K, d_perm, *rank_out, 1, st);
 }
 
 // =====================================================================================

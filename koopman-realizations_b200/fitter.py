@@ -295,6 +295,12 @@ class Fitter:
         pr = A.kf_problem(M=int(M), nzeta=int(nzeta), m=int(m), model=A.MODEL_CODE[model_type],
                           alpha=int(alpha_ptr), beta=int(beta_ptr), u=int(u_ptr), pc_cols=int(pc_cols))
         self._check(self.lib.kf_accumulate_dev(self.ctx, basis.ref(), C.byref(pr), int(reset)), "kf_accumulate_dev")
+        if reset or getattr(self, "_acc_dims", None) is None:
+            # the dimensions kf_solve_dev will write with: the host buffers of solve_dev are sized from THESE, never from the
+            # caller's idea of P / pc_cols (a mismatch would overflow them — the ABI carries no buffer sizes)
+            _, _, P = self.dims(basis, model_type, int(m))
+            self._acc_dims = (P, int(pc_cols) if 0 < int(pc_cols) < P else P)
+            self._solve_state = None
 
     def regressors_dev(self, basis, model_type, M, nzeta, m, alpha_ptr, beta_ptr, u_ptr, out_ptr, ld=None):
         """Lift-only mode on device buffers (kf_regressors_dev): [Px | Py] (M x 2P, column-major, ld >= M) written to
@@ -313,25 +319,48 @@ class Fitter:
         self._check(self.lib.kf_accum_buffer(self.ctx, C.byref(p), C.byref(n)), "kf_accum_buffer")
         return p.value, n.value
 
-    def solve_dev(self, P, want_gram=False, pc_cols=0, **solve_kw):
-        """Solve from the (all-reduced) accumulator; pc_cols must match the one given to accumulate_dev."""
-        sv, keep_t = self._solve_struct(**solve_kw)
-        nt = max(1, sv.nt) if not sv.least_squares else 1
-        res = A.kf_result()
-        Pc = int(pc_cols) if 0 < int(pc_cols) < P else P
-        K = np.zeros((P, Pc, nt), order="F")
-        perm = np.zeros(P, dtype=np.int32)
-        obj, l1, gap = np.zeros(nt), np.zeros(nt), np.zeros(nt)
-        iters = np.zeros(nt, dtype=np.int32)
-        res.K, res.perm = A.dptr(K), perm.ctypes.data_as(A.c_int_p)
-        res.objective, res.l1norm, res.qp_iters = A.dptr(obj), A.dptr(l1), iters.ctypes.data_as(A.c_int_p)
-        res.qp_gap = A.dptr(gap)
-        out = {}
-        if want_gram:
-            out["G"], out["C"] = np.zeros((P, P), order="F"), np.zeros((P, P), order="F")
-            res.G, res.C = A.dptr(out["G"]), A.dptr(out["C"])
-        self._check(self.lib.kf_solve_dev(self.ctx, C.byref(sv), C.byref(res)), "kf_solve_dev")
+    def solve_dev(self, P=None, want_gram=False, pc_cols=None, **solve_kw):
+        """Solve from the (all-reduced) accumulator.  The output buffers are sized from the layout recorded by accumulate_dev;
+        P / pc_cols, if given, are only checked against it.
+
+        Returns the result dict, or None when the library asks for ANOTHER data pass (KF_EAGAIN: ill-conditioned regressor,
+        Gram-route refinement).  The caller then repeats accumulate_dev(..., reset=False) on the same shard(s), all-reduces
+        accum_buffer() and calls solve_dev again with the same arguments; `fit_sharded` does this loop."""
+        dims = getattr(self, "_acc_dims", None)
+        if dims is None:
+            raise A.KoopfitError("solve_dev: nothing accumulated (call accumulate_dev first)")
+        Pa, Pca = dims
+        if P is not None and int(P) != Pa:
+            raise A.KoopfitError(f"solve_dev: P = {P} does not match the accumulated regressor width {Pa}")
+        if pc_cols is not None and (int(pc_cols) if 0 < int(pc_cols) < Pa else Pa) != Pca:
+            raise A.KoopfitError(f"solve_dev: pc_cols = {pc_cols} does not match the accumulated layout ({Pca} columns)")
+        P, Pc = Pa, Pca
+        st = getattr(self, "_solve_state", None)
+        if st is None:                      # first call: allocate; a continuation after KF_EAGAIN reuses the same buffers
+            sv, keep_t = self._solve_struct(**solve_kw)
+            nt = max(1, sv.nt) if not sv.least_squares else 1
+            res = A.kf_result()
+            K = np.zeros((P, Pc, nt), order="F")
+            perm = np.zeros(P, dtype=np.int32)
+            obj, l1, gap = np.zeros(nt), np.zeros(nt), np.zeros(nt)
+            iters = np.zeros(nt, dtype=np.int32)
+            res.K, res.perm = A.dptr(K), perm.ctypes.data_as(A.c_int_p)
+            res.objective, res.l1norm, res.qp_iters = A.dptr(obj), A.dptr(l1), iters.ctypes.data_as(A.c_int_p)
+            res.qp_gap = A.dptr(gap)
+            out = {}
+            if want_gram:
+                out["G"], out["C"] = np.zeros((P, P), order="F"), np.zeros((P, P), order="F")
+                res.G, res.C = A.dptr(out["G"]), A.dptr(out["C"])
+            st = dict(sv=sv, keep_t=keep_t, nt=nt, res=res, K=K, perm=perm, obj=obj, l1=l1, gap=gap, iters=iters, out=out)
+        rc = self.lib.kf_solve_dev(self.ctx, C.byref(st["sv"]), C.byref(st["res"]))
+        if rc == A.KF_EAGAIN:
+            self._solve_state = st
+            return None
+        self._solve_state = None
+        self._acc_dims = None
+        self._check(rc, "kf_solve_dev")
+        res, K, nt, out = st["res"], st["K"], st["nt"], st["out"]
         info = {f: getattr(res.info, f) for f, _ in A.kf_info._fields_}
-        out.update(K=K[:, :, 0] if nt == 1 else K, K_all=K, rank=info["rank"], perm=perm, info=info,
-                   objective=obj, l1norm=l1, qp_iters=iters, qp_gap=gap)
+        out.update(K=K[:, :, 0] if nt == 1 else K, K_all=K, rank=info["rank"], perm=st["perm"], info=info, P=P,
+                   objective=st["obj"], l1norm=st["l1"], qp_iters=st["iters"], qp_gap=st["gap"])
         return out

@@ -41,7 +41,8 @@ class DeviceArrayView:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
-def fit_sharded(fitter, basis, model_type, alpha_dev, beta_dev, u_dev, P, budgets=None, group=None, split="budgets", **solve_kw):
+def fit_sharded(fitter, basis, model_type, alpha_dev, beta_dev, u_dev, P=None, budgets=None, group=None, split="budgets", pc_cols=0,
+                **solve_kw):
     """One rank's part of a snapshot-sharded fit (one process per GPU).
 
     alpha_dev / beta_dev / u_dev: this rank's shard as CUDA tensors of shape (nzeta, M_r) / (m, M_r), float64,
@@ -57,16 +58,28 @@ def fit_sharded(fitter, basis, model_type, alpha_dev, beta_dev, u_dev, P, budget
 
     nzeta, M = alpha_dev.shape
     m = u_dev.shape[0]
-    fitter.accumulate_dev(basis, model_type, M, nzeta, m, alpha_dev.data_ptr(), beta_dev.data_ptr(), u_dev.data_ptr(), reset=True)
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    if world > 1:
-        ptr, n = fitter.accum_buffer()
-        fitter.sync()
-        allreduce_sum_(torch.as_tensor(DeviceArrayView(ptr, n), device=alpha_dev.device), group)
-        torch.cuda.synchronize(alpha_dev.device)
+
+    def data_pass(reset):
+        fitter.accumulate_dev(basis, model_type, M, nzeta, m, alpha_dev.data_ptr(), beta_dev.data_ptr(), u_dev.data_ptr(),
+                              reset=reset, pc_cols=pc_cols)
+        if world > 1:
+            ptr, n = fitter.accum_buffer()
+            fitter.sync()
+            allreduce_sum_(torch.as_tensor(DeviceArrayView(ptr, n), device=alpha_dev.device), group)
+            torch.cuda.synchronize(alpha_dev.device)
+
+    data_pass(True)
+    P = fitter._acc_dims[0]      # the regressor width the library accumulated with (a caller-supplied P is only checked)
     if budgets is None:
-        return fitter.solve_dev(P, **solve_kw)
+        # least squares: an ill-conditioned regressor makes the library ask for extra data passes (solve_dev returns None:
+        # KF_EAGAIN, Gram-route refinement); every rank takes the same decision, so the collectives stay matched
+        while True:
+            res = fitter.solve_dev(P, **solve_kw)
+            if res is not None:
+                return res
+            data_pass(False)
     budgets = np.atleast_1d(np.asarray(budgets, dtype=np.float64))
     if world > 1 and split == "columns":
         return _solve_column_split(fitter, P, budgets, rank, world, alpha_dev.device, group, **solve_kw)

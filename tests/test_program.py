@@ -78,7 +78,7 @@ def test_library_exports_every_declared_symbol():
     lib = A.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.kf_version() == 100
+    assert lib.kf_version() == 200
     # dictionary dimensions are host-only logic
     b = A.Basis(["poly"], [2], 6)
     nf, N, P = C.c_int(), C.c_int(), C.c_int()
