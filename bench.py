@@ -22,6 +22,12 @@ import sys
 import tempfile
 import time
 
+if "reference" in sys.argv:
+    # The CPU arm uses every host core whatever the launcher exported: torchrun sets OMP_NUM_THREADS=1 for its workers, which
+    # would time the reference on ONE core (and made the N > 1 reference runs of round 1 time out).  Must precede `import numpy`.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -89,14 +95,45 @@ def gen_torch(M, device, seed):
     return alpha, beta, u
 
 
-def fp64_peak_tflops():
-    """Roofline denominator: MEASURED cuBLAS DGEMM FP64 on this pool's B200
-    (profiles/r01_fp64_dgemm_peak.json, tools/fp64_peak.py); MEASURED_PEAKS.json has no FP64 entry."""
+def fp64_peak_committed():
+    """The builder's earlier measurement (profiles/r01_fp64_dgemm_peak.json): kept as a cross-check only."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_dgemm_peak.json")))
-        return float(d["dgemm_tflops_sustained"]), "measured cuBLAS DGEMM 8192^3 fp64 on this pool (profiles/r01_fp64_dgemm_peak.json)"
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_dgemm_peak.json")))["dgemm_tflops_sustained"])
     except Exception:
-        return 37.0, "fallback: nominal B200 FP64 tensor 37 TFLOP/s"
+        return None
+
+
+def fp64_peak_measured(dev, n=8192, reps=12):
+    """Roofline denominator measured IN THIS RUN on the bench box: cuBLAS DGEMM n^3 in FP64 (torch.matmul), CUDA events, after
+    warm-up; `burst` = best single GEMM, `sustained` = all reps back to back.  MEASURED_PEAKS.json carries no FP64 figure."""
+    import torch
+    a = torch.randn((n, n), dtype=torch.float64, device=dev)
+    b = torch.randn((n, n), dtype=torch.float64, device=dev)
+    c = torch.empty((n, n), dtype=torch.float64, device=dev)
+    for _ in range(3):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize(dev)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    evs[0].record()
+    for i in range(reps):
+        torch.matmul(a, b, out=c)
+        evs[i + 1].record()
+    torch.cuda.synchronize(dev)
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(reps)]
+    flop = 2.0 * n ** 3
+    del a, b, c
+    return {"burst": flop / (min(per) * 1e-3) / 1e12, "sustained": flop * reps / (evs[0].elapsed_time(evs[reps]) * 1e-3) / 1e12}
+
+
+def gram_traffic_from_profile():
+    """dram bytes per launch of the Gram kernel from the committed ncu capture (NOT measured in this run)."""
+    for name in ("r02_gram_tma_traffic.json", "r01_gram_tma_traffic.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return float(d["dram_bytes_per_launch"]), f"profiles/{name} ({d.get('source', 'ncu --set full')})"
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -138,10 +175,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_CPU_SOLVE_S = None
+
+
 def cpu_fit_rates(sample, threads):
     """Time the oracle (kind 'port': NumPy/SciPy restatement, OpenBLAS) on a bounded sample of the workload.
-    Returns lift+Gram rate (snapshots/s), solve seconds, and what was timed."""
+    Returns lift+Gram rate (snapshots/s), solve seconds, and what was timed.  The per-snapshot part (lift + Gram) is timed
+    on every call; the P = 4096 dgeqp3 solve — paid once per fit, independent of the snapshot count — is timed ONCE per
+    process and reused (it is ~15 s on 16 cores; timing it in each of 25 steps is what overran the driver's limit in round 1)."""
+    global _CPU_SOLVE_S
     import oracle as O
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=threads)
+    except Exception:
+        pass
     _, _, centres = workload_constants()
     prog = O.build_program(OBS_TYPE, OBS_DEGREE, NZETA, centres)
     alpha, beta, u = gen_numpy(sample, seed=1234)
@@ -149,11 +197,13 @@ def cpu_fit_rates(sample, threads):
     Px, Py = O.build_regressors("bilinear", prog, alpha, beta, u)
     G, C = O.gram(Px, Py)
     t_lg = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    K = O.mldivide(Px, Py)          # dgeqp3 — the routine behind MATLAB's `\` (Ksysid.m:1069)
-    t_solve = time.perf_counter() - t0
-    assert K.shape == (P_REG, P_REG) and np.all(np.isfinite(G)) and np.all(np.isfinite(C))
-    return sample / t_lg, t_solve, t_lg
+    assert np.all(np.isfinite(G)) and np.all(np.isfinite(C))
+    if _CPU_SOLVE_S is None:
+        t0 = time.perf_counter()
+        K = O.mldivide(Px, Py)          # dgeqp3 — the routine behind MATLAB's `\` (Ksysid.m:1069)
+        _CPU_SOLVE_S = time.perf_counter() - t0
+        assert K.shape == (P_REG, P_REG)
+    return sample / t_lg, _CPU_SOLVE_S, t_lg
 
 
 def run_reference(args, rank):
@@ -178,10 +228,11 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, extra={"cpu_sample_snapshots": sample}),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{sample} snapshots of the same workload: NumPy lift + OpenBLAS Gram timed per snapshot, "
-                                       f"dgeqp3 solve (P=4096) timed once; extrapolated linearly in M to the {args.snapshots_per_gpu * args.gpus}-snapshot job"},
+            "config": config_dict(args),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "cpu_sample_snapshots": sample,
+                             "sample": f"{sample} snapshots of the same workload: NumPy lift + OpenBLAS Gram timed per snapshot in every step, "
+                                       f"dgeqp3 solve (P=4096) timed once per run; extrapolated linearly in M to the "
+                                       f"{args.snapshots_per_gpu * args.gpus}-snapshot job"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -198,6 +249,47 @@ def config_dict(args, extra=None):
     return d
 
 
+def lasso3a_sweep(fit, rank, world, dev, reps=2):
+    """BASELINE config 3a as an extra (`"lasso3a"` in the JSON line): snake data, bilinear, fourier degree 4 (P = 1464), the
+    lasso vector logspace(-2, 2, 64) swept by the exact active-set solver.  One kf_fit call per rank on its shard of the
+    snapshot pairs (host buffers): all-reduce of the partial Grams, then the sweep is split by COLUMNS of K over the ranks inside
+    the library (Ksysid.m:1370-1387 re-fits per lasso value).  Time = whole call, max over ranks; certified by the Frank-Wolfe gaps."""
+    import io
+    import contextlib
+    import torch
+    import torch.distributed as dist
+    from koopfit.ksysid import Ksysid
+    from koopfit.sharding import shard_bounds
+    z = np.load(os.path.join(ROOT, "tests", "golden", "snake_data.npz"))
+    data = {}
+    for split in ("train", "val"):
+        data[split] = [{k: z[f"{split}{i}_{k}"] for k in ("t", "y", "u")} for i in range(int(z[f"{split}_n"]))]
+    lassos = np.logspace(-2, 2, 64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ks = Ksysid(data, model_type="bilinear", obs_type=["fourier"], obs_degree=[4], lasso=lassos, dim_red=False, fitter=fit)
+    N, sp = ks.params["N"], ks.snapshotPairs
+    lo, hi = shard_bounds(sp["alpha"].shape[0], rank, world)
+    al, be, uu = (np.asfortranarray(sp[k][lo:hi]) for k in ("alpha", "beta", "u"))
+    secs, res = [], None
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        res = fit.fit(ks.basis, "bilinear", al, be, uu, least_squares=False, t=lassos * N, psd_shift="never")
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        secs.append(float(tt.item()))
+    rel = res["qp_gap"] / np.abs(res["objective"])
+    return {"workload": "BASELINE config 3a: snake-data, bilinear, fourier 4 (P = 1464), 64 budgets logspace(-2,2,64)*N, exact active set",
+            "n_gpus": world, "seconds": min(secs), "seconds_all": secs, "solve_ms": res["info"]["t_solve_ms"],
+            "lift_gram_ms": res["info"]["t_lift_gram_ms"], "budgets": int(lassos.size), "total_steps": int(res["qp_iters"].sum()),
+            "unconverged": int(res["info"]["qp_capped"]), "worst_rel_gap": float(rel.max()),
+            "split": "columns of K over the ranks, step scalars reduced on the device (NCCL, in stream order)" if world > 1 else "single GPU",
+            "api": "kf_fit (host shard per rank; library-owned NCCL communicator)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,6 +301,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra pc_cols = N measurement")
+    ap.add_argument("--no-lasso3a", action="store_true", help="skip the extra config-3a lasso sweep")
+    ap.add_argument("--workload", default="config5", choices=["config5", "lasso3a"],
+                    help="lasso3a: only the config-3a lasso sweep (prints its own JSON line, metric lasso_sweep_seconds)")
     ap.add_argument("--option", action="append", default=[], help="kf_set_option name=value")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -228,44 +323,53 @@ def main():
     import torch
     import torch.distributed as dist
     import koopfit
-    from koopfit.sharding import DeviceArrayView, allreduce_sum_
 
     if world != args.gpus and world > 1:
         args.gpus = world
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    fit = koopfit.Fitter(device=local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    M = args.snapshots_per_gpu
-    _, _, centres = workload_constants()
-    basis = koopfit.Basis(OBS_TYPE, OBS_DEGREE, NZETA, centres)
-    fit = koopfit.Fitter(device=local_rank)
-    fit.set_option("profile", 1)
+        # the data-path collective lives INSIDE libkoopfit.so: rank 0 draws the NCCL id, torch.distributed only carries it over
+        ids = [koopfit.Fitter.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        fit.comm_init(world, rank, ids[0])
     for kv in args.option:
         k, v = kv.split("=")
         fit.set_option(k, float(v))
-    alpha, beta, u = gen_torch(M, dev, seed=1000 + rank)
-    torch.cuda.synchronize()
-    kstream = torch.cuda.ExternalStream(fit.stream, device=dev)
-
-    def step_resident(pc_cols=0):
-        fit.accumulate_dev(basis, "bilinear", M, NZETA, M_IN, alpha.data_ptr(), beta.data_ptr(), u.data_ptr(), reset=True,
-                           pc_cols=pc_cols)
-        if world > 1:
-            ptr, n = fit.accum_buffer()
-            fit.sync()
-            buf = torch.as_tensor(DeviceArrayView(ptr, n), device=dev)
-            allreduce_sum_(buf)                      # the one collective: sum of the packed partial Grams (NCCL)
-            torch.cuda.synchronize()
-        return fit.solve_dev(P_REG, ls_method="gram", pc_cols=pc_cols)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         fit.sync()
+
+    if args.workload == "lasso3a":
+        out = lasso3a_sweep(fit, rank, world, dev)
+        if rank == 0:
+            emit({"metric": "lasso_sweep_seconds", "value": out["seconds"], "unit": "s", "n_gpus": world, "steps": 1, "warmup": 1,
+                  "ms_per_step": 1e3 * out["seconds"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                  "data": "reference fixture (snake-data.mat)", "config": {"workload": out["workload"]}, "lasso3a": out})
+        fit.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fit.set_option("profile", 1)
+    M = args.snapshots_per_gpu
+    _, _, centres = workload_constants()
+    basis = koopfit.Basis(OBS_TYPE, OBS_DEGREE, NZETA, centres)
+    alpha, beta, u = gen_torch(M, dev, seed=1000 + rank)
+    torch.cuda.synchronize()
+    kstream = torch.cuda.ExternalStream(fit.stream, device=dev)
+
+    def step_resident(pc_cols=0):
+        # kf_fit_dev: lift + Gram of this rank's device-resident shard, [N > 1: ONE ncclAllReduce of the packed partial Grams,
+        # inside the library], assemble, pivoted-Cholesky solve (refinement passes if the conditioning asks for them), K to the host
+        return fit.fit_dev(basis, "bilinear", M, NZETA, M_IN, alpha.data_ptr(), beta.data_ptr(), u.data_ptr(), ls_method="gram",
+                           pc_cols=pc_cols)
 
     # ---------------- device-resident timing (value) ----------------
     for _ in range(args.warmup):
@@ -291,9 +395,10 @@ def main():
     ms_step = float(tmax.item()) / args.steps
     value = M * world / (ms_step * 1e-3)
     assert res["rank"] == P_REG, f"unexpected rank {res['rank']}"
+    assert res["info"]["passes"] == 1, "the benchmarked workload is well conditioned: one data pass"
     assert np.all(np.isfinite(res["K"]))
 
-    # ---------------- end-to-end through the public host API (kf_fit, host buffers) ----------------
+    # ---------------- end-to-end through the public host API (kf_fit, host buffers) at every N ----------------
     h_alpha = torch.empty((NZETA, M), dtype=torch.float64).pin_memory()
     h_beta = torch.empty((NZETA, M), dtype=torch.float64).pin_memory()
     h_u = torch.empty((M_IN, M), dtype=torch.float64).pin_memory()
@@ -302,33 +407,21 @@ def main():
     na, nb, nu = h_alpha.numpy().T, h_beta.numpy().T, h_u.numpy().T     # (M x nzeta) column-major views
     h2d = (2 * NZETA + M_IN) * 8 * M
     d2h = P_REG * P_REG * 8
-    e2e_val = None
-    if world == 1:
-        def step_e2e():
-            return fit.fit(basis, "bilinear", na, nb, nu, ls_method="gram")
-        step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            r2 = step_e2e()
-        barrier()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
-        e2e_val = M / (e2e_ms * 1e-3)
-    else:
-        # multi-rank end to end: pinned host shard -> device copies inside the timed region, then the staged path
-        def step_e2e():
-            alpha.copy_(h_alpha, non_blocking=True); beta.copy_(h_beta, non_blocking=True); u.copy_(h_u, non_blocking=True)
-            torch.cuda.synchronize()
-            return step_resident()
-        step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            r2 = step_e2e()
-        barrier()
-        tt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.e2e_steps], dtype=torch.float64, device=dev)
+
+    def step_e2e():
+        # this rank's HOST shard: block-wise H2D overlapped with the lift + Gram, in-library all-reduce, solve, K to the host
+        return fit.fit(basis, "bilinear", na, nb, nu, ls_method="gram")
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        r2 = step_e2e()
+    barrier()
+    tt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_val = M * world / (float(tt.item()) * 1e-3)
+    e2e_val = M * world / (float(tt.item()) * 1e-3)
+    assert r2["rank"] == P_REG
 
     # ---------------- opt-in fast mode (not the headline): only K(:,1:N), the columns A and B are cut from ----------------
     fast = None
@@ -369,46 +462,73 @@ def main():
                 hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
             except Exception:
                 pass
-            lift_only = {"bound": "hbm", "kernel": "kf_lift_tile_kernel (materialised [Px | Py], not on the fit path)", "pairs": Ml,
+            lift_only = {"bound": "hbm", "kernel": "materialising lift ([Px | Py] written to HBM; not on the fit path)", "pairs": Ml,
                          "achieved": lbytes / lms / 1e6, "peak": hbm, "unit": "GB/s", "frac": lbytes / lms / 1e6 / hbm,
                          "algorithmic_bytes_per_pair": 8.0 * (2 * NZETA + M_IN) + 16.0 * P_REG, "ms": lms}
             del out_buf
         except Exception as exc:      # an extra, never the reason for a failed bench
             lift_only = {"error": str(exc)[:200]}
 
+    # ---------------- FP64 tensor peak measured in this run (rank 0), inputs freed first ----------------
+    del alpha, beta, u
+    torch.cuda.empty_cache()
+    peak_now = fp64_peak_measured(dev) if rank == 0 else None
+
+    # ---------------- extra: config 3a lasso sweep at this N ----------------
+    lasso3a = None
+    if not args.no_lasso3a:
+        try:
+            fit.set_option("profile", 0)
+            lasso3a = lasso3a_sweep(fit, rank, world, dev)
+        except Exception as exc:
+            lasso3a = {"error": str(exc)[:300]}
+
     if rank == 0:
-        peak, peak_src = fp64_peak_tflops()
+        peak = peak_now["sustained"]
+        committed = fp64_peak_committed()
         tiles_flops = flops_issued / args.steps                      # DMMA flops issued per step (incl. solver GEMMs)
         gram_flops = 1000 * 2.0 * 128 * 128 * M                       # 10 Kronecker blocks x (36 G + 64 C) tiles
         gk = float(np.mean(gram_ms)) if gram_ms and np.mean(gram_ms) > 0 else float(np.mean(liftgram_ms))
-        achieved = gram_flops / (gk * 1e-3) / 1e12
+        lg = float(np.mean(liftgram_ms))
+        # achieved: issued DMMA flops of the Gram kernel / the MEASURED device time of the whole lift + Gram phase of a step
+        # (CUDA events on the library's stream around all launches) — conservative: the lifts and the pipeline tails are inside.
+        achieved = gram_flops / (lg * 1e-3) / 1e12
+        traffic, traffic_src = gram_traffic_from_profile()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_dict(args),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "kf_fit (host buffers)" if world == 1 else "pinned host shard -> kf_accumulate_dev/all_reduce/kf_solve_dev"},
+                    "api": "kf_fit: this rank's pinned HOST shard, block-wise H2D overlapped with lift + Gram, "
+                           + ("ncclAllReduce inside the library, " if world > 1 else "") + "solve, K to the host"},
             "gpu_launches": int(launches),
             "fast_mode": fast,
             "lift_only": lift_only,
+            "lasso3a": lasso3a,
             "roofline": {"bound": "tensor", "kernel": "kf_gram_tma_kernel<true> (FP64 DMMA.8x8x4 Gram/cross-covariance, tensor-map TMA operands)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (4096-snapshot panel) from
-                         # the ncu --set full capture in profiles/r01_gram_tma_ncu_summary.txt: 587 MB + 119 MB
-                         "traffic": 7.07e8, "traffic_unit": "bytes per launch (ncu, 4096-snapshot chunk; 67 MB panel + accumulator RMW)",
+                         "traffic": traffic, "traffic_unit": "bytes per launch (one 4096-snapshot panel)",
+                         "traffic_source": f"NOT measured in this run: {traffic_src}" if traffic_src else None,
                          "algorithmic_flops_per_launch": FLOPS_ALGO_PER_PAIR * 4096, "issued_flops_per_launch": 1000 * 2.0 * 128 * 128 * 4096,
-                         "peak_source": peak_src,
+                         "peak_source": "cuBLAS DGEMM 8192^3 fp64 (torch.matmul) measured in THIS run on this box, 12 GEMMs back to back "
+                                        "(sustained); MEASURED_PEAKS.json has no FP64 entry",
+                         "peak_burst": peak_now["burst"], "peak_committed_crosscheck": committed,
+                         "time_basis": "lift_gram_ms_per_step: CUDA events on the library's stream around the whole lift + Gram phase",
                          "flops_basis": "DMMA flops actually issued per step by the Gram kernel (Kronecker blocks: 1000 tiles x 2x128x128 per snapshot = 3.28e7/pair)",
-                         "achieved_algorithmic": FLOPS_ALGO_PER_PAIR * M / (gk * 1e-3) / 1e12,
+                         "achieved_algorithmic": FLOPS_ALGO_PER_PAIR * M / (lg * 1e-3) / 1e12,
                          "algorithmic_flops_per_pair": FLOPS_ALGO_PER_PAIR, "issued_flops_per_pair": 1000 * 2.0 * 128 * 128,
-                         "gram_kernel_ms_per_step": gk, "lift_gram_ms_per_step": float(np.mean(liftgram_ms)),
+                         "gram_kernel_ms_per_step_estimate": gk,
+                         "gram_kernel_ms_note": "ESTIMATE: mean of the isolated every-61st-launch samples x launches per step (not a measured total)",
+                         "achieved_kernel_only_estimate": gram_flops / (gk * 1e-3) / 1e12,
+                         "lift_gram_ms_per_step": lg,
                          "solve_ms_per_step": float(np.mean(solve_ms)), "dmma_flops_issued_per_step_all_kernels": tiles_flops},
         }
         if not args.no_cpu_baseline:
             rate_lg, t_solve, t_lg = cpu_fit_rates(args.cpu_sample, os.cpu_count())
             Mjob = M * world
             line["cpu_baseline"] = {"value": Mjob / (Mjob / rate_lg + t_solve), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "cpu_sample_snapshots": args.cpu_sample,
                                     "sample": f"{args.cpu_sample} snapshots of the same workload (oracle: NumPy lift + OpenBLAS Gram {t_lg:.1f} s, "
                                               f"dgeqp3 solve {t_solve:.1f} s), per-snapshot part extrapolated linearly to {Mjob} snapshots"}
         emit(line)

@@ -151,6 +151,11 @@ int kf_lift(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V,
  * LS or all nt budgets.  HOST pointers in `prob`; copies are inside the call. */
 int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out);
 
+/* kf_fit with DEVICE pointers in `prob` (column-major, leading dimension M; this rank's shard on a multi-GPU context):
+ * lift + Gram, the all-reduce over the context's communicator if it has one, the solve including any refinement passes.
+ * Outputs go to HOST pointers as in kf_fit. */
+int kf_fit_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out);
+
 /* The same fit from the RAW merged training series: get_scale (Ksysid.m:180-229), get_zeta (868-907) and
  * get_snapshotPairs (910-984, snapshots = Inf) run on the device, so the series crosses the boundary once
  * (T (1 + n + m) doubles instead of M (2 nzeta + m)) and the pairs are written straight into the buffers the lift reads. */
@@ -247,6 +252,38 @@ int kf_solve_dev(kf_ctx* ctx, const kf_solve* solve, kf_result* out);
 int kf_sync(kf_ctx* ctx);                            /* cudaStreamSynchronize(context stream) */
 void* kf_stream(kf_ctx* ctx);                        /* the context's cudaStream_t */
 
+/* ---- multi-GPU inside the library ---------------------------------------------------------
+ * The reference's call site is ONE process (Ksysid.train_models -> get_Koopman, Ksysid.m:1357, 1373), so the library
+ * owns the NCCL communicators (NCCL is resolved with dlopen at run time) and the MEX shim reaches every visible GPU
+ * with one call:
+ *
+ *   kf_create_multi / kf_fit_multi   one process, ndev devices (device_ids NULL or ndev <= 0: all visible devices): a
+ *       context and a host thread per device, ncclCommInitAll.  kf_fit_multi has kf_fit's contract on the FULL host
+ *       snapshot pairs: rows are split into contiguous shards, every device copies its shard in blocks and lifts /
+ *       contracts each block as it arrives, ONE ncclAllReduce sums the packed partial Grams (and the snapshot count) over
+ *       NVLink, the solve is replicated (deterministic: every device takes the same rank / refinement decisions),
+ *       device 0 writes K, G, C, perm and the per-budget outputs, every device its own rows of Px / Py.  A lasso vector
+ *       solved by the exact active-set solver is split by COLUMNS of K over the devices (Ksysid.m:1370-1387: the
+ *       reference re-fits per lasso value); the step scalars are reduced on the device in stream order.
+ *   kf_comm_unique_id / kf_comm_init_rank   one process per GPU (torchrun / MPI / MATLAB parpool): rank 0 draws the
+ *       128-byte id, the caller broadcasts it, every rank's context joins; kf_fit on such a context takes THIS RANK's
+ *       shard of the snapshot pairs and behaves as above (every rank receives the full result).
+ * KF_LS_QR is refused on a multi-GPU fit (it needs all regressors on one device); KF_LS_AUTO takes the Gram route, which
+ * re-orthogonalises by itself on ill-conditioned data (kf_info.refine_passes). */
+typedef struct kf_multi kf_multi;
+int  kf_create_multi(kf_multi** mc, const int* device_ids, int ndev);
+void kf_destroy_multi(kf_multi* mc);
+int  kf_multi_size(const kf_multi* mc);
+kf_ctx* kf_multi_ctx(kf_multi* mc, int i);                 /* device i's context (kf_counters, kf_last_times, ...) */
+const char* kf_multi_last_error(const kf_multi* mc);
+int  kf_multi_set_option(kf_multi* mc, const char* name, double value);   /* kf_set_option on every device */
+int  kf_fit_multi(kf_multi* mc, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out);
+#define KF_COMM_ID_BYTES 128
+int  kf_comm_unique_id(void* id, size_t bytes);            /* ncclGetUniqueId (rank 0) */
+int  kf_comm_init_rank(kf_ctx* ctx, int nranks, int rank, const void* id, size_t bytes);   /* ncclCommInitRank on ctx's device */
+int  kf_comm_destroy(kf_ctx* ctx);                         /* also done by kf_destroy */
+int  kf_comm_info(const kf_ctx* ctx, int* nranks, int* rank, int* nccl_version);
+
 /* ---- instrumentation for bench.py / tests ----------------------------- */
 /* flops issued to the FP64 tensor pipe and kernel launches since the last reset */
 int kf_counters(kf_ctx* ctx, double* dmma_flops, long long* launches, int reset);
@@ -259,7 +296,8 @@ int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, dou
  *   "as_frac" (active set: bound on the pattern change per step, fraction of the support, default 0.05, self-tuning downwards),
  *   "as_ws_gb" (active set: bound on the factor workspace), "lift_tile" (materialising lift: shared-memory tile kernel = 1),
  *   "refine" (Gram-route refinement: 0 off, 1 adaptive = default, 2 always at least one extra pass), "refine_kappa" (pivot-ratio
- *   threshold, default 1e3), "refine_level_tol" (dynamic range one level resolves, default 1e-5), "refine_max" (level limit, 4) */
+ *   threshold, default 1e3), "refine_level_tol" (dynamic range one level resolves, default 1e-5), "refine_max" (level limit, 4),
+ *   "qp_split" (multi-GPU context: split the active-set lasso sweep by columns over the ranks, default 1) */
 int kf_set_option(kf_ctx* ctx, const char* name, double value);
 
 #ifdef __cplusplus

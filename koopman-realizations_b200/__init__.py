@@ -6,4 +6,4 @@ include/koopfit.h (libkoopfit.so: hand-written sm_100a CUDA).  Import as
 """
 from . import _abi  # noqa: F401
 from ._abi import Basis, KoopfitError  # noqa: F401
-from .fitter import Fitter  # noqa: F401
+from .fitter import Fitter, MultiFitter  # noqa: F401

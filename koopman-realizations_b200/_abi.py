@@ -168,6 +168,7 @@ def load():
         "kf_block_table": (i, [i, i, i, c_int_p, c_int_p, c_int_p]),
         "kf_lift": (i, [vp, P(kf_basis), ll, c_double_p, c_double_p]),
         "kf_fit": (i, [vp, P(kf_basis), P(kf_problem), P(kf_solve), P(kf_result)]),
+        "kf_fit_dev": (i, [vp, P(kf_basis), P(kf_problem), P(kf_solve), P(kf_result)]),
         "kf_fit_series": (i, [vp, P(kf_basis), P(kf_series), P(kf_solve), P(kf_scale), P(kf_result)]),
         "kf_series_pairs": (ll, [ll, i, c_double_p]),
         "kf_fit_batch": (i, [vp, i, P(P(kf_basis)), P(kf_problem), P(kf_solve), P(kf_result)]),
@@ -184,6 +185,17 @@ def load():
         "kf_counters": (i, [vp, c_double_p, P(ll), i]),
         "kf_last_times": (i, [vp, c_double_p, c_double_p, c_double_p]),
         "kf_set_option": (i, [vp, C.c_char_p, d]),
+        "kf_create_multi": (i, [P(vp), c_int_p, i]),
+        "kf_destroy_multi": (None, [vp]),
+        "kf_multi_size": (i, [vp]),
+        "kf_multi_ctx": (vp, [vp, i]),
+        "kf_multi_last_error": (C.c_char_p, [vp]),
+        "kf_multi_set_option": (i, [vp, C.c_char_p, d]),
+        "kf_fit_multi": (i, [vp, P(kf_basis), P(kf_problem), P(kf_solve), P(kf_result)]),
+        "kf_comm_unique_id": (i, [vp, C.c_size_t]),
+        "kf_comm_init_rank": (i, [vp, i, i, vp, C.c_size_t]),
+        "kf_comm_destroy": (i, [vp]),
+        "kf_comm_info": (i, [vp, c_int_p, c_int_p, c_int_p]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)      # AttributeError if the header and the library disagree
@@ -193,5 +205,7 @@ def load():
 
 
 EXPORTS = ["kf_create", "kf_destroy", "kf_last_error", "kf_version", "kf_basis_dims", "kf_block_table",
-           "kf_lift", "kf_fit", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_set_qp_partition", "kf_mldivide", "kf_accumulate_dev", "kf_regressors_dev", "kf_lift_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
-           "kf_stream", "kf_counters", "kf_last_times", "kf_set_option"]
+           "kf_lift", "kf_fit", "kf_fit_dev", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_set_qp_partition", "kf_mldivide", "kf_accumulate_dev", "kf_regressors_dev", "kf_lift_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
+           "kf_stream", "kf_counters", "kf_last_times", "kf_set_option",
+           "kf_create_multi", "kf_destroy_multi", "kf_multi_size", "kf_multi_ctx", "kf_multi_last_error", "kf_multi_set_option", "kf_fit_multi",
+           "kf_comm_unique_id", "kf_comm_init_rank", "kf_comm_destroy", "kf_comm_info"]

@@ -211,8 +211,9 @@ bool same_layout(const KfLayout& L, const KfProgram& p, const kf_problem* pr, in
            L.N == p.N() && L.Pc == Pc;
 }
 
-// lift + Gram of one shard whose snapshots are on the device
-int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
+// lift + Gram of one shard whose snapshots are on the device; chunks [c0, c1) of the shard only (c1 < 0: to the end), so that
+// a host shard can be accumulated block by block while the next block is still being copied in (fit_host_shard)
+int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 = 0, long long c1 = -1) {
     KF_TRY(check_problem(ctx, pr));
     if (reset || !same_layout(ctx->lay, ctx->prog, pr, 0)) {
         if (!reset && ctx->lay.valid) {
@@ -230,18 +231,25 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
     const int ntasks = ntasks_of(L);
     const bool weighted = (L.model == KF_BILINEAR);
     const long long nchunks = (pr->M + L.Mc - 1) / L.Mc;
+    if (c1 < 0 || c1 > nchunks) c1 = nchunks;
+    const bool first = (c0 == 0), last = (c1 == nchunks);
     // Two software pipelines: even chunks run lift -> Gram on stream A (panel 0, slab set 0), odd chunks on
     // stream B (panel 1, slab set 1).  The pipelines are independent (own panel, own accumulator slabs), so the
     // tail wave / epilogue of one Gram launch is filled by the next chunk's CTAs and the lifts hide under DMMAs.
     const bool overlap = ctx->opt_overlap && nchunks > 1;
     cudaStream_t S[2] = {ctx->stream, overlap ? ctx->stream2 : ctx->stream};
 
-    KF_CUDA(ctx, cudaEventRecord(ctx->ev[0], S[0]));
-    if (overlap) KF_CUDA(ctx, cudaStreamWaitEvent(S[1], ctx->ev[0], 0));
+    if (first) {
+        KF_CUDA(ctx, cudaEventRecord(ctx->ev[0], S[0]));
+        ctx->gram_ms_sampled = 0.f;
+        ctx->gram_samples = 0;
+    }
+    if (overlap) {   // fork: pipeline B starts behind everything the context stream has been told to wait for
+        KF_CUDA(ctx, cudaEventRecord(ctx->ev_fork, S[0]));
+        KF_CUDA(ctx, cudaStreamWaitEvent(S[1], ctx->ev_fork, 0));
+    }
 
-    float gram_ms_sampled = 0.f;
-    int gram_samples = 0;
-    for (long long c = 0; c < nchunks; ++c) {
+    for (long long c = c0; c < c1; ++c) {
         const int b = (int)(c & 1);
         cudaStream_t sl = S[b], sg = S[b];
         KfLiftArgs a{};
@@ -277,8 +285,8 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
             KF_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
             float ms = 0.f;
             KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-            gram_ms_sampled += ms;
-            ++gram_samples;
+            ctx->gram_ms_sampled += ms;
+            ++ctx->gram_samples;
         }
         ctx->dmma_flops += (double)L.tiles.size() * 2.0 * KF_TILE_ELEMS * (double)L.Mc;
     }
@@ -287,8 +295,13 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset) {
         KF_CUDA(ctx, cudaStreamWaitEvent(S[0], ctx->ev[7], 0));
     }
     KF_CUDA(ctx, cudaEventRecord(ctx->ev[1], S[0]));
-    ctx->accum_M += pr->M;
-    ctx->last_gram_kernel_ms = gram_samples ? gram_ms_sampled / gram_samples * (float)nchunks : 0.f;
+    if (last) {
+        ctx->accum_M += pr->M;
+        // an ESTIMATE: mean duration of the sampled (isolated) Gram launches x the number of launches
+        ctx->last_gram_kernel_ms = ctx->gram_samples ? ctx->gram_ms_sampled / ctx->gram_samples * (float)nchunks : 0.f;
+        ctx->last_gram_launches = nchunks;
+        ctx->last_gram_sampled = ctx->gram_samples;
+    }
     return KF_OK;
 }
 
@@ -668,10 +681,31 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
             }
             std::vector<KfQpResult> qr(nb);
             const bool active_set = ctx->opt_qp_method == 2 || (ctx->opt_qp_method == 0 && P > 256);
-            const bool split = active_set && ctx->qp_hi > ctx->qp_lo;     // column partition across ranks
-            if (active_set)
-                KF_TRY(kf_solve_l1ball_as(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1, sv->qp_max_iter,
-                                          Kt, qr.data(), st));
+            // "lasso sweeps are split across GPUs" (north_star): with the library's own communicator the exact active-set sweep is
+            // split by COLUMNS of K automatically — rank r factors the columns shard_bounds(P, r, nranks) for all budgets, the
+            // step scalars are summed in stream order over NCCL, and the column blocks are exchanged at the end, so every rank
+            // ends up with the complete K of every budget.  (A caller-set partition, kf_set_qp_partition, takes precedence.)
+            const bool auto_split = active_set && ctx->comm && ctx->nranks > 1 && !(ctx->qp_hi > ctx->qp_lo) && c1 <= c0 && P <= 4096 &&
+                                    ctx->opt_qp_split;
+            std::vector<size_t> goff, gcnt;
+            if (auto_split) {
+                const int base = P / ctx->nranks, extra = P % ctx->nranks;
+                for (int r = 0; r < ctx->nranks; ++r) {
+                    const int lo = r * base + std::min(r, extra), hi = lo + base + (r < extra ? 1 : 0);
+                    goff.push_back((size_t)lo * Pp);
+                    gcnt.push_back((size_t)(hi - lo) * Pp);
+                    if (r == ctx->rank) { ctx->qp_lo = lo; ctx->qp_hi = hi; }
+                }
+            }
+            const bool split = active_set && !auto_split && ctx->qp_hi > ctx->qp_lo;     // caller's column partition across ranks
+            if (active_set) {
+                const int rc_as = kf_solve_l1ball_as(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1,
+                                                     sv->qp_max_iter, Kt, qr.data(), st);
+                if (auto_split) { ctx->qp_lo = 0; ctx->qp_hi = 0; }
+                if (rc_as) return rc_as;
+                if (auto_split)
+                    for (int b = 0; b < nb; ++b) KF_TRY(kf_comm_gather_blocks(ctx, Kt + (size_t)b * Pp * Pp, goff.data(), gcnt.data(), st));
+            }
             else
                 KF_TRY(kf_solve_l1ball_multi(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1, sv->qp_max_iter,
                                              sv->qp_tol, Kt, qr.data(), st));
@@ -723,41 +757,63 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
 
 }  // namespace
 
-// the fit from DEVICE snapshot pairs (prob->alpha/beta/u are device pointers, column-major, ld = M); the dictionary is prepared
-int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* solve, kf_result* out, double t0) {
+// the fit from DEVICE snapshot pairs (prob->alpha/beta/u are device pointers, column-major, ld = M); the dictionary is prepared.
+// accumulated: the caller has already run the lift + Gram of the shard (kf_fit_host_shard overlaps it with the copies).
+// host_row0 / host_ld: where this shard's rows sit in the caller's Px / Py (kf_fit_multi: one row block per device).
+int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* solve, kf_result* out, double t0, bool accumulated,
+                        long long host_row0, long long host_ld) {
     const long long M = prob->M;
     const double* d_alpha = prob->alpha;
     const double* d_beta = prob->beta;
     const double* d_u = prob->u;
-    ctx->lay.valid = false;
-    KF_TRY(accumulate_dev(ctx, prob, true));
+    if (host_ld <= 0) host_ld = M;
+    const bool multi = ctx->comm && ctx->nranks > 1;
+    if (!accumulated) {
+        ctx->lay.valid = false;
+        KF_TRY(accumulate_dev(ctx, prob, true));
+    }
     KF_TRY(finish_accum(ctx));
+    if (multi) {
+        // the ONE data-path collective of a snapshot-sharded fit: sum of the packed partial Grams (+ the snapshot count)
+        KF_TRY(write_trailer(ctx));
+        KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+        KF_TRY(kf_comm_allreduce(ctx, ctx->d_accum.as<double>(), (size_t)ctx->lay.slab, 0, ctx->stream));
+        KF_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    }
     KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->last_lift_gram_ms = ms;
     out->info.t_lift_gram_ms = ms;
     out->info.passes = 1;
+    ctx->last_allreduce_ms = 0.f;
+    if (multi) KF_CUDA(ctx, cudaEventElapsedTime(&ctx->last_allreduce_ms, ctx->ev[2], ctx->ev[3]));
     // optional materialised regressors (koopData.Px / Py, Ksysid.m:1085-1086)
     if (out->Px || out->Py) {
         const int P = ctx->lay.P;
         KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
-        KfLiftArgs a{};
-        a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
-        a.order = ctx->d_order.as<int>();
-        a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->lay.N;
-        a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
-        a.alpha = d_alpha; a.beta = d_beta; a.u = d_u; a.M = M;
+        KfLiftArgs a = lift_args_of(ctx, prob);
+        a.N = ctx->lay.N;
         if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * M * sizeof(double)));
         a.full = ctx->d_full.as<double>();
         KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, M, ctx->stream));
-        if (out->Px) KF_CUDA(ctx, cudaMemcpyAsync(out->Px, ctx->d_qr.p, (size_t)M * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        if (out->Py) KF_CUDA(ctx, cudaMemcpyAsync(out->Py, ctx->d_qr.as<double>() + (size_t)M * P, (size_t)M * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        const size_t w = (size_t)M * sizeof(double);
+        if (out->Px) KF_CUDA(ctx, cudaMemcpy2DAsync(out->Px + host_row0, (size_t)host_ld * sizeof(double), ctx->d_qr.p, w, w, P,
+                                                    cudaMemcpyDeviceToHost, ctx->stream));
+        if (out->Py) KF_CUDA(ctx, cudaMemcpy2DAsync(out->Py + host_row0, (size_t)host_ld * sizeof(double), ctx->d_qr.as<double>() + (size_t)M * P,
+                                                    w, w, P, cudaMemcpyDeviceToHost, ctx->stream));
     }
     int method = solve->ls_method;
     if (solve->least_squares && method == KF_LS_AUTO) {
         const double need = (double)M * 2.0 * ctx->lay.P * sizeof(double);
         method = (need <= ctx->opt_qr_max_gb * 1073741824.0) ? KF_LS_QR : KF_LS_GRAM;
+    }
+    if (multi && method == KF_LS_QR) {
+        if (solve->ls_method == KF_LS_QR) {
+            ctx->err = "KF_LS_QR factors the materialised regressors of ONE device; a snapshot-sharded fit solves by the (refined) Gram route";
+            return KF_EUNSUPPORTED;
+        }
+        method = KF_LS_GRAM;
     }
     int rc;
     if (solve->least_squares && method == KF_LS_QR) {
@@ -769,12 +825,8 @@ int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* sol
         KF_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
         KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
         if (!(out->Px || out->Py)) {   // not materialised above
-            KfLiftArgs a{};
-            a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
-            a.order = ctx->d_order.as<int>();
-            a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->lay.N;
-            a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
-            a.alpha = d_alpha; a.beta = d_beta; a.u = d_u; a.M = M;
+            KfLiftArgs a = lift_args_of(ctx, prob);
+            a.N = ctx->lay.N;
             if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * M * sizeof(double)));
             a.full = ctx->d_full.as<double>();
             KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, M, st));
@@ -809,6 +861,10 @@ int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* sol
             KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
             rc = refine_pass(ctx, prob);
             if (rc) break;
+            if (multi) {
+                rc = kf_comm_allreduce(ctx, ctx->rf.d_G2C2.as<double>(), (size_t)2 * ctx->lay.Pp * ctx->lay.Pp, 0, ctx->stream);
+                if (rc) break;
+            }
             KF_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
             KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             float rms = 0.f;
@@ -823,6 +879,72 @@ int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* sol
     ctx->rf.pending = false;
     out->info.t_total_ms = now_ms() - t0;
     return rc;
+}
+
+// The fit of rows [lo, hi) of the HOST snapshot pairs in `prob` (column-major, leading dimension prob->M) on this context's
+// device.  The shard is copied in blocks on a copy stream and every block is lifted and contracted as soon as it has arrived,
+// so the PCIe transfer hides under the DMMA work of the previous block (pinned host memory makes the copies truly asynchronous;
+// pageable memory — what MATLAB hands over — is staged by the driver and still overlaps with the kernels already queued).
+int kf_fit_host_shard(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, long long lo, long long hi, const kf_solve* solve,
+                      kf_result* out) {
+    if (!ctx || !out || !solve || !prob) return KF_EINVAL;
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double t0 = now_ms();
+    std::memset(&out->info, 0, sizeof(out->info));
+    KF_TRY(prepare_program(ctx, basis));
+    KF_TRY(check_problem(ctx, prob));
+    if (lo < 0 || hi > prob->M || hi <= lo) {
+        ctx->err = "kf_fit: empty or out-of-range snapshot shard";
+        return KF_EINVAL;
+    }
+    // host -> device: alpha | beta | u, column-major, ld = Mr  (Ksysid.m:1005)
+    const long long Mh = prob->M, Mr = hi - lo;
+    const size_t nz = (size_t)Mr * prob->nzeta, nu = (size_t)Mr * prob->m;
+    KF_CUDA(ctx, ctx->d_in.ensure((2 * nz + nu + 2) * sizeof(double)));
+    double* d_alpha = ctx->d_in.as<double>();
+    double* d_beta = d_alpha + nz;
+    double* d_u = d_beta + nz;
+    kf_problem dp = *prob;
+    dp.M = Mr;
+    dp.alpha = d_alpha;
+    dp.beta = d_beta;
+    dp.u = d_u;
+    // layout first: the copy blocks are whole chunks of the lifted panel
+    ctx->lay.valid = false;
+    KF_TRY(accumulate_dev(ctx, &dp, true, 0, 0));
+    const long long Mc = ctx->lay.Mc, nchunks = (Mr + Mc - 1) / Mc;
+    long long per = std::max<long long>(2, (nchunks + 15) / 16);       // <= 16 blocks, an even number of chunks each
+    per += per & 1;
+    const long long nblk = (nchunks + per - 1) / per;
+    while ((long long)ctx->copy_ev.size() < nblk) {
+        cudaEvent_t e = nullptr;
+        KF_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->copy_ev.push_back(e);
+    }
+    // the copies may only overwrite d_in once everything queued on the context stream (an earlier fit) is done
+    KF_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    KF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+    auto copy_block = [&](long long b) -> int {
+        const long long r0 = b * per * Mc, r1 = std::min(Mr, (b + 1) * per * Mc);
+        const size_t w = (size_t)(r1 - r0) * sizeof(double);
+        cudaStream_t cs = ctx->copy_stream;
+        KF_CUDA(ctx, cudaMemcpy2DAsync(d_alpha + r0, (size_t)Mr * sizeof(double), prob->alpha + lo + r0, (size_t)Mh * sizeof(double), w,
+                                       prob->nzeta, cudaMemcpyHostToDevice, cs));
+        KF_CUDA(ctx, cudaMemcpy2DAsync(d_beta + r0, (size_t)Mr * sizeof(double), prob->beta + lo + r0, (size_t)Mh * sizeof(double), w,
+                                       prob->nzeta, cudaMemcpyHostToDevice, cs));
+        if (prob->m > 0)
+            KF_CUDA(ctx, cudaMemcpy2DAsync(d_u + r0, (size_t)Mr * sizeof(double), prob->u + lo + r0, (size_t)Mh * sizeof(double), w, prob->m,
+                                           cudaMemcpyHostToDevice, cs));
+        KF_CUDA(ctx, cudaEventRecord(ctx->copy_ev[b], cs));
+        return KF_OK;
+    };
+    KF_TRY(copy_block(0));
+    for (long long b = 0; b < nblk; ++b) {
+        if (b + 1 < nblk) KF_TRY(copy_block(b + 1));
+        KF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[b], 0));
+        KF_TRY(accumulate_dev(ctx, &dp, false, b * per, std::min(nchunks, (b + 1) * per)));
+    }
+    return kf_fit_device_pairs(ctx, &dp, solve, out, t0, true, lo, Mh);
 }
 
 // ====================================================================== C ABI
@@ -860,7 +982,9 @@ int kf_create(kf_ctx** out, int device) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     if (!ok) {
         g_create_err = "kf_create: stream/event creation failed";
@@ -884,8 +1008,12 @@ void kf_destroy(kf_ctx* ctx) {
     for (KfBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    kf_comm_destroy(ctx);
+    for (cudaEvent_t e : ctx->copy_ev) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
@@ -1020,27 +1148,18 @@ int kf_sync(kf_ctx* ctx) {
 void* kf_stream(kf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int kf_fit(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out) {
-    if (!ctx || !out || !solve) return KF_EINVAL;
+    if (!ctx || !out || !solve || !prob) return KF_EINVAL;
+    return kf_fit_host_shard(ctx, basis, prob, 0, prob->M, solve, out);
+}
+
+int kf_fit_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, const kf_solve* solve, kf_result* out) {
+    if (!ctx || !out || !solve || !prob) return KF_EINVAL;
     KF_CUDA(ctx, cudaSetDevice(ctx->device));
     const double t0 = now_ms();
     std::memset(&out->info, 0, sizeof(out->info));
     KF_TRY(prepare_program(ctx, basis));
     KF_TRY(check_problem(ctx, prob));
-    // host -> device: alpha | beta | u, column-major, ld = M  (Ksysid.m:1005)
-    const long long M = prob->M;
-    const size_t nz = (size_t)M * prob->nzeta, nu = (size_t)M * prob->m;
-    KF_CUDA(ctx, ctx->d_in.ensure((2 * nz + nu + 2) * sizeof(double)));
-    double* d_alpha = ctx->d_in.as<double>();
-    double* d_beta = d_alpha + nz;
-    double* d_u = d_beta + nz;
-    KF_CUDA(ctx, cudaMemcpyAsync(d_alpha, prob->alpha, nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    KF_CUDA(ctx, cudaMemcpyAsync(d_beta, prob->beta, nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (nu) KF_CUDA(ctx, cudaMemcpyAsync(d_u, prob->u, nu * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    kf_problem dp = *prob;
-    dp.alpha = d_alpha;
-    dp.beta = d_beta;
-    dp.u = d_u;
-    return kf_fit_device_pairs(ctx, &dp, solve, out, t0);
+    return kf_fit_device_pairs(ctx, prob, solve, out, t0, false, 0, 0);
 }
 
 long long kf_series_pairs(long long T, int nd, const double* t) {
@@ -1111,7 +1230,7 @@ int kf_fit_series(kf_ctx* ctx, const kf_basis* basis, const kf_series* ser, cons
     dp.M = M; dp.nzeta = nzeta; dp.m = m; dp.model = ser->model;
     dp.alpha = d_alpha; dp.beta = d_beta; dp.u = d_uo; dp.pc_cols = ser->pc_cols;
     KF_TRY(check_problem(ctx, &dp));
-    return kf_fit_device_pairs(ctx, &dp, solve, out, t0);
+    return kf_fit_device_pairs(ctx, &dp, solve, out, t0, false, 0, 0);
 }
 
 int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, const kf_solve* solves, kf_result* outs) {
@@ -1241,6 +1360,7 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "lift_tile") ctx->opt_lift_tile = (int)value;
     else if (n == "lift_ls") ctx->opt_lift_ls = (int)value;
     else if (n == "graphs") ctx->opt_graphs = (int)value;
+    else if (n == "qp_split") ctx->opt_qp_split = (int)value;
     else if (n == "refine") ctx->opt_refine = (int)value;
     else if (n == "refine_kappa") ctx->opt_refine_kappa = value;
     else if (n == "refine_level_tol") ctx->opt_refine_level_tol = value;

@@ -133,6 +133,13 @@ struct kf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_fork = nullptr;
+    cudaStream_t copy_stream = nullptr;      // host -> device copies of kf_fit, overlapped with the lift + Gram
+    std::vector<cudaEvent_t> copy_ev;
+    // NCCL communicator of a multi-GPU fit (comm.cu): one rank per context; nullptr = single GPU
+    void* comm = nullptr;
+    int nranks = 1, rank = 0;
+    int comm_owned = 0;
     std::string err;
     int sm_count = 148;
 
@@ -161,6 +168,7 @@ struct kf_ctx {
     int opt_lift_ls = 0;      // materialising lift: snapshots per tile (8 | 16 | 32 | 64; 0 = auto)
     int opt_lift_tile = 1;    // materialising lift: whole program per 16-snapshot tile in shared memory (0: level-by-level kernel)
     int opt_tma = 1;          // Gram kernel operand path: 1 = tensor-map TMA + mbarrier ring, 0 = per-thread cp.async
+    int opt_qp_split = 1;     // multi-GPU context: split the active-set lasso sweep by columns of K over the ranks
     int opt_refine = 1;       // Gram-route refinement: 0 off, 1 adaptive, 2 always one extra pass
     double opt_refine_kappa = 1e3;      // refine when the pivot ratio of the first factorisation exceeds this
     double opt_refine_level_tol = 1e-5; // dynamic range of |R_jj| one level resolves (its square must stay well above eps)
@@ -189,6 +197,11 @@ struct kf_ctx {
     double dmma_flops = 0;
     long long launches = 0;
     float last_lift_gram_ms = 0, last_gram_kernel_ms = 0, last_solve_ms = 0, last_refine_ms = 0;
+    float gram_ms_sampled = 0;
+    int gram_samples = 0;
+    long long last_gram_launches = 0;
+    int last_gram_sampled = 0;
+    float last_allreduce_ms = 0;
     long long accum_M = 0;    // snapshots accumulated since reset
 };
 
@@ -287,7 +300,16 @@ int kf_pp_scale(kf_ctx* ctx, const double* d_y, const double* d_u, long long T, 
 int kf_pp_count_pairs(kf_ctx* ctx, const double* d_t, long long T, int nd, long long* M_out, cudaStream_t st);
 int kf_pp_pairs(kf_ctx* ctx, const double* d_t, const double* d_y, const double* d_u, const double* d_scale, long long T, int n, int m,
                 int nd, long long M, double* d_alpha, double* d_beta, double* d_uo, cudaStream_t st);
-int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* solve, kf_result* out, double t0);
+int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* solve, kf_result* out, double t0, bool accumulated = false,
+                        long long host_row0 = 0, long long host_ld = 0);
+// api.cu: the fit of rows [lo, hi) of the host snapshot pairs on this context's device (kf_fit, kf_fit_multi)
+int kf_fit_host_shard(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, long long lo, long long hi, const kf_solve* solve,
+                      kf_result* out);
+// comm.cu: collectives on the context's NCCL communicator (no-ops without one), asynchronous on `st`
+int kf_comm_allreduce(kf_ctx* ctx, double* buf, size_t count, int op_max, cudaStream_t st);
+int kf_comm_allgather(kf_ctx* ctx, const double* send, double* recv, size_t count_per_rank, cudaStream_t st);
+int kf_comm_allreduce_u64(kf_ctx* ctx, unsigned long long* buf, size_t count, cudaStream_t st);
+int kf_comm_gather_blocks(kf_ctx* ctx, double* buf, const size_t* offs, const size_t* counts, cudaStream_t st);
 
 // rollout.cu
 int kf_rollout_impl(kf_ctx* ctx, int nmodels, const kf_model* mdls, int ntrials, const int* T, const double* const* zeta0,

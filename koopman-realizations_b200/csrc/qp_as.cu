@@ -331,26 +331,27 @@ __global__ void __launch_bounds__(256) kf_as_index_kernel(const double* SG, long
     if (tid == 0) cnt[col] = base;
 }
 
-// single CTA: scal = [sum_j s'a_j, sum_j s'b_j, skipped pivots] over this rank's columns (fixed order: deterministic)
-__global__ void __launch_bounds__(256) kf_as_sums_kernel(const double* col_num, const double* col_den, const int* col_dead, int P, AsCols cs,
-                                                         double* scal) {
-    __shared__ double r0[256], r1[256], r2[256];
-    double n = 0.0, d = 0.0, dd = 0.0;
+// single CTA: scal = [sum_j s'a_j, sum_j s'b_j, skipped pivots, support size] over this rank's columns (fixed order: deterministic)
+__global__ void __launch_bounds__(256) kf_as_sums_kernel(const double* col_num, const double* col_den, const int* col_dead, const int* cnt,
+                                                         int P, AsCols cs, double* scal) {
+    __shared__ double r0[256], r1[256], r2[256], r3[256];
+    double n = 0.0, d = 0.0, dd = 0.0, nz = 0.0;
     for (int i = threadIdx.x; i < P; i += 256) {
         if (!cs.on(i)) continue;
-        n += col_num[i]; d += col_den[i]; dd += col_dead[i];
+        n += col_num[i]; d += col_den[i]; dd += col_dead[i]; nz += cnt[i];
     }
-    r0[threadIdx.x] = n; r1[threadIdx.x] = d; r2[threadIdx.x] = dd;
+    r0[threadIdx.x] = n; r1[threadIdx.x] = d; r2[threadIdx.x] = dd; r3[threadIdx.x] = nz;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
         if (threadIdx.x < s) {
             r0[threadIdx.x] += r0[threadIdx.x + s];
             r1[threadIdx.x] += r1[threadIdx.x + s];
             r2[threadIdx.x] += r2[threadIdx.x + s];
+            r3[threadIdx.x] += r3[threadIdx.x + s];
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { scal[0] = r0[0]; scal[1] = r1[0]; scal[2] = r2[0]; }
+    if (threadIdx.x == 0) { scal[0] = r0[0]; scal[1] = r1[0]; scal[2] = r2[0]; scal[3] = r3[0]; }   // [3]: support size
 }
 
 // Pattern changes that trial multipliers would cause: K(lam) = A - lam B and grad(lam) = G A - lam G B - C are both
@@ -469,6 +470,10 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
         ctx->err = "active-set QP solver: a column partition cannot be combined with pinned delay columns";
         return KF_EUNSUPPORTED;
     }
+    // Two ways to sum the step scalars over the ranks: the library's own NCCL communicator (kf_comm_init_rank /
+    // kf_create_multi) reduces the small DEVICE buffers in stream order, before they are read back — no host staging, no
+    // extra synchronisation; a caller-supplied hook (kf_set_qp_partition) reduces the host copies.
+    const bool dev_reduce = split && !ctx->qp_allreduce && ctx->comm && ctx->nranks > 1;
     auto reduce = [&](double* v, int n, int op) -> int {       // op 0 = sum, 1 = max over the ranks
         if (!split || !ctx->qp_allreduce) return KF_OK;
         if (ctx->qp_allreduce(ctx->qp_user, v, n, op)) {
@@ -540,6 +545,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
         KF_CUDA(ctx, cudaMemsetAsync(d_counts, 0, AS_NL * sizeof(unsigned long long), st));
         kf_as_count_kernel<<<egrid, 256, 0, st>>>(Am, Bm, SG, GA, GB, C, ld, P, cs, L, nl, rel, d_counts);
         KF_CUDA(ctx, cudaGetLastError());
+        if (dev_reduce) KF_TRY(kf_comm_allreduce_u64(ctx, d_counts, AS_NL, st));
         KF_CUDA(ctx, cudaMemcpyAsync(h_counts, d_counts, AS_NL * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         KF_CUDA(ctx, cudaStreamSynchronize(st));
         ctx->launches += 1;
@@ -589,9 +595,10 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
             }
             c0 = c1;
         }
-        kf_as_sums_kernel<<<1, 256, 0, st>>>(d_num, d_den, d_dead, P, cs, d_scal);
+        kf_as_sums_kernel<<<1, 256, 0, st>>>(d_num, d_den, d_dead, d_cnt, P, cs, d_scal);
+        if (dev_reduce) KF_TRY(kf_comm_allreduce(ctx, d_scal, 4, 0, st));   // s'a, s'b, skipped pivots, support size over the ranks
         double sums[4] = {0, 0, 0, 0};
-        KF_CUDA(ctx, cudaMemcpyAsync(sums, d_scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaMemcpyAsync(sums, d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (ncol > 0)
             for (int q = 0; q < 2; ++q) {        // GA = G A, GB = G B on this rank's columns  (G symmetric: row i of G = column i)
                 KfGemmGrid g{};
@@ -601,8 +608,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
                 KF_TRY(kf_launch_gemm_grid(ctx, g, st));
             }
         KF_CUDA(ctx, cudaStreamSynchronize(st));
-        for (int j = 0; j < nown; ++j) sums[3] += h_cnt[h_cols[j]];
-        KF_TRY(reduce(sums, 4, 0));                 // s'a, s'b, skipped pivots, support size: summed over the ranks
+        KF_TRY(reduce(sums, 4, 0));                 // hook path: s'a, s'b, skipped pivots, support size summed over the ranks
         const double nnz = sums[3];
         const double limit = std::max(frac * nnz, (double)P);
         // The multiplier that meets the budget on the current pattern, lam_b = (sum s'a - t) / sum s'b, under two step

@@ -114,17 +114,11 @@ class Fitter:
         sv.qp_tol = float(qp_tol)
         return sv, keep
 
-    def fit(self, basis, model_type, alpha, beta, u, want_gram=False, want_regressors=False, pc_cols=0, **solve_kw):
-        """get_Koopman for host snapshot pairs (Ksysid.m:987-1092): returns dict with K (P x P, or
-        P x P x nt for a budget vector), rank, perm, info and optionally G, C, Px, Py.
-        pc_cols > 0 (opt-in fast mode, least squares only): only the first pc_cols columns of K are computed."""
-        alpha, beta, u = A.fcol(alpha), A.fcol(beta), A.fcol(u)
-        M, nzeta = alpha.shape
-        m = u.shape[1]
+    def _run_fit(self, call, what, basis, model_type, M, nzeta, m, pa, pb, pu, want_gram, want_regressors, pc_cols, solve_kw,
+                 rows_out=None):
         _, N, P = self.dims(basis, model_type, m)
         Pc = int(pc_cols) if 0 < int(pc_cols) < P else P
-        pr = A.kf_problem(M=M, nzeta=nzeta, m=m, model=A.MODEL_CODE[model_type],
-                          alpha=alpha.ctypes.data, beta=beta.ctypes.data, u=u.ctypes.data, pc_cols=int(pc_cols))
+        pr = A.kf_problem(M=M, nzeta=nzeta, m=m, model=A.MODEL_CODE[model_type], alpha=pa, beta=pb, u=pu, pc_cols=int(pc_cols))
         sv, keep_t = self._solve_struct(**solve_kw)
         nt = max(1, sv.nt) if not sv.least_squares else 1
         res = A.kf_result()
@@ -140,13 +134,58 @@ class Fitter:
             out["G"], out["C"] = np.zeros((P, P), order="F"), np.zeros((P, P), order="F")
             res.G, res.C = A.dptr(out["G"]), A.dptr(out["C"])
         if want_regressors:
-            out["Px"], out["Py"] = np.zeros((M, P), order="F"), np.zeros((M, P), order="F")
+            rows = M if rows_out is None else rows_out
+            out["Px"], out["Py"] = np.zeros((rows, P), order="F"), np.zeros((rows, P), order="F")
             res.Px, res.Py = A.dptr(out["Px"]), A.dptr(out["Py"])
-        self._check(self.lib.kf_fit(self.ctx, basis.ref(), C.byref(pr), C.byref(sv), C.byref(res)), "kf_fit")
+        call(basis.ref(), C.byref(pr), C.byref(sv), C.byref(res))
         info = {f: getattr(res.info, f) for f, _ in A.kf_info._fields_}
         out.update(K=K[:, :, 0] if nt == 1 else K, K_all=K, rank=info["rank"], perm=perm, info=info, N=N, P=P,
                    objective=obj, l1norm=l1, qp_iters=iters, qp_gap=gap)
         return out
+
+    def fit(self, basis, model_type, alpha, beta, u, want_gram=False, want_regressors=False, pc_cols=0, **solve_kw):
+        """get_Koopman for host snapshot pairs (Ksysid.m:987-1092): returns dict with K (P x P, or
+        P x P x nt for a budget vector), rank, perm, info and optionally G, C, Px, Py.
+        pc_cols > 0 (opt-in fast mode, least squares only): only the first pc_cols columns of K are computed.
+        On a context that joined a communicator (comm_init) alpha / beta / u are THIS RANK's shard."""
+        alpha, beta, u = A.fcol(alpha), A.fcol(beta), A.fcol(u)
+        M, nzeta = alpha.shape
+        m = u.shape[1]
+
+        def call(b, pr, sv, res):
+            self._check(self.lib.kf_fit(self.ctx, b, pr, sv, res), "kf_fit")
+        return self._run_fit(call, "kf_fit", basis, model_type, M, nzeta, m, alpha.ctypes.data, beta.ctypes.data, u.ctypes.data,
+                             want_gram, want_regressors, pc_cols, solve_kw)
+
+    def fit_dev(self, basis, model_type, M, nzeta, m, alpha_ptr, beta_ptr, u_ptr, want_gram=False, pc_cols=0, **solve_kw):
+        """kf_fit_dev: the whole fit from DEVICE-resident snapshot pairs (pointers from torch tensors' data_ptr(); column-major
+        M x nzeta, i.e. contiguous torch tensors of shape (nzeta, M)); on a multi-GPU context the all-reduce and any
+        refinement passes run inside the library."""
+        def call(b, pr, sv, res):
+            self._check(self.lib.kf_fit_dev(self.ctx, b, pr, sv, res), "kf_fit_dev")
+        return self._run_fit(call, "kf_fit_dev", basis, model_type, int(M), int(nzeta), int(m), int(alpha_ptr), int(beta_ptr), int(u_ptr),
+                             want_gram, False, pc_cols, solve_kw)
+
+    # ------------------------------------------------------------------ multi-GPU: one process per GPU
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id (kf_comm_unique_id); draw it on rank 0 and broadcast it to the other ranks."""
+        lib = A.load()
+        buf = C.create_string_buffer(128)
+        rc = lib.kf_comm_unique_id(buf, 128)
+        if rc:
+            raise A.KoopfitError("kf_comm_unique_id failed: NCCL unavailable")
+        return buf.raw
+
+    def comm_init(self, nranks, rank, unique_id):
+        """Join the library-owned NCCL communicator (kf_comm_init_rank); collective over all ranks."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.kf_comm_init_rank(self.ctx, int(nranks), int(rank), buf, 128), "kf_comm_init_rank")
+
+    def comm_info(self):
+        n, r, v = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.kf_comm_info(self.ctx, C.byref(n), C.byref(r), C.byref(v)), "kf_comm_info")
+        return {"nranks": n.value, "rank": r.value, "nccl_version": v.value}
 
     def fit_series(self, basis, model_type, t, y, u, nd=0, prescaled=False, want_gram=False, want_regressors=False, pc_cols=0,
                    **solve_kw):
@@ -364,3 +403,45 @@ class Fitter:
         out.update(K=K[:, :, 0] if nt == 1 else K, K_all=K, rank=info["rank"], perm=st["perm"], info=info, P=P,
                    objective=st["obj"], l1norm=st["l1"], qp_iters=st["iters"], qp_gap=st["gap"])
         return out
+
+
+class MultiFitter(Fitter):
+    """One process, several GPUs (kf_create_multi / kf_fit_multi): what the MEX shim uses to reach every visible B200 from a
+    single MATLAB session.  `fit` has Fitter.fit's contract on the FULL host snapshot pairs; the split into per-device shards,
+    the NCCL all-reduce of the partial Grams and the column split of a lasso sweep happen inside the library."""
+
+    def __init__(self, devices=None):
+        self.lib = A.load()
+        self.mc = C.c_void_p()
+        if devices is None:
+            rc = self.lib.kf_create_multi(C.byref(self.mc), None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.kf_create_multi(C.byref(self.mc), arr, len(devices))
+        if rc:
+            raise A.KoopfitError(f"kf_create_multi failed ({A.ERRORS.get(rc, rc)}): {self.lib.kf_last_error(None).decode()}")
+        self.ndev = self.lib.kf_multi_size(self.mc)
+        self.ctx = C.c_void_p(self.lib.kf_multi_ctx(self.mc, 0))       # device 0's context: dims, options, counters
+
+    def close(self):
+        if getattr(self, "mc", None) and self.mc.value:
+            self.lib.kf_destroy_multi(self.mc)
+            self.mc = C.c_void_p()
+            self.ctx = C.c_void_p()
+
+    def set_option(self, name, value):
+        rc = self.lib.kf_multi_set_option(self.mc, name.encode(), float(value))
+        if rc:
+            raise A.KoopfitError(f"kf_multi_set_option({name}) failed")
+
+    def fit(self, basis, model_type, alpha, beta, u, want_gram=False, want_regressors=False, pc_cols=0, **solve_kw):
+        alpha, beta, u = A.fcol(alpha), A.fcol(beta), A.fcol(u)
+        M, nzeta = alpha.shape
+        m = u.shape[1]
+
+        def call(b, pr, sv, res):
+            rc = self.lib.kf_fit_multi(self.mc, b, pr, sv, res)
+            if rc:
+                raise A.KoopfitError(f"kf_fit_multi failed ({A.ERRORS.get(rc, rc)}): {self.lib.kf_multi_last_error(self.mc).decode()}")
+        return self._run_fit(call, "kf_fit_multi", basis, model_type, M, nzeta, m, alpha.ctypes.data, beta.ctypes.data, u.ctypes.data,
+                             want_gram, want_regressors, pc_cols, solve_kw)
