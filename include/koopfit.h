@@ -67,7 +67,9 @@ typedef struct {
     int pc_cols;            /* opt-in fast mode: compute only the first pc_cols columns of K (and C); 0 = all P.
                                Downstream only K(:,1:N) (linear, bilinear: A, B — Ksysid.m:1199-1200, 1258-1259) or
                                K(:,1:nzeta) (nonlinear: F — 1329) is consumed; least-squares branch only. */
-    int reserved;
+    int nw;                 /* `loaded` model (Ksysid.m:88-93, 539-626): columns of w; 0 = unloaded.  The lifted state becomes
+                               [1; w] (x) psi  (psi, w_1 psi, ..., w_nw psi: Ksysid.m:594-599), so P = N (nw+1) [+ m | x (m+1)] */
+    const double* w;        /* M x nw load of every snapshot pair (snapshotPairs.w, Ksysid.m:953-957), or NULL */
 } kf_problem;
 
 /* how to solve (Ksysid.m:1068-1080) */
@@ -215,6 +217,16 @@ typedef struct {
  * Error metrics (get_error, 1882-1898) stay on the host. */
 int kf_rollout(kf_ctx* ctx, const kf_basis* basis, int nmodels, const kf_model* models, int ntrials, const int* T,
                const double* const* zeta0, const double* const* u, int nout, double* const* ysim);
+
+/* ---- consumer side: bilinear MPC cost assembly ------------------
+ * Kmpc.get_costB_bilinear (Kmpc.m:569-596): the state-dependent condensed input matrix of the bilinear MPC problem, rebuilt at
+ * every control step from the fitted model (A: N x N, B = [B_1 ... B_m]: N x N m as get_BLmodel returns them, Ksysid.m:1258-1259).
+ *   block row i (i = 1..h) of the first block column = A^(i-1) Beta(z_i),  Beta(z) = B kron(I_m, z)  (Ksysid.m:1288-1289),
+ *   z_i = z(i,:) when z has `horizon` rows, z(1,:) when it has one;  block column c = the first one shifted down by c-1 blocks.
+ * nbatch problems in one launch: z is nbatch consecutive (nz x N) column-major matrices, Bout nbatch consecutive
+ * (N (h+1)) x (m h) column-major matrices (HOST buffers). */
+int kf_mpc_costB_bilinear(kf_ctx* ctx, int N, int m, int horizon, int nbatch, const double* A, const double* B, int nz,
+                          const double* z, double* Bout);
 
 /* ---- lasso sweep split across ranks (one process per GPU) -------------------
  * After the all-reduce of the partial Grams every rank holds the same G, C.  With a column partition the exact

@@ -40,7 +40,13 @@ class kf_basis(C.Structure):
 class kf_problem(C.Structure):
     _fields_ = [("M", C.c_longlong), ("nzeta", C.c_int), ("m", C.c_int), ("model", C.c_int),
                 ("alpha", C.c_void_p), ("beta", C.c_void_p), ("u", C.c_void_p),
-                ("pc_cols", C.c_int), ("reserved", C.c_int)]
+                ("pc_cols", C.c_int), ("nw", C.c_int), ("w", C.c_void_p)]
+
+
+def regressor_width(model_type, N, m, nw=0):
+    """P of the regressor (Ksysid.m:1019-1028): N (nw+1) + m | N (nw+1) (m+1) | N (nw+1)."""
+    NL = N * (nw + 1)
+    return {"linear": NL + m, "bilinear": NL * (m + 1), "nonlinear": NL}[model_type]
 
 
 class kf_solve(C.Structure):
@@ -173,6 +179,7 @@ def load():
         "kf_series_pairs": (ll, [ll, i, c_double_p]),
         "kf_fit_batch": (i, [vp, i, P(P(kf_basis)), P(kf_problem), P(kf_solve), P(kf_result)]),
         "kf_rollout": (i, [vp, P(kf_basis), i, P(kf_model), i, c_int_p, P(c_double_p), P(c_double_p), i, P(c_double_p)]),
+        "kf_mpc_costB_bilinear": (i, [vp, i, i, i, i, c_double_p, c_double_p, i, c_double_p, c_double_p]),
         "kf_set_qp_partition": (i, [vp, i, i, ALLREDUCE_FN, vp]),
         "kf_mldivide": (i, [vp, ll, i, i, c_double_p, c_double_p, c_double_p, c_int_p, c_int_p]),
         "kf_accumulate_dev": (i, [vp, P(kf_basis), P(kf_problem), i]),
@@ -205,7 +212,7 @@ def load():
 
 
 EXPORTS = ["kf_create", "kf_destroy", "kf_last_error", "kf_version", "kf_basis_dims", "kf_block_table",
-           "kf_lift", "kf_fit", "kf_fit_dev", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_set_qp_partition", "kf_mldivide", "kf_accumulate_dev", "kf_regressors_dev", "kf_lift_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
+           "kf_lift", "kf_fit", "kf_fit_dev", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_mpc_costB_bilinear", "kf_set_qp_partition", "kf_mldivide", "kf_accumulate_dev", "kf_regressors_dev", "kf_lift_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
            "kf_stream", "kf_counters", "kf_last_times", "kf_set_option",
            "kf_create_multi", "kf_destroy_multi", "kf_multi_size", "kf_multi_ctx", "kf_multi_last_error", "kf_multi_set_option", "kf_fit_multi",
            "kf_comm_unique_id", "kf_comm_init_rank", "kf_comm_destroy", "kf_comm_info"]

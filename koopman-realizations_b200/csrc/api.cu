@@ -55,6 +55,14 @@ int check_problem(kf_ctx* ctx, const kf_problem* pr) {
         ctx->err = "Invalid model_type chosen. Must be linear, bilinear, or nonlinear.";   // Ksysid.m:103
         return KF_EINVAL;
     }
+    if (pr->nw < 0 || (pr->nw > 0 && !pr->w)) {
+        ctx->err = "kf_problem: a loaded model (nw > 0) needs the loads w (M x nw)";
+        return KF_EINVAL;
+    }
+    if (pr->nw > 0 && pr->pc_cols > 0) {
+        ctx->err = "kf_problem: pc_cols is not supported for loaded models";
+        return KF_EINVAL;
+    }
     const int nv = pr->nzeta + (pr->model == KF_NONLINEAR ? pr->m : 0);
     if (ctx->prog.nv != nv) {
         ctx->err = "kf_basis.nv must equal nzeta (linear, bilinear) or nzeta+m (nonlinear)";
@@ -73,7 +81,9 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
     L.nv = p.nv;
     L.n_full = p.n_full();
     L.N = p.N();
-    L.P = kf_regressor_width(L.model, L.N, L.m);
+    L.nw = pr->nw;
+    L.dense = pr->nw > 0;
+    L.P = kf_regressor_width(L.model, L.N, L.m, L.nw);
     L.Rx = L.N + (L.model == KF_LINEAR ? L.m : 0);
     L.Rxp = (int)kf_roundup(L.Rx, KF_BM);
     L.Ny = L.N;
@@ -85,6 +95,19 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
     L.rows = L.w_off + (int)kf_roundup(L.nW, 8);
     L.Pp = (int)kf_roundup(L.P, KF_BM);
     L.Pc = (pr->pc_cols > 0 && pr->pc_cols < L.P) ? pr->pc_cols : L.P;
+    if (L.dense) {
+        // `loaded` model: [1; u] (x) [1; w] (x) psi.  The weighted-block accumulator is specialised to [1; u] (x) psi, so G and C are
+        // accumulated densely from the materialised regressors of each chunk (dense_pass) — same collective, same solvers.
+        L.slab = 2LL * L.Pp * L.Pp + KF_ACC_TRAILER;
+        long long Mc = ctx->opt_chunk > 0 ? ctx->opt_chunk : (long long)(ctx->opt_panel_mb * 1048576.0 / (8.0 * (2.0 * L.P + KF_BM)));
+        Mc = std::max<long long>(256, std::min<long long>(Mc / 256 * 256, 8192));
+        L.Mc = (int)Mc;
+        L.nsplit = 1;
+        L.valid = true;
+        KF_CUDA(ctx, ctx->rf.d_dense.ensure((size_t)L.slab * sizeof(double)));
+        ctx->lay = L;
+        return KF_OK;
+    }
 
     // chunk: one panel should stay L2-resident
     long long Mc = ctx->opt_chunk > 0 ? ctx->opt_chunk
@@ -205,11 +228,14 @@ int ntasks_of(const KfLayout& L) {
 
 bool same_layout(const KfLayout& L, const KfProgram& p, const kf_problem* pr, int Mc_hint) {
     (void)Mc_hint;
-    const int P = kf_regressor_width(pr->model, p.N(), pr->m);
+    const int P = kf_regressor_width(pr->model, p.N(), pr->m, pr->nw);
     const int Pc = (pr->pc_cols > 0 && pr->pc_cols < P) ? pr->pc_cols : P;
     return L.valid && L.model == pr->model && L.m == pr->m && L.nzeta == pr->nzeta && L.n_full == p.n_full() &&
-           L.N == p.N() && L.Pc == Pc;
+           L.N == p.N() && L.Pc == Pc && L.nw == pr->nw;
 }
+
+int dense_pass(kf_ctx* ctx, const kf_problem* pr, const double* St, double* GC, int Mc, long long c0, long long c1);
+double* accum_base(kf_ctx* ctx) { return ctx->lay.dense ? ctx->rf.d_dense.as<double>() : ctx->d_accum.as<double>(); }
 
 // lift + Gram of one shard whose snapshots are on the device; chunks [c0, c1) of the shard only (c1 < 0: to the end), so that
 // a host shard can be accumulated block by block while the next block is still being copied in (fit_host_shard)
@@ -222,12 +248,23 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
         }
         KF_TRY(make_layout(ctx, pr));
         const KfLayout& L = ctx->lay;
-        KF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)2 * L.nsplit * L.slab * sizeof(double), ctx->stream));
+        if (L.dense) KF_CUDA(ctx, cudaMemsetAsync(ctx->rf.d_dense.p, 0, (size_t)L.slab * sizeof(double), ctx->stream));
+        else KF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)2 * L.nsplit * L.slab * sizeof(double), ctx->stream));
         ctx->accum_M = 0;
         ctx->rf.pending = false;
     }
     const KfLayout& L = ctx->lay;
     const KfProgram& p = ctx->prog;
+    if (L.dense) {
+        const long long nch = (pr->M + L.Mc - 1) / L.Mc;
+        if (c1 < 0 || c1 > nch) c1 = nch;
+        if (c0 == 0) KF_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        KF_TRY(dense_pass(ctx, pr, nullptr, ctx->rf.d_dense.as<double>(), L.Mc, c0, c1));
+        KF_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (c1 == nch) ctx->accum_M += pr->M;
+        ctx->last_gram_kernel_ms = 0.f;
+        return KF_OK;
+    }
     const int ntasks = ntasks_of(L);
     const bool weighted = (L.model == KF_BILINEAR);
     const long long nchunks = (pr->M + L.Mc - 1) / L.Mc;
@@ -307,6 +344,7 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
 
 int finish_accum(kf_ctx* ctx) {
     const KfLayout& L = ctx->lay;
+    if (L.dense) return KF_OK;
     KF_TRY(kf_reduce_slabs(ctx, ctx->d_accum.as<double>(), L.slab, 2 * L.nsplit, ctx->stream));
     return KF_OK;
 }
@@ -316,7 +354,7 @@ int finish_accum(kf_ctx* ctx) {
 int write_trailer(kf_ctx* ctx) {
     const KfLayout& L = ctx->lay;
     ctx->accum_M_d = (double)ctx->accum_M;
-    KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_accum.as<double>() + (L.slab - KF_ACC_TRAILER), &ctx->accum_M_d, sizeof(double),
+    KF_CUDA(ctx, cudaMemcpyAsync(accum_base(ctx) + (L.slab - KF_ACC_TRAILER), &ctx->accum_M_d, sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->stream));
     return KF_OK;
 }
@@ -336,6 +374,7 @@ KfLiftArgs lift_args_of(kf_ctx* ctx, const kf_problem* pr) {
     a.nv = p.nv; a.n_full = p.n_full(); a.n_pcs = p.n_pcs; a.N = p.N();
     a.nzeta = pr->nzeta; a.m = pr->m; a.model = pr->model;
     a.alpha = pr->alpha; a.beta = pr->beta; a.u = pr->u; a.M = pr->M;
+    a.w = pr->nw > 0 ? pr->w : nullptr; a.nw = pr->nw;
     return a;
 }
 
@@ -362,33 +401,45 @@ int refine_pass(kf_ctx* ctx, const kf_problem* pr) {
         ctx->err = "refinement pass: no pending refinement for this problem layout";
         return KF_EINVAL;
     }
+    return dense_pass(ctx, pr, R.d_St.as<double>(), R.d_G2C2.as<double>(), R.Mc, 0, -1);
+}
+
+// Dense accumulation over the chunks [c0, c1) of a shard:  GC = [G | C] (each Pp x Pp) += Z Z' and Z Py', with Z = S Px
+// (St = S' column-major, the refinement basis) or Z = Px (St == nullptr: the plain dense Gram of a `loaded` model).
+int dense_pass(kf_ctx* ctx, const kf_problem* pr, const double* St, double* GC, int Mc, long long c0, long long c1) {
+    KfRefine& R = ctx->rf;
+    const KfLayout& L = ctx->lay;
     cudaStream_t st = ctx->stream;
-    const int P = L.P, Pp = L.Pp, Mc = R.Mc;
+    const int P = L.P, Pp = L.Pp;
     const long long rp_rows = 2LL * P + KF_BM;          // rows [0,P) Px, [P,2P) Py, finite padding behind (k range runs to Pp)
-    const bool fresh = ctx->rf.d_RP.bytes < (size_t)rp_rows * Mc * sizeof(double);
+    const bool fresh = R.d_RP.bytes < (size_t)rp_rows * Mc * sizeof(double);
     KF_CUDA(ctx, R.d_RP.ensure((size_t)rp_rows * Mc * sizeof(double)));
-    KF_CUDA(ctx, R.d_Z.ensure((size_t)Pp * Mc * sizeof(double)));
+    if (St) KF_CUDA(ctx, R.d_Z.ensure((size_t)Pp * Mc * sizeof(double)));
     if (fresh) KF_CUDA(ctx, cudaMemsetAsync(R.d_RP.p, 0, (size_t)rp_rows * Mc * sizeof(double), st));
     if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * ctx->prog.n_full() * Mc * sizeof(double)));
     double* RP = R.d_RP.as<double>();
-    double* Z = R.d_Z.as<double>();
-    double* G2 = R.d_G2C2.as<double>();
+    double* Z = St ? R.d_Z.as<double>() : RP;
+    double* G2 = GC;
     double* C2 = G2 + (size_t)Pp * Pp;
     const long long nchunks = (pr->M + Mc - 1) / Mc;
-    for (long long c = 0; c < nchunks; ++c) {
+    if (c1 < 0 || c1 > nchunks) c1 = nchunks;
+    for (long long c = c0; c < c1; ++c) {
         const long long count = std::min<long long>(Mc, pr->M - c * Mc);
         if (count < Mc) KF_CUDA(ctx, cudaMemsetAsync(RP, 0, (size_t)2 * P * Mc * sizeof(double), st));   // tail columns contribute zeros
         KfLiftArgs a = lift_args_of(ctx, pr);
+        a.N = L.N;
         a.start = c * Mc;
         a.Mc = Mc;
         a.full = ctx->d_full.as<double>();
         KF_TRY(kf_launch_regressors(ctx, a, RP, nullptr, Mc, st));
-        KfGemmGrid g{};
-        g.A = R.d_St.as<double>(); g.lda = Pp;           // A[q][i] = S(q, i): row q of S contiguous in i (= S' column-major)
-        g.B = RP; g.ldb = Mc;                            // B[i][snapshot]
-        g.out = Z; g.ldm = Mc; g.ldn = 1;
-        g.m = P; g.n = Mc; g.k0 = 0; g.k1 = Pp; g.alpha = 1.0; g.accumulate = 0;
-        KF_TRY(kf_launch_gemm_bkmajor(ctx, g, st));
+        if (St) {
+            KfGemmGrid g{};
+            g.A = St; g.lda = Pp;                            // A[q][i] = S(q, i): row q of S contiguous in i (= S' column-major)
+            g.B = RP; g.ldb = Mc;                            // B[i][snapshot]
+            g.out = Z; g.ldm = Mc; g.ldn = 1;
+            g.m = P; g.n = Mc; g.k0 = 0; g.k1 = Pp; g.alpha = 1.0; g.accumulate = 0;
+            KF_TRY(kf_launch_gemm_bkmajor(ctx, g, st));
+        }
         KfGemmGrid gg{};                                 // G2(m, n) += sum_s Z[m][s] Z[n][s], lower tiles
         gg.A = Z; gg.B = Z; gg.lda = gg.ldb = Mc; gg.out = G2; gg.ldm = 1; gg.ldn = Pp;
         gg.m = P; gg.n = P; gg.k0 = 0; gg.k1 = Mc; gg.alpha = 1.0; gg.accumulate = 1; gg.lower_only = 1;
@@ -553,13 +604,19 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
     KF_CUDA(ctx, ctx->d_misc.ensure(4096));
     KF_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
     if (!ctx->rf.pending) {
+        if (L.dense) {
+            double* GC = ctx->rf.d_dense.as<double>();
+            KF_TRY(kf_rf_symmetrize(ctx, GC, Pp, st));
+            KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_G.p, GC, mat, cudaMemcpyDeviceToDevice, st));
+            KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_C.p, GC + (size_t)Pp * Pp, mat, cudaMemcpyDeviceToDevice, st));
+        } else
         KF_TRY(kf_assemble(ctx, ctx->d_accum.as<double>(), ctx->d_tilemeta.as<KfTile>(), (int)L.tiles.size(), L,
                            ctx->d_G.as<double>(), ctx->d_C.as<double>(), st));
         KF_TRY(copy_out_matrix(ctx, ctx->d_G.as<double>(), Pp, P, out->G));
         KF_TRY(copy_out_matrix(ctx, ctx->d_C.as<double>(), Pp, P, out->C));
         // total snapshot count: the trailer of the accumulator if it went through an all-reduce, else this rank's count
         double tr = 0;
-        KF_CUDA(ctx, cudaMemcpyAsync(&tr, ctx->d_accum.as<double>() + (L.slab - KF_ACC_TRAILER), sizeof(double), cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaMemcpyAsync(&tr, accum_base(ctx) + (L.slab - KF_ACC_TRAILER), sizeof(double), cudaMemcpyDeviceToHost, st));
         KF_CUDA(ctx, cudaStreamSynchronize(st));
         ctx->rf.M_total = tr >= 1.0 ? (long long)(tr + 0.5) : ctx->accum_M;
     }
@@ -777,7 +834,7 @@ int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* sol
         // the ONE data-path collective of a snapshot-sharded fit: sum of the packed partial Grams (+ the snapshot count)
         KF_TRY(write_trailer(ctx));
         KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-        KF_TRY(kf_comm_allreduce(ctx, ctx->d_accum.as<double>(), (size_t)ctx->lay.slab, 0, ctx->stream));
+        KF_TRY(kf_comm_allreduce(ctx, accum_base(ctx), (size_t)ctx->lay.slab, 0, ctx->stream));
         KF_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     }
     KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -899,16 +956,18 @@ int kf_fit_host_shard(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob
     }
     // host -> device: alpha | beta | u, column-major, ld = Mr  (Ksysid.m:1005)
     const long long Mh = prob->M, Mr = hi - lo;
-    const size_t nz = (size_t)Mr * prob->nzeta, nu = (size_t)Mr * prob->m;
-    KF_CUDA(ctx, ctx->d_in.ensure((2 * nz + nu + 2) * sizeof(double)));
+    const size_t nz = (size_t)Mr * prob->nzeta, nu = (size_t)Mr * prob->m, nwd = (size_t)Mr * prob->nw;
+    KF_CUDA(ctx, ctx->d_in.ensure((2 * nz + nu + nwd + 2) * sizeof(double)));
     double* d_alpha = ctx->d_in.as<double>();
     double* d_beta = d_alpha + nz;
     double* d_u = d_beta + nz;
+    double* d_w = d_u + nu;
     kf_problem dp = *prob;
     dp.M = Mr;
     dp.alpha = d_alpha;
     dp.beta = d_beta;
     dp.u = d_u;
+    dp.w = prob->nw > 0 ? d_w : nullptr;
     // layout first: the copy blocks are whole chunks of the lifted panel
     ctx->lay.valid = false;
     KF_TRY(accumulate_dev(ctx, &dp, true, 0, 0));
@@ -934,6 +993,9 @@ int kf_fit_host_shard(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob
                                        prob->nzeta, cudaMemcpyHostToDevice, cs));
         if (prob->m > 0)
             KF_CUDA(ctx, cudaMemcpy2DAsync(d_u + r0, (size_t)Mr * sizeof(double), prob->u + lo + r0, (size_t)Mh * sizeof(double), w, prob->m,
+                                           cudaMemcpyHostToDevice, cs));
+        if (prob->nw > 0)
+            KF_CUDA(ctx, cudaMemcpy2DAsync(d_w + r0, (size_t)Mr * sizeof(double), prob->w + lo + r0, (size_t)Mh * sizeof(double), w, prob->nw,
                                            cudaMemcpyHostToDevice, cs));
         KF_CUDA(ctx, cudaEventRecord(ctx->copy_ev[b], cs));
         return KF_OK;
@@ -1003,7 +1065,7 @@ void kf_destroy(kf_ctx* ctx) {
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,
                      &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups,
-                     &ctx->rf.d_S, &ctx->rf.d_St, &ctx->rf.d_Sp, &ctx->rf.d_G2C2, &ctx->rf.d_RP, &ctx->rf.d_Z};
+                     &ctx->rf.d_S, &ctx->rf.d_St, &ctx->rf.d_Sp, &ctx->rf.d_G2C2, &ctx->rf.d_RP, &ctx->rf.d_Z, &ctx->rf.d_dense};
     if (ctx->pchol_graph.exec) cudaGraphExecDestroy(ctx->pchol_graph.exec);
     for (KfBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i)
@@ -1084,12 +1146,7 @@ int kf_regressors_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob
     ctx->lay.valid = false;
     KF_TRY(check_problem(ctx, prob));
     if (ld < prob->M) { ctx->err = "kf_regressors_dev: ld < M"; return KF_EINVAL; }
-    KfLiftArgs a{};
-    a.ops = ctx->d_ops.as<KfOp>(); a.centres = ctx->d_centres.as<double>(); a.pcs = ctx->d_pcs.as<double>();
-    a.order = ctx->d_order.as<int>();
-    a.nv = ctx->prog.nv; a.n_full = ctx->prog.n_full(); a.n_pcs = ctx->prog.n_pcs; a.N = ctx->prog.N();
-    a.nzeta = prob->nzeta; a.m = prob->m; a.model = prob->model;
-    a.alpha = prob->alpha; a.beta = prob->beta; a.u = prob->u; a.M = prob->M;
+    KfLiftArgs a = lift_args_of(ctx, prob);
     if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * prob->M * sizeof(double)));
     a.full = ctx->d_full.as<double>();
     return kf_launch_regressors(ctx, a, dev_PxPy, nullptr, ld, ctx->stream);
@@ -1116,7 +1173,7 @@ int kf_accum_buffer(kf_ctx* ctx, double** dev_ptr, size_t* count) {
     }
     KF_TRY(finish_accum(ctx));     // all slabs -> slab 0 (the folded slabs are zeroed, so this is idempotent)
     KF_TRY(write_trailer(ctx));    // + this rank's snapshot count, summed by the same all-reduce
-    if (dev_ptr) *dev_ptr = ctx->d_accum.as<double>();
+    if (dev_ptr) *dev_ptr = accum_base(ctx);
     if (count) *count = (size_t)ctx->lay.slab;
     return KF_OK;
 }
@@ -1249,7 +1306,7 @@ int kf_fit_batch(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_
         // every budget (evaluate_rand_models.m fits its nonlinear models with lasso = 4, usually inactive) it is the QP answer too
         const bool solve_ok = solves[i].least_squares ||
                               (solves[i].nt >= 1 && solves[i].t && !solves[i].delay_constraint && solves[i].psd_shift != KF_PSD_ALWAYS);
-        const bool ok = solve_ok && P <= 32 && probs[i].pc_cols == 0 && bases[i]->n_pcs == 0 && probs[i].M > 0 && probs[i].alpha &&
+        const bool ok = solve_ok && P <= 32 && probs[i].pc_cols == 0 && probs[i].nw == 0 && bases[i]->n_pcs == 0 && probs[i].M > 0 && probs[i].alpha &&
                         probs[i].beta && (probs[i].m == 0 || probs[i].u) && !outs[i].G && !outs[i].C && !outs[i].Px && !outs[i].Py &&
                         (probs[i].model == KF_LINEAR || probs[i].model == KF_BILINEAR || probs[i].model == KF_NONLINEAR) &&
                         bases[i]->nv == probs[i].nzeta + (probs[i].model == KF_NONLINEAR ? probs[i].m : 0);

@@ -86,7 +86,8 @@ struct KfTile {
 };
 
 struct KfLayout {
-    int model = 0, m = 0, nzeta = 0, nv = 0;
+    int model = 0, m = 0, nzeta = 0, nv = 0, nw = 0;
+    bool dense = false;       // `loaded` models: G, C accumulated densely from the materialised regressors (rf.d_dense)
     int n_full = 0, N = 0, P = 0;
     int Pc = 0;               // columns of C / K actually computed (pc_cols fast mode), <= P
     int Rx = 0, Rxp = 0;      // rows of the X section: N (+m for linear), padded to BM
@@ -117,6 +118,7 @@ struct KfRefine {
     KfBuf d_S, d_St, d_Sp;    // basis S (row = new feature, column = original; column-major), its transpose, Pi S
     KfBuf d_G2C2;             // [G2 | C2] of the new features: what the ranks all-reduce in a refinement pass
     KfBuf d_RP, d_Z;          // chunk panels: materialised [Px | Py] rows and the transformed features
+    KfBuf d_dense;            // `loaded` models: dense accumulator [G | C | trailer] (2 Pp^2 + KF_ACC_TRAILER doubles)
 };
 
 // the blocked pivoted Cholesky of kf_solve_gram_ls as an instantiated CUDA graph, valid for one set of buffers / sizes
@@ -256,6 +258,7 @@ struct KfLiftArgs {
     int nv, n_full, n_pcs, N;
     int nzeta, m, model;
     const double* alpha; const double* beta; const double* u;   // device, column-major, ld = M
+    const double* w; int nw;                                    // loads (M x nw, ld = M) of a `loaded` model, or nullptr / 0
     long long M, start;   // chunk = snapshots [start, start+Mc)
     int Mc;
     double* panel; long long ld;   // panel row stride (= Mc)

@@ -91,26 +91,32 @@ __global__ void __launch_bounds__(LIFT_THREADS) kf_lift_econ_kernel(const KfLift
 }
 
 // Complete materialised regressors AB = [Px | Py] (M x 2P, ld): columns [0,N) and [P,P+N)
-// already hold psi(x), psi(y).  linear: append u to both (Ksysid.m:1062-1063); bilinear:
-// blocks u_k * psi (Ksysid.m:510-511).
-__global__ void kf_regressor_post_kernel(int model, int N, int P, int m, const double* __restrict__ u, long long M, long long ldu,
-                                         double* AB, long long ld) {
+// already hold psi(x), psi(y).  Kronecker blocks u_ka * (w_kc * psi) (bilinear: Ksysid.m:510-511; loaded: 594-599, 604-605),
+// and for the linear model u appended to both (Ksysid.m:1062-1063).
+__global__ void kf_regressor_post_kernel(int model, int N, int P, int m, int nw, const double* __restrict__ u, const double* __restrict__ w,
+                                         long long M, long long ldu, double* AB, long long ld) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= M) return;
-    if (model == KF_LINEAR) {
+    const int nku = model == KF_BILINEAR ? m : 0;
+    const int j0 = blockIdx.y * 64;
+    for (int ka = 0; ka <= nku; ++ka)
+        for (int kc = 0; kc <= nw; ++kc) {
+            if (ka == 0 && kc == 0) continue;
+            const double ua = ka ? u[(long long)(ka - 1) * ldu + s] : 1.0, wc = kc ? w[(long long)(kc - 1) * ldu + s] : 1.0;
+            const long long col = (long long)(ka * (nw + 1) + kc) * N;
+            for (int j = j0; j < min(N, j0 + 64); ++j) {
+                double x = AB[(long long)j * ld + s], y = AB[(long long)(P + j) * ld + s];
+                if (kc) { x = KF_MUL(wc, x); y = KF_MUL(wc, y); }
+                if (ka) { x = KF_MUL(ua, x); y = KF_MUL(ua, y); }
+                AB[(col + j) * ld + s] = x;
+                AB[(P + col + j) * ld + s] = y;
+            }
+        }
+    if (model == KF_LINEAR && blockIdx.y == 0) {
         for (int i = 0; i < m; ++i) {
             const double ui = u[(long long)i * ldu + s];
-            AB[(long long)(N + i) * ld + s] = ui;
-            AB[(long long)(P + N + i) * ld + s] = ui;
-        }
-    } else if (model == KF_BILINEAR) {
-        const int j0 = blockIdx.y * 64;
-        for (int k = 0; k < m; ++k) {
-            const double uk = u[(long long)k * ldu + s];
-            for (int j = j0; j < min(N, j0 + 64); ++j) {
-                AB[(long long)((k + 1) * N + j) * ld + s] = KF_MUL(uk, AB[(long long)j * ld + s]);
-                AB[(long long)(P + (k + 1) * N + j) * ld + s] = KF_MUL(uk, AB[(long long)(P + j) * ld + s]);
-            }
+            AB[((long long)N * (nw + 1) + i) * ld + s] = ui;
+            AB[((long long)P + (long long)N * (nw + 1) + i) * ld + s] = ui;
         }
     }
 }
@@ -140,6 +146,7 @@ struct KfLiftTileArgs {
     int P;
     int max_slots, max_ops, max_nst;
     const double* alpha; const double* beta; const double* u; long long M;   // M = points of this launch
+    const double* w; int nw;            // loads of a `loaded` model (mode 1): blocks w_c psi, Ksysid.m:594-599
     long long ldin;                     // leading dimension of alpha / beta / u (>= M; a chunk of a longer column)
     double* out; long long ld;
 };
@@ -162,8 +169,8 @@ template <int LS>
 __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTileArgs a) {
     extern __shared__ __align__(16) double lt_smem[];
     double* sh = lt_smem;                              // [max_slots][LS]; slots 0 .. nv-1 are the variables
-    double* su = sh + (size_t)a.max_slots * LS;        // [m][LS]   inputs u of the tile
-    double* se = su + (size_t)a.m * LS;                // [N][LS]   econ features (dim_red only, single group)
+    double* su = sh + (size_t)a.max_slots * LS;        // [m + nw][LS]   inputs u, then loads w, of the tile
+    double* se = su + (size_t)(a.m + a.nw) * LS;       // [N][LS]   econ features (dim_red only, single group)
     LtOp* sop = reinterpret_cast<LtOp*>(se + (a.n_pcs > 0 ? (size_t)a.N * LS : 0));   // [max_ops] in level order
     LtStore* sst = reinterpret_cast<LtStore*>(sop + a.max_ops);                       // [max_nst] (slot, output row)
     __shared__ LtGroup grp;
@@ -180,13 +187,14 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long g0 = tile * LS;
         // ---- A: the variables v (slots 0 .. nv-1) and u of the tile; the tail of the last tile is zero
-        for (int idx = tid; idx < (a.nv + a.m) * LS; idx += LT_THREADS) {
+        for (int idx = tid; idx < (a.nv + a.m + a.nw) * LS; idx += LT_THREADS) {
             const int k = idx / LS, s = idx & (LS - 1);
             const long long gs = g0 + s;
             double v = 0.0;
             if (gs < a.M) {
                 if (k < a.nv) v = k < a.nzeta ? src[(long long)k * a.ldin + gs] : a.u[(long long)(k - a.nzeta) * a.ldin + gs];
-                else v = a.u[(long long)(k - a.nv) * a.ldin + gs];
+                else if (k < a.nv + a.m) v = a.u[(long long)(k - a.nv) * a.ldin + gs];
+                else v = a.w[(long long)(k - a.nv - a.m) * a.ldin + gs];
             }
             if (k < a.nv) sh[k * LS + s] = v; else su[(k - a.nv) * LS + s] = v;
         }
@@ -261,15 +269,23 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
                     if (!direct) { const LtStore sr = sst[e]; slot = sr.slot; row = sr.row; }
                     const double2 v = *reinterpret_cast<const double2*>(psi + slot * LS + p2);
                     put(base + (long long)row * a.ld, v.x, v.y);
-                    if (a.mode == 1 && a.model == KF_BILINEAR) {       // blocks u_k psi  (Ksysid.m:510-511)
-                        for (int k = 0; k < a.m; ++k) {
-                            const double u0 = su[k * LS + p2], u1 = su[k * LS + p2 + 1];
-                            put(base + ((long long)(k + 1) * a.N + row) * a.ld, KF_MUL(u0, v.x), KF_MUL(u1, v.y));
-                        }
+                    if (a.mode == 1 && (a.model == KF_BILINEAR || a.nw > 0)) {
+                        // Kronecker blocks: column (ka (nw+1) + kc) N + row holds u_ka * (w_kc * psi)  — [1; u] (x) [1; w] (x) psi with
+                        // the reference's association (psi_L = [psi; w_c psi] first, Ksysid.m:594-599; then u_k psi_L, 510-511 / 604-605)
+                        const int nku = a.model == KF_BILINEAR ? a.m : 0;
+                        for (int ka = 0; ka <= nku; ++ka)
+                            for (int kc = 0; kc <= a.nw; ++kc) {
+                                if (ka == 0 && kc == 0) continue;
+                                double x0 = v.x, x1 = v.y;
+                                if (kc) { x0 = KF_MUL(su[(a.m + kc - 1) * LS + p2], x0); x1 = KF_MUL(su[(a.m + kc - 1) * LS + p2 + 1], x1); }
+                                if (ka) { x0 = KF_MUL(su[(ka - 1) * LS + p2], x0); x1 = KF_MUL(su[(ka - 1) * LS + p2 + 1], x1); }
+                                put(base + ((long long)(ka * (a.nw + 1) + kc) * a.N + row) * a.ld, x0, x1);
+                            }
                     }
                 }
-                if (a.mode == 1 && a.model == KF_LINEAR && g == 0) {   // [psi, u]  (Ksysid.m:1062-1063)
-                    for (int i = rr; i < a.m; i += NR) put(base + (long long)(a.N + i) * a.ld, su[i * LS + p2], su[i * LS + p2 + 1]);
+                if (a.mode == 1 && a.model == KF_LINEAR && g == 0) {   // [psi_L, u]  (Ksysid.m:1062-1063)
+                    for (int i = rr; i < a.m; i += NR)
+                        put(base + ((long long)a.N * (a.nw + 1) + i) * a.ld, su[i * LS + p2], su[i * LS + p2 + 1]);
                 }
             }
         }
@@ -300,7 +316,7 @@ bool lift_tile_launch(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, cudaStream_t s
     if (nlev > LT_MAXLEV || a.M <= 0) return false;
     const KfProgram& p = ctx->prog;
     auto bytes = [&](int ls, int slots, int ops, int nst) {
-        return ((size_t)slots + (size_t)a.m + (a.n_pcs > 0 ? (size_t)a.N : 0)) * ls * sizeof(double) + (size_t)ops * sizeof(LtOp) +
+        return ((size_t)slots + (size_t)a.m + (size_t)a.nw + (a.n_pcs > 0 ? (size_t)a.N : 0)) * ls * sizeof(double) + (size_t)ops * sizeof(LtOp) +
                (size_t)nst * sizeof(LtStore) + 64;
     };
     // Tile width LS (snapshots per tile = contiguous bytes per output row / 8): the wider, the longer the contiguous runs the
@@ -430,13 +446,14 @@ int kf_launch_regressors(kf_ctx* ctx, const KfLiftArgs& a0, double* AB, double* 
     if (a.Mc <= 0) { a.start = 0; a.Mc = (int)a.M; }
     const long long count = std::min<long long>(a.Mc, a.M - a.start);
     if (count <= 0) return KF_OK;
-    const int P = kf_regressor_width(a.model, a.N, a.m);
+    const int P = kf_regressor_width(a.model, a.N, a.m, a.nw);
     if (ctx->opt_lift_tile) {
         KfLiftTileArgs t{};
         t.ops = a.ops; t.centres = a.centres; t.pcs = a.pcs; t.order = a.order;
         t.nv = a.nv; t.n_full = a.n_full; t.n_pcs = a.n_pcs; t.N = a.N;
         t.nzeta = a.nzeta; t.m = a.m; t.model = a.model; t.mode = 1; t.P = P;
         t.alpha = a.alpha + a.start; t.beta = a.beta + a.start; t.u = a.u ? a.u + a.start : a.u; t.M = count; t.ldin = a.M;
+        t.w = (a.nw > 0 && a.w) ? a.w + a.start : nullptr; t.nw = a.nw;
         t.out = AB; t.ld = ldp;
         int rc = KF_OK;
         if (lift_tile_launch(ctx, t, 2, st, &rc)) return rc;
@@ -451,9 +468,10 @@ int kf_launch_regressors(kf_ctx* ctx, const KfLiftArgs& a0, double* AB, double* 
     a.nsides = 2;
     a.extras = 0;
     KF_TRY(kf_launch_lift(ctx, a, st));
-    if (a.model != KF_NONLINEAR) {
-        dim3 grid((unsigned)((count + 127) / 128), a.model == KF_BILINEAR ? (a.N + 63) / 64 : 1);
-        kf_regressor_post_kernel<<<grid, 128, 0, st>>>(a.model, a.N, P, a.m, a.u + a.start, count, a.M, AB, ldp);
+    if (a.model != KF_NONLINEAR || a.nw > 0) {
+        dim3 grid((unsigned)((count + 127) / 128), (a.model == KF_BILINEAR || a.nw > 0) ? (a.N + 63) / 64 : 1);
+        kf_regressor_post_kernel<<<grid, 128, 0, st>>>(a.model, a.N, P, a.m, a.nw, a.u ? a.u + a.start : a.u, a.nw > 0 ? a.w + a.start : nullptr,
+                                                       count, a.M, AB, ldp);
         KF_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     }

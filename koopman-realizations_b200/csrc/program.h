@@ -58,7 +58,8 @@ int kf_block_rows(int type, int degree, int nv, int* rows, int* cols, std::vecto
 // compile a kf_basis; returns KF_OK or KF_EINVAL with `err` set
 int kf_build_program(const kf_basis* basis, KfProgram& prog, std::string& err);
 
-// regressor width (Ksysid.m:1019-1028)
-inline int kf_regressor_width(int model, int N, int m) {
-    return model == KF_LINEAR ? N + m : (model == KF_BILINEAR ? N * (m + 1) : N);
+// regressor width (Ksysid.m:1019-1028); nw > 0: `loaded` model, the lifted state is [1; w] (x) psi (Ksysid.m:594-599)
+inline int kf_regressor_width(int model, int N, int m, int nw = 0) {
+    const int NL = N * (nw + 1);
+    return model == KF_LINEAR ? NL + m : (model == KF_BILINEAR ? NL * (m + 1) : NL);
 }

@@ -41,6 +41,8 @@ class Fitter:
 
     def set_option(self, name, value):
         self._check(self.lib.kf_set_option(self.ctx, name.encode(), float(value)), "kf_set_option")
+        if name == "qp_method":
+            self._qp_method = int(value)
 
     def set_qp_partition(self, col_lo, col_hi, allreduce=None):
         """Column partition of the exact active-set QP solver (kf_set_qp_partition): this rank solves the columns
@@ -115,10 +117,12 @@ class Fitter:
         return sv, keep
 
     def _run_fit(self, call, what, basis, model_type, M, nzeta, m, pa, pb, pu, want_gram, want_regressors, pc_cols, solve_kw,
-                 rows_out=None):
-        _, N, P = self.dims(basis, model_type, m)
+                 rows_out=None, pw=None, nw=0):
+        _, N, _ = self.dims(basis, model_type, m)
+        P = A.regressor_width(model_type, N, m, nw)
         Pc = int(pc_cols) if 0 < int(pc_cols) < P else P
-        pr = A.kf_problem(M=M, nzeta=nzeta, m=m, model=A.MODEL_CODE[model_type], alpha=pa, beta=pb, u=pu, pc_cols=int(pc_cols))
+        pr = A.kf_problem(M=M, nzeta=nzeta, m=m, model=A.MODEL_CODE[model_type], alpha=pa, beta=pb, u=pu, pc_cols=int(pc_cols),
+                          nw=int(nw), w=pw)
         sv, keep_t = self._solve_struct(**solve_kw)
         nt = max(1, sv.nt) if not sv.least_squares else 1
         res = A.kf_result()
@@ -143,19 +147,22 @@ class Fitter:
                    objective=obj, l1norm=l1, qp_iters=iters, qp_gap=gap)
         return out
 
-    def fit(self, basis, model_type, alpha, beta, u, want_gram=False, want_regressors=False, pc_cols=0, **solve_kw):
+    def fit(self, basis, model_type, alpha, beta, u, want_gram=False, want_regressors=False, pc_cols=0, w=None, **solve_kw):
         """get_Koopman for host snapshot pairs (Ksysid.m:987-1092): returns dict with K (P x P, or
         P x P x nt for a budget vector), rank, perm, info and optionally G, C, Px, Py.
         pc_cols > 0 (opt-in fast mode, least squares only): only the first pc_cols columns of K are computed.
+        w (M x nw): the loads of a `loaded` model (snapshotPairs.w): the lifted state becomes [1; w] (x) psi.
         On a context that joined a communicator (comm_init) alpha / beta / u are THIS RANK's shard."""
         alpha, beta, u = A.fcol(alpha), A.fcol(beta), A.fcol(u)
         M, nzeta = alpha.shape
         m = u.shape[1]
+        w = None if w is None or np.size(w) == 0 else A.fcol(np.asarray(w, dtype=np.float64).reshape(M, -1))
 
         def call(b, pr, sv, res):
             self._check(self.lib.kf_fit(self.ctx, b, pr, sv, res), "kf_fit")
         return self._run_fit(call, "kf_fit", basis, model_type, M, nzeta, m, alpha.ctypes.data, beta.ctypes.data, u.ctypes.data,
-                             want_gram, want_regressors, pc_cols, solve_kw)
+                             want_gram, want_regressors, pc_cols, solve_kw, pw=None if w is None else w.ctypes.data,
+                             nw=0 if w is None else w.shape[1])
 
     def fit_dev(self, basis, model_type, M, nzeta, m, alpha_ptr, beta_ptr, u_ptr, want_gram=False, pc_cols=0, **solve_kw):
         """kf_fit_dev: the whole fit from DEVICE-resident snapshot pairs (pointers from torch tensors' data_ptr(); column-major
@@ -315,6 +322,24 @@ class Fitter:
         self._check(self.lib.kf_rollout(self.ctx, basis.ref(), nc, mds, nt, T, z0, up, nout, yp), "kf_rollout")
         return out
 
+    def mpc_costB_bilinear(self, Amat, Bmat, z, horizon):
+        """Kmpc.get_costB_bilinear (Kmpc.m:569-596) on the GPU.  Amat (N x N), Bmat (N x N m) of the bilinear model; z: (N,),
+        (1, N) or (horizon, N) lifted state(s) along the horizon, or a batch (nbatch, nz, N).  Returns B of shape
+        (N (h+1), m h), or (nbatch, N (h+1), m h) for a batch."""
+        Amat, Bmat = A.fcol(Amat), A.fcol(Bmat)
+        N = Amat.shape[0]
+        m = Bmat.shape[1] // N
+        z = np.asarray(z, dtype=np.float64)
+        batched = z.ndim == 3
+        zb = z if batched else np.atleast_2d(z)[None, :, :]
+        nb, nz = zb.shape[0], zb.shape[1]
+        zf = np.ascontiguousarray(np.transpose(zb, (0, 2, 1)))          # per problem: (N, nz) C-order == (nz x N) column-major
+        out = np.zeros((nb, m * horizon, N * (horizon + 1)))             # per problem: C-order (cols, rows) == column-major
+        self._check(self.lib.kf_mpc_costB_bilinear(self.ctx, N, m, int(horizon), nb, A.dptr(Amat), A.dptr(Bmat), nz, A.dptr(zf),
+                                                   A.dptr(out)), "kf_mpc_costB_bilinear")
+        res = np.transpose(out, (0, 2, 1))
+        return res if batched else res[0]
+
     def mldivide(self, Amat, Bmat):
         """MATLAB `A \\ B` (QRCP basic solution) on the GPU; returns X, rank, perm."""
         Amat, Bmat = A.fcol(Amat), A.fcol(Bmat)
@@ -434,14 +459,16 @@ class MultiFitter(Fitter):
         if rc:
             raise A.KoopfitError(f"kf_multi_set_option({name}) failed")
 
-    def fit(self, basis, model_type, alpha, beta, u, want_gram=False, want_regressors=False, pc_cols=0, **solve_kw):
+    def fit(self, basis, model_type, alpha, beta, u, want_gram=False, want_regressors=False, pc_cols=0, w=None, **solve_kw):
         alpha, beta, u = A.fcol(alpha), A.fcol(beta), A.fcol(u)
         M, nzeta = alpha.shape
         m = u.shape[1]
+        w = None if w is None or np.size(w) == 0 else A.fcol(np.asarray(w, dtype=np.float64).reshape(M, -1))
 
         def call(b, pr, sv, res):
             rc = self.lib.kf_fit_multi(self.mc, b, pr, sv, res)
             if rc:
                 raise A.KoopfitError(f"kf_fit_multi failed ({A.ERRORS.get(rc, rc)}): {self.lib.kf_multi_last_error(self.mc).decode()}")
         return self._run_fit(call, "kf_fit_multi", basis, model_type, M, nzeta, m, alpha.ctypes.data, beta.ctypes.data, u.ctypes.data,
-                             want_gram, want_regressors, pc_cols, solve_kw)
+                             want_gram, want_regressors, pc_cols, solve_kw, pw=None if w is None else w.ctypes.data,
+                             nw=0 if w is None else w.shape[1])

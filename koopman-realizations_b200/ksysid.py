@@ -24,20 +24,28 @@ from .fitter import Fitter
 
 # ------------------------------------------------------------------ host pre-processing
 def merge_trials(trials):
-    """Ksysid.m:380-401."""
+    """Ksysid.m:380-401 (every numeric field: the load w rides along when every trial has one)."""
     if isinstance(trials, dict):
         return trials
-    return {k: np.concatenate([np.asarray(t[k], dtype=np.float64) for t in trials], axis=0) for k in ("t", "y", "u")}
+    out = {k: np.concatenate([np.asarray(t[k], dtype=np.float64) for t in trials], axis=0) for k in ("t", "y", "u")}
+    if all("w" in t for t in trials):
+        out["w"] = np.concatenate([np.asarray(t["w"], dtype=np.float64).reshape(len(t["t"]), -1) for t in trials], axis=0)
+    return out
 
 
 def _scale_factors(data):
-    """Ksysid.m:187-204: centre and half-range per column, unit factor for constant columns."""
+    """Ksysid.m:187-204: centre and half-range per column, unit factor for constant columns; the load w (246-265) is only
+    shifted to zero where it is constant and scaled into [-1, 1] where it varies."""
     out = {}
     for k in ("y", "u"):
         mn, mx = data[k].min(axis=0), data[k].max(axis=0)
         half = (mx - mn) / 2.0
         out[k + "_offset"] = (mx + mn) / 2.0
         out[k + "_factor"] = np.where(half == 0, 1.0, half)
+    if "w" in data:
+        mn, mx = data["w"].min(axis=0), data["w"].max(axis=0)
+        out["w_offset"] = (mx + mn) / 2.0
+        out["w_factor"] = np.where(mn != mx, (mx - mn) / 2.0, 1.0)
     return out
 
 
@@ -90,12 +98,13 @@ class Ksysid:
         self.obs_degree = [int(d) for d in np.atleast_1d(self.obs_degree)]
         if self.model_type not in ("linear", "bilinear", "nonlinear"):
             raise ValueError("Invalid model_type chosen. Must be linear, bilinear, or nonlinear.")   # 103
-        if self.loaded:
-            raise NotImplementedError("loaded (w) dictionaries are outside the hot-path scope (SURVEY §2a)")
+        if self.loaded and not all("w" in t for t in data4sysid["train"]):
+            raise ValueError("You have specified a loaded system, but your training data does not have the required load field (w)")  # 107-109
         if self.time_type not in ("discrete", "continuous"):
             raise ValueError("time_type must be discrete or continuous")
         self.liftinput = {"linear": 0, "nonlinear": 1, "bilinear": 2}[self.model_type]
         self._ls_method = extras["ls_method"]
+        self._rng_seed = int(extras["rng_seed"])            # seed of the `snapshots < Inf` draw (MATLAB's stream is not reproducible here)
         # opt-in: compute only the K columns the model consumes (K(:,1:N) or K(:,1:nzeta)); model['K'] is then P x Pc
         self._fast_cols = bool(extras["fast_cols"])
         # opt-in: train_models hands the raw merged series to the GPU (bilinear / nonlinear models, snapshots = Inf)
@@ -108,16 +117,19 @@ class Ksysid:
         self.params["nd"] = int(self.delays)
         n, m, nd = self.params["n"], self.params["m"], self.params["nd"]
         self.params["nzeta"] = n * (nd + 1) + m * nd
-        self.params["nw"] = 0
-
         # merge + scale (Ksysid.m:119-128)
         merged = merge_trials(data4sysid["train"])
+        self.params["nw"] = merged["w"].shape[1] if (self.loaded and "w" in merged) else 0      # Ksysid.m:88-93
         self._merged_raw = merged
         sc = _scale_factors(merged)
         self.params["scale"] = sc
         self.scaledown = {"y": lambda y: (y - sc["y_offset"]) / sc["y_factor"], "u": lambda u: (u - sc["u_offset"]) / sc["u_factor"]}
         self.scaleup = {"y": lambda y: y * sc["y_factor"] + sc["y_offset"], "u": lambda u: u * sc["u_factor"] + sc["u_offset"]}
         self.traindata = {"t": merged["t"], "y": self.scaledown["y"](merged["y"]), "u": self.scaledown["u"](merged["u"])}
+        if "w" in merged:
+            self.scaledown["w"] = lambda w: (w - sc["w_offset"]) / sc["w_factor"]
+            self.scaleup["w"] = lambda w: w * sc["w_factor"] + sc["w_offset"]
+            self.traindata["w"] = self.scaledown["w"](merged["w"])
         self.valdata = [self.scale_data(v) for v in data4sysid["val"]]
         self.snapshotPairs = self.get_snapshotPairs(self.traindata, self.snapshots)
 
@@ -127,6 +139,10 @@ class Ksysid:
         self.fitter = extras["fitter"] or Fitter(device=extras["device"])
         self.lift = {"full": lambda v: self._lift(v, econ=False), "econ_full": lambda v: self._lift(v, econ=True),
                      "econ_full_input": self._lift_input}
+        if self.loaded:                                       # def_observables_loaded (Ksysid.m:539-626), econ_* (1580-1611)
+            self.lift["full_loaded"] = lambda v, w: self._lift_loaded(v, w, econ=False)
+            self.lift["econ_full_loaded"] = lambda v, w: self._lift_loaded(v, w, econ=True)
+            self.lift["econ_full_loaded_input"] = self._lift_loaded_input
         if self.dim_red is None or self.dim_red:            # `if ~obj.dim_red ... else` with [] -> reduce (137-141)
             self._reduce_dimension()
         self.params["N"] = self.fitter.dims(self.basis, self.model_type, m)[1]
@@ -139,8 +155,11 @@ class Ksysid:
     def scale_data(self, trial, down=True):
         """Ksysid.m:308-343."""
         f = self.scaledown if down else self.scaleup
-        return {"t": np.asarray(trial["t"], float), "y": f["y"](np.asarray(trial["y"], float)),
-                "u": f["u"](np.asarray(trial["u"], float))}
+        out = {"t": np.asarray(trial["t"], float), "y": f["y"](np.asarray(trial["y"], float)),
+               "u": f["u"](np.asarray(trial["u"], float))}
+        if "w" in trial and "w" in f:                         # Ksysid.m:328-330
+            out["w"] = f["w"](np.asarray(trial["w"], float).reshape(len(out["t"]), -1))
+        return out
 
     def get_zeta(self, data):
         """Ksysid.m:868-907."""
@@ -163,10 +182,13 @@ class Ksysid:
         num_max = good.size - 1
         idx = good[:num_max]
         if np.isfinite(snapshots) and snapshots <= num_max - 1:
-            idx = np.sort(np.random.default_rng(0).choice(idx, size=int(snapshots), replace=False))
+            idx = np.sort(np.random.default_rng(getattr(self, '_rng_seed', 0)).choice(idx, size=int(snapshots), replace=False))
         elif np.isfinite(snapshots):
             print(f"Number of snapshot pairs cannot exceed {num_max}. Taking {num_max} pairs instead.")
-        return {"alpha": zeta[:-1][idx], "beta": zeta[1:][idx], "u": uzeta[:-1][idx]}
+        pairs = {"alpha": zeta[:-1][idx], "beta": zeta[1:][idx], "u": uzeta[:-1][idx]}
+        if "w" in data:                                       # wzeta(1:end-1) at the kept points (Ksysid.m:953-957, 980-982)
+            pairs["w"] = np.asarray(data["w"], float).reshape(len(t), -1)[nd:][:-1][idx]
+        return pairs
 
     # ------------------------------------------------------------------ lifting
     def _lift(self, v, econ=True):
@@ -183,6 +205,18 @@ class Ksysid:
     def _lift_input(self, zeta, u):
         """lift.econ_full_input (Ksysid.m:1593-1604): [psi; u_1 psi; ...; u_m psi]."""
         z = self._lift(zeta)
+        u = np.asarray(u, float)
+        return np.concatenate([z] + [u[..., k:k + 1] * z for k in range(u.shape[-1])], axis=-1)
+
+    def _lift_loaded(self, v, w, econ=True):
+        """lift.econ_full_loaded (Ksysid.m:1607-1611): [psi; w_1 psi; ...; w_nw psi] = [1; w] (x) psi."""
+        z = self._lift(v, econ=econ)
+        w = np.asarray(w, float)
+        return np.concatenate([z] + [w[..., c:c + 1] * z for c in range(w.shape[-1])], axis=-1)
+
+    def _lift_loaded_input(self, zeta, w, u):
+        """lift.econ_full_loaded_input (Ksysid.m:1580-1590): [psi_L; u_1 psi_L; ...; u_m psi_L]."""
+        z = self._lift_loaded(zeta, w)
         u = np.asarray(u, float)
         return np.concatenate([z] + [u[..., k:k + 1] * z for k in range(u.shape[-1])], axis=-1)
 
@@ -223,22 +257,29 @@ class Ksysid:
         N = self.params["N"]
         lasso = self.lasso if lasso is None else np.atleast_1d(np.asarray(lasso, dtype=np.float64))
         want_reg = self.model_type == "linear"              # get_model needs koopData.Px / Py (1206-1216)
+        w = snapshotPairs.get("w") if self.loaded else None  # nw = 0 without the field (Ksysid.m:1006-1011)
+        NL = N * ((w.shape[1] if w is not None else 0) + 1)
         if np.all(self.lasso >= 1e6):                       # branch test on the PROPERTY (Ksysid.m:1068)
-            pc = (self.params["nzeta"] if self.model_type == "nonlinear" else N) if self._fast_cols else 0
+            pc = (self.params["nzeta"] if self.model_type == "nonlinear" else N) if (self._fast_cols and w is None) else 0
             res = self.fitter.fit(self.basis, self.model_type, snapshotPairs["alpha"], snapshotPairs["beta"],
                                   snapshotPairs["u"], want_regressors=want_reg, least_squares=True, ls_method=self._ls_method,
-                                  pc_cols=pc)
+                                  pc_cols=pc, w=w)
         else:
             res = self.fitter.fit(self.basis, self.model_type, snapshotPairs["alpha"], snapshotPairs["beta"],
                                   snapshotPairs["u"], want_regressors=want_reg, least_squares=False, t=lasso * N,
                                   delay_constraint=(self.model_type == "linear" and self.params["nd"] >= 1),
-                                  n=self.params["n"], nd=self.params["nd"])
+                                  n=self.params["n"], nd=self.params["nd"], w=w)
         out = []
-        for i in range(res["K_all"].shape[2]):
-            kd = {"K": np.array(res["K_all"][:, :, i]), "u": snapshotPairs["u"], "alpha": snapshotPairs["alpha"],
+        # the reference re-runs get_Koopman once per lasso entry (train_models 1370-1387): a vector whose entries are all >= 1e6
+        # gives length(lasso) identical least-squares candidates
+        ncand = max(res["K_all"].shape[2], len(lasso) if np.all(self.lasso >= 1e6) else 0)
+        for i in range(ncand):
+            kd = {"K": np.array(res["K_all"][:, :, min(i, res["K_all"].shape[2] - 1)]), "u": snapshotPairs["u"], "alpha": snapshotPairs["alpha"],
                   "info": res["info"], "rank": res["rank"]}
+            if w is not None:
+                kd["w"] = w                                  # Ksysid.m:1088-1090
             if want_reg:
-                kd["Px"], kd["Py"] = res["Px"][:, :N], res["Py"][:, :N]     # Ksysid.m:1085-1086
+                kd["Px"], kd["Py"] = res["Px"][:, :NL], res["Py"][:, :NL]     # Ksysid.m:1085-1086: N (nw+1) state columns
             out.append(kd)
         return out
 
@@ -258,7 +299,8 @@ class Ksysid:
 
     def get_model(self, koopData):
         """Ksysid.m:1179-1235: A, B, C and the projection M = (L \\ R)' (applied to A, B only for discrete models)."""
-        N, n = self.params["N"], self.params["n"]
+        n = self.params["n"]
+        N = self.params["N"] * ((self.params["nw"] if "w" in koopData else 0) + 1)      # N (nw+1), Ksysid.m:1192-1203
         UT = self._UT(koopData["K"])[:N, :]
         Amat, Bmat = UT[:N, :N], UT[:N, N:]
         Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
@@ -271,7 +313,8 @@ class Ksysid:
 
     def get_BLmodel(self, koopData):
         """Ksysid.m:1238-1282."""
-        N, n, m = self.params["N"], self.params["n"], self.params["m"]
+        n, m = self.params["n"], self.params["m"]
+        N = self.params["N"] * ((self.params["nw"] if "w" in koopData else 0) + 1)      # Ksysid.m:1251-1259
         UT = self._UT(koopData["K"])[:N, :]
         Amat, Bmat = UT[:N, :N], UT[:N, N:]
         Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
@@ -283,6 +326,9 @@ class Ksysid:
         nz, n = self.params["nzeta"], self.params["n"]
         Kc = self._UT(koopData["K"]).T if self.time_type == "continuous" else koopData["K"]    # Ksysid.m:1308-1311
         F = np.array(Kc[:, :nz].T)
+        if self.loaded and "w" in koopData:                  # F = K(:,1:nzeta)' basis_loaded, F_func(zeta, u, w) (Ksysid.m:1320-1327)
+            return {"F_sym": F, "F_func": lambda zeta, u, w: F @ self._lift_loaded(np.concatenate([np.ravel(zeta), np.ravel(u)]), np.ravel(w)),
+                    "params": self.params, "C": np.eye(n), "K": koopData["K"]}
         return {"F_sym": F, "F_func": lambda zeta, u: F @ self._lift(np.concatenate([np.ravel(zeta), np.ravel(u)])),
                 "params": self.params, "C": np.eye(n), "K": koopData["K"]}
 
@@ -385,10 +431,34 @@ class Ksysid:
             states[j + 1] = x
         return self._val_result(setup, states)
 
+    def _val_loaded(self, model, valdata):
+        """Loaded linear / bilinear validation (Ksysid.m:1657-1670, 1751-1764): the lifted state is re-expanded with the ACTUAL
+        load every step, znow = kron(I_{nw+1}, z(1:N)) [1; w_j]; z+ = A znow + B u (linear) or A znow + Beta(znow) u (bilinear).
+        Host side like the reference (a T-step sequential recursion of one trial)."""
+        setup = self._val_setup(valdata)
+        treal, yreal, ureal, zetareal = setup
+        nd, N, m = self.params["nd"], self.params["N"], self.params["m"]
+        wreal = np.asarray(valdata["w"], float).reshape(len(valdata["t"]), -1)[nd:]
+        z = self._lift_loaded(zetareal[0], wreal[0])
+        states = np.zeros((len(treal), z.size))
+        states[0] = z
+        for j in range(len(treal) - 1):
+            znow = np.kron(np.concatenate([[1.0], wreal[j]]), z[:N])
+            if self.model_type == "bilinear":
+                z = model["A"] @ znow + (model["B"] @ np.kron(np.eye(m), znow.reshape(-1, 1))) @ ureal[j]
+            else:
+                z = model["A"] @ znow + model["B"] @ ureal[j]
+            states[j + 1] = z
+        res = self._val_result(setup, states)
+        res["sim"]["w"], res["real"]["w"] = wreal, wreal
+        return res
+
     def val_model(self, model, valdata):
-        """Ksysid.m:1623-1722 (discrete, unloaded): z+ = A z + B u (1685), y = C z; on the GPU (kf_rollout)."""
+        """Ksysid.m:1623-1722 (discrete): z+ = A z + B u (1685), y = C z; on the GPU (kf_rollout) for unloaded models."""
         if self.time_type == "continuous":
             return self._val_continuous(model, valdata)
+        if self.loaded:
+            return self._val_loaded(model, valdata)
         setups, sims = self._rollout([model], [valdata], self.params["N"])
         return self._val_result(setups[0], sims[0][0])
 
@@ -396,6 +466,8 @@ class Ksysid:
         """Ksysid.m:1725-1820: z+ = A z + Beta(z) u (1783)."""
         if self.time_type == "continuous":
             return self._val_continuous(model, valdata)
+        if self.loaded:
+            return self._val_loaded(model, valdata)
         setups, sims = self._rollout([model], [valdata], self.params["N"])
         return self._val_result(setups[0], sims[0][0])
 

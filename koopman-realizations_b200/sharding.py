@@ -129,13 +129,25 @@ def _solve_column_split(fitter, P, budgets, rank, world, device, group, **solve_
     import torch
     import torch.distributed as dist
     lo, hi = column_bounds(P, rank, world)
+    # the cases the column-split solver refuses are the same on every rank: fail BEFORE the first collective, everywhere
+    if P > 4096 or solve_kw.get("delay_constraint"):
+        raise ValueError("column-split lasso sweep: P <= 4096 and no pinned delay columns (linear model with delays) required")
+    prev_method = getattr(fitter, "_qp_method", 0)
     fitter.set_option("qp_method", 2)
     fitter.set_qp_partition(lo, hi, make_allreduce(device, group))
+    err = None
     try:
         res = fitter.solve_dev(P, least_squares=False, t=budgets, **solve_kw)
+    except Exception as exc:                    # a rank-local failure must not leave the others blocked in a collective
+        err, res = exc, None
     finally:
         fitter.set_qp_partition(0, 0)
-        fitter.set_option("qp_method", 0)
+        fitter.set_option("qp_method", prev_method)
+    on_gpu0 = dist.get_backend(group) == "nccl"
+    flag = torch.tensor([1.0 if err is not None else 0.0], dtype=torch.float64, device=device if on_gpu0 else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if float(flag.item()) > 0:
+        raise RuntimeError(f"column-split lasso sweep failed on at least one rank (this rank: {err!r})")
     nt = budgets.size
     wmax = max(column_bounds(P, r, world)[1] - column_bounds(P, r, world)[0] for r in range(world))
     mine = np.zeros((nt, wmax, P))                       # [budget][column][row]: contiguous column blocks

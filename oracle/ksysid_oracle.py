@@ -37,7 +37,7 @@ __all__ = [
     "solve_l1ball_qp", "l1ball_project", "get_koopman", "get_model", "get_BLmodel",
     "get_NLmodel", "val_model", "val_BLmodel", "val_NLmodel", "get_error", "pca_matlab",
     "econ_reduce", "KsysidOracle", "OP_VAR", "OP_CONST", "OP_MUL", "OP_COS", "OP_SIN",
-    "OP_HERM", "OP_GAUSS", "needs_psd_shift", "delay_constraint_targets",
+    "OP_HERM", "OP_GAUSS", "needs_psd_shift", "delay_constraint_targets", "load_lift", "mpc_costB_bilinear",
 ]
 
 OP_VAR, OP_CONST, OP_MUL, OP_COS, OP_SIN, OP_HERM, OP_GAUSS = range(7)
@@ -85,8 +85,10 @@ def load_rand_systems(path):
 
 
 def merge_trials(trials):
-    """Vertical concatenation of every numeric field (Ksysid.m:380-401)."""
-    return {k: np.concatenate([tr[k] for tr in trials], axis=0) for k in ("t", "y", "u")}
+    """Vertical concatenation of every numeric field (Ksysid.m:380-401); the load w rides along when every trial has one."""
+    keys = ("t", "y", "u") + (("w",) if all("w" in tr for tr in trials) else ())
+    return {k: np.concatenate([np.asarray(tr[k], dtype=np.float64).reshape(len(tr["t"]), -1) if k != "t" else tr[k]
+                               for tr in trials], axis=0) for k in keys}
 
 
 def get_scale(data):
@@ -100,14 +102,22 @@ def get_scale(data):
         s = np.where(s == 0, 1.0, s)
         sc[k + "_offset"], sc[k + "_factor"] = dc, s
         out[k] = (data[k] - dc) / s
+    if "w" in data:      # Ksysid.m:246-265: a constant load is only shifted to zero, a varying one scaled into [-1, 1]
+        mn, mx = data["w"].min(axis=0), data["w"].max(axis=0)
+        sc["w_offset"] = (mx + mn) / 2.0
+        sc["w_factor"] = np.where(mn != mx, (mx - mn) / 2.0, 1.0)
+        out["w"] = (data["w"] - sc["w_offset"]) / sc["w_factor"]
     return out, sc
 
 
 def scale_data(trial, sc, down=True):
     """Scale a trial with the train factors (Ksysid.m:308-343)."""
     if down:
-        return {"t": trial["t"], "y": (trial["y"] - sc["y_offset"]) / sc["y_factor"],
-                "u": (trial["u"] - sc["u_offset"]) / sc["u_factor"]}
+        out = {"t": trial["t"], "y": (trial["y"] - sc["y_offset"]) / sc["y_factor"],
+               "u": (trial["u"] - sc["u_offset"]) / sc["u_factor"]}
+        if "w" in trial and "w_offset" in sc:            # Ksysid.m:328-330
+            out["w"] = (np.asarray(trial["w"], dtype=np.float64).reshape(len(trial["t"]), -1) - sc["w_offset"]) / sc["w_factor"]
+        return out
     return {"t": trial["t"], "y": trial["y"] * sc["y_factor"] + sc["y_offset"],
             "u": trial["u"] * sc["u_factor"] + sc["u_offset"]}
 
@@ -141,7 +151,10 @@ def get_snapshot_pairs(data, nd, snapshots=np.inf):
     if np.isfinite(snapshots) and snapshots <= num_max - 1:
         raise NotImplementedError("snapshots < all needs MATLAB RandStream('mlfg6331_64') (Ksysid.m:974)")
     idx = good[:num_max]
-    return {"alpha": zeta[:-1][idx], "beta": zeta[1:][idx], "u": uzeta[:-1][idx]}
+    pairs = {"alpha": zeta[:-1][idx], "beta": zeta[1:][idx], "u": uzeta[:-1][idx]}
+    if "w" in data:                                      # wzeta(1:end-1) at the kept points (Ksysid.m:953-957, 980-982)
+        pairs["w"] = data["w"][nd:][:-1][idx]
+    return pairs
 
 
 # --------------------------------------------------------------------------- dictionaries
@@ -335,16 +348,26 @@ def lift(prog, V):
     return np.concatenate([V, F @ prog.pcs, np.ones((F.shape[0], 1))], axis=1)
 
 
-def regressor_width(model_type, N, m):
-    """P: N+m linear, N(m+1) bilinear, N nonlinear (Ksysid.m:1019-1028)."""
-    return {"linear": N + m, "bilinear": N * (m + 1), "nonlinear": N}[model_type]
+def regressor_width(model_type, N, m, nw=0):
+    """P: N+m linear, N(m+1) bilinear, N nonlinear, with N -> N (nw+1) for a loaded model (Ksysid.m:1019-1028)."""
+    NL = N * (nw + 1)
+    return {"linear": NL + m, "bilinear": NL * (m + 1), "nonlinear": NL}[model_type]
 
 
-def build_regressors(model_type, prog, alpha, beta, u):
-    """Px, Py of get_Koopman's lift loop (Ksysid.m:1030-1065); same u on both sides."""
+def load_lift(psi, w):
+    """lift.full_loaded: [psi; w_1 psi; ...; w_nw psi] = [1; w] (x) psi per row (Ksysid.m:594-599, 1607-1611)."""
+    if w is None or np.size(w) == 0:
+        return psi
+    w = np.asarray(w, dtype=np.float64).reshape(psi.shape[0], -1)
+    return np.concatenate([psi] + [w[:, c:c + 1] * psi for c in range(w.shape[1])], axis=1)
+
+
+def build_regressors(model_type, prog, alpha, beta, u, w=None):
+    """Px, Py of get_Koopman's lift loop (Ksysid.m:1030-1065); same u (and, for a loaded model, same w) on both sides."""
     if model_type == "nonlinear":
-        return lift(prog, np.concatenate([alpha, u], axis=1)), lift(prog, np.concatenate([beta, u], axis=1))
-    psx, psy = lift(prog, alpha), lift(prog, beta)
+        return (load_lift(lift(prog, np.concatenate([alpha, u], axis=1)), w),
+                load_lift(lift(prog, np.concatenate([beta, u], axis=1)), w))
+    psx, psy = load_lift(lift(prog, alpha), w), load_lift(lift(prog, beta), w)
     if model_type == "linear":
         return np.concatenate([psx, u], axis=1), np.concatenate([psy, u], axis=1)
     if model_type == "bilinear":   # [psi; kron(I_m, psi) u] (510-511)
@@ -682,17 +705,22 @@ def solve_l1ball_qp(G, C, t, fixed=None, tol=1e-13, max_outer=200, verbose=False
     return assemble(Kcur), {"lam": lam, "active": True}
 
 
-def get_koopman(model_type, prog, pairs, lasso=1e6, N=None, n=None, nd=0, psd_shift="as_reference"):
+def get_koopman(model_type, prog, pairs, lasso=1e6, N=None, n=None, nd=0, psd_shift="as_reference", loaded=False, ls_branch=None):
     """get_Koopman (Ksysid.m:987-1092) for one lasso value.
 
     lasso >= 1e6 -> K = Px \\ Py (1068-1069); otherwise the L1-ball QP with
     t = lasso * N (996) on G (+1e-6 I if any eigenvalue is negative, 1117-1120)
     and, for linear models with delays, the pinned delay columns (1139-1164).
     """
-    Px, Py = build_regressors(model_type, prog, pairs["alpha"], pairs["beta"], pairs["u"])
+    w = pairs.get("w") if loaded else None
+    Px, Py = build_regressors(model_type, prog, pairs["alpha"], pairs["beta"], pairs["u"], w)
     N = prog.N if N is None else N
-    koop = {"Px": Px, "Py": Py, "u": pairs["u"], "alpha": pairs["alpha"], "N": N}
-    if np.all(np.atleast_1d(lasso) >= 1e6):
+    koop = {"Px": Px, "Py": Py, "u": pairs["u"], "alpha": pairs["alpha"], "N": N, "nw": 0 if w is None else w.shape[1]}
+    if w is not None:
+        koop["w"] = w
+    if ls_branch is None:                                # the caller decides from the whole lasso property (Ksysid.m:1068);
+        ls_branch = bool(np.all(np.atleast_1d(lasso) >= 1e6))   # a bare call decides from the value it was given
+    if ls_branch:
         K, info = mldivide(Px, Py, return_info=True)
         koop.update(K=K, info=info)
         return koop
@@ -719,7 +747,7 @@ def continuous_UT(K, Ts):
 def get_model(koop, n, Ts=None):
     """Linear model A,B,C with the projection M = (L \\ R)' (Ksysid.m:1179-1235); Ts given = continuous time:
     A, B from the matrix logarithm and NOT projected (1220-1222)."""
-    K, N = koop["K"], koop["N"]
+    K, N = koop["K"], koop["N"] * (koop.get("nw", 0) + 1)       # N (nw+1) for a loaded model (Ksysid.m:1199-1203)
     UT = K.T if Ts is None else continuous_UT(K, Ts)
     A, B = UT[:N, :N], UT[:N, N:]
     Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
@@ -734,7 +762,7 @@ def get_model(koop, n, Ts=None):
 
 def get_BLmodel(koop, n, Ts=None):
     """Bilinear model: A, B=[B_1..B_m], Beta(z)=B kron(I_m,z) (Ksysid.m:1238-1295)."""
-    K, N = koop["K"], koop["N"]
+    K, N = koop["K"], koop["N"] * (koop.get("nw", 0) + 1)
     UT = K.T if Ts is None else continuous_UT(K, Ts)
     A, B = UT[:N, :N], UT[:N, N:]
     Cy = np.concatenate([np.eye(n), np.zeros((n, N - n))], axis=1)
@@ -762,14 +790,24 @@ def _val_setup(val, nd):
     return val["t"][nd:], val["y"][nd:], val["u"][nd:], zetareal
 
 
-def val_model(model, prog, val, nd, nzeta):
-    """Open-loop rollout z+ = A z + B u (Ksysid.m:1623-1714, discrete, unloaded)."""
+def val_model(model, prog, val, nd, nzeta, loaded=False):
+    """Open-loop rollout z+ = A z + B u (Ksysid.m:1623-1714, discrete).  Loaded: the lifted state is re-expanded with the
+    ACTUAL load every step, znow = kron(I, z(1:N)) [1; w_j] (1666)."""
     treal, yreal, ureal, zetareal = _val_setup(val, nd)
     A, B, C = model["A"], model["B"], model["C"]
     T = len(treal)
     ysim = np.zeros_like(yreal)
     ysim[0] = yreal[0]
     z = lift(prog, zetareal[0])[0]
+    if loaded:
+        wreal = np.asarray(val["w"], dtype=np.float64).reshape(len(val["t"]), -1)[nd:]
+        N = z.size
+        z = np.kron(np.concatenate([[1.0], wreal[0]]), z)
+        for j in range(T - 1):
+            znow = np.kron(np.concatenate([[1.0], wreal[j]]), z[:N])
+            z = A @ znow + B @ ureal[j]
+            ysim[j + 1] = C @ z
+        return {"y": ysim, "yreal": yreal, "error": get_error(ysim, yreal, treal)}
     for j in range(T - 1):
         z = A @ z + B @ ureal[j]
         ysim[j + 1] = C @ z
@@ -804,6 +842,29 @@ def val_NLmodel(model, prog, val, nd, nzeta, n):
         zeta = F @ lift(prog, np.concatenate([zeta, ureal[j]]))[0]
         ysim[j + 1] = zeta[:n]
     return {"y": ysim, "yreal": yreal, "error": get_error(ysim, yreal, treal)}
+
+
+# --------------------------------------------------------------------------- consumer side (Kmpc)
+def mpc_costB_bilinear(A, B, z, horizon):
+    """Kmpc.get_costB_bilinear (Kmpc.m:569-596): Bcol block i = A^(i-1) Beta(z_i), Beta(z) = B kron(I_m, z)
+    (Ksysid.m:1288-1289; z_i = z(i,:) if z has several rows, else z(1,:)); every further block column is the previous one
+    shifted down by N rows (Lshift, 586-594).  Returns the N (h+1) x m h matrix."""
+    A, B = np.asarray(A, dtype=np.float64), np.asarray(B, dtype=np.float64)
+    z = np.atleast_2d(np.asarray(z, dtype=np.float64))
+    N = A.shape[0]
+    m = B.shape[1] // N
+    Bcol = np.zeros((N * (horizon + 1), m))
+    Ap = np.eye(N)
+    for i in range(1, horizon + 1):
+        zi = z[i - 1] if z.shape[0] > 1 else z[0]
+        Bmodel = B @ np.kron(np.eye(m), zi.reshape(-1, 1))
+        Bcol[N * i:N * (i + 1)] = Ap @ Bmodel
+        Ap = A @ Ap
+    out = np.zeros((N * (horizon + 1), m * horizon))
+    out[:, :m] = Bcol
+    for c in range(1, horizon):
+        out[N:, c * m:(c + 1) * m] = out[:-N, (c - 1) * m:c * m]
+    return out
 
 
 # --------------------------------------------------------------------------- dimension reduction
@@ -851,7 +912,8 @@ class KsysidOracle:
         self.nzeta = self.n * (self.nd + 1) + self.m * self.nd
         self.model_type = model_type
         lasso = np.atleast_1d(np.asarray(lasso, dtype=np.float64)).copy()
-        lasso[np.isinf(lasso)] = 1e6                      # parse_args 155-157
+        if np.all(np.isinf(lasso)):                       # parse_args 154-156: `if obj.lasso == Inf` is true only when ALL
+            lasso = np.array([1e6])                       # entries are Inf, and the property then becomes the scalar 1e6
         self.lasso = lasso
         merged = merge_trials(data4sysid["train"])
         self.traindata, self.scale = get_scale(merged)
@@ -867,11 +929,11 @@ class KsysidOracle:
         """train_models (Ksysid.m:1344-1389): one full fit per lasso value; model = candidates[0].
         The LS/QP branch test is on the whole lasso PROPERTY (1068)."""
         lasso = self.lasso if lasso is None else np.atleast_1d(np.asarray(lasso, dtype=np.float64))
-        ls_branch = bool(np.all(self.lasso >= 1e6))
-        self.koopData, self.candidates = [], []
+        ls_branch = bool(np.all(self.lasso >= 1e6))       # the test is on the PROPERTY (1068): a mixed vector sends EVERY entry,
+        self.koopData, self.candidates = [], []           # even one >= 1e6, through the QP with t = lasso(i) * N
         for lam in lasso:
-            koop = get_koopman(self.model_type, self.prog, self.pairs,
-                               lasso=(1e6 if ls_branch else lam), N=self.N, n=self.n, nd=self.nd)
+            koop = get_koopman(self.model_type, self.prog, self.pairs, lasso=lam, N=self.N, n=self.n, nd=self.nd,
+                               ls_branch=ls_branch)
             if self.model_type == "nonlinear":
                 mdl = get_NLmodel(koop, self.nzeta, self.n)
             elif self.model_type == "bilinear":

@@ -70,7 +70,7 @@ def test_library_exports_every_declared_symbol():
     """libkoopfit.so loads and exports exactly what include/koopfit.h declares (no compute calls)."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     hdr = open(os.path.join(root, "include", "koopfit.h")).read()
-    declared = set(re.findall(r"\b(kf_[a-z_0-9]+)\s*\(", hdr)) - {"kf_ctx"}
+    declared = set(re.findall(r"\b(kf_[A-Za-z_0-9]+)\s*\(", hdr)) - {"kf_ctx"}
     assert declared == set(A.EXPORTS), declared ^ set(A.EXPORTS)
     if not os.path.exists(A.LIB_PATH):
         import __graft_entry__ as g
@@ -132,3 +132,16 @@ def test_lift_feature_groups(hostlift, types, degs, nv, max_slots):
             assert ngroups.value >= 1 and (used.value <= max_slots or ngroups.value == nf.value - nv or used.value <= nv + 1 + 2 * max(degs))
             if nf.value > 4 * max_slots:
                 assert ngroups.value >= 2
+
+
+def test_mex_shim_compiles_against_the_abi():
+    """matlab/koopfit_mex.cpp cannot run here (no MATLAB / Octave), but it must at least COMPILE against include/koopfit.h
+    and a stub of the MEX API (tests/mex_stub/mex.h): catches ABI drift (renamed fields, changed signatures) in the shim."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-I", os.path.join(root, "tests", "mex_stub"),
+                        "-I", os.path.join(root, "include"), os.path.join(root, "matlab", "koopfit_mex.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    src = open(os.path.join(root, "matlab", "koopfit_mex.cpp")).read()
+    for entry in ("kf_fit_multi", "kf_fit_series", "kf_fit_batch", "kf_rollout", "kf_lift", "kf_mldivide", "kf_mpc_costB_bilinear"):
+        assert entry in src, entry
