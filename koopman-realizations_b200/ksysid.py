@@ -401,7 +401,7 @@ class Ksysid:
         sim = {"t": treal, "u": ureal, "y": np.ascontiguousarray(states[:, :n])}
         if states.shape[1] >= nz:
             sim["zeta"] = np.ascontiguousarray(states[:, :nz])
-        if self.model_type != "nonlinear" and states.shape[1] == self.params["N"]:
+        if self.model_type != "nonlinear" and states.shape[1] in (self.params["N"], self.params["N"] * (self.params["nw"] + 1)):
             sim["z"] = states
         res = {"t": treal, "sim": sim, "real": {"t": treal, "u": ureal, "y": yreal}}
         res["error"] = self.get_error(res["sim"], res["real"])
