@@ -48,3 +48,30 @@ bil = sio.loadmat(sim + "bilinear_poly-3_n-6_m-3_del-0_2020-06-09_16-43.mat", sq
 np.savez_compressed(os.path.join(HERE, "arm_blockM_Z.npz"), lin_Y=lin.Y, lin_Z=lin.Z, bil_Y=bil.Y, bil_Z=bil.Z)
 for f in sorted(os.listdir(HERE)):
     print(f, os.path.getsize(os.path.join(HERE, f)))
+
+# Config 4 at file level: one random system from EVERY shipped `rsys-all` file (35 files, 292 systems in all) plus
+# two of the 20 single-system files of rand-systems_2021-01-11_11-24 (50 training trials each).  The full 312-system set is
+# 56 MB of float64 trajectories — too large to commit — so the fixture samples every FILE instead of every system.
+import glob  # noqa: E402
+
+out = {}
+k = 0
+src = []
+for d in sorted(glob.glob(REF + "datafiles/rand-systems_*")):
+    f = sorted(glob.glob(d + "/rsys-all*.mat"))
+    if not f:
+        continue
+    rs = O.load_rand_systems(f[0])
+    i = len(rs) - 1                                   # the LAST system of the file (rsys_subset.npz holds the first three of file 1)
+    out.update(pack(rs[i], prefix=f"s{k}_"))
+    src.append(f"{os.path.basename(d)}/{os.path.basename(f[0])}#{i}")
+    k += 1
+single = REF + "datafiles/rand-systems_2021-01-11_11-24 (1)/"
+for name in ("rsys-1_train-50_val-1.mat", "rsys-20_train-50_val-1.mat"):
+    out.update(pack(O.load_data4sysid(single + name), prefix=f"s{k}_"))       # a single-system file is a plain data4sysid
+    src.append(f"rand-systems_2021-01-11_11-24 (1)/{name}#0")
+    k += 1
+out["nsys"] = np.array(k)
+out["source"] = np.array(src)
+np.savez_compressed(os.path.join(HERE, "rsys_files.npz"), **out)
+print("rsys_files.npz", k, "systems", os.path.getsize(os.path.join(HERE, "rsys_files.npz")))

@@ -1,0 +1,185 @@
+"""The parity net at the sizes BASELINE.json names:
+  * config 4 at FILE level: one random system from every shipped rsys-all file (35) + two 50-trial single files through
+    kf_fit_batch, compared with the ORACLE on K and on the script's normed_mean_error (evaluate_rand_models.m:69-72);
+  * config 2: validation RMSE on all 5 arm val trials (north_star: identical to 1e-6);
+  * config 3a: ALL 64 budgets of logspace(-2, 2, 64) certified by the Frank-Wolfe gap recomputed in NumPy;
+  * config 5: G, C on 10^5 snapshots of the benchmark workload against the oracle (1e-13), K against the oracle's normal equations;
+  * the default KF_PSD_AS_REFERENCE branch on an ill-conditioned Gram.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import koopfit
+import oracle as O
+from conftest import GOLDEN, unpack
+from koopfit.ksysid import Ksysid
+
+pytestmark = pytest.mark.gpu
+
+
+def relF(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+FITS = [("linear", d, None) for d in range(1, 14)] + [("bilinear", d, None) for d in range(1, 7)] + [("nonlinear", d, 4.0) for d in range(1, 5)]
+
+
+def test_config4_every_file_batched_vs_oracle(fitter):
+    """evaluate_rand_models.m:45-144 on 37 shipped systems (one per data file): 23 fits each, ALL in one kf_fit_batch call.
+    Per fit: K against mldivide (LS) / the QP objective (lasso = 4), and the normalised validation error the script plots,
+    error.mean / mean|y_real| (69-72), from a GPU rollout of the GPU model against the oracle's rollout of the oracle's model."""
+    z = np.load(os.path.join(GOLDEN, "rsys_files.npz"))
+    systems = [unpack(z, prefix=f"s{i}_") for i in range(int(z["nsys"]))]
+    assert len(systems) == 37
+    problems, meta = [], []
+    for si, d in enumerate(systems):
+        base = O.KsysidOracle(d, model_type="linear", obs_type=["poly"], obs_degree=[1])
+        a, b, u = (np.asfortranarray(base.pairs[k]) for k in ("alpha", "beta", "u"))
+        for model, deg, lasso in FITS:
+            nv = 1 + (1 if model == "nonlinear" else 0)
+            prog = O.build_program(["poly"], [deg], nv)
+            pb = dict(basis=koopfit.Basis(["poly"], [deg], nv), model_type=model, alpha=a, beta=b, u=u)
+            if lasso is not None:
+                pb.update(least_squares=False, t=[lasso * prog.N], psd_shift="as_reference")
+            problems.append(pb)
+            meta.append((si, model, deg, prog, lasso, base))
+    res = fitter.fit_batch(problems)
+    assert len(res) == 23 * 37
+    worst_k, worst_e, checked = 0.0, 0.0, 0
+    for pb, r, (si, model, deg, prog, lasso, base) in zip(problems, res, meta):
+        Px, Py = O.build_regressors(model, prog, pb["alpha"], pb["beta"], pb["u"])
+        N = prog.N
+        val = base.valdata[0]
+        yr = val["y"]
+        if lasso is None:
+            Ko, info = O.mldivide(Px, Py, return_info=True)
+            assert r["rank"] == info["rank"], (si, model, deg)
+            ek = relF(r["K"], Ko)
+            assert ek < 1e-8, (si, model, deg, ek)
+            worst_k = max(worst_k, ek)
+        else:
+            G, C = O.gram(Px, Py)
+            if O.needs_psd_shift(G):
+                G = G + 1e-6 * np.eye(G.shape[0])
+            Ko, _ = O.solve_l1ball_qp(G, C, lasso * N)
+            fo, fg = O.qp_objective(G, C, Ko), O.qp_objective(G, C, r["K"])
+            assert abs(fg - fo) <= 1e-8 * abs(fo), (si, model, deg)
+        # the script's metric, GPU model + GPU rollout vs oracle model + oracle rollout
+        koop = {"K": Ko, "N": N, "Px": Px, "Py": Py, "u": pb["u"]}
+        kg = {"K": r["K"], "N": N, "Px": Px, "Py": Py, "u": pb["u"]}
+        zeta0, ur = val["y"][0], val["u"]
+        if model == "linear":
+            mo, mg = O.get_model(koop, 1), O.get_model(kg, 1)
+            sim = fitter.rollout(pb["basis"], model, 1, 1, 1, [{"A": mg["A"], "B": mg["B"]}], [(zeta0, ur)], nout=1)[0][0]
+            want = O.val_model(mo, prog, val, 0, 1)["error"]["mean"]
+        elif model == "bilinear":
+            mo, mg = O.get_BLmodel(koop, 1), O.get_BLmodel(kg, 1)
+            sim = fitter.rollout(pb["basis"], model, 1, 1, 1, [{"A": mg["A"], "B": mg["B"]}], [(zeta0, ur)], nout=1)[0][0]
+            want = O.val_BLmodel(mo, prog, val, 0, 1)["error"]["mean"]
+        else:
+            sim = fitter.rollout(pb["basis"], model, 1, 1, 1, [{"F": np.array(r["K"][:, :1].T)}], [(zeta0, ur)], nout=1)[0][0]
+            want = O.val_NLmodel({"F": np.array(Ko[:, :1].T)}, prog, val, 0, 1, 1)["error"]["mean"]
+        got = np.mean(np.abs(sim - yr), axis=0)
+        zero = np.mean(np.abs(yr), axis=0)                           # mean_error_zeros (line 70)
+        ne_g, ne_o = got / zero, want / zero                         # normed_mean_error (line 71)
+        if np.all(np.isfinite(ne_o)) and np.all(ne_o < 1e3):        # a diverging high-degree rollout is chaotic in both codes
+            e = float(np.max(np.abs(ne_g - ne_o) / np.maximum(1.0, np.abs(ne_o))))
+            assert e < 1e-6, (si, model, deg, ne_g, ne_o)
+            worst_e = max(worst_e, e)
+            checked += 1
+    assert checked >= 0.9 * len(res), checked
+    print(f"config 4: {len(res)} fits, worst K error {worst_k:.2e}, worst normed-mean-error difference {worst_e:.2e} ({checked} rollouts compared)")
+
+
+@pytest.mark.parametrize("model", ["linear", "nonlinear"])
+def test_config2_validation_rmse_on_all_arm_val_trials(fitter, arm_data, model):
+    """Config 2 (poly 3, delays = 1): the GPU-fitted model's open-loop RMSE on each of the 5 arm validation trials equals the
+    oracle's to 1e-6 (north_star), through the Ksysid mirror (GPU fit + GPU rollouts)."""
+    import io
+    import contextlib
+    k = O.KsysidOracle(arm_data, model_type=model, obs_type=["poly"], obs_degree=[3], delays=1).train_models()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ks = Ksysid(arm_data, model_type=model, obs_type=["poly"], obs_degree=[3], delays=1, dim_red=False, fitter=fitter).train_models()
+    results = ks.validate_candidates([ks.model])[0]
+    assert len(results) == 5
+    for trial in range(5):
+        want = k.validate(trial=trial)["error"]["rmse"]
+        got = results[trial]["error"]["rmse"]
+        if np.all(np.isfinite(want)) and np.max(want) < 1e3:
+            assert np.abs(got - want).max() < 1e-6 * max(1.0, np.max(want)), (trial, got, want)
+
+
+def test_config3a_all_64_budgets_certified(fitter, snake_data):
+    """Config 3a at full size, the WHOLE lasso vector logspace(-2, 2, 64) * N in one kf_fit call: every budget feasible and
+    certified — the Frank-Wolfe gap recomputed in NumPy from the oracle's G, C bounds f(K) - f* by 1e-8 |f| (north_star)."""
+    k = O.KsysidOracle(snake_data, model_type="bilinear", obs_type=["fourier"], obs_degree=[4])
+    Px, Py = O.build_regressors("bilinear", k.prog, k.pairs["alpha"], k.pairs["beta"], k.pairs["u"])
+    G, C = O.gram(Px, Py)
+    ts = np.logspace(-2, 2, 64) * k.N
+    basis = koopfit.Basis(["fourier"], [4], 3)
+    res = fitter.fit(basis, "bilinear", k.pairs["alpha"], k.pairs["beta"], k.pairs["u"], least_squares=False, t=ts, psd_shift="as_reference")
+    assert res["info"]["qp_capped"] == 0
+    fs = []
+    for i, t in enumerate(ts):
+        K = res["K_all"][:, :, i]
+        assert np.abs(K).sum() <= t * (1 + 1e-12)
+        grad = G @ K - C
+        f = 0.5 * np.sum(K * (grad - C))
+        gap = float(np.sum(grad * K) + t * np.abs(grad).max())
+        assert gap <= 1e-8 * abs(f), (i, t, gap, f)
+        assert abs(res["objective"][i] - f) <= 1e-9 * abs(f) and res["qp_gap"][i] <= 1e-8 * abs(f)
+        fs.append(f)
+    assert all(b < a for a, b in zip(fs, fs[1:]))
+
+
+def test_config5_parity_on_1e5_snapshots(fitter):
+    """The benchmark workload (n = 12, m = 3, {poly, gaussian} [3, 569] -> N = 1024, bilinear P = 4096) on its first 10^5
+    snapshots: G, C from the Kronecker-block DMMA accumulator against the oracle's dense Px'Px, Px'Py (1e-13);
+    K against the oracle's normal equations (cond(Px) ~ 8e2, so Cholesky of the oracle's G is good to ~1e-10)."""
+    import bench
+    import scipy.linalg as sla
+    M = 100_000
+    _, _, centres = bench.workload_constants()
+    alpha, beta, u = bench.gen_numpy(M, seed=7)
+    basis = koopfit.Basis(bench.OBS_TYPE, bench.OBS_DEGREE, bench.NZETA, centres)
+    res = fitter.fit(basis, "bilinear", alpha, beta, u, want_gram=True, ls_method="gram")
+    assert res["rank"] == 4096 and res["info"]["passes"] == 1
+    prog = O.build_program(bench.OBS_TYPE, bench.OBS_DEGREE, bench.NZETA, centres)
+    G = np.zeros((4096, 4096))
+    C = np.zeros((4096, 4096))
+    for lo in range(0, M, 10_000):                       # blocked: the dense regressors of 10^5 snapshots would be 6.6 GB
+        Px, Py = O.build_regressors("bilinear", prog, alpha[lo:lo + 10_000], beta[lo:lo + 10_000], u[lo:lo + 10_000])
+        G += Px.T @ Px
+        C += Px.T @ Py
+    assert relF(res["G"], G) < 1e-13 and relF(res["C"], C) < 1e-13
+    Ko = sla.cho_solve(sla.cho_factor(G), C)
+    assert relF(res["K"], Ko) < 1e-9
+
+
+def test_default_psd_branch_on_an_ill_conditioned_gram(fitter):
+    """KF_PSD_AS_REFERENCE (the default) replaces `any(eig(G) < 0)` (Ksysid.m:1117-1120) by "the pivoted Cholesky finds G rank
+    deficient at the pivot tolerance": a full-rank but ill-conditioned G (pivot ratio ~1e-5, far above the tolerance) must NOT
+    be shifted, an exactly rank-deficient one must, and kf_info reports the pivots either way."""
+    rng = np.random.default_rng(3)
+    M, n, m = 6000, 3, 1
+    alpha = 2 * rng.random((M, n)) - 1
+    alpha[:, 2] = alpha[:, 0] + 1e-5 * rng.standard_normal(M)          # nearly dependent state: cond(G) ~ 1e10
+    u = 2 * rng.random((M, m)) - 1
+    beta = np.clip(0.9 * alpha + 0.1 * u, -1, 1)
+    basis = koopfit.Basis(["poly"], [1], n)
+    prog = O.build_program(["poly"], [1], n)
+    Px, Py = O.build_regressors("linear", prog, alpha, beta, u)
+    G, C = O.gram(Px, Py)
+    t = [0.5 * np.abs(np.linalg.lstsq(Px, Py, rcond=None)[0]).sum()]
+    res = fitter.fit(basis, "linear", alpha, beta, u, least_squares=False, t=t)                # psd_shift default = as_reference
+    info = res["info"]
+    assert info["psd_shift_applied"] == 0 and info["rank"] == Px.shape[1]
+    assert 1e-7 < info["min_pivot"] / info["max_pivot"] < 1e-3
+    Ko, _ = O.solve_l1ball_qp(G, C, t[0])
+    fo, fg = O.qp_objective(G, C, Ko), O.qp_objective(G, C, res["K"])
+    assert abs(fg - fo) <= 1e-8 * abs(fo)
+    alpha[:, 2] = alpha[:, 0]                                          # exactly dependent -> the reference's eig test is noise; we shift
+    res = fitter.fit(basis, "linear", alpha, np.clip(0.9 * alpha + 0.1 * u, -1, 1), u, least_squares=False, t=t)
+    assert res["info"]["psd_shift_applied"] == 1 and res["info"]["rank"] == Px.shape[1]      # rank of the SHIFTED G
