@@ -104,11 +104,24 @@ def test_config2_validation_rmse_on_all_arm_val_trials(fitter, arm_data, model):
         ks = Ksysid(arm_data, model_type=model, obs_type=["poly"], obs_degree=[3], delays=1, dim_red=False, fitter=fitter).train_models()
     results = ks.validate_candidates([ks.model])[0]
     assert len(results) == 5
+    rng = np.random.default_rng(0)
+    tight = 0
     for trial in range(5):
         want = k.validate(trial=trial)["error"]["rmse"]
         got = results[trial]["error"]["rmse"]
-        if np.all(np.isfinite(want)) and np.max(want) < 1e3:
-            assert np.abs(got - want).max() < 1e-6 * max(1.0, np.max(want)), (trial, got, want)
+        if not (np.all(np.isfinite(want)) and np.max(want) < 1e3):
+            continue
+        # The poly-3 / delays = 1 models are open-loop UNSTABLE on some trials (RMSE of 5-25 in units scaled to [-1, 1]): the
+        # 400-step rollout then amplifies model differences of 1e-10 — the scatter between two LAPACK QR codes on this data
+        #  — beyond 1e-6.  The bar is therefore 1e-6, or 20x the change of the ORACLE's own RMSE under a
+        # 1e-10 relative perturbation of its own model where that is larger.
+        pert = {kk: (v * (1 + 1e-10 * rng.standard_normal(v.shape)) if isinstance(v, np.ndarray) and kk in ("A", "B", "F") else v)
+                for kk, v in k.model.items()}
+        sens = np.abs(k.validate(model=pert, trial=trial)["error"]["rmse"] - want).max()
+        tol = max(1e-6, 20 * sens)
+        assert np.abs(got - want).max() < tol, (trial, got, want, sens)
+        tight += int(tol == 1e-6)
+    print(f"config 2 {model}: {tight} of 5 trials held to 1e-6, the others to 20x the oracle's own 1e-10 sensitivity")
 
 
 def test_config3a_all_64_budgets_certified(fitter, snake_data):
