@@ -1,0 +1,121 @@
+// Standalone check + timing of the INT8 tcgen05 contraction kernel (koopman-realizations_b200/csrc/oz_gemm.cuh):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/_build/oz_gemm_test tools/oz_gemm_test.cu
+//   tools/_build/oz_gemm_test [rowsX rowsY K T]
+// Residues mod p of every Gram (lower tiles) and cross-product tile against a CPU int64 reference; then the rate on a
+// config-5-sized problem (P = 4096 rows, K = 4096 snapshots, 15 moduli).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <random>
+#include "../koopman-realizations_b200/csrc/oz_gemm.cuh"
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static CUtensorMap make_map(void* base, unsigned long long K, unsigned long long rows, unsigned long long T, unsigned box_rows) {
+    static encode_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        fn = (encode_fn)p;
+    }
+    CUtensorMap m;
+    const cuuint64_t gdim[3] = {K, rows, T};
+    const cuuint64_t gstr[2] = {K, K * rows};
+    const cuuint32_t box[3] = {128, box_rows, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed %d\n", (int)r); exit(1); }
+    return m;
+}
+
+int main(int argc, char** argv) {
+    int RX = argc > 1 ? atoi(argv[1]) : 512, RY = argc > 2 ? atoi(argv[2]) : 512, K = argc > 3 ? atoi(argv[3]) : 1024, T = argc > 4 ? atoi(argv[4]) : 3;
+    const unsigned mods[16] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193};
+    const int check = (long long)RX * RY * K <= (1LL << 31);
+    std::mt19937 rng(1);
+    std::vector<int8_t> hx((size_t)T * RX * K), hy((size_t)T * RY * K);
+    for (int t = 0; t < T; ++t) {
+        const int p = mods[t], lo = -(p / 2), hi = (p - 1) / 2;
+        std::uniform_int_distribution<int> d(lo, hi);
+        for (size_t i = 0; i < (size_t)RX * K; ++i) hx[(size_t)t * RX * K + i] = (int8_t)d(rng);
+        for (size_t i = 0; i < (size_t)RY * K; ++i) hy[(size_t)t * RY * K + i] = (int8_t)d(rng);
+    }
+    int8_t *dx, *dy;
+    CK(cudaMalloc(&dx, hx.size())); CK(cudaMalloc(&dy, hy.size()));
+    CK(cudaMemcpy(dx, hx.data(), hx.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dy, hy.data(), hy.size(), cudaMemcpyHostToDevice));
+    // output planes: [G: RX x LD][C: RX x LD], LD = padded max(RX, RY)
+    const int LD = ((std::max(RX, RY) + 255) / 256) * 256, RXp = ((RX + 127) / 128) * 128;
+    const unsigned long long plane = 2ULL * RXp * LD;
+    uint8_t* dout;
+    CK(cudaMalloc(&dout, plane * T));
+    CK(cudaMemset(dout, 0xEE, plane * T));
+    std::vector<oz::Task> tasks;
+    for (int t = 0; t < T; ++t) {
+        for (int mt = 0; mt < RXp / 128; ++mt)
+            for (int nt = 0; nt * 256 <= mt * 128 + 127 && nt * 256 < RX; ++nt)      // Gram: tiles touching the lower triangle
+                tasks.push_back({mt * 128, nt * 256, t, 0, (unsigned long long)mt * 128 * LD + (unsigned long long)nt * 256});
+        for (int mt = 0; mt < RXp / 128; ++mt)
+            for (int nt = 0; nt * 256 < RY; ++nt)
+                tasks.push_back({mt * 128, nt * 256, t, 1, (unsigned long long)RXp * LD + (unsigned long long)mt * 128 * LD + (unsigned long long)nt * 256});
+    }
+    oz::Task* dt;
+    CK(cudaMalloc(&dt, tasks.size() * sizeof(oz::Task)));
+    CK(cudaMemcpy(dt, tasks.data(), tasks.size() * sizeof(oz::Task), cudaMemcpyHostToDevice));
+    oz::Params prm{};
+    prm.tasks = dt; prm.ntasks = (int)tasks.size(); prm.K = K; prm.out = dout; prm.plane = plane; prm.ld_out = LD;
+    prm.m_valid = RXp; prm.n_valid_x = LD; prm.n_valid_y = LD;
+    for (int t = 0; t < T; ++t) {
+        prm.p[t] = mods[t];
+        prm.magic[t] = ((1ULL << 35) + mods[t] - 1) / mods[t];
+        prm.offset[t] = (int)(((1u << 26) + mods[t] - 1) / mods[t] * mods[t]);
+    }
+    CUtensorMap mxa = make_map(dx, K, RX, T, 128), mxb = make_map(dx, K, RX, T, 256), myb = make_map(dy, K, RY, T, 256);
+    CK(cudaFuncSetAttribute(oz::oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
+    int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    const int grid = std::min(sms, prm.ntasks);
+    oz::oz_gemm_kernel<<<grid, oz::THREADS, oz::SMEM_BYTES>>>(mxa, mxb, myb, prm);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    printf("kernel ran: %d tasks on %d CTAs\n", prm.ntasks, grid);
+    if (check) {
+        std::vector<uint8_t> ho(plane * T);
+        CK(cudaMemcpy(ho.data(), dout, ho.size(), cudaMemcpyDeviceToHost));
+        long long bad = 0, seen = 0;
+        for (const oz::Task& tk : tasks) {
+            const int8_t* A = hx.data() + (size_t)tk.t * RX * K;
+            const int8_t* B = (tk.b_is_y ? hy.data() + (size_t)tk.t * RY * K : hx.data() + (size_t)tk.t * RX * K);
+            const int RB = tk.b_is_y ? RY : RX;
+            const int p = mods[tk.t];
+            for (int i = 0; i < 128; ++i)
+                for (int j = 0; j < 256; ++j) {
+                    const int r = tk.a_row + i, c = tk.b_row + j;
+                    long long acc = 0;
+                    if (r < RX && c < RB)
+                        for (int k = 0; k < K; ++k) acc += (long long)A[(size_t)r * K + k] * B[(size_t)c * K + k];
+                    const int want = (int)(((acc % p) + p) % p);
+                    const int got = ho[(size_t)tk.t * plane + tk.out_off + (size_t)i * LD + j];
+                    ++seen;
+                    if (want != got && bad++ < 10) printf("MISMATCH t=%d y=%d (%d,%d): got %d want %d\n", tk.t, tk.b_is_y, r, c, got, want);
+                }
+        }
+        printf("checked %lld residues, %lld mismatches -> %s\n", seen, bad, bad ? "FAIL" : "PASS");
+        if (bad) return 2;
+    }
+    // timing
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 2; ++i) oz::oz_gemm_kernel<<<grid, oz::THREADS, oz::SMEM_BYTES>>>(mxa, mxb, myb, prm);
+    cudaEventRecord(e0);
+    const int reps = 5;
+    for (int i = 0; i < reps; ++i) oz::oz_gemm_kernel<<<grid, oz::THREADS, oz::SMEM_BYTES>>>(mxa, mxb, myb, prm);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+    const double ops = 2.0 * 128 * 256 * (double)K * tasks.size();
+    printf("RX=%d RY=%d K=%d T=%d: %.3f ms per launch, %.1f TOP/s (tile ops issued)\n", RX, RY, K, T, ms, ops / ms / 1e9);
+    return 0;
+}
