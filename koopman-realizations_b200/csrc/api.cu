@@ -117,6 +117,26 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
     Mc = kf_roundup(Mc, 256);
     L.Mc = (int)Mc;
 
+    // Gram engine: the INT8 tensor cores (Ozaki scheme II, ozaki.cu) for the large contractions, the FP64 DMMA kernel otherwise
+    if ((ctx->opt_gram_engine == 2 || (ctx->opt_gram_engine == 0 && L.P >= 1024 && pr->M >= 4LL * L.Mc)) && kf_oz_supported(L)) {
+        L.oz = true;
+        L.dense = true;
+        L.slab = 2LL * L.Pp * L.Pp + KF_ACC_TRAILER;
+        L.nsplit = 1;
+        const size_t panel_bytes = (size_t)L.rows * L.Mc * sizeof(double);
+        for (int b = 0; b < 2; ++b) {
+            KF_CUDA(ctx, ctx->d_panel[b].ensure(panel_bytes));
+            KF_CUDA(ctx, cudaMemsetAsync(ctx->d_panel[b].p, 0, panel_bytes, ctx->stream));
+        }
+        if (p.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * L.n_full * L.Mc * sizeof(double)));
+        KF_CUDA(ctx, ctx->rf.d_dense.ensure((size_t)L.slab * sizeof(double)));
+        KF_CUDA(ctx, ctx->rf.d_dense2.ensure((size_t)L.slab * sizeof(double)));
+        KF_TRY(kf_oz_prepare(ctx, L));
+        L.valid = true;
+        ctx->lay = L;
+        return KF_OK;
+    }
+
     const int tmx = L.Rxp / KF_BM, tny = L.Nyp / KF_BN;
     for (int a = 0; a <= (L.model == KF_BILINEAR ? L.m : 0); ++a)
         for (int b = a; b <= (L.model == KF_BILINEAR ? L.m : 0); ++b) {
@@ -248,6 +268,7 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
         }
         KF_TRY(make_layout(ctx, pr));
         const KfLayout& L = ctx->lay;
+        if (L.oz) KF_CUDA(ctx, cudaMemsetAsync(ctx->rf.d_dense2.p, 0, (size_t)L.slab * sizeof(double), ctx->stream));
         if (L.dense) KF_CUDA(ctx, cudaMemsetAsync(ctx->rf.d_dense.p, 0, (size_t)L.slab * sizeof(double), ctx->stream));
         else KF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)2 * L.nsplit * L.slab * sizeof(double), ctx->stream));
         ctx->accum_M = 0;
@@ -255,7 +276,7 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
     }
     const KfLayout& L = ctx->lay;
     const KfProgram& p = ctx->prog;
-    if (L.dense) {
+    if (L.dense && !L.oz) {
         const long long nch = (pr->M + L.Mc - 1) / L.Mc;
         if (c1 < 0 || c1 > nch) c1 = nch;
         if (c0 == 0) KF_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -265,7 +286,7 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
         ctx->last_gram_kernel_ms = 0.f;
         return KF_OK;
     }
-    const int ntasks = ntasks_of(L);
+    const int ntasks = L.oz ? 0 : ntasks_of(L);
     const bool weighted = (L.model == KF_BILINEAR);
     const long long nchunks = (pr->M + L.Mc - 1) / L.Mc;
     if (c1 < 0 || c1 > nchunks) c1 = nchunks;
@@ -312,7 +333,10 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
             }
             KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], sg));
         }
-        if (ctx->opt_tma)
+        if (L.oz) {
+            double* acc = (b ? ctx->rf.d_dense2 : ctx->rf.d_dense).as<double>();
+            KF_TRY(kf_oz_chunk(ctx, L, b, ctx->d_panel[b].as<double>(), acc, acc + (size_t)L.Pp * L.Pp, sg));
+        } else if (ctx->opt_tma)
             KF_TRY(kf_launch_gram_tma(ctx, ctx->d_tma_tasks[b].as<KfTmaTask>(), ntasks, weighted, ctx->tmap[b], sg));
         else
             KF_TRY(kf_launch_gemm_tasks(ctx, ctx->d_tasks[b].as<KfGemmTask>(), ntasks, weighted, sg));
@@ -325,7 +349,7 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
             ctx->gram_ms_sampled += ms;
             ++ctx->gram_samples;
         }
-        ctx->dmma_flops += (double)L.tiles.size() * 2.0 * KF_TILE_ELEMS * (double)L.Mc;
+        if (!L.oz) ctx->dmma_flops += (double)L.tiles.size() * 2.0 * KF_TILE_ELEMS * (double)L.Mc;
     }
     if (overlap) {   // join pipeline B into the context stream
         KF_CUDA(ctx, cudaEventRecord(ctx->ev[7], S[1]));
@@ -344,6 +368,11 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
 
 int finish_accum(kf_ctx* ctx) {
     const KfLayout& L = ctx->lay;
+    if (L.oz) {      // fold the second pipeline's accumulators into the first (and clear them: idempotent)
+        KF_TRY(kf_oz_finish(ctx, L, ctx->rf.d_dense.as<double>(), ctx->rf.d_dense2.as<double>(), ctx->stream));
+        KF_CUDA(ctx, cudaMemsetAsync(ctx->rf.d_dense2.p, 0, (size_t)2 * L.Pp * L.Pp * sizeof(double), ctx->stream));
+        return KF_OK;
+    }
     if (L.dense) return KF_OK;
     KF_TRY(kf_reduce_slabs(ctx, ctx->d_accum.as<double>(), L.slab, 2 * L.nsplit, ctx->stream));
     return KF_OK;
@@ -604,7 +633,9 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
     KF_CUDA(ctx, ctx->d_misc.ensure(4096));
     KF_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
     if (!ctx->rf.pending) {
-        if (L.dense) {
+        if (L.oz) {
+            KF_TRY(kf_oz_to_gc(ctx, L, ctx->rf.d_dense.as<double>(), ctx->d_G.as<double>(), ctx->d_C.as<double>(), st));
+        } else if (L.dense) {
             double* GC = ctx->rf.d_dense.as<double>();
             KF_TRY(kf_rf_symmetrize(ctx, GC, Pp, st));
             KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_G.p, GC, mat, cudaMemcpyDeviceToDevice, st));
@@ -1065,7 +1096,9 @@ void kf_destroy(kf_ctx* ctx) {
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,
                      &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups,
-                     &ctx->rf.d_S, &ctx->rf.d_St, &ctx->rf.d_Sp, &ctx->rf.d_G2C2, &ctx->rf.d_RP, &ctx->rf.d_Z, &ctx->rf.d_dense};
+                     &ctx->rf.d_S, &ctx->rf.d_St, &ctx->rf.d_Sp, &ctx->rf.d_G2C2, &ctx->rf.d_RP, &ctx->rf.d_Z, &ctx->rf.d_dense,
+                     &ctx->rf.d_dense2};
+    kf_oz_destroy(ctx);
     if (ctx->pchol_graph.exec) cudaGraphExecDestroy(ctx->pchol_graph.exec);
     for (KfBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i)
@@ -1417,6 +1450,7 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "lift_tile") ctx->opt_lift_tile = (int)value;
     else if (n == "lift_ls") ctx->opt_lift_ls = (int)value;
     else if (n == "graphs") ctx->opt_graphs = (int)value;
+    else if (n == "gram_engine") ctx->opt_gram_engine = (int)value;
     else if (n == "qp_split") ctx->opt_qp_split = (int)value;
     else if (n == "refine") ctx->opt_refine = (int)value;
     else if (n == "refine_kappa") ctx->opt_refine_kappa = value;

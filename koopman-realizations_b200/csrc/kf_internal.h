@@ -87,7 +87,8 @@ struct KfTile {
 
 struct KfLayout {
     int model = 0, m = 0, nzeta = 0, nv = 0, nw = 0;
-    bool dense = false;       // `loaded` models: G, C accumulated densely from the materialised regressors (rf.d_dense)
+    bool dense = false;       // G, C accumulated densely (rf.d_dense): `loaded` models, and the INT8 engine
+    bool oz = false;          // INT8 tensor-core engine (ozaki.cu): accumulators are ROW-major [G | C] per chunk pipeline
     int n_full = 0, N = 0, P = 0;
     int Pc = 0;               // columns of C / K actually computed (pc_cols fast mode), <= P
     int Rx = 0, Rxp = 0;      // rows of the X section: N (+m for linear), padded to BM
@@ -118,7 +119,8 @@ struct KfRefine {
     KfBuf d_S, d_St, d_Sp;    // basis S (row = new feature, column = original; column-major), its transpose, Pi S
     KfBuf d_G2C2;             // [G2 | C2] of the new features: what the ranks all-reduce in a refinement pass
     KfBuf d_RP, d_Z;          // chunk panels: materialised [Px | Py] rows and the transformed features
-    KfBuf d_dense;            // `loaded` models: dense accumulator [G | C | trailer] (2 Pp^2 + KF_ACC_TRAILER doubles)
+    KfBuf d_dense;            // dense accumulator [G | C | trailer] (2 Pp^2 + KF_ACC_TRAILER doubles): `loaded` models, INT8 engine
+    KfBuf d_dense2;           // INT8 engine: the accumulator set of the second chunk pipeline
 };
 
 // the blocked pivoted Cholesky of kf_solve_gram_ls as an instantiated CUDA graph, valid for one set of buffers / sizes
@@ -131,8 +133,13 @@ struct KfPcholGraph {
     double flops = 0;
 };
 
+struct KfOzState;   // ozaki.cu
+
 struct kf_ctx {
     int device = 0;
+    KfOzState* oz = nullptr;
+    int opt_gram_engine = 0;  // 0 auto, 1 FP64 DMMA, 2 INT8 tensor cores (Ozaki scheme II, FP64-exact)
+    double i8_ops = 0;        // INT8 tensor-core operations issued
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_fork = nullptr;
@@ -293,6 +300,14 @@ int kf_pchol_solve(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const doubl
 // Householder QRCP basic solution of A X = B;  AB = [A | B] (M x (P+Pc), ld = ldab) is overwritten
 int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long long ldab, double* X, long long ldx,
                    int* d_perm, int* rank_out, double* min_piv, double* max_piv, cudaStream_t st);
+
+// ozaki.cu: FP64-exact Gram / cross products on the INT8 tensor cores
+bool kf_oz_supported(const KfLayout& L);
+int kf_oz_prepare(kf_ctx* ctx, KfLayout& L);
+int kf_oz_chunk(kf_ctx* ctx, const KfLayout& L, int b, const double* panel, double* accG, double* accC, cudaStream_t st);
+int kf_oz_finish(kf_ctx* ctx, const KfLayout& L, double* acc0, const double* acc1, cudaStream_t st);
+int kf_oz_to_gc(kf_ctx* ctx, const KfLayout& L, const double* acc, double* G, double* C, cudaStream_t st);
+void kf_oz_destroy(kf_ctx* ctx);
 
 // batch.cu
 int kf_fit_batch_small(kf_ctx* ctx, int nprob, const kf_basis* const* bases, const kf_problem* probs, const kf_solve* solves, kf_result* outs,

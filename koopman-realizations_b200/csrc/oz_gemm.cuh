@@ -43,8 +43,8 @@ struct Params {
     int ld_out;                 // row stride of the output planes (elements)
     int m_valid, n_valid_x, n_valid_y;   // rows beyond these are padding (not stored)
     unsigned p[32];             // moduli
-    unsigned long long magic[32];   // ceil(2^35 / p)
-    int offset[32];             // multiple of p >= 2^26: makes the accumulator non-negative before the division
+    unsigned long long magic[32];   // ceil(2^37 / p): floor(a / p) = (a * magic) >> 37 exactly for a < 2^29
+    int offset[32];             // multiple of p >= 2^27 (|accumulator| <= K * 128^2 <= 2^27 for K <= 8192): makes it non-negative
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -210,8 +210,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap tmap_xa, const __grid_constan
                     uint32_t w = 0;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const unsigned a = (unsigned)((int)v[q * 4 + e] + off);              // >= 0, < 2^27 + p
-                        const unsigned quo = (unsigned)(((unsigned long long)a * mg) >> 35);
+                        const unsigned a = (unsigned)((int)v[q * 4 + e] + off);              // >= 0, < 2^28 + p
+                        const unsigned quo = (unsigned)(((unsigned long long)a * mg) >> 37);
                         const unsigned r = a - quo * p;                                        // in [0, p)
                         w |= (r & 0xFFu) << (8 * e);
                     }

@@ -71,8 +71,8 @@ int main(int argc, char** argv) {
     prm.m_valid = RXp; prm.n_valid_x = LD; prm.n_valid_y = LD;
     for (int t = 0; t < T; ++t) {
         prm.p[t] = mods[t];
-        prm.magic[t] = ((1ULL << 35) + mods[t] - 1) / mods[t];
-        prm.offset[t] = (int)(((1u << 26) + mods[t] - 1) / mods[t] * mods[t]);
+        prm.magic[t] = ((1ULL << 37) + mods[t] - 1) / mods[t];
+        prm.offset[t] = (int)(((1u << 27) + mods[t] - 1) / mods[t] * mods[t]);
     }
     CUtensorMap mxa = make_map(dx, K, RX, T, 128), mxb = make_map(dx, K, RX, T, 256), myb = make_map(dy, K, RY, T, 256);
     CK(cudaFuncSetAttribute(oz::oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz::SMEM_BYTES));
