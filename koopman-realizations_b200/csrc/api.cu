@@ -1451,6 +1451,7 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "lift_ls") ctx->opt_lift_ls = (int)value;
     else if (n == "graphs") ctx->opt_graphs = (int)value;
     else if (n == "gram_engine") ctx->opt_gram_engine = (int)value;
+    else if (n == "oz_sym") ctx->opt_oz_sym = (int)value;
     else if (n == "qp_split") ctx->opt_qp_split = (int)value;
     else if (n == "refine") ctx->opt_refine = (int)value;
     else if (n == "refine_kappa") ctx->opt_refine_kappa = value;

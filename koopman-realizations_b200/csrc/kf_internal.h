@@ -138,6 +138,7 @@ struct KfOzState;   // ozaki.cu
 struct kf_ctx {
     int device = 0;
     KfOzState* oz = nullptr;
+    int opt_oz_sym = 1;       // INT8 engine: exploit the Kronecker block symmetry of a bilinear regressor
     int opt_gram_engine = 0;  // 0 auto, 1 FP64 DMMA, 2 INT8 tensor cores (Ozaki scheme II, FP64-exact)
     double i8_ops = 0;        // INT8 tensor-core operations issued
     cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -306,7 +307,7 @@ bool kf_oz_supported(const KfLayout& L);
 int kf_oz_prepare(kf_ctx* ctx, KfLayout& L);
 int kf_oz_chunk(kf_ctx* ctx, const KfLayout& L, int b, const double* panel, double* accG, double* accC, cudaStream_t st);
 int kf_oz_finish(kf_ctx* ctx, const KfLayout& L, double* acc0, const double* acc1, cudaStream_t st);
-int kf_oz_to_gc(kf_ctx* ctx, const KfLayout& L, const double* acc, double* G, double* C, cudaStream_t st);
+int kf_oz_to_gc(kf_ctx* ctx, const KfLayout& L, double* acc, double* G, double* C, cudaStream_t st);
 void kf_oz_destroy(kf_ctx* ctx);
 
 // batch.cu

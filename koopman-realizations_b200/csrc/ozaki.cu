@@ -144,6 +144,10 @@ struct OzCrtArgs {
     const int* e_fx; const int* e_fy; const int* e_u;
     double* accG; double* accC;      // row-major [m * Pp + n] accumulators (G: n <= m only)
     int Pp;
+    int symC;                        // the C symmetry is in use as well
+    int symN;                        // > 0: Kronecker block size N of a bilinear regressor whose block symmetry is exploited:
+                                     //   G block (a, b): only local rows >= local columns are computed (the block is symmetric),
+                                     //   C block (a, b): only a <= b (C_(a,b) = C_(b,a));  0: everything on / below the diagonal
     OzConst c;
 };
 
@@ -156,6 +160,10 @@ __global__ void __launch_bounds__(256) oz_crt_kernel(const OzCrtArgs a) {
     const bool isC = blockIdx.z != 0;
     const int ncols = isC ? a.yrows : a.xrows;
     if (n0 >= ncols || (!isC && n0 > m)) return;      // the Gram is computed on / below the diagonal only
+    if (a.symN) {                                     // whole 4-column group outside the computed part of its Kronecker block
+        const int ba = m / a.symN, bb = n0 / a.symN, r = m % a.symN, c0 = n0 % a.symN;     // (4 | N: a group never straddles blocks)
+        if (isC ? (a.symC && ba > bb) : (c0 > r)) return;
+    }
     const uint8_t* src = a.res + (isC ? a.c_off : 0ull) + (size_t)m * a.LD + n0;
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, s3[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(256) oz_crt_kernel(const OzCrtArgs a) {
     for (int e = 0; e < 4; ++e) {
         const int n = n0 + e;
         double x = 0.0;
-        if (n < ncols && (isC || n <= m)) {      // above the diagonal the Gram tiles may not have been computed
+        if (n < ncols && (isC || n <= m) && (!a.symN || isC || (n % a.symN) <= (m % a.symN))) {   // computed entries only
             const int en = isC ? (a.e_fy[n % a.nfy] + a.e_u[n / a.nfy]) : (a.e_fx[n % a.nfx] + a.e_u[n / a.nfx]);
             const double f1 = s1[e] - ((s1[e] + OZ_MAGIC) - OZ_MAGIC);       // centred fraction of the leading sum (exact)
             const double f = f1 + (s2[e] + s3[e]);
@@ -190,6 +198,18 @@ __global__ void __launch_bounds__(256) oz_crt_kernel(const OzCrtArgs a) {
     o0.x += v[0]; o0.y += v[1]; o1.x += v[2]; o1.y += v[3];
     p2[0] = o0;
     p2[1] = o1;
+}
+
+// fill the entries the block symmetry skipped (row-major accumulators): G block (a >= b): local upper = transposed local lower;
+// C block (a > b) = C block (b, a)
+__global__ void oz_mirror_kernel(double* __restrict__ accG, double* __restrict__ accC, int Pp, int P, int N, int doC) {
+    const long long n_el = (long long)P * P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(e / P), n = (int)(e % P);
+        const int ba = m / N, bb = n / N, r = m % N, c = n % N;
+        if (ba >= bb && c > r) accG[(size_t)m * Pp + n] = accG[(size_t)(ba * N + c) * Pp + bb * N + r];
+        if (doC && ba > bb) accC[(size_t)m * Pp + n] = accC[(size_t)(bb * N + r) * Pp + ba * N + c];
+    }
 }
 
 __global__ void oz_add_kernel(double* __restrict__ a, const double* __restrict__ b, long long n) {
@@ -253,6 +273,8 @@ OzConst make_consts() {
 struct KfOzState {
     bool ready = false;
     int xrows = 0, yrows = 0, LD = 0, Mc = 0, nfx = 0, nfy = 0, nblk = 1, Pp = 0;
+    int symN = 0;             // Kronecker block symmetry in use (bilinear, N a multiple of 256)
+    bool symC = false;        // ... for the cross product too (all of Py wanted)
     unsigned long long plane = 0, c_off = 0;
     KfBuf d_rx[2], d_ry[2], d_res[2], d_exp[2], d_rowlist, d_tasks;
     CUtensorMap mxa[2], mxb[2], myb[2];
@@ -305,15 +327,25 @@ int kf_oz_prepare(kf_ctx* ctx, KfLayout& L) {
     S.nrowlist = (int)rows.size();
     KF_CUDA(ctx, S.d_rowlist.ensure(rows.size() * sizeof(int)));
     KF_CUDA(ctx, cudaMemcpyAsync(S.d_rowlist.p, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    // Kronecker structure of the bilinear regressor Px = [1; u] (x) psi: G block (a, b) = sum u_a u_b psi psi' is itself symmetric and
+    // C block (a, b) = C block (b, a) — 15.3 N^2 instead of 24.5 N^2 tile area (the same saving the DMMA path takes with its
+    // weighted blocks).  Needs whole tiles per block (N a multiple of 256); C only when all of Py is wanted.
+    S.symN = (bil && L.N % 256 == 0 && ctx->opt_oz_sym) ? L.N : 0;
+    const bool symC = S.symN && S.yrows == S.xrows;
     std::vector<oz::Task> tasks;
     for (int t = 0; t < OZ_T; ++t) {
         for (int mt = 0; mt * 128 < S.xrows; ++mt)
-            for (int nt = 0; nt * 256 <= mt * 128 + 127 && nt * 256 < S.xrows; ++nt)
+            for (int nt = 0; nt * 256 <= mt * 128 + 127 && nt * 256 < S.xrows; ++nt) {
+                if (S.symN && (nt * 256) % S.symN > (mt * 128) % S.symN + 127) continue;        // local upper tile of a block
                 tasks.push_back({mt * 128, nt * 256, t, 0, (unsigned long long)mt * 128 * S.LD + (unsigned long long)nt * 256});
+            }
         for (int mt = 0; mt * 128 < S.xrows; ++mt)
-            for (int nt = 0; nt * 256 < S.yrows; ++nt)
+            for (int nt = 0; nt * 256 < S.yrows; ++nt) {
+                if (symC && (mt * 128) / S.symN > (nt * 256) / S.symN) continue;               // block a > b: mirrored from (b, a)
                 tasks.push_back({mt * 128, nt * 256, t, 1, S.c_off + (unsigned long long)mt * 128 * S.LD + (unsigned long long)nt * 256});
+            }
     }
+    S.symC = symC;
     S.ntasks = (int)tasks.size();
     KF_CUDA(ctx, S.d_tasks.ensure(tasks.size() * sizeof(oz::Task)));
     KF_CUDA(ctx, cudaMemcpyAsync(S.d_tasks.p, tasks.data(), tasks.size() * sizeof(oz::Task), cudaMemcpyHostToDevice, ctx->stream));
@@ -386,6 +418,8 @@ int kf_oz_chunk(kf_ctx* ctx, const KfLayout& L, int b, const double* panel, doub
     ca.xrows = S.xrows; ca.yrows = S.yrows; ca.nfx = S.nfx; ca.nfy = S.nfy;
     ca.e_fx = e_fx; ca.e_fy = e_fy; ca.e_u = e_u;
     ca.accG = accG; ca.accC = accC; ca.Pp = S.Pp;
+    ca.symN = S.symN;
+    ca.symC = S.symC ? 1 : 0;
     ca.c = S.c;
     oz_crt_kernel<<<dim3((S.LD / 4 + 255) / 256, S.xrows, 2), 256, 0, st>>>(ca);
     KF_CUDA(ctx, cudaGetLastError());
@@ -402,7 +436,14 @@ int kf_oz_finish(kf_ctx* ctx, const KfLayout& L, double* acc0, const double* acc
     ctx->launches += 1;
     return KF_OK;
 }
-int kf_oz_to_gc(kf_ctx* ctx, const KfLayout& L, const double* acc, double* G, double* C, cudaStream_t st) {
+int kf_oz_to_gc(kf_ctx* ctx, const KfLayout& L, double* acc, double* G, double* C, cudaStream_t st) {
+    KfOzState& S = *ctx->oz;
+    if (S.symN) {
+        // the mirror reads entries it never writes (computed ones) and writes entries it never reads: safe in place
+        oz_mirror_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(acc, acc + (size_t)L.Pp * L.Pp, L.Pp, L.P, S.symN, S.symC ? 1 : 0);
+        KF_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
     KF_TRY(kf_rf_transpose(ctx, acc, G, L.Pp, st));                         // row-major lower -> column-major lower
     KF_TRY(kf_rf_symmetrize(ctx, G, L.Pp, st));
     KF_TRY(kf_rf_transpose(ctx, acc + (size_t)L.Pp * L.Pp, C, L.Pp, st));

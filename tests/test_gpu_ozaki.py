@@ -115,3 +115,33 @@ def test_int8_engine_scales_rows_of_very_different_magnitude(i8):
     G = (Px.astype(np.longdouble).T @ Px.astype(np.longdouble)).astype(np.float64)
     nrm = np.sqrt(np.diag(G))
     assert np.max(np.abs(res["G"] - G) / np.outer(nrm, nrm)) < 1e-15
+
+
+@pytest.mark.parametrize("pc", [0, 256])
+def test_int8_engine_kronecker_block_symmetry(fitter, pc):
+    """Bilinear regressor with N a multiple of 256: only the lower half of every G block and the C blocks (a <= b) are
+    contracted, the rest is mirrored (G_(a,b) is symmetric, C_(a,b) = C_(b,a)); same G, C, K as without the shortcut and as the
+    oracle.  pc_cols = N restricts Py to its first block: the C symmetry is then not used, the G symmetry still is."""
+    n, m, M = 4, 2, 9000
+    alpha, beta, u = synth(M, n, m, seed=21)
+    cen = 2 * np.random.default_rng(4).random((n, 241)) - 1
+    basis = koopfit.Basis(["poly", "gaussian"], [2, 241], n, cen)          # N = 4 + 10 + 241 + 1 = 256
+    prog = O.build_program(["poly", "gaussian"], [2, 241], n, cen)
+    assert prog.N == 256
+    Px, Py = O.build_regressors("bilinear", prog, alpha, beta, u)
+    out = {}
+    for sym in (1, 0):
+        fitter.set_option("gram_engine", 2)
+        fitter.set_option("oz_sym", sym)
+        try:
+            out[sym] = fitter.fit(basis, "bilinear", alpha, beta, u, want_gram=True, ls_method="gram", pc_cols=pc)
+        finally:
+            fitter.set_option("gram_engine", 0)
+            fitter.set_option("oz_sym", 1)
+    G, C = Px.T @ Px, Px.T @ Py
+    assert relF(out[1]["G"], G) < 1e-13 and np.array_equal(out[1]["G"], out[1]["G"].T)
+    cols = slice(0, pc if pc else C.shape[1])
+    assert relF(out[1]["C"][:, cols], C[:, cols]) < 1e-13
+    assert np.array_equal(out[1]["G"], out[0]["G"])                      # exact integer arithmetic: the mirrored entries are identical
+    assert np.array_equal(out[1]["C"][:, cols], out[0]["C"][:, cols])
+    assert relF(out[1]["K"], out[0]["K"]) < 1e-12
