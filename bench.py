@@ -125,9 +125,9 @@ def fp64_peak_measured(dev, n=8192, reps=12):
     return {"burst": flop / (min(per) * 1e-3) / 1e12, "sustained": flop * reps / (evs[0].elapsed_time(evs[reps]) * 1e-3) / 1e12}
 
 
-def gram_traffic_from_profile():
-    """dram bytes per launch of the Gram kernel from the committed ncu capture (NOT measured in this run)."""
-    for name in ("r02_gram_tma_traffic.json", "r01_gram_tma_traffic.json"):
+def gram_traffic_from_profile(kernel="gram_tma"):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (NOT measured in this run)."""
+    for name in (f"r02_{kernel}_traffic.json", f"r01_{kernel}_traffic.json"):
         try:
             d = json.load(open(os.path.join(ROOT, "profiles", name)))
             return float(d["dram_bytes_per_launch"]), f"profiles/{name} ({d.get('source', 'ncu --set full')})"
@@ -376,6 +376,7 @@ def main():
         res = step_resident()
     barrier()
     fit.counters(reset=True)
+    fit.engine_info(reset=True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gram_ms, liftgram_ms, solve_ms = [], [], []
@@ -389,6 +390,7 @@ def main():
     clocks = sampler.stop() if sampler else None
     ms_total = e0.elapsed_time(e1)
     flops_issued, launches = fit.counters()
+    eng = fit.engine_info()
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -484,16 +486,68 @@ def main():
             lasso3a = {"error": str(exc)[:300]}
 
     if rank == 0:
-        peak = peak_now["sustained"]
         committed = fp64_peak_committed()
         tiles_flops = flops_issued / args.steps                      # DMMA flops issued per step (incl. solver GEMMs)
-        gram_flops = 1000 * 2.0 * 128 * 128 * M                       # 10 Kronecker blocks x (36 G + 64 C) tiles
         gk = float(np.mean(gram_ms)) if gram_ms and np.mean(gram_ms) > 0 else float(np.mean(liftgram_ms))
         lg = float(np.mean(liftgram_ms))
-        # achieved: issued DMMA flops of the Gram kernel / the MEASURED device time of the whole lift + Gram phase of a step
-        # (CUDA events on the library's stream around all launches) — conservative: the lifts and the pipeline tails are inside.
-        achieved = gram_flops / (lg * 1e-3) / 1e12
-        traffic, traffic_src = gram_traffic_from_profile()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        if eng["engine"] == 2:
+            # INT8 tensor-core engine (Ozaki scheme II, FP64-exact): the dominant kernel is oz_gemm_kernel (tcgen05.mma kind::i8).
+            # achieved = INT8 operations issued per contraction launch / mean duration of the sampled launches (CUDA events on
+            # the launching stream, launch isolated from the other pipeline); peak = 2 x the MEASURED dense bf16 rate of this
+            # pool's B200 (INT8 runs at twice the bf16 rate on these tensor cores): burst figure, the kernel is timed alone.
+            launches_per_step = max(eng["gram_launches"], 1)
+            k_ms = gk / launches_per_step
+            ach = eng["i8_ops_per_launch"] / (k_ms * 1e-3) / 1e12
+            bf16 = float(peaks.get("bf16_tflops", 1654.5))
+            peak_i8 = 2.0 * bf16
+            traffic, traffic_src = gram_traffic_from_profile("oz_gemm")
+            roof = {"bound": "tensor", "kernel": "oz::oz_gemm_kernel (tcgen05.mma kind::i8, INT32 accumulators in TMEM, TMA operands; "
+                                                   "15 residue GEMMs per panel = one FP64-exact Gram / cross product, Ozaki scheme II)",
+                    "achieved": ach, "peak": peak_i8, "unit": "TFLOP/s", "frac": ach / peak_i8,
+                    "unit_note": "INT8 tensor operations (TOP/s); 2 ops per multiply-accumulate",
+                    "peak_source": f"2 x MEASURED_PEAKS.json bf16_tflops ({bf16}, burst: cuBLAS bf16 8192^3 timed alone) - the INT8 rate of the "
+                                   "tcgen05 tensor cores is twice the bf16 rate; nominal INT8 dense peak 4500",
+                    "frac_of_nominal_4500": ach / 4500.0,
+                    "traffic": traffic, "traffic_unit": "bytes per launch (one 4096-snapshot panel, all 15 moduli)",
+                    "traffic_source": f"NOT measured in this run: {traffic_src}" if traffic_src else None,
+                    "kernel_ms_per_launch": k_ms, "launches_per_step": launches_per_step, "sampled_launches_per_step": eng["gram_sampled"],
+                    "time_basis": "mean of the isolated, sampled contraction launches (CUDA events on the launching stream)",
+                    "int8_ops_per_launch": eng["i8_ops_per_launch"],
+                    "algorithmic_flops_per_pair": FLOPS_ALGO_PER_PAIR,
+                    "fp64_equivalent_achieved": FLOPS_ALGO_PER_PAIR * M / (lg * 1e-3) / 1e12,
+                    "fp64_equivalent_note": "algorithmic FP64 flops P(P+1) + 2 P Pc per pair / measured lift + Gram phase: what an FP64 "
+                                            "tensor pipe would have to sustain; this box's measured cuBLAS DGEMM peak is below",
+                    "fp64_dgemm_peak_this_run": peak_now["sustained"], "fp64_dgemm_peak_committed_crosscheck": committed,
+                    "lift_gram_ms_per_step": lg, "solve_ms_per_step": float(np.mean(solve_ms)),
+                    "engine": "int8 (auto: P >= 1024 and >= 4 panels; kf_set_option gram_engine=1 selects the FP64 DMMA kernel)"}
+        else:
+            peak = peak_now["sustained"]
+            gram_flops = 1000 * 2.0 * 128 * 128 * M                       # 10 Kronecker blocks x (36 G + 64 C) tiles
+            achieved = gram_flops / (lg * 1e-3) / 1e12
+            traffic, traffic_src = gram_traffic_from_profile("gram_tma")
+            roof = {"bound": "tensor", "kernel": "kf_gram_tma_kernel<true> (FP64 DMMA.8x8x4 Gram/cross-covariance, tensor-map TMA operands)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic, "traffic_unit": "bytes per launch (one 4096-snapshot panel)",
+                    "traffic_source": f"NOT measured in this run: {traffic_src}" if traffic_src else None,
+                    "algorithmic_flops_per_launch": FLOPS_ALGO_PER_PAIR * 4096, "issued_flops_per_launch": 1000 * 2.0 * 128 * 128 * 4096,
+                    "peak_source": "cuBLAS DGEMM 8192^3 fp64 (torch.matmul) measured in THIS run on this box, 12 GEMMs back to back "
+                                   "(sustained); MEASURED_PEAKS.json has no FP64 entry",
+                    "peak_burst": peak_now["burst"], "peak_committed_crosscheck": committed,
+                    "time_basis": "lift_gram_ms_per_step: CUDA events on the library's stream around the whole lift + Gram phase",
+                    "flops_basis": "DMMA flops actually issued per step by the Gram kernel (Kronecker blocks: 1000 tiles x 2x128x128 per snapshot = 3.28e7/pair)",
+                    "achieved_algorithmic": FLOPS_ALGO_PER_PAIR * M / (lg * 1e-3) / 1e12,
+                    "algorithmic_flops_per_pair": FLOPS_ALGO_PER_PAIR, "issued_flops_per_pair": 1000 * 2.0 * 128 * 128,
+                    "gram_kernel_ms_per_step_estimate": gk,
+                    "gram_kernel_ms_note": "ESTIMATE: mean of the isolated every-61st-launch samples x launches per step (not a measured total)",
+                    "achieved_kernel_only_estimate": gram_flops / (gk * 1e-3) / 1e12,
+                    "lift_gram_ms_per_step": lg,
+                    "solve_ms_per_step": float(np.mean(solve_ms)), "dmma_flops_issued_per_step_all_kernels": tiles_flops,
+                    "engine": "fp64 dmma"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -506,23 +560,7 @@ def main():
             "fast_mode": fast,
             "lift_only": lift_only,
             "lasso3a": lasso3a,
-            "roofline": {"bound": "tensor", "kernel": "kf_gram_tma_kernel<true> (FP64 DMMA.8x8x4 Gram/cross-covariance, tensor-map TMA operands)",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_unit": "bytes per launch (one 4096-snapshot panel)",
-                         "traffic_source": f"NOT measured in this run: {traffic_src}" if traffic_src else None,
-                         "algorithmic_flops_per_launch": FLOPS_ALGO_PER_PAIR * 4096, "issued_flops_per_launch": 1000 * 2.0 * 128 * 128 * 4096,
-                         "peak_source": "cuBLAS DGEMM 8192^3 fp64 (torch.matmul) measured in THIS run on this box, 12 GEMMs back to back "
-                                        "(sustained); MEASURED_PEAKS.json has no FP64 entry",
-                         "peak_burst": peak_now["burst"], "peak_committed_crosscheck": committed,
-                         "time_basis": "lift_gram_ms_per_step: CUDA events on the library's stream around the whole lift + Gram phase",
-                         "flops_basis": "DMMA flops actually issued per step by the Gram kernel (Kronecker blocks: 1000 tiles x 2x128x128 per snapshot = 3.28e7/pair)",
-                         "achieved_algorithmic": FLOPS_ALGO_PER_PAIR * M / (lg * 1e-3) / 1e12,
-                         "algorithmic_flops_per_pair": FLOPS_ALGO_PER_PAIR, "issued_flops_per_pair": 1000 * 2.0 * 128 * 128,
-                         "gram_kernel_ms_per_step_estimate": gk,
-                         "gram_kernel_ms_note": "ESTIMATE: mean of the isolated every-61st-launch samples x launches per step (not a measured total)",
-                         "achieved_kernel_only_estimate": gram_flops / (gk * 1e-3) / 1e12,
-                         "lift_gram_ms_per_step": lg,
-                         "solve_ms_per_step": float(np.mean(solve_ms)), "dmma_flops_issued_per_step_all_kernels": tiles_flops},
+            "roofline": roof,
         }
         if not args.no_cpu_baseline:
             rate_lg, t_solve, t_lg = cpu_fit_rates(args.cpu_sample, os.cpu_count())

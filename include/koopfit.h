@@ -299,7 +299,12 @@ int  kf_comm_info(const kf_ctx* ctx, int* nranks, int* rank, int* nccl_version);
 /* ---- instrumentation for bench.py / tests ----------------------------- */
 /* flops issued to the FP64 tensor pipe and kernel launches since the last reset */
 int kf_counters(kf_ctx* ctx, double* dmma_flops, long long* launches, int reset);
-/* device time (ms, CUDA events on the context stream) of the last lift+Gram phase and solve phase */
+/* which Gram engine the last accumulation used (1: FP64 DMMA, 2: INT8 tensor cores / Ozaki scheme II — FP64-exact), the INT8
+ * tensor operations issued since the last reset and per contraction launch, the contraction launches of the last accumulation
+ * and how many of them were timed in isolation ("profile" option) */
+int kf_engine_info(kf_ctx* ctx, int* engine, double* i8_ops, double* i8_ops_per_launch, long long* gram_launches, int* gram_sampled, int reset);
+/* device time (ms, CUDA events on the context stream) of the last lift+Gram phase and solve phase; gram_kernel_ms is an ESTIMATE:
+ * mean duration of the isolated, sampled contraction launches x the number of launches */
 int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, double* solve_ms);
 /* tuning knobs; returns KF_EINVAL if unknown:
  *   "chunk" (snapshots per L2-resident panel), "panel_mb", "splitk", "overlap" (two chunk pipelines), "tma" (Gram operands by
@@ -309,7 +314,9 @@ int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, dou
  *   "as_ws_gb" (active set: bound on the factor workspace), "lift_tile" (materialising lift: shared-memory tile kernel = 1),
  *   "refine" (Gram-route refinement: 0 off, 1 adaptive = default, 2 always at least one extra pass), "refine_kappa" (pivot-ratio
  *   threshold, default 1e3), "refine_level_tol" (dynamic range one level resolves, default 1e-5), "refine_max" (level limit, 4),
- *   "qp_split" (multi-GPU context: split the active-set lasso sweep by columns over the ranks, default 1) */
+ *   "qp_split" (multi-GPU context: split the active-set lasso sweep by columns over the ranks, default 1),
+ *   "gram_engine" (0 auto: INT8 tensor cores for P >= 1024 and >= 4 panels of snapshots, FP64 DMMA otherwise; 1 DMMA; 2 INT8),
+ *   "oz_sym" (INT8 engine: exploit the Kronecker block symmetry of a bilinear regressor, default 1) */
 int kf_set_option(kf_ctx* ctx, const char* name, double value);
 
 #ifdef __cplusplus

@@ -190,6 +190,7 @@ def load():
         "kf_sync": (i, [vp]),
         "kf_stream": (vp, [vp]),
         "kf_counters": (i, [vp, c_double_p, P(ll), i]),
+        "kf_engine_info": (i, [vp, c_int_p, c_double_p, c_double_p, P(ll), c_int_p, i]),
         "kf_last_times": (i, [vp, c_double_p, c_double_p, c_double_p]),
         "kf_set_option": (i, [vp, C.c_char_p, d]),
         "kf_create_multi": (i, [P(vp), c_int_p, i]),
@@ -213,6 +214,6 @@ def load():
 
 EXPORTS = ["kf_create", "kf_destroy", "kf_last_error", "kf_version", "kf_basis_dims", "kf_block_table",
            "kf_lift", "kf_fit", "kf_fit_dev", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_mpc_costB_bilinear", "kf_set_qp_partition", "kf_mldivide", "kf_accumulate_dev", "kf_regressors_dev", "kf_lift_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
-           "kf_stream", "kf_counters", "kf_last_times", "kf_set_option",
+           "kf_stream", "kf_counters", "kf_engine_info", "kf_last_times", "kf_set_option",
            "kf_create_multi", "kf_destroy_multi", "kf_multi_size", "kf_multi_ctx", "kf_multi_last_error", "kf_multi_set_option", "kf_fit_multi",
            "kf_comm_unique_id", "kf_comm_init_rank", "kf_comm_destroy", "kf_comm_info"]

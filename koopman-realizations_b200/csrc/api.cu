@@ -123,14 +123,17 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
         L.dense = true;
         L.slab = 2LL * L.Pp * L.Pp + KF_ACC_TRAILER;
         L.nsplit = 1;
+        // chunk pipelines in flight (option "oz_pipes")
+        L.npipes = std::max(2, std::min(ctx->opt_oz_pipes, KF_MAX_PIPES));
         const size_t panel_bytes = (size_t)L.rows * L.Mc * sizeof(double);
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < L.npipes; ++b) {
             KF_CUDA(ctx, ctx->d_panel[b].ensure(panel_bytes));
             KF_CUDA(ctx, cudaMemsetAsync(ctx->d_panel[b].p, 0, panel_bytes, ctx->stream));
         }
-        if (p.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * L.n_full * L.Mc * sizeof(double)));
+        if (p.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)L.npipes * 2 * L.n_full * L.Mc * sizeof(double)));   // dim_red scratch per pipeline
         KF_CUDA(ctx, ctx->rf.d_dense.ensure((size_t)L.slab * sizeof(double)));
         KF_CUDA(ctx, ctx->rf.d_dense2.ensure((size_t)L.slab * sizeof(double)));
+        for (int b = 2; b < L.npipes; ++b) KF_CUDA(ctx, ctx->rf.d_dense_x[b - 2].ensure((size_t)L.slab * sizeof(double)));
         KF_TRY(kf_oz_prepare(ctx, L));
         L.valid = true;
         ctx->lay = L;
@@ -171,7 +174,7 @@ int make_layout(kf_ctx* ctx, const kf_problem* pr) {
         KF_CUDA(ctx, ctx->d_panel[b].ensure(panel_bytes));
         KF_CUDA(ctx, cudaMemsetAsync(ctx->d_panel[b].p, 0, panel_bytes, ctx->stream));   // pad rows must be finite
     }
-    if (p.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * L.n_full * L.Mc * sizeof(double)));
+    if (p.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * 2 * L.n_full * L.Mc * sizeof(double)));   // dim_red scratch, one per chunk pipeline
     // two slab sets (one per chunk pipeline) x nsplit split-K slabs; folded into slab 0 by kf_reduce_slabs
     KF_CUDA(ctx, ctx->d_accum.ensure((size_t)2 * nsplit * L.slab * sizeof(double)));
     KF_CUDA(ctx, ctx->d_tilemeta.ensure(sizeof(KfTile) * T));
@@ -268,7 +271,10 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
         }
         KF_TRY(make_layout(ctx, pr));
         const KfLayout& L = ctx->lay;
-        if (L.oz) KF_CUDA(ctx, cudaMemsetAsync(ctx->rf.d_dense2.p, 0, (size_t)L.slab * sizeof(double), ctx->stream));
+        if (L.oz) {
+            KF_CUDA(ctx, cudaMemsetAsync(ctx->rf.d_dense2.p, 0, (size_t)L.slab * sizeof(double), ctx->stream));
+            for (int b = 2; b < L.npipes; ++b) KF_CUDA(ctx, cudaMemsetAsync(ctx->rf.d_dense_x[b - 2].p, 0, (size_t)L.slab * sizeof(double), ctx->stream));
+        }
         if (L.dense) KF_CUDA(ctx, cudaMemsetAsync(ctx->rf.d_dense.p, 0, (size_t)L.slab * sizeof(double), ctx->stream));
         else KF_CUDA(ctx, cudaMemsetAsync(ctx->d_accum.p, 0, (size_t)2 * L.nsplit * L.slab * sizeof(double), ctx->stream));
         ctx->accum_M = 0;
@@ -295,7 +301,8 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
     // stream B (panel 1, slab set 1).  The pipelines are independent (own panel, own accumulator slabs), so the
     // tail wave / epilogue of one Gram launch is filled by the next chunk's CTAs and the lifts hide under DMMAs.
     const bool overlap = ctx->opt_overlap && nchunks > 1;
-    cudaStream_t S[2] = {ctx->stream, overlap ? ctx->stream2 : ctx->stream};
+    const int NP = overlap ? (L.oz ? L.npipes : 2) : 1;
+    cudaStream_t S[KF_MAX_PIPES] = {ctx->stream, overlap ? ctx->stream2 : ctx->stream, ctx->stream_x[0], ctx->stream_x[1]};
 
     if (first) {
         KF_CUDA(ctx, cudaEventRecord(ctx->ev[0], S[0]));
@@ -304,11 +311,11 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
     }
     if (overlap) {   // fork: pipeline B starts behind everything the context stream has been told to wait for
         KF_CUDA(ctx, cudaEventRecord(ctx->ev_fork, S[0]));
-        KF_CUDA(ctx, cudaStreamWaitEvent(S[1], ctx->ev_fork, 0));
+        for (int q = 1; q < NP; ++q) KF_CUDA(ctx, cudaStreamWaitEvent(S[q], ctx->ev_fork, 0));
     }
 
     for (long long c = c0; c < c1; ++c) {
-        const int b = (int)(c & 1);
+        const int b = (int)(c % NP);
         cudaStream_t sl = S[b], sg = S[b];
         KfLiftArgs a{};
         a.ops = ctx->d_ops.as<KfOp>();
@@ -320,40 +327,48 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
         a.alpha = pr->alpha; a.beta = pr->beta; a.u = pr->u;
         a.M = pr->M; a.start = c * L.Mc; a.Mc = L.Mc;
         a.panel = ctx->d_panel[b].as<double>(); a.ld = L.Mc;
-        a.full = ctx->d_full.as<double>();
+        a.full = ctx->d_full.as<double>() + (p.n_pcs ? (size_t)b * 2 * L.n_full * L.Mc : 0);   // own scratch: the pipelines lift concurrently
         a.x_off = L.x_off; a.y_off = L.y_off; a.w_off = L.w_off; a.nW = L.nW;
         KF_TRY(kf_launch_lift(ctx, a, sl));
         // CUDA-event timing of the Gram kernel on the stream it is launched on.  A sampled launch is isolated
         // from the other pipeline (which waits), so the duration is the kernel's own, not a time-shared one.
         const bool sample = ctx->opt_profile && (nchunks < 8 || (c % 61) == 3);
         if (sample) {
-            if (overlap) {
-                KF_CUDA(ctx, cudaEventRecord(ctx->ev[6], S[1 - b]));
-                KF_CUDA(ctx, cudaStreamWaitEvent(sg, ctx->ev[6], 0));
+            if (overlap) {       // isolate the sampled launch: wait for every other pipeline
+                for (int q = 0; q < NP; ++q)
+                    if (q != b) {
+                        KF_CUDA(ctx, cudaEventRecord(ctx->ev_join[q], S[q]));
+                        KF_CUDA(ctx, cudaStreamWaitEvent(sg, ctx->ev_join[q], 0));
+                    }
             }
-            KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], sg));
+            if (!L.oz) KF_CUDA(ctx, cudaEventRecord(ctx->ev[2], sg));
         }
         if (L.oz) {
-            double* acc = (b ? ctx->rf.d_dense2 : ctx->rf.d_dense).as<double>();
-            KF_TRY(kf_oz_chunk(ctx, L, b, ctx->d_panel[b].as<double>(), acc, acc + (size_t)L.Pp * L.Pp, sg));
+            double* acc = (b == 0 ? ctx->rf.d_dense : b == 1 ? ctx->rf.d_dense2 : ctx->rf.d_dense_x[b - 2]).as<double>();
+            KF_TRY(kf_oz_chunk(ctx, L, b, ctx->d_panel[b].as<double>(), acc, acc + (size_t)L.Pp * L.Pp, sg, sample ? ctx->ev[2] : nullptr,
+                               sample ? ctx->ev[8] : nullptr));
         } else if (ctx->opt_tma)
             KF_TRY(kf_launch_gram_tma(ctx, ctx->d_tma_tasks[b].as<KfTmaTask>(), ntasks, weighted, ctx->tmap[b], sg));
         else
             KF_TRY(kf_launch_gemm_tasks(ctx, ctx->d_tasks[b].as<KfGemmTask>(), ntasks, weighted, sg));
         if (sample) {
             KF_CUDA(ctx, cudaEventRecord(ctx->ev[3], sg));
-            if (overlap) KF_CUDA(ctx, cudaStreamWaitEvent(S[1 - b], ctx->ev[3], 0));
+            if (overlap)
+                for (int q = 0; q < NP; ++q)
+                    if (q != b) KF_CUDA(ctx, cudaStreamWaitEvent(S[q], ctx->ev[3], 0));
             KF_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
             float ms = 0.f;
-            KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+            KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], L.oz ? ctx->ev[8] : ctx->ev[3]));
             ctx->gram_ms_sampled += ms;
             ++ctx->gram_samples;
         }
         if (!L.oz) ctx->dmma_flops += (double)L.tiles.size() * 2.0 * KF_TILE_ELEMS * (double)L.Mc;
     }
-    if (overlap) {   // join pipeline B into the context stream
-        KF_CUDA(ctx, cudaEventRecord(ctx->ev[7], S[1]));
-        KF_CUDA(ctx, cudaStreamWaitEvent(S[0], ctx->ev[7], 0));
+    if (overlap) {   // join the other pipelines into the context stream
+        for (int q = 1; q < NP; ++q) {
+            KF_CUDA(ctx, cudaEventRecord(ctx->ev_join[q], S[q]));
+            KF_CUDA(ctx, cudaStreamWaitEvent(S[0], ctx->ev_join[q], 0));
+        }
     }
     KF_CUDA(ctx, cudaEventRecord(ctx->ev[1], S[0]));
     if (last) {
@@ -361,6 +376,7 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
         // an ESTIMATE: mean duration of the sampled (isolated) Gram launches x the number of launches
         ctx->last_gram_kernel_ms = ctx->gram_samples ? ctx->gram_ms_sampled / ctx->gram_samples * (float)nchunks : 0.f;
         ctx->last_gram_launches = nchunks;
+        ctx->last_engine = L.oz ? 2 : 1;
         ctx->last_gram_sampled = ctx->gram_samples;
     }
     return KF_OK;
@@ -370,7 +386,8 @@ int finish_accum(kf_ctx* ctx) {
     const KfLayout& L = ctx->lay;
     if (L.oz) {      // fold the second pipeline's accumulators into the first (and clear them: idempotent)
         KF_TRY(kf_oz_finish(ctx, L, ctx->rf.d_dense.as<double>(), ctx->rf.d_dense2.as<double>(), ctx->stream));
-        KF_CUDA(ctx, cudaMemsetAsync(ctx->rf.d_dense2.p, 0, (size_t)2 * L.Pp * L.Pp * sizeof(double), ctx->stream));
+        for (int b = 2; b < L.npipes; ++b)
+            KF_TRY(kf_oz_finish(ctx, L, ctx->rf.d_dense.as<double>(), ctx->rf.d_dense_x[b - 2].as<double>(), ctx->stream));
         return KF_OK;
     }
     if (L.dense) return KF_OK;
@@ -1077,8 +1094,11 @@ int kf_create(kf_ctx** out, int device) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->stream_x[0], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->stream_x[1], cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    for (int i = 0; i < 9 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    for (int i = 0; i < KF_MAX_PIPES && ok; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         g_create_err = "kf_create: stream/event creation failed";
         delete ctx;
@@ -1092,22 +1112,26 @@ void kf_destroy(kf_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_full,
+    KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_panel[2], &ctx->d_panel[3], &ctx->d_full,
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,
                      &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups,
                      &ctx->rf.d_S, &ctx->rf.d_St, &ctx->rf.d_Sp, &ctx->rf.d_G2C2, &ctx->rf.d_RP, &ctx->rf.d_Z, &ctx->rf.d_dense,
-                     &ctx->rf.d_dense2};
+                     &ctx->rf.d_dense2, &ctx->rf.d_dense_x[0], &ctx->rf.d_dense_x[1]};
     kf_oz_destroy(ctx);
     if (ctx->pchol_graph.exec) cudaGraphExecDestroy(ctx->pchol_graph.exec);
     for (KfBuf* b : bufs) b->release();
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 9; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     kf_comm_destroy(ctx);
     for (cudaEvent_t e : ctx->copy_ev) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->stream_x[i]) cudaStreamDestroy(ctx->stream_x[i]);
+    for (int i = 0; i < KF_MAX_PIPES; ++i)
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
@@ -1232,6 +1256,7 @@ int kf_sync(kf_ctx* ctx) {
     if (!ctx) return KF_EINVAL;
     KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
+    for (int i = 0; i < 2; ++i) KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream_x[i]));
     return KF_OK;
 }
 
@@ -1422,6 +1447,17 @@ int kf_counters(kf_ctx* ctx, double* dmma_flops, long long* launches, int reset)
     return KF_OK;
 }
 
+int kf_engine_info(kf_ctx* ctx, int* engine, double* i8_ops, double* i8_ops_per_launch, long long* gram_launches, int* gram_sampled, int reset) {
+    if (!ctx) return KF_EINVAL;
+    if (engine) *engine = ctx->last_engine;
+    if (i8_ops) *i8_ops = ctx->i8_ops;
+    if (i8_ops_per_launch) *i8_ops_per_launch = ctx->i8_ops_per_launch;
+    if (gram_launches) *gram_launches = ctx->last_gram_launches;
+    if (gram_sampled) *gram_sampled = ctx->last_gram_sampled;
+    if (reset) ctx->i8_ops = 0;
+    return KF_OK;
+}
+
 int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, double* solve_ms) {
     if (!ctx) return KF_EINVAL;
     if (lift_gram_ms) {
@@ -1452,6 +1488,7 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "graphs") ctx->opt_graphs = (int)value;
     else if (n == "gram_engine") ctx->opt_gram_engine = (int)value;
     else if (n == "oz_sym") ctx->opt_oz_sym = (int)value;
+    else if (n == "oz_pipes") ctx->opt_oz_pipes = (int)value;
     else if (n == "qp_split") ctx->opt_qp_split = (int)value;
     else if (n == "refine") ctx->opt_refine = (int)value;
     else if (n == "refine_kappa") ctx->opt_refine_kappa = value;

@@ -96,6 +96,7 @@ struct KfLayout {
     int nW = 0;               // weight rows (bilinear): (m+1)(m+2)/2
     int x_off = 0, y_off = 0, w_off = 0, rows = 0;   // panel row offsets / total rows
     int Mc = 0;               // snapshots per panel (multiple of KF_BK)
+    int npipes = 2;           // chunk pipelines in flight
     int nsplit = 1;           // split-K slabs
     std::vector<KfTile> tiles;
     int Pp = 0;               // P padded to BM: leading dimension of G, C, K work matrices
@@ -104,6 +105,7 @@ struct KfLayout {
     bool valid = false;
 };
 constexpr int KF_ACC_TRAILER = 16;
+constexpr int KF_MAX_PIPES = 4;     // chunk pipelines of the INT8 engine (the DMMA path uses two)
 
 // state of the Gram-route refinement (multi-level pivoted Cholesky-QR; api.cu: gram_ls_step / refine_pass)
 struct KfRefine {
@@ -121,6 +123,7 @@ struct KfRefine {
     KfBuf d_RP, d_Z;          // chunk panels: materialised [Px | Py] rows and the transformed features
     KfBuf d_dense;            // dense accumulator [G | C | trailer] (2 Pp^2 + KF_ACC_TRAILER doubles): `loaded` models, INT8 engine
     KfBuf d_dense2;           // INT8 engine: the accumulator set of the second chunk pipeline
+    KfBuf d_dense_x[2];       // ... of pipelines 2, 3
 };
 
 // the blocked pivoted Cholesky of kf_solve_gram_ls as an instantiated CUDA graph, valid for one set of buffers / sizes
@@ -141,8 +144,14 @@ struct kf_ctx {
     int opt_oz_sym = 1;       // INT8 engine: exploit the Kronecker block symmetry of a bilinear regressor
     int opt_gram_engine = 0;  // 0 auto, 1 FP64 DMMA, 2 INT8 tensor cores (Ozaki scheme II, FP64-exact)
     double i8_ops = 0;        // INT8 tensor-core operations issued
+    double i8_ops_per_launch = 0;
+    int last_engine = 1;      // engine of the last accumulate: 1 DMMA, 2 INT8
     cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t ev[8] = {};
+    cudaStream_t stream_x[2] = {nullptr, nullptr};     // pipelines 2, 3 of the INT8 engine
+    cudaEvent_t ev_join[KF_MAX_PIPES] = {};
+    int opt_oz_pipes = 2;     // INT8 engine: chunk pipelines in flight (2..4; measured: 3 and 4 give nothing over 2 — the element-wise
+                              // kernels do not run beside the persistent contraction, profiles/r02_int8_engine_summary.md)
+    cudaEvent_t ev[9] = {};
     cudaEvent_t ev_fork = nullptr;
     cudaStream_t copy_stream = nullptr;      // host -> device copies of kf_fit, overlapped with the lift + Gram
     std::vector<cudaEvent_t> copy_ev;
@@ -158,7 +167,7 @@ struct kf_ctx {
 
     std::vector<int> level_start;   // offsets into the level-sorted feature order
     KfBuf d_order;
-    KfBuf d_ops, d_centres, d_pcs, d_panel[2], d_full, d_tasks[2], d_tma_tasks[2], d_accum, d_tilemeta;
+    KfBuf d_ops, d_centres, d_pcs, d_panel[KF_MAX_PIPES], d_full, d_tasks[2], d_tma_tasks[2], d_accum, d_tilemeta;
     CUtensorMap tmap[2];            // tensor maps of the two panels (SWIZZLE_128B, box 16 x 64)
     KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3, d_Kt;
     KfBuf d_lift_groups;                 // feature groups of the materialising lift (ops | store lists | group records)
@@ -305,8 +314,9 @@ int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long lon
 // ozaki.cu: FP64-exact Gram / cross products on the INT8 tensor cores
 bool kf_oz_supported(const KfLayout& L);
 int kf_oz_prepare(kf_ctx* ctx, KfLayout& L);
-int kf_oz_chunk(kf_ctx* ctx, const KfLayout& L, int b, const double* panel, double* accG, double* accC, cudaStream_t st);
-int kf_oz_finish(kf_ctx* ctx, const KfLayout& L, double* acc0, const double* acc1, cudaStream_t st);
+int kf_oz_chunk(kf_ctx* ctx, const KfLayout& L, int b, const double* panel, double* accG, double* accC, cudaStream_t st,
+                cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+int kf_oz_finish(kf_ctx* ctx, const KfLayout& L, double* acc0, double* acc1, cudaStream_t st);
 int kf_oz_to_gc(kf_ctx* ctx, const KfLayout& L, double* acc, double* G, double* C, cudaStream_t st);
 void kf_oz_destroy(kf_ctx* ctx);
 

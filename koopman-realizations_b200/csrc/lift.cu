@@ -390,6 +390,13 @@ void kf_program_levels(const KfProgram& p, std::vector<int>& order, std::vector<
 }
 
 int kf_launch_lift(kf_ctx* ctx, const KfLiftArgs& a, cudaStream_t st) {
+    static bool carve = false;
+    if (!carve) {      // run beside the INT8 contraction of the other chunk pipeline (see kf_oz_prepare)
+        cudaFuncSetAttribute(kf_lift_level_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(kf_lift_econ_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaGetLastError();
+        carve = true;
+    }
     const int nsides = a.nsides > 0 ? a.nsides : 2;
     const unsigned gx = (unsigned)((a.Mc + LIFT_THREADS - 1) / LIFT_THREADS);
     const int nlev = (int)ctx->level_start.size() - 1;

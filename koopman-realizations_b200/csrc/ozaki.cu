@@ -7,13 +7,15 @@
 //      coprime moduli p_t <= 256 (centred, [-128, 127]); the bilinear rows u_a psi_j are formed on the fly     (oz_residue_kernel)
 //   3. T INT8 GEMMs with INT32 accumulation in TMEM:  c_t = (A_t B_t') mod p_t   (oz_gemm.cuh: tcgen05.mma kind::i8, TMA)
 //   4. CRT:  x = sum_k a_m[k] b_n[k]  EXACTLY, because |x| <= Mc 2^(2s) < prod(p_t) / 2:  x / M = frac( sum_t c_t y_t / p_t ),
-//      evaluated as three EXACT 40-bit fixed-point sums in FP64, then  G[m][n] += x 2^(e_m + e_n - 2s)              (oz_crt_kernel)
+//      evaluated as two EXACT 41-bit fixed-point sums in FP64, then  G[m][n] += x 2^(e_m + e_n - 2s)              (oz_crt_kernel)
 // Every product z_m[k] z_n[k] of the rounded operands is summed exactly; the only roundings are the 51-bit fixed-point
 // conversion of the operands (relative to the row maximum) and one FP64 rounding of the chunk's contribution — measured
 // 8e-17 relative Frobenius error against an extended-precision Gram, i.e. BELOW plain FP64 accumulation (3.8e-16).
 // 15 INT8 GEMMs replace one FP64 GEMM; at the measured 2.96 POP/s that is 3.7x the DMMA kernel's rate on the same panel.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "kf_internal.h"
@@ -24,16 +26,19 @@ namespace {
 
 constexpr int OZ_T = 15;
 constexpr int OZ_S = 51;
-const unsigned OZ_MODS[OZ_T] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197};
-__constant__ int OZ_MODS_D[OZ_T] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197};
+// pairwise coprime, <= 256.  255 is left out on purpose: for every p <= 253 the centred residue |r| <= p/2 + 1 fits an int8
+// as it is, and for p = 256 the wrap of the byte IS the reduction, so the residue kernel needs no range fix.
+const unsigned OZ_MODS[OZ_T] = {256, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193};
+__constant__ int OZ_MODS_D[OZ_T] = {256, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193};
 
 struct OzConst {
     double inv_p[OZ_T];          // 1 / p_t
     double pd[OZ_T];             // p_t
-    // CRT weights y_t / p_t (y_t = (M / p_t)^-1 mod p_t) as three 40-bit fixed-point pieces held in doubles:
-    // y_t / p_t = v1 + v2 + v3 (+ < 2^-120), v1 on the 2^-40 grid, v2 on the 2^-80 grid, v3 on the 2^-120 grid.  A residue
-    // (8 bits) times a piece and the sum of 15 such products stay below 53 bits, so the three sums are EXACT in FP64.
-    double v1[OZ_T], v2[OZ_T], v3[OZ_T];
+    // CRT weights y_t / p_t (y_t = (M / p_t)^-1 mod p_t) as two 41-bit fixed-point pieces held in doubles:
+    // y_t / p_t = v1 + v2 (+ < 2^-82), v1 on the 2^-41 grid, v2 on the 2^-82 grid.  A residue (8 bits) times a piece and the
+    // sum of 15 such products stay within 53 bits, so both sums are EXACT in FP64; the neglected tail is an absolute error of
+    // M 2^-70 ~ 2^47 in x, 14 bits BELOW the rounding floor 2^-53 sum|a||b| ~ 2^61 of an FP64 dot product of the same operands.
+    double v1[OZ_T], v2[OZ_T];
     double m_hi, m_lo;           // prod p_t as a double-double
 };
 constexpr double OZ_MAGIC = 6755399441055744.0;   // 1.5 * 2^52: (x + MAGIC) - MAGIC = rint(x) for |x| < 2^51
@@ -106,13 +111,17 @@ __global__ void __launch_bounds__(128) oz_residue_kernel(const OzResArgs a) {
             ex += a.e_u[blk];
         }
         const double sc = ldexp(1.0, OZ_S - ex);
+        int xl[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) f[q] = rint(f[q] * sc);   // exact integers, |f| <= 2^51
+        for (int q = 0; q < 16; ++q) {
+            f[q] = rint(f[q] * sc);                               // exact integer, |f| <= 2^51
+            xl[q] = __double2loint(f[q] + OZ_MAGIC);              // its low 32 bits (f + MAGIC is exact: both integers, sum < 2^53)
+        }
         const size_t plane = (size_t)a.rows * a.Mc;
         int8_t* dst = a.out + (size_t)row * a.Mc + k0;
 #pragma unroll 1
         for (int t = 0; t < OZ_T; ++t) {
-            const double ip = a.c.inv_p[t], pd = a.c.pd[t];
+            const double ip = a.c.inv_p[t];
             const int pi = OZ_MODS_D[t];
             uint32_t w[4];
 #pragma unroll
@@ -120,11 +129,12 @@ __global__ void __launch_bounds__(128) oz_residue_kernel(const OzResArgs a) {
                 uint32_t pk = 0;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const double x = f[g * 4 + e];
-                    const double q = fma(x, ip, OZ_MAGIC) - OZ_MAGIC;          // rint(x / p) up to +-1 (|x / p| < 2^44)
-                    int r = __double2loint(fma(-q, pd, x) + OZ_MAGIC);          // exact: x - q p, |r| <= p/2 + 1, as an int
-                    r = r > 127 ? r - pi : (r < -128 ? r + pi : r);
-                    pk |= ((uint32_t)r & 0xFFu) << (8 * e);
+                    // q = rint(x / p) up to +-1, read as an integer from the low mantissa bits of x / p + MAGIC; the residue
+                    // r = x - q p is small (|r| <= p/2 + 1), so its low 32 bits follow from the low 32 bits of x and q:
+                    // ONE FP64 instruction and one integer multiply-add per (element, modulus)
+                    const int ql = __double2loint(fma(f[g * 4 + e], ip, OZ_MAGIC));
+                    const int r = xl[g * 4 + e] - ql * pi;
+                    pk |= ((uint32_t)r & 0xFFu) << (8 * e);         // p <= 253: r in [-127, 127]; p = 256: the byte wrap is the reduction
                 }
                 w[g] = pk;
             }
@@ -152,7 +162,7 @@ struct OzCrtArgs {
 };
 
 // grid: (column groups of 1024, rows, 2 planes); thread = 4 consecutive n of one row m.
-// x / M = frac(sum_t c_t y_t / p_t): the three fixed-point sums are exact, the fraction is centred (|x| < M / 4 by construction),
+// x / M = frac(sum_t c_t y_t / p_t): the two fixed-point sums are exact, the fraction is centred (|x| < M / 4 by construction),
 // and x = M f carries ~2 ulp relative to |x| ITSELF (small entries — nearly orthogonal rows — keep their relative accuracy).
 __global__ void __launch_bounds__(256) oz_crt_kernel(const OzCrtArgs a) {
     const int m = blockIdx.y;
@@ -165,17 +175,16 @@ __global__ void __launch_bounds__(256) oz_crt_kernel(const OzCrtArgs a) {
         if (isC ? (a.symC && ba > bb) : (c0 > r)) return;
     }
     const uint8_t* src = a.res + (isC ? a.c_off : 0ull) + (size_t)m * a.LD + n0;
-    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, s3[4] = {0, 0, 0, 0};
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int t = 0; t < OZ_T; ++t) {
         const uint32_t pk = *reinterpret_cast<const uint32_t*>(src + (size_t)t * a.plane);
-        const double v1 = a.c.v1[t], v2 = a.c.v2[t], v3 = a.c.v3[t];
+        const double v1 = a.c.v1[t], v2 = a.c.v2[t];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const double c = __hiloint2double(0x43300000, (int)((pk >> (8 * e)) & 0xFFu)) - 4503599627370496.0;   // byte -> double, exact
             s1[e] = fma(c, v1, s1[e]);
             s2[e] = fma(c, v2, s2[e]);
-            s3[e] = fma(c, v3, s3[e]);
         }
     }
     const int em = a.e_fx[m % a.nfx] + a.e_u[m / a.nfx];
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(256) oz_crt_kernel(const OzCrtArgs a) {
         if (n < ncols && (isC || n <= m) && (!a.symN || isC || (n % a.symN) <= (m % a.symN))) {   // computed entries only
             const int en = isC ? (a.e_fy[n % a.nfy] + a.e_u[n / a.nfy]) : (a.e_fx[n % a.nfx] + a.e_u[n / a.nfx]);
             const double f1 = s1[e] - ((s1[e] + OZ_MAGIC) - OZ_MAGIC);       // centred fraction of the leading sum (exact)
-            const double f = f1 + (s2[e] + s3[e]);
+            const double f = f1 + s2[e];
             x = ldexp(fma(f, a.c.m_hi, f * a.c.m_lo), em + en - 2 * OZ_S);
         }
         v[e] = x;
@@ -254,12 +263,11 @@ OzConst make_consts() {
             if (s != t) mp = (unsigned)(((unsigned long long)mp * (OZ_MODS[s] % p)) % p);
         unsigned y = 1;
         while ((unsigned long long)mp * y % p != 1) ++y;      // inverse by search (p <= 256)
-        // y / p to 120 fraction bits, cut into three 40-bit pieces
-        const unsigned __int128 Nf = ((unsigned __int128)y << 120) / p;
-        const unsigned long long mask = (1ull << 40) - 1;
-        c.v1[t] = std::ldexp((double)(unsigned long long)(Nf >> 80), -40);
-        c.v2[t] = std::ldexp((double)((unsigned long long)(Nf >> 40) & mask), -80);
-        c.v3[t] = std::ldexp((double)((unsigned long long)Nf & mask), -120);
+        // y / p to 82 fraction bits, cut into two 41-bit pieces
+        const unsigned __int128 Nf = ((unsigned __int128)y << 82) / p;
+        const unsigned long long mask = (1ull << 41) - 1;
+        c.v1[t] = std::ldexp((double)(unsigned long long)(Nf >> 41), -41);
+        c.v2[t] = std::ldexp((double)((unsigned long long)Nf & mask), -82);
     }
     c.m_hi = (double)M;
     const unsigned __int128 mh = (unsigned __int128)c.m_hi;
@@ -276,8 +284,8 @@ struct KfOzState {
     int symN = 0;             // Kronecker block symmetry in use (bilinear, N a multiple of 256)
     bool symC = false;        // ... for the cross product too (all of Py wanted)
     unsigned long long plane = 0, c_off = 0;
-    KfBuf d_rx[2], d_ry[2], d_res[2], d_exp[2], d_rowlist, d_tasks;
-    CUtensorMap mxa[2], mxb[2], myb[2];
+    KfBuf d_rx[KF_MAX_PIPES], d_ry[KF_MAX_PIPES], d_res[KF_MAX_PIPES], d_exp[KF_MAX_PIPES], d_rowlist, d_tasks;
+    CUtensorMap mxa[KF_MAX_PIPES], mxb[KF_MAX_PIPES], myb[KF_MAX_PIPES];
     oz::Params prm{};
     int ntasks = 0;
     int nrowlist = 0;
@@ -285,7 +293,7 @@ struct KfOzState {
 };
 
 static void oz_release(KfOzState* s) {
-    for (int b = 0; b < 2; ++b) { s->d_rx[b].release(); s->d_ry[b].release(); s->d_res[b].release(); s->d_exp[b].release(); }
+    for (int b = 0; b < KF_MAX_PIPES; ++b) { s->d_rx[b].release(); s->d_ry[b].release(); s->d_res[b].release(); s->d_exp[b].release(); }
     s->d_rowlist.release();
     s->d_tasks.release();
 }
@@ -349,7 +357,7 @@ int kf_oz_prepare(kf_ctx* ctx, KfLayout& L) {
     S.ntasks = (int)tasks.size();
     KF_CUDA(ctx, S.d_tasks.ensure(tasks.size() * sizeof(oz::Task)));
     KF_CUDA(ctx, cudaMemcpyAsync(S.d_tasks.p, tasks.data(), tasks.size() * sizeof(oz::Task), cudaMemcpyHostToDevice, ctx->stream));
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < L.npipes; ++b) {
         KF_CUDA(ctx, S.d_rx[b].ensure((size_t)OZ_T * S.xrows * S.Mc));
         KF_CUDA(ctx, S.d_ry[b].ensure((size_t)OZ_T * S.yrows * S.Mc));
         KF_CUDA(ctx, S.d_res[b].ensure((size_t)OZ_T * S.plane));
@@ -378,14 +386,49 @@ int kf_oz_prepare(kf_ctx* ctx, KfLayout& L) {
         p.offset[t] = (int)(((1u << 27) + OZ_MODS[t] - 1) / OZ_MODS[t] * OZ_MODS[t]);
     }
     KF_CUDA(ctx, kf_ensure_smem(ctx, oz::oz_gemm_kernel, oz::SMEM_BYTES));
+    // the element-wise kernels of one chunk pipeline should run BESIDE the other pipeline's contraction (which holds 197 KB of
+    // shared memory per SM): ask for the same shared-memory carveout so that no SM has to be reconfigured between them
+    cudaFuncSetAttribute(oz_rowmax_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(oz_residue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(oz_crt_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
     S.ready = true;
     return KF_OK;
 }
 
 // One chunk: the lifted panel of pipeline b (already written by the lift on stream st) -> exponents -> residues -> INT8 GEMMs
 // -> CRT accumulate into this pipeline's dense accumulator set (accG, accC row-major, Pp x Pp each).
-int kf_oz_chunk(kf_ctx* ctx, const KfLayout& L, int b, const double* panel, double* accG, double* accC, cudaStream_t st) {
+// KF_OZ_TRACE=1: CUDA-event timeline of the first chunks (which kernels of the two pipelines overlap) printed by kf_oz_finish
+static std::vector<cudaEvent_t> g_tr_ev;
+static std::vector<int> g_tr_tag;
+static int g_tr_on = -1;
+static void tr_mark(int tag, cudaStream_t st) {
+    if (g_tr_on < 0) g_tr_on = getenv("KF_OZ_TRACE") ? 1 : 0;
+    if (!g_tr_on || g_tr_ev.size() > 400) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_tr_ev.push_back(e);
+    g_tr_tag.push_back(tag);
+}
+static void tr_dump() {
+    if (g_tr_on != 1 || g_tr_ev.empty()) return;
+    cudaDeviceSynchronize();
+    for (size_t i = 0; i < g_tr_ev.size(); ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g_tr_ev[0], g_tr_ev[i]);
+        printf("TRACE pipe %d stage %d t=%.3f ms\n", g_tr_tag[i] / 10, g_tr_tag[i] % 10, ms);
+    }
+    for (cudaEvent_t e : g_tr_ev) cudaEventDestroy(e);
+    g_tr_ev.clear();
+    g_tr_tag.clear();
+    g_tr_on = 0;
+}
+
+int kf_oz_chunk(kf_ctx* ctx, const KfLayout& L, int b, const double* panel, double* accG, double* accC, cudaStream_t st, cudaEvent_t ev0,
+                cudaEvent_t ev1) {
     KfOzState& S = *ctx->oz;
+    tr_mark(b * 10 + 0, st);
     int* e_all = S.d_exp[b].as<int>();
     // exponent table layout: [e_u (8 ints: index 0 stays 0)] [X features] [Y features]
     int* e_u = e_all;
@@ -403,13 +446,18 @@ int kf_oz_chunk(kf_ctx* ctx, const KfLayout& L, int b, const double* panel, doub
     ra.e_u = e_u;
     ra.c = S.c;
     const dim3 gx((L.Mc / 16 + 127) / 128, S.nfx), gy((L.Mc / 16 + 127) / 128, S.nfy);
+    tr_mark(b * 10 + 1, st);
     ra.psi = panel + (long long)L.x_off * L.Mc; ra.nfeat = S.nfx; ra.rows = S.xrows; ra.e_feat = e_fx; ra.out = S.d_rx[b].as<int8_t>();
     oz_residue_kernel<<<gx, 128, 0, st>>>(ra);
     ra.psi = panel + (long long)L.y_off * L.Mc; ra.nfeat = S.nfy; ra.rows = S.yrows; ra.e_feat = e_fy; ra.out = S.d_ry[b].as<int8_t>();
     oz_residue_kernel<<<gy, 128, 0, st>>>(ra);
     oz::Params p = S.prm;
     p.out = S.d_res[b].as<uint8_t>();
+    tr_mark(b * 10 + 2, st);
+    if (ev0) KF_CUDA(ctx, cudaEventRecord(ev0, st));       // sampled launches: CUDA events tightly around the INT8 contraction
     oz::oz_gemm_kernel<<<std::min(ctx->sm_count, S.ntasks), oz::THREADS, oz::SMEM_BYTES, st>>>(S.mxa[b], S.mxb[b], S.myb[b], p);
+    if (ev1) KF_CUDA(ctx, cudaEventRecord(ev1, st));
+    tr_mark(b * 10 + 3, st);
     OzCrtArgs ca{};
     ca.res = S.d_res[b].as<uint8_t>();
     ca.plane = S.plane;
@@ -422,17 +470,21 @@ int kf_oz_chunk(kf_ctx* ctx, const KfLayout& L, int b, const double* panel, doub
     ca.symC = S.symC ? 1 : 0;
     ca.c = S.c;
     oz_crt_kernel<<<dim3((S.LD / 4 + 255) / 256, S.xrows, 2), 256, 0, st>>>(ca);
+    tr_mark(b * 10 + 4, st);
     KF_CUDA(ctx, cudaGetLastError());
     ctx->launches += 5 + (S.nblk > 1 ? 1 : 0);
     ctx->i8_ops += 2.0 * oz::BM * oz::BN * (double)L.Mc * S.ntasks;
+    ctx->i8_ops_per_launch = 2.0 * oz::BM * oz::BN * (double)L.Mc * S.ntasks;
     return KF_OK;
 }
 
 // acc[0] += acc[1] (the two chunk pipelines), then the row-major accumulators become the column-major G (symmetric) and C
-int kf_oz_finish(kf_ctx* ctx, const KfLayout& L, double* acc0, const double* acc1, cudaStream_t st) {
+int kf_oz_finish(kf_ctx* ctx, const KfLayout& L, double* acc0, double* acc1, cudaStream_t st) {
+    tr_dump();
     const long long n = 2LL * L.Pp * L.Pp;
     oz_add_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(acc0, acc1, n);
     KF_CUDA(ctx, cudaGetLastError());
+    KF_CUDA(ctx, cudaMemsetAsync(acc1, 0, (size_t)n * sizeof(double), st));      // folded: a second call adds zeros (idempotent)
     ctx->launches += 1;
     return KF_OK;
 }

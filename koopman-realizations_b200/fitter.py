@@ -67,6 +67,13 @@ class Fitter:
         self._check(self.lib.kf_counters(self.ctx, C.byref(f), C.byref(n), int(reset)), "kf_counters")
         return f.value, n.value
 
+    def engine_info(self, reset=False):
+        """Gram engine of the last accumulation (1 FP64 DMMA, 2 INT8 tensor cores) and its INT8 operation counters."""
+        e, n, s_ = C.c_int(), C.c_longlong(), C.c_int()
+        ops, per = C.c_double(), C.c_double()
+        self._check(self.lib.kf_engine_info(self.ctx, C.byref(e), C.byref(ops), C.byref(per), C.byref(n), C.byref(s_), int(reset)), "kf_engine_info")
+        return {"engine": e.value, "i8_ops": ops.value, "i8_ops_per_launch": per.value, "gram_launches": n.value, "gram_sampled": s_.value}
+
     def last_times(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._check(self.lib.kf_last_times(self.ctx, C.byref(a), C.byref(b), C.byref(c)), "kf_last_times")

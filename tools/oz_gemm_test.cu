@@ -32,6 +32,12 @@ static CUtensorMap make_map(void* base, unsigned long long K, unsigned long long
     return m;
 }
 
+__global__ void busy_kernel(double* out, int iters) {
+    double x = threadIdx.x * 1e-3, y = 1.0000001;
+    for (int i = 0; i < iters; ++i) x = fma(x, y, 1e-9);
+    if (x == 123.456) out[0] = x;
+}
+
 int main(int argc, char** argv) {
     int RX = argc > 1 ? atoi(argv[1]) : 512, RY = argc > 2 ? atoi(argv[2]) : 512, K = argc > 3 ? atoi(argv[3]) : 1024, T = argc > 4 ? atoi(argv[4]) : 3;
     const unsigned mods[16] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193};
@@ -117,5 +123,31 @@ int main(int argc, char** argv) {
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
     const double ops = 2.0 * 128 * 256 * (double)K * tasks.size();
     printf("RX=%d RY=%d K=%d T=%d: %.3f ms per launch, %.1f TOP/s (tile ops issued)\n", RX, RY, K, T, ms, ops / ms / 1e9);
+    // co-residency experiment: does an element-wise kernel on another stream run BESIDE the persistent contraction?
+    {
+        cudaStream_t sa, sb;
+        cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
+        double* dd; CK(cudaMalloc(&dd, 8));
+        const int iters = argc > 5 ? atoi(argv[5]) : 20000;
+        const int bgrid = argc > 6 ? atoi(argv[6]) : 148 * 4;
+        cudaEvent_t a0, a1, b0, b1, t0, t1;
+        cudaEventCreate(&a0); cudaEventCreate(&a1); cudaEventCreate(&b0); cudaEventCreate(&b1); cudaEventCreate(&t0); cudaEventCreate(&t1);
+        busy_kernel<<<bgrid, 256, 0, sb>>>(dd, iters);
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(b0, sb); busy_kernel<<<bgrid, 256, 0, sb>>>(dd, iters); cudaEventRecord(b1, sb);
+        CK(cudaDeviceSynchronize());
+        float tb = 0; cudaEventElapsedTime(&tb, b0, b1);
+        cudaEventRecord(t0, sa);
+        cudaStreamWaitEvent(sb, t0, 0);
+        cudaEventRecord(a0, sa); oz::oz_gemm_kernel<<<grid, oz::THREADS, oz::SMEM_BYTES, sa>>>(mxa, mxb, myb, prm); cudaEventRecord(a1, sa);
+        cudaEventRecord(b0, sb); busy_kernel<<<bgrid, 256, 0, sb>>>(dd, iters); cudaEventRecord(b1, sb);
+        cudaStreamWaitEvent(sa, b1, 0);
+        cudaEventRecord(t1, sa);
+        CK(cudaDeviceSynchronize());
+        float ta = 0, tb2 = 0, tt = 0;
+        cudaEventElapsedTime(&ta, a0, a1); cudaEventElapsedTime(&tb2, b0, b1); cudaEventElapsedTime(&tt, t0, t1);
+        printf("co-run: gemm alone %.3f ms, busy alone %.3f ms | together: gemm %.3f, busy %.3f, total %.3f ms (sum of alone %.3f)\n", ms, tb, ta, tb2, tt, ms + tb);
+    }
     return 0;
 }
