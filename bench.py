@@ -503,16 +503,19 @@ def main():
             launches_per_step = max(eng["gram_launches"], 1)
             k_ms = gk / launches_per_step
             ach = eng["i8_ops_per_launch"] / (k_ms * 1e-3) / 1e12
-            bf16 = float(peaks.get("bf16_tflops", 1654.5))
+            bf16 = float(peaks.get("bf16_tflops_sustained", 1377.3))
+            bf16_burst = float(peaks.get("bf16_tflops", 1654.5))
             peak_i8 = 2.0 * bf16
             traffic, traffic_src = gram_traffic_from_profile("oz_gemm")
             roof = {"bound": "tensor", "kernel": "oz::oz_gemm_kernel (tcgen05.mma kind::i8, INT32 accumulators in TMEM, TMA operands; "
                                                    "15 residue GEMMs per panel = one FP64-exact Gram / cross product, Ozaki scheme II)",
                     "achieved": ach, "peak": peak_i8, "unit": "TFLOP/s", "frac": ach / peak_i8,
                     "unit_note": "INT8 tensor operations (TOP/s); 2 ops per multiply-accumulate",
-                    "peak_source": f"2 x MEASURED_PEAKS.json bf16_tflops ({bf16}, burst: cuBLAS bf16 8192^3 timed alone) - the INT8 rate of the "
-                                   "tcgen05 tensor cores is twice the bf16 rate; nominal INT8 dense peak 4500",
-                    "frac_of_nominal_4500": ach / 4500.0,
+                    "peak_source": f"2 x MEASURED_PEAKS.json bf16_tflops_sustained ({bf16}: cuBLAS bf16 8192^3 back to back for 4 s) - the INT8 rate "
+                                   "of the tcgen05 tensor cores is twice the bf16 rate, and the sampled launches sit INSIDE a long step that runs "
+                                   "at the 1 kW power cap (see clocks: sw_power_cap, SM clock well below max), so the sustained figure applies; "
+                                   "nominal INT8 dense peak 4500",
+                    "frac_of_2x_bf16_burst": ach / (2.0 * bf16_burst), "frac_of_nominal_4500": ach / 4500.0,
                     "traffic": traffic, "traffic_unit": "bytes per launch (one 4096-snapshot panel, all 15 moduli)",
                     "traffic_source": f"NOT measured in this run: {traffic_src}" if traffic_src else None,
                     "kernel_ms_per_launch": k_ms, "launches_per_step": launches_per_step, "sampled_launches_per_step": eng["gram_sampled"],
