@@ -28,6 +28,7 @@ int prepare_program(kf_ctx* ctx, const kf_basis* basis) {
         return rc;
     }
     const KfProgram& p = ctx->prog;
+    ctx->prog_gen += 1;
     KF_CUDA(ctx, ctx->d_ops.ensure(sizeof(KfOp) * p.ops.size()));
     KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ops.p, p.ops.data(), sizeof(KfOp) * p.ops.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!p.centres.empty()) {
@@ -329,7 +330,11 @@ int accumulate_dev(kf_ctx* ctx, const kf_problem* pr, bool reset, long long c0 =
         a.panel = ctx->d_panel[b].as<double>(); a.ld = L.Mc;
         a.full = ctx->d_full.as<double>() + (p.n_pcs ? (size_t)b * 2 * L.n_full * L.Mc : 0);   // own scratch: the pipelines lift concurrently
         a.x_off = L.x_off; a.y_off = L.y_off; a.w_off = L.w_off; a.nW = L.nW;
-        KF_TRY(kf_launch_lift(ctx, a, sl));
+        {
+            int lrc = KF_OK;
+            if (!(ctx->opt_lift_panel_fit && kf_launch_lift_panel_tile(ctx, a, sl, &lrc))) KF_TRY(kf_launch_lift(ctx, a, sl));
+            else if (lrc) return lrc;
+        }
         // CUDA-event timing of the Gram kernel on the stream it is launched on.  A sampled launch is isolated
         // from the other pipeline (which waits), so the duration is the kernel's own, not a time-shared one.
         const bool sample = ctx->opt_profile && (nchunks < 8 || (c % 61) == 3);
@@ -1485,6 +1490,10 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "as_frac") ctx->opt_as_frac = value;
     else if (n == "lift_tile") ctx->opt_lift_tile = (int)value;
     else if (n == "lift_ls") ctx->opt_lift_ls = (int)value;
+    else if (n == "lift_wide") ctx->opt_lift_wide = (int)value;
+    else if (n == "lift_smem_kb") ctx->opt_lift_smem_kb = value;
+    else if (n == "lift_minb") ctx->opt_lift_minb = (int)value;
+    else if (n == "lift_panel_fit") ctx->opt_lift_panel_fit = (int)value;
     else if (n == "graphs") ctx->opt_graphs = (int)value;
     else if (n == "gram_engine") ctx->opt_gram_engine = (int)value;
     else if (n == "oz_sym") ctx->opt_oz_sym = (int)value;

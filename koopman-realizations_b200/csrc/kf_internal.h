@@ -170,6 +170,10 @@ struct kf_ctx {
     KfBuf d_ops, d_centres, d_pcs, d_panel[KF_MAX_PIPES], d_full, d_tasks[2], d_tma_tasks[2], d_accum, d_tilemeta;
     CUtensorMap tmap[2];            // tensor maps of the two panels (SWIZZLE_128B, box 16 x 64)
     KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3, d_Kt;
+    int opt_lift_panel_fit = 0;          // fit path: lift the panel with the shared-memory tile evaluator instead of the level kernel
+    int opt_lift_wide = 1;               // materialising lift: wide tiles (32 / 64 snapshots: long DRAM runs, table-free stores)
+    int opt_lift_minb = 2;               // ... resident CTAs per SM the kernel is compiled for (2: 128 registers, 3: 80)
+    double opt_lift_smem_kb = 64;        // ... shared memory per CTA (decides the size of the feature groups and the CTAs per SM)
     KfBuf d_lift_groups;                 // feature groups of the materialising lift (ops | store lists | group records)
     KfBuf d_series;                      // raw merged series t | y | u and the scale factors (kf_fit_series)
     KfBuf d_as_mat, d_as_aux, d_as_ws;   // active-set QP solver: pattern/solution matrices, index lists, Cholesky factors
@@ -199,6 +203,11 @@ struct kf_ctx {
     std::vector<LtOp> lt_ops;
     std::vector<LtStore> lt_store;
     std::vector<LtGroup> lt_groups;
+    // the uploaded group tables are reused while (program, tile width, group size) stay the same: the panel pipeline launches
+    // the tile evaluator once per chunk and must not pay a host synchronisation each time
+    unsigned long long prog_gen = 0;     // bumped by every prepare_program
+    unsigned long long lt_key[4] = {~0ull, 0, 0, 0};
+    int lt_max[3] = {0, 0, 0};           // max_slots, max_ops, max_nst of the cached groups
 
     // column partition of the active-set QP solver across ranks (kf_set_qp_partition)
     int qp_lo = 0, qp_hi = 0;
@@ -284,6 +293,8 @@ struct KfLiftArgs {
 };
 void kf_program_levels(const KfProgram& p, std::vector<int>& order, std::vector<int>& level_start);
 int kf_launch_lift(kf_ctx* ctx, const KfLiftArgs& a, cudaStream_t st);
+// the panel lift through the shared-memory tile evaluator; false: not applicable (use kf_launch_lift)
+bool kf_launch_lift_panel_tile(kf_ctx* ctx, const KfLiftArgs& a, cudaStream_t st, int* rc, long long limit = -1);
 // materialised lift of arbitrary points: V (rows x nv, ld=rows) -> Psi (rows x N, ld = ldo)
 int kf_launch_lift_points(kf_ctx* ctx, const KfOp* ops, const double* centres, const double* pcs, int nv, int n_full,
                           int n_pcs, const double* V, long long rows, double* full, double* out, long long ldo,

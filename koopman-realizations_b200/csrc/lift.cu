@@ -144,6 +144,7 @@ struct KfLiftTileArgs {
     int nzeta, m, model;
     int mode;                           // 0: points V -> Psi (rows x N);  1: regressors [Px | Py] (M x 2P)
     int P;
+    int side_off;                       // mode 0 with two sides (panel mode): psi(beta) goes to rows side_off .. of `out`
     int max_slots, max_ops, max_nst;
     const double* alpha; const double* beta; const double* u; long long M;   // M = points of this launch
     const double* w; int nw;            // loads of a `loaded` model (mode 1): blocks w_c psi, Ksysid.m:594-599
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
                 }
             };
             if (ok0) {
-                double* base = a.out + (a.mode == 0 ? 0 : (long long)(side ? a.P : 0) * a.ld) + gs;
+                double* base = a.out + (long long)(side ? (a.mode == 0 ? a.side_off : a.P) : 0) * a.ld + gs;
                 const bool direct = a.n_pcs > 0 || a.ngroups == 1;       // slot = output row = feature index
                 const int nrow = direct ? a.N : grp.nst;
                 const double* psi = a.n_pcs > 0 ? se : sh;
@@ -293,6 +294,219 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming variant (the default for n_pcs == 0).  Measured on this pool's B200 (tools/store_pattern_bench.cu,
+// profiles/r02_store_pattern_microbench.txt; profiles/r02_lift_stream_ncu_summary.txt):
+//  (1) what the DRAM sees decides the write rate, not the store mechanism: a pure store kernel with this access pattern
+//      (feature-major rows, one tile of LS snapshots at a time) writes 3.7-4.2 TB/s with 128-byte runs, 4.6 / 5.9 TB/s with
+//      256-byte runs on unaligned / 128-byte-aligned rows, 5.0 / 5.9 TB/s with 512-byte runs — st.global and TMA tensor stores
+//      (UTMASTG) give the same figures;
+//  (2) kf_lift_tile_kernel spends its issue slots, not bandwidth: ncu's source view put 60 % of its 1.0e9 warp instructions
+//      into the table-driven store loop and 30 % into per-element gaussian evaluation, 1.6 IPC, 25 % of the warps resident.
+// Hence: tiles of 32 (aligned rows) or 64 snapshots; only the features that other features READ (for a monomial dictionary
+// of degree d: the degrees < d) are held in shared memory; every output row is produced by ONE row op in registers — a product
+// of two slots, a gaussian of the variables, a copy of a slot — applied to 4 snapshots per thread and stored straight to
+// global memory as complete half runs, together with its bilinear blocks u_k psi (u_k in registers).  Leaves never touch shared
+// memory, the store phase has no table lookup, no barrier and ~10 instructions per lifted element, and since the slots are
+// few a whole dictionary usually is ONE group: the inputs of a tile are read once and nothing is evaluated twice.  The next
+// tile's inputs are fetched into registers before the row phase, so their latency hides under the stores.
+constexpr int LW_PRE = 8;          // prefetch registers per thread (inputs of the next tile)
+
+// a thread's 4 snapshots of a row: the pairs 2t, 2t+1 and LS/2 + 2t, LS/2 + 2t + 1 — every 128-bit access of LS/4 consecutive
+// threads covers a contiguous half run (128 B at LS = 32, 256 B at LS = 64)
+template <int LS> __device__ __forceinline__ void lq_ld(const double* row, int t2, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(row + t2), b = *reinterpret_cast<const double2*>(row + LS / 2 + t2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <int LS> __device__ __forceinline__ void lq_st(double* row, int t2, const double (&v)[4]) {
+    *reinterpret_cast<double2*>(row + t2) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(row + LS / 2 + t2) = make_double2(v[2], v[3]);
+}
+
+// one op on a snapshot quad; operands are shared-memory slots (GAUSS: the variables, slots 0 .. nv-1)
+template <int LS>
+__device__ __forceinline__ void lq_eval(const LtOp& op, const double* sh, int t2, int nv, const double* __restrict__ centres, double (&v)[4]) {
+    if (op.kind == KF_OP_MUL) {
+        double x[4], y[4];
+        lq_ld<LS>(sh + op.a * LS, t2, x);
+        lq_ld<LS>(sh + op.b * LS, t2, y);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] = KF_MUL(x[t], y[t]);
+    } else if (op.kind == KF_OP_GAUSS) {                 // exp(-||v - c||^2): the operation order of kf_eval_op, the centre read once per quad
+        const double* __restrict__ c = centres + (size_t)op.a * nv;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < nv; ++i) {
+            const double ci = __ldg(c + i);
+            double x[4];
+            lq_ld<LS>(sh + i * LS, t2, x);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const double d = KF_SUB(x[t], ci);
+                acc[t] = KF_ADD(acc[t], KF_MUL(d, d));
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] = exp(-acc[t]);
+    } else if (op.kind == KF_OP_VAR) {
+        lq_ld<LS>(sh + op.a * LS, t2, v);
+    } else {
+        KfOp o{};
+        o.kind = op.kind; o.a = op.a; o.b = op.b; o.c = op.c;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const double* col = sh + (t < 2 ? t2 + t : LS / 2 + t2 + t - 2);
+            v[t] = kf_eval_op(o, nv, centres, [&](int k) -> double { return col[k * LS]; });
+        }
+    }
+}
+
+template <int LS, int MINB>
+__global__ void __launch_bounds__(LT_THREADS, MINB) kf_lift_stream_kernel(const KfLiftTileArgs a) {
+    extern __shared__ __align__(16) double lt_smem[];
+    double* sh = lt_smem;                              // [max_slots][LS]; slots 0 .. nv-1 are the variables
+    double* su = sh + (size_t)a.max_slots * LS;        // [m + nw][LS]   inputs u, then loads w, of the tile
+    LtOp* sop = reinterpret_cast<LtOp*>(su + (size_t)(a.m + a.nw) * LS);   // [nops slot ops | nst row ops]
+    const double** inrow = reinterpret_cast<const double**>(sop + a.max_ops);   // [nv + m + nw] first element of every input row
+    __shared__ LtGroup grp;
+    const int tid = threadIdx.x;
+    const int side = blockIdx.y / a.ngroups, g = blockIdx.y % a.ngroups;
+    const long long ntiles = (a.M + LS - 1) / LS;
+    const int nrows_in = a.nv + a.m + a.nw;
+    if (tid == 0) grp = a.groups[g];
+    for (int k = tid; k < nrows_in; k += LT_THREADS) {
+        const double* r;
+        if (k < a.nv) r = k < a.nzeta ? (side ? a.beta : a.alpha) + (long long)k * a.ldin : a.u + (long long)(k - a.nzeta) * a.ldin;
+        else if (k < a.nv + a.m) r = a.u + (long long)(k - a.nv) * a.ldin;
+        else r = a.w + (long long)(k - a.nv - a.m) * a.ldin;
+        inrow[k] = r;
+    }
+    __syncthreads();
+    for (int e = tid; e < grp.nops + grp.nst; e += LT_THREADS) sop[e] = a.gops[grp.op_off + e];
+    // inputs: value (row k = tid / LS + i * (LT_THREADS / LS), snapshot tid % LS) of a tile goes to register i
+    constexpr int KSTEP = LT_THREADS / LS;
+    const int sn = tid & (LS - 1), k0 = tid / LS;
+    const bool use_pre = nrows_in <= LW_PRE * KSTEP;
+    auto fetch = [&](long long g0, int k) -> double {
+        const long long gs = g0 + sn;
+        return (k < nrows_in && gs < a.M) ? inrow[k][gs] : 0.0;     // the tail of the last tile is zero
+    };
+    auto place = [&](int k, double v) {
+        if (k < nrows_in) (k < a.nv ? sh + k * LS : su + (k - a.nv) * LS)[sn] = v;
+    };
+    double pre[LW_PRE];
+    if (use_pre) {
+#pragma unroll
+        for (int i = 0; i < LW_PRE; ++i) pre[i] = fetch((long long)blockIdx.x * LS, k0 + i * KSTEP);
+    }
+    constexpr int QS = LS / 4, NF = LT_THREADS / QS;   // threads per row, rows in flight per CTA
+    const int t2 = (tid % QS) * 2, fs = tid / QS;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long g0 = tile * LS;
+        // ---- A: inputs of the tile into shared memory
+        if (use_pre) {
+#pragma unroll
+            for (int i = 0; i < LW_PRE; ++i) place(k0 + i * KSTEP, pre[i]);
+        } else {
+            for (int k = k0; k < nrows_in; k += KSTEP) place(k, fetch(g0, k));
+        }
+        __syncthreads();
+        // ---- B: the features other features read, level by level, into their slots
+        for (int l = 0; l < grp.nlevels; ++l) {
+            const int first = grp.level_start[l], last = grp.level_start[l + 1];
+            for (int e = first + fs; e < last; e += NF) {
+                const LtOp op = sop[e];
+                double v[4];
+                lq_eval<LS>(op, sh, t2, a.nv, a.centres, v);
+                lq_st<LS>(sh + op.j * LS, t2, v);
+            }
+            if (last > first) __syncthreads();
+        }
+        // inputs of this CTA's next tile: in flight during the row phase
+        if (use_pre && tile + gridDim.x < ntiles) {
+#pragma unroll
+            for (int i = 0; i < LW_PRE; ++i) pre[i] = fetch((tile + gridDim.x) * LS, k0 + i * KSTEP);
+        }
+        // ---- C: one row op per output row, evaluated in registers and stored with its blocks u_ka (w_kc psi)
+        {
+            const long long gA = g0 + t2, gB = gA + LS / 2;
+            const bool full = g0 + LS <= a.M;
+            const bool okA0 = gA < a.M, okA1 = gA + 1 < a.M, okB0 = gB < a.M, okB1 = gB + 1 < a.M;
+            auto put = [&](double* dst, const double (&x)[4]) {      // dst: the row's element of snapshot gA (16-byte aligned: launcher)
+                if (full) {
+                    *reinterpret_cast<double2*>(dst) = make_double2(x[0], x[1]);
+                    *reinterpret_cast<double2*>(dst + LS / 2) = make_double2(x[2], x[3]);
+                } else {
+                    if (okA1) *reinterpret_cast<double2*>(dst) = make_double2(x[0], x[1]); else if (okA0) dst[0] = x[0];
+                    if (okB1) *reinterpret_cast<double2*>(dst + LS / 2) = make_double2(x[2], x[3]); else if (okB0) dst[LS / 2] = x[2];
+                }
+            };
+            double* base = a.out + (long long)(side ? (a.mode == 0 ? a.side_off : a.P) : 0) * a.ld + gA;
+            const long long rstep = (long long)NF * a.ld, bstep = (long long)a.N * a.ld;
+            double* dst = base + (long long)(grp.row0 + fs) * a.ld;
+            const LtOp* rop = sop + grp.nops;
+            const int nku = (a.mode == 1 && a.model == KF_BILINEAR) ? a.m : 0;
+            const int nw = a.mode == 1 ? a.nw : 0;
+            if (nw == 0 && nku == 0) {
+                for (int e = fs; e < grp.nst; e += NF, dst += rstep) {
+                    double v[4];
+                    lq_eval<LS>(rop[e], sh, t2, a.nv, a.centres, v);
+                    put(dst, v);
+                }
+            } else if (nw == 0 && nku <= 3) {                // u_k psi, the u_k quads in registers  (Ksysid.m:510-511)
+                double uu[3][4];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (k < nku) lq_ld<LS>(su + k * LS, t2, uu[k]);
+                    else { uu[k][0] = uu[k][1] = uu[k][2] = uu[k][3] = 0.0; }
+                }
+                for (int e = fs; e < grp.nst; e += NF, dst += rstep) {
+                    double v[4];
+                    lq_eval<LS>(rop[e], sh, t2, a.nv, a.centres, v);
+                    put(dst, v);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (k < nku) {
+                            double x[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) x[t] = KF_MUL(uu[k][t], v[t]);
+                            put(dst + (k + 1) * bstep, x);
+                        }
+                }
+            } else {
+                // column (ka (nw+1) + kc) N + row holds u_ka * (w_kc * psi) — [1; u] (x) [1; w] (x) psi with the reference's
+                // association (psi_L = [psi; w_c psi] first, Ksysid.m:594-599; then u_k psi_L, 510-511 / 604-605)
+                for (int e = fs; e < grp.nst; e += NF, dst += rstep) {
+                    double v[4];
+                    lq_eval<LS>(rop[e], sh, t2, a.nv, a.centres, v);
+                    for (int ka = 0; ka <= nku; ++ka)
+                        for (int kc = 0; kc <= nw; ++kc) {
+                            double x[4] = {v[0], v[1], v[2], v[3]}, f[4];
+                            if (kc) {
+                                lq_ld<LS>(su + (a.m + kc - 1) * LS, t2, f);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) x[t] = KF_MUL(f[t], x[t]);
+                            }
+                            if (ka) {
+                                lq_ld<LS>(su + (ka - 1) * LS, t2, f);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) x[t] = KF_MUL(f[t], x[t]);
+                            }
+                            put(dst + (long long)(ka * (nw + 1) + kc) * bstep, x);
+                        }
+                }
+            }
+            if (a.mode == 1 && a.model == KF_LINEAR && g == 0) {   // [psi_L, u]  (Ksysid.m:1062-1063)
+                for (int i = fs; i < a.m; i += NF) {
+                    double x[4];
+                    lq_ld<LS>(su + i * LS, t2, x);
+                    put(base + ((long long)a.N * (a.nw + 1) + i) * a.ld, x);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // launches the tile kernel if the program fits (levels, shared memory); returns false otherwise
 template <int LS>
 bool lift_tile_launch_ls(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, size_t smem, cudaStream_t st, int* rc) {
@@ -310,46 +524,138 @@ bool lift_tile_launch_ls(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, size_t smem
     return true;
 }
 
+// group tables (ops | store lists | group records) of ctx->lt_* -> device; the previous tables may still be read by kernels on
+// another stream of this context, and the new ones must be visible to every stream that launches an evaluator afterwards
+bool lift_groups_upload(kf_ctx* ctx, cudaStream_t st, int* rc) {
+    const size_t nb_ops = ctx->lt_ops.size() * sizeof(LtOp), nb_st = ctx->lt_store.size() * sizeof(LtStore), nb_g = ctx->lt_groups.size() * sizeof(LtGroup);
+    const size_t o_st = (nb_ops + 15) & ~(size_t)15, o_g = (o_st + nb_st + 15) & ~(size_t)15;
+    if (cudaDeviceSynchronize() != cudaSuccess || ctx->d_lift_groups.ensure(o_g + nb_g) != cudaSuccess) { cudaGetLastError(); return false; }
+    char* b0 = ctx->d_lift_groups.as<char>();
+    cudaMemcpyAsync(b0, ctx->lt_ops.data(), nb_ops, cudaMemcpyHostToDevice, st);
+    if (nb_st) cudaMemcpyAsync(b0 + o_st, ctx->lt_store.data(), nb_st, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(b0 + o_g, ctx->lt_groups.data(), nb_g, cudaMemcpyHostToDevice, st);
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        *rc = KF_ECUDA;
+        ctx->err = "lift groups upload failed";
+        return false;
+    }
+    return true;
+}
+void lift_groups_bind(kf_ctx* ctx, KfLiftTileArgs& a) {
+    const size_t nb_ops = ctx->lt_ops.size() * sizeof(LtOp), nb_st = ctx->lt_store.size() * sizeof(LtStore);
+    const size_t o_st = (nb_ops + 15) & ~(size_t)15, o_g = (o_st + nb_st + 15) & ~(size_t)15;
+    char* base = ctx->d_lift_groups.as<char>();
+    a.gops = reinterpret_cast<const LtOp*>(base);
+    a.gstore = reinterpret_cast<const LtStore*>(base + o_st);
+    a.groups = reinterpret_cast<const LtGroup*>(base + o_g);
+    a.ngroups = (int)ctx->lt_groups.size();
+    a.max_slots = ctx->lt_max[0]; a.max_ops = ctx->lt_max[1]; a.max_nst = ctx->lt_max[2];
+}
+
+// Builds (or reuses) the dependency-closed feature groups of the narrow tile kernel for a slot budget and makes them resident on
+// the device.  false: the program cannot be grouped (dependency chain too deep) or the upload failed (*rc set).
+bool lift_groups_prepare(kf_ctx* ctx, KfLiftTileArgs& a, int slots_target, bool single, cudaStream_t st, int* rc) {
+    const KfProgram& p = ctx->prog;
+    const unsigned long long key[4] = {ctx->prog_gen, 0ull, (unsigned long long)slots_target, single ? 1ull : 0ull};
+    const bool cached = std::equal(key, key + 4, ctx->lt_key) && !ctx->lt_groups.empty();
+    if (!cached) {
+        ctx->lt_key[0] = ~0ull;
+        if (!kf_build_lift_groups(p, slots_target, single, ctx->lt_ops, ctx->lt_store, ctx->lt_groups)) return false;
+        ctx->lt_max[0] = ctx->lt_max[1] = ctx->lt_max[2] = 0;
+        for (const LtGroup& g : ctx->lt_groups) {
+            ctx->lt_max[0] = std::max(ctx->lt_max[0], g.nslots);
+            ctx->lt_max[1] = std::max(ctx->lt_max[1], g.nops);
+            ctx->lt_max[2] = std::max(ctx->lt_max[2], g.nst);
+        }
+        if (!lift_groups_upload(ctx, st, rc)) return false;
+        std::copy(key, key + 4, ctx->lt_key);
+    }
+    lift_groups_bind(ctx, a);
+    return true;
+}
+
+template <int LS, int MINB>
+bool lift_stream_launch_ls(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, size_t smem, cudaStream_t st, int* rc) {
+    if (kf_ensure_smem(ctx, kf_lift_stream_kernel<LS, MINB>, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const long long ntiles = (a.M + LS - 1) / LS;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(MINB, (227 * 1024) / (smem + 1024)));
+    const int rows = std::max(1, (ctx->sm_count * per_sm) / std::max(1, nsides * a.ngroups));
+    const unsigned gx = (unsigned)std::min<long long>(ntiles, (long long)rows);
+    kf_lift_stream_kernel<LS, MINB><<<dim3(gx, nsides * a.ngroups), LT_THREADS, smem, st>>>(a);
+    if (cudaGetLastError() != cudaSuccess) { *rc = KF_ECUDA; ctx->err = "kf_lift_stream_kernel launch failed"; }
+    ctx->launches += 1;
+    return true;
+}
+
+// streaming kernel: needs 16-byte aligned vector stores (even ld, aligned base), no dim_red, enough snapshots to fill tiles
+bool lift_stream_launch(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, cudaStream_t st, int* rc) {
+    if (!ctx->opt_lift_wide || a.n_pcs > 0 || (a.ld & 1) || (reinterpret_cast<unsigned long long>(a.out) & 15ull) || a.M < 256) return false;
+    if (a.mode == 0 && nsides > 1 && (((long long)a.side_off * a.ld) & 1)) return false;
+    const KfProgram& p = ctx->prog;
+    // tile width: 256-byte runs reach the full write rate only on 128-byte-aligned rows; otherwise 512-byte runs
+    const bool aligned = (a.ld % 16 == 0) && (reinterpret_cast<unsigned long long>(a.out) % 128 == 0);
+    int ls = ctx->opt_lift_ls;
+    if (ls != 32 && ls != 64) ls = aligned ? 32 : 64;
+    const int n = p.n_full();
+    const long long ntiles = (a.M + ls - 1) / ls;
+    // few tiles (a panel of the fit path, a short series): split the rows so that every SM has work
+    int max_rows = 0;
+    if (ntiles * nsides < 2LL * ctx->sm_count) {
+        const int parts = (int)((2LL * ctx->sm_count + ntiles * nsides - 1) / (ntiles * nsides));
+        max_rows = std::max(32, (n + parts - 1) / parts);
+    }
+    auto bytes = [&](int slots, int ops) {
+        return ((size_t)slots + (size_t)a.m + (size_t)a.nw) * ls * sizeof(double) + (size_t)ops * sizeof(LtOp) +
+               (size_t)(a.nv + a.m + a.nw) * sizeof(double*) + 64;
+    };
+    const double budget = std::max(16.0, ctx->opt_lift_smem_kb) * 1024.0;      // slots per CTA: >= 3 CTAs per SM by default
+    const int slots_target = std::max(p.nv + 8, (int)(budget / (ls * sizeof(double))) - a.m - a.nw);
+    {
+        const unsigned long long key[4] = {ctx->prog_gen, 1ull, (unsigned long long)slots_target, (unsigned long long)max_rows};
+        const bool cached = std::equal(key, key + 4, ctx->lt_key) && !ctx->lt_groups.empty();
+        if (!cached) {
+            ctx->lt_key[0] = ~0ull;
+            ctx->lt_store.clear();
+            if (!kf_build_lift_rowgroups(p, slots_target, max_rows, ctx->lt_ops, ctx->lt_groups)) return false;
+            ctx->lt_max[0] = ctx->lt_max[1] = ctx->lt_max[2] = 0;
+            for (const LtGroup& g : ctx->lt_groups) {
+                ctx->lt_max[0] = std::max(ctx->lt_max[0], g.nslots);
+                ctx->lt_max[1] = std::max(ctx->lt_max[1], g.nops + g.nst);
+                ctx->lt_max[2] = std::max(ctx->lt_max[2], g.nst);
+            }
+            if (!lift_groups_upload(ctx, st, rc)) return *rc != KF_OK;
+            std::copy(key, key + 4, ctx->lt_key);
+        }
+        lift_groups_bind(ctx, a);
+    }
+    const size_t b = bytes(a.max_slots, a.max_ops);
+    if (b > 200 * 1024) return false;                    // does not fit: the narrow kernel takes it
+    if (ctx->opt_lift_minb >= 3)
+        return ls == 64 ? lift_stream_launch_ls<64, 3>(ctx, a, nsides, b, st, rc) : lift_stream_launch_ls<32, 3>(ctx, a, nsides, b, st, rc);
+    return ls == 64 ? lift_stream_launch_ls<64, 2>(ctx, a, nsides, b, st, rc) : lift_stream_launch_ls<32, 2>(ctx, a, nsides, b, st, rc);
+}
+
 bool lift_tile_launch(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, cudaStream_t st, int* rc) {
     *rc = KF_OK;
     const int nlev = (int)ctx->level_start.size() - 1;
     if (nlev > LT_MAXLEV || a.M <= 0) return false;
+    if (lift_stream_launch(ctx, a, nsides, st, rc)) return true;
+    if (*rc) return true;
     const KfProgram& p = ctx->prog;
     auto bytes = [&](int ls, int slots, int ops, int nst) {
         return ((size_t)slots + (size_t)a.m + (size_t)a.nw + (a.n_pcs > 0 ? (size_t)a.N : 0)) * ls * sizeof(double) + (size_t)ops * sizeof(LtOp) +
                (size_t)nst * sizeof(LtStore) + 64;
     };
-    // Tile width LS (snapshots per tile = contiguous bytes per output row / 8): the wider, the longer the contiguous runs the
-    // DRAM sees (128-byte runs scattered over GBs cap the write rate near 2.6 TB/s), but the fewer features fit a CTA, i.e.
-    // more dependency-closed groups.  Option lift_ls forces it; default 16.
+    // Narrow tiles (8 / 16 snapshots; dim_red, odd leading dimensions, few snapshots).  Option lift_ls forces the width.
     int ls = ctx->opt_lift_ls;
-    if (ls != 8 && ls != 16 && ls != 32 && ls != 64) ls = 16;      // measured: 32 ties, 64 and 8 lose (profiles/r01_lift_only_bandwidth.json)
+    if (ls != 8 && ls != 16 && ls != 32 && ls != 64) ls = 16;
     if (a.n_pcs > 0 && ls > 16) ls = 16;                 // dim_red needs every feature in one CTA
     const int slots_target = std::max(p.nv + 8, (int)((56 * 1024) / (ls * sizeof(double))));
     const bool single = a.n_pcs > 0 || bytes(ls, p.n_full(), p.n_full(), p.n_full()) <= 74 * 1024;
-    if (!kf_build_lift_groups(p, slots_target, single, ctx->lt_ops, ctx->lt_store, ctx->lt_groups)) return false;
-    a.ngroups = (int)ctx->lt_groups.size();
-    a.max_slots = a.max_ops = a.max_nst = 0;
-    for (const LtGroup& g : ctx->lt_groups) {
-        a.max_slots = std::max(a.max_slots, g.nslots);
-        a.max_ops = std::max(a.max_ops, g.nops);
-        a.max_nst = std::max(a.max_nst, g.nst);
-    }
-    const size_t nb_ops = ctx->lt_ops.size() * sizeof(LtOp), nb_st = ctx->lt_store.size() * sizeof(LtStore), nb_g = ctx->lt_groups.size() * sizeof(LtGroup);
-    const size_t o_st = (nb_ops + 15) & ~(size_t)15, o_g = (o_st + nb_st + 15) & ~(size_t)15;
-    if (ctx->d_lift_groups.ensure(o_g + nb_g) != cudaSuccess) { cudaGetLastError(); return false; }
-    char* base = ctx->d_lift_groups.as<char>();
-    cudaMemcpyAsync(base, ctx->lt_ops.data(), nb_ops, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(base + o_st, ctx->lt_store.data(), nb_st, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(base + o_g, ctx->lt_groups.data(), nb_g, cudaMemcpyHostToDevice, st);
-    if (cudaStreamSynchronize(st) != cudaSuccess) {     // the host vectors are reused by the next launch
-        *rc = KF_ECUDA;
-        ctx->err = "lift groups upload failed";
-        return true;
-    }
-    a.gops = reinterpret_cast<const LtOp*>(base);
-    a.gstore = reinterpret_cast<const LtStore*>(base + o_st);
-    a.groups = reinterpret_cast<const LtGroup*>(base + o_g);
+    if (!lift_groups_prepare(ctx, a, slots_target, single, st, rc)) return *rc != KF_OK;
     for (;;) {
         const size_t b = bytes(ls, a.max_slots, a.max_ops, a.max_nst);
         if (b <= 200 * 1024) {
@@ -443,6 +749,57 @@ int kf_launch_lift_points(kf_ctx* ctx, const KfOp* ops, const double* centres, c
         return KF_EINVAL;
     }
     return kf_launch_lift(ctx, a, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Panel lift through the shared-memory tile evaluator: psi(alpha) -> panel rows [x_off, x_off + N), psi(beta) -> rows
+// [y_off, y_off + N) for the chunk [start, start + Mc) (feature-major, ld = Mc, L2-resident), plus the u rows (linear)
+// and the Kronecker weight rows u_a u_b (bilinear).  ~3x the rate of the level-by-level kernel, which re-reads product
+// factors from the panel and pays one launch per dependency level.
+__global__ void kf_panel_extras_kernel(const KfLiftArgs a, long long count) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.Mc) return;
+    const bool valid = s < count;
+    const long long gs = a.start + s;
+    if (a.model == KF_LINEAR) {
+        double* sec = a.panel + (long long)a.x_off * a.ld + s;
+        for (int i = 0; i < a.m; ++i) sec[(long long)(a.N + i) * a.ld] = valid ? a.u[(long long)i * a.M + gs] : 0.0;
+    } else if (a.model == KF_BILINEAR && a.nW > 0) {
+        double* w = a.panel + (long long)a.w_off * a.ld + s;
+        for (int p = 0; p <= a.m; ++p) {
+            const double up = (p && valid) ? a.u[(long long)(p - 1) * a.M + gs] : 1.0;
+            for (int q = p; q <= a.m; ++q) {
+                const double uq = (q && valid) ? a.u[(long long)(q - 1) * a.M + gs] : 1.0;
+                w[(long long)pair_index(p, q, a.m) * a.ld] = valid ? (p ? KF_MUL(up, uq) : uq) : 0.0;
+            }
+        }
+    }
+}
+
+// returns false if the tile evaluator cannot take the program (then the caller uses the level kernel)
+bool kf_launch_lift_panel_tile(kf_ctx* ctx, const KfLiftArgs& a, cudaStream_t st, int* rc, long long limit) {
+    *rc = KF_OK;
+    long long count = std::min<long long>(a.Mc, a.M - a.start);
+    if (limit >= 0) count = std::min(count, limit);      // snapshots of the chunk that belong to this call
+    if (count <= 0 || !ctx->opt_lift_tile) return false;
+    KfLiftTileArgs t{};
+    t.ops = a.ops; t.centres = a.centres; t.pcs = a.pcs; t.order = a.order;
+    t.nv = a.nv; t.n_full = a.n_full; t.n_pcs = a.n_pcs; t.N = a.N;
+    t.nzeta = a.nzeta; t.m = 0; t.nw = 0; t.model = a.model; t.mode = 0; t.P = a.N;   // variables beyond nzeta (nonlinear) come from u
+    t.alpha = a.alpha + a.start; t.beta = a.beta + a.start; t.u = a.u ? a.u + a.start : a.u; t.M = count; t.ldin = a.M;
+    t.out = a.panel + (long long)a.x_off * a.ld; t.ld = a.ld; t.side_off = a.y_off - a.x_off;
+    if (count < a.Mc) {                              // tail of the last chunk: the tile kernel stores valid snapshots only
+        const size_t bytes = (size_t)(a.y_off + a.N - a.x_off) * a.ld * sizeof(double);
+        if (cudaMemsetAsync(a.panel + (long long)a.x_off * a.ld, 0, bytes, st) != cudaSuccess) { *rc = KF_ECUDA; return true; }
+    }
+    if (!lift_tile_launch(ctx, t, a.nsides > 0 ? a.nsides : 2, st, rc)) return false;
+    if (*rc) return true;
+    if (a.extras && (a.model == KF_LINEAR || (a.model == KF_BILINEAR && a.nW > 0))) {
+        kf_panel_extras_kernel<<<(a.Mc + 255) / 256, 256, 0, st>>>(a, count);
+        if (cudaGetLastError() != cudaSuccess) { *rc = KF_ECUDA; ctx->err = "kf_panel_extras_kernel launch failed"; }
+        ctx->launches += 1;
+    }
+    return true;
 }
 
 // Materialised regressors of the snapshots [a0.start, a0.start + count) (count = min(a0.Mc, a0.M - a0.start); a0.Mc <= 0: all):

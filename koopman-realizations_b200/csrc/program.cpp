@@ -229,10 +229,17 @@ bool kf_build_lift_groups(const KfProgram& p, int max_slots, bool single, std::v
         }
         // evaluation order: by depth, then by feature index; slots: variables 0 .. nv-1, then in that order (or identity)
         std::sort(members.begin(), members.end(), [&](int x, int y) { return depth[x] != depth[y] ? depth[x] < depth[y] : x < y; });
+        // slots: variables 0 .. nv-1, then the parents that are not outputs of this group, then the outputs [max(j, nv), j1) in
+        // feature order — the stored rows are ONE contiguous slot range (slot0 + e <-> row0 + e), so the store phase needs no table
         std::fill(slot.begin(), slot.end(), -1);
         for (int v = 0; v < nv; ++v) slot[v] = v;
         int next = nv;
-        for (int f : members) slot[f] = single ? f : next++;
+        if (!single) {
+            for (int f : members) if (f < j) slot[f] = next++;
+            for (int f = std::max(j, nv); f < j1; ++f) slot[f] = next++;
+        } else {
+            for (int f : members) slot[f] = f;
+        }
         LtGroup G{};
         G.op_off = (int)gops.size(); G.st_off = (int)gstore.size();
         G.nslots = single ? n : next;
@@ -254,9 +261,91 @@ bool kf_build_lift_groups(const KfProgram& p, int max_slots, bool single, std::v
             for (int v = 0; v < nv; ++v) gstore.push_back(LtStore{v, v});      // the variables are rows 0 .. nv-1 of psi
         for (int f = std::max(j, nv); f < j1; ++f) gstore.push_back(LtStore{slot[f], f});
         G.nst = (int)gstore.size() - G.st_off;
+        G.slot0 = gstore[G.st_off].slot; G.row0 = gstore[G.st_off].row;
         groups.push_back(G);
         j = j1;
     }
     return true;
 }
 
+
+bool kf_build_lift_rowgroups(const KfProgram& p, int max_slots, int max_rows, std::vector<LtOp>& gops, std::vector<LtGroup>& groups) {
+    const int n = p.n_full(), nv = p.nv;
+    std::vector<int> depth(n, 0);
+    for (int j = 0; j < n; ++j) {
+        const KfOp& op = p.ops[j];
+        if (op.kind == KF_OP_MUL) {
+            const int da = op.a < nv ? -1 : depth[op.a], db = op.b < nv ? -1 : depth[op.b];
+            depth[j] = 1 + std::max(da, db);
+        }
+    }
+    gops.clear(); groups.clear();
+    std::vector<char> in(n, 0), isp(n, 0);
+    std::vector<int> members, parents, stack, add, newp, slot(n, -1);
+    int j = 0;
+    while (j < n) {
+        for (int f : members) in[f] = 0;
+        for (int f : parents) isp[f] = 0;
+        members.clear(); parents.clear();
+        int j1 = j;
+        while (j1 < n && (max_rows <= 0 || j1 - j < max_rows)) {
+            stack.assign(1, j1);
+            add.clear(); newp.clear();
+            while (!stack.empty()) {                   // closure of feature j1; every operand met on the way becomes a parent
+                const int f = stack.back(); stack.pop_back();
+                if (f < nv || in[f]) continue;
+                in[f] = 1; add.push_back(f);
+                const KfOp& op = p.ops[f];
+                if (op.kind == KF_OP_MUL)
+                    for (int q : {op.a, op.b})
+                        if (q >= nv) {
+                            if (!isp[q]) { isp[q] = 1; newp.push_back(q); }
+                            stack.push_back(q);
+                        }
+            }
+            if (j1 > j && nv + (int)parents.size() + (int)newp.size() > max_slots) {
+                for (int f : add) in[f] = 0;
+                for (int f : newp) isp[f] = 0;
+                break;
+            }
+            members.insert(members.end(), add.begin(), add.end());
+            parents.insert(parents.end(), newp.begin(), newp.end());
+            ++j1;
+        }
+        std::sort(parents.begin(), parents.end(), [&](int x, int y) { return depth[x] != depth[y] ? depth[x] < depth[y] : x < y; });
+        for (int v = 0; v < nv; ++v) slot[v] = v;
+        int next = nv;
+        for (int f : parents) slot[f] = next++;
+        LtGroup G{};
+        G.op_off = (int)gops.size();
+        G.nslots = next;
+        int lev = -1;
+        for (int f : parents) {
+            while (lev < depth[f]) {
+                if (G.nlevels >= KF_LT_MAXLEV) return false;
+                G.level_start[G.nlevels++] = (int)gops.size() - G.op_off;
+                ++lev;
+            }
+            const KfOp& op = p.ops[f];
+            LtOp o{op.kind, op.a, op.b, slot[f], op.c};
+            if (op.kind == KF_OP_MUL) { o.a = slot[op.a]; o.b = slot[op.b]; }
+            gops.push_back(o);
+        }
+        G.level_start[G.nlevels] = (int)gops.size() - G.op_off;
+        G.nops = (int)gops.size() - G.op_off;
+        G.rop_off = (int)gops.size();
+        for (int f = j; f < j1; ++f) {
+            const KfOp& op = p.ops[f];
+            LtOp o{op.kind, op.a, op.b, -1, op.c};
+            if (f < nv) o = LtOp{KF_OP_VAR, f, 0, -1, 0.0};
+            else if (isp[f]) o = LtOp{KF_OP_VAR, slot[f], 0, -1, 0.0};
+            else if (op.kind == KF_OP_MUL) { o.a = slot[op.a]; o.b = slot[op.b]; }
+            gops.push_back(o);
+        }
+        G.st_off = 0; G.nst = j1 - j; G.row0 = j; G.slot0 = -1;
+        groups.push_back(G);
+        for (int f : parents) slot[f] = -1;
+        j = j1;
+    }
+    return true;
+}

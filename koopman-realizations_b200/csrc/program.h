@@ -42,12 +42,22 @@ struct LtGroup {
     int op_off, nops;                  // ops of the group in the global op array
     int st_off, nst;                   // stored features in the global store array
     int nslots, nlevels;
+    int slot0, row0;                   // the stored features are contiguous: slot0 + e holds output row row0 + e, e < nst
+    int rop_off;                       // row groups (kf_build_lift_rowgroups): the nst row ops follow the slot ops in the op array
     int level_start[KF_LT_MAXLEV + 1]; // offsets into the group's ops; a level only reads slots written by earlier levels
 };
 // Partition into groups of at most max_slots slots (single: one group with slot = feature index, whatever its size).
 // Returns false if a dependency chain is deeper than KF_LT_MAXLEV levels.
 bool kf_build_lift_groups(const KfProgram& p, int max_slots, bool single, std::vector<LtOp>& gops, std::vector<LtStore>& gstore,
                           std::vector<LtGroup>& groups);
+
+// Row groups of the streaming lift kernel: a group is a contiguous range of output rows [row0, row0 + nst); only the features
+// that some member of the group READS (its parents) get a shared-memory slot and are evaluated level by level (ops
+// [op_off, op_off + nops), j = slot); every output row then has ONE row op (gops[rop_off + e], operands = slots, j unused):
+// a copy of a slot (KF_OP_VAR) or the feature's own op, evaluated in registers and stored straight to global memory — leaves
+// (most monomials, every gaussian) never touch shared memory.  A group ends when its parents exceed max_slots or it has
+// max_rows rows (max_rows <= 0: no limit).  Returns false if a dependency chain is deeper than KF_LT_MAXLEV levels.
+bool kf_build_lift_rowgroups(const KfProgram& p, int max_slots, int max_rows, std::vector<LtOp>& gops, std::vector<LtGroup>& groups);
 
 // rows of partitions(total, ones(1,nvars)) in the reference's order, appended to `out` (row-major)
 void kf_partitions_ones(int total, int nvars, std::vector<int>& out);

@@ -82,6 +82,7 @@ extern "C" int hostlift_groups(const kf_basis* basis, int max_slots, int single,
         for (int e = 0; e < g.nst; ++e) {
             const LtStore& sr = gstore[g.st_off + e];
             if (sr.slot < 0 || sr.slot >= g.nslots || sr.row < 0 || sr.row >= nf || wlevel[sr.slot] == (1 << 30)) return -6;
+            if (sr.slot != g.slot0 + e || sr.row != g.row0 + e) return -8;      // one contiguous slot range <-> one contiguous row range
             stored[sr.row] += 1;
         }
         std::vector<double> sh(g.nslots);
@@ -99,4 +100,61 @@ extern "C" int hostlift_groups(const kf_basis* basis, int max_slots, int single,
     for (int j = 0; j < nf; ++j)
         if (stored[j] != 1) return -7;
     return 0;
+}
+
+// The lift evaluated by ROW GROUPS exactly as kf_lift_stream_kernel does: slot ops level by level, then one row op per output
+// row.  Invariants: operands are variables or slots written by an earlier level; the groups tile [0, n_full) in order; the
+// slot / row budgets hold.  out: rows x n_full column-major.
+extern "C" int hostlift_rowgroups(const kf_basis* basis, int max_slots, int max_rows, long long rows, const double* V, double* out,
+                                  int* ngroups, int* max_used) {
+    KfProgram prog;
+    std::string err;
+    int rc = kf_build_program(basis, prog, err);
+    if (rc) return rc;
+    std::vector<LtOp> gops;
+    std::vector<LtGroup> groups;
+    if (!kf_build_lift_rowgroups(prog, max_slots, max_rows, gops, groups)) return -1;
+    const int nf = prog.n_full(), nv = prog.nv;
+    *ngroups = (int)groups.size();
+    *max_used = 0;
+    int next_row = 0;
+    for (const LtGroup& g : groups) {
+        if (g.nslots > *max_used) *max_used = g.nslots;
+        if (g.row0 != next_row || g.nst <= 0) return -2;
+        if (max_rows > 0 && g.nst > max_rows) return -9;
+        next_row += g.nst;
+        std::vector<int> wlevel(g.nslots, 1 << 30);
+        for (int v = 0; v < nv; ++v) wlevel[v] = -1;
+        for (int l = 0; l < g.nlevels; ++l)
+            for (int e = g.level_start[l]; e < g.level_start[l + 1]; ++e) {
+                const LtOp& op = gops[g.op_off + e];
+                if (op.j < nv || op.j >= g.nslots || wlevel[op.j] != (1 << 30)) return -3;
+                if (op.kind == KF_OP_MUL && (wlevel[op.a] >= l || wlevel[op.b] >= l)) return -4;
+                if ((op.kind == KF_OP_COS || op.kind == KF_OP_SIN || op.kind == KF_OP_HERM) && op.a >= nv) return -5;
+                wlevel[op.j] = l;
+            }
+        if (g.level_start[g.nlevels] != g.nops || g.rop_off != g.op_off + g.nops) return -6;
+        for (int e = 0; e < g.nst; ++e) {
+            const LtOp& op = gops[g.rop_off + e];
+            if (op.kind == KF_OP_MUL && (op.a < 0 || op.b < 0 || op.a >= g.nslots || op.b >= g.nslots || wlevel[op.a] == (1 << 30) || wlevel[op.b] == (1 << 30))) return -7;
+            if (op.kind == KF_OP_VAR && (op.a < 0 || op.a >= g.nslots || wlevel[op.a] == (1 << 30))) return -8;
+        }
+        std::vector<double> sh(g.nslots);
+        for (long long s = 0; s < rows; ++s) {
+            for (int i = 0; i < nv; ++i) sh[i] = V[(size_t)i * rows + s];
+            for (int e = 0; e < g.nops; ++e) {
+                const LtOp& op = gops[g.op_off + e];
+                KfOp o{};
+                o.kind = op.kind; o.a = op.a; o.b = op.b; o.c = op.c;
+                sh[op.j] = kf_eval_op(o, nv, prog.centres.data(), [&](int k) { return sh[k]; });
+            }
+            for (int e = 0; e < g.nst; ++e) {
+                const LtOp& op = gops[g.rop_off + e];
+                KfOp o{};
+                o.kind = op.kind; o.a = op.a; o.b = op.b; o.c = op.c;
+                out[(size_t)(g.row0 + e) * rows + s] = kf_eval_op(o, nv, prog.centres.data(), [&](int k) { return sh[k]; });
+            }
+        }
+    }
+    return next_row == nf ? 0 : -10;
 }

@@ -321,3 +321,47 @@ def test_device_lift_only_mode(fitter, model, types, degs, nz, m, M):
     fitter.sync()
     want = O.lift(prog, V)
     assert np.abs(psi.cpu().numpy().T - want).max() < (1e-300 if exact else 1e-14)
+
+
+@pytest.mark.parametrize("model,types,degs,nz,m,M", [
+    ("bilinear", ["poly"], [4], 8, 2, 9001),                       # 495 features in several groups, odd row count -> narrow kernel only
+    ("bilinear", ["poly"], [4], 8, 2, 9002),                       # even, rows not 128-byte aligned: 64-snapshot tiles, ragged last tile
+    ("bilinear", ["poly", "gaussian"], [2, 300], 6, 5, 4096),      # m = 5: general block loop; aligned rows: 32-snapshot tiles
+    ("linear", ["poly", "gaussian"], [3, 40], 10, 3, 8192),        # u rows appended
+    ("nonlinear", ["poly", "fourier_sparser", "hermite"], [3, 2, 3], 9, 3, 12288 + 6),   # variables 10..12 come from u
+])
+def test_materialised_regressors_wide_tiles(fitter, model, types, degs, nz, m, M):
+    """kf_regressors_dev through the wide-tile kernel (32 / 64 snapshots per tile, contiguous slot ranges, quad-wise gaussians):
+    identical bytes to the narrow tile kernel (lift_wide = 0) for both tile widths, and the oracle's [Px | Py]
+    (Ksysid.m:1019-1065)."""
+    import torch
+    rng = np.random.default_rng(M)
+    alpha, beta, u = 2 * rng.random((M, nz)) - 1, 2 * rng.random((M, nz)) - 1, 2 * rng.random((M, m)) - 1
+    nv = nz + (m if model == "nonlinear" else 0)
+    cen = centres_for(types, degs, nv)
+    basis = koopfit.Basis(types, degs, nv, cen)
+    prog = O.build_program(types, degs, nv, cen)
+    Px, Py = O.build_regressors(model, prog, alpha, beta, u)
+    P = Px.shape[1]
+    dev = torch.device("cuda", 0)
+    ta, tb, tu = (torch.from_numpy(np.ascontiguousarray(x.T)).to(dev) for x in (alpha, beta, u))
+    outs = []
+    try:
+        for wide, ls, kb in ((0, 0, 64), (1, 0, 64), (1, 32, 24), (1, 64, 48)):
+            fitter.set_option("lift_wide", wide)
+            fitter.set_option("lift_ls", ls)
+            fitter.set_option("lift_smem_kb", kb)
+            out = torch.full((2 * P, M), float("nan"), dtype=torch.float64, device=dev)
+            fitter.regressors_dev(basis, model, M, nz, m, ta.data_ptr(), tb.data_ptr(), tu.data_ptr(), out.data_ptr())
+            fitter.sync()
+            outs.append(out.cpu().numpy().T)
+    finally:
+        fitter.set_option("lift_wide", 1)
+        fitter.set_option("lift_ls", 0)
+        fitter.set_option("lift_smem_kb", 64)
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
+    if all(t in ("poly", "hermite") for t in types):
+        assert np.array_equal(outs[0][:, :P], Px) and np.array_equal(outs[0][:, P:], Py)
+    else:
+        assert np.abs(outs[0][:, :P] - Px).max() < 1e-14 and np.abs(outs[0][:, P:] - Py).max() < 1e-14

@@ -134,6 +134,37 @@ def test_lift_feature_groups(hostlift, types, degs, nv, max_slots):
                 assert ngroups.value >= 2
 
 
+@pytest.mark.parametrize("types,degs,nv,max_slots,max_rows", [
+    (["poly"], [4], 8, 120, 0), (["poly"], [3], 12, 64, 100), (["poly", "gaussian"], [3, 569], 12, 128, 0),
+    (["poly", "gaussian"], [3, 569], 12, 40, 200), (["fourier"], [4], 3, 100, 0), (["fourier_sparser"], [3], 4, 40, 17),
+    (["hermite", "poly"], [3, 2], 4, 30, 0), (["poly"], [13], 1, 6, 0), (["gaussian"], [50], 5, 16, 8),
+])
+def test_lift_row_groups(hostlift, types, degs, nv, max_slots, max_rows):
+    """Row groups of the streaming lift kernel (program.cpp:kf_build_lift_rowgroups, evaluated on the host exactly as
+    kf_lift_stream_kernel does): only the features a group reads hold a slot, operands are written by an earlier level, the
+    groups tile the output rows in order, and the evaluation reproduces the plain one bit for bit."""
+    rng = np.random.default_rng(1)
+    ng = sum(d for t, d in zip(types, degs) if t == "gaussian")
+    cen = 2 * rng.random((nv, ng)) - 1 if ng else None
+    b = A.Basis(types, degs, nv, centres=cen)
+    nf, N = C.c_int(), C.c_int()
+    assert hostlift.hostlift_dims(b.ref(), C.byref(nf), C.byref(N)) == 0
+    rows = 7
+    V = np.asfortranarray(2 * rng.random((rows, nv)) - 1)
+    plain = np.zeros((rows, nf.value), order="F")
+    assert hostlift.hostlift_full(b.ref(), C.c_longlong(rows), A.dptr(V), A.dptr(plain)) == 0
+    out = np.full((rows, nf.value), np.nan, order="F")
+    ngroups, used = C.c_int(), C.c_int()
+    rc = hostlift.hostlift_rowgroups(b.ref(), max_slots, max_rows, C.c_longlong(rows), A.dptr(V), A.dptr(out), C.byref(ngroups), C.byref(used))
+    assert rc == 0, rc
+    assert np.array_equal(out, plain)
+    assert used.value <= max(max_slots, nv + 2 * max(degs) + 2)      # a single row's closure may exceed the budget
+    if max_rows:
+        assert ngroups.value >= -(-nf.value // max_rows)
+    if types == ["poly", "gaussian"] and max_rows == 0:
+        assert ngroups.value == 1 and used.value <= nv + 78          # only (some of) the degree-2 monomials are read by other features
+
+
 def test_mex_shim_compiles_against_the_abi():
     """matlab/koopfit_mex.cpp cannot run here (no MATLAB / Octave), but it must at least COMPILE against include/koopfit.h
     and a stub of the MEX API (tests/mex_stub/mex.h): catches ABI drift (renamed fields, changed signatures) in the shim."""

@@ -37,9 +37,13 @@ for name, fn, nbytes in (("fill_write_only", lambda: buf.fill_(1.5), 8.0 * (1 <<
 out["calibration_GB_s"] = cal
 print(cal, flush=True)
 del buf, buf2
+VARIANTS = [(1, 0, 1, 64, 2), (1, 0, 1, 64, 3), (1, 32, 1, 64, 2), (1, 64, 1, 64, 2), (1, 64, 1, 64, 3), (1, 0, 1, 32, 3), (1, 0, 1, 100, 2), (1, 0, 0, 64, 2), (0, 0, 0, 64, 2)]
+if len(sys.argv) > 1 and sys.argv[1] == "short":
+    VARIANTS = [(1, 0, 1, 64, 2), (1, 0, 0, 64, 2)]
 cases = [("poly4_nv12_bilinear_m3", ["poly"], [4], None, 12, 3, "bilinear", 133000),
          ("poly3_nv12_linear_m3", ["poly"], [3], None, 12, 3, "linear", 1050000),
-         ("config5_poly3_gauss569_bilinear", ["poly", "gaussian"], [3, 569], 2 * rng.random((12, 569)) - 1, 12, 3, "bilinear", 133000)]
+         ("config5_poly3_gauss569_bilinear", ["poly", "gaussian"], [3, 569], 2 * rng.random((12, 569)) - 1, 12, 3, "bilinear", 133000),
+         ("config5_dictionary_65536_pairs_aligned", ["poly", "gaussian"], [3, 569], 2 * rng.random((12, 569)) - 1, 12, 3, "bilinear", 65536)]
 for name, types, degs, cen, nz, m, model, M in cases:
     basis = koopfit.Basis(types, degs, nz, centres=cen)
     _, N, P = fit.dims(basis, model, m)
@@ -49,9 +53,12 @@ for name, types, degs, cen, nz, m, model, M in cases:
     o = torch.empty((2 * P, M), dtype=torch.float64, device=dev)
     alg = M * (8.0 * (2 * nz + m) + 16.0 * P)
     rec = {"case": name, "M": M, "N": N, "P": P, "algorithmic_bytes": alg, "output_GB": 16.0 * P * M / 1e9}
-    for tile, ls in ((1, 0), (1, 16), (1, 32), (1, 64), (0, 0)):
+    for tile, ls, wide, kb, minb in VARIANTS:
+        fit.set_option("lift_minb", minb)
         fit.set_option("lift_tile", tile)
         fit.set_option("lift_ls", ls)
+        fit.set_option("lift_wide", wide)
+        fit.set_option("lift_smem_kb", kb)
         for _ in range(3):
             fit.regressors_dev(basis, model, M, nz, m, a.data_ptr(), b.data_ptr(), u.data_ptr(), o.data_ptr())
         fit.sync()
@@ -64,10 +71,13 @@ for name, types, degs, cen, nz, m, model, M in cases:
             e1.record(st)
         fit.sync(); torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / reps
-        key = ("tile_kernel" if ls == 0 else f"tile_kernel_ls{ls}") if tile else "level_kernel"
+        key = ((f"stream_kernel_{kb}kb_minb{minb}" if wide else "tile_kernel") + ("" if ls == 0 else f"_ls{ls}")) if tile else "level_kernel"
         rec[key] = {"ms": round(ms, 4), "GB_s": round(alg / ms / 1e6, 1), "frac_of_hbm_peak": round(alg / ms / 1e6 / peak, 4)}
     fit.set_option("lift_ls", 0)
     fit.set_option("lift_tile", 1)
+    fit.set_option("lift_wide", 1)
+    fit.set_option("lift_smem_kb", 64)
+    fit.set_option("lift_minb", 2)
     print(rec, flush=True)
     out["cases"].append(rec)
     del o
