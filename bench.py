@@ -464,7 +464,7 @@ def main():
                 hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
             except Exception:
                 pass
-            lift_only = {"bound": "hbm", "kernel": "materialising lift ([Px | Py] written to HBM; not on the fit path)", "pairs": Ml,
+            lift_only = {"bound": "hbm", "kernel": "kf_lift_stream_kernel: materialising lift ([Px | Py] written to HBM; not on the fit path)", "pairs": Ml,
                          "achieved": lbytes / lms / 1e6, "peak": hbm, "unit": "GB/s", "frac": lbytes / lms / 1e6 / hbm,
                          "algorithmic_bytes_per_pair": 8.0 * (2 * NZETA + M_IN) + 16.0 * P_REG, "ms": lms}
             del out_buf

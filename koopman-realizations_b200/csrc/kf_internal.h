@@ -173,7 +173,7 @@ struct kf_ctx {
     int opt_lift_panel_fit = 0;          // fit path: lift the panel with the shared-memory tile evaluator instead of the level kernel
     int opt_lift_wide = 1;               // materialising lift: wide tiles (32 / 64 snapshots: long DRAM runs, table-free stores)
     int opt_lift_minb = 2;               // ... resident CTAs per SM the kernel is compiled for (2: 128 registers, 3: 80)
-    double opt_lift_smem_kb = 64;        // ... shared memory per CTA (decides the size of the feature groups and the CTAs per SM)
+    double opt_lift_smem_kb = 110;       // ... shared memory per CTA (decides the size of the feature groups and the CTAs per SM)
     KfBuf d_lift_groups;                 // feature groups of the materialising lift (ops | store lists | group records)
     KfBuf d_series;                      // raw merged series t | y | u and the scale factors (kf_fit_series)
     KfBuf d_as_mat, d_as_aux, d_as_ws;   // active-set QP solver: pattern/solution matrices, index lists, Cholesky factors
@@ -208,6 +208,8 @@ struct kf_ctx {
     unsigned long long prog_gen = 0;     // bumped by every prepare_program
     unsigned long long lt_key[4] = {~0ull, 0, 0, 0};
     int lt_max[3] = {0, 0, 0};           // max_slots, max_ops, max_nst of the cached groups
+    unsigned long long lt_plan_key[3] = {~0ull, 0, 0};   // streaming lift: cached tile-width decision for unaligned rows
+    bool lt_plan_narrow = false;
 
     // column partition of the active-set QP solver across ranks (kf_set_qp_partition)
     int qp_lo = 0, qp_hi = 0;

@@ -15,6 +15,7 @@
 // ~4e5 threads instead of 3e3.  A product reads its two factors back from the panel
 // (written by an earlier level, L2 hits).
 #include <algorithm>
+#include <cstring>
 
 #include "kf_internal.h"
 #include "lift_eval.h"
@@ -145,6 +146,9 @@ struct KfLiftTileArgs {
     int mode;                           // 0: points V -> Psi (rows x N);  1: regressors [Px | Py] (M x 2P)
     int P;
     int side_off;                       // mode 0 with two sides (panel mode): psi(beta) goes to rows side_off .. of `out`
+    const unsigned long long* rops;     // streaming kernel: packed row op of every output row (LtRop)
+    const double* rconst;               // ... constants of the primitive row ops
+    int ncent;                          // ... centre doubles staged in shared memory (0: read through L1)
     int max_slots, max_ops, max_nst;
     const double* alpha; const double* beta; const double* u; long long M;   // M = points of this launch
     const double* w; int nw;            // loads of a `loaded` model (mode 1): blocks w_c psi, Ksysid.m:594-599
@@ -310,7 +314,9 @@ __global__ void __launch_bounds__(LT_THREADS) kf_lift_tile_kernel(const KfLiftTi
 // memory, the store phase has no table lookup, no barrier and ~10 instructions per lifted element, and since the slots are
 // few a whole dictionary usually is ONE group: the inputs of a tile are read once and nothing is evaluated twice.  The next
 // tile's inputs are fetched into registers before the row phase, so their latency hides under the stores.
-constexpr int LW_PRE = 8;          // prefetch registers per thread (inputs of the next tile)
+// a row op packed into 8 bytes (shared memory: one per output row of the group)
+struct LtRop { unsigned short a, b; unsigned char kind, pad; unsigned short ci; };
+static_assert(sizeof(LtRop) == 8, "LtRop is 8 bytes");
 
 // a thread's 4 snapshots of a row: the pairs 2t, 2t+1 and LS/2 + 2t, LS/2 + 2t + 1 — every 128-bit access of LS/4 consecutive
 // threads covers a contiguous half run (128 B at LS = 32, 256 B at LS = 64)
@@ -323,20 +329,21 @@ template <int LS> __device__ __forceinline__ void lq_st(double* row, int t2, con
     *reinterpret_cast<double2*>(row + LS / 2 + t2) = make_double2(v[2], v[3]);
 }
 
-// one op on a snapshot quad; operands are shared-memory slots (GAUSS: the variables, slots 0 .. nv-1)
-template <int LS>
-__device__ __forceinline__ void lq_eval(const LtOp& op, const double* sh, int t2, int nv, const double* __restrict__ centres, double (&v)[4]) {
-    if (op.kind == KF_OP_MUL) {
+// one op on a snapshot quad; operands are shared-memory slots (GAUSS: the variables, slots 0 .. nv-1; centres in shared memory
+// or read through L1).  c is only read by the primitive kinds.
+template <int LS, class GetC>
+__device__ __forceinline__ void lq_eval(int kind, int oa, int ob, GetC getc, const double* sh, int t2, int nv, const double* cen, double (&v)[4]) {
+    if (kind == KF_OP_MUL) {
         double x[4], y[4];
-        lq_ld<LS>(sh + op.a * LS, t2, x);
-        lq_ld<LS>(sh + op.b * LS, t2, y);
+        lq_ld<LS>(sh + oa * LS, t2, x);
+        lq_ld<LS>(sh + ob * LS, t2, y);
 #pragma unroll
         for (int t = 0; t < 4; ++t) v[t] = KF_MUL(x[t], y[t]);
-    } else if (op.kind == KF_OP_GAUSS) {                 // exp(-||v - c||^2): the operation order of kf_eval_op, the centre read once per quad
-        const double* __restrict__ c = centres + (size_t)op.a * nv;
+    } else if (kind == KF_OP_GAUSS) {                    // exp(-||v - c||^2): the operation order of kf_eval_op, the centre read once per quad
+        const double* c = cen + (size_t)oa * nv;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         for (int i = 0; i < nv; ++i) {
-            const double ci = __ldg(c + i);
+            const double ci = c[i];
             double x[4];
             lq_ld<LS>(sh + i * LS, t2, x);
 #pragma unroll
@@ -347,31 +354,40 @@ __device__ __forceinline__ void lq_eval(const LtOp& op, const double* sh, int t2
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) v[t] = exp(-acc[t]);
-    } else if (op.kind == KF_OP_VAR) {
-        lq_ld<LS>(sh + op.a * LS, t2, v);
+    } else if (kind == KF_OP_VAR) {
+        lq_ld<LS>(sh + oa * LS, t2, v);
     } else {
         KfOp o{};
-        o.kind = op.kind; o.a = op.a; o.b = op.b; o.c = op.c;
+        o.kind = kind; o.a = oa; o.b = ob; o.c = getc();
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const double* col = sh + (t < 2 ? t2 + t : LS / 2 + t2 + t - 2);
-            v[t] = kf_eval_op(o, nv, centres, [&](int k) -> double { return col[k * LS]; });
+            v[t] = kf_eval_op(o, nv, cen, [&](int k) -> double { return col[k * LS]; });
         }
     }
+}
+
+__device__ __forceinline__ void lw_cp_async8(double* dst_smem, const double* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int n = valid ? 8 : 0;                         // 0 source bytes: the destination is zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(d), "l"(src), "r"(n) : "memory");
 }
 
 template <int LS, int MINB>
 __global__ void __launch_bounds__(LT_THREADS, MINB) kf_lift_stream_kernel(const KfLiftTileArgs a) {
     extern __shared__ __align__(16) double lt_smem[];
+    const int nrows_in = a.nv + a.m + a.nw;
     double* sh = lt_smem;                              // [max_slots][LS]; slots 0 .. nv-1 are the variables
     double* su = sh + (size_t)a.max_slots * LS;        // [m + nw][LS]   inputs u, then loads w, of the tile
-    LtOp* sop = reinterpret_cast<LtOp*>(su + (size_t)(a.m + a.nw) * LS);   // [nops slot ops | nst row ops]
-    const double** inrow = reinterpret_cast<const double**>(sop + a.max_ops);   // [nv + m + nw] first element of every input row
+    double* stage = su + (size_t)(a.m + a.nw) * LS;    // [nv + m + nw][LS]  landing buffer of the NEXT tile's inputs (cp.async)
+    double* scen = stage + (size_t)nrows_in * LS;      // [ncent] gaussian centres (when they fit)
+    LtOp* sop = reinterpret_cast<LtOp*>(scen + a.ncent);                        // [max_ops] slot ops in level order
+    LtRop* srop = reinterpret_cast<LtRop*>(sop + a.max_ops);                    // [max_nst] packed row ops
+    const double** inrow = reinterpret_cast<const double**>(srop + a.max_nst);  // [nv + m + nw] first element of every input row
     __shared__ LtGroup grp;
     const int tid = threadIdx.x;
     const int side = blockIdx.y / a.ngroups, g = blockIdx.y % a.ngroups;
     const long long ntiles = (a.M + LS - 1) / LS;
-    const int nrows_in = a.nv + a.m + a.nw;
     if (tid == 0) grp = a.groups[g];
     for (int k = tid; k < nrows_in; k += LT_THREADS) {
         const double* r;
@@ -381,50 +397,41 @@ __global__ void __launch_bounds__(LT_THREADS, MINB) kf_lift_stream_kernel(const 
         inrow[k] = r;
     }
     __syncthreads();
-    for (int e = tid; e < grp.nops + grp.nst; e += LT_THREADS) sop[e] = a.gops[grp.op_off + e];
-    // inputs: value (row k = tid / LS + i * (LT_THREADS / LS), snapshot tid % LS) of a tile goes to register i
+    for (int e = tid; e < grp.nops; e += LT_THREADS) sop[e] = a.gops[grp.op_off + e];
+    for (int e = tid; e < grp.nst; e += LT_THREADS) reinterpret_cast<unsigned long long*>(srop)[e] = a.rops[grp.row0 + e];
+    for (int e = tid; e < a.ncent; e += LT_THREADS) scen[e] = a.centres[e];
+    const double* cen = a.ncent > 0 ? scen : a.centres;
+    // inputs of a tile: (row k, snapshot sn) -> stage[k][sn], asynchronously; the tail of the last tile is zero-filled
     constexpr int KSTEP = LT_THREADS / LS;
     const int sn = tid & (LS - 1), k0 = tid / LS;
-    const bool use_pre = nrows_in <= LW_PRE * KSTEP;
-    auto fetch = [&](long long g0, int k) -> double {
+    auto fetch_tile = [&](long long g0) {
         const long long gs = g0 + sn;
-        return (k < nrows_in && gs < a.M) ? inrow[k][gs] : 0.0;     // the tail of the last tile is zero
+        const bool ok = gs < a.M;
+        for (int k = k0; k < nrows_in; k += KSTEP) lw_cp_async8(stage + k * LS + sn, inrow[k] + (ok ? gs : 0), ok);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto place = [&](int k, double v) {
-        if (k < nrows_in) (k < a.nv ? sh + k * LS : su + (k - a.nv) * LS)[sn] = v;
-    };
-    double pre[LW_PRE];
-    if (use_pre) {
-#pragma unroll
-        for (int i = 0; i < LW_PRE; ++i) pre[i] = fetch((long long)blockIdx.x * LS, k0 + i * KSTEP);
-    }
+    fetch_tile((long long)blockIdx.x * LS);
     constexpr int QS = LS / 4, NF = LT_THREADS / QS;   // threads per row, rows in flight per CTA
     const int t2 = (tid % QS) * 2, fs = tid / QS;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long g0 = tile * LS;
-        // ---- A: inputs of the tile into shared memory
-        if (use_pre) {
-#pragma unroll
-            for (int i = 0; i < LW_PRE; ++i) place(k0 + i * KSTEP, pre[i]);
-        } else {
-            for (int k = k0; k < nrows_in; k += KSTEP) place(k, fetch(g0, k));
-        }
+        // ---- A: the inputs that landed in the stage buffer -> variable slots and u / w rows
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        for (int k = k0; k < nrows_in; k += KSTEP) (k < a.nv ? sh + k * LS : su + (k - a.nv) * LS)[sn] = stage[k * LS + sn];
+        __syncthreads();
+        // the next tile of this CTA: in flight during the evaluation and the row phase
+        if (tile + gridDim.x < ntiles) fetch_tile((tile + gridDim.x) * LS);
         // ---- B: the features other features read, level by level, into their slots
         for (int l = 0; l < grp.nlevels; ++l) {
             const int first = grp.level_start[l], last = grp.level_start[l + 1];
             for (int e = first + fs; e < last; e += NF) {
                 const LtOp op = sop[e];
                 double v[4];
-                lq_eval<LS>(op, sh, t2, a.nv, a.centres, v);
+                lq_eval<LS>(op.kind, op.a, op.b, [&]() { return op.c; }, sh, t2, a.nv, cen, v);
                 lq_st<LS>(sh + op.j * LS, t2, v);
             }
             if (last > first) __syncthreads();
-        }
-        // inputs of this CTA's next tile: in flight during the row phase
-        if (use_pre && tile + gridDim.x < ntiles) {
-#pragma unroll
-            for (int i = 0; i < LW_PRE; ++i) pre[i] = fetch((tile + gridDim.x) * LS, k0 + i * KSTEP);
         }
         // ---- C: one row op per output row, evaluated in registers and stored with its blocks u_ka (w_kc psi)
         {
@@ -440,16 +447,19 @@ __global__ void __launch_bounds__(LT_THREADS, MINB) kf_lift_stream_kernel(const 
                     if (okB1) *reinterpret_cast<double2*>(dst + LS / 2) = make_double2(x[2], x[3]); else if (okB0) dst[LS / 2] = x[2];
                 }
             };
+            auto row = [&](int e, double (&v)[4]) {
+                const LtRop r = srop[e];
+                lq_eval<LS>(r.kind, r.a, r.b, [&]() { return __ldg(a.rconst + r.ci); }, sh, t2, a.nv, cen, v);
+            };
             double* base = a.out + (long long)(side ? (a.mode == 0 ? a.side_off : a.P) : 0) * a.ld + gA;
             const long long rstep = (long long)NF * a.ld, bstep = (long long)a.N * a.ld;
             double* dst = base + (long long)(grp.row0 + fs) * a.ld;
-            const LtOp* rop = sop + grp.nops;
             const int nku = (a.mode == 1 && a.model == KF_BILINEAR) ? a.m : 0;
             const int nw = a.mode == 1 ? a.nw : 0;
             if (nw == 0 && nku == 0) {
                 for (int e = fs; e < grp.nst; e += NF, dst += rstep) {
                     double v[4];
-                    lq_eval<LS>(rop[e], sh, t2, a.nv, a.centres, v);
+                    row(e, v);
                     put(dst, v);
                 }
             } else if (nw == 0 && nku <= 3) {                // u_k psi, the u_k quads in registers  (Ksysid.m:510-511)
@@ -461,7 +471,7 @@ __global__ void __launch_bounds__(LT_THREADS, MINB) kf_lift_stream_kernel(const 
                 }
                 for (int e = fs; e < grp.nst; e += NF, dst += rstep) {
                     double v[4];
-                    lq_eval<LS>(rop[e], sh, t2, a.nv, a.centres, v);
+                    row(e, v);
                     put(dst, v);
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__(LT_THREADS, MINB) kf_lift_stream_kernel(const 
                 // association (psi_L = [psi; w_c psi] first, Ksysid.m:594-599; then u_k psi_L, 510-511 / 604-605)
                 for (int e = fs; e < grp.nst; e += NF, dst += rstep) {
                     double v[4];
-                    lq_eval<LS>(rop[e], sh, t2, a.nv, a.centres, v);
+                    row(e, v);
                     for (int ka = 0; ka <= nku; ++ka)
                         for (int kc = 0; kc <= nw; ++kc) {
                             double x[4] = {v[0], v[1], v[2], v[3]}, f[4];
@@ -503,8 +513,9 @@ __global__ void __launch_bounds__(LT_THREADS, MINB) kf_lift_stream_kernel(const 
                 }
             }
         }
-        __syncthreads();
+        // (the barrier at the top of the next iteration separates this tile's readers from the next tile's writers)
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // launches the tile kernel if the program fits (levels, shared memory); returns false otherwise
@@ -595,43 +606,92 @@ bool lift_stream_launch(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, cudaStream_t
     if (!ctx->opt_lift_wide || a.n_pcs > 0 || (a.ld & 1) || (reinterpret_cast<unsigned long long>(a.out) & 15ull) || a.M < 256) return false;
     if (a.mode == 0 && nsides > 1 && (((long long)a.side_off * a.ld) & 1)) return false;
     const KfProgram& p = ctx->prog;
-    // tile width: 256-byte runs reach the full write rate only on 128-byte-aligned rows; otherwise 512-byte runs
+    if (p.ngauss > 65535) return false;
+    // tile width: 256-byte runs reach the full write rate only on 128-byte-aligned rows; otherwise 512-byte runs — unless the
+    // wider tile would split the dictionary into more groups (parents evaluated once per group)
     const bool aligned = (a.ld % 16 == 0) && (reinterpret_cast<unsigned long long>(a.out) % 128 == 0);
-    int ls = ctx->opt_lift_ls;
-    if (ls != 32 && ls != 64) ls = aligned ? 32 : 64;
     const int n = p.n_full();
-    const long long ntiles = (a.M + ls - 1) / ls;
-    // few tiles (a panel of the fit path, a short series): split the rows so that every SM has work
-    int max_rows = 0;
-    if (ntiles * nsides < 2LL * ctx->sm_count) {
-        const int parts = (int)((2LL * ctx->sm_count + ntiles * nsides - 1) / (ntiles * nsides));
-        max_rows = std::max(32, (n + parts - 1) / parts);
-    }
-    auto bytes = [&](int slots, int ops) {
-        return ((size_t)slots + (size_t)a.m + (size_t)a.nw) * ls * sizeof(double) + (size_t)ops * sizeof(LtOp) +
-               (size_t)(a.nv + a.m + a.nw) * sizeof(double*) + 64;
+    const int nin = a.nv + a.m + a.nw;
+    const double budget = std::max(16.0, ctx->opt_lift_smem_kb) * 1024.0;      // per CTA: 2 CTAs per SM
+    int ls = ctx->opt_lift_ls, max_rows = 0, slots_target = 0;
+    const bool ls_auto = ls != 32 && ls != 64;
+    if (ls_auto) ls = aligned ? 32 : 64;
+    auto plan = [&](int w) {
+        const long long ntiles = (a.M + w - 1) / w;
+        // few tiles (a panel of the fit path, a short series): split the rows so that every SM has work
+        max_rows = 0;
+        if (ntiles * nsides < 2LL * ctx->sm_count) {
+            const int parts = (int)((2LL * ctx->sm_count + ntiles * nsides - 1) / (ntiles * nsides));
+            max_rows = std::max(32, (n + parts - 1) / parts);
+        }
+        slots_target = std::max(p.nv + 8, (int)((budget - 8.0 * std::min(n, max_rows > 0 ? max_rows : n)) / (w * sizeof(double))) - a.m - a.nw - nin);
     };
-    const double budget = std::max(16.0, ctx->opt_lift_smem_kb) * 1024.0;      // slots per CTA: >= 3 CTAs per SM by default
-    const int slots_target = std::max(p.nv + 8, (int)(budget / (ls * sizeof(double))) - a.m - a.nw);
+    plan(ls);
+    if (ls_auto && ls == 64) {
+        // cached decision per (program, budget): does the 64-wide plan need more groups than the 32-wide one?
+        const unsigned long long pk[3] = {ctx->prog_gen, (unsigned long long)budget, (unsigned long long)(a.m + a.nw)};
+        if (!std::equal(pk, pk + 3, ctx->lt_plan_key)) {
+            std::vector<LtOp> ops_tmp;
+            std::vector<LtGroup> g64, g32;
+            const bool ok64 = kf_build_lift_rowgroups(p, slots_target, 0, ops_tmp, g64);
+            const int st64 = slots_target;
+            plan(32);
+            const bool ok32 = kf_build_lift_rowgroups(p, slots_target, 0, ops_tmp, g32);
+            ctx->lt_plan_narrow = ok32 && (!ok64 || g32.size() < g64.size());
+            std::copy(pk, pk + 3, ctx->lt_plan_key);
+            (void)st64;
+        }
+        ls = ctx->lt_plan_narrow ? 32 : 64;
+        plan(ls);
+    }
+    auto bytes = [&](int slots, int ops, int nst, int ncent) {
+        return ((size_t)slots + (size_t)a.m + (size_t)a.nw + (size_t)nin) * ls * sizeof(double) + (size_t)ncent * sizeof(double) +
+               (size_t)ops * sizeof(LtOp) + (size_t)nst * sizeof(LtRop) + (size_t)nin * sizeof(double*) + 64;
+    };
     {
         const unsigned long long key[4] = {ctx->prog_gen, 1ull, (unsigned long long)slots_target, (unsigned long long)max_rows};
         const bool cached = std::equal(key, key + 4, ctx->lt_key) && !ctx->lt_groups.empty();
         if (!cached) {
             ctx->lt_key[0] = ~0ull;
-            ctx->lt_store.clear();
             if (!kf_build_lift_rowgroups(p, slots_target, max_rows, ctx->lt_ops, ctx->lt_groups)) return false;
             ctx->lt_max[0] = ctx->lt_max[1] = ctx->lt_max[2] = 0;
             for (const LtGroup& g : ctx->lt_groups) {
+                if (g.nslots > 65535) return false;
                 ctx->lt_max[0] = std::max(ctx->lt_max[0], g.nslots);
-                ctx->lt_max[1] = std::max(ctx->lt_max[1], g.nops + g.nst);
+                ctx->lt_max[1] = std::max(ctx->lt_max[1], g.nops);
                 ctx->lt_max[2] = std::max(ctx->lt_max[2], g.nst);
             }
+            // the row ops packed to 8 bytes (indexed by output row) | the constants of the primitive ops, in the `store` segment
+            std::vector<double> consts;
+            std::vector<LtRop> rops((size_t)n);
+            for (const LtGroup& g : ctx->lt_groups)
+                for (int e = 0; e < g.nst; ++e) {
+                    const LtOp& o = ctx->lt_ops[(size_t)g.rop_off + e];
+                    LtRop r{};
+                    r.kind = (unsigned char)o.kind; r.a = (unsigned short)o.a; r.b = (unsigned short)o.b;
+                    if (o.kind != KF_OP_MUL && o.kind != KF_OP_VAR && o.kind != KF_OP_GAUSS) {
+                        size_t ci = std::find(consts.begin(), consts.end(), o.c) - consts.begin();
+                        if (ci == consts.size()) consts.push_back(o.c);
+                        if (ci > 65535) return false;
+                        r.ci = (unsigned short)ci;
+                    }
+                    rops[(size_t)g.row0 + e] = r;
+                }
+            if (consts.empty()) consts.push_back(0.0);
+            static_assert(sizeof(LtStore) == 8 && sizeof(LtRop) == 8, "the packed row ops travel in the store segment");
+            ctx->lt_store.resize(rops.size() + consts.size());
+            std::memcpy(ctx->lt_store.data(), rops.data(), rops.size() * sizeof(LtRop));
+            std::memcpy(ctx->lt_store.data() + rops.size(), consts.data(), consts.size() * sizeof(double));
             if (!lift_groups_upload(ctx, st, rc)) return *rc != KF_OK;
             std::copy(key, key + 4, ctx->lt_key);
         }
         lift_groups_bind(ctx, a);
+        a.rops = reinterpret_cast<const unsigned long long*>(a.gstore);
+        a.rconst = reinterpret_cast<const double*>(a.gstore) + n;
     }
-    const size_t b = bytes(a.max_slots, a.max_ops);
+    const int ncent_all = p.ngauss * p.nv;
+    a.ncent = (ncent_all > 0 && bytes(a.max_slots, a.max_ops, a.max_nst, ncent_all) <= (size_t)std::max(budget, 100.0 * 1024)) ? ncent_all : 0;
+    const size_t b = bytes(a.max_slots, a.max_ops, a.max_nst, a.ncent);
     if (b > 200 * 1024) return false;                    // does not fit: the narrow kernel takes it
     if (ctx->opt_lift_minb >= 3)
         return ls == 64 ? lift_stream_launch_ls<64, 3>(ctx, a, nsides, b, st, rc) : lift_stream_launch_ls<32, 3>(ctx, a, nsides, b, st, rc);

@@ -37,9 +37,9 @@ for name, fn, nbytes in (("fill_write_only", lambda: buf.fill_(1.5), 8.0 * (1 <<
 out["calibration_GB_s"] = cal
 print(cal, flush=True)
 del buf, buf2
-VARIANTS = [(1, 0, 1, 64, 2), (1, 0, 1, 64, 3), (1, 32, 1, 64, 2), (1, 64, 1, 64, 2), (1, 64, 1, 64, 3), (1, 0, 1, 32, 3), (1, 0, 1, 100, 2), (1, 0, 0, 64, 2), (0, 0, 0, 64, 2)]
+VARIANTS = [(1, 0, 1, 110, 2), (1, 32, 1, 110, 2), (1, 64, 1, 110, 2), (1, 0, 1, 72, 3), (1, 0, 0, 64, 2)]
 if len(sys.argv) > 1 and sys.argv[1] == "short":
-    VARIANTS = [(1, 0, 1, 64, 2), (1, 0, 0, 64, 2)]
+    VARIANTS = [(1, 0, 1, 110, 2), (1, 0, 0, 64, 2)]
 cases = [("poly4_nv12_bilinear_m3", ["poly"], [4], None, 12, 3, "bilinear", 133000),
          ("poly3_nv12_linear_m3", ["poly"], [3], None, 12, 3, "linear", 1050000),
          ("config5_poly3_gauss569_bilinear", ["poly", "gaussian"], [3, 569], 2 * rng.random((12, 569)) - 1, 12, 3, "bilinear", 133000),
@@ -76,7 +76,7 @@ for name, types, degs, cen, nz, m, model, M in cases:
     fit.set_option("lift_ls", 0)
     fit.set_option("lift_tile", 1)
     fit.set_option("lift_wide", 1)
-    fit.set_option("lift_smem_kb", 64)
+    fit.set_option("lift_smem_kb", 110)
     fit.set_option("lift_minb", 2)
     print(rec, flush=True)
     out["cases"].append(rec)

@@ -11,7 +11,7 @@ dev = torch.device("cuda", 0)
 fit = koopfit.Fitter(0)
 rng = np.random.default_rng(2)
 M, nz, m = 65536, 12, 3
-kbs = [float(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["64"])]
+kbs = [float(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["100"])]
 for types, degs, cen, model in ((["poly", "gaussian"], [3, 569], 2 * rng.random((12, 569)) - 1, "bilinear"), (["poly"], [4], None, "bilinear"),
                                 (["poly"], [3], None, "linear")):
     basis = koopfit.Basis(types, degs, nz, centres=cen)
