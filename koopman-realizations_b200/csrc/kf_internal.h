@@ -170,7 +170,7 @@ struct kf_ctx {
     KfBuf d_ops, d_centres, d_pcs, d_panel[KF_MAX_PIPES], d_full, d_tasks[2], d_tma_tasks[2], d_accum, d_tilemeta;
     CUtensorMap tmap[2];            // tensor maps of the two panels (SWIZZLE_128B, box 16 x 64)
     KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3, d_Kt;
-    int opt_lift_panel_fit = 0;          // fit path: lift the panel with the shared-memory tile evaluator instead of the level kernel
+    int opt_lift_panel_fit = 1;          // fit path: lift the panel with the shared-memory tile evaluator instead of the level kernel
     int opt_lift_wide = 1;               // materialising lift: wide tiles (32 / 64 snapshots: long DRAM runs, table-free stores)
     int opt_lift_minb = 2;               // ... resident CTAs per SM the kernel is compiled for (2: 128 registers, 3: 80)
     double opt_lift_smem_kb = 110;       // ... shared memory per CTA (decides the size of the feature groups and the CTAs per SM)
