@@ -901,17 +901,19 @@ int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* sol
     // optional materialised regressors (koopData.Px / Py, Ksysid.m:1085-1086)
     if (out->Px || out->Py) {
         const int P = ctx->lay.P;
-        KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
+        const long long ldq = kf_qr_ld(M);       // rows padded with zeros to a multiple of 64 (blocked QR, aligned operand rows)
+        KF_CUDA(ctx, ctx->d_qr.ensure((size_t)ldq * 2 * P * sizeof(double)));
         KfLiftArgs a = lift_args_of(ctx, prob);
         a.N = ctx->lay.N;
         if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * M * sizeof(double)));
         a.full = ctx->d_full.as<double>();
-        KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, M, ctx->stream));
-        const size_t w = (size_t)M * sizeof(double);
-        if (out->Px) KF_CUDA(ctx, cudaMemcpy2DAsync(out->Px + host_row0, (size_t)host_ld * sizeof(double), ctx->d_qr.p, w, w, P,
+        if (ldq > M) KF_CUDA(ctx, cudaMemset2DAsync(ctx->d_qr.as<double>() + M, (size_t)ldq * sizeof(double), 0, (size_t)(ldq - M) * sizeof(double), 2 * (size_t)P, ctx->stream));
+        KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, ldq, ctx->stream));
+        const size_t w = (size_t)M * sizeof(double), wq = (size_t)ldq * sizeof(double);
+        if (out->Px) KF_CUDA(ctx, cudaMemcpy2DAsync(out->Px + host_row0, (size_t)host_ld * sizeof(double), ctx->d_qr.p, wq, w, P,
                                                     cudaMemcpyDeviceToHost, ctx->stream));
-        if (out->Py) KF_CUDA(ctx, cudaMemcpy2DAsync(out->Py + host_row0, (size_t)host_ld * sizeof(double), ctx->d_qr.as<double>() + (size_t)M * P,
-                                                    w, w, P, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out->Py) KF_CUDA(ctx, cudaMemcpy2DAsync(out->Py + host_row0, (size_t)host_ld * sizeof(double), ctx->d_qr.as<double>() + (size_t)ldq * P,
+                                                    wq, w, P, cudaMemcpyDeviceToHost, ctx->stream));
     }
     int method = solve->ls_method;
     if (solve->least_squares && method == KF_LS_AUTO) {
@@ -933,13 +935,15 @@ int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* sol
         const int P = ctx->lay.P, Pp = ctx->lay.Pp;
         cudaStream_t st = ctx->stream;
         KF_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-        KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * 2 * P * sizeof(double)));
+        const long long ldq = kf_qr_ld(M);
+        KF_CUDA(ctx, ctx->d_qr.ensure((size_t)ldq * 2 * P * sizeof(double)));
         if (!(out->Px || out->Py)) {   // not materialised above
             KfLiftArgs a = lift_args_of(ctx, prob);
             a.N = ctx->lay.N;
             if (ctx->prog.n_pcs) KF_CUDA(ctx, ctx->d_full.ensure((size_t)2 * a.n_full * M * sizeof(double)));
             a.full = ctx->d_full.as<double>();
-            KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, M, st));
+            if (ldq > M) KF_CUDA(ctx, cudaMemset2DAsync(ctx->d_qr.as<double>() + M, (size_t)ldq * sizeof(double), 0, (size_t)(ldq - M) * sizeof(double), 2 * (size_t)P, st));
+            KF_TRY(kf_launch_regressors(ctx, a, ctx->d_qr.as<double>(), nullptr, ldq, st));
         }
         KF_CUDA(ctx, ctx->d_K.ensure((size_t)Pp * Pp * sizeof(double)));
         KF_CUDA(ctx, ctx->d_misc.ensure(1024 + (size_t)Pp * sizeof(int)));
@@ -947,7 +951,7 @@ int kf_fit_device_pairs(kf_ctx* ctx, const kf_problem* prob, const kf_solve* sol
         int rank = 0;
         double minp = 0, maxp = 0;
         const int Pc = ctx->lay.Pc;
-        KF_TRY(kf_solve_qr_ls(ctx, M, P, Pc, ctx->d_qr.as<double>(), M, ctx->d_K.as<double>(), Pp, d_perm, &rank, &minp, &maxp, st));
+        KF_TRY(kf_solve_qr_ls(ctx, M, P, Pc, ctx->d_qr.as<double>(), ldq, ctx->d_K.as<double>(), Pp, d_perm, &rank, &minp, &maxp, st));
         out->info.rank = rank;
         out->info.ls_method_used = KF_LS_QR;
         out->info.min_pivot = minp;
@@ -1120,7 +1124,7 @@ void kf_destroy(kf_ctx* ctx) {
     KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_panel[2], &ctx->d_panel[3], &ctx->d_full,
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,
-                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups,
+                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups, &ctx->d_bqr,
                      &ctx->rf.d_S, &ctx->rf.d_St, &ctx->rf.d_Sp, &ctx->rf.d_G2C2, &ctx->rf.d_RP, &ctx->rf.d_Z, &ctx->rf.d_dense,
                      &ctx->rf.d_dense2, &ctx->rf.d_dense_x[0], &ctx->rf.d_dense_x[1]};
     kf_oz_destroy(ctx);
@@ -1423,16 +1427,19 @@ int kf_mldivide(kf_ctx* ctx, long long M, int P, int Pc, const double* A, const 
     KF_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int Pp = (int)kf_roundup(P, KF_BM);
-    KF_CUDA(ctx, ctx->d_qr.ensure((size_t)M * (P + Pc) * sizeof(double)));
+    const long long ldq = kf_qr_ld(M);
+    KF_CUDA(ctx, ctx->d_qr.ensure((size_t)ldq * (P + Pc) * sizeof(double)));
     KF_CUDA(ctx, ctx->d_K2.ensure((size_t)Pp * Pc * sizeof(double)));
     KF_CUDA(ctx, ctx->d_misc.ensure(1024 + (size_t)Pp * sizeof(int)));
     double* AB = ctx->d_qr.as<double>();
-    KF_CUDA(ctx, cudaMemcpyAsync(AB, A, (size_t)M * P * sizeof(double), cudaMemcpyHostToDevice, st));
-    KF_CUDA(ctx, cudaMemcpyAsync(AB + (size_t)M * P, B, (size_t)M * Pc * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (ldq > M) KF_CUDA(ctx, cudaMemset2DAsync(AB + M, (size_t)ldq * sizeof(double), 0, (size_t)(ldq - M) * sizeof(double), (size_t)(P + Pc), st));
+    KF_CUDA(ctx, cudaMemcpy2DAsync(AB, (size_t)ldq * sizeof(double), A, (size_t)M * sizeof(double), (size_t)M * sizeof(double), P, cudaMemcpyHostToDevice, st));
+    KF_CUDA(ctx, cudaMemcpy2DAsync(AB + (size_t)ldq * P, (size_t)ldq * sizeof(double), B, (size_t)M * sizeof(double), (size_t)M * sizeof(double), Pc,
+                                   cudaMemcpyHostToDevice, st));
     int* d_perm = reinterpret_cast<int*>(ctx->d_misc.as<char>() + 1024);
     int r = 0;
     double minp = 0, maxp = 0;
-    KF_TRY(kf_solve_qr_ls(ctx, M, P, Pc, AB, M, ctx->d_K2.as<double>(), Pp, d_perm, &r, &minp, &maxp, st));
+    KF_TRY(kf_solve_qr_ls(ctx, M, P, Pc, AB, ldq, ctx->d_K2.as<double>(), Pp, d_perm, &r, &minp, &maxp, st));
     KF_CUDA(ctx, cudaMemcpy2DAsync(X, (size_t)P * sizeof(double), ctx->d_K2.p, (size_t)Pp * sizeof(double), (size_t)P * sizeof(double), Pc,
                                    cudaMemcpyDeviceToHost, st));
     if (perm) KF_CUDA(ctx, cudaMemcpyAsync(perm, d_perm, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
@@ -1490,6 +1497,9 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "as_frac") ctx->opt_as_frac = value;
     else if (n == "lift_tile") ctx->opt_lift_tile = (int)value;
     else if (n == "lift_ls") ctx->opt_lift_ls = (int)value;
+    else if (n == "qr_blocked") ctx->opt_qr_blocked = (int)value;
+    else if (n == "qr_nb") ctx->opt_qr_nb = (int)value;
+    else if (n == "qr_ksplit") ctx->opt_qr_ksplit = (int)value;
     else if (n == "lift_wide") ctx->opt_lift_wide = (int)value;
     else if (n == "lift_smem_kb") ctx->opt_lift_smem_kb = value;
     else if (n == "lift_minb") ctx->opt_lift_minb = (int)value;

@@ -42,6 +42,12 @@ __global__ void __launch_bounds__(KF_GEMM_THREADS, GramCfg::MINB) kf_gemm_grid_k
     t.out = g.out + (long long)tm * KF_CTA_M * g.ldm + (long long)tn * KF_CTA_N * g.ldn;
     t.lda = g.lda; t.ldb = g.ldb; t.ldm = g.ldm; t.ldn = g.ldn;
     t.k0 = g.k0; t.k1 = g.k1;
+    if (gridDim.z > 1) {      // split-K: chunk z of the k range (multiples of KF_BK) -> slab z
+        const int kc = ((g.k1 - g.k0 + (int)gridDim.z - 1) / (int)gridDim.z + KF_BK - 1) / KF_BK * KF_BK;
+        t.k0 = g.k0 + (int)blockIdx.z * kc;
+        t.k1 = min(g.k1, t.k0 + kc);
+        t.out += (long long)blockIdx.z * g.slab;
+    }
     t.a_rows = min(KF_CTA_M, g.m - tm * KF_CTA_M);
     t.b_rows = min(KF_CTA_N, g.n - tn * KF_CTA_N);
     t.alpha = g.alpha;
@@ -124,6 +130,13 @@ int kf_launch_gemm_grid(kf_ctx* ctx, const KfGemmGrid& g, cudaStream_t st) {
     if (g.m <= 0 || g.n <= 0 || g.k1 <= g.k0) return KF_OK;
     KF_CUDA(ctx, ensure_attrs(ctx));
     dim3 grid((g.n + KF_CTA_N - 1) / KF_CTA_N, (g.m + KF_CTA_M - 1) / KF_CTA_M);
+    if (g.ksplit > 1) {
+        if (g.ksplit != kf_gemm_ksplit(g.k1 - g.k0, g.ksplit) || g.accumulate) {     // an empty chunk would leave its slab unwritten
+            ctx->err = "kf_launch_gemm_grid: ksplit must come from kf_gemm_ksplit and accumulate must be 0";
+            return KF_EINVAL;
+        }
+        grid.z = g.ksplit;
+    }
     kf_gemm_grid_kernel<<<grid, KF_GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
     KF_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

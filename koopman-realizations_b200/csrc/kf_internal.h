@@ -171,9 +171,13 @@ struct kf_ctx {
     CUtensorMap tmap[2];            // tensor maps of the two panels (SWIZZLE_128B, box 16 x 64)
     KfBuf d_G, d_C, d_K, d_W, d_in, d_misc, d_qr, d_tmp, d_K2, d_K3, d_Kt;
     int opt_lift_panel_fit = 1;          // fit path: lift the panel with the shared-memory tile evaluator instead of the level kernel
+    int opt_qr_blocked = 1;              // QRCP route: blocked Householder QR of the tall matrix first (BLAS-3), pivoted QR of its R factor after
+    int opt_qr_ksplit = 64;              // ... two-level summation of the products over the rows: number of k chunks (1: off)
+    int opt_qr_nb = 64;                  // ... panel width (32 | 64 | 128)
     int opt_lift_wide = 1;               // materialising lift: wide tiles (32 / 64 snapshots: long DRAM runs, table-free stores)
     int opt_lift_minb = 2;               // ... resident CTAs per SM the kernel is compiled for (2: 128 registers, 3: 80)
     double opt_lift_smem_kb = 110;       // ... shared memory per CTA (decides the size of the feature groups and the CTAs per SM)
+    KfBuf d_bqr;                         // blocked QR: V panel, S, T, W, W2, tau
     KfBuf d_lift_groups;                 // feature groups of the materialising lift (ops | store lists | group records)
     KfBuf d_series;                      // raw merged series t | y | u and the scale factors (kf_fit_series)
     KfBuf d_as_mat, d_as_aux, d_as_ws;   // active-set QP solver: pattern/solution matrices, index lists, Cholesky factors
@@ -274,8 +278,16 @@ struct KfGemmGrid {
     int k0, k1;
     double alpha; int accumulate;
     int lower_only;    // 1: skip tiles strictly above the diagonal (tn > tm)
+    int ksplit;        // > 1 (kf_launch_gemm_grid, accumulate = 0): the k range is cut into ksplit chunks, chunk z writes its partial
+    long long slab;    //     product to out + z * slab; the caller sums the slabs (kf_reduce_slabs) — a two-level summation
 };
 int kf_launch_gemm_grid(kf_ctx* ctx, const KfGemmGrid& g, cudaStream_t st);
+// number of non-empty k chunks (multiples of KF_BK) when a range of K is cut into about `want` pieces
+inline int kf_gemm_ksplit(int K, int want) {
+    if (want <= 1 || K <= KF_BK) return 1;
+    const int kc = (int)kf_roundup((K + want - 1) / want, KF_BK);
+    return (K + kc - 1) / kc;
+}
 int kf_launch_gemm_bkmajor(kf_ctx* ctx, const KfGemmGrid& g, cudaStream_t st);   // B stored k-major: B[k * ldb + n]
 
 // lift.cu
@@ -320,7 +332,9 @@ int kf_rf_gather_rows(kf_ctx* ctx, const double* S, const int* d_perm, int P, in
 int kf_rf_update_basis(kf_ctx* ctx, int P, int Pp, double* W, const int* d_perm, int r, double* S, double* Sp_out, cudaStream_t st);
 int kf_pchol_solve(kf_ctx* ctx, int P, int Pp, int ncols, double* W, const double* C, double* K, const int* d_perm, int r, int scatter,
                    cudaStream_t st);
-// Householder QRCP basic solution of A X = B;  AB = [A | B] (M x (P+Pc), ld = ldab) is overwritten
+// Householder QRCP basic solution of A X = B;  AB = [A | B] (M x (P+Pc), ld = ldab) is overwritten.  ldab = kf_qr_ld(M) with the
+// rows [M, ldab) ZERO enables the blocked route (stage 1: blocked Householder QR on the DMMA GEMMs; stage 2: QRCP of R).
+inline long long kf_qr_ld(long long M) { return kf_roundup(M, 64); }
 int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long long ldab, double* X, long long ldx,
                    int* d_perm, int* rank_out, double* min_piv, double* max_piv, cudaStream_t st);
 

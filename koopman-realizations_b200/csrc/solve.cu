@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(256) kf_qr_colnorms_kernel(const double* __res
 }
 
 // one CTA: pivot, swap, reflector (dlarfg) for column j
-__global__ void __launch_bounds__(1024) kf_qr_pivot_kernel(double* A, long long ld, long long M, int P, int j, double* vn,
+__global__ void __launch_bounds__(1024) kf_qr_pivot_kernel(double* A, long long ld, long long M, long long Mtol, int P, int j, double* vn,
                                                            int* perm, QrState* st) {
     if (st->done) return;
     __shared__ double sh[32];
@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(1024) kf_qr_pivot_kernel(double* A, long long 
                 st->r11 = nrm;
                 // eps(x) = distance to the next double above x
                 const double e = (nrm > 0.0) ? (__longlong_as_double(__double_as_longlong(nrm) + 1) - nrm) : 0.0;
-                st->tol = (double)(M > P ? M : P) * e;
+                st->tol = (double)(Mtol > P ? Mtol : P) * e;      // max(size(A)) * eps(|R_11|), the rows of the ORIGINAL matrix
             }
             if (!(nrm > st->tol)) {
                 st->rank = j;
@@ -943,6 +943,95 @@ __global__ void kf_qr_gather_rhs_kernel(const double* __restrict__ AB, long long
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage 1 of the blocked QRCP route: Householder QR WITHOUT pivoting of the tall matrix, 128 columns at a time, the trailing
+// matrix and the right-hand sides updated with the compact WY form on the DMMA GEMMs:  A = Q1 R1.  Column pivoting then only
+// has to look at R1 (P x P): R1 Pi = Q2 R2 gives A Pi = (Q1 Q2) R2, the same factorisation — column norms and every later
+// pivot decision are invariant under the orthogonal Q1 — with the BLAS-2 part on a matrix that no longer depends on M.
+constexpr int BQ_NB = 128;         // largest panel width
+
+// reflector of column j (rows j .. M-1) by one CTA: dlarfg; tau[j] = 0 for a zero tail
+__device__ void bqr_house(double* cj, long long M, int j, double* tau, double* sh) {
+    const int tid = threadIdx.x;
+    double s = 0.0;
+    for (long long i = j + 1 + tid; i < M; i += blockDim.x) s = fma(cj[i], cj[i], s);
+    const double xnorm2 = block_sum(s, sh);
+    const double alpha = cj[j];
+    double t = 0.0, beta = alpha, scale = 0.0;
+    if (xnorm2 > 0.0) {
+        beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+        t = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+    }
+    __syncthreads();
+    for (long long i = j + 1 + tid; i < M; i += blockDim.x) cj[i] *= scale;
+    if (tid == 0) { cj[j] = beta; tau[j] = t; }
+}
+__global__ void __launch_bounds__(1024) kf_bqr_house_kernel(double* A, long long ld, long long M, int j, double* tau) {
+    __shared__ double sh[32];
+    bqr_house(A + (long long)j * ld, M, j, tau, sh);
+}
+// apply H_j to the panel columns j+1 .. jend-1 (one CTA each); the CTA of column j+1 then forms ITS reflector, so a panel
+// costs one launch per column
+__global__ void __launch_bounds__(1024) kf_bqr_step_kernel(double* A, long long ld, long long M, int j, double* tau, int do_house) {
+    __shared__ double sh[32];
+    const int c = j + 1 + blockIdx.x;
+    const double* v = A + (long long)j * ld;
+    double* col = A + (long long)c * ld;
+    const double t = tau[j];
+    if (t != 0.0) {
+        double s = 0.0;
+        for (long long i = j + 1 + threadIdx.x; i < M; i += blockDim.x) s = fma(v[i], col[i], s);
+        const double w = t * (block_sum(s, sh) + col[j]);
+        for (long long i = j + 1 + threadIdx.x; i < M; i += blockDim.x) col[i] = fma(-w, v[i], col[i]);
+        __syncthreads();
+        if (threadIdx.x == 0) col[j] -= w;
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && do_house) bqr_house(col, M, c, tau, sh);
+}
+// explicit V of a panel: Vp (rows x nb, ld = rows) for the matrix rows q0 .. (q0 = p0 rounded down to a multiple of 64, roff = p0 - q0):
+// unit lower trapezoidal below row roff, zero above; columns >= jb zero
+__global__ void kf_bqr_vpanel_kernel(const double* __restrict__ A, long long ld, int p0, int roff, int jb, int nb, long long rows, double* Vp) {
+    const long long n = rows * nb;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e % rows - roff;             // row relative to p0
+        const int i = (int)(e / rows);
+        double v = 0.0;
+        if (i < jb && r >= i) v = (r == i) ? 1.0 : A[(long long)(p0 + i) * ld + p0 + r];
+        Vp[e] = v;
+    }
+}
+// T factor of the panel (dlarft, forward / columnwise): T(0:j, j) = -tau_j T(0:j, 0:j) S(0:j, j), S = Vp' Vp; T upper triangular
+__global__ void __launch_bounds__(BQ_NB) kf_bqr_tfactor_kernel(const double* __restrict__ S, const double* __restrict__ tau, int jb, int nb, double* T) {
+    extern __shared__ double sT[];      // [nb][nb + 1]
+    const int i = threadIdx.x;
+    const int lds = nb + 1;
+    for (int k = 0; k < nb; ++k) sT[i * lds + k] = 0.0;
+    __syncthreads();
+    for (int j = 0; j < jb; ++j) {
+        const double tj = tau[j];
+        double acc = 0.0;
+        if (i < j) {
+            for (int k = i; k < j; ++k) acc = fma(sT[i * lds + k], S[(long long)j * nb + k], acc);
+            acc *= -tj;
+        } else if (i == j) acc = tj;
+        __syncthreads();
+        if (i <= j) sT[i * lds + j] = acc;
+        __syncthreads();
+    }
+    for (int k = 0; k < nb; ++k) T[(long long)k * nb + i] = sT[i * lds + k];   // column-major T
+}
+// zero the part of the first `P` columns below the diagonal (the Householder vectors) within the top `rows` rows
+__global__ void kf_bqr_clear_lower_kernel(double* A, long long ld, int P, int rows) {
+    const long long n = (long long)P * rows;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e % rows), c = (int)(e / rows);
+        if (r > c) A[(long long)c * ld + r] = 0.0;
+    }
+}
+
 }  // namespace
 
 // backward substitution only:  U X = Z with U = L' stored mirrored in W
@@ -978,6 +1067,69 @@ static int trsm_backward(kf_ctx* ctx, const double* W, long long ld, int r, cons
     return KF_OK;
 }
 
+// stage 1 (see above): on return the top min(M, P) rows of AB hold [R1 | Q1' B]; *rows_out = rows the pivoted stage works on
+static int bqr_stage1(kf_ctx* ctx, long long Mp, int P, int Pc, double* AB, long long ld, int* rows_out, cudaStream_t st) {
+    const int ncols = P + Pc;
+    const int nfac = (int)std::min<long long>(Mp, P);
+    const int nb = (ctx->opt_qr_nb == 32 || ctx->opt_qr_nb == 64 || ctx->opt_qr_nb == 128) ? ctx->opt_qr_nb : 64;
+    // V'A2 and V'V contract over all rows: cut into chunks of ~256 rows summed in a second level (a single sequential
+    // accumulation over 1e4 rows cost a digit on config 2a / 2b: 7e-10 instead of 1e-10 against the extended-precision solution)
+    const int kmax = std::max(1, std::min(ctx->opt_qr_ksplit, 64));
+    KF_CUDA(ctx, ctx->d_bqr.ensure(((size_t)Mp * nb + (size_t)nb * nb * (kmax + 1) + (size_t)nb * ncols * (kmax + 1) + (size_t)P + 64) * sizeof(double)));
+    double* Vp = ctx->d_bqr.as<double>();
+    double* S = Vp + (size_t)Mp * nb;                    // kmax slabs
+    double* T = S + (size_t)nb * nb * kmax;
+    double* W = T + (size_t)nb * nb;                     // kmax slabs
+    double* W2 = W + (size_t)nb * ncols * kmax;
+    double* tau = W2 + (size_t)nb * ncols;
+    const size_t tsm = (size_t)nb * (nb + 1) * sizeof(double);
+    KF_CUDA(ctx, kf_ensure_smem(ctx, kf_bqr_tfactor_kernel, (size_t)BQ_NB * (BQ_NB + 1) * sizeof(double)));
+    for (int p0 = 0; p0 < nfac; p0 += nb) {
+        const int jb = std::min(nb, nfac - p0);
+        if (!(ctx->opt_qr_blocked == 2 && p0 > 0)) kf_bqr_house_kernel<<<1, 1024, 0, st>>>(AB, ld, Mp, p0, tau);
+        if (ctx->opt_qr_blocked == 2) {                  // diagnostic: every reflector applied to ALL remaining columns, no compact WY
+            for (int j = p0; j < p0 + jb; ++j)
+                if (ncols - j - 1 > 0) kf_bqr_step_kernel<<<ncols - j - 1, 1024, 0, st>>>(AB, ld, Mp, j, tau, (j + 1 < nfac) ? 1 : 0);
+            ctx->launches += jb;
+            continue;
+        }
+        for (int j = p0; j + 1 < p0 + jb; ++j) kf_bqr_step_kernel<<<p0 + jb - j - 1, 1024, 0, st>>>(AB, ld, Mp, j, tau, 1);
+        ctx->launches += jb;
+        const int c0 = p0 + jb, nc = ncols - c0;
+        if (nc <= 0) break;
+        const int q0 = p0 / 64 * 64, roff = p0 - q0;     // operand rows start at a multiple of 64 (GEMM tile / alignment); Vp is zero above p0
+        const long long rows = Mp - q0;
+        kf_bqr_vpanel_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(AB, ld, p0, roff, jb, nb, rows, Vp);
+        KfGemmGrid g{};
+        g.A = Vp; g.lda = rows; g.B = Vp; g.ldb = rows; g.out = S; g.ldm = 1; g.ldn = nb;         // S = Vp' Vp
+        g.m = nb; g.n = nb; g.k0 = 0; g.k1 = (int)rows; g.alpha = 1.0; g.accumulate = 0;
+        const int nz = kf_gemm_ksplit((int)rows, std::min<long long>(kmax, std::max<long long>(1, rows / 256)));
+        g.ksplit = nz; g.slab = (long long)nb * nb;
+        KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+        KF_TRY(kf_reduce_slabs(ctx, S, g.slab, nz, st));
+        kf_bqr_tfactor_kernel<<<1, nb, tsm, st>>>(S, tau + p0, jb, nb, T);
+        g.A = Vp; g.lda = rows; g.B = AB + (long long)c0 * ld + q0; g.ldb = ld; g.out = W; g.ldm = 1; g.ldn = nb;   // W = Vp' A2
+        g.m = nb; g.n = nc; g.k0 = 0; g.k1 = (int)rows;
+        g.ksplit = nz; g.slab = (long long)nb * nc;
+        KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+        KF_TRY(kf_reduce_slabs(ctx, W, g.slab, nz, st));
+        g.ksplit = 0; g.slab = 0;
+        g.A = T; g.lda = nb; g.B = W; g.ldb = nb; g.out = W2; g.ldm = 1; g.ldn = nb;              // W2 = T' W
+        g.m = nb; g.n = nc; g.k0 = 0; g.k1 = nb;
+        KF_TRY(kf_launch_gemm_grid(ctx, g, st));
+        g.A = W2; g.lda = nb; g.B = Vp; g.ldb = rows; g.out = AB + (long long)c0 * ld + q0; g.ldm = ld; g.ldn = 1;   // A2 -= Vp W2
+        g.m = nc; g.n = (int)rows; g.k0 = 0; g.k1 = nb; g.alpha = -1.0; g.accumulate = 1;
+        KF_TRY(kf_launch_gemm_bkmajor(ctx, g, st));
+        ctx->launches += 2;
+    }
+    KF_CUDA(ctx, cudaGetLastError());
+    kf_bqr_clear_lower_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(AB, ld, P, nfac);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    *rows_out = nfac;
+    return KF_OK;
+}
+
 int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long long ldab, double* X, long long ldx, int* d_perm,
                    int* rank_out, double* min_piv, double* max_piv, cudaStream_t st) {
     // X: Pp x Pc output (column-major, ld = ldx >= Pp), rows = original column index of A
@@ -994,12 +1146,20 @@ int kf_solve_qr_ls(kf_ctx* ctx, long long M, int P, int Pc, double* AB, long lon
         KF_CUDA(ctx, cudaMemcpyAsync(d_perm, id.data(), sizeof(int) * P, cudaMemcpyHostToDevice, st));
         KF_CUDA(ctx, cudaStreamSynchronize(st));
     }
-    kf_qr_colnorms_kernel<<<P, 256, 0, st>>>(AB, ldab, M, vn);
-    const int steps = (int)std::min<long long>(M, P);
+    // tall problems: blocked unpivoted QR first, then the pivoted factorisation only sees R1 (P rows)
+    long long Mw = M;                                    // rows the pivoted stage works on
+    const long long Mp = kf_qr_ld(M);
+    if (ctx->opt_qr_blocked && ldab == Mp && P >= 2 * BQ_NB && M >= (long long)P + P / 2) {
+        int rows = 0;
+        KF_TRY(bqr_stage1(ctx, Mp, P, Pc, AB, ldab, &rows, st));
+        Mw = rows;
+    }
+    kf_qr_colnorms_kernel<<<P, 256, 0, st>>>(AB, ldab, Mw, vn);
+    const int steps = (int)std::min<long long>(Mw, P);
     const int ncols = P + Pc;
     for (int j = 0; j < steps; ++j) {
-        kf_qr_pivot_kernel<<<1, 1024, 0, st>>>(AB, ldab, M, P, j, vn, d_perm, d_state);
-        if (ncols - j - 1 > 0) kf_qr_apply_kernel<<<ncols - j - 1, 256, 0, st>>>(AB, ldab, M, P, j, vn, d_state);
+        kf_qr_pivot_kernel<<<1, 1024, 0, st>>>(AB, ldab, Mw, M, P, j, vn, d_perm, d_state);
+        if (ncols - j - 1 > 0) kf_qr_apply_kernel<<<ncols - j - 1, 256, 0, st>>>(AB, ldab, Mw, P, j, vn, d_state);
     }
     KF_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2LL * steps + 1;

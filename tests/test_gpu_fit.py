@@ -365,3 +365,29 @@ def test_materialised_regressors_wide_tiles(fitter, model, types, degs, nz, m, M
         assert np.array_equal(outs[0][:, :P], Px) and np.array_equal(outs[0][:, P:], Py)
     else:
         assert np.abs(outs[0][:, :P] - Px).max() < 1e-14 and np.abs(outs[0][:, P:] - Py).max() < 1e-14
+
+
+@pytest.mark.parametrize("M,P,Pc,dep", [(5000, 600, 37, 5), (3001, 256, 256, 0), (9000, 1100, 300, 40)])
+def test_blocked_qrcp_matches_unblocked(fitter, M, P, Pc, dep):
+    """Blocked route of kf_mldivide (stage 1: 128-column Householder panels + compact-WY updates on the DMMA GEMMs; stage 2:
+    column-pivoted QR of R1) against the column-by-column QRCP (option qr_blocked = 0) and the LAPACK oracle: same rank, same
+    basic set, the basic solution of MATLAB's A \\ B (Ksysid.m:1069, 1216)."""
+    rng = np.random.default_rng(M + P)
+    A = rng.standard_normal((M, P)) * np.logspace(0, -5, P)[None, :]        # graded columns: cond ~ 1e5+
+    idx = rng.choice(P, 3 * dep, replace=False).reshape(dep, 3)               # disjoint triples: no tied residuals between dependent columns
+    for i, j, k in idx:                                                       # exact dependencies -> rank P - dep
+        A[:, i] = 0.5 * A[:, j] - 2.0 * A[:, k]
+    B = rng.standard_normal((M, Pc))
+    Xo, info = O.mldivide(A, B, return_info=True)
+    res = {}
+    try:
+        for blocked in (1, 0):
+            fitter.set_option("qr_blocked", blocked)
+            res[blocked] = fitter.mldivide(A, B)
+    finally:
+        fitter.set_option("qr_blocked", 1)
+    (X1, r1, p1), (X0, r0, p0) = res[1], res[0]
+    assert r1 == r0 == info["rank"] == P - dep
+    assert set(p1[:r1].tolist()) == set(p0[:r0].tolist()) == set(info["perm"][:r1].tolist())
+    assert np.all(X1[p1[r1:]] == 0)
+    assert relF(X1, X0) < 1e-10 and relF(X1, Xo) < 1e-9
