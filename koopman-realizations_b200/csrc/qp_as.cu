@@ -17,6 +17,8 @@
 // vector is traversed in ascending order of t, each budget warm-started from the support of the previous one.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
 #include <numeric>
 
 #include "kf_internal.h"
@@ -78,6 +80,12 @@ __global__ void __launch_bounds__(AS_THREADS, MINB) kf_as_chol_kernel(const AsAr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col = a.cols[blockIdx.x];
     const int n = a.cnt[col];
+    // this column's a_j, b_j are rewritten on the new support at the end: clear what the old support left behind (columns whose
+    // support did not change are not launched at all and keep their a_j, b_j, s'a, s'b)
+    for (int i = tid; i < a.P; i += AS_THREADS) {
+        a.Aout[i + (long long)col * a.ld] = 0.0;
+        a.Bout[i + (long long)col * a.ld] = 0.0;
+    }
     if (n == 0) {
         if (tid == 0) { a.col_num[col] = 0.0; a.col_den[col] = 0.0; a.col_dead[col] = 0; }
         return;
@@ -397,7 +405,7 @@ __global__ void __launch_bounds__(256) kf_as_count_kernel(const double* A, const
 
 // K = A - lam B on the support; entries whose sign flipped leave (K = 0), dual violators enter with sign -sign(grad)
 __global__ void kf_as_apply_kernel(const double* A, const double* B, double* SG, const double* GA, const double* GB, const double* C, double* K,
-                                   long long ld, int P, AsCols cs, double lam, double rel) {
+                                   long long ld, int P, AsCols cs, double lam, double rel, int* chg) {
     const long long n = (long long)P * (cs.hi - cs.lo);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(e % P), c = cs.lo + (int)(e / P);
@@ -407,12 +415,64 @@ __global__ void kf_as_apply_kernel(const double* A, const double* B, double* SG,
         double k = 0.0;
         if (s != 0.0) {
             k = fma(-lam, B[o], A[o]);
-            if (!(k * s > 0.0)) { k = 0.0; SG[o] = 0.0; }
+            if (!(k * s > 0.0)) { k = 0.0; SG[o] = 0.0; chg[c] = 1; }
         } else {
             const double g = fma(-lam, GB[o], GA[o]) - C[o];
-            if (fabs(g) > lam * (1.0 + rel)) SG[o] = g > 0.0 ? -1.0 : 1.0;
+            if (fabs(g) > lam * (1.0 + rel)) { SG[o] = g > 0.0 ? -1.0 : 1.0; chg[c] = 1; }
         }
         K[o] = k;
+    }
+}
+
+// Diagnostic (option as_diag): how much of every column's factor would survive a step if the support were kept in order of
+// entry ("age") instead of ascending index — leaving entries invalidate the factor from their position on, entering ones
+// are appended.  birth[i][c] = step at which entry (i, c) joined the support (0: not in it).  stats += [flops of a full
+// refactorisation, flops with reuse, entering, leaving, columns whose support changed, columns]
+__global__ void __launch_bounds__(256) kf_as_diag_kernel(const double* A, const double* B, const double* SG, const double* GA, const double* GB,
+                                                         const double* C, long long ld, int P, AsCols cs, double lam, double rel, int stepno,
+                                                         int* birth, double* stats) {
+    const int c = cs.lo + blockIdx.x;
+    if (!cs.on(c)) return;
+    __shared__ int s_min, s_keep, s_n, s_in, s_out;
+    if (threadIdx.x == 0) { s_min = 0x7fffffff; s_keep = 0; s_n = 0; s_in = 0; s_out = 0; }
+    __syncthreads();
+    int* bc = birth + (long long)c * P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const long long o = i + (long long)c * ld;
+        const double sg = SG[o];
+        if (sg != 0.0) {
+            atomicAdd(&s_n, 1);
+            if (bc[i] == 0) bc[i] = 1;      // cold-start entries
+            const double k = fma(-lam, B[o], A[o]);
+            if (!(k * sg > 0.0)) { atomicMin(&s_min, bc[i]); atomicAdd(&s_out, 1); }
+        } else {
+            const double g = fma(-lam, GB[o], GA[o]) - C[o];
+            if (fabs(g) > lam * (1.0 + rel)) atomicAdd(&s_in, 1);
+        }
+    }
+    __syncthreads();
+    const int bmin = s_min;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const long long o = i + (long long)c * ld;
+        const double sg = SG[o];
+        if (sg != 0.0) {
+            const double k = fma(-lam, B[o], A[o]);
+            if (!(k * sg > 0.0)) bc[i] = 0;
+            else if (bc[i] < bmin) atomicAdd(&s_keep, 1);
+        } else {
+            const double g = fma(-lam, GB[o], GA[o]) - C[o];
+            if (fabs(g) > lam * (1.0 + rel)) bc[i] = stepno;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double n1 = (double)(s_n - s_out + s_in), keep = (double)s_keep;
+        atomicAdd(stats + 0, n1 * n1 * n1 / 3.0);
+        atomicAdd(stats + 1, (s_in + s_out) ? (n1 - keep) * keep * keep + (n1 * n1 * n1 - keep * keep * keep) / 3.0 : 0.0);
+        atomicAdd(stats + 2, (double)s_in);
+        atomicAdd(stats + 3, (double)s_out);
+        atomicAdd(stats + 4, (s_in + s_out) ? 1.0 : 0.0);
+        atomicAdd(stats + 5, 1.0);
     }
 }
 
@@ -492,7 +552,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     double* Bm = Am + mat;
     double* GA = Bm + mat;      // G A
     double* GB = GA + mat;      // G B
-    const size_t n_int = (size_t)P * P + 3ull * P + 8;
+    const size_t n_int = (size_t)P * P + 4ull * P + 8;
     const size_t n_dbl = 2ull * P + 8;
     KF_CUDA(ctx, ctx->d_as_aux.ensure(n_dbl * sizeof(double) + (size_t)(P + AS_NL + 2) * sizeof(long long) + n_int * sizeof(int) + 64));
     double* d_num = ctx->d_as_aux.as<double>();
@@ -504,6 +564,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     int* d_cnt = d_idx + (size_t)P * P;
     int* d_cols = d_cnt + P;
     int* d_dead = d_cols + P;
+    int* d_chg = d_dead + P;        // [column]: support changed since its last factorisation
 
     // workspace for the factors: bounded (option as_ws_gb, default 8 GB), columns are processed in chunks that fit
     size_t free_b = 0, total_b = 0;
@@ -530,7 +591,10 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return t[x] < t[y]; });
 
-    std::vector<int> h_cnt(P), h_cols(P);
+    KfBuf diag_birth;                     // option as_diag only
+    int diag_step = 0;
+    std::vector<int> h_cnt(P), h_cols(P), h_chg(P);
+    long long cols_factored = 0;
     std::vector<long long> h_off(P);
     unsigned long long h_counts[AS_NL];
     double lam_prev = 0.0, lam_now = 0.0;
@@ -557,12 +621,15 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     auto step = [&](double tb, double* Kout) -> int {
         kf_as_index_kernel<<<P, 256, 0, st>>>(SG, ld, P, cs, d_idx, d_cnt);
         KF_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
-        KF_CUDA(ctx, cudaMemsetAsync(Am + (size_t)cs.lo * ld, 0, (size_t)ncol * ld * sizeof(double), st));
-        KF_CUDA(ctx, cudaMemsetAsync(Bm + (size_t)cs.lo * ld, 0, (size_t)ncol * ld * sizeof(double), st));
+        KF_CUDA(ctx, cudaMemcpyAsync(h_chg.data(), d_chg, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
+        KF_CUDA(ctx, cudaMemsetAsync(d_chg, 0, sizeof(int) * P, st));
         KF_CUDA(ctx, cudaStreamSynchronize(st));
+        // only the columns whose support changed are factored again: a_j = G_SS^-1 c_S and b_j = G_SS^-1 s_S depend on the pattern
+        // alone (config 3a: about half of all column-steps are unchanged)
         int nown = 0;
         for (int j = cs.lo; j < cs.hi; ++j)
-            if (cs.on(j)) h_cols[nown++] = j;
+            if (cs.on(j) && (h_chg[j] || !ctx->opt_as_skip)) h_cols[nown++] = j;
+        cols_factored += nown;
         std::stable_sort(h_cols.begin(), h_cols.begin() + nown, [&](int x, int y) { return h_cnt[x] > h_cnt[y]; });   // heavy columns first
         AsArgs a{};
         a.G = G; a.ldg = ld; a.C = C; a.SG = SG; a.Aout = Am; a.Bout = Bm; a.ld = ld;
@@ -650,7 +717,25 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
                 changed = (long long)cnts[0];
             }
         }
-        kf_as_apply_kernel<<<egrid, 256, 0, st>>>(Am, Bm, SG, GA, GB, C, Kout, ld, P, cs, lam, rel);
+        if (ctx->opt_as_diag) {
+            if (!diag_birth.p) {
+                KF_CUDA(ctx, diag_birth.ensure((size_t)P * P * sizeof(int) + 8 * sizeof(double)));
+                KF_CUDA(ctx, cudaMemsetAsync(diag_birth.p, 0, diag_birth.bytes, st));
+            }
+            double* d_stats = reinterpret_cast<double*>(diag_birth.as<char>() + (size_t)P * P * sizeof(int));
+            kf_as_diag_kernel<<<ncol, 256, 0, st>>>(Am, Bm, SG, GA, GB, C, ld, P, cs, lam, rel, ++diag_step + 1, diag_birth.as<int>(), d_stats);
+            if (diag_step % 50 == 0) {
+                double hs[6];
+                KF_CUDA(ctx, cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+                KF_CUDA(ctx, cudaStreamSynchronize(st));
+                static auto t_start = std::chrono::steady_clock::now();
+                if (diag_step == 50) t_start = std::chrono::steady_clock::now();
+                fprintf(stderr, "[as_diag] +%.3f s ", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+                fprintf(stderr, "[as_diag] step %d: full %.3e flop, with age-ordered reuse %.3e (%.2fx), entering %.0f leaving %.0f, changed columns %.0f of %.0f\n",
+                        diag_step, hs[0], hs[1], hs[0] / std::max(hs[1], 1.0), hs[2], hs[3], hs[4], hs[5]);
+            }
+        }
+        kf_as_apply_kernel<<<egrid, 256, 0, st>>>(Am, Bm, SG, GA, GB, C, Kout, ld, P, cs, lam, rel, d_chg);
         KF_CUDA(ctx, cudaGetLastError());
         ctx->launches += 5;
         lam_now = lam;
@@ -665,6 +750,9 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     KF_CUDA(ctx, cudaMemcpyAsync(&cmax, d_scal, sizeof(double), cudaMemcpyDeviceToHost, st));
     KF_CUDA(ctx, cudaStreamSynchronize(st));
     kf_as_init_kernel<<<egrid, 256, 0, st>>>(C, cmax, SG, ld, P, Pp, cs);
+    KF_CUDA(ctx, cudaMemsetAsync(d_chg, 1, sizeof(int) * P, st));        // every column is new (any non-zero value is a flag)
+    KF_CUDA(ctx, cudaMemsetAsync(Am, 0, mat * sizeof(double), st));
+    KF_CUDA(ctx, cudaMemsetAsync(Bm, 0, mat * sizeof(double), st));
     ctx->launches += 2;
     lam_prev = cmax;
     // ---- the budgets, ascending.  The iteration is a contraction only while the pattern change per step is small enough
@@ -684,6 +772,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
             if (attempt) {
                 frac = std::max(0.5 * frac, 0.002);
                 KF_CUDA(ctx, cudaMemcpyAsync(SG, SG_save, mat * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                KF_CUDA(ctx, cudaMemsetAsync(d_chg, 1, sizeof(int) * P, st));      // the pattern was replaced wholesale
                 lam_prev = lam_save;
             }
             long long prev_changed = -1;
@@ -708,5 +797,6 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
         res[b].l1 = 0;
         res[b].objective = 0;
     }
+    diag_birth.release();
     return KF_OK;
 }

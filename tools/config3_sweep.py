@@ -13,6 +13,8 @@ snake = unpack(np.load(os.path.join(GOLDEN, "snake_data.npz")))
 fit = koopfit.Fitter(0)
 if os.environ.get("KF_AS_FRAC"):
     fit.set_option("as_frac", float(os.environ["KF_AS_FRAC"]))
+if os.environ.get("KF_AS_DIAG"):
+    fit.set_option("as_diag", 1)
 nb = int(os.environ.get("KF_SWEEP_N", "64"))
 lassos = np.logspace(-2, 2, 64)[:nb]
 ks = Ksysid(snake, model_type="bilinear", obs_type=["fourier"], obs_degree=[4], lasso=lassos, dim_red=False, fitter=fit)
