@@ -13,6 +13,8 @@ snake = unpack(np.load(os.path.join(GOLDEN, "snake_data.npz")))
 fit = koopfit.Fitter(0)
 if os.environ.get("KF_AS_FRAC"):
     fit.set_option("as_frac", float(os.environ["KF_AS_FRAC"]))
+for kv in filter(None, os.environ.get("KF_OPTS", "").split(",")):
+    fit.set_option(kv.split("=")[0], float(kv.split("=")[1]))
 if os.environ.get("KF_AS_DIAG"):
     fit.set_option("as_diag", 1)
 nb = int(os.environ.get("KF_SWEEP_N", "64"))
