@@ -809,12 +809,26 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
             }
             const bool split = active_set && !auto_split && ctx->qp_hi > ctx->qp_lo;     // caller's column partition across ranks
             if (active_set) {
-                const int rc_as = kf_solve_l1ball_as(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1,
+                // the columns are DEALT round-robin to the ranks (rank r: columns r, r + R, ...; as a contiguous block of a column-
+                // permuted C): the support sizes differ systematically between column ranges (config 3a: the psi and the u psi
+                // halves), so contiguous blocks of the original order leave ranks idle
+                const double* Cs = ctx->d_C.as<double>();
+                if (auto_split) {
+                    KF_CUDA(ctx, ctx->d_deal.ensure(mat));
+                    KF_TRY(kf_qp_deal_cols(ctx, ctx->d_C.as<double>(), ctx->d_deal.as<double>(), P, Pp, ctx->nranks, 1, st));
+                    Cs = ctx->d_deal.as<double>();
+                }
+                const int rc_as = kf_solve_l1ball_as(ctx, P, Pp, ctx->d_G.as<double>(), Cs, nb, tf.data(), c0, c1,
                                                      sv->qp_max_iter, Kt, qr.data(), st);
                 if (auto_split) { ctx->qp_lo = 0; ctx->qp_hi = 0; }
                 if (rc_as) return rc_as;
                 if (auto_split)
-                    for (int b = 0; b < nb; ++b) KF_TRY(kf_comm_gather_blocks(ctx, Kt + (size_t)b * Pp * Pp, goff.data(), gcnt.data(), st));
+                    for (int b = 0; b < nb; ++b) {
+                        double* Kb = Kt + (size_t)b * Pp * Pp;
+                        KF_TRY(kf_comm_gather_blocks(ctx, Kb, goff.data(), gcnt.data(), st));
+                        KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_deal.as<double>(), Kb, mat, cudaMemcpyDeviceToDevice, st));   // back to the original column order
+                        KF_TRY(kf_qp_deal_cols(ctx, ctx->d_deal.as<double>(), Kb, P, Pp, ctx->nranks, 0, st));
+                    }
             }
             else
                 KF_TRY(kf_solve_l1ball_multi(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1, sv->qp_max_iter,
@@ -1124,7 +1138,7 @@ void kf_destroy(kf_ctx* ctx) {
     KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_panel[2], &ctx->d_panel[3], &ctx->d_full,
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,
-                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups, &ctx->d_bqr,
+                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups, &ctx->d_bqr, &ctx->d_deal,
                      &ctx->rf.d_S, &ctx->rf.d_St, &ctx->rf.d_Sp, &ctx->rf.d_G2C2, &ctx->rf.d_RP, &ctx->rf.d_Z, &ctx->rf.d_dense,
                      &ctx->rf.d_dense2, &ctx->rf.d_dense_x[0], &ctx->rf.d_dense_x[1]};
     kf_oz_destroy(ctx);

@@ -177,6 +177,7 @@ struct kf_ctx {
     int opt_lift_wide = 1;               // materialising lift: wide tiles (32 / 64 snapshots: long DRAM runs, table-free stores)
     int opt_lift_minb = 2;               // ... resident CTAs per SM the kernel is compiled for (2: 128 registers, 3: 80)
     double opt_lift_smem_kb = 110;       // ... shared memory per CTA (decides the size of the feature groups and the CTAs per SM)
+    KfBuf d_deal;                        // lasso sweep split by columns: C with its columns dealt round-robin to the ranks / scratch
     KfBuf d_bqr;                         // blocked QR: V panel, S, T, W, W2, tau
     KfBuf d_lift_groups;                 // feature groups of the materialising lift (ops | store lists | group records)
     KfBuf d_series;                      // raw merged series t | y | u and the scale factors (kf_fit_series)
@@ -381,6 +382,7 @@ int kf_solve_l1ball_multi(kf_ctx* ctx, int P, int Pp, const double* G, const dou
 int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, int nb, const double* t, int fix_c0, int fix_c1,
                        int max_iter, double* K_all, KfQpResult* res, cudaStream_t st);
 int kf_qp_scale_free(kf_ctx* ctx, double* K, int P, int Pp, int fix_c0, int fix_c1, double s, cudaStream_t st);
+int kf_qp_deal_cols(kf_ctx* ctx, const double* src, double* dst, int P, int Pp, int R, int gather, cudaStream_t st);
 int kf_add_diag(kf_ctx* ctx, double* G, int Pp, int P, double shift, cudaStream_t st);
 int kf_qp_evaluate(kf_ctx* ctx, int P, int Pp, const double* G, const double* C, const double* K, int fix_c0, int fix_c1, double t_free,
                    KfQpResult* res, cudaStream_t st, int own_lo = 0, int own_hi = 0);

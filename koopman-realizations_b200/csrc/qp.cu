@@ -481,6 +481,26 @@ int kf_solve_l1ball_multi(kf_ctx* ctx, int P, int Pp, const double* G, const dou
 }
 
 // K(:, free columns) *= s   (feasibility to rounding after a solve)
+// dst(:, p) = src(:, r + k R) for p = lo_r + k (gather = 1: columns dealt round-robin into the ranks' contiguous blocks), or the
+// inverse dst(:, r + k R) = src(:, p) (gather = 0).  base / extra: block sizes of shard_bounds(P, r, R).
+__global__ void kf_qp_deal_cols_kernel(const double* __restrict__ src, double* __restrict__ dst, long long ld, int P, int R, int gather) {
+    const int p = blockIdx.x;                      // position in the dealt order
+    const int base = P / R, extra = P % R;
+    const int big = extra * (base + 1);
+    const int r = p < big ? p / (base + 1) : extra + (p - big) / max(base, 1);
+    const int k = p - (r * base + min(r, extra));
+    const int c = r + k * R;                       // original column
+    const double* s = src + (long long)(gather ? c : p) * ld;
+    double* d = dst + (long long)(gather ? p : c) * ld;
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) d[i] = s[i];
+}
+int kf_qp_deal_cols(kf_ctx* ctx, const double* src, double* dst, int P, int Pp, int R, int gather, cudaStream_t st) {
+    kf_qp_deal_cols_kernel<<<P, 256, 0, st>>>(src, dst, Pp, P, R, gather);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return KF_OK;
+}
+
 int kf_qp_scale_free(kf_ctx* ctx, double* K, int P, int Pp, int fix_c0, int fix_c1, double s, cudaStream_t st) {
     Scratch sc;
     KF_TRY(carve(ctx, Pp, 1, &sc));
