@@ -147,6 +147,14 @@ int kf_block_table(int type, int degree, int nv, int* rows, int* cols, int* tabl
  * V (rows x nv) -> Psi (rows x N), both column-major HOST buffers; runs on the GPU. */
 int kf_lift(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V, double* Psi);
 
+/* Principal components of the lifted points: replaces `[coeffs, ~, ~, ~, explained] = pca(Psi)` in the dim_red branch of
+ * get_econ_observables (Ksysid.m:1495-1517; lift_snapshots 1394-1432).  V (rows x nv, column-major HOST buffer) is lifted
+ * through the FULL dictionary of `basis` (no pcs); mu (n_full) = feature means, latent (n_full) = eigenvalues of the sample
+ * covariance in decreasing order, coeff (n_full x n_full, column-major) = principal directions with MATLAB's sign convention
+ * (largest component of every column positive).  Everything runs on the GPU: two lift passes (means, then the Gram of the
+ * CENTRED features on the DMMA GEMM) and a one-sided Jacobi eigensolver.  Any of mu / latent / coeff may be NULL. */
+int kf_pca(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V, double* mu, double* latent, double* coeff);
+
 /* ---- the fit ----------------------------------------------------------
  * Replaces Ksysid.get_Koopman (Ksysid.m:987-1092) + solve_KoopmanQP (1095-1176) and the
  * lasso loop of train_models (1370-1387): lifts once, accumulates G, C once, solves

@@ -173,6 +173,7 @@ def load():
         "kf_basis_dims": (i, [P(kf_basis), i, i, c_int_p, c_int_p, c_int_p]),
         "kf_block_table": (i, [i, i, i, c_int_p, c_int_p, c_int_p]),
         "kf_lift": (i, [vp, P(kf_basis), ll, c_double_p, c_double_p]),
+        "kf_pca": (i, [vp, P(kf_basis), ll, c_double_p, c_double_p, c_double_p, c_double_p]),
         "kf_fit": (i, [vp, P(kf_basis), P(kf_problem), P(kf_solve), P(kf_result)]),
         "kf_fit_dev": (i, [vp, P(kf_basis), P(kf_problem), P(kf_solve), P(kf_result)]),
         "kf_fit_series": (i, [vp, P(kf_basis), P(kf_series), P(kf_solve), P(kf_scale), P(kf_result)]),
@@ -213,7 +214,7 @@ def load():
 
 
 EXPORTS = ["kf_create", "kf_destroy", "kf_last_error", "kf_version", "kf_basis_dims", "kf_block_table",
-           "kf_lift", "kf_fit", "kf_fit_dev", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_mpc_costB_bilinear", "kf_set_qp_partition", "kf_mldivide", "kf_accumulate_dev", "kf_regressors_dev", "kf_lift_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
+           "kf_lift", "kf_pca", "kf_fit", "kf_fit_dev", "kf_fit_series", "kf_series_pairs", "kf_fit_batch", "kf_rollout", "kf_mpc_costB_bilinear", "kf_set_qp_partition", "kf_mldivide", "kf_accumulate_dev", "kf_regressors_dev", "kf_lift_dev", "kf_accum_buffer", "kf_solve_dev", "kf_sync",
            "kf_stream", "kf_counters", "kf_engine_info", "kf_last_times", "kf_set_option",
            "kf_create_multi", "kf_destroy_multi", "kf_multi_size", "kf_multi_ctx", "kf_multi_last_error", "kf_multi_set_option", "kf_fit_multi",
            "kf_comm_unique_id", "kf_comm_init_rank", "kf_comm_destroy", "kf_comm_info"]

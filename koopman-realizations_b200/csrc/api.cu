@@ -1138,7 +1138,7 @@ void kf_destroy(kf_ctx* ctx) {
     KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_panel[2], &ctx->d_panel[3], &ctx->d_full,
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,
-                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups, &ctx->d_bqr, &ctx->d_deal,
+                     &ctx->d_as_mat, &ctx->d_as_aux, &ctx->d_as_ws, &ctx->d_series, &ctx->d_lift_groups, &ctx->d_bqr, &ctx->d_deal, &ctx->d_pca,
                      &ctx->rf.d_S, &ctx->rf.d_St, &ctx->rf.d_Sp, &ctx->rf.d_G2C2, &ctx->rf.d_RP, &ctx->rf.d_Z, &ctx->rf.d_dense,
                      &ctx->rf.d_dense2, &ctx->rf.d_dense_x[0], &ctx->rf.d_dense_x[1]};
     kf_oz_destroy(ctx);
@@ -1209,6 +1209,20 @@ int kf_lift(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V,
     KF_CUDA(ctx, cudaMemcpyAsync(Psi, ctx->d_tmp.p, vout, cudaMemcpyDeviceToHost, ctx->stream));
     KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KF_OK;
+}
+
+int kf_pca(kf_ctx* ctx, const kf_basis* basis, long long rows, const double* V, double* mu, double* latent, double* coeff) {
+    if (!ctx) return KF_EINVAL;
+    if (rows < 2 || !V) {
+        ctx->err = "kf_pca: rows >= 2 and V required";
+        return KF_EINVAL;
+    }
+    KF_CUDA(ctx, cudaSetDevice(ctx->device));
+    KF_TRY(prepare_program(ctx, basis));
+    const size_t vin = (size_t)rows * ctx->prog.nv * sizeof(double);
+    KF_CUDA(ctx, ctx->d_in.ensure(vin));
+    KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, V, vin, cudaMemcpyHostToDevice, ctx->stream));
+    return kf_pca_points(ctx, rows, ctx->d_in.as<double>(), mu, latent, coeff);
 }
 
 int kf_accumulate_dev(kf_ctx* ctx, const kf_basis* basis, const kf_problem* prob, int reset) {

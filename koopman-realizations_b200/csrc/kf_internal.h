@@ -177,6 +177,8 @@ struct kf_ctx {
     int opt_lift_wide = 1;               // materialising lift: wide tiles (32 / 64 snapshots: long DRAM runs, table-free stores)
     int opt_lift_minb = 2;               // ... resident CTAs per SM the kernel is compiled for (2: 128 registers, 3: 80)
     double opt_lift_smem_kb = 110;       // ... shared memory per CTA (decides the size of the feature groups and the CTAs per SM)
+    int last_pca_sweeps = 0;
+    KfBuf d_pca;                         // PCA: lifted chunk, centred Gram (+ split-K slabs), Jacobi work matrices
     KfBuf d_deal;                        // lasso sweep split by columns: C with its columns dealt round-robin to the ranks / scratch
     KfBuf d_bqr;                         // blocked QR: V panel, S, T, W, W2, tau
     KfBuf d_lift_groups;                 // feature groups of the materialising lift (ops | store lists | group records)
@@ -312,6 +314,10 @@ void kf_program_levels(const KfProgram& p, std::vector<int>& order, std::vector<
 int kf_launch_lift(kf_ctx* ctx, const KfLiftArgs& a, cudaStream_t st);
 // the panel lift through the shared-memory tile evaluator; false: not applicable (use kf_launch_lift)
 bool kf_launch_lift_panel_tile(kf_ctx* ctx, const KfLiftArgs& a, cudaStream_t st, int* rc, long long limit = -1);
+int kf_launch_lift_points_chunk(kf_ctx* ctx, const KfOp* ops, const double* centres, int nv, int n_full, const double* V, long long total,
+                                long long c0, long long cnt, double* out, long long ldo, cudaStream_t st);
+// pca.cu: principal components of the lifted points (device eigensolver)
+int kf_pca_points(kf_ctx* ctx, long long rows, const double* d_V, double* mu, double* latent, double* coeff);
 // materialised lift of arbitrary points: V (rows x nv, ld=rows) -> Psi (rows x N, ld = ldo)
 int kf_launch_lift_points(kf_ctx* ctx, const KfOp* ops, const double* centres, const double* pcs, int nv, int n_full,
                           int n_pcs, const double* V, long long rows, double* full, double* out, long long ldo,

@@ -782,6 +782,35 @@ int kf_launch_lift(kf_ctx* ctx, const KfLiftArgs& a, cudaStream_t st) {
     return KF_OK;
 }
 
+// the points [c0, c0 + cnt) of V (total x nv, ld = total) -> out (N x cnt, ld = ldo); no dim_red
+int kf_launch_lift_points_chunk(kf_ctx* ctx, const KfOp* ops, const double* centres, int nv, int n_full, const double* V, long long total,
+                                long long c0, long long cnt, double* out, long long ldo, cudaStream_t st) {
+    if (cnt <= 0) return KF_OK;
+    if (ctx->opt_lift_tile) {
+        KfLiftTileArgs t{};
+        t.ops = ops; t.centres = centres; t.pcs = nullptr; t.order = ctx->d_order.as<int>();
+        t.nv = nv; t.n_full = n_full; t.n_pcs = 0; t.N = n_full;
+        t.nzeta = nv; t.m = 0; t.model = KF_NONLINEAR; t.mode = 0; t.P = t.N;
+        t.alpha = V + c0; t.beta = V + c0; t.u = V + c0; t.M = cnt; t.ldin = total; t.out = out; t.ld = ldo;
+        int rc = KF_OK;
+        if (lift_tile_launch(ctx, t, 1, st, &rc)) return rc;
+    }
+    KfLiftArgs a{};
+    a.ops = ops; a.centres = centres; a.pcs = nullptr; a.order = ctx->d_order.as<int>();
+    a.nv = nv; a.n_full = n_full; a.n_pcs = 0; a.N = n_full;
+    a.nzeta = nv; a.m = 0; a.model = KF_NONLINEAR;
+    a.alpha = V; a.beta = V; a.u = V;
+    if (c0 + cnt != total) {       // the level kernel uses M both as the input leading dimension and as the end of the data
+        ctx->err = "chunked point lift: this dictionary needs the level-by-level kernel, which only takes the last chunk";
+        return KF_EUNSUPPORTED;
+    }
+    a.M = total; a.start = c0; a.Mc = (int)cnt;
+    a.panel = out; a.ld = ldo; a.full = nullptr;
+    a.x_off = 0; a.y_off = 0; a.w_off = 0; a.nW = 0;
+    a.nsides = 1; a.extras = 0;
+    return kf_launch_lift(ctx, a, st);
+}
+
 int kf_launch_lift_points(kf_ctx* ctx, const KfOp* ops, const double* centres, const double* pcs, int nv, int n_full,
                           int n_pcs, const double* V, long long rows, double* full, double* out, long long ldo,
                           cudaStream_t st) {

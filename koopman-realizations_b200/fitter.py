@@ -103,6 +103,17 @@ class Fitter:
         self._check(self.lib.kf_lift(self.ctx, basis.ref(), rows, A.dptr(V), A.dptr(out)), "kf_lift")
         return out
 
+    def pca(self, basis, V):
+        """MATLAB `pca` of the lifted rows of V (Ksysid.m:1498) on the GPU: returns mu (n_full), latent (decreasing), coeff
+        (n_full x n_full, MATLAB sign convention).  `basis` must be the full dictionary (no pcs)."""
+        V = A.fcol(np.atleast_2d(V))
+        rows = V.shape[0]
+        nf, _, _ = self.dims(basis, "nonlinear", 0)
+        mu, latent = np.empty(nf), np.empty(nf)
+        coeff = np.empty((nf, nf), order="F")
+        self._check(self.lib.kf_pca(self.ctx, basis.ref(), rows, A.dptr(V), A.dptr(mu), A.dptr(latent), A.dptr(coeff)), "kf_pca")
+        return mu, latent, coeff
+
     # ------------------------------------------------------------------ the fit
     @staticmethod
     def _solve_struct(least_squares=True, ls_method="auto", pivot_tol=0.0, t=None, psd_shift="as_reference",

@@ -221,29 +221,13 @@ class Ksysid:
         return np.concatenate([z] + [u[..., k:k + 1] * z for k in range(u.shape[-1])], axis=-1)
 
     def _reduce_dimension(self):
-        """lift_snapshots + get_econ_observables with dim_red (Ksysid.m:1394-1432, 1495-1517).
-        The covariance of the lifted alpha snapshots comes from the same GPU lift + Gram pass: with the
-        constant observable last, G = Psi'Psi gives both sum(psi psi') and sum(psi)."""
+        """lift_snapshots + get_econ_observables with dim_red (Ksysid.m:1394-1432, 1495-1517): `pca` runs on the GPU."""
         print("Performing dimensional reduction...")
         sp = self.snapshotPairs
         m = self.params["m"]
-        # a 'nonlinear' pass over [alpha, u] (or alpha alone) accumulates Psi_full' Psi_full
-        if self.model_type == "nonlinear":
-            res = self.fitter.fit(self.basis, "nonlinear", sp["alpha"], sp["alpha"], sp["u"], want_gram=True, ls_method="gram")
-        else:
-            res = self.fitter.fit(self.basis, "nonlinear", sp["alpha"], sp["alpha"], np.zeros((sp["alpha"].shape[0], 0)),
-                                  want_gram=True, ls_method="gram")
-        G = res["G"]
-        M = sp["alpha"].shape[0]
-        mu = G[:, -1] / M                                   # last observable is the constant 1
-        cov = (G - M * np.outer(mu, mu)) / (M - 1)
-        lam, vec = np.linalg.eigh((cov + cov.T) / 2)
-        lam, vec = lam[::-1], vec[:, ::-1]
-        lam = np.maximum(lam, 0.0)
-        for j in range(vec.shape[1]):                       # MATLAB pca sign convention
-            i = np.argmax(np.abs(vec[:, j]))
-            if vec[i, j] < 0:
-                vec[:, j] = -vec[:, j]
+        # pca of the lifted [alpha, u] (nonlinear) or alpha points, on the GPU: means, centred Gram, Jacobi eigensolver (kf_pca)
+        V = np.concatenate([sp["alpha"], sp["u"]], axis=1) if self.model_type == "nonlinear" else sp["alpha"]
+        _, lam, vec = self.fitter.pca(self.basis, V)
         explained = 100.0 * lam / lam.sum()
         num_pcs = 1
         while explained[:num_pcs].sum() < 99:               # Ksysid.m:1501-1504

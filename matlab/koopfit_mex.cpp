@@ -13,6 +13,7 @@
 //   Kcell             = koopfit_mex('fit_batch', problems)       problems: struct array (alpha, beta, u, model_type, desc, opts)
 //   ysim              = koopfit_mex('rollout', desc, model_type, models, zeta0, u, nout)             val_* (Ksysid.m:1623-1879)
 //   Psi               = koopfit_mex('lift', desc, nv, V)                                             lift.econ_full
+//   [coeff, latent, mu] = koopfit_mex('pca', desc, nv, V)                                          pca(Psi) of dim_red (Ksysid.m:1498)
 //   X                 = koopfit_mex('mldivide', A, B)                                                A \ B (Ksysid.m:1216)
 //   B                 = koopfit_mex('mpc_costB', A, Bmodel, z, horizon)                              Kmpc.m:569-596
 //   koopfit_mex('set_option', name, value);   n = koopfit_mex('devices')
@@ -350,6 +351,25 @@ static void cmd_lift(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
     if (mxGetM(V) && kf_lift(ctx0(), &bs.b, (long long)mxGetM(V), mxGetPr(V), mxGetPr(plhs[0]))) mexErrMsgIdAndTxt("koopfit:lift", "%s", kf_last_error(ctx0()));
 }
 
+// [coeff, latent, mu] = koopfit_mex('pca', desc, nv, V): the pca call of get_econ_observables (Ksysid.m:1498) on the lifted rows of V
+static void cmd_pca(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    need(nrhs >= 4, "koopfit:args", "usage: [coeff, latent, mu] = koopfit_mex('pca', desc, nv, V)");
+    const int nv = (int)mxGetScalar(prhs[2]);
+    const mxArray* V = dbl(prhs[3], "V");
+    need((int)mxGetN(V) == nv && mxGetM(V) >= 2, "koopfit:args", "V must have nv columns and at least two rows");
+    Basis bs;
+    parse_basis(prhs[1], nv, bs);
+    int nf = 0;
+    if (kf_basis_dims(&bs.b, KF_NONLINEAR, 0, &nf, NULL, NULL)) mexErrMsgIdAndTxt("koopfit:basis", "%s", kf_last_error(NULL));
+    plhs[0] = mxCreateDoubleMatrix(nf, nf, mxREAL);
+    mxArray* latent = mxCreateDoubleMatrix(nf, 1, mxREAL);
+    mxArray* mu = mxCreateDoubleMatrix(1, nf, mxREAL);
+    if (kf_pca(ctx0(), &bs.b, (long long)mxGetM(V), mxGetPr(V), mxGetPr(mu), mxGetPr(latent), mxGetPr(plhs[0])))
+        mexErrMsgIdAndTxt("koopfit:pca", "%s", kf_last_error(ctx0()));
+    if (nlhs > 1) plhs[1] = latent; else mxDestroyArray(latent);
+    if (nlhs > 2) plhs[2] = mu; else mxDestroyArray(mu);
+}
+
 static void cmd_mldivide(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     need(nrhs >= 3, "koopfit:args", "usage: [X, rank] = koopfit_mex('mldivide', A, B)");
     const mxArray *A = dbl(prhs[1], "A"), *B = dbl(prhs[2], "B");
@@ -380,13 +400,14 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         mexLock();
         mexAtExit(at_exit);
     }
-    need(nrhs >= 1 && mxIsChar(prhs[0]), "koopfit:args", "first argument: 'fit' | 'fit_series' | 'fit_batch' | 'rollout' | 'lift' | 'mldivide' | 'mpc_costB' | 'set_option' | 'devices'");
+    need(nrhs >= 1 && mxIsChar(prhs[0]), "koopfit:args", "first argument: 'fit' | 'fit_series' | 'fit_batch' | 'rollout' | 'lift' | 'pca' | 'mldivide' | 'mpc_costB' | 'set_option' | 'devices'");
     const std::string cmd = str_of(prhs[0], "command");
     if (cmd == "fit") cmd_fit(nlhs, plhs, nrhs, prhs);
     else if (cmd == "fit_series") cmd_fit_series(nlhs, plhs, nrhs, prhs);
     else if (cmd == "fit_batch") cmd_fit_batch(nlhs, plhs, nrhs, prhs);
     else if (cmd == "rollout") cmd_rollout(nlhs, plhs, nrhs, prhs);
     else if (cmd == "lift") cmd_lift(nlhs, plhs, nrhs, prhs);
+    else if (cmd == "pca") cmd_pca(nlhs, plhs, nrhs, prhs);
     else if (cmd == "mldivide") cmd_mldivide(nlhs, plhs, nrhs, prhs);
     else if (cmd == "mpc_costB") cmd_mpc_costB(nlhs, plhs, nrhs, prhs);
     else if (cmd == "set_option") {

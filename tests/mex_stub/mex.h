@@ -32,6 +32,7 @@ void mxSetCell(mxArray*, mwIndex, mxArray*);
 void mxSetField(mxArray*, mwIndex, const char*, mxArray*);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray* mxCreateDoubleScalar(double);
+void mxDestroyArray(mxArray*);
 mxArray* mxCreateNumericArray(mwSize, const mwSize*, mxClassID, mxComplexity);
 mxArray* mxCreateStructMatrix(mwSize, mwSize, int, const char**);
 mxArray* mxCreateCellMatrix(mwSize, mwSize);

@@ -59,7 +59,40 @@ def test_default_dim_red_reproduces_golden_Z(fitter, arm_data, golden_Z):
     Y, Zg = golden_Z["lin_Y"], golden_Z["lin_Z"]
     Z = ks.lift["econ_full"](ks.scaledown["y"](Y[:Zg.shape[0]]))
     assert Z.shape == Zg.shape
-    assert np.abs(Z - Zg).max() < 1e-9
+    # round 1 (covariance as G - M mu mu' + host eigh) needed 1e-9 here; the device pca (centred Gram + Jacobi) is at the oracle's level
+    assert np.abs(Z - Zg).max() < 1e-11
+
+
+@pytest.mark.parametrize("types,degs,nv,M", [(["poly"], [3], 6, 5000), (["poly", "gaussian", "fourier_sparser"], [2, 20, 2], 4, 40000),
+                                             (["hermite"], [2], 3, 300)])
+def test_device_pca_matches_centred_svd(fitter, types, degs, nv, M):
+    """kf_pca (means + centred Gram on the DMMA GEMM + one-sided Jacobi on the device) against MATLAB's pca algorithm — the SVD of
+    the centred lifted data (Ksysid.m:1498): variances, principal directions (sign convention included) and means; odd and even
+    dictionary sizes, several chunks of points."""
+    rng = np.random.default_rng(M)
+    V = (2 * rng.random((M, nv)) - 1) * np.linspace(1.0, 0.2, nv)[None, :]
+    cen = 2 * rng.random((nv, 20)) - 1 if "gaussian" in types else None
+    basis = koopfit.Basis(types, degs, nv, cen)
+    prog = O.build_program(types, degs, nv, cen)
+    Psi = O.lift(prog, V)
+    mu, latent, coeff = fitter.pca(basis, V)
+    n = Psi.shape[1]
+    assert latent.shape == (n,) and coeff.shape == (n, n)
+    mu_o = Psi.mean(axis=0)
+    assert np.abs(mu - mu_o).max() < 1e-13
+    Xc = Psi - mu_o
+    _, sv, Vt = np.linalg.svd(Xc, full_matrices=False)
+    lat_o = sv ** 2 / (M - 1)
+    assert np.all(np.diff(latent) <= 0)
+    assert np.abs(latent - lat_o).max() < 1e-13 * lat_o[0]
+    assert np.abs(coeff.T @ coeff - np.eye(n)).max() < 1e-13
+    cov = Xc.T @ Xc / (M - 1)
+    assert np.abs(cov @ coeff - coeff * latent[None, :]).max() < 1e-13 * lat_o[0]         # eigen-residual
+    # directions with a well separated variance agree with the SVD's, sign convention included
+    gap = np.minimum(np.abs(np.diff(lat_o, prepend=np.inf)), np.abs(np.diff(lat_o, append=-np.inf)))
+    for j in np.nonzero(gap > 1e-6 * lat_o[0])[0]:
+        v = Vt[j] * (1.0 if Vt[j][np.argmax(np.abs(Vt[j]))] > 0 else -1.0)
+        assert np.abs(coeff[:, j] - v).max() < 1e-8 * lat_o[0] / gap[j]
 
 
 def test_train_models_with_lasso_vector(fitter, snake_data):

@@ -174,5 +174,5 @@ def test_mex_shim_compiles_against_the_abi():
                         "-I", os.path.join(root, "include"), os.path.join(root, "matlab", "koopfit_mex.cpp")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     src = open(os.path.join(root, "matlab", "koopfit_mex.cpp")).read()
-    for entry in ("kf_fit_multi", "kf_fit_series", "kf_fit_batch", "kf_rollout", "kf_lift", "kf_mldivide", "kf_mpc_costB_bilinear"):
+    for entry in ("kf_fit_multi", "kf_fit_series", "kf_fit_batch", "kf_rollout", "kf_lift", "kf_pca", "kf_mldivide", "kf_mpc_costB_bilinear"):
         assert entry in src, entry
