@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 #include "kf_internal.h"
@@ -28,7 +29,19 @@ int prepare_program(kf_ctx* ctx, const kf_basis* basis) {
         return rc;
     }
     const KfProgram& p = ctx->prog;
-    ctx->prog_gen += 1;
+    {   // the lift-group tables on the device are keyed by the dictionary: the same dictionary again (a loop of fits) keeps them
+        unsigned long long h = 1469598103934665603ull;
+        auto mix = [&](const void* data, size_t nbytes) {
+            const unsigned char* b = static_cast<const unsigned char*>(data);
+            for (size_t i = 0; i < nbytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+        };
+        const int dims[3] = {p.nv, p.n_pcs, p.ngauss};
+        mix(dims, sizeof(dims));
+        mix(p.ops.data(), p.ops.size() * sizeof(KfOp));
+        mix(p.centres.data(), p.centres.size() * sizeof(double));
+        mix(p.pcs.data(), p.pcs.size() * sizeof(double));
+        if (h != ctx->prog_hash || ctx->prog_gen == 0) { ctx->prog_hash = h; ctx->prog_gen += 1; }
+    }
     KF_CUDA(ctx, ctx->d_ops.ensure(sizeof(KfOp) * p.ops.size()));
     KF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ops.p, p.ops.data(), sizeof(KfOp) * p.ops.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!p.centres.empty()) {
@@ -808,6 +821,7 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
                 }
             }
             const bool split = active_set && !auto_split && ctx->qp_hi > ctx->qp_lo;     // caller's column partition across ranks
+            double td0 = now_ms();
             if (active_set) {
                 // the columns are DEALT round-robin to the ranks (rank r: columns r, r + R, ...; as a contiguous block of a column-
                 // permuted C): the support sizes differ systematically between column ranges (config 3a: the psi and the u psi
@@ -818,8 +832,10 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
                     KF_TRY(kf_qp_deal_cols(ctx, ctx->d_C.as<double>(), ctx->d_deal.as<double>(), P, Pp, ctx->nranks, 1, st));
                     Cs = ctx->d_deal.as<double>();
                 }
+                td0 = now_ms();
                 const int rc_as = kf_solve_l1ball_as(ctx, P, Pp, ctx->d_G.as<double>(), Cs, nb, tf.data(), c0, c1,
                                                      sv->qp_max_iter, Kt, qr.data(), st);
+                if (ctx->opt_as_diag) { cudaStreamSynchronize(st); fprintf(stderr, "[as_diag] rank %d: active-set sweep %.1f ms\n", ctx->rank, now_ms() - td0); }
                 if (auto_split) { ctx->qp_lo = 0; ctx->qp_hi = 0; }
                 if (rc_as) return rc_as;
                 if (auto_split)
@@ -849,6 +865,8 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
                 }
                 return KF_OK;
             };
+            const double td1 = now_ms();
+            if (ctx->opt_as_diag) { cudaStreamSynchronize(st); fprintf(stderr, "[as_diag] rank %d: sweep + column exchange %.1f ms\n", ctx->rank, td1 - td0); }
             for (int b = 0; b < nb; ++b) {
                 const int it = act[g0 + b];
                 capped += qr[b].capped;
@@ -865,6 +883,7 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
                 if (out->K) KF_TRY(copy_out_matrix(ctx, Kt + (size_t)b * Pp * Pp, Pp, P, out->K + (size_t)it * P * P));
             }
             KF_CUDA(ctx, cudaStreamSynchronize(st));
+            if (ctx->opt_as_diag) fprintf(stderr, "[as_diag] rank %d: evaluation + copy-out of %d budgets %.1f ms\n", ctx->rank, nb, now_ms() - td1);
         }
         out->info.passes = 1;
         out->info.qp_capped = capped;

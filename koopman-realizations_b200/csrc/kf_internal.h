@@ -214,7 +214,8 @@ struct kf_ctx {
     std::vector<LtGroup> lt_groups;
     // the uploaded group tables are reused while (program, tile width, group size) stay the same: the panel pipeline launches
     // the tile evaluator once per chunk and must not pay a host synchronisation each time
-    unsigned long long prog_gen = 0;     // bumped by every prepare_program
+    unsigned long long prog_gen = 0;     // bumped by prepare_program when the dictionary changed
+    unsigned long long prog_hash = 0;    // FNV-1a of the compiled dictionary
     unsigned long long lt_key[4] = {~0ull, 0, 0, 0};
     int lt_max[3] = {0, 0, 0};           // max_slots, max_ops, max_nst of the cached groups
     unsigned long long lt_plan_key[3] = {~0ull, 0, 0};   // streaming lift: cached tile-width decision for unaligned rows

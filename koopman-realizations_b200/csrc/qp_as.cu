@@ -593,6 +593,9 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
 
     KfBuf diag_birth;                     // option as_diag only
     int diag_step = 0;
+    double seg[4] = {0, 0, 0, 0};         // as_diag: host wall time of the step segments (index | factor + GEMM | counts | rest)
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     std::vector<int> h_cnt(P), h_cols(P), h_chg(P);
     long long cols_factored = 0;
     std::vector<long long> h_off(P);
@@ -619,6 +622,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
 
     // one exact step on the current pattern SG for budget tb; K -> Kout, pattern updated
     auto step = [&](double tb, double* Kout) -> int {
+        const auto ts0 = tnow();
         kf_as_index_kernel<<<P, 256, 0, st>>>(SG, ld, P, cs, d_idx, d_cnt);
         KF_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
         KF_CUDA(ctx, cudaMemcpyAsync(h_chg.data(), d_chg, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
@@ -626,6 +630,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
         KF_CUDA(ctx, cudaStreamSynchronize(st));
         // only the columns whose support changed are factored again: a_j = G_SS^-1 c_S and b_j = G_SS^-1 s_S depend on the pattern
         // alone (config 3a: about half of all column-steps are unchanged)
+        const auto ts1 = tnow();
         int nown = 0;
         for (int j = cs.lo; j < cs.hi; ++j)
             if (cs.on(j) && (h_chg[j] || !ctx->opt_as_skip)) h_cols[nown++] = j;
@@ -675,6 +680,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
                 KF_TRY(kf_launch_gemm_grid(ctx, g, st));
             }
         KF_CUDA(ctx, cudaStreamSynchronize(st));
+        const auto ts2 = tnow();
         KF_TRY(reduce(sums, 4, 0));                 // hook path: s'a, s'b, skipped pivots, support size summed over the ranks
         const double nnz = sums[3];
         const double limit = std::max(frac * nnz, (double)P);
@@ -718,6 +724,11 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
             }
         }
         if (ctx->opt_as_diag) {
+            const auto ts3 = tnow();
+            seg[0] += secs(ts0, ts1); seg[1] += secs(ts1, ts2); seg[2] += secs(ts2, ts3);
+            if ((diag_step + 1) % 50 == 0)
+                fprintf(stderr, "[as_diag] segments so far: index+readback %.3f s, factor+sums+GEMM %.3f s, counts %.3f s (columns factored %lld)\n",
+                        seg[0], seg[1], seg[2], cols_factored);
             if (!diag_birth.p) {
                 KF_CUDA(ctx, diag_birth.ensure((size_t)P * P * sizeof(int) + 8 * sizeof(double)));
                 KF_CUDA(ctx, cudaMemsetAsync(diag_birth.p, 0, diag_birth.bytes, st));
