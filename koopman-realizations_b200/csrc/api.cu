@@ -1551,6 +1551,7 @@ int kf_set_option(kf_ctx* ctx, const char* name, double value) {
     else if (n == "as_frac") ctx->opt_as_frac = value;
     else if (n == "as_diag") ctx->opt_as_diag = (int)value;
     else if (n == "as_skip") ctx->opt_as_skip = (int)value;
+    else if (n == "as_level") ctx->opt_as_level = (int)value;
     else if (n == "lift_tile") ctx->opt_lift_tile = (int)value;
     else if (n == "lift_ls") ctx->opt_lift_ls = (int)value;
     else if (n == "qr_blocked") ctx->opt_qr_blocked = (int)value;

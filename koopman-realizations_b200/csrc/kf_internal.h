@@ -193,6 +193,7 @@ struct kf_ctx {
     double opt_qr_max_gb = 16; // KF_LS_AUTO takes the QRCP route when [Px|Py] is at most this large
     int opt_profile = 0;      // sample Gram-kernel durations with CUDA events (adds syncs)
     int opt_qp_method = 0;    // L1-ball QP: 0 auto (coordinate descent for P <= 256, exact active set above), 1 CD, 2 active set
+    int opt_as_level = -1;    // active-set solver: level-synchronous factorisation (-1 off (default: measured no gain), 0 auto when a rank has few columns, 1 always)
     int opt_as_skip = 1;      // active-set solver: columns whose support did not change keep their a_j, b_j (no refactorisation)
     int opt_as_diag = 0;      // active-set solver: print how much factor reuse an age-ordered support would allow (diagnostic)
     double opt_as_frac = 0.05; // active-set solver: bound on the pattern change per step, as a fraction of the support size

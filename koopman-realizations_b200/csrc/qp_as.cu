@@ -48,6 +48,11 @@ struct AsArgs {
     double* col_num; double* col_den;   // [column]: s'a, s'b
     int* col_dead;             // [column]: pivots skipped (numerically singular G_SS)
     int P;
+    // Level-synchronous mode (few columns per rank: a column gets several CTAs).  mode 0: the whole column in one CTA.  mode 1: ONE
+    // block column J0, row tile blockIdx.y + tile_off of it (tile 0 holds the diagonal block; the other tiles are launched after it
+    // and read the diagonal factor and the skipped-pivot flags back from global memory).  mode 2: back-substitution + scatter only.
+    int mode, J0, tile_off;
+    int* dead;                 // mode 1 / 2: [launch slot][P] skipped-pivot flags
 };
 
 __device__ __forceinline__ int as_ldl(int n) { return (n + 2 + 1) & ~1; }
@@ -82,14 +87,16 @@ __global__ void __launch_bounds__(AS_THREADS, MINB) kf_as_chol_kernel(const AsAr
     const int n = a.cnt[col];
     // this column's a_j, b_j are rewritten on the new support at the end: clear what the old support left behind (columns whose
     // support did not change are not launched at all and keep their a_j, b_j, s'a, s'b)
-    for (int i = tid; i < a.P; i += AS_THREADS) {
-        a.Aout[i + (long long)col * a.ld] = 0.0;
-        a.Bout[i + (long long)col * a.ld] = 0.0;
-    }
+    if (a.mode != 1)
+        for (int i = tid; i < a.P; i += AS_THREADS) {
+            a.Aout[i + (long long)col * a.ld] = 0.0;
+            a.Bout[i + (long long)col * a.ld] = 0.0;
+        }
     if (n == 0) {
-        if (tid == 0) { a.col_num[col] = 0.0; a.col_den[col] = 0.0; a.col_dead[col] = 0; }
+        if (tid == 0 && a.mode != 1) { a.col_num[col] = 0.0; a.col_den[col] = 0.0; a.col_dead[col] = 0; }
         return;
     }
+    if (a.mode == 1 && (a.J0 >= n || a.J0 + (blockIdx.y + a.tile_off) * TM >= n + 2)) return;      // nothing of this tile exists
     const int ldl = as_ldl(n);
     double* __restrict__ L = a.ws + a.ws_off[blockIdx.x];
     const int* gidx = a.idx + (long long)col * a.P;
@@ -101,9 +108,13 @@ __global__ void __launch_bounds__(AS_THREADS, MINB) kf_as_chol_kernel(const AsAr
     int ndead = 0;
 
     const int tr = tid % RT, tc = tid / RT;   // thread owns tile rows tr + RT i (i < TR) and tile columns TC tc + j (j < TC)
-    for (int J0 = 0; J0 < n; J0 += AS_NB) {
+    int* gdead = a.dead ? a.dead + (long long)blockIdx.x * a.P : nullptr;
+    const int jb_first = a.mode == 1 ? a.J0 : 0, jb_end = a.mode == 0 ? n : (a.mode == 1 ? min(n, a.J0 + 1) : 0);
+    for (int J0 = jb_first; J0 < jb_end; J0 += AS_NB) {
         const int w = min(AS_NB, n - J0);
-        for (int R0 = J0; R0 < nrows; R0 += TM) {
+        const int r_first = a.mode == 1 ? J0 + (blockIdx.y + a.tile_off) * TM : J0;
+        const int r_end = a.mode == 1 ? min(nrows, r_first + 1) : nrows;
+        for (int R0 = r_first; R0 < r_end; R0 += TM) {
             double acc[TR][TC];
 #pragma unroll
             for (int i = 0; i < TR; ++i)
@@ -209,6 +220,17 @@ __global__ void __launch_bounds__(AS_THREADS, MINB) kf_as_chol_kernel(const AsAr
                         if (c < w && lane < w) sD[lane * (AS_NB + 1) + c] = lane >= c ? x[c] : 0.0;
                 }
                 __syncthreads();
+                if (a.mode == 1 && tid < w) gdead[J0 + tid] = sDead[tid];
+            } else if (a.mode == 1) {
+                // a later tile of the block column: the diagonal factor was written by the tile-0 launch
+                for (int e = tid; e < AS_NB * AS_NB; e += AS_THREADS) {
+                    const int r = e % AS_NB, c = e / AS_NB;
+                    sD[r * (AS_NB + 1) + c] = (r < w && c <= r) ? L[(J0 + r) + (long long)(J0 + c) * ldl] : 0.0;
+                }
+                if (tid < AS_NB) sDead[tid] = tid < w ? gdead[J0 + tid] : 0;
+                __syncthreads();
+                if (tid < AS_NB) sInv[tid] = tid < w ? 1.0 / sD[tid * (AS_NB + 1) + tid] : 0.0;
+                __syncthreads();
             }
             // ---- rows below the diagonal block: X = T * L_D^-T (one thread per row), write the block column of L
             if (tid < TM) {
@@ -235,8 +257,12 @@ __global__ void __launch_bounds__(AS_THREADS, MINB) kf_as_chol_kernel(const AsAr
             }
             __syncthreads();
         }
-        if (tid == 0)
+        if (tid == 0 && (a.mode == 0 || r_first == J0))
             for (int c = 0; c < w; ++c) ndead += sDead[c];
+    }
+    if (a.mode == 1) {          // only the tile-0 CTA counted: one writer per column and launch
+        if (tid == 0 && blockIdx.y + a.tile_off == 0) a.col_dead[col] = (a.J0 == 0 ? 0 : a.col_dead[col]) + ndead;
+        return;
     }
 
     // ---- back-substitution L' x = y for both right-hand sides (y = rows n, n+1 of L); x lives in shared memory
@@ -302,7 +328,7 @@ __global__ void __launch_bounds__(AS_THREADS, MINB) kf_as_chol_kernel(const AsAr
         for (int q = 0; q < AS_THREADS / 32; ++q) { sn += red[0][q]; sd += red[1][q]; }
         a.col_num[col] = sn;
         a.col_den[col] = sd;
-        a.col_dead[col] = ndead;
+        if (a.mode == 0) a.col_dead[col] = ndead;
     }
 }
 
@@ -552,7 +578,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     double* Bm = Am + mat;
     double* GA = Bm + mat;      // G A
     double* GB = GA + mat;      // G B
-    const size_t n_int = (size_t)P * P + 4ull * P + 8;
+    const size_t n_int = 2ull * P * P + 4ull * P + 8;
     const size_t n_dbl = 2ull * P + 8;
     KF_CUDA(ctx, ctx->d_as_aux.ensure(n_dbl * sizeof(double) + (size_t)(P + AS_NL + 2) * sizeof(long long) + n_int * sizeof(int) + 64));
     double* d_num = ctx->d_as_aux.as<double>();
@@ -565,6 +591,7 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
     int* d_cols = d_cnt + P;
     int* d_dead = d_cols + P;
     int* d_chg = d_dead + P;        // [column]: support changed since its last factorisation
+    int* d_deadflags = d_chg + P + 8;   // [launch slot][P]: skipped pivots (level-synchronous mode)
 
     // workspace for the factors: bounded (option as_ws_gb, default 8 GB), columns are processed in chunks that fit
     size_t free_b = 0, total_b = 0;
@@ -657,15 +684,43 @@ int kf_solve_l1ball_as(kf_ctx* ctx, int P, int Pp, const double* G, const double
             KF_CUDA(ctx, cudaMemcpyAsync(d_cols, h_cols.data(), sizeof(int) * nown, cudaMemcpyHostToDevice, st));
             KF_CUDA(ctx, cudaMemcpyAsync(d_off, h_off.data(), sizeof(long long) * nown, cudaMemcpyHostToDevice, st));
         }
-        int c0 = 0;
-        for (int c1 : chunk_end) {
-            if (c1 > c0) {
-                a.cols = d_cols + c0; a.ws_off = d_off + c0;
-                kf_as_chol_kernel<128, 4, 4, 2><<<c1 - c0, AS_THREADS, smem, st>>>(a);
-                KF_CUDA(ctx, cudaGetLastError());
-                ctx->launches += 1;
+        // Few columns for the CTA slots of this GPU (a rank of a column-split sweep): one CTA per column would make the step as long
+        // as ONE heavy column's ~30 dependent block columns x its row tiles.  Level-synchronous instead: per block column one launch
+        // for the diagonal tiles and one for all the other row tiles of all columns, then the back-substitutions.
+        const bool level = nown > 0 && chunk_end.size() == 1 &&
+                           (ctx->opt_as_level == 1 || (ctx->opt_as_level == 0 && nown <= 2 * ctx->sm_count && h_cnt[h_cols[0]] >= 256));
+        a.dead = d_deadflags;
+        if (level) {
+            a.cols = d_cols; a.ws_off = d_off;
+            const int nmax = h_cnt[h_cols[0]];
+            int active = nown;
+            for (int J0 = 0; J0 < nmax; J0 += AS_NB) {
+                while (active > 0 && h_cnt[h_cols[active - 1]] <= J0) --active;      // heavy first: the live columns are a prefix
+                a.mode = 1; a.J0 = J0; a.tile_off = 0;
+                kf_as_chol_kernel<128, 4, 4, 2><<<dim3(active, 1), AS_THREADS, smem, st>>>(a);
+                const int ntiles = (nmax + 2 - J0 + 127) / 128;
+                if (ntiles > 1) {
+                    a.tile_off = 1;
+                    kf_as_chol_kernel<128, 4, 4, 2><<<dim3(active, ntiles - 1), AS_THREADS, smem, st>>>(a);
+                }
+                ctx->launches += 2;
             }
-            c0 = c1;
+            a.mode = 2; a.J0 = 0; a.tile_off = 0;
+            kf_as_chol_kernel<128, 4, 4, 2><<<nown, AS_THREADS, smem, st>>>(a);
+            KF_CUDA(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        } else {
+            a.mode = 0;
+            int c0 = 0;
+            for (int c1 : chunk_end) {
+                if (c1 > c0) {
+                    a.cols = d_cols + c0; a.ws_off = d_off + c0;
+                    kf_as_chol_kernel<128, 4, 4, 2><<<c1 - c0, AS_THREADS, smem, st>>>(a);
+                    KF_CUDA(ctx, cudaGetLastError());
+                    ctx->launches += 1;
+                }
+                c0 = c1;
+            }
         }
         kf_as_sums_kernel<<<1, 256, 0, st>>>(d_num, d_den, d_dead, d_cnt, P, cs, d_scal);
         if (dev_reduce) KF_TRY(kf_comm_allreduce(ctx, d_scal, 4, 0, st));   // s'a, s'b, skipped pivots, support size over the ranks
