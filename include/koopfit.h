@@ -324,7 +324,16 @@ int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, dou
  *   threshold, default 1e3), "refine_level_tol" (dynamic range one level resolves, default 1e-5), "refine_max" (level limit, 4),
  *   "qp_split" (multi-GPU context: split the active-set lasso sweep by columns over the ranks, default 1),
  *   "gram_engine" (0 auto: INT8 tensor cores for P >= 1024 and >= 4 panels of snapshots, FP64 DMMA otherwise; 1 DMMA; 2 INT8),
- *   "oz_sym" (INT8 engine: exploit the Kronecker block symmetry of a bilinear regressor, default 1) */
+ *   "oz_sym" (INT8 engine: exploit the Kronecker block symmetry of a bilinear regressor, default 1),
+ *   "lift_wide" (materialising lift / panel lift: streaming kernel with 32- or 64-snapshot tiles = 1, default), "lift_ls" (force the
+ *   tile width: 32 | 64; 8 | 16 for the narrow fallback kernel), "lift_smem_kb" (shared memory per CTA of the streaming kernel,
+ *   default 110), "lift_minb" (2 | 3 resident CTAs per SM it is compiled for), "lift_panel_fit" (fit path: panel lift through the
+ *   streaming evaluator, default 1),
+ *   "qr_blocked" (QRCP route: 1 = blocked Householder QR of the tall matrix, then pivoted QR of R1 = default; 0 = column by column;
+ *   2 = diagnostic: two-stage without compact WY), "qr_nb" (panel width 32 | 64 | 128, default 64), "qr_ksplit" (chunks of the
+ *   two-level summation over the rows, default 64),
+ *   "as_skip" (active set: columns whose support did not change are not factored again, default 1), "as_level" (level-synchronous
+ *   factorisation: -1 off = default, 0 auto, 1 always), "as_diag" (print per-step diagnostics to stderr) */
 int kf_set_option(kf_ctx* ctx, const char* name, double value);
 
 #ifdef __cplusplus
