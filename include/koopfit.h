@@ -317,7 +317,7 @@ int kf_last_times(kf_ctx* ctx, double* lift_gram_ms, double* gram_kernel_ms, dou
 /* tuning knobs; returns KF_EINVAL if unknown:
  *   "chunk" (snapshots per L2-resident panel), "panel_mb", "splitk", "overlap" (two chunk pipelines), "tma" (Gram operands by
  *   tensor-map TMA = 1 / cp.async = 0), "profile" (sample Gram-kernel durations), "qr_max_gb" (KF_LS_AUTO takes the QRCP route
- *   up to this size of [Px | Py]), "qp_method" (0 auto: coordinate descent for P <= 256, exact active set above; 1; 2),
+ *   up to this size of [Px | Py]), "qp_method" (0 auto = 2: exact active set; 1: coordinate descent in lockstep; 2),
  *   "as_frac" (active set: bound on the pattern change per step, fraction of the support, default 0.05, self-tuning downwards),
  *   "as_ws_gb" (active set: bound on the factor workspace), "lift_tile" (materialising lift: shared-memory tile kernel = 1),
  *   "refine" (Gram-route refinement: 0 off, 1 adaptive = default, 2 always at least one extra pass), "refine_kappa" (pivot-ratio

@@ -13,6 +13,10 @@ namespace {
 
 thread_local std::string g_create_err;
 
+}  // namespace
+std::mutex& kf_smem_table_mutex() { static std::mutex m; return m; }
+std::map<std::pair<int, const void*>, size_t>& kf_smem_table() { static std::map<std::pair<int, const void*>, size_t> t; return t; }
+namespace {
 double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -810,13 +814,15 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
                                                    (size_t)P * sizeof(double), (size_t)P * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, st));
             }
             std::vector<KfQpResult> qr(nb);
-            const bool active_set = ctx->opt_qp_method == 2 || (ctx->opt_qp_method == 0 && P > 256);
+            // auto = the exact active-set solver at every size: on the reference's own small dictionaries the lockstep coordinate
+            // descent needs 1e4-1e5 sweeps per multiplier (config 3b, P = 16: 2.0 s against 0.09 s; gaussian 30, P = 68: minutes)
+            const bool active_set = ctx->opt_qp_method == 2 || ctx->opt_qp_method == 0;
             // "lasso sweeps are split across GPUs" (north_star): with the library's own communicator the exact active-set sweep is
             // split by COLUMNS of K automatically — rank r factors the columns shard_bounds(P, r, nranks) for all budgets, the
             // step scalars are summed in stream order over NCCL, and the column blocks are exchanged at the end, so every rank
             // ends up with the complete K of every budget.  (A caller-set partition, kf_set_qp_partition, takes precedence.)
-            const bool auto_split = active_set && ctx->comm && ctx->nranks > 1 && !(ctx->qp_hi > ctx->qp_lo) && c1 <= c0 && P <= 4096 &&
-                                    ctx->opt_qp_split;
+            const bool auto_split = active_set && ctx->comm && ctx->nranks > 1 && !(ctx->qp_hi > ctx->qp_lo) && c1 <= c0 && P > 256 &&
+                                    P <= 4096 && ctx->opt_qp_split;
             std::vector<size_t> goff, gcnt;
             if (auto_split) {
                 const int base = P / ctx->nranks, extra = P % ctx->nranks;
@@ -872,6 +878,20 @@ int solve_from_accum(kf_ctx* ctx, const kf_solve* sv, kf_result* out) {
                 }
                 return KF_OK;
             };
+            // Safety net of the auto choice on small problems: a budget the active-set iteration did not settle (step cap, or a
+            // certified gap above the 1e-8 objective tolerance — numerically singular Grams with psd_shift = never) sends the group
+            // through the coordinate descent, slow but monotone.
+            if (active_set && ctx->opt_qp_method == 0 && P <= 256 && !split && !auto_split) {
+                bool redo = false;
+                for (int b = 0; b < nb && !redo; ++b) {
+                    KfQpResult ev{};
+                    KF_TRY(evaluate(b, &ev));
+                    redo = qr[b].capped || !(ev.gap <= 1e-8 * std::max(std::fabs(ev.objective), 1e-300));
+                }
+                if (redo)
+                    KF_TRY(kf_solve_l1ball_multi(ctx, P, Pp, ctx->d_G.as<double>(), ctx->d_C.as<double>(), nb, tf.data(), c0, c1, sv->qp_max_iter,
+                                                 sv->qp_tol, Kt, qr.data(), st));
+            }
             const double td1 = now_ms();
             if (ctx->opt_as_diag) { cudaStreamSynchronize(st); fprintf(stderr, "[as_diag] rank %d: sweep + column exchange %.1f ms\n", ctx->rank, td1 - td0); }
             for (int b = 0; b < nb; ++b) {

@@ -6,6 +6,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <mutex>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -192,7 +194,7 @@ struct kf_ctx {
     double opt_panel_mb = 64; // target size of one L2-resident panel (24/48/64 MB measured: 31.7/32.5/32.8 TF)
     double opt_qr_max_gb = 16; // KF_LS_AUTO takes the QRCP route when [Px|Py] is at most this large
     int opt_profile = 0;      // sample Gram-kernel durations with CUDA events (adds syncs)
-    int opt_qp_method = 0;    // L1-ball QP: 0 auto (coordinate descent for P <= 256, exact active set above), 1 CD, 2 active set
+    int opt_qp_method = 0;    // L1-ball QP: 0 auto = 2 (exact active set), 1 coordinate descent, 2 active set
     int opt_as_level = -1;    // active-set solver: level-synchronous factorisation (-1 off (default: measured no gain), 0 auto when a rank has few columns, 1 always)
     int opt_as_skip = 1;      // active-set solver: columns whose support did not change keep their a_j, b_j (no refactorisation)
     int opt_as_diag = 0;      // active-set solver: print how much factor reuse an age-ordered support would allow (diagnostic)
@@ -257,9 +259,15 @@ struct kf_ctx {
     } while (0)
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize of `func` raised to at least `bytes` on the context's device
+std::mutex& kf_smem_table_mutex();
+std::map<std::pair<int, const void*>, size_t>& kf_smem_table();
 template <class F>
 inline cudaError_t kf_ensure_smem(kf_ctx* ctx, F* func, size_t bytes) {
-    size_t& have = ctx->smem_attr[reinterpret_cast<const void*>(func)];
+    // The attribute is per DEVICE and function, not per context: several contexts (Fitter objects, the per-device contexts of
+    // kf_create_multi) share it, and a context that set a smaller value after another one's larger request would make that
+    // one's next launch fail with "invalid argument".  Hence a process-wide table that only ever grows (api.cu).
+    std::lock_guard<std::mutex> lock(kf_smem_table_mutex());
+    size_t& have = kf_smem_table()[std::make_pair(ctx->device, reinterpret_cast<const void*>(func))];
     if (have == 0) have = 48 * 1024;
     if (bytes <= have) return cudaSuccess;
     const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
