@@ -1180,7 +1180,9 @@ int kf_create(kf_ctx** out, int device) {
 void kf_destroy(kf_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaDeviceSynchronize();
+    // this context's streams only: a device-wide synchronisation would invalidate a CUDA-graph capture of another context
+    for (cudaStream_t q : {ctx->stream, ctx->stream2, ctx->stream_x[0], ctx->stream_x[1], ctx->copy_stream})
+        if (q) cudaStreamSynchronize(q);
     KfBuf* bufs[] = {&ctx->d_order, &ctx->d_ops, &ctx->d_centres, &ctx->d_pcs, &ctx->d_panel[0], &ctx->d_panel[1], &ctx->d_panel[2], &ctx->d_panel[3], &ctx->d_full,
                      &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tma_tasks[0], &ctx->d_tma_tasks[1], &ctx->d_accum, &ctx->d_tilemeta, &ctx->d_G, &ctx->d_C, &ctx->d_K,
                      &ctx->d_W, &ctx->d_in, &ctx->d_misc, &ctx->d_qr, &ctx->d_tmp, &ctx->d_K2, &ctx->d_K3, &ctx->d_Kt,

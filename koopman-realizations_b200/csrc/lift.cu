@@ -540,12 +540,20 @@ bool lift_tile_launch_ls(kf_ctx* ctx, KfLiftTileArgs& a, int nsides, size_t smem
 bool lift_groups_upload(kf_ctx* ctx, cudaStream_t st, int* rc) {
     const size_t nb_ops = ctx->lt_ops.size() * sizeof(LtOp), nb_st = ctx->lt_store.size() * sizeof(LtStore), nb_g = ctx->lt_groups.size() * sizeof(LtGroup);
     const size_t o_st = (nb_ops + 15) & ~(size_t)15, o_g = (o_st + nb_st + 15) & ~(size_t)15;
-    if (cudaDeviceSynchronize() != cudaSuccess || ctx->d_lift_groups.ensure(o_g + nb_g) != cudaSuccess) { cudaGetLastError(); return false; }
+    // (this context's streams only: a device-wide synchronisation would invalidate a CUDA-graph capture running in another
+    // thread's context on the same device)
+    auto sync_own = [&]() -> bool {
+        cudaStream_t own[] = {ctx->stream, ctx->stream2, ctx->stream_x[0], ctx->stream_x[1]};
+        for (cudaStream_t q : own)
+            if (q && cudaStreamSynchronize(q) != cudaSuccess) return false;
+        return true;
+    };
+    if (!sync_own() || ctx->d_lift_groups.ensure(o_g + nb_g) != cudaSuccess) { cudaGetLastError(); return false; }
     char* b0 = ctx->d_lift_groups.as<char>();
     cudaMemcpyAsync(b0, ctx->lt_ops.data(), nb_ops, cudaMemcpyHostToDevice, st);
     if (nb_st) cudaMemcpyAsync(b0 + o_st, ctx->lt_store.data(), nb_st, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(b0 + o_g, ctx->lt_groups.data(), nb_g, cudaMemcpyHostToDevice, st);
-    if (cudaDeviceSynchronize() != cudaSuccess) {
+    if (cudaStreamSynchronize(st) != cudaSuccess || !sync_own()) {
         *rc = KF_ECUDA;
         ctx->err = "lift groups upload failed";
         return false;
