@@ -229,9 +229,6 @@ struct kf_ctx {
     kf_allreduce_fn qp_allreduce = nullptr;
     void* qp_user = nullptr;
 
-    // largest dynamic shared-memory limit requested per kernel ON THIS CONTEXT'S DEVICE (the attribute is per device and
-    // only ever grows: a smaller value would make a later, larger launch fail)
-    std::map<const void*, size_t> smem_attr;
 
     KfPcholGraph pchol_graph;
     int opt_graphs = 1;       // replay the launch-bound pivoted-Cholesky loop as a CUDA graph

@@ -224,7 +224,6 @@ class Ksysid:
         """lift_snapshots + get_econ_observables with dim_red (Ksysid.m:1394-1432, 1495-1517): `pca` runs on the GPU."""
         print("Performing dimensional reduction...")
         sp = self.snapshotPairs
-        m = self.params["m"]
         # pca of the lifted [alpha, u] (nonlinear) or alpha points, on the GPU: means, centred Gram, Jacobi eigensolver (kf_pca)
         V = np.concatenate([sp["alpha"], sp["u"]], axis=1) if self.model_type == "nonlinear" else sp["alpha"]
         _, lam, vec = self.fitter.pca(self.basis, V)
