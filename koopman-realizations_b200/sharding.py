@@ -21,6 +21,17 @@ def shard_bounds(M, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def dealt_columns(P, world):
+    """Column order of the lasso sweep split inside the library (csrc/qp.cu: kf_qp_deal_cols_kernel): position p of the dealt
+    order holds original column dealt_columns(P, world)[p]; rank r owns the positions shard_bounds(P, r, world), i.e. the original
+    columns r, r + world, r + 2 world, ... — a round-robin deal, so that column ranges with systematically different support
+    sizes (config 3a: the psi and the u psi halves of K) spread over all ranks."""
+    order = []
+    for r in range(int(world)):
+        order.extend(range(r, int(P), int(world)))
+    return order
+
+
 def allreduce_sum_(tensor, group=None):
     """In-place sum over ranks of the packed partial-Gram accumulator; no-op for a single process."""
     import torch.distributed as dist

@@ -179,3 +179,22 @@ def test_column_split_gathers_the_column_blocks():
         assert info["nranks"] == 2 and info["max_lo"] == 6.0
         assert part == (0, 0) and method == 0              # restored
         assert bounds == ((0, 6) if rank == 0 else (6, 11))
+
+
+def test_dealt_columns_match_the_library_kernel_formula():
+    """The round-robin deal of the columns of K over the ranks (kf_qp_deal_cols_kernel, csrc/qp.cu) restated from its index
+    arithmetic: a permutation whose rank blocks are exactly shard_bounds(P, r, world) and hold the columns r, r + world, ..."""
+    from koopfit.sharding import dealt_columns, shard_bounds
+    for P, R in ((1464, 8), (1464, 2), (17, 4), (5, 8), (252, 3)):
+        base, extra = divmod(P, R)
+        big = extra * (base + 1)
+        kernel = []
+        for p in range(P):                                  # the kernel's mapping position -> original column
+            r = p // (base + 1) if p < big else extra + (p - big) // max(base, 1)
+            k = p - (r * base + min(r, extra))
+            kernel.append(r + k * R)
+        assert kernel == dealt_columns(P, R)
+        assert sorted(kernel) == list(range(P))
+        for r in range(R):
+            lo, hi = shard_bounds(P, r, R)
+            assert kernel[lo:hi] == list(range(r, P, R))
