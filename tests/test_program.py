@@ -165,6 +165,43 @@ def test_lift_row_groups(hostlift, types, degs, nv, max_slots, max_rows):
         assert ngroups.value == 1 and used.value <= nv + 78          # only (some of) the degree-2 monomials are read by other features
 
 
+def test_lift_row_groups_random_dictionaries(hostlift):
+    """Randomised sweep over dictionaries, slot budgets and row limits: the row-group evaluation (what kf_lift_stream_kernel runs)
+    always reproduces the plain evaluation bit for bit and its invariants hold (hostlift_rowgroups returns 0)."""
+    rng = np.random.default_rng(2024)
+    kinds = ["poly", "hermite", "fourier_sparser", "gaussian", "fourier"]
+    for trial in range(40):
+        nv = int(rng.integers(1, 7))
+        nb = int(rng.integers(1, 4))
+        types = [kinds[int(rng.integers(0, len(kinds)))] for _ in range(nb)]
+        degs = []
+        for t in types:
+            if t == "gaussian":
+                degs.append(int(rng.integers(1, 40)))
+            elif t == "fourier":
+                degs.append(int(rng.integers(1, 3)) if nv <= 3 else 1)
+            else:
+                degs.append(int(rng.integers(1, 5 if nv <= 4 else 4)))
+        ng = sum(d for t, d in zip(types, degs) if t == "gaussian")
+        cen = 2 * rng.random((nv, ng)) - 1 if ng else None
+        b = A.Basis(types, degs, nv, centres=cen)
+        nf, N = C.c_int(), C.c_int()
+        assert hostlift.hostlift_dims(b.ref(), C.byref(nf), C.byref(N)) == 0
+        if nf.value > 6000:
+            continue
+        rows = 3
+        V = np.asfortranarray(2 * rng.random((rows, nv)) - 1)
+        plain = np.zeros((rows, nf.value), order="F")
+        assert hostlift.hostlift_full(b.ref(), C.c_longlong(rows), A.dptr(V), A.dptr(plain)) == 0
+        max_slots = int(rng.integers(nv + 2, nv + 200))
+        max_rows = int(rng.choice([0, 0, 7, 64, 500]))
+        out = np.full((rows, nf.value), np.nan, order="F")
+        ngroups, used = C.c_int(), C.c_int()
+        rc = hostlift.hostlift_rowgroups(b.ref(), max_slots, max_rows, C.c_longlong(rows), A.dptr(V), A.dptr(out), C.byref(ngroups), C.byref(used))
+        assert rc == 0, (rc, types, degs, nv, max_slots, max_rows)
+        assert np.array_equal(out, plain), (types, degs, nv, max_slots, max_rows)
+
+
 def test_mex_shim_compiles_against_the_abi():
     """matlab/koopfit_mex.cpp cannot run here (no MATLAB / Octave), but it must at least COMPILE against include/koopfit.h
     and a stub of the MEX API (tests/mex_stub/mex.h): catches ABI drift (renamed fields, changed signatures) in the shim."""
